@@ -1,0 +1,242 @@
+/*
+ * sqgpu.h -- C-ABI of the B200 (sm_100a) decomposition hot-path engine.
+ *
+ * This is the drop-in boundary for ONE path of SQUANDER (rakytap/sequential-quantum-gate-decomposer):
+ * apply a parametrised gate structure to a 2^n x C complex128 matrix (C = 1: state vector), reduce the
+ * trace cost and its parameter gradient, for a batch of parameter vectors.
+ *
+ * The boundary mirrors the accelerator plug-in the reference already has for Maxeler DFE boards
+ * (dlopen'd C symbols, squander/src-cpp/common/common_DFE.cpp:47-53,160-166) -- same life cycle
+ * (init / upload matrix / evaluate gate sets / release), but fp64 end to end and with the gate structure sent
+ * once instead of once per call. Each entry point names the reference interface it replaces.
+ *
+ * Conventions
+ *  - complex128 buffers are interleaved {re, im} doubles == QGD_Complex16 (common/include/QGDTypes.h:38-43),
+ *    row-major, element (r, c) at data[2*(r*stride + c)]  (common/include/matrix_base.hpp:38-59).
+ *  - every function returns SQGPU_OK (0) or a negative sqgpu_status; sqgpu_last_error() gives the text
+ *    (the reference throws std::string, Gate.cpp:435-446; the host shim rethrows it -- see INTEGRATION.md).
+ *  - host pointers are borrowed for the duration of the call only; the library owns all device memory.
+ *  - a handle is bound to one CUDA device; calls on one handle are serialised by an internal mutex
+ *    (the DFE bridge serialises with a rw-mutex, common_DFE.cpp:33,61-68).
+ *  - there is NO CPU fallback: without a usable CUDA device every compute entry point fails with
+ *    SQGPU_ERR_NO_DEVICE.
+ */
+#ifndef SQGPU_H_INCLUDED
+#define SQGPU_H_INCLUDED
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SQGPU_ABI_VERSION 1
+
+typedef enum sqgpu_status {
+    SQGPU_OK = 0,
+    SQGPU_ERR_NO_DEVICE = -1,   /* no CUDA device / driver, or device index out of range            */
+    SQGPU_ERR_INVALID = -2,     /* bad argument (sizes, qubit indices, unsupported gate type, ...)   */
+    SQGPU_ERR_STATE = -3,       /* call order: matrix / circuit / hamiltonian not set yet            */
+    SQGPU_ERR_CUDA = -4,        /* a CUDA runtime call failed; text in sqgpu_last_error()            */
+    SQGPU_ERR_UNSUPPORTED = -5, /* valid in the reference, not implemented on the device path (yet)  */
+    SQGPU_ERR_NOMEM = -6        /* device or pinned-host allocation failed                           */
+} sqgpu_status;
+
+/* Gate type codes: numerically identical to the reference enum gate_type
+ * (squander/src-cpp/gates/include/Gate.h:39-79) so descriptors can be filled straight from Gate::get_type(). */
+typedef enum sqgpu_gate_type {
+    SQGPU_GENERAL = 1,
+    SQGPU_CZ = 4,
+    SQGPU_CNOT = 5,
+    SQGPU_CH = 6,
+    SQGPU_U3 = 7,
+    SQGPU_RY = 8,
+    SQGPU_RX = 9,
+    SQGPU_RZ = 10,
+    SQGPU_X = 12,
+    SQGPU_SX = 13,
+    SQGPU_CRY = 14,
+    SQGPU_SYC = 15,
+    SQGPU_BLOCK = 16, /* never sent to the engine: blocks are flattened (Gates_block::get_flat_circuit, Gates_block.cpp:3827-3856) */
+    SQGPU_ADAPTIVE = 18,
+    SQGPU_Y = 23,
+    SQGPU_Z = 24,
+    SQGPU_H = 25,
+    SQGPU_CROT = 27,
+    SQGPU_R = 28,
+    SQGPU_T = 29,
+    SQGPU_TDG = 30,
+    SQGPU_U1 = 31,
+    SQGPU_U2 = 32,
+    SQGPU_CR = 33,
+    SQGPU_S = 34,
+    SQGPU_SDG = 35,
+    SQGPU_CU = 36,
+    SQGPU_CP = 38,
+    SQGPU_CRX = 39,
+    SQGPU_CRZ = 40,
+    SQGPU_CCX = 41,
+    SQGPU_SWAP = 42,
+    SQGPU_CSWAP = 43,
+    SQGPU_RXX = 44,
+    SQGPU_RYY = 45,
+    SQGPU_RZZ = 46,
+    SQGPU_SXDG = 47,
+    /* descriptor-stream markers understood only by the oracle harness (oracle/ref_harness.cpp) to rebuild the
+     * reference's nested Gates_block structure; the engine rejects them. */
+    SQGPU_BLOCK_BEGIN = 1001,
+    SQGPU_BLOCK_END = 1002
+} sqgpu_gate_type;
+
+/* Cost-function variants: numerically identical to the reference enum cost_function_type
+ * (squander/src-cpp/decomposition/include/Optimization_Interface.h:43-45). */
+typedef enum sqgpu_cost_variant {
+    SQGPU_FROBENIUS_NORM = 0,
+    SQGPU_FROBENIUS_NORM_CORRECTION1 = 1,
+    SQGPU_FROBENIUS_NORM_CORRECTION2 = 2,
+    SQGPU_HILBERT_SCHMIDT_TEST = 3,
+    SQGPU_HILBERT_SCHMIDT_TEST_CORRECTION1 = 4,
+    SQGPU_HILBERT_SCHMIDT_TEST_CORRECTION2 = 5,
+    SQGPU_SUM_OF_SQUARES = 6,
+    SQGPU_INFIDELITY = 9
+} sqgpu_cost_variant;
+
+#define SQGPU_MAX_GENERAL_QUBITS 5
+
+/* One gate of the flattened circuit, in application order (gate 0 is applied first:
+ * Gates_block::apply_to_inner, Gates_block.cpp:683-708). Replaces DFEgate_kernel_type
+ * (common/include/common_DFE.h:62-70), which carried fixed-point angles; here the angles stay in the fp64
+ * parameter vector and the descriptor only says where to read them. */
+typedef struct sqgpu_gate_desc {
+    int32_t type;        /* sqgpu_gate_type                                                                      */
+    int32_t target;      /* target qubit (Gate::target_qbit); first target for SWAP/CSWAP/RXX/RYY/RZZ; -1 GENERAL */
+    int32_t control;     /* control qubit (Gate::control_qbit) or -1                                              */
+    int32_t target2;     /* second target (SWAP, CSWAP, RXX, RYY, RZZ) or -1                                       */
+    int32_t control2;    /* second control (CCX) or -1                                                            */
+    int32_t param_start; /* index of the gate's first parameter (Gate::parameter_start_idx)                       */
+    int32_t n_params;    /* Gate::parameter_num; must match the type                                              */
+    int32_t n_qubits;    /* GENERAL only: k = number of involved qubits, 1..SQGPU_MAX_GENERAL_QUBITS              */
+    int32_t qubits[8];   /* GENERAL only: the k involved qubits, ascending; local-index bit j <-> qubits[j]
+                            (apply_large_kernel_to_input.cpp:160-169)                                             */
+    int64_t matrix_off;  /* GENERAL only: offset (complex elements) of the row-major 2^k x 2^k kernel in the pool */
+} sqgpu_gate_desc;
+
+typedef struct sqgpu_ctx* sqgpu_handle_t;
+
+/* ---- life cycle ------------------------------------------------------------------------------------------- */
+
+/* replaces get_accelerator_avail_num (common_DFE.cpp:47). *count = visible CUDA devices with cc >= 10.0. */
+int sqgpu_device_count(int* count);
+
+/* replaces initialize_DFE(accelerator_num) (common_DFE.cpp:52,178-184): bind a context to CUDA device `device`. */
+int sqgpu_create(int device, sqgpu_handle_t* out);
+
+/* replaces releive_DFE (common_DFE.cpp:49,110-113). */
+int sqgpu_destroy(sqgpu_handle_t h);
+
+/* text of the last failure on the calling thread ("" if none). Never NULL. */
+const char* sqgpu_last_error(void);
+
+int sqgpu_abi_version(void);
+
+/* ---- inputs ------------------------------------------------------------------------------------------------ */
+
+/* replaces load2LMEM(QGD_Complex16*, rows, cols) (common_DFE.cpp:50,129-132) and the per-evaluation
+ * Umtx.copy_to(matrix_new) (Optimization_Interface.cpp:661-663): upload the 2^n x cols matrix (cols = 1: state
+ * vector) once; it stays resident until the next upload. */
+int sqgpu_upload_matrix(sqgpu_handle_t h, const double* data, int rows, int cols, int stride);
+
+/* replaces the per-call DFE descriptor flattening (Gates_block::convert_to_DFE_gates, Gates_block.cpp:4202-4278):
+ * send the flattened gate structure once. `matrix_pool` (may be NULL) holds the constant kernels of GENERAL gates,
+ * pool_len complex elements. */
+int sqgpu_set_circuit(sqgpu_handle_t h, const sqgpu_gate_desc* gates, int n_gates, int n_params, int qbit_num,
+                      const double* matrix_pool, int64_t pool_len);
+
+/* replaces Optimization_Interface::set_cost_function_variant / set_trace_offset and the members
+ * prev_cost_fnv_val, correction1_scale, correction2_scale (Optimization_Interface.h:83-89, .cpp:74-76,1785-1800). */
+int sqgpu_set_cost(sqgpu_handle_t h, int variant, int trace_offset, double prev_cost_fnv_val,
+                   double correction1_scale, double correction2_scale);
+
+/* ---- the hot path ------------------------------------------------------------------------------------------ */
+
+/* replaces Optimization_Interface::optimization_problem_batched (Optimization_Interface.cpp:939-1033; the DFE
+ * version calcqgdKernelDFE, common_DFE.cpp:51,61-68): cost[b] = f(params[b*P .. b*P+P)), b < batch. */
+int sqgpu_cost_batched(sqgpu_handle_t h, const double* params, int batch, double* cost);
+
+/* replaces Optimization_Interface::optimization_problem_combined_non_static (Optimization_Interface.cpp:1145-1490),
+ * batched (the reference has no batched cost+gradient entry; batch = 1 is the reference call):
+ * cost[b] and grad[b*P + i] = d cost / d params[b*P + i]. */
+int sqgpu_cost_grad_batched(sqgpu_handle_t h, const double* params, int batch, double* cost, double* grad);
+
+/* Raw trace terms before the non-linear cost formulas, for column-sharded multi-GPU runs (the caller sums them over
+ * ranks, then calls sqgpu_cost_from_traces). Mirrors the {trace, correction1, correction2} triple calcqgdKernelDFE
+ * returns per gate set (Optimization_Interface.cpp:806-832). Layout: traces[b][k][t][2], k = 0 the circuit itself,
+ * k = 1..P the P derivatives (only if with_grad), t < 3 = {main diagonal, one-bit-flip, two-bit-flip sums}, {re, im}.
+ * `cols_total` written = local column count (the normalisation the cost formulas use is the summed one). */
+int sqgpu_traces_batched(sqgpu_handle_t h, const double* params, int batch, int with_grad, double* traces);
+
+/* cost (and gradient if grad != NULL) from (possibly rank-summed) trace terms; cols_total = summed column count. */
+int sqgpu_cost_from_traces(sqgpu_handle_t h, const double* traces, int batch, int with_grad, int cols_total,
+                           double* cost, double* grad);
+
+/* replaces Gates_block::apply_to(parameters, input) (Gates_block.cpp:605-710) for the Circuit.apply_to binding
+ * (qgd_Circuit_Wrapper.cpp:861-995): transform `inout` (rows x cols, any cols >= 1) in place. Does not touch the
+ * resident matrix. */
+int sqgpu_apply(sqgpu_handle_t h, const double* params, double* inout, int rows, int cols, int stride);
+
+/* replaces Gates_block::apply_derivate_to (Gates_block.cpp:1011-1150): out holds P matrices of rows x cols
+ * (compact, stride = cols), out[i] = d(C(params) * in)/d params[i], with the reference's conventions (zero rows
+ * where a controlled gate is inactive, kernels/apply_kernel_to_input.cpp:93-97). */
+int sqgpu_apply_derivative(sqgpu_handle_t h, const double* params, const double* in, int rows, int cols, int stride,
+                           double* out);
+
+/* single gate on a matrix / state vector: Gate::apply_to(parameters, input) (Gate.cpp:500-526 -> apply_kernel_to,
+ * Gate.cpp:1477-1768). `deriv_param` < 0: the gate itself; otherwise its derivative with respect to its
+ * deriv_param-th parameter (Gate::apply_derivative_to_precomputed, Gate.cpp:644-706). */
+int sqgpu_apply_gate(sqgpu_handle_t h, const sqgpu_gate_desc* gate, const double* gate_params,
+                     const double* matrix_pool, int deriv_param, double* inout, int rows, int cols, int stride);
+
+/* ---- VQE (state-vector) path ------------------------------------------------------------------------------- */
+
+/* replaces the Matrix_sparse Hamiltonian member of Variational_Quantum_Eigensolver_Base
+ * (common/include/matrix_sparse.h:38; ctor variational_quantum_eigensolver/...Base.cpp): CSR, complex128 values,
+ * int32 indices, n_rows = 2^n. */
+int sqgpu_set_hamiltonian_csr(sqgpu_handle_t h, int n_rows, int64_t nnz, const int32_t* indptr, const int32_t* indices,
+                              const double* values);
+
+/* replaces Variational_Quantum_Eigensolver_Base::optimization_problem (…Base.cpp:1088-1121) batched over parameter
+ * sets: energy[b] = Re <psi(params_b)| H |psi(params_b)>, psi = C(params_b) * (resident state vector). */
+int sqgpu_vqe_energy_batched(sqgpu_handle_t h, const double* params, int batch, double* energy);
+
+/* replaces Variational_Quantum_Eigensolver_Base::optimization_problem_combined_non_static (…Base.cpp:1131-1199):
+ * grad[b*P+i] = 2 Re <d_i psi| H |psi>. */
+int sqgpu_vqe_energy_grad_batched(sqgpu_handle_t h, const double* params, int batch, double* energy, double* grad);
+
+/* ---- device-resident variants (inputs/outputs are device pointers on the handle's device; enqueue on `stream`,
+ *      a cudaStream_t passed as void*; no host synchronisation) -- what bench.py's `value` times ------------ */
+
+int sqgpu_cost_batched_dev(sqgpu_handle_t h, const double* d_params, int batch, double* d_cost, void* stream);
+int sqgpu_cost_grad_batched_dev(sqgpu_handle_t h, const double* d_params, int batch, double* d_cost, double* d_grad,
+                                void* stream);
+int sqgpu_traces_batched_dev(sqgpu_handle_t h, const double* d_params, int batch, int with_grad, double* d_traces,
+                             void* stream);
+int sqgpu_cost_from_traces_dev(sqgpu_handle_t h, const double* d_traces, int batch, int with_grad, int cols_total,
+                               double* d_cost, double* d_grad, void* stream);
+int sqgpu_apply_gate_dev(sqgpu_handle_t h, const sqgpu_gate_desc* gate, const double* gate_params,
+                         const double* matrix_pool, int deriv_param, double* d_inout, int rows, int cols, int stride,
+                         void* stream);
+int sqgpu_vqe_energy_batched_dev(sqgpu_handle_t h, const double* d_params, int batch, double* d_energy, void* stream);
+
+/* ---- introspection for bench.py / tests -------------------------------------------------------------------- */
+
+/* number of kernels this library has launched on the handle since creation (bench.py's gpu_launches). */
+int sqgpu_launch_count(sqgpu_handle_t h, int64_t* count);
+
+/* name and average device time (ms, CUDA events on the launching stream) of the dominant kernel of the last
+ * batched evaluation -- bench.py's roofline numerator. name_len includes the terminating NUL. */
+int sqgpu_last_kernel_time(sqgpu_handle_t h, char* name, int name_len, double* ms, int* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SQGPU_H_INCLUDED */

@@ -1,0 +1,342 @@
+"""ctypes bindings of the two CPU checkers. TEST INFRASTRUCTURE ONLY.
+
+  * ``Port``  -- oracle/libsqoracle.so, the plain-C restatement (sq_oracle.c); always available (gcc).
+  * ``Ref``   -- oracle/_ref/libsqref.so, the reference's OWN translation units behind ref_harness.cpp; built in the
+                 container that has /root/reference, shipped prebuilt to the GPU box.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this module; the
+product package never does.
+"""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import importlib
+
+abi = importlib.import_module("sequential-quantum-gate-decomposer_b200.abi")
+
+PORT_PATH = os.path.join(HERE, "libsqoracle.so")
+REF_PATH = os.path.join(HERE, "_ref", "libsqref.so")
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+_gp = C.POINTER(abi.GateDesc)
+
+
+def build_port():
+    subprocess.check_call(["make", "-s", "-C", HERE, "port"])
+
+
+def build_ref():
+    """Only possible where /root/reference exists."""
+    subprocess.check_call(["make", "-s", "-j8", "-C", HERE, "ref"])
+
+
+def _c128(a):
+    return np.ascontiguousarray(a, dtype=np.complex128)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _dptr(a):
+    return a.ctypes.data_as(_dp) if a is not None and a.size else None
+
+
+def _descs(d):
+    d = np.ascontiguousarray(d, dtype=abi.GATE_DESC_DTYPE)
+    return d, d.ctypes.data_as(_gp)
+
+
+class Port:
+    """sq_oracle.c"""
+
+    def __init__(self):
+        if not os.path.exists(PORT_PATH) or os.path.getmtime(PORT_PATH) < os.path.getmtime(os.path.join(HERE, "sq_oracle.c")):
+            build_port()
+        L = self.lib = C.CDLL(PORT_PATH)
+        L.sqo_gate_kernel.argtypes = [C.c_int, _dp, _dp]
+        L.sqo_gate_derivative_kernel.argtypes = [C.c_int, _dp, C.c_int, _dp]
+        L.sqo_apply_gate.argtypes = [_gp, _dp, _dp, C.c_int, _dp, C.c_int, C.c_int, C.c_int]
+        L.sqo_apply_circuit.argtypes = [_gp, C.c_int, _dp, _dp, _dp, C.c_int, C.c_int, C.c_int]
+        L.sqo_apply_derivate.argtypes = [_gp, C.c_int, C.c_int, _dp, _dp, _dp, C.c_int, C.c_int, C.c_int, _dp]
+        L.sqo_traces.argtypes = [_dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp]
+        L.sqo_cost_from_traces.argtypes = [C.c_int, _dp, C.c_int, C.c_double, C.c_double, C.c_double]
+        L.sqo_cost_from_traces.restype = C.c_double
+        L.sqo_grad_from_traces.argtypes = [C.c_int, _dp, _dp, C.c_int, C.c_double, C.c_double, C.c_double]
+        L.sqo_grad_from_traces.restype = C.c_double
+        L.sqo_cost.argtypes = [_gp, C.c_int, _dp, _dp, _dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                               C.c_double, C.c_double, C.c_double, _dp]
+        L.sqo_cost_grad.argtypes = [_gp, C.c_int, C.c_int, _dp, _dp, _dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                    C.c_int, C.c_double, C.c_double, C.c_double, _dp, _dp]
+        L.sqo_csr_matvec.argtypes = [C.c_int, _ip, _ip, _dp, _dp, _dp]
+        L.sqo_vqe_energy.argtypes = [_gp, C.c_int, _dp, _dp, _dp, C.c_int, _ip, _ip, _dp, _dp]
+        L.sqo_vqe_energy_grad.argtypes = [_gp, C.c_int, C.c_int, _dp, _dp, _dp, C.c_int, _ip, _ip, _dp, _dp, _dp]
+
+    def gate_kernel(self, type_, gate_params):
+        k = np.zeros(16, dtype=np.complex128)
+        p = _f64(gate_params)
+        dim = self.lib.sqo_gate_kernel(type_, _dptr(p), _dptr(k.view(np.float64)))
+        if dim < 0:
+            raise Exception("port: no kernel for gate type %d" % type_)
+        return k[: dim * dim].reshape(dim, dim).copy()
+
+    def gate_derivative_kernel(self, type_, gate_params, pidx):
+        k = np.zeros(16, dtype=np.complex128)
+        p = _f64(gate_params)
+        dim = self.lib.sqo_gate_derivative_kernel(type_, _dptr(p), pidx, _dptr(k.view(np.float64)))
+        if dim < 0:
+            raise Exception("port: no derivative kernel for gate type %d" % type_)
+        return k[: dim * dim].reshape(dim, dim).copy()
+
+    def apply_gate(self, desc_row, params, mtx, pool=None, deriv_param=-1):
+        """returns a transformed copy; params = the whole circuit parameter vector (desc.param_start indexes it)"""
+        m = np.array(mtx, dtype=np.complex128, order="C", copy=True)
+        m2 = m.reshape(m.shape[0], -1)
+        d, dptr = _descs(np.asarray(desc_row).reshape(1))
+        p = _f64(params)
+        pl = _c128(pool) if pool is not None else np.zeros(0, dtype=np.complex128)
+        rc = self.lib.sqo_apply_gate(dptr, _dptr(p), _dptr(pl.view(np.float64)), deriv_param,
+                                     _dptr(m2.view(np.float64)), m2.shape[0], m2.shape[1], m2.shape[1])
+        if rc:
+            raise Exception("port: apply_gate failed")
+        return m
+
+    def apply_circuit(self, descs, params, mtx, pool=None):
+        m = np.array(mtx, dtype=np.complex128, order="C", copy=True)
+        m2 = m.reshape(m.shape[0], -1)
+        d, dptr = _descs(descs)
+        p = _f64(params)
+        pl = _c128(pool) if pool is not None else np.zeros(0, dtype=np.complex128)
+        rc = self.lib.sqo_apply_circuit(dptr, len(d), _dptr(p), _dptr(pl.view(np.float64)), _dptr(m2.view(np.float64)),
+                                        m2.shape[0], m2.shape[1], m2.shape[1])
+        if rc:
+            raise Exception("port: apply_circuit failed")
+        return m
+
+    def apply_derivate(self, descs, n_params, params, mtx, pool=None):
+        m = _c128(mtx)
+        m2 = m.reshape(m.shape[0], -1)
+        d, dptr = _descs(descs)
+        p = _f64(params)
+        pl = _c128(pool) if pool is not None else np.zeros(0, dtype=np.complex128)
+        out = np.zeros((max(n_params, 1),) + m2.shape, dtype=np.complex128)
+        rc = self.lib.sqo_apply_derivate(dptr, len(d), n_params, _dptr(p), _dptr(pl.view(np.float64)),
+                                         _dptr(m2.view(np.float64)), m2.shape[0], m2.shape[1], m2.shape[1],
+                                         _dptr(out.view(np.float64)))
+        if rc:
+            raise Exception("port: apply_derivate failed")
+        return out[:n_params].reshape((n_params,) + m.shape)
+
+    def traces(self, mtx, qbit_num, trace_offset=0):
+        m = _c128(mtx)
+        out = np.zeros(6)
+        self.lib.sqo_traces(_dptr(m.view(np.float64)), m.shape[0], m.shape[1], m.shape[1], qbit_num, trace_offset,
+                            _dptr(out))
+        return out
+
+    def cost_from_traces(self, variant, tr6, cols, prev=1.0, c1=1 / 1.7, c2=0.5):
+        t = _f64(tr6)
+        return self.lib.sqo_cost_from_traces(variant, _dptr(t), cols, prev, c1, c2)
+
+    def cost(self, descs, params, umtx, qbit_num, variant=0, trace_offset=0, prev=1.0, c1=1 / 1.7, c2=0.5, pool=None):
+        U = _c128(umtx)
+        d, dptr = _descs(descs)
+        p = _f64(params)
+        pl = _c128(pool) if pool is not None else np.zeros(0, dtype=np.complex128)
+        out = np.zeros(1)
+        rc = self.lib.sqo_cost(dptr, len(d), _dptr(p), _dptr(pl.view(np.float64)), _dptr(U.view(np.float64)),
+                               U.shape[0], U.shape[1], U.shape[1], qbit_num, variant, trace_offset, prev, c1, c2,
+                               _dptr(out))
+        if rc:
+            raise Exception("port: cost failed")
+        return float(out[0])
+
+    def cost_grad(self, descs, n_params, params, umtx, qbit_num, variant=0, trace_offset=0, prev=1.0, c1=1 / 1.7,
+                  c2=0.5, pool=None):
+        U = _c128(umtx)
+        d, dptr = _descs(descs)
+        p = _f64(params)
+        pl = _c128(pool) if pool is not None else np.zeros(0, dtype=np.complex128)
+        out = np.zeros(1)
+        grad = np.zeros(max(n_params, 1))
+        rc = self.lib.sqo_cost_grad(dptr, len(d), n_params, _dptr(p), _dptr(pl.view(np.float64)),
+                                    _dptr(U.view(np.float64)), U.shape[0], U.shape[1], U.shape[1], qbit_num, variant,
+                                    trace_offset, prev, c1, c2, _dptr(out), _dptr(grad))
+        if rc:
+            raise Exception("port: cost_grad failed")
+        return float(out[0]), grad[:n_params]
+
+    def vqe_energy(self, descs, params, state0, indptr, indices, data, pool=None):
+        d, dptr = _descs(descs)
+        p = _f64(params)
+        s0 = _c128(state0).reshape(-1)
+        ip = np.ascontiguousarray(indptr, dtype=np.int32)
+        ix = np.ascontiguousarray(indices, dtype=np.int32)
+        v = _c128(data)
+        pl = _c128(pool) if pool is not None else np.zeros(0, dtype=np.complex128)
+        out = np.zeros(1)
+        rc = self.lib.sqo_vqe_energy(dptr, len(d), _dptr(p), _dptr(pl.view(np.float64)), _dptr(s0.view(np.float64)),
+                                     s0.size, ip.ctypes.data_as(_ip), ix.ctypes.data_as(_ip),
+                                     _dptr(v.view(np.float64)), _dptr(out))
+        if rc:
+            raise Exception("port: vqe_energy failed")
+        return float(out[0])
+
+    def vqe_energy_grad(self, descs, n_params, params, state0, indptr, indices, data, pool=None):
+        d, dptr = _descs(descs)
+        p = _f64(params)
+        s0 = _c128(state0).reshape(-1)
+        ip = np.ascontiguousarray(indptr, dtype=np.int32)
+        ix = np.ascontiguousarray(indices, dtype=np.int32)
+        v = _c128(data)
+        pl = _c128(pool) if pool is not None else np.zeros(0, dtype=np.complex128)
+        out = np.zeros(1)
+        grad = np.zeros(max(n_params, 1))
+        rc = self.lib.sqo_vqe_energy_grad(dptr, len(d), n_params, _dptr(p), _dptr(pl.view(np.float64)),
+                                          _dptr(s0.view(np.float64)), s0.size, ip.ctypes.data_as(_ip),
+                                          ix.ctypes.data_as(_ip), _dptr(v.view(np.float64)), _dptr(out), _dptr(grad))
+        if rc:
+            raise Exception("port: vqe_energy_grad failed")
+        return float(out[0]), grad[:n_params]
+
+
+class Ref:
+    """the reference's own code (oracle/_ref/libsqref.so)"""
+
+    @staticmethod
+    def available():
+        return os.path.exists(REF_PATH)
+
+    def __init__(self):
+        if not os.path.exists(REF_PATH):
+            if os.path.isdir("/root/reference"):
+                build_ref()
+            else:
+                raise FileNotFoundError(REF_PATH + " missing and /root/reference not present to build it")
+        L = self.lib = C.CDLL(REF_PATH)
+        L.sqref_last_error.restype = C.c_char_p
+        L.sqref_circuit_create.restype = C.c_void_p
+        L.sqref_circuit_create.argtypes = [C.c_int, _gp, C.c_int, _dp]
+        L.sqref_circuit_free.argtypes = [C.c_void_p]
+        L.sqref_circuit_param_num.argtypes = [C.c_void_p]
+        L.sqref_circuit_set_min_fusion.argtypes = [C.c_void_p, C.c_int]
+        L.sqref_circuit_apply.argtypes = [C.c_void_p, _dp, C.c_int, _dp, C.c_int, C.c_int, C.c_int]
+        L.sqref_circuit_apply_derivate.argtypes = [C.c_void_p, _dp, C.c_int, _dp, C.c_int, C.c_int, C.c_int, _dp]
+        L.sqref_decomp_create.restype = C.c_void_p
+        L.sqref_decomp_create.argtypes = [_dp, C.c_int, C.c_int, C.c_int, _gp, C.c_int, _dp]
+        L.sqref_decomp_free.argtypes = [C.c_void_p]
+        L.sqref_decomp_param_num.argtypes = [C.c_void_p]
+        L.sqref_decomp_set_cost.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]
+        L.sqref_decomp_set_parallel.argtypes = [C.c_void_p, C.c_int]
+        L.sqref_decomp_cost.argtypes = [C.c_void_p, _dp, C.c_int, _dp]
+        L.sqref_decomp_cost_batched.argtypes = [C.c_void_p, _dp, C.c_int, C.c_int, _dp]
+        L.sqref_decomp_cost_grad.argtypes = [C.c_void_p, _dp, C.c_int, _dp, _dp]
+        L.sqref_traces.argtypes = [_dp, C.c_int, C.c_int, C.c_int, C.c_int, _dp]
+
+    def _err(self):
+        return self.lib.sqref_last_error().decode("utf-8", "replace")
+
+    def circuit(self, qbit_num, descs, pool=None):
+        return RefCircuit(self, qbit_num, descs, pool)
+
+    def decomp(self, umtx, qbit_num, descs, pool=None):
+        return RefDecomp(self, umtx, qbit_num, descs, pool)
+
+
+class RefCircuit:
+    def __init__(self, ref, qbit_num, descs, pool=None):
+        self.ref = ref
+        d, dptr = _descs(descs)
+        pl = _c128(pool) if pool is not None else np.zeros(0, dtype=np.complex128)
+        self.h = ref.lib.sqref_circuit_create(qbit_num, dptr, len(d), _dptr(pl.view(np.float64)))
+        if not self.h:
+            raise Exception("ref: circuit_create failed: " + ref._err())
+        self.n_params = ref.lib.sqref_circuit_param_num(self.h)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.ref.lib.sqref_circuit_free(self.h)
+            self.h = None
+
+    def set_min_fusion(self, mf):
+        self.ref.lib.sqref_circuit_set_min_fusion(self.h, mf)
+
+    def apply(self, params, mtx, parallel=0):
+        m = np.array(mtx, dtype=np.complex128, order="C", copy=True)
+        m2 = m.reshape(m.shape[0], -1)
+        p = _f64(params)
+        rc = self.ref.lib.sqref_circuit_apply(self.h, _dptr(p), p.size, _dptr(m2.view(np.float64)), m2.shape[0],
+                                              m2.shape[1], parallel)
+        if rc:
+            raise Exception("ref: apply failed: " + self.ref._err())
+        return m
+
+    def apply_derivate(self, params, mtx, parallel=0):
+        m = _c128(mtx)
+        m2 = m.reshape(m.shape[0], -1)
+        p = _f64(params)
+        out = np.zeros((max(self.n_params, 1),) + m2.shape, dtype=np.complex128)
+        rc = self.ref.lib.sqref_circuit_apply_derivate(self.h, _dptr(p), p.size, _dptr(m2.view(np.float64)),
+                                                       m2.shape[0], m2.shape[1], parallel,
+                                                       _dptr(out.view(np.float64)))
+        if rc:
+            raise Exception("ref: apply_derivate failed: " + self.ref._err())
+        return out[: self.n_params].reshape((self.n_params,) + m.shape)
+
+
+class RefDecomp:
+    def __init__(self, ref, umtx, qbit_num, descs, pool=None):
+        self.ref = ref
+        U = _c128(umtx)
+        d, dptr = _descs(descs)
+        pl = _c128(pool) if pool is not None else np.zeros(0, dtype=np.complex128)
+        self.h = ref.lib.sqref_decomp_create(_dptr(U.view(np.float64)), U.shape[0], U.shape[1], qbit_num, dptr, len(d),
+                                             _dptr(pl.view(np.float64)))
+        if not self.h:
+            raise Exception("ref: decomp_create failed: " + ref._err())
+        self.n_params = ref.lib.sqref_decomp_param_num(self.h)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.ref.lib.sqref_decomp_free(self.h)
+            self.h = None
+
+    def set_cost(self, variant=0, trace_offset=0, prev=1.0, c1=1 / 1.7, c2=0.5):
+        if self.ref.lib.sqref_decomp_set_cost(self.h, variant, trace_offset, prev, c1, c2):
+            raise Exception("ref: set_cost failed: " + self.ref._err())
+
+    def set_parallel(self, parallel):
+        if self.ref.lib.sqref_decomp_set_parallel(self.h, parallel):
+            raise Exception("ref: set_parallel failed: " + self.ref._err())
+
+    def cost(self, params):
+        p = _f64(params)
+        out = np.zeros(1)
+        if self.ref.lib.sqref_decomp_cost(self.h, _dptr(p), p.size, _dptr(out)):
+            raise Exception("ref: cost failed: " + self.ref._err())
+        return float(out[0])
+
+    def cost_batched(self, params):
+        p = _f64(params)
+        out = np.zeros(p.shape[0])
+        if self.ref.lib.sqref_decomp_cost_batched(self.h, _dptr(p), p.shape[1], p.shape[0], _dptr(out)):
+            raise Exception("ref: cost_batched failed: " + self.ref._err())
+        return out
+
+    def cost_grad(self, params):
+        p = _f64(params)
+        out = np.zeros(1)
+        g = np.zeros(max(p.size, 1))
+        if self.ref.lib.sqref_decomp_cost_grad(self.h, _dptr(p), p.size, _dptr(out), _dptr(g)):
+            raise Exception("ref: cost_grad failed: " + self.ref._err())
+        return float(out[0]), g[: p.size]

@@ -1,0 +1,241 @@
+"""Host-side mirror of the reference's ``Circuit`` (= C++ ``Gates_block``) for the hot path.
+
+Same method names and argument meaning as the CPython wrapper squander/gates/qgd_Circuit_Wrapper.cpp:3109-3302
+(``add_U3(target_qbit)``, ``add_CNOT(target_qbit, control_qbit)``, ``add_Circuit``, ``get_Parameter_Num``,
+``apply_to(parameters, unitary)`` in place, ``apply_derivate_to``, ``get_Matrix`` ...). The class only keeps the
+gate structure; every numerical call goes to the CUDA engine through the C-ABI (engine.Engine) -- there is no
+CPU evaluation here.
+
+Parameter layout follows Gates_block::add_gate (Gates_block.cpp:2500-2525): gates own consecutive slices of one
+flat parameter vector in insertion order, nested circuits included.
+"""
+import numpy as np
+
+from . import abi
+
+
+class _Gate:
+    __slots__ = ("type", "target", "control", "target2", "control2", "qubits", "matrix")
+
+    def __init__(self, type_, target=-1, control=-1, target2=-1, control2=-1, qubits=None, matrix=None):
+        self.type = type_
+        self.target = target
+        self.control = control
+        self.target2 = target2
+        self.control2 = control2
+        self.qubits = qubits
+        self.matrix = matrix
+
+    @property
+    def n_params(self):
+        return abi.PARAM_COUNT[self.type]
+
+
+class Circuit:
+    """Ordered gate structure over ``qbit_num`` qubits; gate 0 is applied first (Gates_block.cpp:683-708)."""
+
+    def __init__(self, qbit_num):
+        qbit_num = int(qbit_num)
+        if qbit_num < 1 or qbit_num > 30:
+            raise Exception("Circuit: number of qubits should be between 1 and 30")
+        self.qbit_num = qbit_num
+        self._items = []  # _Gate or Circuit
+        self._min_fusion = 14  # Gates_block.cpp:91,113 (kept for API parity; the engine plans its own windows)
+        self._engine = None
+        self._engine_key = None
+
+    # ---- structure ------------------------------------------------------------------------------------------
+    def _check_q(self, *qs):
+        for q in qs:
+            if q < 0 or q >= self.qbit_num:
+                raise Exception("Circuit: qubit index %d out of range for %d qubits" % (q, self.qbit_num))
+        if len(set(qs)) != len(qs):
+            raise Exception("Circuit: target and control qubits must differ")
+
+    def _add(self, gate):
+        self._items.append(gate)
+        self._engine_key = None
+
+    def _add_1q(self, type_, target_qbit):
+        self._check_q(int(target_qbit))
+        self._add(_Gate(type_, target=int(target_qbit)))
+
+    def _add_c1q(self, type_, target_qbit, control_qbit):
+        self._check_q(int(target_qbit), int(control_qbit))
+        self._add(_Gate(type_, target=int(target_qbit), control=int(control_qbit)))
+
+    def _add_2t(self, type_, target_qbits):
+        t = [int(q) for q in target_qbits]
+        if len(t) != 2:
+            raise Exception("gate requires exactly 2 target qubits")
+        self._check_q(*t)
+        self._add(_Gate(type_, target=t[0], target2=t[1]))
+
+    def add_U1(self, target_qbit): self._add_1q(abi.U1, target_qbit)
+    def add_U2(self, target_qbit): self._add_1q(abi.U2, target_qbit)
+    def add_U3(self, target_qbit): self._add_1q(abi.U3, target_qbit)
+    def add_RX(self, target_qbit): self._add_1q(abi.RX, target_qbit)
+    def add_RY(self, target_qbit): self._add_1q(abi.RY, target_qbit)
+    def add_RZ(self, target_qbit): self._add_1q(abi.RZ, target_qbit)
+    def add_R(self, target_qbit): self._add_1q(abi.R, target_qbit)
+    def add_H(self, target_qbit): self._add_1q(abi.H, target_qbit)
+    def add_X(self, target_qbit): self._add_1q(abi.X, target_qbit)
+    def add_Y(self, target_qbit): self._add_1q(abi.Y, target_qbit)
+    def add_Z(self, target_qbit): self._add_1q(abi.Z, target_qbit)
+    def add_S(self, target_qbit): self._add_1q(abi.S, target_qbit)
+    def add_Sdg(self, target_qbit): self._add_1q(abi.SDG, target_qbit)
+    def add_T(self, target_qbit): self._add_1q(abi.T, target_qbit)
+    def add_Tdg(self, target_qbit): self._add_1q(abi.TDG, target_qbit)
+    def add_SX(self, target_qbit): self._add_1q(abi.SX, target_qbit)
+    def add_SXdg(self, target_qbit): self._add_1q(abi.SXDG, target_qbit)
+    def add_CNOT(self, target_qbit, control_qbit): self._add_c1q(abi.CNOT, target_qbit, control_qbit)
+    def add_CZ(self, target_qbit, control_qbit): self._add_c1q(abi.CZ, target_qbit, control_qbit)
+    def add_CH(self, target_qbit, control_qbit): self._add_c1q(abi.CH, target_qbit, control_qbit)
+    def add_CU(self, target_qbit, control_qbit): self._add_c1q(abi.CU, target_qbit, control_qbit)
+    def add_CRY(self, target_qbit, control_qbit): self._add_c1q(abi.CRY, target_qbit, control_qbit)
+    def add_CRX(self, target_qbit, control_qbit): self._add_c1q(abi.CRX, target_qbit, control_qbit)
+    def add_CRZ(self, target_qbit, control_qbit): self._add_c1q(abi.CRZ, target_qbit, control_qbit)
+    def add_CP(self, target_qbit, control_qbit): self._add_c1q(abi.CP, target_qbit, control_qbit)
+    def add_CR(self, target_qbit, control_qbit): self._add_c1q(abi.CR, target_qbit, control_qbit)
+    def add_adaptive(self, target_qbit, control_qbit): self._add_c1q(abi.ADAPTIVE, target_qbit, control_qbit)
+    def add_RXX(self, target_qbits): self._add_2t(abi.RXX, target_qbits)
+    def add_RYY(self, target_qbits): self._add_2t(abi.RYY, target_qbits)
+    def add_RZZ(self, target_qbits): self._add_2t(abi.RZZ, target_qbits)
+    def add_SWAP(self, target_qbits): self._add_2t(abi.SWAP, target_qbits)
+
+    def add_CCX(self, target_qbit, control_qbits):
+        c = [int(q) for q in control_qbits]
+        if len(c) != 2:
+            raise Exception("CCX requires exactly 2 control qubits")
+        self._check_q(int(target_qbit), *c)
+        self._add(_Gate(abi.CCX, target=int(target_qbit), control=c[0], control2=c[1]))
+
+    def add_CSWAP(self, target_qbits, control_qbits):
+        t = [int(q) for q in target_qbits]
+        c = [int(q) for q in control_qbits]
+        if len(t) != 2 or len(c) != 1:
+            raise Exception("CSWAP requires 2 target qubits and 1 control qubit")
+        self._check_q(*t, *c)
+        self._add(_Gate(abi.CSWAP, target=t[0], target2=t[1], control=c[0]))
+
+    def add_GENERAL(self, operation_mtx, target_qbits, control_qbits=None):
+        """Constant dense block on ``target_qbits`` (a GENERAL_OPERATION with a local 2^k x 2^k matrix,
+        Gate.cpp:1586-1660). Local index bit j belongs to the j-th *ascending* target qubit
+        (apply_large_kernel_to_input.cpp:160-169)."""
+        if control_qbits:
+            raise Exception("add_GENERAL: controlled general gates are not supported on the device path")
+        q = sorted(int(x) for x in target_qbits)
+        self._check_q(*q)
+        k = len(q)
+        if k < 1 or k > 5:
+            raise Exception("add_GENERAL: 1..5 target qubits supported")
+        m = np.ascontiguousarray(operation_mtx, dtype=np.complex128)
+        if m.shape != (1 << k, 1 << k):
+            raise Exception("add_GENERAL: operation matrix has invalid size")
+        self._add(_Gate(abi.GENERAL, qubits=q, matrix=m))
+
+    def add_Circuit(self, circuit):
+        if circuit.qbit_num != self.qbit_num:
+            raise Exception("add_Circuit: qubit count mismatch")
+        self._add(circuit)
+
+    # ---- queries --------------------------------------------------------------------------------------------
+    def get_Qbit_Num(self):
+        return self.qbit_num
+
+    def get_Parameter_Num(self):
+        return sum(it.get_Parameter_Num() if isinstance(it, Circuit) else it.n_params for it in self._items)
+
+    def get_Gate_Num(self):
+        return len(self._items)
+
+    def set_min_fusion(self, min_fusion):
+        self._min_fusion = int(min_fusion)
+
+    def _flat_gates(self):
+        for it in self._items:
+            if isinstance(it, Circuit):
+                yield from it._flat_gates()
+            else:
+                yield it
+
+    def get_Flat_Circuit(self):
+        """Un-nested copy (Gates_block::get_flat_circuit, Gates_block.cpp:3827-3856)."""
+        c = Circuit(self.qbit_num)
+        c._items = list(self._flat_gates())
+        return c
+
+    def descriptors(self, nested=False):
+        """(descs, pool): the sqgpu_gate_desc array in application order and the constant-kernel pool.
+
+        nested=True keeps the block structure as BLOCK_BEGIN/BLOCK_END markers (only the oracle harness reads
+        those); the engine always gets nested=False."""
+        rows = []
+        pool = []
+        state = {"p": 0, "off": 0}
+
+        def emit(c):
+            for it in c._items:
+                if isinstance(it, Circuit):
+                    if nested:
+                        rows.append((abi.BLOCK_BEGIN, -1, -1, -1, -1, state["p"], 0, 0, (0,) * 8, 0))
+                    emit(it)
+                    if nested:
+                        rows.append((abi.BLOCK_END, -1, -1, -1, -1, state["p"], 0, 0, (0,) * 8, 0))
+                    continue
+                q = tuple(it.qubits) + (0,) * (8 - len(it.qubits)) if it.qubits else (0,) * 8
+                nq = len(it.qubits) if it.qubits else 0
+                off = 0
+                if it.matrix is not None:
+                    off = state["off"]
+                    pool.append(it.matrix.reshape(-1))
+                    state["off"] += it.matrix.size
+                rows.append((it.type, it.target, it.control, it.target2, it.control2, state["p"], it.n_params, nq, q,
+                             off))
+                state["p"] += it.n_params
+
+        emit(self)
+        descs = np.array(rows, dtype=abi.GATE_DESC_DTYPE) if rows else np.zeros(0, dtype=abi.GATE_DESC_DTYPE)
+        pool_arr = np.concatenate(pool) if pool else np.zeros(0, dtype=np.complex128)
+        return descs, np.ascontiguousarray(pool_arr, dtype=np.complex128)
+
+    # ---- numerics (all on the GPU through the C-ABI) --------------------------------------------------------
+    def _get_engine(self):
+        from .engine import Engine
+
+        key = (len(self._items), self.get_Parameter_Num(), id(self))
+        if self._engine is None:
+            self._engine = Engine(0)
+        if self._engine_key != key:
+            self._engine.set_circuit(self)
+            self._engine_key = key
+        return self._engine
+
+    def apply_to(self, parameters, unitary, parallel=1, is_f32=False):
+        """In place ``unitary <- C(parameters) @ unitary`` for a 2^n x cols complex128 array (cols = 1 or a 1-D
+        array: state vector). Mirrors qgd_Circuit_Wrapper_apply_to (qgd_Circuit_Wrapper.cpp:861-995)."""
+        if is_f32:
+            raise Exception("apply_to: the device path is fp64 only")
+        self._get_engine().apply(parameters, unitary)
+
+    def apply_derivate_to(self, parameters, unitary, parallel=1, is_f32=False):
+        """List of P arrays d(C @ unitary)/d parameters[i] (Gates_block::apply_derivate_to)."""
+        if is_f32:
+            raise Exception("apply_derivate_to: the device path is fp64 only")
+        return self._get_engine().apply_derivative(parameters, unitary)
+
+    def apply_to_combined(self, parameters, unitary, parallel=1, is_f32=False):
+        """[C @ unitary, d_0, ..., d_{P-1}] (Gates_block::apply_to_combined, Gates_block.cpp:1320-1364)."""
+        out = np.array(unitary, dtype=np.complex128, copy=True)
+        eng = self._get_engine()
+        derivs = eng.apply_derivative(parameters, unitary)
+        eng.apply(parameters, out)
+        return [out] + derivs
+
+    def get_Matrix(self, parameters=None, is_f32=False):
+        """C(parameters) as a dense 2^n x 2^n matrix (apply_to on the identity, Gates_block::get_matrix)."""
+        if parameters is None:
+            parameters = np.zeros(0)
+        m = np.eye(1 << self.qbit_num, dtype=np.complex128)
+        self._get_engine().apply(parameters, m)
+        return m

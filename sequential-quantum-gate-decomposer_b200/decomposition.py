@@ -1,0 +1,174 @@
+"""Host-side mirror of the cost path of the reference decomposition classes.
+
+``N_Qubit_Decomposition_adaptive`` keeps the constructor and method names of the CPython wrapper
+(squander/decomposition/qgd_N_Qubit_Decompositions_Wrapper.cpp:281-291, 3125-3248) for the calls that sit on the
+hot path: ``add_Adaptive_Layers``, ``add_Finalyzing_Layer_To_Gate_Structure``, ``set_Gate_Structure``,
+``get_Parameter_Num``, ``set_Cost_Function_Variant``, ``set_Trace_Offset``, ``Optimization_Problem``,
+``Optimization_Problem_Grad``, ``Optimization_Problem_Combined``, ``Optimization_Problem_Batch``,
+``Optimization_Problem_Combined_Unitary``, ``get_Matrix``. ``accelerator_num`` is the number of GPUs, exactly the
+kwarg the reference reserves for accelerators (Optimization_Interface.cpp:189-197); it must be >= 1 here --
+the CPU path belongs to the reference, not to this package.
+
+The optimizers / synthesis strategies above these calls are out of scope and not mirrored.
+"""
+import numpy as np
+
+from . import abi
+from .circuit import Circuit
+from .engine import Engine
+
+
+class N_Qubit_Decomposition_custom:
+    """Cost path of Optimization_Interface over a user-supplied gate structure."""
+
+    def __init__(self, Umtx, qbit_num=-1, config=None, accelerator_num=1, device=0):
+        U = np.ascontiguousarray(Umtx, dtype=np.complex128)
+        if U.ndim != 2:
+            raise Exception("Umtx should be a 2 dimensional complex array")
+        rows = U.shape[0]
+        n = int(round(np.log2(rows)))
+        if (1 << n) != rows:
+            raise Exception("Umtx should have 2^n rows")
+        if qbit_num not in (-1, n):
+            raise Exception("qbit_num does not match the size of Umtx")
+        if U.shape[1] > rows:
+            raise Exception("Umtx cannot have more columns than rows")
+        if accelerator_num < 1:
+            raise Exception("accelerator_num should be >= 1: this package only provides the GPU path")
+        self.qbit_num = n
+        self.Umtx = U
+        self.config = dict(config or {})
+        self.accelerator_num = int(accelerator_num)
+        self._circuit = Circuit(n)
+        self._variant = abi.FROBENIUS_NORM
+        self._trace_offset = 0
+        self._prev_cost = 1.0  # Optimization_Interface.cpp:74-76
+        self._c1 = 1 / 1.7
+        self._c2 = 1 / 2.0
+        self._engine = Engine(device)
+        self._engine.upload_matrix(U)
+        self._dirty = True
+
+    # ---- gate structure -------------------------------------------------------------------------------------
+    def set_Gate_Structure(self, circuit):
+        """Optimization_Interface::set_custom_gate_structure (Optimization_Interface.cpp:1770-1778)."""
+        if circuit.qbit_num != self.qbit_num:
+            raise Exception("set_Gate_Structure: qubit count mismatch")
+        self._circuit = Circuit(self.qbit_num)
+        self._circuit._items = list(circuit._items)  # release_gates(); combine(gate_structure_in)
+        self._dirty = True
+
+    def get_Circuit(self):
+        return self._circuit
+
+    def get_Parameter_Num(self):
+        return self._circuit.get_Parameter_Num()
+
+    def get_Qbit_Num(self):
+        return self.qbit_num
+
+    # ---- cost configuration ---------------------------------------------------------------------------------
+    def set_Cost_Function_Variant(self, costfnc=0):
+        self._variant = int(costfnc)
+        self._dirty = True
+
+    def set_Trace_Offset(self, trace_offset=0):
+        self._trace_offset = int(trace_offset)
+        self._dirty = True
+
+    def get_Trace_Offset(self):
+        return self._trace_offset
+
+    def set_Previous_Cost_Function_Value(self, value):
+        """prev_cost_fnv_val, written by the ADAM engines (optimization_engines/ADAM.cpp:201)."""
+        self._prev_cost = float(value)
+        self._dirty = True
+
+    def _sync(self):
+        if self._dirty:
+            self._engine.set_circuit(self._circuit)
+            self._engine.set_cost(self._variant, self._trace_offset, self._prev_cost, self._c1, self._c2)
+            self._dirty = False
+        return self._engine
+
+    # ---- the hot path ---------------------------------------------------------------------------------------
+    def Optimization_Problem(self, parameters):
+        """Optimization_Interface::optimization_problem (Optimization_Interface.cpp:634-668)."""
+        return float(self._sync().cost_batched(np.asarray(parameters, dtype=np.float64).reshape(1, -1))[0])
+
+    def Optimization_Problem_Batch(self, parameters):
+        """optimization_problem_batched (Optimization_Interface.cpp:939-1033): rows of a 2-D array."""
+        p = np.asarray(parameters, dtype=np.float64)
+        if p.ndim != 2:
+            raise Exception("Optimization_Problem_Batch: parameters should be a 2 dimensional array")
+        return self._sync().cost_batched(p)
+
+    def Optimization_Problem_Combined(self, parameters):
+        """optimization_problem_combined (Optimization_Interface.cpp:1145-1490): (f0, grad)."""
+        c, g = self._sync().cost_grad_batched(np.asarray(parameters, dtype=np.float64).reshape(1, -1))
+        return float(c[0]), g[0]
+
+    def Optimization_Problem_Combined_Batch(self, parameters):
+        """Batched (f, grad): the entry the GPU engine adds; row b equals
+        Optimization_Problem_Combined(parameters[b])."""
+        return self._sync().cost_grad_batched(np.asarray(parameters, dtype=np.float64))
+
+    def Optimization_Problem_Grad(self, parameters):
+        """optimization_problem_grad (Optimization_Interface.cpp:1124-1133)."""
+        return self.Optimization_Problem_Combined(parameters)[1]
+
+    def Optimization_Problem_Combined_Unitary(self, parameters):
+        """optimization_problem_combined_unitary (Optimization_Interface.cpp:1525-1547): (C Umtx, [d_i C Umtx])."""
+        eng = self._sync()
+        derivs = eng.apply_derivative(parameters, self.Umtx)
+        m = self.Umtx.copy()
+        eng.apply(parameters, m)
+        return m, derivs
+
+    def get_Matrix(self, parameters):
+        """Unitary of the gate structure itself (Gates_block::get_matrix)."""
+        self._sync()
+        m = np.eye(1 << self.qbit_num, dtype=np.complex128)
+        self._engine.apply(parameters, m)
+        return m
+
+
+class N_Qubit_Decomposition_adaptive(N_Qubit_Decomposition_custom):
+    """Adaptive gate structure builder + cost path (N_Qubit_Decomposition_adaptive.cpp:1820-1966)."""
+
+    def __init__(self, Umtx, qbit_num=-1, level_limit_max=8, level_limit_min=0, topology=None, config=None,
+                 accelerator_num=1, device=0):
+        super().__init__(Umtx, qbit_num=qbit_num, config=config, accelerator_num=accelerator_num, device=device)
+        self.level_limit = int(level_limit_max)
+        self.level_limit_min = int(level_limit_min)
+        self.topology = [tuple(int(q) for q in pair) for pair in (topology or [])]
+        for pair in self.topology:
+            if len(pair) != 2:
+                raise Exception("The connectivity data should contains two qubits.")
+            if max(pair) >= self.qbit_num:
+                raise Exception("Label of control/target qubit should be less than the number of qubits in the register.")
+
+    def add_Adaptive_Layers(self):
+        """One level: for every pair a sub-block [U3(target), U3(control), Adaptive(target, control)]
+        (N_Qubit_Decomposition_adaptive.cpp:1840-1881), appended to the top-level structure one by one
+        (gate_structure->combine(layer), :1806-1811). Deterministic order only (the randomized order needs the
+        reference's RNG stream and sits above the hot path)."""
+        if self.topology:
+            pairs = [(t, c) for (c, t) in self.topology]  # (*it)[0] is the control, [1] the target (:1849-1850)
+        else:
+            pairs = [(t, c) for t in range(self.qbit_num) for c in range(t + 1, self.qbit_num)]
+        for t, c in pairs:
+            layer = Circuit(self.qbit_num)
+            layer.add_U3(t)
+            layer.add_U3(c)
+            layer.add_adaptive(t, c)
+            self._circuit.add_Circuit(layer)
+        self._dirty = True
+
+    def add_Finalyzing_Layer_To_Gate_Structure(self):
+        """U3 on every qubit (N_Qubit_Decomposition_adaptive.cpp:1947-1966)."""
+        block = Circuit(self.qbit_num)
+        for q in range(self.qbit_num):
+            block.add_U3(q)
+        self._circuit.add_Circuit(block)
+        self._dirty = True
