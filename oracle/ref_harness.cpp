@@ -23,9 +23,18 @@
 #include "Variational_Quantum_Eigensolver_Base.h"
 #include "matrix_sparse.h"
 
+// The reference runs BLAS single-threaded inside its own TBB tasks (dot(): openblas_set_num_threads(1) / MKL
+// equivalents, common/dot.cpp:40-50). The build here leaves BLAS "undefined" (=0), so pin the scipy-bundled OpenBLAS
+// to one thread once; parallelism comes from the parallel_for shim exactly as TBB would provide it.
+extern "C" void scipy_openblas_set_num_threads(int);
+
 namespace {
 
 thread_local std::string g_err;
+
+struct BlasInit {
+    BlasInit() { scipy_openblas_set_num_threads(1); }
+} g_blas_init;
 
 struct DecompAccess : public N_Qubit_Decomposition_custom {
     using N_Qubit_Decomposition_custom::N_Qubit_Decomposition_custom;
@@ -33,7 +42,7 @@ struct DecompAccess : public N_Qubit_Decomposition_custom {
     void set_scales(double c1, double c2) { correction1_scale = c1; correction2_scale = c2; }
     void set_parallel(int p) {
         Config_Element e;
-        e.set_property("parallel", (long)p);
+        e.set_property("parallel", (long long)p);  // read back as long long (Decomposition_Base.cpp:1187-1190)
         config["parallel"] = e;
     }
 };

@@ -91,17 +91,13 @@ void parallel_for(I first, I last, const F& f) {
     for (I i = first; i < last; ++i) f(i);
 }
 
+// parallel_invoke runs its tasks one after the other: every call site on the hot path pairs one cheap task with one
+// that opens a wide parallel_for (Gates_block::apply_to_combined, Gates_block.cpp:1344-1364), and OpenMP -- unlike
+// TBB -- would serialise that inner loop if the invoke itself were a 2-thread parallel region.
 template <typename F0, typename F1>
 void parallel_invoke(const F0& f0, const F1& f1) {
-    if (shim_serial() || omp_in_parallel()) { f0(); f1(); return; }
-    // two top-level tasks; each may open its own (nested => serial) loops
-#pragma omp parallel sections num_threads(2)
-    {
-#pragma omp section
-        f0();
-#pragma omp section
-        f1();
-    }
+    f0();
+    f1();
 }
 template <typename F0, typename F1, typename F2>
 void parallel_invoke(const F0& f0, const F1& f1, const F2& f2) { f0(); f1(); f2(); }

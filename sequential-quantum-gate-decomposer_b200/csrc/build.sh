@@ -1,0 +1,8 @@
+#!/bin/bash
+# Builds libsqgpu.so in-tree for sm_100a (cross-compiles without a GPU). Usage: ./build.sh [extra nvcc flags]
+set -e
+cd "$(dirname "$0")"
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+$NVCC -std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo \
+      -Xcompiler -fPIC,-O3,-Wall,-Wno-unused-function -shared -cudart static \
+      -ccbin /usr/bin/g++ "$@" -o libsqgpu.so sqgpu.cu

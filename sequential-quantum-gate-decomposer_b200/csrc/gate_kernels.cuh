@@ -1,0 +1,158 @@
+// gate_kernels.cuh -- closed-form gate kernels built ON THE DEVICE from the parameter vector, one thread per
+// (parameter set, gate). Replaces the host-side per-gate builders of the reference
+// (squander/src-cpp/gates/include/gate_kernel_templates.h; dispatch in U3.cpp:89-142, RY.cpp:27-105, CU.cpp:100-180,
+// R.cpp, U2.cpp, RXX/RYY/RZZ.cpp) and Gates_block's sincos batch (Gates_block.cpp:269-279).
+//
+// Conventions copied from the reference: the stored parameter of a "theta" slot is theta/2 and sincos is taken of the
+// stored value (U3.cpp:49-51, Gate.cpp:1430-1446); Adaptive == CRY with an identity activation (Adaptive.cpp:28-32,
+// common/common.cpp:35-38); derivative kernels are the reference's explicit ones, including their zeroed entries
+// (gate_kernel_templates.h:554-609).
+#pragma once
+#include "sq_types.cuh"
+#include "../../include/sqgpu.h"
+
+namespace sq {
+
+struct Trig {
+    double s[4], c[4];
+};
+
+__device__ __forceinline__ void k2(cplx* k, double r0, double i0, double r1, double i1, double r2, double i2, double r3,
+                                   double i3) {
+    k[0] = cmake(r0, i0);
+    k[1] = cmake(r1, i1);
+    k[2] = cmake(r2, i2);
+    k[3] = cmake(r3, i3);
+}
+
+__device__ __forceinline__ void rot_phase(cplx* k, double sg, double cg) {  // multiply_2x2_by_phase :611-619
+#pragma unroll
+    for (int i = 0; i < 4; ++i) k[i] = cmake(k[i].x * cg - k[i].y * sg, k[i].x * sg + k[i].y * cg);
+}
+
+// U3 body shared by U3 and CU. which: -1 forward, 0/1/2 derivative wrt theta/phi/lambda.
+__device__ __forceinline__ void u3_body(cplx* k, int which, double st, double ct, double sp, double cp, double sl,
+                                        double cl) {
+    const double spl = sp * cl + cp * sl;
+    const double cpl = cp * cl - sp * sl;
+    if (which < 0) k2(k, ct, 0.0, -st * cl, -st * sl, st * cp, st * sp, ct * cpl, ct * spl);
+    else if (which == 0) k2(k, -st, 0.0, -ct * cl, -ct * sl, ct * cp, ct * sp, -st * cpl, -st * spl);
+    else if (which == 1) k2(k, 0.0, 0.0, 0.0, 0.0, -st * sp, st * cp, -ct * spl, ct * cpl);
+    else k2(k, 0.0, 0.0, st * sl, -st * cl, 0.0, 0.0, -ct * spl, ct * cpl);
+}
+
+__device__ __forceinline__ void zero16(cplx* k) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) k[i] = czero();
+}
+
+// Writes the dim x dim kernel of `type` (which < 0) or its derivative wrt parameter `which`. Returns dim (0: unknown).
+__device__ inline int build_gate_kernel(int type, const Trig& t, int which, cplx* k) {
+    const double s0 = t.s[0], c0 = t.c[0], s1 = t.s[1], c1 = t.c[1], s2 = t.s[2], c2 = t.c[2], s3 = t.s[3], c3 = t.c[3];
+    const double sq2 = 0.70710678118654752440;  // M_SQRT1_2
+    const bool fwd = which < 0;
+    switch (type) {
+        case SQGPU_U3: u3_body(k, which, s0, c0, s1, c1, s2, c2); return 2;
+        case SQGPU_CU:
+            if (which == 3) {  // d/dgamma = i * kernel  (:647-656)
+                u3_body(k, -1, s0, c0, s1, c1, s2, c2);
+                rot_phase(k, s3, c3);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) k[i] = cmake(-k[i].y, k[i].x);
+            } else {
+                u3_body(k, which, s0, c0, s1, c1, s2, c2);
+                rot_phase(k, s3, c3);
+            }
+            return 2;
+        case SQGPU_RX: case SQGPU_CRX:
+            if (fwd) k2(k, c0, 0, 0, -s0, 0, -s0, c0, 0); else k2(k, -s0, 0, 0, -c0, 0, -c0, -s0, 0);
+            return 2;
+        case SQGPU_RY: case SQGPU_CRY: case SQGPU_ADAPTIVE:
+            if (fwd) k2(k, c0, 0, -s0, 0, s0, 0, c0, 0); else k2(k, -s0, 0, -c0, 0, c0, 0, -s0, 0);
+            return 2;
+        case SQGPU_RZ: case SQGPU_CRZ:
+            if (fwd) k2(k, c0, -s0, 0, 0, 0, 0, c0, s0); else k2(k, -s0, -c0, 0, 0, 0, 0, -s0, c0);
+            return 2;
+        case SQGPU_U1: case SQGPU_CP:
+            if (fwd) k2(k, 1, 0, 0, 0, 0, 0, c0, s0); else k2(k, 0, 0, 0, 0, 0, 0, -s0, c0);
+            return 2;
+        case SQGPU_U2: {
+            const double spl = s0 * c1 + c0 * s1, cpl = c0 * c1 - s0 * s1;
+            if (fwd) k2(k, sq2, 0, -sq2 * c1, -sq2 * s1, sq2 * c0, sq2 * s0, sq2 * cpl, sq2 * spl);
+            else if (which == 0) k2(k, 0, 0, 0, 0, -sq2 * s0, sq2 * c0, -sq2 * spl, sq2 * cpl);
+            else k2(k, 0, 0, sq2 * s1, -sq2 * c1, 0, 0, -sq2 * spl, sq2 * cpl);
+            return 2;
+        }
+        case SQGPU_R: case SQGPU_CR:
+            if (fwd) k2(k, c0, 0, -s0 * s1, -s0 * c1, s0 * s1, -s0 * c1, c0, 0);
+            else if (which == 0) k2(k, -s0, 0, -c0 * s1, -c0 * c1, c0 * s1, -c0 * c1, -s0, 0);
+            else k2(k, 0, 0, -s0 * c1, s0 * s1, s0 * c1, s0 * s1, 0, 0);
+            return 2;
+        case SQGPU_X: case SQGPU_CNOT: case SQGPU_CCX: k2(k, 0, 0, 1, 0, 1, 0, 0, 0); return 2;
+        case SQGPU_Y: k2(k, 0, 0, 0, -1, 0, 1, 0, 0); return 2;
+        case SQGPU_Z: case SQGPU_CZ: k2(k, 1, 0, 0, 0, 0, 0, -1, 0); return 2;
+        case SQGPU_H: case SQGPU_CH: k2(k, sq2, 0, sq2, 0, sq2, 0, -sq2, 0); return 2;
+        case SQGPU_S: k2(k, 1, 0, 0, 0, 0, 0, 0, 1); return 2;
+        case SQGPU_SDG: k2(k, 1, 0, 0, 0, 0, 0, 0, -1); return 2;
+        case SQGPU_T: k2(k, 1, 0, 0, 0, 0, 0, sq2, sq2); return 2;
+        case SQGPU_TDG: k2(k, 1, 0, 0, 0, 0, 0, sq2, -sq2); return 2;
+        case SQGPU_SX: k2(k, .5, .5, .5, -.5, .5, -.5, .5, .5); return 2;
+        case SQGPU_SXDG: k2(k, .5, -.5, .5, .5, .5, .5, .5, -.5); return 2;
+        case SQGPU_RXX: {  // :669-695
+            zero16(k);
+            const cplx d = fwd ? cmake(c0, 0) : cmake(-s0, 0), o = fwd ? cmake(0, -s0) : cmake(0, -c0);
+            k[0] = d; k[5] = d; k[10] = d; k[15] = d; k[3] = o; k[6] = o; k[9] = o; k[12] = o;
+            return 4;
+        }
+        case SQGPU_RYY: {  // :704-730
+            zero16(k);
+            const cplx d = fwd ? cmake(c0, 0) : cmake(-s0, 0);
+            const cplx op = fwd ? cmake(0, s0) : cmake(0, c0), om = fwd ? cmake(0, -s0) : cmake(0, -c0);
+            k[0] = d; k[5] = d; k[10] = d; k[15] = d; k[3] = op; k[12] = op; k[6] = om; k[9] = om;
+            return 4;
+        }
+        case SQGPU_RZZ: {  // :739-765
+            zero16(k);
+            const cplx m = fwd ? cmake(c0, -s0) : cmake(-s0, -c0), p = fwd ? cmake(c0, s0) : cmake(-s0, c0);
+            k[0] = m; k[15] = m; k[5] = p; k[10] = p;
+            return 4;
+        }
+        case SQGPU_SWAP: case SQGPU_CSWAP:
+            zero16(k);
+            k[0] = cmake(1, 0); k[6] = cmake(1, 0); k[9] = cmake(1, 0); k[15] = cmake(1, 0);
+            return 4;
+        default: return 0;
+    }
+}
+
+// One thread per (parameter set b, op): fills the forward kernel table and the derivative kernel table.
+// ktab[b * kern_total + op.kern_off + ...], dktab[b * dkern_total + op.dkern_off + p * dim*dim + ...].
+__global__ void build_kernel_tables(const DevOp* __restrict__ ops, int n_ops, const double* __restrict__ params,
+                                    int n_params, int batch, cplx* __restrict__ ktab, int kern_total,
+                                    cplx* __restrict__ dktab, int dkern_total, int with_deriv) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= batch * n_ops) return;
+    const int b = idx / n_ops;
+    const DevOp op = ops[idx - b * n_ops];
+    if (op.kern_off < 0) return;  // constant kernel (GENERAL) lives in the pool
+    Trig t;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        t.s[i] = 0.0;
+        t.c[i] = 1.0;
+        if (i < op.n_params) sincos(params[(size_t)b * n_params + op.param_start + i], &t.s[i], &t.c[i]);
+    }
+    cplx k[16];
+    const int dim = build_gate_kernel(op.type, t, -1, k);
+    cplx* dst = ktab + (size_t)b * kern_total + op.kern_off;
+    for (int i = 0; i < dim * dim; ++i) dst[i] = k[i];
+    if (with_deriv) {
+        for (int p = 0; p < op.n_params; ++p) {
+            build_gate_kernel(op.type, t, p, k);
+            cplx* dd = dktab + (size_t)b * dkern_total + op.dkern_off + p * dim * dim;
+            for (int i = 0; i < dim * dim; ++i) dd[i] = k[i];
+        }
+    }
+}
+
+}  // namespace sq

@@ -1,0 +1,129 @@
+// reduce.cuh -- deterministic reduction of the executor's per-CTA partials and the cost / gradient formulas.
+//
+//   reduce_partials   : tr_part[y][chunk][6], w_part[y][chunk][w_total]  ->  traces[y][1+P][3][2]
+//                       k = 0: the three trace terms of C(theta) U; k = 1+p: dL_p = sum_{r,c} dK_p[r][c] W[r][c], the
+//                       derivative of the functional L = sum_t omega_t T_t (stored in slot t = 0).
+//   cost_from_traces  : calculate_cost_function (decomposition/Optimization_Interface.cpp:677-735) and the gradient
+//                       component formulas (Optimization_Interface.cpp:1397-1458) on (possibly rank-summed) traces.
+//   make_omega        : weights of the second pass for the Hilbert-Schmidt-with-corrections variants.
+#pragma once
+#include "sq_types.cuh"
+#include "../../include/sqgpu.h"
+
+namespace sq {
+
+// traces layout helpers
+__host__ __device__ __forceinline__ size_t tr_index(int y, int k, int n_k, int t) { return (((size_t)y * n_k + k) * 3 + t) * 2; }
+
+__global__ void reduce_partials(const double* __restrict__ tr_part, int nchunks, const cplx* __restrict__ w_part,
+                                int w_total, const DevOp* __restrict__ ops, const int* __restrict__ param_op,
+                                const cplx* __restrict__ dktab, int dkern_total, int n_params, int with_grad,
+                                double* __restrict__ traces) {
+    const int y = blockIdx.x;
+    const int n_k = 1 + (with_grad ? n_params : 0);
+    if (threadIdx.x < 6) {
+        double s = 0;
+        for (int ch = 0; ch < nchunks; ++ch) s += tr_part[((size_t)y * nchunks + ch) * 6 + threadIdx.x];
+        traces[tr_index(y, 0, n_k, 0) + threadIdx.x] = s;
+    }
+    if (!with_grad) return;
+    for (int p = threadIdx.x; p < n_params; p += blockDim.x) {
+        const DevOp op = ops[param_op[p]];
+        const int d2 = op.dim * op.dim;
+        const cplx* dk = dktab + (size_t)y * dkern_total + op.dkern_off + (p - op.param_start) * d2;
+        cplx acc = czero();
+        for (int e = 0; e < d2; ++e) {
+            cplx w = czero();
+            for (int ch = 0; ch < nchunks; ++ch) w = cadd(w, w_part[((size_t)y * nchunks + ch) * w_total + op.w_off + e]);
+            acc = cfma(dk[e], w, acc);
+        }
+        double* dst = traces + tr_index(y, 1 + p, n_k, 0);
+        dst[0] = acc.x;
+        dst[1] = acc.y;
+        dst[2] = dst[3] = dst[4] = dst[5] = 0.0;
+    }
+}
+
+struct CostCfg {
+    int variant;
+    double prev, c1, c2;
+};
+
+__device__ __forceinline__ double cost_formula(const CostCfg& c, const double* t, double n) {
+    const double sp = sqrt(c.prev);
+    switch (c.variant) {
+        case SQGPU_FROBENIUS_NORM: return 1.0 - t[0] / n;
+        case SQGPU_FROBENIUS_NORM_CORRECTION1: return (1.0 - t[0] / n) - sp * (t[2] / n) * c.c1;
+        case SQGPU_FROBENIUS_NORM_CORRECTION2: return (1.0 - t[0] / n) - sp * ((t[2] / n) * c.c1 + (t[4] / n) * c.c2);
+        case SQGPU_HILBERT_SCHMIDT_TEST: { const double d = 1.0 / n; return 1.0 - d * d * (t[0] * t[0] + t[1] * t[1]); }
+        case SQGPU_HILBERT_SCHMIDT_TEST_CORRECTION1: {
+            const double d = 1.0 / n;
+            return 1 - d * d * (t[0] * t[0] + t[1] * t[1] + sp * c.c1 * (t[2] * t[2] + t[3] * t[3]));
+        }
+        case SQGPU_HILBERT_SCHMIDT_TEST_CORRECTION2: {
+            const double d = 1.0 / n;
+            return 1 - d * d * (t[0] * t[0] + t[1] * t[1] + sp * (c.c1 * (t[2] * t[2] + t[3] * t[3]) + c.c2 * (t[4] * t[4] + t[5] * t[5])));
+        }
+        case SQGPU_INFIDELITY: return 1.0 - ((t[0] * t[0] + t[1] * t[1]) / n + 1) / (n + 1);
+        default: return nan("");
+    }
+}
+
+// dl = {Re, Im} of dL_p with the omega of `make_omega` / the variant defaults
+__device__ __forceinline__ double grad_formula(const CostCfg& c, const double* t, const double* dl, double n) {
+    switch (c.variant) {
+        case SQGPU_FROBENIUS_NORM:
+        case SQGPU_FROBENIUS_NORM_CORRECTION1:
+        case SQGPU_FROBENIUS_NORM_CORRECTION2: return (1.0 - dl[0] / n) - 1.0;
+        case SQGPU_HILBERT_SCHMIDT_TEST: {
+            const double d = 1.0 / n;
+            return -2.0 * d * d * t[0] * dl[0] - 2.0 * d * d * t[1] * dl[1];
+        }
+        case SQGPU_HILBERT_SCHMIDT_TEST_CORRECTION1:
+        case SQGPU_HILBERT_SCHMIDT_TEST_CORRECTION2: {
+            const double d = 1.0 / n;
+            return -2.0 * d * d * dl[0];
+        }
+        case SQGPU_INFIDELITY: return -2.0 / n / (n + 1) * t[0] * dl[0] - 2.0 / n / (n + 1) * t[1] * dl[1];
+        default: return nan("");
+    }
+}
+
+__global__ void cost_from_traces(const double* __restrict__ traces, int n_params, int with_grad, int cols_total,
+                                 CostCfg cfg, double* __restrict__ cost, double* __restrict__ grad) {
+    const int y = blockIdx.x;
+    const int n_k = 1 + (with_grad ? n_params : 0);
+    const double* t = traces + tr_index(y, 0, n_k, 0);
+    const double n = (double)cols_total;
+    if (threadIdx.x == 0 && cost) cost[y] = cost_formula(cfg, t, n);
+    if (!with_grad || !grad) return;
+    for (int p = threadIdx.x; p < n_params; p += blockDim.x)
+        grad[(size_t)y * n_params + p] = grad_formula(cfg, t, traces + tr_index(y, 1 + p, n_k, 0), n);
+}
+
+// omega[y][3]: weights of the trace types in L. Variant defaults need no data; the HS-with-corrections variants take
+// w_t * conj(T_t) from the traces of a cost-only pre-pass (Optimization_Interface.cpp:1414-1434).
+__global__ void make_omega(const double* __restrict__ traces, int n_k, CostCfg cfg, int batch, cplx* __restrict__ omega) {
+    const int y = blockIdx.x * blockDim.x + threadIdx.x;
+    if (y >= batch) return;
+    const double sp = sqrt(cfg.prev);
+    cplx w0 = cmake(1.0, 0.0), w1 = czero(), w2 = czero();
+    switch (cfg.variant) {
+        case SQGPU_FROBENIUS_NORM_CORRECTION1: w1 = cmake(sp * cfg.c1, 0); break;
+        case SQGPU_FROBENIUS_NORM_CORRECTION2: w1 = cmake(sp * cfg.c1, 0); w2 = cmake(sp * cfg.c2, 0); break;
+        case SQGPU_HILBERT_SCHMIDT_TEST_CORRECTION1:
+        case SQGPU_HILBERT_SCHMIDT_TEST_CORRECTION2: {
+            const double* t = traces + tr_index(y, 0, n_k, 0);
+            w0 = cmake(t[0], -t[1]);
+            w1 = cmake(sp * cfg.c1 * t[2], -sp * cfg.c1 * t[3]);
+            if (cfg.variant == SQGPU_HILBERT_SCHMIDT_TEST_CORRECTION2) w2 = cmake(sp * cfg.c2 * t[4], -sp * cfg.c2 * t[5]);
+            break;
+        }
+        default: break;
+    }
+    omega[(size_t)y * 3 + 0] = w0;
+    omega[(size_t)y * 3 + 1] = w1;
+    omega[(size_t)y * 3 + 2] = w2;
+}
+
+}  // namespace sq

@@ -1,0 +1,1166 @@
+// sqgpu.cu -- context, circuit lowering and the extern "C" entry points declared in include/sqgpu.h.
+//
+// Host side of the B200 engine: owns device memory (grow-only workspaces, the resident matrix of
+// sqgpu_upload_matrix == the reference's load2LMEM, common/common_DFE.cpp:129-132), lowers the gate descriptors to
+// the device program once per sqgpu_set_circuit, and launches
+//   build_kernel_tables -> fused_exec<COST|GRAD|APPLY> (or the streaming kernels) -> reduce_partials -> cost_from_traces
+// on one stream without host round trips. No CPU evaluation path exists in this file.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/sqgpu.h"
+#include "exec_fused.cuh"
+#include "exec_stream.cuh"
+#include "gate_kernels.cuh"
+#include "reduce.cuh"
+#include "sq_types.cuh"
+#include "vqe.cuh"
+
+using namespace sq;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                      \
+    do {                                                                                                    \
+        cudaError_t _e = (expr);                                                                            \
+        if (_e != cudaSuccess)                                                                              \
+            return fail(_e == cudaErrorMemoryAllocation ? SQGPU_ERR_NOMEM : SQGPU_ERR_CUDA, "%s failed: %s", \
+                        #expr, cudaGetErrorString(_e));                                                     \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return SQGPU_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            return fail(SQGPU_ERR_NOMEM, "cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+        }
+        cap = want;
+        return SQGPU_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct KernelTimer {  // CUDA-event timing of the dominant kernel on the launching stream
+    static const int RING = 64;
+    cudaEvent_t e0[RING], e1[RING];
+    int n = 0;
+    bool init = false;
+    std::string name;
+    void ensure() {
+        if (init) return;
+        for (int i = 0; i < RING; ++i) {
+            cudaEventCreate(&e0[i]);
+            cudaEventCreate(&e1[i]);
+        }
+        init = true;
+    }
+    void destroy() {
+        if (!init) return;
+        for (int i = 0; i < RING; ++i) {
+            cudaEventDestroy(e0[i]);
+            cudaEventDestroy(e1[i]);
+        }
+        init = false;
+    }
+};
+
+}  // namespace
+
+struct sqgpu_ctx {
+    int device = 0;
+    int sm_count = 148;
+    int smem_optin = 0;
+    std::mutex mtx;
+    cudaStream_t stream = nullptr;
+
+    // resident matrix (sqgpu_upload_matrix)
+    DevBuf U;
+    int rows = 0, cols = 0;
+
+    // circuit
+    std::vector<DevOp> ops;
+    std::vector<int> param_op;
+    DevBuf dOps, dParamOp, dPool;
+    int n_params = 0, qbit_num = 0, n_ops = 0;
+    int kern_total = 0, dkern_total = 0, w_total = 0, wmax = 4;
+    bool has_dense = false, all_unitary = true, circuit_set = false;
+    std::vector<cplx> pool;
+
+    // cost configuration
+    CostCfg cfg{SQGPU_FROBENIUS_NORM, 1.0, 1.0 / 1.7, 0.5};
+    int trace_offset = 0;
+
+    // workspaces
+    DevBuf wParams, wKtab, wDKtab, wTrPart, wWPart, wTraces, wOmega, wCost, wGrad, wMat, wDerivIdx, wTraces0;
+
+    // Hamiltonian (VQE)
+    DevBuf hIndptr, hIndices, hValues;
+    int h_rows = 0;
+    long long h_nnz = 0;
+
+    long long launches = 0;
+    KernelTimer timer;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        cudaGetDevice(&cur);
+        if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+int n_trace_types_of(int variant) {
+    switch (variant) {
+        case SQGPU_FROBENIUS_NORM_CORRECTION1:
+        case SQGPU_HILBERT_SCHMIDT_TEST_CORRECTION1: return 2;
+        case SQGPU_FROBENIUS_NORM_CORRECTION2:
+        case SQGPU_HILBERT_SCHMIDT_TEST_CORRECTION2: return 3;
+        default: return 1;
+    }
+}
+
+bool variant_supported(int v) {
+    return v == SQGPU_FROBENIUS_NORM || v == SQGPU_FROBENIUS_NORM_CORRECTION1 || v == SQGPU_FROBENIUS_NORM_CORRECTION2 ||
+           v == SQGPU_HILBERT_SCHMIDT_TEST || v == SQGPU_HILBERT_SCHMIDT_TEST_CORRECTION1 ||
+           v == SQGPU_HILBERT_SCHMIDT_TEST_CORRECTION2 || v == SQGPU_INFIDELITY;
+}
+
+// the trace offset only enters the Frobenius-family cost functions (get_cost_function*, :73-404); get_trace* ignore it
+int effective_offset(const sqgpu_ctx* c) { return c->cfg.variant <= SQGPU_FROBENIUS_NORM_CORRECTION2 ? c->trace_offset : 0; }
+
+int param_count_of(int type) {
+    switch (type) {
+        case SQGPU_U3: return 3;
+        case SQGPU_CU: return 4;
+        case SQGPU_U2: case SQGPU_R: case SQGPU_CR: return 2;
+        case SQGPU_RX: case SQGPU_RY: case SQGPU_RZ: case SQGPU_U1: case SQGPU_CRY: case SQGPU_CRX: case SQGPU_CRZ:
+        case SQGPU_CP: case SQGPU_ADAPTIVE: case SQGPU_RXX: case SQGPU_RYY: case SQGPU_RZZ: return 1;
+        case SQGPU_GENERAL: case SQGPU_CZ: case SQGPU_CNOT: case SQGPU_CH: case SQGPU_X: case SQGPU_Y: case SQGPU_Z:
+        case SQGPU_H: case SQGPU_S: case SQGPU_SDG: case SQGPU_T: case SQGPU_TDG: case SQGPU_SX: case SQGPU_SXDG:
+        case SQGPU_CCX: case SQGPU_SWAP: case SQGPU_CSWAP: return 0;
+        default: return -1;  // CROT, SYC: not on the device path yet
+    }
+}
+
+// Lower one descriptor to a DevOp (offsets are assigned by the caller). Returns 0 or a status.
+int lower_gate(const sqgpu_gate_desc& g, int qbit_num, const double* pool, int64_t pool_len, DevOp* out, bool* unitary) {
+    DevOp op;
+    memset(&op, 0, sizeof(op));
+    op.type = g.type;
+    op.kern_off = -1;
+    op.dkern_off = -1;
+    op.w_off = -1;
+    const int np = param_count_of(g.type);
+    if (np < 0) return fail(SQGPU_ERR_UNSUPPORTED, "gate type %d is not supported on the device path", g.type);
+    if (g.n_params != np) return fail(SQGPU_ERR_INVALID, "gate type %d takes %d parameters, descriptor says %d", g.type, np, g.n_params);
+    op.n_params = np;
+    op.param_start = g.param_start;
+    auto qok = [&](int q) { return q >= 0 && q < qbit_num; };
+    *unitary = true;
+    if (g.type == SQGPU_GENERAL) {
+        const int k = g.n_qubits;
+        if (k < 1 || k > SQGPU_MAX_GENERAL_QUBITS) return fail(SQGPU_ERR_INVALID, "GENERAL gate: 1..5 qubits supported, got %d", k);
+        const int dim = 1 << k;
+        if (!pool || g.matrix_off < 0 || g.matrix_off + (int64_t)dim * dim > pool_len) return fail(SQGPU_ERR_INVALID, "GENERAL gate: kernel outside the matrix pool");
+        for (int j = 0; j < k; ++j) {
+            if (!qok(g.qubits[j])) return fail(SQGPU_ERR_INVALID, "GENERAL gate: qubit %d out of range", g.qubits[j]);
+            if (j && g.qubits[j] <= g.qubits[j - 1]) return fail(SQGPU_ERR_INVALID, "GENERAL gate: qubits must be ascending");
+        }
+        op.pool_off = g.matrix_off;
+        if (k == 1) {
+            op.dim = 2;
+            op.target = g.qubits[0];
+        } else {
+            op.dim = dim;
+            op.nq = k;
+            for (int j = 0; j < k; ++j) op.q[j] = g.qubits[j];
+        }
+        // K K^dagger == I ? (the adjoint sweep un-applies gates with K^dagger)
+        const double* K = pool + 2 * g.matrix_off;
+        double worst = 0;
+        for (int r = 0; r < dim; ++r)
+            for (int c = 0; c < dim; ++c) {
+                double re = 0, im = 0;
+                for (int l = 0; l < dim; ++l) {
+                    const double ar = K[2 * (r * dim + l)], ai = K[2 * (r * dim + l) + 1];
+                    const double br = K[2 * (c * dim + l)], bi = -K[2 * (c * dim + l) + 1];
+                    re += ar * br - ai * bi;
+                    im += ar * bi + ai * br;
+                }
+                worst = std::max(worst, std::max(std::fabs(re - (r == c ? 1.0 : 0.0)), std::fabs(im)));
+            }
+        *unitary = worst < 1e-9;
+        *out = op;
+        return SQGPU_OK;
+    }
+    const bool two_target = g.type == SQGPU_RXX || g.type == SQGPU_RYY || g.type == SQGPU_RZZ || g.type == SQGPU_SWAP || g.type == SQGPU_CSWAP;
+    if (!qok(g.target)) return fail(SQGPU_ERR_INVALID, "gate type %d: target qubit %d out of range", g.type, g.target);
+    unsigned cm = 0;
+    const bool needs_ctrl = g.type == SQGPU_CNOT || g.type == SQGPU_CZ || g.type == SQGPU_CH || g.type == SQGPU_CU ||
+                            g.type == SQGPU_CRY || g.type == SQGPU_CRX || g.type == SQGPU_CRZ || g.type == SQGPU_CP ||
+                            g.type == SQGPU_CR || g.type == SQGPU_ADAPTIVE || g.type == SQGPU_CCX || g.type == SQGPU_CSWAP;
+    if (needs_ctrl) {
+        if (!qok(g.control) || g.control == g.target) return fail(SQGPU_ERR_INVALID, "gate type %d: bad control qubit %d", g.type, g.control);
+        cm |= 1u << g.control;
+        if (g.type == SQGPU_CCX) {
+            if (!qok(g.control2) || g.control2 == g.target || g.control2 == g.control) return fail(SQGPU_ERR_INVALID, "CCX: bad second control qubit %d", g.control2);
+            cm |= 1u << g.control2;
+        }
+    } else if (g.control >= 0) {
+        return fail(SQGPU_ERR_INVALID, "gate type %d takes no control qubit", g.type);
+    }
+    op.ctrl_mask = cm;
+    if (two_target) {
+        if (!qok(g.target2) || g.target2 == g.target || ((cm >> g.target2) & 1)) return fail(SQGPU_ERR_INVALID, "gate type %d: bad second target qubit %d", g.type, g.target2);
+        op.dim = 4;
+        op.nq = 2;
+        op.q[0] = std::min(g.target, g.target2);
+        op.q[1] = std::max(g.target, g.target2);
+    } else {
+        op.dim = 2;
+        op.target = g.target;
+    }
+    *out = op;
+    return SQGPU_OK;
+}
+
+// ---- launch planning for the fused executor ---------------------------------------------------------------------
+
+struct FusedPlan {
+    bool ok = false;
+    int log_ct = 0, threads = 32;
+    int tiles = 0, tiles_per_cta = 1, chunks = 1;
+    bool w_in_smem = false;
+    size_t smem = 0;
+};
+
+size_t fused_smem(int mode, int rows, int ct, int threads, bool has_dense, int wmax, int w_total, bool w_in_smem) {
+    size_t s = (size_t)rows * ct * sizeof(cplx) * (mode == MODE_GRAD ? 2 : 1);
+    if (has_dense) s += (size_t)DENSE_STAGE * sizeof(cplx);
+    const int nwarps = threads / 32;
+    if (mode == MODE_GRAD) {
+        s += (size_t)2 * nwarps * wmax * sizeof(cplx);
+        if (w_in_smem) s += (size_t)w_total * sizeof(cplx);
+    }
+    s += (size_t)nwarps * 6 * sizeof(double);
+    return s;
+}
+
+FusedPlan plan_fused(const sqgpu_ctx* c, int mode, int rows, int cols, int ysets) {
+    FusedPlan p;
+    const size_t budget = (size_t)c->smem_optin;
+    int max_log = 3;
+    while ((1 << max_log) > cols && max_log > 0) --max_log;  // no wider than the matrix (cols = 1: state vector)
+    for (int lc = max_log; lc >= 0; --lc) {
+        const int ct = 1 << lc;
+        int items = (rows / 2) * ct;
+        int threads = std::min(FUSED_THREADS, std::max(32, ((items + 1) / 2 + 31) / 32 * 32));
+        const bool grad = mode == MODE_GRAD;
+        bool wsm = grad && c->w_total > 0;
+        size_t s = fused_smem(mode, rows, ct, threads, c->has_dense, c->wmax, c->w_total, wsm);
+        if (s > budget && wsm) {
+            wsm = false;
+            s = fused_smem(mode, rows, ct, threads, c->has_dense, c->wmax, c->w_total, false);
+        }
+        if (s > budget) continue;
+        // prefer tiles that leave shared memory for the W accumulator: a narrower tile with W in smem beats a wider
+        // one without only when the wider one cannot hold W; keep the first (widest) fit.
+        p.ok = true;
+        p.log_ct = lc;
+        p.threads = threads;
+        p.smem = s;
+        p.w_in_smem = wsm;
+        p.tiles = (cols + ct - 1) / ct;
+        if (grad && !wsm) {
+            p.tiles_per_cta = 1;
+            p.chunks = p.tiles;
+        } else {
+            const int want_ctas = c->sm_count * 24;
+            int chunks = std::min(p.tiles, std::max(1, (want_ctas + ysets - 1) / ysets));
+            p.tiles_per_cta = (p.tiles + chunks - 1) / chunks;
+            p.chunks = (p.tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
+        }
+        if (mode == MODE_APPLY) {
+            p.tiles_per_cta = 1;
+            p.chunks = p.tiles;
+        }
+        return p;
+    }
+    return p;
+}
+
+template <int MODE>
+cudaError_t launch_fused_mode(const ExecArgs& a, const FusedPlan& p, int ysets, cudaStream_t st) {
+    dim3 grid(p.chunks, ysets);
+    cudaError_t e = cudaSuccess;
+#define SQ_LAUNCH(LC)                                                                                          \
+    case LC:                                                                                                   \
+        e = cudaFuncSetAttribute(fused_exec<MODE, LC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem); \
+        if (e != cudaSuccess) return e;                                                                        \
+        fused_exec<MODE, LC><<<grid, p.threads, p.smem, st>>>(a);                                              \
+        break;
+    switch (p.log_ct) {
+        SQ_LAUNCH(0)
+        SQ_LAUNCH(1)
+        SQ_LAUNCH(2)
+        SQ_LAUNCH(3)
+    }
+#undef SQ_LAUNCH
+    return cudaGetLastError();
+}
+
+// ---- building blocks (all enqueue on `st`, no host sync) --------------------------------------------------------
+
+int run_tables(sqgpu_ctx* c, const double* d_params, int batch, bool with_deriv, cudaStream_t st) {
+    int rc;
+    if ((rc = c->wKtab.ensure(std::max<size_t>(1, (size_t)batch * c->kern_total) * sizeof(cplx)))) return rc;
+    if ((rc = c->wDKtab.ensure(std::max<size_t>(1, (size_t)batch * c->dkern_total) * sizeof(cplx)))) return rc;
+    const long long total = (long long)batch * c->n_ops;
+    if (total == 0) return SQGPU_OK;
+    const int thr = 128;
+    build_kernel_tables<<<(unsigned)((total + thr - 1) / thr), thr, 0, st>>>(
+        c->dOps.as<DevOp>(), c->n_ops, d_params, c->n_params, batch, c->wKtab.as<cplx>(), c->kern_total,
+        c->wDKtab.as<cplx>(), c->dkern_total, with_deriv ? 1 : 0);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return SQGPU_OK;
+}
+
+void fill_common_args(const sqgpu_ctx* c, const FusedPlan& p, ExecArgs& a, int rows, int cols) {
+    memset(&a, 0, sizeof(a));
+    a.rows = rows;
+    a.cols = cols;
+    a.n = c->qbit_num;
+    a.ct = 1 << p.log_ct;
+    a.log_ct = p.log_ct;
+    a.tiles = p.tiles;
+    a.tiles_per_cta = p.tiles_per_cta;
+    a.ops = c->dOps.as<DevOp>();
+    a.n_ops = c->n_ops;
+    a.ktab = c->wKtab.as<cplx>();
+    a.kern_total = c->kern_total;
+    a.dktab = c->wDKtab.as<cplx>();
+    a.dkern_total = c->dkern_total;
+    a.pool = c->dPool.as<cplx>();
+    a.has_dense = c->has_dense ? 1 : 0;
+    a.wmax = c->wmax;
+    a.w_total = c->w_total;
+    a.w_in_smem = p.w_in_smem ? 1 : 0;
+}
+
+void time_begin(sqgpu_ctx* c, const char* name, cudaStream_t st) {
+    c->timer.ensure();
+    c->timer.name = name;
+    cudaEventRecord(c->timer.e0[c->timer.n % KernelTimer::RING], st);
+}
+void time_end(sqgpu_ctx* c, cudaStream_t st) {
+    cudaEventRecord(c->timer.e1[c->timer.n % KernelTimer::RING], st);
+    c->timer.n++;
+}
+
+// one executor pass over the resident matrix for `batch` parameter sets whose kernel tables are already built:
+// fills wTrPart (and wWPart), then reduces into d_traces[batch][1+P or 1][3][2].
+int run_exec_resident(sqgpu_ctx* c, int batch, bool grad, const cplx* d_omega, double* d_traces, cudaStream_t st) {
+    const int mode = grad ? MODE_GRAD : MODE_COST;
+    FusedPlan p = plan_fused(c, mode, c->rows, c->cols, batch);
+    if (!p.ok)
+        return fail(SQGPU_ERR_UNSUPPORTED, "%d-qubit %s does not fit the shared-memory executor (rows = %d); "
+                    "the streaming executor for this size is not implemented yet", c->qbit_num, grad ? "gradient" : "cost", c->rows);
+    int rc;
+    if ((rc = c->wTrPart.ensure((size_t)batch * p.chunks * 6 * sizeof(double)))) return rc;
+    if (grad && (rc = c->wWPart.ensure(std::max<size_t>(1, (size_t)batch * p.chunks * c->w_total) * sizeof(cplx)))) return rc;
+    ExecArgs a;
+    fill_common_args(c, p, a, c->rows, c->cols);
+    a.in = c->U.as<cplx>();
+    a.in_ystride = 0;
+    a.ld_in = c->cols;
+    a.trace_offset = effective_offset(c);
+    a.n_trace_types = n_trace_types_of(c->cfg.variant);
+    a.tr_part = c->wTrPart.as<double>();
+    a.w_part = c->wWPart.as<cplx>();
+    a.omega = d_omega;
+    time_begin(c, grad ? "fused_exec<GRAD>" : "fused_exec<COST>", st);
+    cudaError_t e = grad ? launch_fused_mode<MODE_GRAD>(a, p, batch, st) : launch_fused_mode<MODE_COST>(a, p, batch, st);
+    time_end(c, st);
+    c->launches++;
+    if (e != cudaSuccess) return fail(SQGPU_ERR_CUDA, "fused_exec launch failed: %s", cudaGetErrorString(e));
+    reduce_partials<<<batch, 128, 0, st>>>(c->wTrPart.as<double>(), p.chunks, c->wWPart.as<cplx>(), c->w_total,
+                                           c->dOps.as<DevOp>(), c->dParamOp.as<int>(), c->wDKtab.as<cplx>(),
+                                           c->dkern_total, c->n_params, grad ? 1 : 0, d_traces);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return SQGPU_OK;
+}
+
+int check_ready(const sqgpu_ctx* c, bool need_matrix) {
+    if (!c->circuit_set) return fail(SQGPU_ERR_STATE, "no circuit set (call sqgpu_set_circuit first)");
+    if (need_matrix) {
+        if (!c->U.p) return fail(SQGPU_ERR_STATE, "no matrix uploaded (call sqgpu_upload_matrix first)");
+        if (c->rows != (1 << c->qbit_num))
+            return fail(SQGPU_ERR_INVALID, "Wrong matrix size: the circuit has %d qubits, the matrix %d rows", c->qbit_num, c->rows);
+    }
+    return SQGPU_OK;
+}
+
+// max parameter sets per executor launch so that the W partials stay below ~1.5 GiB
+int batch_slice(const sqgpu_ctx* c, int batch, bool grad) {
+    if (!grad || c->w_total == 0) return std::min(batch, 65535);
+    FusedPlan p = plan_fused(c, MODE_GRAD, c->rows, c->cols, batch);
+    const size_t per = (size_t)std::max(1, p.chunks) * c->w_total * sizeof(cplx);
+    const size_t lim = (size_t)1536 << 20;
+    return (int)std::max<size_t>(1, std::min<size_t>((size_t)std::min(batch, 65535), lim / std::max<size_t>(per, 1)));
+}
+
+// traces for a batch (device pointers). Layout d_traces[batch][n_k][3][2], n_k = 1 + (with_grad ? P : 0).
+int traces_dev(sqgpu_ctx* c, const double* d_params, int batch, bool with_grad, double* d_traces, cudaStream_t st,
+               bool allow_two_pass) {
+    int rc = check_ready(c, true);
+    if (rc) return rc;
+    if (batch <= 0) return SQGPU_OK;
+    if (c->cols + effective_offset(c) > c->rows) return fail(SQGPU_ERR_INVALID, "trace_offset %d + cols %d exceeds rows %d", effective_offset(c), c->cols, c->rows);
+    if (with_grad && !c->all_unitary) return fail(SQGPU_ERR_UNSUPPORTED, "gradient with a non-unitary GENERAL gate is not supported (the adjoint sweep needs K^-1 = K^dagger)");
+    const bool hs_corr = c->cfg.variant == SQGPU_HILBERT_SCHMIDT_TEST_CORRECTION1 || c->cfg.variant == SQGPU_HILBERT_SCHMIDT_TEST_CORRECTION2;
+    if (with_grad && hs_corr && !allow_two_pass)
+        return fail(SQGPU_ERR_UNSUPPORTED, "raw gradient traces for the Hilbert-Schmidt correction variants need the globally summed traces first");
+    const int n_k = 1 + (with_grad ? c->n_params : 0);
+    const int slice = batch_slice(c, batch, with_grad);
+    for (int b0 = 0; b0 < batch; b0 += slice) {
+        const int nb = std::min(slice, batch - b0);
+        const double* dp = d_params + (size_t)b0 * c->n_params;
+        double* dt = d_traces + (size_t)b0 * n_k * 6;
+        if ((rc = run_tables(c, dp, nb, with_grad, st))) return rc;
+        if (!with_grad) {
+            if ((rc = run_exec_resident(c, nb, false, nullptr, dt, st))) return rc;
+            continue;
+        }
+        if ((rc = c->wOmega.ensure((size_t)nb * 3 * sizeof(cplx)))) return rc;
+        const double* tr_for_omega = nullptr;
+        int nk_for_omega = 1;
+        if (hs_corr) {  // pass 1: traces of the circuit itself, pass 2 uses omega_t = w_t conj(T_t)
+            if ((rc = c->wTraces0.ensure((size_t)nb * 6 * sizeof(double)))) return rc;
+            if ((rc = run_exec_resident(c, nb, false, nullptr, c->wTraces0.as<double>(), st))) return rc;
+            tr_for_omega = c->wTraces0.as<double>();
+        }
+        make_omega<<<(nb + 127) / 128, 128, 0, st>>>(tr_for_omega, nk_for_omega, c->cfg, nb, c->wOmega.as<cplx>());
+        c->launches++;
+        CUDA_TRY(cudaGetLastError());
+        if ((rc = run_exec_resident(c, nb, true, c->wOmega.as<cplx>(), dt, st))) return rc;
+    }
+    return SQGPU_OK;
+}
+
+int cost_from_traces_dev(sqgpu_ctx* c, const double* d_traces, int batch, bool with_grad, int cols_total, double* d_cost,
+                         double* d_grad, cudaStream_t st) {
+    if (batch <= 0) return SQGPU_OK;
+    if (!variant_supported(c->cfg.variant)) return fail(SQGPU_ERR_UNSUPPORTED, "cost function variant %d is not supported on the device path", c->cfg.variant);
+    for (int b0 = 0; b0 < batch; b0 += 65535) {
+        const int nb = std::min(65535, batch - b0);
+        const int n_k = 1 + (with_grad ? c->n_params : 0);
+        cost_from_traces<<<nb, 128, 0, st>>>(d_traces + (size_t)b0 * n_k * 6, c->n_params, with_grad ? 1 : 0, cols_total, c->cfg,
+                                             d_cost ? d_cost + b0 : nullptr, d_grad ? d_grad + (size_t)b0 * c->n_params : nullptr);
+        c->launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return SQGPU_OK;
+}
+
+int eval_dev(sqgpu_ctx* c, const double* d_params, int batch, bool with_grad, double* d_cost, double* d_grad, cudaStream_t st) {
+    if (!variant_supported(c->cfg.variant)) return fail(SQGPU_ERR_UNSUPPORTED, "cost function variant %d is not supported on the device path", c->cfg.variant);
+    int rc = check_ready(c, true);
+    if (rc) return rc;
+    const int n_k = 1 + (with_grad ? c->n_params : 0);
+    if ((rc = c->wTraces.ensure(std::max<size_t>(1, (size_t)batch * n_k * 6) * sizeof(double)))) return rc;
+    if ((rc = traces_dev(c, d_params, batch, with_grad, c->wTraces.as<double>(), st, true))) return rc;
+    return cost_from_traces_dev(c, c->wTraces.as<double>(), batch, with_grad, c->cols, d_cost, d_grad, st);
+}
+
+// ---- apply paths -------------------------------------------------------------------------------------------------
+
+StreamGate make_stream_gate(const DevOp& op, cplx* data, long long ystride, int rows, int cols, int ld, const cplx* K, long long k_ystride) {
+    StreamGate g;
+    memset(&g, 0, sizeof(g));
+    g.data = data;
+    g.ystride = ystride;
+    g.rows = rows;
+    g.cols = cols;
+    g.ld = ld;
+    g.log_cols = -1;
+    for (int l = 0; l < 31; ++l)
+        if ((1 << l) == cols) g.log_cols = l;
+    g.target = op.target;
+    g.ctrl_mask = op.ctrl_mask;
+    unsigned m = op.ctrl_mask;
+    if (op.dim == 2) m |= 1u << op.target;
+    g.nfix = 0;
+    for (int b = 0; b < 31; ++b)
+        if ((m >> b) & 1) g.fix[g.nfix++] = b;
+    g.K = K;
+    g.k_ystride = k_ystride;
+    g.nq = op.nq;
+    for (int j = 0; j < 5; ++j) g.q[j] = op.q[j];
+    return g;
+}
+
+// one gate on a device matrix with the streaming kernels
+int launch_stream_gate(sqgpu_ctx* c, const DevOp& op, bool deriv, cplx* data, long long ystride, int ysets, int rows, int cols,
+                       int ld, const cplx* K, long long k_ystride, cudaStream_t st) {
+    StreamGate g = make_stream_gate(op, data, ystride, rows, cols, ld, K, k_ystride);
+    if (op.dim == 2) {
+        const long long items = (long long)(rows >> (deriv ? 1 : g.nfix)) * cols;
+        const int thr = 256;
+        const unsigned blocks = (unsigned)std::min<long long>((items + thr - 1) / thr, (long long)c->sm_count * 64);
+        dim3 grid(std::max(1u, blocks), ysets);
+        if (deriv) gate1q_stream<true><<<grid, thr, 0, st>>>(g);
+        else gate1q_stream<false><<<grid, thr, 0, st>>>(g);
+    } else {
+        const long long items = (long long)(rows >> op.nq) * cols;
+        const int thr = 128;
+        const unsigned blocks = (unsigned)std::min<long long>((items + thr - 1) / thr, (long long)c->sm_count * 32);
+        dim3 grid(std::max(1u, blocks), ysets);
+#define SQ_KQ(KQ)                                                            \
+    case KQ:                                                                 \
+        if (deriv) gatekq_stream<KQ, true><<<grid, thr, 0, st>>>(g);         \
+        else gatekq_stream<KQ, false><<<grid, thr, 0, st>>>(g);              \
+        break;
+        switch (op.nq) {
+            SQ_KQ(2)
+            SQ_KQ(3)
+            SQ_KQ(4)
+            SQ_KQ(5)
+            default: return fail(SQGPU_ERR_INVALID, "dense gate on %d qubits", op.nq);
+        }
+#undef SQ_KQ
+    }
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return SQGPU_OK;
+}
+
+// apply the whole program (kernel-table set 0) to `ysets` device matrices; deriv_op[y] (host) >= 0 selects the op whose
+// derivative kernel (parameter deriv_p[y]) replaces the forward one in matrix y.
+int apply_program_dev(sqgpu_ctx* c, const cplx* d_in, long long in_ystride, cplx* d_out, long long out_ystride, int ysets,
+                      int rows, int cols, const std::vector<int>* deriv_op, const std::vector<int>* deriv_p, cudaStream_t st) {
+    int rc;
+    FusedPlan p = plan_fused(c, MODE_APPLY, rows, cols, ysets);
+    if (p.ok) {
+        const int* d_dop = nullptr;
+        const int* d_dp = nullptr;
+        if (deriv_op) {
+            if ((rc = c->wDerivIdx.ensure((size_t)2 * ysets * sizeof(int)))) return rc;
+            CUDA_TRY(cudaMemcpyAsync(c->wDerivIdx.p, deriv_op->data(), ysets * sizeof(int), cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(c->wDerivIdx.as<int>() + ysets, deriv_p->data(), ysets * sizeof(int), cudaMemcpyHostToDevice, st));
+            d_dop = c->wDerivIdx.as<int>();
+            d_dp = c->wDerivIdx.as<int>() + ysets;
+        }
+        ExecArgs a;
+        fill_common_args(c, p, a, rows, cols);
+        a.in = d_in;
+        a.out = d_out;
+        a.in_ystride = in_ystride;
+        a.out_ystride = out_ystride;
+        a.ld_in = cols;
+        a.ld_out = cols;
+        a.k_shared = 1;
+        a.deriv_op = d_dop;
+        a.deriv_pidx = d_dp;
+        for (int y0 = 0; y0 < ysets; y0 += 65535) {
+            const int ny = std::min(65535, ysets - y0);
+            ExecArgs b = a;
+            b.in = d_in + (size_t)y0 * in_ystride;
+            b.out = d_out + (size_t)y0 * out_ystride;
+            if (d_dop) {
+                b.deriv_op = d_dop + y0;
+                b.deriv_pidx = d_dp + y0;
+            }
+            time_begin(c, "fused_exec<APPLY>", st);
+            cudaError_t e = launch_fused_mode<MODE_APPLY>(b, p, ny, st);
+            time_end(c, st);
+            c->launches++;
+            if (e != cudaSuccess) return fail(SQGPU_ERR_CUDA, "fused_exec<APPLY> launch failed: %s", cudaGetErrorString(e));
+        }
+        return SQGPU_OK;
+    }
+    // streaming route: matrices too tall for shared memory. out[y] <- in[y] first, then gate by gate in place.
+    const long long n_elem = (long long)rows * cols;
+    for (int y = 0; y < ysets; ++y) {
+        const cplx* src = d_in + (size_t)y * in_ystride;
+        cplx* dst = d_out + (size_t)y * out_ystride;
+        if (src != dst) CUDA_TRY(cudaMemcpyAsync(dst, src, n_elem * sizeof(cplx), cudaMemcpyDeviceToDevice, st));
+    }
+    for (int k = 0; k < c->n_ops; ++k) {
+        const DevOp& op = c->ops[k];
+        const cplx* Kf = op.kern_off >= 0 ? c->wKtab.as<cplx>() + op.kern_off : c->dPool.as<cplx>() + op.pool_off;
+        if (!deriv_op) {
+            if ((rc = launch_stream_gate(c, op, false, d_out, out_ystride, ysets, rows, cols, cols, Kf, 0, st))) return rc;
+            continue;
+        }
+        // matrices whose derivative op is k use the derivative kernel; batch the rest in contiguous runs
+        int y = 0;
+        while (y < ysets) {
+            const bool d = (*deriv_op)[y] == k;
+            int y1 = y + 1;
+            if (!d)
+                while (y1 < ysets && (*deriv_op)[y1] != k) ++y1;
+            const cplx* K = d ? c->wDKtab.as<cplx>() + op.dkern_off + (size_t)(*deriv_p)[y] * op.dim * op.dim : Kf;
+            if ((rc = launch_stream_gate(c, op, d, d_out + (size_t)y * out_ystride, out_ystride, y1 - y, rows, cols, cols, K, 0, st))) return rc;
+            y = y1;
+        }
+    }
+    return SQGPU_OK;
+}
+
+int set_cost_checked(sqgpu_ctx* c, int variant, int trace_offset, double prev, double c1, double c2) {
+    if (!variant_supported(variant)) return fail(SQGPU_ERR_UNSUPPORTED, "cost function variant %d is not supported on the device path", variant);
+    if (trace_offset < 0) return fail(SQGPU_ERR_INVALID, "negative trace offset");
+    if (prev < 0) return fail(SQGPU_ERR_INVALID, "negative previous cost function value");
+    c->cfg.variant = variant;
+    c->cfg.prev = prev;
+    c->cfg.c1 = c1;
+    c->cfg.c2 = c2;
+    c->trace_offset = trace_offset;
+    return SQGPU_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================================
+// extern "C" entry points
+// =====================================================================================================================
+
+extern "C" {
+
+const char* sqgpu_last_error(void) { return g_last_error.c_str(); }
+
+int sqgpu_abi_version(void) { return SQGPU_ABI_VERSION; }
+
+int sqgpu_device_count(int* count) {
+    if (!count) return fail(SQGPU_ERR_INVALID, "count is NULL");
+    *count = 0;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(SQGPU_ERR_NO_DEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    int ok = 0;
+    for (int d = 0; d < n; ++d) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major >= 10) ++ok;
+    }
+    *count = ok;
+    return SQGPU_OK;
+}
+
+int sqgpu_create(int device, sqgpu_handle_t* out) {
+    if (!out) return fail(SQGPU_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(SQGPU_ERR_NO_DEVICE, "no CUDA device available (%s); the sqgpu engine has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    if (device < 0 || device >= n) return fail(SQGPU_ERR_NO_DEVICE, "device %d out of range (%d visible)", device, n);
+    int major = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+    if (major < 10) return fail(SQGPU_ERR_NO_DEVICE, "device %d has compute capability %d.x; this library is built for sm_100a only", device, major);
+    DeviceGuard guard(device);
+    sqgpu_ctx* c = new sqgpu_ctx();
+    c->device = device;
+    cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete c;
+        return fail(SQGPU_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+    }
+    *out = c;
+    return SQGPU_OK;
+}
+
+int sqgpu_destroy(sqgpu_handle_t c) {
+    if (!c) return SQGPU_OK;
+    {
+        DeviceGuard guard(c->device);
+        std::lock_guard<std::mutex> lk(c->mtx);
+        cudaStreamSynchronize(c->stream);
+        DevBuf* bufs[] = {&c->U, &c->dOps, &c->dParamOp, &c->dPool, &c->wParams, &c->wKtab, &c->wDKtab, &c->wTrPart, &c->wWPart,
+                          &c->wTraces, &c->wOmega, &c->wCost, &c->wGrad, &c->wMat, &c->wDerivIdx, &c->wTraces0,
+                          &c->hIndptr, &c->hIndices, &c->hValues};
+        for (DevBuf* b : bufs) b->release();
+        c->timer.destroy();
+        cudaStreamDestroy(c->stream);
+    }
+    delete c;
+    return SQGPU_OK;
+}
+
+int sqgpu_upload_matrix(sqgpu_handle_t c, const double* data, int rows, int cols, int stride) {
+    if (!c) return fail(SQGPU_ERR_INVALID, "NULL handle");
+    if (!data || rows <= 0 || cols <= 0 || stride < cols) return fail(SQGPU_ERR_INVALID, "bad matrix arguments");
+    if (rows & (rows - 1)) return fail(SQGPU_ERR_INVALID, "rows must be a power of two, got %d", rows);
+    if (cols > rows) return fail(SQGPU_ERR_INVALID, "cols (%d) cannot exceed rows (%d)", cols, rows);
+    DeviceGuard guard(c->device);
+    std::lock_guard<std::mutex> lk(c->mtx);
+    int rc = c->U.ensure((size_t)rows * cols * sizeof(cplx));
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpy2DAsync(c->U.p, (size_t)cols * sizeof(cplx), data, (size_t)stride * sizeof(cplx), (size_t)cols * sizeof(cplx),
+                               rows, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->rows = rows;
+    c->cols = cols;
+    return SQGPU_OK;
+}
+
+int sqgpu_set_circuit(sqgpu_handle_t c, const sqgpu_gate_desc* gates, int n_gates, int n_params, int qbit_num,
+                      const double* matrix_pool, int64_t pool_len) {
+    if (!c) return fail(SQGPU_ERR_INVALID, "NULL handle");
+    if (n_gates < 0 || n_params < 0 || qbit_num < 1 || qbit_num > 30) return fail(SQGPU_ERR_INVALID, "bad circuit arguments");
+    if (n_gates > 0 && !gates) return fail(SQGPU_ERR_INVALID, "gates is NULL");
+    std::vector<DevOp> ops(n_gates);
+    std::vector<int> param_op(std::max(n_params, 1), -1);
+    int kern_total = 0, dkern_total = 0, w_total = 0, wmax = 4;
+    bool has_dense = false, all_unitary = true;
+    for (int i = 0; i < n_gates; ++i) {
+        bool unitary = true;
+        int rc = lower_gate(gates[i], qbit_num, matrix_pool, pool_len, &ops[i], &unitary);
+        if (rc) return rc;
+        all_unitary = all_unitary && unitary;
+        DevOp& op = ops[i];
+        const int d2 = op.dim * op.dim;
+        if (op.type != SQGPU_GENERAL) {
+            op.kern_off = kern_total;
+            kern_total += d2;
+        }
+        if (op.dim > 2) has_dense = true;
+        if (op.n_params > 0) {
+            if (op.param_start < 0 || op.param_start + op.n_params > n_params)
+                return fail(SQGPU_ERR_INVALID, "gate %d: parameters [%d, %d) outside the parameter vector of length %d", i,
+                            op.param_start, op.param_start + op.n_params, n_params);
+            op.dkern_off = dkern_total;
+            dkern_total += d2 * op.n_params;
+            op.w_off = w_total;
+            w_total += d2;
+            wmax = std::max(wmax, d2);
+            for (int p = 0; p < op.n_params; ++p) {
+                if (param_op[op.param_start + p] != -1) return fail(SQGPU_ERR_INVALID, "parameter %d is used by two gates", op.param_start + p);
+                param_op[op.param_start + p] = i;
+            }
+        }
+    }
+    for (int p = 0; p < n_params; ++p)
+        if (param_op[p] < 0) return fail(SQGPU_ERR_INVALID, "parameter %d is not used by any gate", p);
+
+    DeviceGuard guard(c->device);
+    std::lock_guard<std::mutex> lk(c->mtx);
+    int rc;
+    if ((rc = c->dOps.ensure(std::max<size_t>(1, ops.size()) * sizeof(DevOp)))) return rc;
+    if ((rc = c->dParamOp.ensure(param_op.size() * sizeof(int)))) return rc;
+    if ((rc = c->dPool.ensure(std::max<size_t>(1, (size_t)pool_len) * sizeof(cplx)))) return rc;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (!ops.empty()) CUDA_TRY(cudaMemcpy(c->dOps.p, ops.data(), ops.size() * sizeof(DevOp), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(c->dParamOp.p, param_op.data(), param_op.size() * sizeof(int), cudaMemcpyHostToDevice));
+    if (pool_len > 0) CUDA_TRY(cudaMemcpy(c->dPool.p, matrix_pool, (size_t)pool_len * sizeof(cplx), cudaMemcpyHostToDevice));
+    c->ops.swap(ops);
+    c->param_op.swap(param_op);
+    c->n_ops = n_gates;
+    c->n_params = n_params;
+    c->qbit_num = qbit_num;
+    c->kern_total = kern_total;
+    c->dkern_total = dkern_total;
+    c->w_total = w_total;
+    c->wmax = wmax;
+    c->has_dense = has_dense;
+    c->all_unitary = all_unitary;
+    c->circuit_set = true;
+    return SQGPU_OK;
+}
+
+int sqgpu_set_cost(sqgpu_handle_t c, int variant, int trace_offset, double prev_cost_fnv_val, double correction1_scale,
+                   double correction2_scale) {
+    if (!c) return fail(SQGPU_ERR_INVALID, "NULL handle");
+    std::lock_guard<std::mutex> lk(c->mtx);
+    return set_cost_checked(c, variant, trace_offset, prev_cost_fnv_val, correction1_scale, correction2_scale);
+}
+
+// ---- device-resident entry points ----------------------------------------------------------------------------------
+
+int sqgpu_cost_batched_dev(sqgpu_handle_t c, const double* d_params, int batch, double* d_cost, void* stream) {
+    if (!c) return fail(SQGPU_ERR_INVALID, "NULL handle");
+    if (batch < 0 || (batch > 0 && (!d_params && c->n_params > 0)) || (batch > 0 && !d_cost)) return fail(SQGPU_ERR_INVALID, "bad arguments");
+    DeviceGuard guard(c->device);
+    std::lock_guard<std::mutex> lk(c->mtx);
+    return eval_dev(c, d_params, batch, false, d_cost, nullptr, (cudaStream_t)stream);
+}
+
+int sqgpu_cost_grad_batched_dev(sqgpu_handle_t c, const double* d_params, int batch, double* d_cost, double* d_grad, void* stream) {
+    if (!c) return fail(SQGPU_ERR_INVALID, "NULL handle");
+    if (batch < 0 || (batch > 0 && (!d_params && c->n_params > 0)) || (batch > 0 && (!d_cost || (!d_grad && c->n_params > 0)))) return fail(SQGPU_ERR_INVALID, "bad arguments");
+    DeviceGuard guard(c->device);
+    std::lock_guard<std::mutex> lk(c->mtx);
+    return eval_dev(c, d_params, batch, true, d_cost, d_grad, (cudaStream_t)stream);
+}
+
+int sqgpu_traces_batched_dev(sqgpu_handle_t c, const double* d_params, int batch, int with_grad, double* d_traces, void* stream) {
+    if (!c) return fail(SQGPU_ERR_INVALID, "NULL handle");
+    if (batch < 0 || (batch > 0 && !d_traces)) return fail(SQGPU_ERR_INVALID, "bad arguments");
+    DeviceGuard guard(c->device);
+    std::lock_guard<std::mutex> lk(c->mtx);
+    return traces_dev(c, d_params, batch, with_grad != 0, d_traces, (cudaStream_t)stream, false);
+}
+
+int sqgpu_cost_from_traces_dev(sqgpu_handle_t c, const double* d_traces, int batch, int with_grad, int cols_total,
+                               double* d_cost, double* d_grad, void* stream) {
+    if (!c) return fail(SQGPU_ERR_INVALID, "NULL handle");
+    if (batch < 0 || cols_total <= 0 || (batch > 0 && (!d_traces || !d_cost))) return fail(SQGPU_ERR_INVALID, "bad arguments");
+    DeviceGuard guard(c->device);
+    std::lock_guard<std::mutex> lk(c->mtx);
+    if (!c->circuit_set) return fail(SQGPU_ERR_STATE, "no circuit set");
+    return cost_from_traces_dev(c, d_traces, batch, with_grad != 0, cols_total, d_cost, d_grad, (cudaStream_t)stream);
+}
+
+// ---- host-buffer entry points (what the reference's hooks call) ------------------------------------------------------
+
+static int host_eval(sqgpu_handle_t c, const double* params, int batch, bool with_grad, double* cost, double* grad) {
+    if (!c) return fail(SQGPU_ERR_INVALID, "NULL handle");
+    if (batch < 0) return fail(SQGPU_ERR_INVALID, "negative batch");
+    if (batch == 0) return SQGPU_OK;
+    if ((!params && c->n_params > 0) || !cost || (with_grad && !grad && c->n_params > 0)) return fail(SQGPU_ERR_INVALID, "NULL buffer");
+    DeviceGuard guard(c->device);
+    std::lock_guard<std::mutex> lk(c->mtx);
+    int rc = check_ready(c, true);
+    if (rc) return rc;
+    const size_t np = (size_t)batch * c->n_params;
+    if ((rc = c->wParams.ensure(std::max<size_t>(1, np) * sizeof(double)))) return rc;
+    if ((rc = c->wCost.ensure((size_t)batch * sizeof(double)))) return rc;
+    if (with_grad && (rc = c->wGrad.ensure(std::max<size_t>(1, np) * sizeof(double)))) return rc;
+    if (np) CUDA_TRY(cudaMemcpyAsync(c->wParams.p, params, np * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if ((rc = eval_dev(c, c->wParams.as<double>(), batch, with_grad, c->wCost.as<double>(), with_grad ? c->wGrad.as<double>() : nullptr, c->stream))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(cost, c->wCost.p, (size_t)batch * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (with_grad && np) CUDA_TRY(cudaMemcpyAsync(grad, c->wGrad.p, np * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return SQGPU_OK;
+}
+
+int sqgpu_cost_batched(sqgpu_handle_t c, const double* params, int batch, double* cost) {
+    return host_eval(c, params, batch, false, cost, nullptr);
+}
+
+int sqgpu_cost_grad_batched(sqgpu_handle_t c, const double* params, int batch, double* cost, double* grad) {
+    return host_eval(c, params, batch, true, cost, grad);
+}
+
+int sqgpu_traces_batched(sqgpu_handle_t c, const double* params, int batch, int with_grad, double* traces) {
+    if (!c) return fail(SQGPU_ERR_INVALID, "NULL handle");
+    if (batch < 0) return fail(SQGPU_ERR_INVALID, "negative batch");
+    if (batch == 0) return SQGPU_OK;
+    if ((!params && c->n_params > 0) || !traces) return fail(SQGPU_ERR_INVALID, "NULL buffer");
+    DeviceGuard guard(c->device);
+    std::lock_guard<std::mutex> lk(c->mtx);
+    int rc = check_ready(c, true);
+    if (rc) return rc;
+    const size_t np = (size_t)batch * c->n_params;
+    const int n_k = 1 + (with_grad ? c->n_params : 0);
+    if ((rc = c->wParams.ensure(std::max<size_t>(1, np) * sizeof(double)))) return rc;
+    if ((rc = c->wTraces.ensure((size_t)batch * n_k * 6 * sizeof(double)))) return rc;
+    if (np) CUDA_TRY(cudaMemcpyAsync(c->wParams.p, params, np * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if ((rc = traces_dev(c, c->wParams.as<double>(), batch, with_grad != 0, c->wTraces.as<double>(), c->stream, false))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(traces, c->wTraces.p, (size_t)batch * n_k * 6 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return SQGPU_OK;
+}
+
+int sqgpu_cost_from_traces(sqgpu_handle_t c, const double* traces, int batch, int with_grad, int cols_total, double* cost, double* grad) {
+    if (!c) return fail(SQGPU_ERR_INVALID, "NULL handle");
+    if (batch < 0 || cols_total <= 0) return fail(SQGPU_ERR_INVALID, "bad arguments");
+    if (batch == 0) return SQGPU_OK;
+    if (!traces || !cost || (with_grad && !grad && c->n_params > 0)) return fail(SQGPU_ERR_INVALID, "NULL buffer");
+    DeviceGuard guard(c->device);
+    std::lock_guard<std::mutex> lk(c->mtx);
+    if (!c->circuit_set) return fail(SQGPU_ERR_STATE, "no circuit set");
+    int rc;
+    const size_t np = (size_t)batch * c->n_params;
+    const int n_k = 1 + (with_grad ? c->n_params : 0);
+    if ((rc = c->wTraces.ensure((size_t)batch * n_k * 6 * sizeof(double)))) return rc;
+    if ((rc = c->wCost.ensure((size_t)batch * sizeof(double)))) return rc;
+    if (with_grad && (rc = c->wGrad.ensure(std::max<size_t>(1, np) * sizeof(double)))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(c->wTraces.p, traces, (size_t)batch * n_k * 6 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if ((rc = cost_from_traces_dev(c, c->wTraces.as<double>(), batch, with_grad != 0, cols_total, c->wCost.as<double>(),
+                                   with_grad ? c->wGrad.as<double>() : nullptr, c->stream))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(cost, c->wCost.p, (size_t)batch * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (with_grad && np) CUDA_TRY(cudaMemcpyAsync(grad, c->wGrad.p, np * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return SQGPU_OK;
+}
+
+int sqgpu_apply(sqgpu_handle_t c, const double* params, double* inout, int rows, int cols, int stride) {
+    if (!c) return fail(SQGPU_ERR_INVALID, "NULL handle");
+    if (!inout || rows <= 0 || cols <= 0 || stride < cols) return fail(SQGPU_ERR_INVALID, "bad matrix arguments");
+    DeviceGuard guard(c->device);
+    std::lock_guard<std::mutex> lk(c->mtx);
+    int rc = check_ready(c, false);
+    if (rc) return rc;
+    if (rows != (1 << c->qbit_num)) return fail(SQGPU_ERR_INVALID, "Wrong input size in Gates_block gate apply: %d rows for %d qubits", rows, c->qbit_num);
+    if (!params && c->n_params > 0) return fail(SQGPU_ERR_INVALID, "params is NULL");
+    const size_t bytes = (size_t)rows * cols * sizeof(cplx);
+    if ((rc = c->wMat.ensure(bytes))) return rc;
+    if ((rc = c->wParams.ensure(std::max<size_t>(1, c->n_params) * sizeof(double)))) return rc;
+    if (c->n_params) CUDA_TRY(cudaMemcpyAsync(c->wParams.p, params, c->n_params * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpy2DAsync(c->wMat.p, (size_t)cols * sizeof(cplx), inout, (size_t)stride * sizeof(cplx), (size_t)cols * sizeof(cplx), rows, cudaMemcpyHostToDevice, c->stream));
+    if ((rc = run_tables(c, c->wParams.as<double>(), 1, false, c->stream))) return rc;
+    if ((rc = apply_program_dev(c, c->wMat.as<cplx>(), 0, c->wMat.as<cplx>(), 0, 1, rows, cols, nullptr, nullptr, c->stream))) return rc;
+    CUDA_TRY(cudaMemcpy2DAsync(inout, (size_t)stride * sizeof(cplx), c->wMat.p, (size_t)cols * sizeof(cplx), (size_t)cols * sizeof(cplx), rows, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return SQGPU_OK;
+}
+
+int sqgpu_apply_derivative(sqgpu_handle_t c, const double* params, const double* in, int rows, int cols, int stride, double* out) {
+    if (!c) return fail(SQGPU_ERR_INVALID, "NULL handle");
+    if (!in || rows <= 0 || cols <= 0 || stride < cols) return fail(SQGPU_ERR_INVALID, "bad matrix arguments");
+    DeviceGuard guard(c->device);
+    std::lock_guard<std::mutex> lk(c->mtx);
+    int rc = check_ready(c, false);
+    if (rc) return rc;
+    if (rows != (1 << c->qbit_num)) return fail(SQGPU_ERR_INVALID, "Wrong input size in Gates_block gate apply: %d rows for %d qubits", rows, c->qbit_num);
+    const int P = c->n_params;
+    if (P == 0) return SQGPU_OK;
+    if (!params || !out) return fail(SQGPU_ERR_INVALID, "NULL buffer");
+    const size_t n_elem = (size_t)rows * cols;
+    // derivative matrices are produced in slices of at most ~1 GiB
+    const int slice = (int)std::max<size_t>(1, std::min<size_t>((size_t)P, ((size_t)1 << 30) / (n_elem * sizeof(cplx))));
+    if ((rc = c->wMat.ensure((size_t)(slice + 1) * n_elem * sizeof(cplx)))) return rc;
+    if ((rc = c->wParams.ensure((size_t)P * sizeof(double)))) return rc;
+    cplx* d_in = c->wMat.as<cplx>();
+    cplx* d_out = d_in + n_elem;
+    CUDA_TRY(cudaMemcpyAsync(c->wParams.p, params, P * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpy2DAsync(d_in, (size_t)cols * sizeof(cplx), in, (size_t)stride * sizeof(cplx), (size_t)cols * sizeof(cplx), rows, cudaMemcpyHostToDevice, c->stream));
+    if ((rc = run_tables(c, c->wParams.as<double>(), 1, true, c->stream))) return rc;
+    for (int p0 = 0; p0 < P; p0 += slice) {
+        const int np = std::min(slice, P - p0);
+        std::vector<int> dop(np), dp(np);
+        for (int i = 0; i < np; ++i) {
+            dop[i] = c->param_op[p0 + i];
+            dp[i] = p0 + i - c->ops[dop[i]].param_start;
+        }
+        if ((rc = apply_program_dev(c, d_in, 0, d_out, (long long)n_elem, np, rows, cols, &dop, &dp, c->stream))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(out + 2 * (size_t)p0 * n_elem, d_out, (size_t)np * n_elem * sizeof(cplx), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+    }
+    return SQGPU_OK;
+}
+
+// shared by the host and device single-gate entry points: d_inout is a device matrix
+static int apply_gate_on_device(sqgpu_ctx* c, const sqgpu_gate_desc* gate, const double* gate_params, const double* matrix_pool,
+                                int deriv_param, cplx* d_inout, int rows, int cols, int ld, cudaStream_t st) {
+    int n = 0;
+    while ((1 << n) < rows) ++n;
+    if ((1 << n) != rows) return fail(SQGPU_ERR_INVALID, "rows must be a power of two");
+    sqgpu_gate_desc g = *gate;
+    g.param_start = 0;
+    int64_t pool_len = 0;
+    if (g.type == SQGPU_GENERAL) {
+        if (g.n_qubits < 1 || g.n_qubits > 5) return fail(SQGPU_ERR_INVALID, "GENERAL gate: 1..5 qubits supported");
+        pool_len = g.matrix_off + ((int64_t)1 << (2 * g.n_qubits));
+    }
+    DevOp op;
+    bool unitary;
+    int rc = lower_gate(g, n, matrix_pool, pool_len, &op, &unitary);
+    if (rc) return rc;
+    if (deriv_param >= op.n_params) return fail(SQGPU_ERR_INVALID, "derivative parameter %d out of range", deriv_param);
+    if (deriv_param >= 0 && op.n_params == 0) return fail(SQGPU_ERR_INVALID, "gate has no parameters");
+    if (op.n_params > 0 && !gate_params) return fail(SQGPU_ERR_INVALID, "gate_params is NULL");
+    const int d2 = op.dim * op.dim;
+    // scratch: [op][params(4)][ktab <= 1024][dktab 4 * 16] in one small device buffer (16-byte aligned sections)
+    const size_t off_par = 128, off_k = 256, off_dk = off_k + 1024 * sizeof(cplx);
+    static_assert(sizeof(DevOp) <= 128, "DevOp does not fit its scratch slot");
+    if ((rc = c->wDerivIdx.ensure(off_dk + 4 * 16 * sizeof(cplx)))) return rc;
+    char* base = c->wDerivIdx.as<char>();
+    const cplx* K;
+    if (op.type == SQGPU_GENERAL) {
+        CUDA_TRY(cudaMemcpyAsync(base + off_k, matrix_pool + 2 * g.matrix_off, d2 * sizeof(cplx), cudaMemcpyHostToDevice, st));
+        K = reinterpret_cast<cplx*>(base + off_k);
+    } else {
+        op.kern_off = 0;
+        op.dkern_off = 0;
+        double pbuf[4] = {0, 0, 0, 0};
+        for (int i = 0; i < op.n_params; ++i) pbuf[i] = gate_params[i];
+        CUDA_TRY(cudaMemcpyAsync(base, &op, sizeof(DevOp), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(base + off_par, pbuf, sizeof(pbuf), cudaMemcpyHostToDevice, st));
+        build_kernel_tables<<<1, 32, 0, st>>>(reinterpret_cast<DevOp*>(base), 1, reinterpret_cast<double*>(base + off_par), 4, 1,
+                                              reinterpret_cast<cplx*>(base + off_k), d2, reinterpret_cast<cplx*>(base + off_dk), 4 * d2, 1);
+        c->launches++;
+        CUDA_TRY(cudaGetLastError());
+        K = deriv_param >= 0 ? reinterpret_cast<cplx*>(base + off_dk) + (size_t)deriv_param * d2 : reinterpret_cast<cplx*>(base + off_k);
+    }
+    time_begin(c, op.dim == 2 ? "gate1q_stream" : "gatekq_stream", st);
+    rc = launch_stream_gate(c, op, deriv_param >= 0, d_inout, 0, 1, rows, cols, ld, K, 0, st);
+    time_end(c, st);
+    return rc;
+}
+
+int sqgpu_apply_gate(sqgpu_handle_t c, const sqgpu_gate_desc* gate, const double* gate_params, const double* matrix_pool,
+                     int deriv_param, double* inout, int rows, int cols, int stride) {
+    if (!c) return fail(SQGPU_ERR_INVALID, "NULL handle");
+    if (!gate || !inout || rows <= 0 || cols <= 0 || stride < cols) return fail(SQGPU_ERR_INVALID, "bad arguments");
+    DeviceGuard guard(c->device);
+    std::lock_guard<std::mutex> lk(c->mtx);
+    int rc;
+    if ((rc = c->wMat.ensure((size_t)rows * cols * sizeof(cplx)))) return rc;
+    CUDA_TRY(cudaMemcpy2DAsync(c->wMat.p, (size_t)cols * sizeof(cplx), inout, (size_t)stride * sizeof(cplx), (size_t)cols * sizeof(cplx), rows, cudaMemcpyHostToDevice, c->stream));
+    if ((rc = apply_gate_on_device(c, gate, gate_params, matrix_pool, deriv_param, c->wMat.as<cplx>(), rows, cols, cols, c->stream))) return rc;
+    CUDA_TRY(cudaMemcpy2DAsync(inout, (size_t)stride * sizeof(cplx), c->wMat.p, (size_t)cols * sizeof(cplx), (size_t)cols * sizeof(cplx), rows, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return SQGPU_OK;
+}
+
+int sqgpu_apply_gate_dev(sqgpu_handle_t c, const sqgpu_gate_desc* gate, const double* gate_params, const double* matrix_pool,
+                         int deriv_param, double* d_inout, int rows, int cols, int stride, void* stream) {
+    if (!c) return fail(SQGPU_ERR_INVALID, "NULL handle");
+    if (!gate || !d_inout || rows <= 0 || cols <= 0 || stride < cols) return fail(SQGPU_ERR_INVALID, "bad arguments");
+    DeviceGuard guard(c->device);
+    std::lock_guard<std::mutex> lk(c->mtx);
+    return apply_gate_on_device(c, gate, gate_params, matrix_pool, deriv_param, reinterpret_cast<cplx*>(d_inout), rows, cols, stride, (cudaStream_t)stream);
+}
+
+// ---- VQE ------------------------------------------------------------------------------------------------------------
+
+int sqgpu_set_hamiltonian_csr(sqgpu_handle_t c, int n_rows, int64_t nnz, const int32_t* indptr, const int32_t* indices, const double* values) {
+    if (!c) return fail(SQGPU_ERR_INVALID, "NULL handle");
+    if (n_rows <= 0 || nnz < 0 || !indptr || (nnz > 0 && (!indices || !values))) return fail(SQGPU_ERR_INVALID, "bad CSR arguments");
+    if (indptr[0] != 0 || indptr[n_rows] != nnz) return fail(SQGPU_ERR_INVALID, "inconsistent CSR indptr");
+    DeviceGuard guard(c->device);
+    std::lock_guard<std::mutex> lk(c->mtx);
+    int rc;
+    if ((rc = c->hIndptr.ensure((size_t)(n_rows + 1) * sizeof(int32_t)))) return rc;
+    if ((rc = c->hIndices.ensure(std::max<size_t>(1, (size_t)nnz) * sizeof(int32_t)))) return rc;
+    if ((rc = c->hValues.ensure(std::max<size_t>(1, (size_t)nnz) * sizeof(cplx)))) return rc;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaMemcpy(c->hIndptr.p, indptr, (size_t)(n_rows + 1) * sizeof(int32_t), cudaMemcpyHostToDevice));
+    if (nnz) {
+        CUDA_TRY(cudaMemcpy(c->hIndices.p, indices, (size_t)nnz * sizeof(int32_t), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(c->hValues.p, values, (size_t)nnz * sizeof(cplx), cudaMemcpyHostToDevice));
+    }
+    c->h_rows = n_rows;
+    c->h_nnz = nnz;
+    return SQGPU_OK;
+}
+
+static int vqe_dev(sqgpu_ctx* c, const double* d_params, int batch, bool with_grad, double* d_energy, double* d_grad, cudaStream_t st);
+
+int sqgpu_vqe_energy_batched_dev(sqgpu_handle_t c, const double* d_params, int batch, double* d_energy, void* stream) {
+    if (!c) return fail(SQGPU_ERR_INVALID, "NULL handle");
+    DeviceGuard guard(c->device);
+    std::lock_guard<std::mutex> lk(c->mtx);
+    return vqe_dev(c, d_params, batch, false, d_energy, nullptr, (cudaStream_t)stream);
+}
+
+static int vqe_host(sqgpu_handle_t c, const double* params, int batch, bool with_grad, double* energy, double* grad) {
+    if (!c) return fail(SQGPU_ERR_INVALID, "NULL handle");
+    if (batch < 0) return fail(SQGPU_ERR_INVALID, "negative batch");
+    if (batch == 0) return SQGPU_OK;
+    if ((!params && c->n_params > 0) || !energy || (with_grad && !grad && c->n_params > 0)) return fail(SQGPU_ERR_INVALID, "NULL buffer");
+    DeviceGuard guard(c->device);
+    std::lock_guard<std::mutex> lk(c->mtx);
+    int rc;
+    const size_t np = (size_t)batch * c->n_params;
+    if ((rc = c->wParams.ensure(std::max<size_t>(1, np) * sizeof(double)))) return rc;
+    if ((rc = c->wCost.ensure((size_t)batch * sizeof(double)))) return rc;
+    if (with_grad && (rc = c->wGrad.ensure(std::max<size_t>(1, np) * sizeof(double)))) return rc;
+    if (np) CUDA_TRY(cudaMemcpyAsync(c->wParams.p, params, np * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if ((rc = vqe_dev(c, c->wParams.as<double>(), batch, with_grad, c->wCost.as<double>(), with_grad ? c->wGrad.as<double>() : nullptr, c->stream))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(energy, c->wCost.p, (size_t)batch * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (with_grad && np) CUDA_TRY(cudaMemcpyAsync(grad, c->wGrad.p, np * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return SQGPU_OK;
+}
+
+int sqgpu_vqe_energy_batched(sqgpu_handle_t c, const double* params, int batch, double* energy) {
+    return vqe_host(c, params, batch, false, energy, nullptr);
+}
+
+int sqgpu_vqe_energy_grad_batched(sqgpu_handle_t c, const double* params, int batch, double* energy, double* grad) {
+    return vqe_host(c, params, batch, true, energy, grad);
+}
+
+// ---- introspection ---------------------------------------------------------------------------------------------------
+
+int sqgpu_launch_count(sqgpu_handle_t c, int64_t* count) {
+    if (!c || !count) return fail(SQGPU_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(c->mtx);
+    *count = c->launches;
+    return SQGPU_OK;
+}
+
+int sqgpu_last_kernel_time(sqgpu_handle_t c, char* name, int name_len, double* ms, int* launches) {
+    if (!c || !ms || !launches) return fail(SQGPU_ERR_INVALID, "NULL argument");
+    DeviceGuard guard(c->device);
+    std::lock_guard<std::mutex> lk(c->mtx);
+    *ms = 0;
+    *launches = 0;
+    if (name && name_len > 0) {
+        strncpy(name, c->timer.name.c_str(), name_len - 1);
+        name[name_len - 1] = 0;
+    }
+    if (!c->timer.init || c->timer.n == 0) return SQGPU_OK;
+    const int cnt = std::min(c->timer.n, (int)KernelTimer::RING);
+    double tot = 0;
+    for (int i = 0; i < cnt; ++i) {
+        const int slot = (c->timer.n - 1 - i) % KernelTimer::RING;
+        CUDA_TRY(cudaEventSynchronize(c->timer.e1[slot]));
+        float t = 0;
+        CUDA_TRY(cudaEventElapsedTime(&t, c->timer.e0[slot], c->timer.e1[slot]));
+        tot += t;
+    }
+    *ms = tot / cnt;
+    *launches = cnt;
+    c->timer.n = 0;
+    return SQGPU_OK;
+}
+
+}  // extern "C"
+
+// VQE device path (defined after the C block so it can use the static helpers above)
+#include "vqe_impl.cuh"

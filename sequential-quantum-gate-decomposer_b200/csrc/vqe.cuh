@@ -1,0 +1,130 @@
+// vqe.cuh -- kernels of the state-vector (VQE) cost path and the streaming adjoint step.
+//
+//   csr_matvec_batched  <- mult(Matrix_sparse, Matrix&)                     (common/common.cpp:403-436)
+//   expectation_batched <- Expectation_value_of_energy_real                 (variational_quantum_eigensolver/
+//                                                                            Variational_Quantum_Eigensolver_Base.cpp:584-624)
+//   adjoint1q_stream    :  one backward step of the adjoint gradient on matrices / state vectors in HBM. The reference
+//                          materialises P derivative states (…Base.cpp:1131-1199 -> Gates_block::apply_derivate_to);
+//                          here grad_p = 2 Re <d_p psi | H psi> = 2 Re sum_{r,c} dK_p[r][c] W[r][c] with
+//                          W[r][c] = sum_pairs beta[r] a[c], beta_N = conj(H psi_N), beta_{k-1} = K^T beta_k,
+//                          a_k = K^dagger a_{k+1}  -- the same recurrences as the unitary path (exec_fused.cuh).
+#pragma once
+#include "exec_stream.cuh"
+#include "sq_types.cuh"
+
+namespace sq {
+
+// y[b][r] = sum_e values[e] * x[b][indices[e]]; one warp per row, lanes over the row's non-zeros
+__global__ void csr_matvec_batched(int n_rows, const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                                   const cplx* __restrict__ values, const cplx* __restrict__ x, cplx* __restrict__ yv,
+                                   int conj_out) {
+    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= n_rows) return;
+    const cplx* __restrict__ xb = x + (size_t)blockIdx.y * n_rows;
+    cplx acc = czero();
+    for (int e = indptr[row] + lane; e < indptr[row + 1]; e += 32) acc = cfma(values[e], xb[indices[e]], acc);
+    for (int s = 16; s > 0; s >>= 1) {
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, s);
+        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, s);
+    }
+    if (lane == 0) yv[(size_t)blockIdx.y * n_rows + row] = conj_out ? cmake(acc.x, -acc.y) : acc;
+}
+
+// part[b][blockIdx.x] = sum_i Re(conj(left_i) * right_i)  (right may be stored conjugated: sign_im = -1)
+__global__ void expectation_partial(int n_rows, const cplx* __restrict__ left, const cplx* __restrict__ right,
+                                    double sign_im, double* __restrict__ part) {
+    __shared__ double sred[32];
+    const cplx* __restrict__ l = left + (size_t)blockIdx.y * n_rows;
+    const cplx* __restrict__ r = right + (size_t)blockIdx.y * n_rows;
+    double e = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_rows; i += (long long)gridDim.x * blockDim.x)
+        e += l[i].x * r[i].x + sign_im * l[i].y * r[i].y;
+    for (int s = 16; s > 0; s >>= 1) e += __shfl_xor_sync(0xffffffffu, e, s);
+    if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = e;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += sred[w];
+        part[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = s;
+    }
+}
+
+__global__ void sum_partials(const double* __restrict__ part, int nparts, int width, double scale, double* __restrict__ out,
+                             int out_stride) {
+    // out[y*out_stride + w] = scale * sum_p part[(y*nparts + p)*width + w]
+    const int y = blockIdx.x, w = threadIdx.x;
+    if (w >= width) return;
+    double s = 0;
+    for (int p = 0; p < nparts; ++p) s += part[((size_t)y * nparts + p) * width + w];
+    out[(size_t)y * out_stride + w] = scale * s;
+}
+
+// backward step for a 1-qubit (optionally controlled) gate: a <- K^dagger a, W += beta a^T, beta <- K^T beta.
+// wpart[y][blockIdx.x][8] receives this block's W contribution.
+__global__ void __launch_bounds__(256) adjoint1q_stream(const StreamGate G, cplx* __restrict__ beta, long long beta_ystride,
+                                                        double* __restrict__ wpart, int want_w) {
+    __shared__ double sred[8 * 8];
+    const cplx* __restrict__ K = G.K + (size_t)blockIdx.y * G.k_ystride;
+    const cplx k00 = K[0], k01 = K[1], k10 = K[2], k11 = K[3];
+    cplx* __restrict__ d = G.data + (size_t)blockIdx.y * G.ystride;
+    cplx* __restrict__ bt = beta + (size_t)blockIdx.y * beta_ystride;
+    const long long nitems = (long long)(G.rows >> G.nfix) * G.cols;
+    const int tbit = 1 << G.target;
+    cplx w00 = czero(), w01 = czero(), w10 = czero(), w11 = czero();
+    for (long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x; item < nitems;
+         item += (long long)gridDim.x * blockDim.x) {
+        int g, j;
+        if (G.log_cols >= 0) {
+            g = (int)(item >> G.log_cols);
+            j = (int)(item & (G.cols - 1));
+        } else {
+            g = (int)(item / G.cols);
+            j = (int)(item - (long long)g * G.cols);
+        }
+        int i0 = g;
+        for (int f = 0; f < G.nfix; ++f) i0 = insert_zero(i0, G.fix[f]);
+        i0 |= G.ctrl_mask;
+        const size_t o0 = (size_t)i0 * G.ld + j, o1 = (size_t)(i0 | tbit) * G.ld + j;
+        const cplx p0 = d[o0], p1 = d[o1], b0 = bt[o0], b1 = bt[o1];
+        const cplx a0 = cfmac(k10, p1, cfmac(k00, p0, czero()));
+        const cplx a1 = cfmac(k11, p1, cfmac(k01, p0, czero()));
+        d[o0] = a0;
+        d[o1] = a1;
+        if (want_w) {
+            w00 = cfma(b0, a0, w00);
+            w01 = cfma(b0, a1, w01);
+            w10 = cfma(b1, a0, w10);
+            w11 = cfma(b1, a1, w11);
+        }
+        bt[o0] = cfma(k10, b1, cmul(k00, b0));
+        bt[o1] = cfma(k11, b1, cmul(k01, b0));
+    }
+    if (!want_w) return;
+    double v[8] = {w00.x, w00.y, w01.x, w01.y, w10.x, w10.y, w11.x, w11.y};
+    for (int i = 0; i < 8; ++i)
+        for (int s = 16; s > 0; s >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], s);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0)
+        for (int i = 0; i < 8; ++i) sred[warp * 8 + i] = v[i];
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        double s = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += sred[w * 8 + threadIdx.x];
+        wpart[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 + threadIdx.x] = s;
+    }
+}
+
+// grad[y][p] = scale * Re( sum_e dK_p[e] * W[y][op][e] ) over the parameters of one op
+__global__ void grad_from_w(const cplx* __restrict__ wsum /*[y][4]*/, const cplx* __restrict__ dktab, int dkern_total,
+                            int dkern_off, int n_params_op, int param_start, int n_params, double scale,
+                            double* __restrict__ grad) {
+    const int y = blockIdx.x, p = threadIdx.x;
+    if (p >= n_params_op) return;
+    const cplx* dk = dktab + (size_t)y * dkern_total + dkern_off + p * 4;
+    cplx acc = czero();
+    for (int e = 0; e < 4; ++e) acc = cfma(dk[e], wsum[(size_t)y * 4 + e], acc);
+    grad[(size_t)y * n_params + param_start + p] = scale * acc.x;
+}
+
+}  // namespace sq

@@ -1,0 +1,73 @@
+// vqe_impl.cuh -- host orchestration of the state-vector (VQE) path; included at the end of sqgpu.cu.
+// Variational_Quantum_Eigensolver_Base::optimization_problem (…Base.cpp:1088-1121) and
+// optimization_problem_combined_non_static (:1131-1199), batched over parameter sets.
+#pragma once
+
+static int vqe_dev(sqgpu_ctx* c, const double* d_params, int batch, bool with_grad, double* d_energy, double* d_grad, cudaStream_t st) {
+    int rc = check_ready(c, true);
+    if (rc) return rc;
+    if (batch < 0) return fail(SQGPU_ERR_INVALID, "negative batch");
+    if (batch == 0) return SQGPU_OK;
+    if (c->cols != 1) return fail(SQGPU_ERR_INVALID, "the VQE path needs a state vector (cols = 1), the resident matrix has %d columns", c->cols);
+    if (!c->hIndptr.p || c->h_rows != c->rows) return fail(SQGPU_ERR_STATE, "no Hamiltonian of matching size set (call sqgpu_set_hamiltonian_csr)");
+    if (!d_energy || (with_grad && !d_grad && c->n_params > 0)) return fail(SQGPU_ERR_INVALID, "NULL buffer");
+    for (int k = 0; k < c->n_ops; ++k)
+        if (with_grad && c->ops[k].dim != 2) return fail(SQGPU_ERR_UNSUPPORTED, "VQE gradient with multi-qubit dense gates is not implemented");
+    if (with_grad && !c->all_unitary) return fail(SQGPU_ERR_UNSUPPORTED, "gradient with a non-unitary GENERAL gate is not supported");
+    const int rows = c->rows;
+    // parameter sets per slice: two state buffers of <= 1 GiB each
+    const int slice = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::min(batch, 65535), ((size_t)1 << 30) / ((size_t)rows * sizeof(cplx))));
+    const int nblk = std::min(c->sm_count * 8, std::max(1, rows / 512));
+    if ((rc = c->wMat.ensure((size_t)2 * slice * rows * sizeof(cplx)))) return rc;
+    if ((rc = c->wTrPart.ensure((size_t)slice * nblk * 8 * sizeof(double)))) return rc;
+    if ((rc = c->wOmega.ensure((size_t)slice * 4 * sizeof(cplx)))) return rc;
+    cplx* psi = c->wMat.as<cplx>();
+    cplx* lam = psi + (size_t)slice * rows;
+    for (int b0 = 0; b0 < batch; b0 += slice) {
+        const int nb = std::min(slice, batch - b0);
+        const double* dp = d_params + (size_t)b0 * c->n_params;
+        if ((rc = run_tables(c, dp, nb, with_grad, st))) return rc;
+        {
+            dim3 grid(std::min(c->sm_count * 8, std::max(1, rows / 256)), nb);
+            replicate_matrix<<<grid, 256, 0, st>>>(c->U.as<cplx>(), psi, rows);
+            c->launches++;
+        }
+        time_begin(c, "gate1q_stream", st);
+        for (int k = 0; k < c->n_ops; ++k) {
+            const DevOp& op = c->ops[k];
+            const cplx* K = op.kern_off >= 0 ? c->wKtab.as<cplx>() + op.kern_off : c->dPool.as<cplx>() + op.pool_off;
+            const long long kst = op.kern_off >= 0 ? c->kern_total : 0;
+            if ((rc = launch_stream_gate(c, op, false, psi, rows, nb, rows, 1, 1, K, kst, st))) return rc;
+        }
+        time_end(c, st);
+        {   // beta_N = conj(H psi_N); energy = Re <psi|H psi>
+            dim3 grid((unsigned)(((long long)rows * 32 + 255) / 256), nb);
+            csr_matvec_batched<<<grid, 256, 0, st>>>(rows, c->hIndptr.as<int32_t>(), c->hIndices.as<int32_t>(), c->hValues.as<cplx>(), psi, lam, 1);
+            dim3 g2(nblk, nb);
+            expectation_partial<<<g2, 256, 0, st>>>(rows, psi, lam, -1.0, c->wTrPart.as<double>());
+            sum_partials<<<nb, 32, 0, st>>>(c->wTrPart.as<double>(), nblk, 1, 1.0, d_energy + b0, 1);
+            c->launches += 3;
+            CUDA_TRY(cudaGetLastError());
+        }
+        if (!with_grad) continue;
+        for (int k = c->n_ops - 1; k >= 0; --k) {
+            const DevOp& op = c->ops[k];
+            const cplx* K = op.kern_off >= 0 ? c->wKtab.as<cplx>() + op.kern_off : c->dPool.as<cplx>() + op.pool_off;
+            const long long kst = op.kern_off >= 0 ? c->kern_total : 0;
+            StreamGate g = make_stream_gate(op, psi, rows, rows, 1, 1, K, kst);
+            const long long items = (long long)(rows >> g.nfix);
+            const int blocks = (int)std::max<long long>(1, std::min<long long>((items + 255) / 256, nblk));
+            dim3 grid(blocks, nb);
+            adjoint1q_stream<<<grid, 256, 0, st>>>(g, lam, rows, c->wTrPart.as<double>(), op.n_params > 0 ? 1 : 0);
+            c->launches++;
+            if (op.n_params > 0) {
+                sum_partials<<<nb, 32, 0, st>>>(c->wTrPart.as<double>(), blocks, 8, 1.0, reinterpret_cast<double*>(c->wOmega.p), 8);
+                grad_from_w<<<nb, 32, 0, st>>>(c->wOmega.as<cplx>(), c->wDKtab.as<cplx>(), c->dkern_total, op.dkern_off, op.n_params,
+                                               op.param_start, c->n_params, 2.0, d_grad + (size_t)b0 * c->n_params);
+                c->launches += 2;
+            }
+        }
+        CUDA_TRY(cudaGetLastError());
+    }
+    return SQGPU_OK;
+}

@@ -1,0 +1,93 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library loads, exports every symbol include/sqgpu.h declares,
+the ctypes struct matches the C struct, and -- on a box without a GPU -- fails loudly instead of falling back."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import helpers as H
+
+abi = H.abi
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "sqgpu.h")
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(sqgpu_[a-z0-9_]+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(abi.LIB_PATH):
+        import __graft_entry__ as g
+
+        g.build()
+    return abi.load_library()
+
+
+def test_header_symbols_are_exported_and_bound(lib):
+    syms = declared_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), "libsqgpu.so does not export %s" % s
+        assert s in abi.PROTOTYPES, "abi.PROTOTYPES has no prototype for %s" % s
+    assert sorted(abi.PROTOTYPES) == syms
+    assert lib.sqgpu_abi_version() == 1
+
+
+def test_descriptor_struct_layout_matches_c(tmp_path):
+    src = tmp_path / "sz.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <stddef.h>\n#include "%s"\nint main(){printf("%%zu %%zu %%zu %%zu\\n", sizeof(sqgpu_gate_desc),'
+        " offsetof(sqgpu_gate_desc, n_qubits), offsetof(sqgpu_gate_desc, qubits), offsetof(sqgpu_gate_desc, matrix_off));return 0;}\n"
+        % HEADER
+    )
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-o", str(exe), str(src)])
+    size, o_nq, o_q, o_m = map(int, subprocess.check_output([str(exe)]).split())
+    assert size == C.sizeof(abi.GateDesc) == abi.GATE_DESC_DTYPE.itemsize
+    assert o_nq == abi.GateDesc.n_qubits.offset == abi.GATE_DESC_DTYPE.fields["n_qubits"][1]
+    assert o_q == abi.GateDesc.qubits.offset == abi.GATE_DESC_DTYPE.fields["qubits"][1]
+    assert o_m == abi.GateDesc.matrix_off.offset == abi.GATE_DESC_DTYPE.fields["matrix_off"][1]
+
+
+def test_gate_and_cost_enums_match_header():
+    src = open(HEADER).read()
+    for name, val in re.findall(r"SQGPU_([A-Z0-9_]+)\s*=\s*(-?\d+)", src):
+        if hasattr(abi, name):
+            assert getattr(abi, name) == int(val), name
+        elif hasattr(abi, "ERR_" + name[4:]) and name.startswith("ERR_"):
+            assert getattr(abi, name) == int(val), name
+
+
+def test_no_device_fails_loudly(lib):
+    """no CPU fallback: without a GPU the engine refuses to create a context (and says why)"""
+    n = C.c_int(-1)
+    rc = lib.sqgpu_device_count(C.byref(n))
+    if rc == abi.OK and n.value > 0:
+        pytest.skip("a GPU is visible; covered by the -m gpu tests")
+    h = abi._handle()
+    rc = lib.sqgpu_create(0, C.byref(h))
+    assert rc == abi.ERR_NO_DEVICE
+    assert b"no CPU fallback" in lib.sqgpu_last_error() or b"device" in lib.sqgpu_last_error()
+    with pytest.raises(abi.SqgpuError):
+        H.sq.Engine(0)
+
+
+def test_circuit_descriptors_and_parameter_layout():
+    """Gates_block::add_gate parameter layout (Gates_block.cpp:2500-2525): consecutive slices in insertion order"""
+    c = H.adaptive_circuit(4, 5)
+    assert c.get_Parameter_Num() == 7 * 6 * 5 + 3 * 4  # 222, SURVEY.md §8
+    d, pool = c.descriptors()
+    assert len(d) == 3 * 6 * 5 + 4  # 94 gates
+    assert (np.cumsum(d["n_params"]) - d["n_params"] == d["param_start"]).all()
+    dn, _ = c.descriptors(nested=True)
+    assert (dn["type"] == abi.BLOCK_BEGIN).sum() == 6 * 5 + 1
+    assert [x for x in dn["type"] if x < 1000] == list(d["type"])
+    c10 = H.adaptive_circuit(10, 4)
+    assert (len(c10.descriptors()[0]), c10.get_Parameter_Num()) == (550, 1290)
