@@ -151,6 +151,21 @@ struct DeviceGuard {
     }
 };
 
+// 16 independent DFMA chains per thread: measures the FP64 pipe, nothing else
+__global__ void fp64_fma_burn(double* out, int iters, double m) {
+    double a[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = threadIdx.x * 1e-3 + i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a[i] = fma(a[i], m, 1e-9);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += a[i];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 int n_trace_types_of(int variant) {
     switch (variant) {
         case SQGPU_FROBENIUS_NORM_CORRECTION1:
@@ -1157,6 +1172,34 @@ int sqgpu_last_kernel_time(sqgpu_handle_t c, char* name, int name_len, double* m
     *ms = tot / cnt;
     *launches = cnt;
     c->timer.n = 0;
+    return SQGPU_OK;
+}
+
+int sqgpu_fp64_fma_peak(sqgpu_handle_t c, double* tflops) {
+    if (!c || !tflops) return fail(SQGPU_ERR_INVALID, "NULL argument");
+    DeviceGuard guard(c->device);
+    std::lock_guard<std::mutex> lk(c->mtx);
+    int rc;
+    const int blocks = c->sm_count * 8, thr = 256, iters = 4096;
+    if ((rc = c->wCost.ensure((size_t)blocks * thr * sizeof(double)))) return rc;
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    double best = 0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CUDA_TRY(cudaEventRecord(e0, c->stream));
+        fp64_fma_burn<<<blocks, thr, 0, c->stream>>>(c->wCost.as<double>(), iters, 1.0000001);
+        CUDA_TRY(cudaEventRecord(e1, c->stream));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        c->launches++;
+        const double flops = 2.0 * 16 * (double)iters * blocks * thr;
+        if (rep > 0) best = std::max(best, flops / (ms * 1e-3) * 1e-12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tflops = best;
     return SQGPU_OK;
 }
 

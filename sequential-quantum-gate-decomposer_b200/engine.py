@@ -197,3 +197,8 @@ class Engine:
         n = C.c_int(0)
         abi.check(self.lib, self.lib.sqgpu_last_kernel_time(self._h, buf, 128, C.byref(ms), C.byref(n)))
         return buf.value.decode(), ms.value, n.value
+
+    def fp64_fma_peak(self):
+        t = C.c_double(0)
+        abi.check(self.lib, self.lib.sqgpu_fp64_fma_peak(self._h, C.byref(t)))
+        return t.value
