@@ -1,5 +1,5 @@
 // exec_fused.cuh -- the fused circuit executor: one CTA keeps a tile of CT columns of the 2^n x C matrix in shared
-// memory, runs the WHOLE gate program on it, and emits only trace partials (cost), trace + W partials (adjoint
+// memory, runs the WHOLE device program on it, and emits only trace partials (cost), trace + W partials (adjoint
 // gradient) or the transformed tile (apply / materialised derivative).
 //
 // It replaces, for one column tile, the reference's per-gate passes over the full matrix:
@@ -8,11 +8,16 @@
 //   apply_nqbit_kernel_to_matrix_input_impl         (gates/kernels/apply_large_kernel_to_input.cpp:123-213)
 //   get_cost_function / get_trace* diagonals        (decomposition/N_Qubit_Decomposition_Cost_Function.cpp:73-664)
 // and, for the gradient, the P materialised derivative matrices of Gates_block::apply_derivate_to
-// (gates/Gates_block.cpp:1011-1150) by an adjoint sweep: with a_k the column after k gates and beta_k the row functional
-// e_r^T G_{N-1}...G_{k+1}, the derivative of the trace term wrt a parameter of gate k is sum_pairs beta_k^T dK a_k.
-// The executor accumulates W_k[r][c] = sum_{active pairs, columns} beta_k[r] a_k[c]; the finalize kernel contracts W_k
-// with the reference's derivative kernels dK. Inactive (control = 0) pairs contribute nothing, which is exactly the
-// reference's "zero rows in the derivative" convention (apply_kernel_to_input.cpp:93-97).
+// (gates/Gates_block.cpp:1011-1150) by an adjoint sweep: with a_k the column after k ops and beta_k the row functional
+// e_r^T G_{N-1}...G_{k+1}, the derivative of the trace term wrt a parameter of op k is sum_groups beta_k^T dK a_k.
+// The executor accumulates W_k[r][c] = sum_{groups, columns} beta_k[r] a_k[c]; reduce_partials contracts W_k with the
+// derivative kernels dK (for fused blocks: the product-rule derivative of the block matrix, gate_kernels.cuh).
+// Inactive (control = 0) pairs contribute nothing, which is exactly the reference's "zero rows in the derivative"
+// convention (apply_kernel_to_input.cpp:93-97).
+//
+// The hot ops are the planner's fused blocks: dense 4x4 (two qubits) or 2x2 (one qubit) complex kernels without
+// controls. Each thread keeps the kernel (and, in the backward sweep, the 16 W accumulators) in registers and owns
+// whole amplitude groups, so a block costs one shared-memory round trip and one barrier instead of one per gate.
 //
 // Data layout in shared memory: element (row i, tile column c) at [phys(i) * CT + c], 16 B each, so a quarter-warp
 // (8 lanes, one 128 B shared-memory wavefront) reads whole rows; phys() XOR-swizzles the low row bits so that rows that
@@ -43,7 +48,7 @@ struct ExecArgs {
     const cplx* pool;
     int k_shared;            // 1: every blockIdx.y uses kernel-table set 0 (materialised derivative: one parameter set)
     const int* deriv_op;     // MODE_APPLY: per blockIdx.y the op whose derivative kernel is applied (NULL: none)
-    const int* deriv_pidx;   //             and which of its parameters
+    const int* deriv_slot;   //             and which of its derivative kernels
     int trace_offset;
     int n_trace_types;       // 1: main diagonal only, 2: + one-bit-flip sums, 3: + two-bit-flip sums
     double* tr_part;         // [y][chunks][6]
@@ -51,46 +56,27 @@ struct ExecArgs {
     int w_total;
     int w_in_smem;           // accumulate W over the CTA's tiles in shared memory (else tiles_per_cta must be 1)
     const cplx* omega;       // [y][3] weights of the three trace types in the functional whose gradient is taken
-    int has_dense;           // program contains dim > 2 ops (reserves the 16 KB kernel staging buffer)
+    int has_dense;           // program contains raw dim > 2 ops (reserves the 16 KB kernel staging buffer)
     int wmax;                // max dim*dim over parametric ops (complex), >= 4
 };
 
-static const int FUSED_THREADS = 512;
+static const int FUSED_THREADS = 256;
 static const int DENSE_STAGE = 1024;  // complex elements (32 x 32)
 
 // ---- shared-memory swizzle -------------------------------------------------------------------------------------
-// rows per 128 B wavefront: 8 / ct. The low log2(8/ct) bits of the physical row select the 16 B bank group set.
+// rows per 128 B wavefront: 8 / ct. The low log2(8/ct) bits of the physical row select the 16 B bank group set; they
+// are XORed with images of the higher row bits so that rows differing in any of the lowest free bits do not collide.
 template <int LOG_CT>
 __device__ __forceinline__ int phys_row(int i) {
     if (LOG_CT >= 3) return i;
     if (LOG_CT == 2) return i ^ (__popc(i >> 1) & 1);
     if (LOG_CT == 1) {
-        // images of row bit b >= 2: {3,1,2} for b % 3 == {2,0,1}; bits 0,1 map to themselves
-        const unsigned lo = __popc(i & 0x36DB6DB4) & 1;  // bits b>=2 with b%3 in {2,0}
-        const unsigned hi = __popc(i & 0x6DB6DB64 & ~0x3) & 1;  // placeholder, fixed below
-        (void)hi;
-        const unsigned m_lo = 0x6DB6DB6Cu;  // bits {2,3,5,6,8,9,...}: b%3 in {2,0}, b>=2
-        const unsigned m_hi = 0x36DB6DB4u;  // bits {2,4,5,7,8,10,...}: b%3 in {2,1}, b>=2
-        (void)lo;
+        // image of row bit b: (1, 2, 3)[b % 3]; bits 0 and 1 map to themselves
+        const unsigned m_lo = 0x6DB6DB6Cu;  // bits b >= 2 with b % 3 in {2, 0}
+        const unsigned m_hi = 0x36DB6DB4u;  // bits b >= 2 with b % 3 in {2, 1}
         return i ^ ((__popc((unsigned)i & m_lo) & 1) | ((__popc((unsigned)i & m_hi) & 1) << 1));
     }
     return i ^ (((i >> 3) & 1) * 7);
-}
-
-__device__ __forceinline__ int phys_row_rt(int i, int log_ct) {
-    switch (log_ct) {
-        case 0: return phys_row<0>(i);
-        case 1: return phys_row<1>(i);
-        case 2: return phys_row<2>(i);
-        default: return i;
-    }
-}
-
-// expand a compact group index into a row index with zeros at the (ascending) fixed positions
-__device__ __forceinline__ int expand_fixed(int g, const DevOp& op, int nfix, const int* fix) {
-    int idx = g;
-    for (int f = 0; f < nfix; ++f) idx = insert_zero(idx, fix[f]);
-    return idx;
 }
 
 // reduce 8 per-lane doubles over the warp; lanes with (lane & 3) == 0 end up holding the total of value
@@ -121,32 +107,31 @@ __device__ __forceinline__ void warp_reduce8(double* v, int lane) {
     v[0] += __shfl_xor_sync(full, v[0], 1);
 }
 
-struct OpLocal {  // per-op values every thread needs, loaded once per op
-    int dim, target, nfix, nq;
-    unsigned ctrl_mask;
-    int fix[6];
-    int q[5];
-};
-
-__device__ __forceinline__ void load_op(const DevOp& op, OpLocal& o) {
-    o.dim = op.dim;
-    o.target = op.target;
-    o.ctrl_mask = op.ctrl_mask;
-    o.nq = op.nq;
-    // fixed positions = target(s) and control bits, ascending
-    unsigned m = op.ctrl_mask;
-    if (op.dim == 2) m |= 1u << op.target;
-    else
-        for (int j = 0; j < op.nq; ++j) m |= 1u << op.q[j];
-    o.nfix = 0;
-    while (m) {
-        const int p = __ffs(m) - 1;
-        o.fix[o.nfix++] = p;
-        m &= m - 1;
-    }
+// per-warp W partial (complex w[n]) -> swarp slot; n = 4 or 16
+template <int N>
+__device__ __forceinline__ void warp_store_w(const cplx* w, double* slot, int lane) {
 #pragma unroll
-    for (int j = 0; j < 5; ++j) o.q[j] = op.q[j];
+    for (int part = 0; part < N / 4; ++part) {
+        double v[8];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            v[2 * e] = w[part * 4 + e].x;
+            v[2 * e + 1] = w[part * 4 + e].y;
+        }
+        warp_reduce8(v, lane);
+        if ((lane & 3) == 0) slot[part * 8 + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)] = v[0];
+    }
 }
+
+// compact per-op record staged in shared memory (uniform reads, no global latency on the critical path)
+struct SOp {
+    int32_t dim;       // 2 / 4 for fast ops
+    int32_t q0, q1;    // fast ops: qubit(s) (q0 < q1); raw ops: unused
+    int32_t kern_off;  // kernel-table offset, -1: pool
+    int32_t w_off;
+    int32_t raw;       // 1: generic path (controls / dense >= 8 / derivative op)
+    int32_t pool_lo, pool_hi;
+};
 
 template <int MODE, int LOG_CT>
 __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A) {
@@ -161,20 +146,46 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
 
     cplx* sa = reinterpret_cast<cplx*>(smem_raw);
     cplx* sb = sa + (size_t)rows * CT;                                   // MODE_GRAD only
-    cplx* sk = (MODE == MODE_GRAD) ? sb + (size_t)rows * CT : sb;         // dense kernel staging
-    cplx* swarp = sk + (A.has_dense ? DENSE_STAGE : 0);                   // [2][nwarps][wmax]
+    cplx* sk = (MODE == MODE_GRAD) ? sb + (size_t)rows * CT : sb;         // raw dense kernel staging
+    cplx* skm = sk + (A.has_dense ? DENSE_STAGE : 0);                     // [2][16] prefetched fast-op kernels
+    cplx* swarp = skm + 32;                                               // [2][nwarps][wmax]
     cplx* swacc = swarp + ((MODE == MODE_GRAD) ? 2 * nwarps * A.wmax : 0);  // [w_total] if w_in_smem
     double* sred = reinterpret_cast<double*>(swacc + ((MODE == MODE_GRAD && A.w_in_smem) ? A.w_total : 0));  // [nwarps][6]
+    SOp* sops = reinterpret_cast<SOp*>(sred + nwarps * 6);               // [n_ops]
 
     const int chunk = blockIdx.x;
     const int nchunks = gridDim.x;
     const int deriv_op = (MODE == MODE_APPLY && A.deriv_op) ? A.deriv_op[y] : -1;
-    const int deriv_p = (MODE == MODE_APPLY && A.deriv_pidx) ? A.deriv_pidx[y] : 0;
+    const int deriv_slot = (MODE == MODE_APPLY && A.deriv_slot) ? A.deriv_slot[y] : 0;
 
+    // ---- stage the op table ------------------------------------------------------------------------------------------
+    for (int k = tid; k < A.n_ops; k += nthr) {
+        const DevOp op = A.ops[k];
+        SOp s;
+        s.dim = op.dim;
+        s.kern_off = op.kern_off;
+        s.w_off = op.w_off;
+        s.pool_lo = (int32_t)(op.pool_off & 0xffffffffLL);
+        s.pool_hi = (int32_t)(op.pool_off >> 32);
+        const bool fast = op.ctrl_mask == 0 && (op.dim == 2 || (op.dim == 4 && op.nq == 2)) && k != deriv_op;
+        s.raw = fast ? 0 : 1;
+        s.q0 = op.dim == 2 ? op.target : op.q[0];
+        s.q1 = op.dim == 2 ? 30 : op.q[1];
+        sops[k] = s;
+    }
     if (MODE == MODE_GRAD && A.w_in_smem) {
         for (int e = tid; e < A.w_total; e += nthr) swacc[e] = czero();
     }
     double tsum[6] = {0, 0, 0, 0, 0, 0};  // running trace sums of this CTA (thread 0)
+    __syncthreads();
+
+    // kernel element this thread prefetches for op k (threads 0..15), and the commit into skm[k & 1]
+    auto kernel_elem = [&](int k) -> cplx {
+        const SOp s = sops[k];
+        if (s.raw || tid >= s.dim * s.dim) return czero();
+        const cplx* K = s.kern_off >= 0 ? ktab + s.kern_off : A.pool + (((long long)s.pool_hi << 32) | (unsigned)s.pool_lo);
+        return K[tid];
+    };
 
     for (int ti = 0; ti < A.tiles_per_cta; ++ti) {
         const int tile = chunk * A.tiles_per_cta + ti;
@@ -191,78 +202,116 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                 if (c < valid) v = src[(size_t)i * A.ld_in + c];
                 sa[phys_row<LOG_CT>(i) * CT + c] = v;
             }
+            if (A.n_ops > 0 && tid < 16) skm[tid] = kernel_elem(0);
         }
         __syncthreads();
 
-        // ---- forward sweep: gates[0] first (Gates_block.cpp:683) -----------------------------------------------
+        // ---- forward sweep: op 0 first (Gates_block.cpp:683) ---------------------------------------------------
         for (int k = 0; k < A.n_ops; ++k) {
-            const DevOp& op = A.ops[k];
-            OpLocal o;
-            load_op(op, o);
-            const bool deriv = (MODE == MODE_APPLY) && (k == deriv_op);
-            const cplx* __restrict__ K =
-                deriv ? dktab + op.dkern_off + deriv_p * o.dim * o.dim
-                      : (op.kern_off >= 0 ? ktab + op.kern_off : A.pool + op.pool_off);
-            if (o.dim == 2) {
-                const cplx k00 = K[0], k01 = K[1], k10 = K[2], k11 = K[3];
-                const int tbit = 1 << o.target;
-                if (!deriv) {
-                    const int nitems = (rows >> o.nfix) << LOG_CT;
+            const SOp s = sops[k];
+            cplx next_elem = czero();
+            const bool have_next = k + 1 < A.n_ops;
+            if (have_next && tid < 16) next_elem = kernel_elem(k + 1);
+            if (!s.raw) {
+                const cplx* __restrict__ km = skm + (k & 1) * 16;
+                if (s.dim == 4) {
+                    cplx M[16];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) M[e] = km[e];
+                    const int b0 = 1 << s.q0, b1 = 1 << s.q1;
+                    const int nitems = (rows >> 2) << LOG_CT;
                     for (int item = tid; item < nitems; item += nthr) {
                         const int c = item & (CT - 1);
-                        const int i0 = expand_fixed(item >> LOG_CT, op, o.nfix, o.fix) | o.ctrl_mask;
+                        const int base = insert_zero(insert_zero(item >> LOG_CT, s.q0), s.q1);
+                        const int e0 = phys_row<LOG_CT>(base) * CT + c, e1 = phys_row<LOG_CT>(base | b0) * CT + c;
+                        const int e2 = phys_row<LOG_CT>(base | b1) * CT + c, e3 = phys_row<LOG_CT>(base | b0 | b1) * CT + c;
+                        const cplx v0 = sa[e0], v1 = sa[e1], v2 = sa[e2], v3 = sa[e3];
+                        sa[e0] = cfma(M[3], v3, cfma(M[2], v2, cfma(M[1], v1, cmul(M[0], v0))));
+                        sa[e1] = cfma(M[7], v3, cfma(M[6], v2, cfma(M[5], v1, cmul(M[4], v0))));
+                        sa[e2] = cfma(M[11], v3, cfma(M[10], v2, cfma(M[9], v1, cmul(M[8], v0))));
+                        sa[e3] = cfma(M[15], v3, cfma(M[14], v2, cfma(M[13], v1, cmul(M[12], v0))));
+                    }
+                } else {
+                    const cplx k00 = km[0], k01 = km[1], k10 = km[2], k11 = km[3];
+                    const int tbit = 1 << s.q0;
+                    const int nitems = (rows >> 1) << LOG_CT;
+                    for (int item = tid; item < nitems; item += nthr) {
+                        const int c = item & (CT - 1);
+                        const int i0 = insert_zero(item >> LOG_CT, s.q0);
                         const int e0 = phys_row<LOG_CT>(i0) * CT + c, e1 = phys_row<LOG_CT>(i0 | tbit) * CT + c;
                         const cplx a0 = sa[e0], a1 = sa[e1];
                         sa[e0] = cfma(k01, a1, cmul(k00, a0));
                         sa[e1] = cfma(k11, a1, cmul(k10, a0));
                     }
-                } else {  // derivative kernel: inactive pairs are zero-filled (apply_kernel_to_input.cpp:93-97)
-                    const int nitems = (rows >> 1) << LOG_CT;
-                    for (int item = tid; item < nitems; item += nthr) {
-                        const int c = item & (CT - 1);
-                        const int i0 = insert_zero(item >> LOG_CT, o.target);
-                        const int e0 = phys_row<LOG_CT>(i0) * CT + c, e1 = phys_row<LOG_CT>(i0 | tbit) * CT + c;
-                        if ((i0 & o.ctrl_mask) == o.ctrl_mask) {
+                }
+            } else {
+                // ---- generic path: controlled gates, dense 8..32 kernels, derivative kernels ----------------------
+                const DevOp& op = A.ops[k];
+                const bool deriv = (MODE == MODE_APPLY) && (k == deriv_op);
+                const int dim = op.dim;
+                const cplx* __restrict__ K = deriv ? dktab + op.dkern_off + deriv_slot * dim * dim
+                                                    : (op.kern_off >= 0 ? ktab + op.kern_off : A.pool + op.pool_off);
+                if (dim == 2) {
+                    const cplx k00 = K[0], k01 = K[1], k10 = K[2], k11 = K[3];
+                    const int tbit = 1 << op.target;
+                    const unsigned cm = op.ctrl_mask;
+                    if (!deriv) {
+                        const int f0 = op.fix[0], f1 = op.fix[1], f2 = op.fix[2];
+                        const int nitems = (rows >> op.nfix) << LOG_CT;
+                        for (int item = tid; item < nitems; item += nthr) {
+                            const int c = item & (CT - 1);
+                            const int i0 = insert_zero(insert_zero(insert_zero(item >> LOG_CT, f0), f1), f2) | cm;
+                            const int e0 = phys_row<LOG_CT>(i0) * CT + c, e1 = phys_row<LOG_CT>(i0 | tbit) * CT + c;
                             const cplx a0 = sa[e0], a1 = sa[e1];
                             sa[e0] = cfma(k01, a1, cmul(k00, a0));
                             sa[e1] = cfma(k11, a1, cmul(k10, a0));
-                        } else {
-                            sa[e0] = czero();
-                            sa[e1] = czero();
+                        }
+                    } else {  // derivative kernel: inactive pairs are zero-filled (apply_kernel_to_input.cpp:93-97)
+                        const int nitems = (rows >> 1) << LOG_CT;
+                        for (int item = tid; item < nitems; item += nthr) {
+                            const int c = item & (CT - 1);
+                            const int i0 = insert_zero(item >> LOG_CT, op.target);
+                            const int e0 = phys_row<LOG_CT>(i0) * CT + c, e1 = phys_row<LOG_CT>(i0 | tbit) * CT + c;
+                            if ((i0 & cm) == cm) {
+                                const cplx a0 = sa[e0], a1 = sa[e1];
+                                sa[e0] = cfma(k01, a1, cmul(k00, a0));
+                                sa[e1] = cfma(k11, a1, cmul(k10, a0));
+                            } else {
+                                sa[e0] = czero();
+                                sa[e1] = czero();
+                            }
+                        }
+                    }
+                } else {
+                    // dense dim x dim kernel on ascending qubits (apply_large_kernel_to_input.cpp:160-199)
+                    for (int e = tid; e < dim * dim; e += nthr) sk[e] = K[e];
+                    __syncthreads();
+                    const int nq = op.nq;
+                    const int nitems = (rows >> nq) << LOG_CT;
+                    for (int item = tid; item < nitems; item += nthr) {
+                        const int c = item & (CT - 1);
+                        int base = item >> LOG_CT;
+                        for (int j = 0; j < nq; ++j) base = insert_zero(base, op.q[j]);
+                        const bool active = (base & op.ctrl_mask) == op.ctrl_mask;
+                        if (!active && !deriv) continue;
+                        cplx v[32];
+                        for (int l = 0; l < dim; ++l) {
+                            int r = base;
+                            for (int j = 0; j < nq; ++j) r |= ((l >> j) & 1) << op.q[j];
+                            v[l] = active ? sa[phys_row<LOG_CT>(r) * CT + c] : czero();
+                        }
+                        for (int ro = 0; ro < dim; ++ro) {
+                            cplx acc = czero();
+                            if (active)
+                                for (int l = 0; l < dim; ++l) acc = cfma(sk[ro * dim + l], v[l], acc);
+                            int r = base;
+                            for (int j = 0; j < nq; ++j) r |= ((ro >> j) & 1) << op.q[j];
+                            sa[phys_row<LOG_CT>(r) * CT + c] = acc;
                         }
                     }
                 }
-            } else {
-                // dense dim x dim kernel on ascending qubits (apply_large_kernel_to_input.cpp:160-199)
-                const int dim = o.dim;
-                for (int e = tid; e < dim * dim; e += nthr) sk[e] = K[e];
-                __syncthreads();
-                unsigned qmask = 0;
-                for (int j = 0; j < o.nq; ++j) qmask |= 1u << o.q[j];
-                const int ngroups_all = rows >> o.nq;  // groups over non-target bits (control handled by predicate)
-                const int nitems = ngroups_all << LOG_CT;
-                for (int item = tid; item < nitems; item += nthr) {
-                    const int c = item & (CT - 1);
-                    int base = item >> LOG_CT;
-                    for (int j = 0; j < o.nq; ++j) base = insert_zero(base, o.q[j]);
-                    const bool active = (base & o.ctrl_mask) == o.ctrl_mask;
-                    if (!active && !deriv) continue;
-                    cplx v[32];
-                    for (int l = 0; l < dim; ++l) {
-                        int r = base;
-                        for (int j = 0; j < o.nq; ++j) r |= ((l >> j) & 1) << o.q[j];
-                        v[l] = active ? sa[phys_row<LOG_CT>(r) * CT + c] : czero();
-                    }
-                    for (int ro = 0; ro < dim; ++ro) {
-                        cplx acc = czero();
-                        if (active)
-                            for (int l = 0; l < dim; ++l) acc = cfma(sk[ro * dim + l], v[l], acc);
-                        int r = base;
-                        for (int j = 0; j < o.nq; ++j) r |= ((ro >> j) & 1) << o.q[j];
-                        sa[phys_row<LOG_CT>(r) * CT + c] = acc;
-                    }
-                }
             }
+            if (have_next && tid < 16) skm[((k + 1) & 1) * 16 + tid] = next_elem;
             __syncthreads();
         }
 
@@ -324,6 +373,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
         if (MODE == MODE_GRAD) {
             // ---- beta_N = sum_t omega_t * sum_{masks of type t} e_{(j+off)^mask} per column ---------------------
             for (int e = tid; e < rows * CT; e += nthr) sb[e] = czero();
+            if (A.n_ops > 0 && tid < 16) skm[((A.n_ops - 1) & 1) * 16 + tid] = kernel_elem(A.n_ops - 1);
             __syncthreads();
             {
                 const int off = A.trace_offset;
@@ -351,107 +401,158 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
             // ---- backward sweep ---------------------------------------------------------------------------------
             int buf = 0;
             for (int k = A.n_ops - 1; k >= 0; --k) {
-                const DevOp& op = A.ops[k];
-                OpLocal o;
-                load_op(op, o);
-                const cplx* __restrict__ K = op.kern_off >= 0 ? ktab + op.kern_off : A.pool + op.pool_off;
-                const bool has_w = op.w_off >= 0;
-                if (o.dim == 2) {
-                    const cplx k00 = K[0], k01 = K[1], k10 = K[2], k11 = K[3];
-                    const int tbit = 1 << o.target;
-                    cplx w00 = czero(), w01 = czero(), w10 = czero(), w11 = czero();
-                    const int nitems = (rows >> o.nfix) << LOG_CT;
-                    for (int item = tid; item < nitems; item += nthr) {
-                        const int c = item & (CT - 1);
-                        const int i0 = expand_fixed(item >> LOG_CT, op, o.nfix, o.fix) | o.ctrl_mask;
-                        const int e0 = phys_row<LOG_CT>(i0) * CT + c, e1 = phys_row<LOG_CT>(i0 | tbit) * CT + c;
-                        const cplx p0 = sa[e0], p1 = sa[e1];  // column after the gate
-                        const cplx b0 = sb[e0], b1 = sb[e1];  // row functional after the gate
-                        // a_k = K^dagger a_{k+1}
-                        const cplx a0 = cfmac(k10, p1, cfmac(k00, p0, czero()));
-                        const cplx a1 = cfmac(k11, p1, cfmac(k01, p0, czero()));
-                        sa[e0] = a0;
-                        sa[e1] = a1;
-                        if (has_w) {
-                            w00 = cfma(b0, a0, w00);
-                            w01 = cfma(b0, a1, w01);
-                            w10 = cfma(b1, a0, w10);
-                            w11 = cfma(b1, a1, w11);
+                const SOp s = sops[k];
+                cplx next_elem = czero();
+                const bool have_next = k > 0;
+                if (have_next && tid < 16) next_elem = kernel_elem(k - 1);
+                const bool has_w = s.w_off >= 0;
+                double* wslot = reinterpret_cast<double*>(swarp + (size_t)(buf * nwarps + warp) * A.wmax);
+                int wdim = s.dim;
+                if (!s.raw) {
+                    const cplx* __restrict__ km = skm + (k & 1) * 16;
+                    if (s.dim == 4) {
+                        cplx M[16], W[16];
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) {
+                            M[e] = km[e];
+                            W[e] = czero();
                         }
-                        // beta_{k-1} = K^T beta_k
-                        sb[e0] = cfma(k10, b1, cmul(k00, b0));
-                        sb[e1] = cfma(k11, b1, cmul(k01, b0));
-                    }
-                    if (has_w) {
-                        double v[8] = {w00.x, w00.y, w01.x, w01.y, w10.x, w10.y, w11.x, w11.y};
-                        warp_reduce8(v, lane);
-                        if ((lane & 3) == 0) {
-                            const int idx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-                            reinterpret_cast<double*>(swarp + (size_t)(buf * nwarps + warp) * A.wmax)[idx] = v[0];
+                        const int b0 = 1 << s.q0, b1 = 1 << s.q1;
+                        const int nitems = (rows >> 2) << LOG_CT;
+                        for (int item = tid; item < nitems; item += nthr) {
+                            const int c = item & (CT - 1);
+                            const int base = insert_zero(insert_zero(item >> LOG_CT, s.q0), s.q1);
+                            const int e0 = phys_row<LOG_CT>(base) * CT + c, e1 = phys_row<LOG_CT>(base | b0) * CT + c;
+                            const int e2 = phys_row<LOG_CT>(base | b1) * CT + c, e3 = phys_row<LOG_CT>(base | b0 | b1) * CT + c;
+                            cplx p[4] = {sa[e0], sa[e1], sa[e2], sa[e3]};  // column after the block
+                            cplx b[4] = {sb[e0], sb[e1], sb[e2], sb[e3]};  // row functional after the block
+                            cplx a[4];
+#pragma unroll
+                            for (int cc = 0; cc < 4; ++cc)  // a = M^dagger p
+                                a[cc] = cfmac(M[12 + cc], p[3], cfmac(M[8 + cc], p[2], cfmac(M[4 + cc], p[1], cfmac(M[cc], p[0], czero()))));
+                            sa[e0] = a[0];
+                            sa[e1] = a[1];
+                            sa[e2] = a[2];
+                            sa[e3] = a[3];
+                            if (has_w) {
+#pragma unroll
+                                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                                    for (int cc = 0; cc < 4; ++cc) W[r * 4 + cc] = cfma(b[r], a[cc], W[r * 4 + cc]);
+                            }
+#pragma unroll
+                            for (int cc = 0; cc < 4; ++cc)  // beta' = M^T beta
+                                p[cc] = cfma(M[12 + cc], b[3], cfma(M[8 + cc], b[2], cfma(M[4 + cc], b[1], cmul(M[cc], b[0]))));
+                            sb[e0] = p[0];
+                            sb[e1] = p[1];
+                            sb[e2] = p[2];
+                            sb[e3] = p[3];
                         }
+                        if (has_w) warp_store_w<16>(W, wslot, lane);
+                    } else {
+                        const cplx k00 = km[0], k01 = km[1], k10 = km[2], k11 = km[3];
+                        const int tbit = 1 << s.q0;
+                        cplx W[4] = {czero(), czero(), czero(), czero()};
+                        const int nitems = (rows >> 1) << LOG_CT;
+                        for (int item = tid; item < nitems; item += nthr) {
+                            const int c = item & (CT - 1);
+                            const int i0 = insert_zero(item >> LOG_CT, s.q0);
+                            const int e0 = phys_row<LOG_CT>(i0) * CT + c, e1 = phys_row<LOG_CT>(i0 | tbit) * CT + c;
+                            const cplx p0 = sa[e0], p1 = sa[e1], b0 = sb[e0], b1 = sb[e1];
+                            const cplx a0 = cfmac(k10, p1, cfmac(k00, p0, czero()));
+                            const cplx a1 = cfmac(k11, p1, cfmac(k01, p0, czero()));
+                            sa[e0] = a0;
+                            sa[e1] = a1;
+                            if (has_w) {
+                                W[0] = cfma(b0, a0, W[0]);
+                                W[1] = cfma(b0, a1, W[1]);
+                                W[2] = cfma(b1, a0, W[2]);
+                                W[3] = cfma(b1, a1, W[3]);
+                            }
+                            sb[e0] = cfma(k10, b1, cmul(k00, b0));
+                            sb[e1] = cfma(k11, b1, cmul(k01, b0));
+                        }
+                        if (has_w) warp_store_w<4>(W, wslot, lane);
                     }
                 } else {
-                    const int dim = o.dim;
-                    for (int e = tid; e < dim * dim; e += nthr) sk[e] = K[e];
-                    __syncthreads();
-                    const int nitems = (rows >> o.nq) << LOG_CT;
-                    // dense parametric ops are 4 x 4 (RXX/RYY/RZZ): 16 complex accumulators
-                    cplx wl[16];
-                    if (has_w)
+                    const DevOp& op = A.ops[k];
+                    const cplx* __restrict__ K = op.kern_off >= 0 ? ktab + op.kern_off : A.pool + op.pool_off;
+                    wdim = op.dim;
+                    if (op.dim == 2) {
+                        const cplx k00 = K[0], k01 = K[1], k10 = K[2], k11 = K[3];
+                        const int tbit = 1 << op.target;
+                        const unsigned cm = op.ctrl_mask;
+                        const int f0 = op.fix[0], f1 = op.fix[1], f2 = op.fix[2];
+                        cplx W[4] = {czero(), czero(), czero(), czero()};
+                        const int nitems = (rows >> op.nfix) << LOG_CT;
+                        for (int item = tid; item < nitems; item += nthr) {
+                            const int c = item & (CT - 1);
+                            const int i0 = insert_zero(insert_zero(insert_zero(item >> LOG_CT, f0), f1), f2) | cm;
+                            const int e0 = phys_row<LOG_CT>(i0) * CT + c, e1 = phys_row<LOG_CT>(i0 | tbit) * CT + c;
+                            const cplx p0 = sa[e0], p1 = sa[e1], b0 = sb[e0], b1 = sb[e1];
+                            const cplx a0 = cfmac(k10, p1, cfmac(k00, p0, czero()));
+                            const cplx a1 = cfmac(k11, p1, cfmac(k01, p0, czero()));
+                            sa[e0] = a0;
+                            sa[e1] = a1;
+                            if (has_w) {
+                                W[0] = cfma(b0, a0, W[0]);
+                                W[1] = cfma(b0, a1, W[1]);
+                                W[2] = cfma(b1, a0, W[2]);
+                                W[3] = cfma(b1, a1, W[3]);
+                            }
+                            sb[e0] = cfma(k10, b1, cmul(k00, b0));
+                            sb[e1] = cfma(k11, b1, cmul(k01, b0));
+                        }
+                        if (has_w) warp_store_w<4>(W, wslot, lane);
+                    } else {
+                        const int dim = op.dim, nq = op.nq;
+                        for (int e = tid; e < dim * dim; e += nthr) sk[e] = K[e];
+                        __syncthreads();
+                        const int nitems = (rows >> nq) << LOG_CT;
+                        cplx wl[16];  // raw dense parametric ops are 4 x 4 (controlled two-target gates)
                         for (int e = 0; e < 16; ++e) wl[e] = czero();
-                    for (int item = tid; item < nitems; item += nthr) {
-                        const int c = item & (CT - 1);
-                        int base = item >> LOG_CT;
-                        for (int j = 0; j < o.nq; ++j) base = insert_zero(base, o.q[j]);
-                        if ((base & o.ctrl_mask) != o.ctrl_mask) continue;
-                        cplx pv[32], bv[32];
-                        int addr[32];
-                        for (int l = 0; l < dim; ++l) {
-                            int r = base;
-                            for (int j = 0; j < o.nq; ++j) r |= ((l >> j) & 1) << o.q[j];
-                            addr[l] = phys_row<LOG_CT>(r) * CT + c;
-                            pv[l] = sa[addr[l]];
-                            bv[l] = sb[addr[l]];
-                        }
-                        for (int ro = 0; ro < dim; ++ro) {
-                            cplx acc = czero(), bacc = czero();
+                        for (int item = tid; item < nitems; item += nthr) {
+                            const int c = item & (CT - 1);
+                            int base = item >> LOG_CT;
+                            for (int j = 0; j < nq; ++j) base = insert_zero(base, op.q[j]);
+                            if ((base & op.ctrl_mask) != op.ctrl_mask) continue;
+                            cplx pv[32], bv[32];
+                            int addr[32];
                             for (int l = 0; l < dim; ++l) {
-                                acc = cfmac(sk[l * dim + ro], pv[l], acc);   // (K^dagger p)[ro]
-                                bacc = cfma(sk[l * dim + ro], bv[l], bacc);  // (K^T beta)[ro]
+                                int r = base;
+                                for (int j = 0; j < nq; ++j) r |= ((l >> j) & 1) << op.q[j];
+                                addr[l] = phys_row<LOG_CT>(r) * CT + c;
+                                pv[l] = sa[addr[l]];
+                                bv[l] = sb[addr[l]];
                             }
-                            sa[addr[ro]] = acc;
-                            sb[addr[ro]] = bacc;
-                            if (has_w && dim == 4) {
+                            for (int ro = 0; ro < dim; ++ro) {
+                                cplx acc = czero(), bacc = czero();
+                                for (int l = 0; l < dim; ++l) {
+                                    acc = cfmac(sk[l * dim + ro], pv[l], acc);   // (K^dagger p)[ro]
+                                    bacc = cfma(sk[l * dim + ro], bv[l], bacc);  // (K^T beta)[ro]
+                                }
+                                sa[addr[ro]] = acc;
+                                sb[addr[ro]] = bacc;
+                                if (has_w && dim == 4) {
 #pragma unroll
-                                for (int r2 = 0; r2 < 4; ++r2) wl[r2 * 4 + ro] = cfma(bv[r2], acc, wl[r2 * 4 + ro]);
+                                    for (int r2 = 0; r2 < 4; ++r2) wl[r2 * 4 + ro] = cfma(bv[r2], acc, wl[r2 * 4 + ro]);
+                                }
                             }
                         }
-                    }
-                    if (has_w) {
-                        for (int part = 0; part < 4; ++part) {
-                            double v[8];
-                            for (int e = 0; e < 4; ++e) {
-                                v[2 * e] = wl[part * 4 + e].x;
-                                v[2 * e + 1] = wl[part * 4 + e].y;
-                            }
-                            warp_reduce8(v, lane);
-                            if ((lane & 3) == 0) {
-                                const int idx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-                                reinterpret_cast<double*>(swarp + (size_t)(buf * nwarps + warp) * A.wmax)[part * 8 + idx] = v[0];
-                            }
-                        }
+                        if (has_w) warp_store_w<16>(wl, wslot, lane);
                     }
                 }
+                if (have_next && tid < 16) skm[((k - 1) & 1) * 16 + tid] = next_elem;
                 __syncthreads();
                 if (has_w) {
-                    const int nd = 2 * o.dim * o.dim;  // doubles
+                    const int nd = 2 * wdim * wdim;  // doubles
                     if (tid < nd) {
-                        double s = 0;
+                        double sum = 0;
                         for (int w = 0; w < nwarps; ++w)
-                            s += reinterpret_cast<const double*>(swarp + (size_t)(buf * nwarps + w) * A.wmax)[tid];
-                        if (A.w_in_smem) reinterpret_cast<double*>(swacc + op.w_off)[tid] += s;
+                            sum += reinterpret_cast<const double*>(swarp + (size_t)(buf * nwarps + w) * A.wmax)[tid];
+                        if (A.w_in_smem) reinterpret_cast<double*>(swacc + s.w_off)[tid] += sum;
                         else
-                            reinterpret_cast<double*>(A.w_part + ((size_t)y * nchunks + chunk) * A.w_total + op.w_off)[tid] = s;
+                            reinterpret_cast<double*>(A.w_part + ((size_t)y * nchunks + chunk) * A.w_total + s.w_off)[tid] = sum;
                     }
                     buf ^= 1;
                 }

@@ -125,31 +125,140 @@ __device__ inline int build_gate_kernel(int type, const Trig& t, int which, cplx
     }
 }
 
+// ---- fused blocks ------------------------------------------------------------------------------------------------
+
+// c = a * b for dim x dim row-major complex matrices (dim = 2 or 4); c must not alias a or b
+__device__ __forceinline__ void mat_mul(const cplx* a, const cplx* b, cplx* c, int dim) {
+    for (int r = 0; r < dim; ++r)
+        for (int cc = 0; cc < dim; ++cc) {
+            cplx acc = czero();
+            for (int l = 0; l < dim; ++l) acc = cfma(a[r * dim + l], b[l * dim + cc], acc);
+            c[r * dim + cc] = acc;
+        }
+}
+
+__device__ __forceinline__ void mat_identity(cplx* m, int dim) {
+    for (int e = 0; e < dim * dim; ++e) m[e] = czero();
+    for (int r = 0; r < dim; ++r) m[r * dim + r] = cmake(1.0, 0.0);
+}
+
+// Embed a member's kernel into the block's basis (local index = bit0 <-> lower qubit, bit1 <-> higher qubit).
+// `deriv`: derivative kernels of controlled gates are ZERO (not identity) where the control bit is 0 -- the reference's
+// convention for derivative matrices (kernels/apply_kernel_to_input.cpp:93-97).
+__device__ __forceinline__ void embed_member(const DevMember& m, const cplx* k, bool deriv, int bdim, cplx* e) {
+    if (bdim == 2 || m.dim == 4) {
+        for (int i = 0; i < bdim * bdim; ++i) e[i] = k[i];
+        return;
+    }
+    const int tl = m.tl, ol = 1 - m.tl;
+    for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) {
+            const int tr = (r >> tl) & 1, tc = (c >> tl) & 1, orr = (r >> ol) & 1, oc = (c >> ol) & 1;
+            cplx v = czero();
+            if (orr == oc) {
+                if (m.cl >= 0 && orr == 0) v = (deriv || tr != tc) ? czero() : cmake(1.0, 0.0);
+                else v = k[tr * 2 + tc];
+            }
+            e[r * 4 + c] = v;
+        }
+}
+
+__device__ __forceinline__ void member_trig(const DevMember& m, const double* __restrict__ params, Trig& t) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        t.s[i] = 0.0;
+        t.c[i] = 1.0;
+        if (i < m.n_params) sincos(params[m.param_start + i], &t.s[i], &t.c[i]);
+    }
+}
+
+__device__ __forceinline__ void member_kernel(const DevMember& m, const Trig& t, int which, const cplx* __restrict__ pool,
+                                              cplx* k) {
+    if (m.type == SQGPU_GENERAL) {
+        for (int i = 0; i < m.dim * m.dim; ++i) k[i] = pool[m.pool_off + i];
+        return;
+    }
+    build_gate_kernel(m.type, t, which, k);
+}
+
+// Block matrix M = E_{m-1} ... E_0 and, for every parameter p of member j, dM_p = (E_{m-1}..E_{j+1}) dE_{j,p} (E_{j-1}..E_0).
+// This is the product rule the reference evaluates with full-size matrices (Gates_block::apply_derivate_to,
+// Gates_block.cpp:1011-1150), restricted to the 4 x 4 space the run of gates acts on.
+__device__ inline void build_block(const DevOp& op, const DevMember* __restrict__ members, const double* __restrict__ params,
+                                   const cplx* __restrict__ pool, cplx* __restrict__ kdst, cplx* __restrict__ dkdst,
+                                   bool with_deriv) {
+    const int dim = op.dim, d2 = dim * dim, nm = op.n_members;
+    cplx pre[SQ_MAX_MEMBERS + 1][16];  // pre[j] = E_{j-1} ... E_0
+    cplx k[16], e[16], tmp[16];
+    mat_identity(pre[0], dim);
+    for (int j = 0; j < nm; ++j) {
+        const DevMember m = members[op.member_off + j];
+        Trig t;
+        member_trig(m, params, t);
+        member_kernel(m, t, -1, pool, k);
+        embed_member(m, k, false, dim, e);
+        mat_mul(e, pre[j], pre[j + 1], dim);
+    }
+    for (int i = 0; i < d2; ++i) kdst[i] = pre[nm][i];
+    if (!with_deriv || op.n_params == 0) return;
+    cplx suf[16];  // E_{m-1} ... E_{j+1}
+    mat_identity(suf, dim);
+    for (int j = nm - 1; j >= 0; --j) {
+        const DevMember m = members[op.member_off + j];
+        Trig t;
+        member_trig(m, params, t);
+        for (int p = 0; p < m.n_params; ++p) {
+            member_kernel(m, t, p, pool, k);
+            embed_member(m, k, true, dim, e);
+            mat_mul(e, pre[j], tmp, dim);
+            cplx* dd = dkdst + (size_t)(m.slot0 + p) * d2;
+            // dd = suf * tmp
+            for (int r = 0; r < dim; ++r)
+                for (int cc = 0; cc < dim; ++cc) {
+                    cplx acc = czero();
+                    for (int l = 0; l < dim; ++l) acc = cfma(suf[r * dim + l], tmp[l * dim + cc], acc);
+                    dd[r * dim + cc] = acc;
+                }
+        }
+        member_kernel(m, t, -1, pool, k);
+        embed_member(m, k, false, dim, e);
+        mat_mul(suf, e, tmp, dim);
+        for (int i = 0; i < d2; ++i) suf[i] = tmp[i];
+    }
+}
+
 // One thread per (parameter set b, op): fills the forward kernel table and the derivative kernel table.
-// ktab[b * kern_total + op.kern_off + ...], dktab[b * dkern_total + op.dkern_off + p * dim*dim + ...].
-__global__ void build_kernel_tables(const DevOp* __restrict__ ops, int n_ops, const double* __restrict__ params,
-                                    int n_params, int batch, cplx* __restrict__ ktab, int kern_total,
+// ktab[b * kern_total + op.kern_off + ...], dktab[b * dkern_total + op.dkern_off + slot * dim*dim + ...].
+__global__ void build_kernel_tables(const DevOp* __restrict__ ops, int n_ops, const DevMember* __restrict__ members,
+                                    const double* __restrict__ params, int n_params, int batch,
+                                    const cplx* __restrict__ pool, cplx* __restrict__ ktab, int kern_total,
                                     cplx* __restrict__ dktab, int dkern_total, int with_deriv) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= batch * n_ops) return;
     const int b = idx / n_ops;
     const DevOp op = ops[idx - b * n_ops];
-    if (op.kern_off < 0) return;  // constant kernel (GENERAL) lives in the pool
+    if (op.kern_off < 0) return;  // constant kernel (raw GENERAL) lives in the pool
+    const double* __restrict__ pb = params + (size_t)b * n_params;
+    cplx* kdst = ktab + (size_t)b * kern_total + op.kern_off;
+    cplx* dkdst = dktab + (size_t)b * dkern_total + (op.dkern_off >= 0 ? op.dkern_off : 0);
+    if (op.type == SQ_OP_BLOCK) {
+        build_block(op, members, pb, pool, kdst, dkdst, with_deriv != 0);
+        return;
+    }
     Trig t;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         t.s[i] = 0.0;
         t.c[i] = 1.0;
-        if (i < op.n_params) sincos(params[(size_t)b * n_params + op.param_start + i], &t.s[i], &t.c[i]);
+        if (i < op.n_params) sincos(pb[op.param_start + i], &t.s[i], &t.c[i]);
     }
     cplx k[16];
     const int dim = build_gate_kernel(op.type, t, -1, k);
-    cplx* dst = ktab + (size_t)b * kern_total + op.kern_off;
-    for (int i = 0; i < dim * dim; ++i) dst[i] = k[i];
+    for (int i = 0; i < dim * dim; ++i) kdst[i] = k[i];
     if (with_deriv) {
         for (int p = 0; p < op.n_params; ++p) {
             build_gate_kernel(op.type, t, p, k);
-            cplx* dd = dktab + (size_t)b * dkern_total + op.dkern_off + p * dim * dim;
+            cplx* dd = dkdst + p * dim * dim;
             for (int i = 0; i < dim * dim; ++i) dd[i] = k[i];
         }
     }

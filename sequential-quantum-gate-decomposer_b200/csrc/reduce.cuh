@@ -17,7 +17,7 @@ __host__ __device__ __forceinline__ size_t tr_index(int y, int k, int n_k, int t
 
 __global__ void reduce_partials(const double* __restrict__ tr_part, int nchunks, const cplx* __restrict__ w_part,
                                 int w_total, const DevOp* __restrict__ ops, const int* __restrict__ param_op,
-                                const cplx* __restrict__ dktab, int dkern_total, int n_params, int with_grad,
+                                const int* __restrict__ param_slot, const cplx* __restrict__ dktab, int dkern_total, int n_params, int with_grad,
                                 double* __restrict__ traces) {
     const int y = blockIdx.x;
     const int n_k = 1 + (with_grad ? n_params : 0);
@@ -30,7 +30,7 @@ __global__ void reduce_partials(const double* __restrict__ tr_part, int nchunks,
     for (int p = threadIdx.x; p < n_params; p += blockDim.x) {
         const DevOp op = ops[param_op[p]];
         const int d2 = op.dim * op.dim;
-        const cplx* dk = dktab + (size_t)y * dkern_total + op.dkern_off + (p - op.param_start) * d2;
+        const cplx* dk = dktab + (size_t)y * dkern_total + op.dkern_off + param_slot[p] * d2;
         cplx acc = czero();
         for (int e = 0; e < d2; ++e) {
             cplx w = czero();

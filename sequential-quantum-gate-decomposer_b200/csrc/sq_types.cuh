@@ -28,23 +28,47 @@ __device__ __forceinline__ cplx cfmac(cplx a, cplx b, cplx acc) {
 __device__ __forceinline__ cplx cadd(cplx a, cplx b) { return make_double2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ cplx czero() { return make_double2(0.0, 0.0); }
 
-// One operation of the flattened circuit as the kernels see it. 1-qubit gates (optionally controlled by a bit mask)
-// have dim == 2; everything else (two-target gates, GENERAL blocks) is a dense dim x dim kernel on ascending qubits.
+// One operation of the device program. The host planner (sqgpu.cu: plan_blocks) fuses runs of consecutive gates that act
+// inside one or two qubits into a single dense 2x2 / 4x4 "block" op (type == SQ_OP_BLOCK) whose matrix -- and the
+// derivative of that matrix with respect to every parameter of its member gates -- is built per parameter set by
+// build_kernel_tables. Gates that cannot be fused (controls outside the pair, 3+ qubit dense kernels) stay "raw":
+// a 1-qubit gate with a control bit mask (dim == 2) or a dense dim x dim kernel on ascending qubits.
+enum { SQ_OP_BLOCK = 2000 };
+
 struct DevOp {
-    int32_t type;         // sqgpu_gate_type
+    int32_t type;         // sqgpu_gate_type of a raw op, or SQ_OP_BLOCK
     int32_t dim;          // 2, 4, 8, 16 or 32
     int32_t target;       // dim == 2: target qubit
-    uint32_t ctrl_mask;   // all of these row-index bits must be set for the gate to act
+    uint32_t ctrl_mask;   // raw ops: all of these row-index bits must be set for the gate to act (0 for blocks)
     int32_t nq;           // dim > 2: number of qubits
     int32_t q[5];         // dim > 2: ascending qubits, local bit j <-> q[j]
-    int32_t param_start;  // first parameter
-    int32_t n_params;
+    int32_t param_start;  // raw ops: first parameter
+    int32_t n_params;     // parameters of the op (blocks: of all members)
     int32_t kern_off;     // offset (complex) into the per-parameter-set kernel table; -1: constant kernel in the pool
-    int32_t dkern_off;    // offset (complex) into the per-parameter-set derivative-kernel table (n_params kernels)
+    int32_t dkern_off;    // offset (complex) into the per-parameter-set derivative table (n_params kernels of dim*dim)
     int32_t w_off;        // offset (complex) into the per-parameter-set W accumulator (dim*dim), -1 if no parameters
+    int32_t member_off;   // blocks: first member in the member table
+    int32_t n_members;
+    int32_t nfix;         // number of fixed row-index bits when enumerating the op's groups (targets + controls)
+    int32_t fix[6];       // those bit positions, ascending; unused entries = 30 (insert_zero(.,30) is the identity)
     int32_t pad;
     int64_t pool_off;     // constant kernel offset (complex) in the pool
 };
+
+// A gate inside a fused block, in block-local coordinates.
+struct DevMember {
+    int32_t type;         // sqgpu_gate_type
+    int32_t dim;          // 2: 1-qubit kernel (optionally controlled by the block's other qubit); 4: two-target kernel
+    int32_t tl;           // dim == 2: local target bit (0/1)
+    int32_t cl;           // dim == 2: local control bit or -1
+    int32_t param_start;  // first parameter in the circuit's parameter vector
+    int32_t n_params;
+    int32_t slot0;        // index of the member's first derivative kernel inside the block's derivative table
+    int32_t pad;
+    int64_t pool_off;     // GENERAL members: constant kernel in the pool
+};
+
+static const int SQ_MAX_MEMBERS = 12;  // gates per fused block (local scratch of the table builder)
 
 // insert a zero bit at position t of idx (all higher bits move up)
 __host__ __device__ __forceinline__ int insert_zero(int idx, int t) {

@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -112,10 +113,12 @@ struct sqgpu_ctx {
     int rows = 0, cols = 0;
 
     // circuit
-    std::vector<DevOp> ops;
-    std::vector<int> param_op;
-    DevBuf dOps, dParamOp, dPool;
-    int n_params = 0, qbit_num = 0, n_ops = 0;
+    std::vector<DevOp> ops;          // device program (fused blocks + raw ops)
+    std::vector<DevMember> members;  // gates inside the fused blocks
+    std::vector<int> param_op;       // parameter -> op that owns it
+    std::vector<int> param_slot;     // parameter -> index of its derivative kernel inside that op
+    DevBuf dOps, dMembers, dParamOp, dPool;
+    int n_params = 0, qbit_num = 0, n_ops = 0, n_gates = 0;
     int kern_total = 0, dkern_total = 0, w_total = 0, wmax = 4;
     bool has_dense = false, all_unitary = true, circuit_set = false;
     std::vector<cplx> pool;
@@ -199,6 +202,35 @@ int param_count_of(int type) {
     }
 }
 
+// fixed row-index bits of an op's group enumeration: its targets and controls, ascending; unused slots = 30
+void fill_fix(DevOp& op) {
+    unsigned m = op.ctrl_mask;
+    if (op.dim == 2) m |= 1u << op.target;
+    else
+        for (int j = 0; j < op.nq; ++j) m |= 1u << op.q[j];
+    op.nfix = 0;
+    for (int b = 0; b < 30; ++b)
+        if ((m >> b) & 1) {
+            if (op.nfix < 6) op.fix[op.nfix] = b;
+            op.nfix++;
+        }
+    for (int f = op.nfix; f < 6; ++f) op.fix[f] = 30;
+}
+
+unsigned support_mask(const DevOp& op) {
+    unsigned m = op.ctrl_mask;
+    if (op.dim == 2) m |= 1u << op.target;
+    else
+        for (int j = 0; j < op.nq; ++j) m |= 1u << op.q[j];
+    return m;
+}
+
+int popcount32(unsigned v) {
+    int c = 0;
+    for (; v; v &= v - 1) ++c;
+    return c;
+}
+
 // Lower one descriptor to a DevOp (offsets are assigned by the caller). Returns 0 or a status.
 int lower_gate(const sqgpu_gate_desc& g, int qbit_num, const double* pool, int64_t pool_len, DevOp* out, bool* unitary) {
     DevOp op;
@@ -224,6 +256,7 @@ int lower_gate(const sqgpu_gate_desc& g, int qbit_num, const double* pool, int64
             if (j && g.qubits[j] <= g.qubits[j - 1]) return fail(SQGPU_ERR_INVALID, "GENERAL gate: qubits must be ascending");
         }
         op.pool_off = g.matrix_off;
+        op.member_off = -1;
         if (k == 1) {
             op.dim = 2;
             op.target = g.qubits[0];
@@ -247,6 +280,7 @@ int lower_gate(const sqgpu_gate_desc& g, int qbit_num, const double* pool, int64
                 worst = std::max(worst, std::max(std::fabs(re - (r == c ? 1.0 : 0.0)), std::fabs(im)));
             }
         *unitary = worst < 1e-9;
+        fill_fix(op);
         *out = op;
         return SQGPU_OK;
     }
@@ -277,6 +311,8 @@ int lower_gate(const sqgpu_gate_desc& g, int qbit_num, const double* pool, int64
         op.dim = 2;
         op.target = g.target;
     }
+    op.member_off = -1;
+    fill_fix(op);
     *out = op;
     return SQGPU_OK;
 }
@@ -291,9 +327,11 @@ struct FusedPlan {
     size_t smem = 0;
 };
 
-size_t fused_smem(int mode, int rows, int ct, int threads, bool has_dense, int wmax, int w_total, bool w_in_smem) {
+size_t fused_smem(int mode, int rows, int ct, int threads, bool has_dense, int wmax, int w_total, bool w_in_smem, int n_ops) {
     size_t s = (size_t)rows * ct * sizeof(cplx) * (mode == MODE_GRAD ? 2 : 1);
     if (has_dense) s += (size_t)DENSE_STAGE * sizeof(cplx);
+    s += 32 * sizeof(cplx);                  // prefetched block kernels
+    s += (size_t)n_ops * sizeof(SOp);        // staged op table
     const int nwarps = threads / 32;
     if (mode == MODE_GRAD) {
         s += (size_t)2 * nwarps * wmax * sizeof(cplx);
@@ -310,14 +348,14 @@ FusedPlan plan_fused(const sqgpu_ctx* c, int mode, int rows, int cols, int ysets
     while ((1 << max_log) > cols && max_log > 0) --max_log;  // no wider than the matrix (cols = 1: state vector)
     for (int lc = max_log; lc >= 0; --lc) {
         const int ct = 1 << lc;
-        int items = (rows / 2) * ct;
-        int threads = std::min(FUSED_THREADS, std::max(32, ((items + 1) / 2 + 31) / 32 * 32));
+        int items = (rows / 4) * ct;  // groups of a 4x4 block
+        int threads = std::min(FUSED_THREADS, std::max(32, (items + 31) / 32 * 32));
         const bool grad = mode == MODE_GRAD;
         bool wsm = grad && c->w_total > 0;
-        size_t s = fused_smem(mode, rows, ct, threads, c->has_dense, c->wmax, c->w_total, wsm);
+        size_t s = fused_smem(mode, rows, ct, threads, c->has_dense, c->wmax, c->w_total, wsm, c->n_ops);
         if (s > budget && wsm) {
             wsm = false;
-            s = fused_smem(mode, rows, ct, threads, c->has_dense, c->wmax, c->w_total, false);
+            s = fused_smem(mode, rows, ct, threads, c->has_dense, c->wmax, c->w_total, false, c->n_ops);
         }
         if (s > budget) continue;
         // prefer tiles that leave shared memory for the W accumulator: a narrower tile with W in smem beats a wider
@@ -374,10 +412,10 @@ int run_tables(sqgpu_ctx* c, const double* d_params, int batch, bool with_deriv,
     if ((rc = c->wDKtab.ensure(std::max<size_t>(1, (size_t)batch * c->dkern_total) * sizeof(cplx)))) return rc;
     const long long total = (long long)batch * c->n_ops;
     if (total == 0) return SQGPU_OK;
-    const int thr = 128;
+    const int thr = 64;
     build_kernel_tables<<<(unsigned)((total + thr - 1) / thr), thr, 0, st>>>(
-        c->dOps.as<DevOp>(), c->n_ops, d_params, c->n_params, batch, c->wKtab.as<cplx>(), c->kern_total,
-        c->wDKtab.as<cplx>(), c->dkern_total, with_deriv ? 1 : 0);
+        c->dOps.as<DevOp>(), c->n_ops, c->dMembers.as<DevMember>(), d_params, c->n_params, batch, c->dPool.as<cplx>(),
+        c->wKtab.as<cplx>(), c->kern_total, c->wDKtab.as<cplx>(), c->dkern_total, with_deriv ? 1 : 0);
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     return SQGPU_OK;
@@ -442,8 +480,8 @@ int run_exec_resident(sqgpu_ctx* c, int batch, bool grad, const cplx* d_omega, d
     c->launches++;
     if (e != cudaSuccess) return fail(SQGPU_ERR_CUDA, "fused_exec launch failed: %s", cudaGetErrorString(e));
     reduce_partials<<<batch, 128, 0, st>>>(c->wTrPart.as<double>(), p.chunks, c->wWPart.as<cplx>(), c->w_total,
-                                           c->dOps.as<DevOp>(), c->dParamOp.as<int>(), c->wDKtab.as<cplx>(),
-                                           c->dkern_total, c->n_params, grad ? 1 : 0, d_traces);
+                                           c->dOps.as<DevOp>(), c->dParamOp.as<int>(), c->dParamOp.as<int>() + std::max(c->n_params, 1),
+                                           c->wDKtab.as<cplx>(), c->dkern_total, c->n_params, grad ? 1 : 0, d_traces);
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     return SQGPU_OK;
@@ -619,7 +657,7 @@ int apply_program_dev(sqgpu_ctx* c, const cplx* d_in, long long in_ystride, cplx
         a.ld_out = cols;
         a.k_shared = 1;
         a.deriv_op = d_dop;
-        a.deriv_pidx = d_dp;
+        a.deriv_slot = d_dp;
         for (int y0 = 0; y0 < ysets; y0 += 65535) {
             const int ny = std::min(65535, ysets - y0);
             ExecArgs b = a;
@@ -627,7 +665,7 @@ int apply_program_dev(sqgpu_ctx* c, const cplx* d_in, long long in_ystride, cplx
             b.out = d_out + (size_t)y0 * out_ystride;
             if (d_dop) {
                 b.deriv_op = d_dop + y0;
-                b.deriv_pidx = d_dp + y0;
+                b.deriv_slot = d_dp + y0;
             }
             time_begin(c, "fused_exec<APPLY>", st);
             cudaError_t e = launch_fused_mode<MODE_APPLY>(b, p, ny, st);
@@ -742,7 +780,7 @@ int sqgpu_destroy(sqgpu_handle_t c) {
         DeviceGuard guard(c->device);
         std::lock_guard<std::mutex> lk(c->mtx);
         cudaStreamSynchronize(c->stream);
-        DevBuf* bufs[] = {&c->U, &c->dOps, &c->dParamOp, &c->dPool, &c->wParams, &c->wKtab, &c->wDKtab, &c->wTrPart, &c->wWPart,
+        DevBuf* bufs[] = {&c->U, &c->dOps, &c->dMembers, &c->dParamOp, &c->dPool, &c->wParams, &c->wKtab, &c->wDKtab, &c->wTrPart, &c->wWPart,
                           &c->wTraces, &c->wOmega, &c->wCost, &c->wGrad, &c->wMat, &c->wDerivIdx, &c->wTraces0,
                           &c->hIndptr, &c->hIndices, &c->hValues};
         for (DevBuf* b : bufs) b->release();
@@ -775,53 +813,144 @@ int sqgpu_set_circuit(sqgpu_handle_t c, const sqgpu_gate_desc* gates, int n_gate
     if (!c) return fail(SQGPU_ERR_INVALID, "NULL handle");
     if (n_gates < 0 || n_params < 0 || qbit_num < 1 || qbit_num > 30) return fail(SQGPU_ERR_INVALID, "bad circuit arguments");
     if (n_gates > 0 && !gates) return fail(SQGPU_ERR_INVALID, "gates is NULL");
-    std::vector<DevOp> ops(n_gates);
-    std::vector<int> param_op(std::max(n_params, 1), -1);
-    int kern_total = 0, dkern_total = 0, w_total = 0, wmax = 4;
-    bool has_dense = false, all_unitary = true;
+    // 1. lower every descriptor to a raw op (validation happens here)
+    std::vector<DevOp> raw(n_gates);
+    bool all_unitary = true;
+    std::vector<char> param_used(std::max(n_params, 1), 0);
     for (int i = 0; i < n_gates; ++i) {
         bool unitary = true;
-        int rc = lower_gate(gates[i], qbit_num, matrix_pool, pool_len, &ops[i], &unitary);
+        int rc = lower_gate(gates[i], qbit_num, matrix_pool, pool_len, &raw[i], &unitary);
         if (rc) return rc;
         all_unitary = all_unitary && unitary;
-        DevOp& op = ops[i];
+        const DevOp& op = raw[i];
+        if (op.n_params > 0) {
+            if (op.param_start < 0 || op.param_start + op.n_params > n_params)
+                return fail(SQGPU_ERR_INVALID, "gate %d: parameters [%d, %d) outside the parameter vector of length %d", i,
+                            op.param_start, op.param_start + op.n_params, n_params);
+            for (int p = 0; p < op.n_params; ++p) {
+                if (param_used[op.param_start + p]) return fail(SQGPU_ERR_INVALID, "parameter %d is used by two gates", op.param_start + p);
+                param_used[op.param_start + p] = 1;
+            }
+        }
+    }
+    for (int p = 0; p < n_params; ++p)
+        if (!param_used[p]) return fail(SQGPU_ERR_INVALID, "parameter %d is not used by any gate", p);
+
+    // 2. plan: fuse runs of consecutive gates whose joint support is at most two qubits into one dense block
+    //    (the device-side analogue of Gates_block's <=2-qubit fusion rule, Gates_block.cpp:632-681, applied to the
+    //    flattened circuit and extended to the gradient by the product rule in build_block)
+    const char* nf = getenv("SQGPU_NO_FUSE");
+    const bool fuse = !(nf && nf[0] == '1');
+    std::vector<DevOp> ops;
+    std::vector<DevMember> members;
+    std::vector<int> param_op(std::max(n_params, 1), -1), param_slot(std::max(n_params, 1), 0);
+    int kern_total = 0, dkern_total = 0, w_total = 0, wmax = 4;
+    bool has_dense = false;
+    std::vector<int> pend;
+    unsigned pend_support = 0;
+
+    auto finish_op = [&](DevOp& op) {
         const int d2 = op.dim * op.dim;
-        if (op.type != SQGPU_GENERAL) {
+        if (!(op.type == SQGPU_GENERAL)) {
             op.kern_off = kern_total;
             kern_total += d2;
         }
         if (op.dim > 2) has_dense = true;
         if (op.n_params > 0) {
-            if (op.param_start < 0 || op.param_start + op.n_params > n_params)
-                return fail(SQGPU_ERR_INVALID, "gate %d: parameters [%d, %d) outside the parameter vector of length %d", i,
-                            op.param_start, op.param_start + op.n_params, n_params);
             op.dkern_off = dkern_total;
             dkern_total += d2 * op.n_params;
             op.w_off = w_total;
             w_total += d2;
             wmax = std::max(wmax, d2);
-            for (int p = 0; p < op.n_params; ++p) {
-                if (param_op[op.param_start + p] != -1) return fail(SQGPU_ERR_INVALID, "parameter %d is used by two gates", op.param_start + p);
-                param_op[op.param_start + p] = i;
-            }
         }
+        ops.push_back(op);
+    };
+    auto flush = [&]() {
+        if (pend.empty()) return;
+        DevOp b;
+        memset(&b, 0, sizeof(b));
+        b.type = SQ_OP_BLOCK;
+        b.kern_off = b.dkern_off = b.w_off = -1;
+        int qs[2], nqs = 0;
+        for (int q = 0; q < 30; ++q)
+            if ((pend_support >> q) & 1) qs[nqs++] = q;
+        if (nqs == 1) {
+            b.dim = 2;
+            b.target = qs[0];
+        } else {
+            b.dim = 4;
+            b.nq = 2;
+            b.q[0] = qs[0];
+            b.q[1] = qs[1];
+        }
+        b.member_off = (int)members.size();
+        b.n_members = (int)pend.size();
+        int slot = 0;
+        for (int gi : pend) {
+            const DevOp& r = raw[gi];
+            DevMember m;
+            memset(&m, 0, sizeof(m));
+            m.type = r.type;
+            m.dim = r.dim;
+            m.tl = (r.dim == 2 && nqs == 2 && r.target == qs[1]) ? 1 : 0;
+            m.cl = (r.dim == 2 && r.ctrl_mask) ? 1 - m.tl : -1;
+            m.param_start = r.param_start;
+            m.n_params = r.n_params;
+            m.slot0 = slot;
+            m.pool_off = r.pool_off;
+            for (int p = 0; p < r.n_params; ++p) {
+                param_op[r.param_start + p] = (int)ops.size();
+                param_slot[r.param_start + p] = slot + p;
+            }
+            slot += r.n_params;
+            members.push_back(m);
+        }
+        b.n_params = slot;
+        fill_fix(b);
+        finish_op(b);
+        pend.clear();
+        pend_support = 0;
+    };
+    for (int i = 0; i < n_gates; ++i) {
+        const DevOp& r = raw[i];
+        const unsigned sup = support_mask(r);
+        const bool fusable = fuse && ((r.dim == 2 && popcount32(r.ctrl_mask) <= 1) || (r.dim == 4 && r.ctrl_mask == 0));
+        if (fusable) {
+            if (!pend.empty() && (popcount32(pend_support | sup) > 2 || (int)pend.size() >= SQ_MAX_MEMBERS)) flush();
+            pend.push_back(i);
+            pend_support |= sup;
+            continue;
+        }
+        flush();
+        DevOp op = r;
+        for (int p = 0; p < op.n_params; ++p) {
+            param_op[op.param_start + p] = (int)ops.size();
+            param_slot[op.param_start + p] = p;
+        }
+        finish_op(op);
     }
-    for (int p = 0; p < n_params; ++p)
-        if (param_op[p] < 0) return fail(SQGPU_ERR_INVALID, "parameter %d is not used by any gate", p);
+    flush();
 
     DeviceGuard guard(c->device);
     std::lock_guard<std::mutex> lk(c->mtx);
     int rc;
+    const size_t np1 = std::max(n_params, 1);
     if ((rc = c->dOps.ensure(std::max<size_t>(1, ops.size()) * sizeof(DevOp)))) return rc;
-    if ((rc = c->dParamOp.ensure(param_op.size() * sizeof(int)))) return rc;
+    if ((rc = c->dMembers.ensure(std::max<size_t>(1, members.size()) * sizeof(DevMember)))) return rc;
+    if ((rc = c->dParamOp.ensure(2 * np1 * sizeof(int)))) return rc;
     if ((rc = c->dPool.ensure(std::max<size_t>(1, (size_t)pool_len) * sizeof(cplx)))) return rc;
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     if (!ops.empty()) CUDA_TRY(cudaMemcpy(c->dOps.p, ops.data(), ops.size() * sizeof(DevOp), cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(c->dParamOp.p, param_op.data(), param_op.size() * sizeof(int), cudaMemcpyHostToDevice));
+    if (!members.empty()) CUDA_TRY(cudaMemcpy(c->dMembers.p, members.data(), members.size() * sizeof(DevMember), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(c->dParamOp.p, param_op.data(), np1 * sizeof(int), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(c->dParamOp.as<int>() + np1, param_slot.data(), np1 * sizeof(int), cudaMemcpyHostToDevice));
     if (pool_len > 0) CUDA_TRY(cudaMemcpy(c->dPool.p, matrix_pool, (size_t)pool_len * sizeof(cplx), cudaMemcpyHostToDevice));
     c->ops.swap(ops);
+    c->members.swap(members);
     c->param_op.swap(param_op);
-    c->n_ops = n_gates;
+    c->param_slot.swap(param_slot);
+    c->n_ops = (int)c->ops.size();
+    c->n_gates = n_gates;
     c->n_params = n_params;
     c->qbit_num = qbit_num;
     c->kern_total = kern_total;
@@ -998,7 +1127,7 @@ int sqgpu_apply_derivative(sqgpu_handle_t c, const double* params, const double*
         std::vector<int> dop(np), dp(np);
         for (int i = 0; i < np; ++i) {
             dop[i] = c->param_op[p0 + i];
-            dp[i] = p0 + i - c->ops[dop[i]].param_start;
+            dp[i] = c->param_slot[p0 + i];
         }
         if ((rc = apply_program_dev(c, d_in, 0, d_out, (long long)n_elem, np, rows, cols, &dop, &dp, c->stream))) return rc;
         CUDA_TRY(cudaMemcpyAsync(out + 2 * (size_t)p0 * n_elem, d_out, (size_t)np * n_elem * sizeof(cplx), cudaMemcpyDeviceToHost, c->stream));
@@ -1044,8 +1173,8 @@ static int apply_gate_on_device(sqgpu_ctx* c, const sqgpu_gate_desc* gate, const
         for (int i = 0; i < op.n_params; ++i) pbuf[i] = gate_params[i];
         CUDA_TRY(cudaMemcpyAsync(base, &op, sizeof(DevOp), cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(base + off_par, pbuf, sizeof(pbuf), cudaMemcpyHostToDevice, st));
-        build_kernel_tables<<<1, 32, 0, st>>>(reinterpret_cast<DevOp*>(base), 1, reinterpret_cast<double*>(base + off_par), 4, 1,
-                                              reinterpret_cast<cplx*>(base + off_k), d2, reinterpret_cast<cplx*>(base + off_dk), 4 * d2, 1);
+        build_kernel_tables<<<1, 32, 0, st>>>(reinterpret_cast<DevOp*>(base), 1, nullptr, reinterpret_cast<double*>(base + off_par), 4, 1,
+                                              nullptr, reinterpret_cast<cplx*>(base + off_k), d2, reinterpret_cast<cplx*>(base + off_dk), 4 * d2, 1);
         c->launches++;
         CUDA_TRY(cudaGetLastError());
         K = deriv_param >= 0 ? reinterpret_cast<cplx*>(base + off_dk) + (size_t)deriv_param * d2 : reinterpret_cast<cplx*>(base + off_k);

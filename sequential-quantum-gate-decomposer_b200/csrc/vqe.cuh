@@ -115,16 +115,84 @@ __global__ void __launch_bounds__(256) adjoint1q_stream(const StreamGate G, cplx
     }
 }
 
-// grad[y][p] = scale * Re( sum_e dK_p[e] * W[y][op][e] ) over the parameters of one op
-__global__ void grad_from_w(const cplx* __restrict__ wsum /*[y][4]*/, const cplx* __restrict__ dktab, int dkern_total,
-                            int dkern_off, int n_params_op, int param_start, int n_params, double scale,
-                            double* __restrict__ grad) {
-    const int y = blockIdx.x, p = threadIdx.x;
-    if (p >= n_params_op) return;
-    const cplx* dk = dktab + (size_t)y * dkern_total + dkern_off + p * 4;
-    cplx acc = czero();
-    for (int e = 0; e < 4; ++e) acc = cfma(dk[e], wsum[(size_t)y * 4 + e], acc);
-    grad[(size_t)y * n_params + param_start + p] = scale * acc.x;
+// backward step for a dense 4 x 4 block on qubits q0 < q1 (no controls): same recurrences, 16 W entries.
+// wpart[y][blockIdx.x][32] receives this block's W contribution.
+__global__ void __launch_bounds__(128) adjoint2q_stream(const StreamGate G, cplx* __restrict__ beta, long long beta_ystride,
+                                                        double* __restrict__ wpart, int want_w) {
+    __shared__ double sred[4 * 32];
+    const cplx* __restrict__ K = G.K + (size_t)blockIdx.y * G.k_ystride;
+    cplx M[16], W[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+        M[e] = K[e];
+        W[e] = czero();
+    }
+    cplx* __restrict__ d = G.data + (size_t)blockIdx.y * G.ystride;
+    cplx* __restrict__ bt = beta + (size_t)blockIdx.y * beta_ystride;
+    const long long nitems = (long long)(G.rows >> 2) * G.cols;
+    const int q0 = G.q[0], q1 = G.q[1];
+    const size_t s0 = (size_t)(1 << q0) * G.ld, s1 = (size_t)(1 << q1) * G.ld;
+    for (long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x; item < nitems;
+         item += (long long)gridDim.x * blockDim.x) {
+        int g, j;
+        if (G.log_cols >= 0) {
+            g = (int)(item >> G.log_cols);
+            j = (int)(item & (G.cols - 1));
+        } else {
+            g = (int)(item / G.cols);
+            j = (int)(item - (long long)g * G.cols);
+        }
+        const int base = insert_zero(insert_zero(g, q0), q1);
+        const size_t o0 = (size_t)base * G.ld + j;
+        const size_t o[4] = {o0, o0 + s0, o0 + s1, o0 + s0 + s1};
+        cplx p[4], b[4], a[4];
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+            p[l] = d[o[l]];
+            b[l] = bt[o[l]];
+        }
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc)
+            a[cc] = cfmac(M[12 + cc], p[3], cfmac(M[8 + cc], p[2], cfmac(M[4 + cc], p[1], cfmac(M[cc], p[0], czero()))));
+#pragma unroll
+        for (int l = 0; l < 4; ++l) d[o[l]] = a[l];
+        if (want_w) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) W[r * 4 + cc] = cfma(b[r], a[cc], W[r * 4 + cc]);
+        }
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc)
+            bt[o[cc]] = cfma(M[12 + cc], b[3], cfma(M[8 + cc], b[2], cfma(M[4 + cc], b[1], cmul(M[cc], b[0]))));
+    }
+    if (!want_w) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+        double re = W[e].x, im = W[e].y;
+        for (int s = 16; s > 0; s >>= 1) {
+            re += __shfl_xor_sync(0xffffffffu, re, s);
+            im += __shfl_xor_sync(0xffffffffu, im, s);
+        }
+        if (lane == 0) {
+            sred[warp * 32 + 2 * e] = re;
+            sred[warp * 32 + 2 * e + 1] = im;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double s = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += sred[w * 32 + threadIdx.x];
+        wpart[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 32 + threadIdx.x] = s;
+    }
+}
+
+// grad[y][p] = scale * Re(dL_p) from the traces buffer reduce_partials wrote
+__global__ void grad_from_traces(const double* __restrict__ traces, int n_params, double scale, double* __restrict__ grad) {
+    const int y = blockIdx.x;
+    for (int p = threadIdx.x; p < n_params; p += blockDim.x)
+        grad[(size_t)y * n_params + p] = scale * traces[(((size_t)y * (1 + n_params) + 1 + p) * 3) * 2];
 }
 
 }  // namespace sq

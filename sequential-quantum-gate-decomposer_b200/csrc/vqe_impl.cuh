@@ -11,16 +11,22 @@ static int vqe_dev(sqgpu_ctx* c, const double* d_params, int batch, bool with_gr
     if (c->cols != 1) return fail(SQGPU_ERR_INVALID, "the VQE path needs a state vector (cols = 1), the resident matrix has %d columns", c->cols);
     if (!c->hIndptr.p || c->h_rows != c->rows) return fail(SQGPU_ERR_STATE, "no Hamiltonian of matching size set (call sqgpu_set_hamiltonian_csr)");
     if (!d_energy || (with_grad && !d_grad && c->n_params > 0)) return fail(SQGPU_ERR_INVALID, "NULL buffer");
-    for (int k = 0; k < c->n_ops; ++k)
-        if (with_grad && c->ops[k].dim != 2) return fail(SQGPU_ERR_UNSUPPORTED, "VQE gradient with multi-qubit dense gates is not implemented");
+    for (int k = 0; k < c->n_ops; ++k) {
+        const DevOp& op = c->ops[k];
+        const bool ok = op.dim == 2 || (op.dim == 4 && op.nq == 2 && op.ctrl_mask == 0);
+        if (with_grad && !ok) return fail(SQGPU_ERR_UNSUPPORTED, "VQE gradient with 3+ qubit dense or multi-controlled gates is not implemented");
+    }
     if (with_grad && !c->all_unitary) return fail(SQGPU_ERR_UNSUPPORTED, "gradient with a non-unitary GENERAL gate is not supported");
     const int rows = c->rows;
     // parameter sets per slice: two state buffers of <= 1 GiB each
     const int slice = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::min(batch, 65535), ((size_t)1 << 30) / ((size_t)rows * sizeof(cplx))));
     const int nblk = std::min(c->sm_count * 8, std::max(1, rows / 512));
     if ((rc = c->wMat.ensure((size_t)2 * slice * rows * sizeof(cplx)))) return rc;
-    if ((rc = c->wTrPart.ensure((size_t)slice * nblk * 8 * sizeof(double)))) return rc;
-    if ((rc = c->wOmega.ensure((size_t)slice * 4 * sizeof(cplx)))) return rc;
+    if ((rc = c->wTrPart.ensure((size_t)slice * (nblk * 32 + 6) * sizeof(double)))) return rc;
+    if (with_grad) {
+        if ((rc = c->wWPart.ensure(std::max<size_t>(1, (size_t)slice * c->w_total) * sizeof(cplx)))) return rc;
+        if ((rc = c->wTraces.ensure((size_t)slice * (1 + c->n_params) * 6 * sizeof(double)))) return rc;
+    }
     cplx* psi = c->wMat.as<cplx>();
     cplx* lam = psi + (size_t)slice * rows;
     for (int b0 = 0; b0 < batch; b0 += slice) {
@@ -55,18 +61,33 @@ static int vqe_dev(sqgpu_ctx* c, const double* d_params, int batch, bool with_gr
             const cplx* K = op.kern_off >= 0 ? c->wKtab.as<cplx>() + op.kern_off : c->dPool.as<cplx>() + op.pool_off;
             const long long kst = op.kern_off >= 0 ? c->kern_total : 0;
             StreamGate g = make_stream_gate(op, psi, rows, rows, 1, 1, K, kst);
-            const long long items = (long long)(rows >> g.nfix);
-            const int blocks = (int)std::max<long long>(1, std::min<long long>((items + 255) / 256, nblk));
-            dim3 grid(blocks, nb);
-            adjoint1q_stream<<<grid, 256, 0, st>>>(g, lam, rows, c->wTrPart.as<double>(), op.n_params > 0 ? 1 : 0);
+            const int want_w = op.n_params > 0 ? 1 : 0;
+            int blocks, width;
+            if (op.dim == 2) {
+                const long long items = (long long)(rows >> g.nfix);
+                blocks = (int)std::max<long long>(1, std::min<long long>((items + 255) / 256, nblk));
+                width = 8;
+                adjoint1q_stream<<<dim3(blocks, nb), 256, 0, st>>>(g, lam, rows, c->wTrPart.as<double>(), want_w);
+            } else {
+                const long long items = (long long)(rows >> 2);
+                blocks = (int)std::max<long long>(1, std::min<long long>((items + 127) / 128, nblk));
+                width = 32;
+                adjoint2q_stream<<<dim3(blocks, nb), 128, 0, st>>>(g, lam, rows, c->wTrPart.as<double>(), want_w);
+            }
             c->launches++;
-            if (op.n_params > 0) {
-                sum_partials<<<nb, 32, 0, st>>>(c->wTrPart.as<double>(), blocks, 8, 1.0, reinterpret_cast<double*>(c->wOmega.p), 8);
-                grad_from_w<<<nb, 32, 0, st>>>(c->wOmega.as<cplx>(), c->wDKtab.as<cplx>(), c->dkern_total, op.dkern_off, op.n_params,
-                                               op.param_start, c->n_params, 2.0, d_grad + (size_t)b0 * c->n_params);
-                c->launches += 2;
+            if (want_w) {
+                sum_partials<<<nb, 32, 0, st>>>(c->wTrPart.as<double>(), blocks, width, 1.0,
+                                                reinterpret_cast<double*>(c->wWPart.as<cplx>() + op.w_off), 2 * c->w_total);
+                c->launches++;
             }
         }
+        // dL_p = sum dK_p W  (same contraction as the unitary path), grad_p = 2 Re dL_p  (…Base.cpp:1180-1186)
+        double* dummy_tr = c->wTrPart.as<double>() + (size_t)slice * nblk * 32;
+        reduce_partials<<<nb, 128, 0, st>>>(dummy_tr, 0, c->wWPart.as<cplx>(), c->w_total, c->dOps.as<DevOp>(), c->dParamOp.as<int>(),
+                                            c->dParamOp.as<int>() + std::max(c->n_params, 1), c->wDKtab.as<cplx>(), c->dkern_total,
+                                            c->n_params, 1, c->wTraces.as<double>());
+        grad_from_traces<<<nb, 128, 0, st>>>(c->wTraces.as<double>(), c->n_params, 2.0, d_grad + (size_t)b0 * c->n_params);
+        c->launches += 2;
         CUDA_TRY(cudaGetLastError());
     }
     return SQGPU_OK;

@@ -29,6 +29,17 @@ def eng(sq):
     e.close()
 
 
+@pytest.fixture(params=["fused", "raw"])
+def plan_mode(request, monkeypatch):
+    """run with the block planner (default) and with SQGPU_NO_FUSE=1 (every gate stays a raw op), so both the fused
+    4x4/2x2 block path and the generic controlled / dense path of the executor are checked against the oracle"""
+    if request.param == "raw":
+        monkeypatch.setenv("SQGPU_NO_FUSE", "1")
+    else:
+        monkeypatch.delenv("SQGPU_NO_FUSE", raising=False)
+    return request.param
+
+
 # ---- single gates (Gate::apply_to, Gate::apply_derivative_to_precomputed) ---------------------------------------
 
 @pytest.mark.parametrize("name", H.ONE_Q + H.CTRL + H.TWO_T + ["CCX", "CSWAP"])
@@ -71,7 +82,7 @@ def test_general_block_every_placement(eng, port, k):
 # ---- whole circuits (Gates_block::apply_to / apply_derivate_to) --------------------------------------------------
 
 @pytest.mark.parametrize("n,cols", [(2, 4), (3, 8), (5, 32), (5, 7), (6, 1), (8, 3), (9, 1), (10, 16)])
-def test_circuit_apply_matches_oracle(eng, port, n, cols):
+def test_circuit_apply_matches_oracle(eng, port, plan_mode, n, cols):
     c = H.random_circuit(n, 40, seed=n * 100 + cols, general_k=(2, 3) if n >= 4 else (2,), nested=True)
     d, pool = c.descriptors()
     P = c.get_Parameter_Num()
@@ -88,7 +99,7 @@ def test_circuit_apply_matches_oracle(eng, port, n, cols):
 
 
 @pytest.mark.parametrize("n,cols", [(3, 8), (5, 7), (6, 1), (7, 5)])
-def test_circuit_derivative_matches_oracle(eng, port, n, cols):
+def test_circuit_derivative_matches_oracle(eng, port, plan_mode, n, cols):
     """P materialised derivative matrices, incl. the zero rows of controlled gates (apply_kernel_to_input.cpp:93-97)"""
     c = H.random_circuit(n, 25, seed=n * 10 + cols, general_k=(2,), nested=True)
     d, pool = c.descriptors()
@@ -120,7 +131,7 @@ def test_column_subset_invariance(eng):
 
 @pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 9])
 @pytest.mark.parametrize("n,levels", [(4, 2), (5, 1)])
-def test_cost_and_gradient_match_oracle(sq, port, variant, n, levels):
+def test_cost_and_gradient_match_oracle(sq, port, plan_mode, variant, n, levels):
     c = H.adaptive_circuit(n, levels)
     d, pool = c.descriptors()
     P = c.get_Parameter_Num()
@@ -143,7 +154,7 @@ def test_cost_and_gradient_match_oracle(sq, port, variant, n, levels):
 
 
 @pytest.mark.parametrize("variant", [0, 1, 2])
-def test_trace_offset_rectangular(sq, port, variant):
+def test_trace_offset_rectangular(sq, port, plan_mode, variant):
     """rectangular Umtx + trace_offset, incl. the f0 < 1e-8 known-answer test
     (tests/decomposition/test_optmization_problem_combined.py:123-184)"""
     n, off, C = 6, 17, 23
@@ -168,7 +179,7 @@ def test_trace_offset_rectangular(sq, port, variant):
     assert close_rel(f2, f_ref2) and close_rel(g2, g_ref2)
 
 
-def test_mixed_gate_circuit_gradient(sq, port):
+def test_mixed_gate_circuit_gradient(sq, port, plan_mode):
     """gradient through every parametric gate family incl. the 4x4 RXX/RYY/RZZ kernels and constant gates"""
     n = 5
     c = H.random_circuit(n, 60, seed=11, general_k=(2, 3))
