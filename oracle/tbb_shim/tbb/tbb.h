@@ -20,6 +20,10 @@
 inline void* scalable_aligned_malloc(size_t size, size_t align) {
     void* p = nullptr;
     if (size == 0) size = align;
+    // TBB's scalable allocator hands out whole cache lines. The reference relies on that slack: the Hilbert-Schmidt
+    // correction-2 path writes a 4th element into a Matrix(1,3) (Optimization_Interface.cpp:719-726 vs :1380), which
+    // lands in the padding under TBB but would corrupt the glibc heap with an exact-size allocation.
+    size = (size + align - 1) / align * align;
     if (posix_memalign(&p, align < sizeof(void*) ? sizeof(void*) : align, size) != 0) return nullptr;
     return p;
 }

@@ -8,6 +8,7 @@ Public surface = the reference's own names for this path (squander/__init__.py:1
 handle) and ``Variational_Quantum_Eigensolver`` (state-vector cost path).
 """
 from . import abi
+from . import qasm
 from .circuit import Circuit
 from .engine import Engine
 from .decomposition import N_Qubit_Decomposition_adaptive, N_Qubit_Decomposition_custom
@@ -16,5 +17,5 @@ from .decomposition import N_Qubit_Decomposition_adaptive, N_Qubit_Decomposition
 qgd_Circuit = Circuit
 
 __all__ = [
-    "abi", "Circuit", "qgd_Circuit", "Engine", "N_Qubit_Decomposition_adaptive", "N_Qubit_Decomposition_custom",
+    "abi", "qasm", "Circuit", "qgd_Circuit", "Engine", "N_Qubit_Decomposition_adaptive", "N_Qubit_Decomposition_custom",
 ]

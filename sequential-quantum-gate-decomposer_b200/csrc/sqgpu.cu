@@ -169,6 +169,45 @@ __global__ void fp64_fma_burn(double* out, int iters, double m) {
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// FP64 tensor-core (DMMA m8n8k4) burn: 4 independent accumulator fragments per warp
+__global__ void fp64_dmma_burn(double* out, int iters) {
+    double a = threadIdx.x * 1e-3 + 1.0, b = 1.0 - threadIdx.x * 1e-4;
+    double c[4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) c[i][0] = c[i][1] = 0.0;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s += c[i][0] + c[i][1];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// both pipes at once: does DMMA run beside DFMA?
+__global__ void fp64_mixed_burn(double* out, int iters, double m) {
+    double a = threadIdx.x * 1e-3 + 1.0, b = 1.0 - threadIdx.x * 1e-4;
+    double c[2][2] = {{0, 0}, {0, 0}};
+    double f[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) f[i] = threadIdx.x * 1e-3 + i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+#pragma unroll
+        for (int i = 0; i < 16; ++i) f[i] = fma(f[i], m, 1e-9);
+    }
+    double s = c[0][0] + c[0][1] + c[1][0] + c[1][1];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += f[i];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 int n_trace_types_of(int variant) {
     switch (variant) {
         case SQGPU_FROBENIUS_NORM_CORRECTION1:
@@ -1325,6 +1364,29 @@ int sqgpu_fp64_fma_peak(sqgpu_handle_t c, double* tflops) {
         c->launches++;
         const double flops = 2.0 * 16 * (double)iters * blocks * thr;
         if (rep > 0) best = std::max(best, flops / (ms * 1e-3) * 1e-12);
+    }
+    // side measurement (stderr, when SQGPU_VERBOSE=1): FP64 tensor-core rate alone and mixed with DFMA
+    const char* vb = getenv("SQGPU_VERBOSE");
+    if (vb && vb[0] == '1') {
+        double best_mma = 0, best_mix = 0;
+        for (int rep = 0; rep < 4; ++rep) {
+            float ms = 0;
+            cudaEventRecord(e0, c->stream);
+            fp64_dmma_burn<<<blocks, thr, 0, c->stream>>>(c->wCost.as<double>(), iters);
+            cudaEventRecord(e1, c->stream);
+            cudaEventSynchronize(e1);
+            cudaEventElapsedTime(&ms, e0, e1);
+            const double fl = 2.0 * 256 * 4 * (double)iters * blocks * (thr / 32);
+            if (rep > 0) best_mma = std::max(best_mma, fl / (ms * 1e-3) * 1e-12);
+            cudaEventRecord(e0, c->stream);
+            fp64_mixed_burn<<<blocks, thr, 0, c->stream>>>(c->wCost.as<double>(), iters, 1.0000001);
+            cudaEventRecord(e1, c->stream);
+            cudaEventSynchronize(e1);
+            cudaEventElapsedTime(&ms, e0, e1);
+            const double fl2 = (2.0 * 256 * 2 * (thr / 32) + 2.0 * 16 * thr) * (double)iters * blocks;
+            if (rep > 0) best_mix = std::max(best_mix, fl2 / (ms * 1e-3) * 1e-12);
+        }
+        fprintf(stderr, "[sqgpu] FP64 peaks: DFMA %.2f TFLOP/s, DMMA m8n8k4 %.2f TFLOP/s, DFMA+DMMA mixed %.2f TFLOP/s\n", best, best_mma, best_mix);
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);

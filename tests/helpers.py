@@ -159,3 +159,41 @@ def hea_zyz_circuit(n, layers, inner_blocks=1):
                 pair(cq + 1, cq + 2, cq + 2, cq + 1)
             pair(cq + 1, cq, cq + 1, cq)
     return c
+
+
+def pauli_exponent_circuit(alpha=0.6217 * np.pi):
+    """the 5-qubit target circuit of the reference's tests/decomposition/test_parametric_circuit.py:50-115, built with
+    the Qiskit -> SQUANDER conventions of Qiskit_IO.py (cx(a, b): control a, target b; rotation angles stored halved).
+    Returns (circuit, parameters)."""
+    c = sq.Circuit(5)
+    p = []
+
+    def h(q):
+        c.add_H(q)
+
+    def cx(a, b):
+        c.add_CNOT(b, a)
+
+    def rx(t, q):
+        c.add_RX(q)
+        p.append(t / 2)
+
+    def rz(t, q):
+        c.add_RZ(q)
+        p.append(t / 2)
+
+    h(1); cx(1, 2)
+    rx(np.pi / 2, 0); rx(np.pi / 2, 1); cx(2, 4); cx(0, 1)
+    rx(np.pi / 2, 0); h(2); cx(0, 2)
+    rx(np.pi / 2, 0); h(3); rz(alpha, 4); cx(0, 3)
+    h(0); rz(-alpha, 1); cx(2, 4)
+    cx(2, 1); rz(-alpha, 4); cx(3, 1)
+    rz(alpha, 1); cx(0, 1); cx(3, 1); cx(4, 1)
+    rz(-alpha, 1); cx(2, 1)
+    rz(alpha, 1); cx(3, 1); cx(4, 1)
+    rz(alpha, 1); cx(2, 4); cx(0, 1)
+    h(0); cx(3, 1); cx(0, 3)
+    rx(-np.pi / 2, 0); h(3); cx(0, 2)
+    rx(-np.pi / 2, 0); h(2); cx(0, 1)
+    rx(-np.pi / 2, 0); rx(-np.pi / 2, 1); cx(2, 4); cx(1, 2); h(1)
+    return c, np.array(p, dtype=np.float64)

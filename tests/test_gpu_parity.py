@@ -303,3 +303,51 @@ def test_errors_are_reported(sq):
     with pytest.raises(Exception):
         e.cost_batched(np.zeros((1, 5)))  # wrong parameter count
     e.close()
+
+
+# ---- golden fixtures (outputs of the reference's own code, tests/golden/make_golden.py) ---------------------------
+
+import golden_cases as G
+
+
+@pytest.mark.parametrize("name", G.COST_CASES)
+def test_golden_cost_and_gradient(sq, name):
+    """BASELINE configs[0] (data/Umtx.mat, adaptive L = 1..5) and configs[1] (data/19CNOT.qasm, HS-test cost) among them"""
+    c = G.load(name)
+    e = sq.Engine(0)
+    e.upload_matrix(c.U)
+    e.set_circuit_raw(c.descs, c.pool, c.P, c.n)
+    for vi, v in enumerate(c.variants):
+        e.set_cost(int(v), c.trace_offset, float(c.prev[0]))
+        f, g = e.cost_grad_batched(c.params)
+        fc = e.cost_batched(c.params)
+        assert close_rel(f, c.cost[vi]) and close_rel(fc, c.cost[vi])
+        for pi in range(len(c.params)):
+            assert close_rel(g[pi], c.grad[vi, pi])
+    e.close()
+
+
+@pytest.mark.parametrize("name", G.MATRIX_CASES)
+def test_golden_matrices(sq, name):
+    c = G.load(name)
+    e = sq.Engine(0)
+    e.set_circuit_raw(c.descs, c.pool, c.P, c.n)
+    m = c.U.copy()
+    e.apply(c.params[0], m)
+    assert np.abs(m - c.applied).max() < ENTRY_TOL
+    d = np.array(e.apply_derivative(c.params[0], c.U))
+    assert np.abs(d[c.deriv_idx] - c.deriv).max() < ENTRY_TOL
+    e.close()
+
+
+def test_golden_general_blocks(sq):
+    c = G.load("GENERAL_n5")
+    e = sq.Engine(0)
+    e.set_circuit_raw(c.descs, c.pool, c.P, c.n)
+    v = c.state_in.copy()
+    e.apply(c.params, v)
+    assert np.abs(v - c.state_out).max() < ENTRY_TOL
+    m = c.U.copy()
+    e.apply(c.params, m)
+    assert np.abs(m - c.applied).max() < ENTRY_TOL
+    e.close()
