@@ -242,6 +242,12 @@ class Ref:
         L.sqref_decomp_cost_batched.argtypes = [C.c_void_p, _dp, C.c_int, C.c_int, _dp]
         L.sqref_decomp_cost_grad.argtypes = [C.c_void_p, _dp, C.c_int, _dp, _dp]
         L.sqref_traces.argtypes = [_dp, C.c_int, C.c_int, C.c_int, C.c_int, _dp]
+        L.sqref_vqe_create.restype = C.c_void_p
+        L.sqref_vqe_create.argtypes = [C.c_int, C.c_int, C.c_int, _ip, _ip, _dp, C.c_int, C.c_int, C.c_int, _gp, C.c_int]
+        L.sqref_vqe_free.argtypes = [C.c_void_p]
+        L.sqref_vqe_param_num.argtypes = [C.c_void_p]
+        L.sqref_vqe_energy.argtypes = [C.c_void_p, _dp, C.c_int, _dp]
+        L.sqref_vqe_energy_grad.argtypes = [C.c_void_p, _dp, C.c_int, _dp, _dp]
 
     def _err(self):
         return self.lib.sqref_last_error().decode("utf-8", "replace")
@@ -251,6 +257,9 @@ class Ref:
 
     def decomp(self, umtx, qbit_num, descs, pool=None):
         return RefDecomp(self, umtx, qbit_num, descs, pool)
+
+    def vqe(self, qbit_num, indptr, indices, data, ansatz="HEA_ZYZ", layers=1, inner_blocks=1, descs=None):
+        return RefVQE(self, qbit_num, indptr, indices, data, ansatz, layers, inner_blocks, descs)
 
 
 class RefCircuit:
@@ -339,4 +348,45 @@ class RefDecomp:
         g = np.zeros(max(p.size, 1))
         if self.ref.lib.sqref_decomp_cost_grad(self.h, _dptr(p), p.size, _dptr(out), _dptr(g)):
             raise Exception("ref: cost_grad failed: " + self.ref._err())
+        return float(out[0]), g[: p.size]
+
+
+class RefVQE:
+    """Variational_Quantum_Eigensolver_Base with its own generated ansatz (or a custom gate structure)"""
+
+    def __init__(self, ref, qbit_num, indptr, indices, data, ansatz, layers, inner_blocks, descs):
+        self.ref = ref
+        ip = np.ascontiguousarray(indptr, dtype=np.int32)
+        ix = np.ascontiguousarray(indices, dtype=np.int32)
+        v = _c128(data)
+        if descs is not None:
+            d, dptr = _descs(descs)
+            nd = len(d)
+        else:
+            dptr, nd = None, 0
+        self.h = ref.lib.sqref_vqe_create(qbit_num, len(ip) - 1, v.size, ip.ctypes.data_as(_ip), ix.ctypes.data_as(_ip),
+                                          _dptr(v.view(np.float64)), 1 if ansatz == "HEA_ZYZ" else 0, layers,
+                                          inner_blocks, dptr, nd)
+        if not self.h:
+            raise Exception("ref: vqe_create failed: " + ref._err())
+        self.n_params = ref.lib.sqref_vqe_param_num(self.h)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.ref.lib.sqref_vqe_free(self.h)
+            self.h = None
+
+    def energy(self, params):
+        p = _f64(params)
+        out = np.zeros(1)
+        if self.ref.lib.sqref_vqe_energy(self.h, _dptr(p), p.size, _dptr(out)):
+            raise Exception("ref: vqe_energy failed: " + self.ref._err())
+        return float(out[0])
+
+    def energy_grad(self, params):
+        p = _f64(params)
+        out = np.zeros(1)
+        g = np.zeros(max(p.size, 1))
+        if self.ref.lib.sqref_vqe_energy_grad(self.h, _dptr(p), p.size, _dptr(out), _dptr(g)):
+            raise Exception("ref: vqe_energy_grad failed: " + self.ref._err())
         return float(out[0]), g[: p.size]

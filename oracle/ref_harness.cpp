@@ -286,6 +286,77 @@ int sqref_decomp_cost_grad(void* h, const double* params, int n_params, double* 
     });
 }
 
+// ---- VQE (state-vector) object ---------------------------------------------------------------------------------------
+
+struct RefVQE {
+    Variational_Quantum_Eigensolver_Base* vqe;
+    std::map<std::string, Config_Element> config;
+    std::vector<QGD_Complex16> hdata;
+    std::vector<int> hind, hptr;
+};
+
+// ansatz: 0 HEA, 1 HEA_ZYZ (generate_circuit(layers, inner_blocks)); descs != NULL: custom gate structure instead
+void* sqref_vqe_create(int qbit_num, int n_rows, int nnz, const int* indptr, const int* indices, const double* values,
+                       int ansatz, int layers, int inner_blocks, const sqgpu_gate_desc* descs, int n_descs) {
+    RefVQE* rv = nullptr;
+    int rc = guarded([&] {
+        rv = new RefVQE();
+        rv->hdata.resize(nnz);
+        memcpy(rv->hdata.data(), values, sizeof(QGD_Complex16) * nnz);
+        rv->hind.assign(indices, indices + nnz);
+        rv->hptr.assign(indptr, indptr + n_rows + 1);
+        Matrix_sparse H(rv->hdata.data(), n_rows, n_rows, nnz, rv->hind.data(), rv->hptr.data());
+        rv->vqe = new Variational_Quantum_Eigensolver_Base(H, qbit_num, rv->config, 0);
+        rv->vqe->set_verbose(0);
+        // |0...0> given explicitly: the reference's own initialize_zero_state() offsets a QGD_Complex16* by 2 elements
+        // while counting doubles (…Base.cpp:1269-1274), leaving amplitude 1 uninitialised and overrunning the buffer.
+        Matrix psi0(1 << qbit_num, 1);
+        memset(psi0.get_data(), 0, sizeof(QGD_Complex16) * psi0.size());
+        psi0[0].real = 1.0;
+        rv->vqe->set_initial_state(psi0);
+        if (descs) {
+            Gates_block* blk = new Gates_block(qbit_num);
+            int pos = 0;
+            build_block(blk, descs, n_descs, &pos, qbit_num, nullptr, 0);
+            rv->vqe->set_custom_gate_structure(blk);
+            delete blk;
+        } else {
+            rv->vqe->set_ansatz(ansatz == 1 ? HEA_ZYZ : HEA);
+            rv->vqe->generate_circuit(layers, inner_blocks);
+        }
+    });
+    if (rc != 0) return nullptr;
+    return rv;
+}
+
+void sqref_vqe_free(void* h) {
+    RefVQE* rv = reinterpret_cast<RefVQE*>(h);
+    if (!rv) return;
+    delete rv->vqe;
+    delete rv;
+}
+
+int sqref_vqe_param_num(void* h) { return reinterpret_cast<RefVQE*>(h)->vqe->get_parameter_num(); }
+
+int sqref_vqe_energy(void* h, const double* params, int n_params, double* energy) {
+    return guarded([&] {
+        Matrix_real p(1, n_params);
+        memcpy(p.get_data(), params, sizeof(double) * n_params);
+        *energy = reinterpret_cast<RefVQE*>(h)->vqe->optimization_problem(p);
+    });
+}
+
+int sqref_vqe_energy_grad(void* h, const double* params, int n_params, double* energy, double* grad) {
+    return guarded([&] {
+        Variational_Quantum_Eigensolver_Base* v = reinterpret_cast<RefVQE*>(h)->vqe;
+        Matrix_real p(1, n_params);
+        memcpy(p.get_data(), params, sizeof(double) * n_params);
+        Matrix_real g(1, n_params);
+        v->optimization_problem_combined_non_static(p, v, energy, g);
+        memcpy(grad, g.get_data(), sizeof(double) * n_params);
+    });
+}
+
 // ---- standalone cost functions on a given matrix (N_Qubit_Decomposition_Cost_Function.cpp) -----------------------
 
 // out[0..5]: Re/Im main trace (with offset), Re/Im one-bit-flip sum, Re/Im two-bit-flip sum, as the reference

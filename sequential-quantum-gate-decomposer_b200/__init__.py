@@ -9,6 +9,7 @@ handle) and ``Variational_Quantum_Eigensolver`` (state-vector cost path).
 """
 from . import abi
 from . import qasm
+from . import dist
 from .circuit import Circuit
 from .engine import Engine
 from .decomposition import N_Qubit_Decomposition_adaptive, N_Qubit_Decomposition_custom
@@ -17,5 +18,5 @@ from .decomposition import N_Qubit_Decomposition_adaptive, N_Qubit_Decomposition
 qgd_Circuit = Circuit
 
 __all__ = [
-    "abi", "qasm", "Circuit", "qgd_Circuit", "Engine", "N_Qubit_Decomposition_adaptive", "N_Qubit_Decomposition_custom",
+    "abi", "qasm", "dist", "Circuit", "qgd_Circuit", "Engine", "N_Qubit_Decomposition_adaptive", "N_Qubit_Decomposition_custom",
 ]

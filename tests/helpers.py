@@ -96,6 +96,7 @@ def heisenberg_csr(n, seed=31415, degree=3):
     (examples/VQE/Heisenberg_VQE.py:43-52, tests/VQE/test_VQE.py:26-74; scipy only)."""
     import scipy.sparse as sp
 
+    assert (n * degree) % 2 == 0, "a regular graph needs n * degree even"
     rng = np.random.default_rng(seed)
     # simple deterministic pseudo-random regular graph: pairing model with retries
     while True:

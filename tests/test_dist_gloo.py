@@ -1,0 +1,154 @@
+"""N > 1 host logic on CPU: world_size = 2 over the gloo backend (127.0.0.1 rendezvous). The CUDA engine is replaced by
+a test double built on the C oracle (tests may use the oracle; the product never does), so what is exercised here is
+the sharding plan, the single collective per evaluation and the lock-step results of dist.ShardedCost."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+import helpers as H
+
+abi = H.abi
+
+
+class OracleEngine:
+    """engine double with the Engine methods dist.ShardedCost uses, evaluated by oracle/sq_oracle.c"""
+
+    def __init__(self, device=0):
+        import pyoracle
+
+        self.port = pyoracle.Port()
+        self.variant, self.off, self.cfg = 0, 0, (1.0, 1 / 1.7, 0.5)
+
+    def upload_matrix(self, U):
+        self.U = np.ascontiguousarray(U)
+
+    def set_circuit(self, circuit):
+        self.descs, self.pool = circuit.descriptors()
+        self.P = circuit.get_Parameter_Num()
+        self.n = circuit.qbit_num
+
+    def set_cost(self, variant, trace_offset, prev, c1, c2):
+        self.variant, self.off, self.cfg = variant, trace_offset, (prev, c1, c2)
+
+    def _omega(self):
+        prev, c1, c2 = self.cfg
+        sp = np.sqrt(prev)
+        return {0: (1, 0, 0), 1: (1, sp * c1, 0), 2: (1, sp * c1, sp * c2)}[self.variant]
+
+    def traces_batched(self, params, with_grad):
+        out = np.zeros((len(params), 1 + (self.P if with_grad else 0), 3, 2))
+        w = self._omega()
+        for b, p in enumerate(params):
+            m = self.port.apply_circuit(self.descs, p, self.U, self.pool)
+            out[b, 0] = self.port.traces(m, self.n, self.off).reshape(3, 2)
+            if with_grad:
+                d = self.port.apply_derivate(self.descs, self.P, p, self.U, self.pool)
+                for k in range(self.P):
+                    t = self.port.traces(d[k], self.n, self.off).reshape(3, 2)
+                    out[b, 1 + k, 0] = w[0] * t[0] + w[1] * t[1] + w[2] * t[2]
+        return out
+
+    def cost_from_traces(self, tr, with_grad, cols_total):
+        prev, c1, c2 = self.cfg
+        cost = np.array([self.port.cost_from_traces(self.variant, t[0].reshape(-1), cols_total, prev, c1, c2) for t in tr])
+        if not with_grad:
+            return cost
+        n = float(cols_total)
+        grad = np.zeros((len(tr), self.P))
+        for b, t in enumerate(tr):
+            T, dl = t[0, 0], t[1:, 0]
+            if self.variant <= 2:
+                grad[b] = (1.0 - dl[:, 0] / n) - 1.0
+            elif self.variant == 3:
+                grad[b] = -2.0 / n / n * (T[0] * dl[:, 0] + T[1] * dl[:, 1])
+            else:
+                grad[b] = -2.0 / n / (n + 1) * (T[0] * dl[:, 0] + T[1] * dl[:, 1])
+        return cost, grad
+
+    def cost_batched(self, params):
+        prev, c1, c2 = self.cfg
+        return np.array([self.port.cost(self.descs, p, self.U, self.n, self.variant, self.off, prev, c1, c2, self.pool) for p in params])
+
+    def cost_grad_batched(self, params):
+        prev, c1, c2 = self.cfg
+        res = [self.port.cost_grad(self.descs, self.P, p, self.U, self.n, self.variant, self.off, prev, c1, c2, self.pool) for p in params]
+        return np.array([r[0] for r in res]), np.array([r[1] for r in res])
+
+
+def _worker(rank, world, port_no, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port_no)
+    import torch.distributed as dist
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sq = H.sq
+        n = 4
+        circ = H.adaptive_circuit(n, 1)
+        P = circ.get_Parameter_Num()
+        U = H.random_unitary(1 << n).conj().T.copy()
+        params = H.random_params(P, batch=5)
+        res = {}
+        for mode in ("batch", "columns"):
+            for variant in (0, 2, 3, 9):
+                sc = sq.dist.ShardedCost(U, circ, variant=variant, mode=mode, prev_cost=0.37, engine_factory=OracleEngine)
+                c, g = sc.cost_grad(params)
+                res[(mode, variant)] = (c, g, sc.cost(params))
+        q.put((rank, res))
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def test_shard_plans():
+    d = H.sq.dist
+    for total, world in ((1024, 8), (23, 4), (5, 2), (256, 3)):
+        blocks = [d.column_shard(total, r, world) for r in range(world)]
+        assert blocks[0][0] == 0 and blocks[-1][1] == total
+        assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
+        sizes = [e - b for b, e in blocks]
+        assert max(sizes) - min(sizes) <= 1
+    assert d.trace_pass_variant(abi.HILBERT_SCHMIDT_TEST) == abi.FROBENIUS_NORM
+    assert d.trace_pass_variant(abi.FROBENIUS_NORM_CORRECTION2) == abi.FROBENIUS_NORM_CORRECTION2
+    with pytest.raises(Exception):
+        d.trace_pass_variant(abi.HILBERT_SCHMIDT_TEST_CORRECTION1)
+
+
+def test_world2_gloo_matches_single_process(port):
+    import torch.multiprocessing as mp
+
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port_no = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port_no, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=240) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    n = 4
+    circ = H.adaptive_circuit(n, 1)
+    d, pool = circ.descriptors()
+    P = circ.get_Parameter_Num()
+    U = H.random_unitary(1 << n).conj().T.copy()
+    params = H.random_params(P, batch=5)
+    for key, (c0, g0, cc0) in results[0].items():
+        mode, variant = key
+        c1, g1, cc1 = results[1][key]
+        assert (c0 == c1).all() and (g0 == g1).all() and (cc0 == cc1).all()  # lock-step: identical on every rank
+        for b in range(5):
+            f_ref, g_ref = port.cost_grad(d, P, params[b], U, n, variant, 0, 0.37)
+            assert abs(c0[b] - f_ref) < 1e-12 and abs(cc0[b] - f_ref) < 1e-12
+            assert np.abs(g0[b] - g_ref).max() < 1e-12

@@ -351,3 +351,27 @@ def test_golden_general_blocks(sq):
     e.apply(c.params, m)
     assert np.abs(m - c.applied).max() < ENTRY_TOL
     e.close()
+
+
+# ---- VQE state-vector path (Variational_Quantum_Eigensolver_Base::optimization_problem{,_combined}) ----------------
+
+@pytest.mark.parametrize("n,layers", [(4, 2), (8, 2), (12, 1)])
+def test_vqe_energy_and_gradient(sq, port, n, layers):
+    indptr, indices, data = H.heisenberg_csr(n)
+    c = H.hea_zyz_circuit(n, layers)
+    d, pool = c.descriptors()
+    P = c.get_Parameter_Num()
+    psi0 = np.zeros(1 << n, dtype=np.complex128)
+    psi0[0] = 1.0
+    e = sq.Engine(0)
+    e.upload_matrix(psi0)
+    e.set_circuit(c)
+    e.set_hamiltonian_csr(indptr, indices, data)
+    ps = H.random_params(P, seed=21, batch=3)
+    en = e.vqe_energy_batched(ps)
+    en2, gr = e.vqe_energy_grad_batched(ps)
+    for b in range(3 if n < 12 else 1):
+        e_ref, g_ref = port.vqe_energy_grad(d, P, ps[b], psi0, indptr, indices, data)
+        assert close_rel(en[b], e_ref) and close_rel(en2[b], e_ref)
+        assert close_rel(gr[b], g_ref)
+    e.close()

@@ -148,3 +148,24 @@ def test_batched_cost_matches_scalar(ref):
     fb = dec.cost_batched(ps)
     for b in range(5):
         assert abs(fb[b] - dec.cost(ps[b])) < 1e-14
+
+
+@pytest.mark.parametrize("n,layers", [(4, 2), (6, 2)])
+def test_vqe_energy_and_gradient_match_reference(port, ref, n, layers):
+    """Heisenberg CSR Hamiltonian + the reference's own HEA_ZYZ ansatz generator (…Base.cpp:1358-1416): energy and
+    gradient of Variational_Quantum_Eigensolver_Base vs the port; also pins helpers.hea_zyz_circuit to that generator."""
+    indptr, indices, data = H.heisenberg_csr(n)
+    v = ref.vqe(n, indptr, indices, data, "HEA_ZYZ", layers, 1)
+    c = H.hea_zyz_circuit(n, layers)
+    d, pool = c.descriptors()
+    P = c.get_Parameter_Num()
+    assert v.n_params == P
+    p = H.random_params(P, seed=21)
+    psi0 = np.zeros(1 << n, dtype=np.complex128)
+    psi0[0] = 1.0
+    e_ref, g_ref = v.energy_grad(p)
+    assert abs(v.energy(p) - e_ref) < 1e-12
+    e, g = port.vqe_energy_grad(d, P, p, psi0, indptr, indices, data)
+    assert abs(e - e_ref) < 1e-12 * max(1.0, abs(e_ref))
+    assert np.abs(g - g_ref).max() < 1e-12 * max(1.0, np.abs(g_ref).max())
+    assert abs(port.vqe_energy(d, p, psi0, indptr, indices, data) - e_ref) < 1e-12 * max(1.0, abs(e_ref))
