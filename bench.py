@@ -287,16 +287,13 @@ def single_gate_microbench(sq, eng, torch, peak_gbs):
                     buf.data_ptr(), rows, cols, cols, stream)
             for _ in range(3):
                 abi.check(eng.lib, eng.lib.sqgpu_apply_gate_dev(*args))
-            e0 = torch.cuda.Event(enable_timing=True)
-            e1 = torch.cuda.Event(enable_timing=True)
-            reps = 10
             torch.cuda.synchronize()
-            e0.record()
+            eng.last_kernel_time()  # reset the library's per-kernel CUDA-event ring
+            reps = 10
             for _ in range(reps):
                 abi.check(eng.lib, eng.lib.sqgpu_apply_gate_dev(*args))
-            e1.record()
             torch.cuda.synchronize()
-            ms = e0.elapsed_time(e1) / reps  # includes the ~2 tiny descriptor copies per call
+            _, ms, nl = eng.last_kernel_time()  # events bracket the streaming kernel only, on the launching stream
             touched = rows * cols / (2 if c >= 0 else 1)
             gbs = 32.0 * touched / (ms * 1e-3) / 1e9
             out.append({"gate": name, "target": t, "control": c, "rows": rows, "cols": cols, "GB/s": round(gbs, 1),

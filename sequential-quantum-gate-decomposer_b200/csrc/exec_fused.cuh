@@ -10,8 +10,10 @@
 // and, for the gradient, the P materialised derivative matrices of Gates_block::apply_derivate_to
 // (gates/Gates_block.cpp:1011-1150) by an adjoint sweep: with a_k the column after k ops and beta_k the row functional
 // e_r^T G_{N-1}...G_{k+1}, the derivative of the trace term wrt a parameter of op k is sum_groups beta_k^T dK a_k.
-// The executor accumulates W_k[r][c] = sum_{groups, columns} beta_k[r] a_k[c]; reduce_partials contracts W_k with the
-// derivative kernels dK (for fused blocks: the product-rule derivative of the block matrix, gate_kernels.cuh).
+// The executor accumulates W'_k[r][c] = sum_{groups, columns} beta_k[r] p_k[c] with p_k = K a_k the column AFTER the op
+// (so the accumulation does not wait for the un-applied column); since a_k = K^dagger p_k, the wanted
+// W_k[r][c] = sum beta_k[r] a_k[c] equals (W'_k conj(K))[r][c] and reduce_partials contracts W'_k with dK K^dagger
+// (for fused blocks dK is the product-rule derivative of the block matrix, gate_kernels.cuh).
 // Inactive (control = 0) pairs contribute nothing, which is exactly the reference's "zero rows in the derivative"
 // convention (apply_kernel_to_input.cpp:93-97).
 //
@@ -77,6 +79,25 @@ __device__ __forceinline__ int phys_row(int i) {
         return i ^ ((__popc((unsigned)i & m_lo) & 1) | ((__popc((unsigned)i & m_hi) & 1) << 1));
     }
     return i ^ (((i >> 3) & 1) * 7);
+}
+
+// shared-memory element indices of the 4 rows of a two-qubit group: base | {0, b0, b1, b0|b1}. For CT = 4 the swizzle
+// parity of (base | x) splits into parity(base) ^ parity(x), so one POPC per group suffices.
+template <int LOG_CT>
+__device__ __forceinline__ void group4_addr(int base, int b0, int b1, int c, int px0, int px1, int& e0, int& e1, int& e2, int& e3) {
+    constexpr int CT = 1 << LOG_CT;
+    if (LOG_CT == 2) {
+        const int pb = __popc(base >> 1) & 1;
+        e0 = ((base) ^ pb) * CT + c;
+        e1 = ((base | b0) ^ (pb ^ px0)) * CT + c;
+        e2 = ((base | b1) ^ (pb ^ px1)) * CT + c;
+        e3 = ((base | b0 | b1) ^ (pb ^ px0 ^ px1)) * CT + c;
+    } else {
+        e0 = phys_row<LOG_CT>(base) * CT + c;
+        e1 = phys_row<LOG_CT>(base | b0) * CT + c;
+        e2 = phys_row<LOG_CT>(base | b1) * CT + c;
+        e3 = phys_row<LOG_CT>(base | b0 | b1) * CT + c;
+    }
 }
 
 // reduce 8 per-lane doubles over the warp; lanes with (lane & 3) == 0 end up holding the total of value
@@ -219,12 +240,13 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
 #pragma unroll
                     for (int e = 0; e < 16; ++e) M[e] = km[e];
                     const int b0 = 1 << s.q0, b1 = 1 << s.q1;
+                    const int px0 = __popc(b0 >> 1) & 1, px1 = __popc(b1 >> 1) & 1;
                     const int nitems = (rows >> 2) << LOG_CT;
                     for (int item = tid; item < nitems; item += nthr) {
                         const int c = item & (CT - 1);
                         const int base = insert_zero(insert_zero(item >> LOG_CT, s.q0), s.q1);
-                        const int e0 = phys_row<LOG_CT>(base) * CT + c, e1 = phys_row<LOG_CT>(base | b0) * CT + c;
-                        const int e2 = phys_row<LOG_CT>(base | b1) * CT + c, e3 = phys_row<LOG_CT>(base | b0 | b1) * CT + c;
+                        int e0, e1, e2, e3;
+                        group4_addr<LOG_CT>(base, b0, b1, c, px0, px1, e0, e1, e2, e3);
                         const cplx v0 = sa[e0], v1 = sa[e1], v2 = sa[e2], v3 = sa[e3];
                         sa[e0] = cfma(M[3], v3, cfma(M[2], v2, cfma(M[1], v1, cmul(M[0], v0))));
                         sa[e1] = cfma(M[7], v3, cfma(M[6], v2, cfma(M[5], v1, cmul(M[4], v0))));
@@ -418,35 +440,31 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                             W[e] = czero();
                         }
                         const int b0 = 1 << s.q0, b1 = 1 << s.q1;
+                        const int px0 = __popc(b0 >> 1) & 1, px1 = __popc(b1 >> 1) & 1;
                         const int nitems = (rows >> 2) << LOG_CT;
                         for (int item = tid; item < nitems; item += nthr) {
                             const int c = item & (CT - 1);
                             const int base = insert_zero(insert_zero(item >> LOG_CT, s.q0), s.q1);
-                            const int e0 = phys_row<LOG_CT>(base) * CT + c, e1 = phys_row<LOG_CT>(base | b0) * CT + c;
-                            const int e2 = phys_row<LOG_CT>(base | b1) * CT + c, e3 = phys_row<LOG_CT>(base | b0 | b1) * CT + c;
-                            cplx p[4] = {sa[e0], sa[e1], sa[e2], sa[e3]};  // column after the block
-                            cplx b[4] = {sb[e0], sb[e1], sb[e2], sb[e3]};  // row functional after the block
-                            cplx a[4];
-#pragma unroll
-                            for (int cc = 0; cc < 4; ++cc)  // a = M^dagger p
-                                a[cc] = cfmac(M[12 + cc], p[3], cfmac(M[8 + cc], p[2], cfmac(M[4 + cc], p[1], cfmac(M[cc], p[0], czero()))));
-                            sa[e0] = a[0];
-                            sa[e1] = a[1];
-                            sa[e2] = a[2];
-                            sa[e3] = a[3];
+                            int e0, e1, e2, e3;
+                            group4_addr<LOG_CT>(base, b0, b1, c, px0, px1, e0, e1, e2, e3);
+                            const cplx p[4] = {sa[e0], sa[e1], sa[e2], sa[e3]};  // column after the block
+                            const cplx b[4] = {sb[e0], sb[e1], sb[e2], sb[e3]};  // row functional after the block
                             if (has_w) {
 #pragma unroll
                                 for (int r = 0; r < 4; ++r)
 #pragma unroll
-                                    for (int cc = 0; cc < 4; ++cc) W[r * 4 + cc] = cfma(b[r], a[cc], W[r * 4 + cc]);
+                                    for (int cc = 0; cc < 4; ++cc) W[r * 4 + cc] = cfma(b[r], p[cc], W[r * 4 + cc]);
                             }
-#pragma unroll
-                            for (int cc = 0; cc < 4; ++cc)  // beta' = M^T beta
-                                p[cc] = cfma(M[12 + cc], b[3], cfma(M[8 + cc], b[2], cfma(M[4 + cc], b[1], cmul(M[cc], b[0]))));
-                            sb[e0] = p[0];
-                            sb[e1] = p[1];
-                            sb[e2] = p[2];
-                            sb[e3] = p[3];
+                            // a = M^dagger p
+                            sa[e0] = cfmac(M[12], p[3], cfmac(M[8], p[2], cfmac(M[4], p[1], cfmac(M[0], p[0], czero()))));
+                            sa[e1] = cfmac(M[13], p[3], cfmac(M[9], p[2], cfmac(M[5], p[1], cfmac(M[1], p[0], czero()))));
+                            sa[e2] = cfmac(M[14], p[3], cfmac(M[10], p[2], cfmac(M[6], p[1], cfmac(M[2], p[0], czero()))));
+                            sa[e3] = cfmac(M[15], p[3], cfmac(M[11], p[2], cfmac(M[7], p[1], cfmac(M[3], p[0], czero()))));
+                            // beta' = M^T beta
+                            sb[e0] = cfma(M[12], b[3], cfma(M[8], b[2], cfma(M[4], b[1], cmul(M[0], b[0]))));
+                            sb[e1] = cfma(M[13], b[3], cfma(M[9], b[2], cfma(M[5], b[1], cmul(M[1], b[0]))));
+                            sb[e2] = cfma(M[14], b[3], cfma(M[10], b[2], cfma(M[6], b[1], cmul(M[2], b[0]))));
+                            sb[e3] = cfma(M[15], b[3], cfma(M[11], b[2], cfma(M[7], b[1], cmul(M[3], b[0]))));
                         }
                         if (has_w) warp_store_w<16>(W, wslot, lane);
                     } else {
@@ -464,10 +482,10 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                             sa[e0] = a0;
                             sa[e1] = a1;
                             if (has_w) {
-                                W[0] = cfma(b0, a0, W[0]);
-                                W[1] = cfma(b0, a1, W[1]);
-                                W[2] = cfma(b1, a0, W[2]);
-                                W[3] = cfma(b1, a1, W[3]);
+                                W[0] = cfma(b0, p0, W[0]);
+                                W[1] = cfma(b0, p1, W[1]);
+                                W[2] = cfma(b1, p0, W[2]);
+                                W[3] = cfma(b1, p1, W[3]);
                             }
                             sb[e0] = cfma(k10, b1, cmul(k00, b0));
                             sb[e1] = cfma(k11, b1, cmul(k01, b0));
@@ -495,10 +513,10 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                             sa[e0] = a0;
                             sa[e1] = a1;
                             if (has_w) {
-                                W[0] = cfma(b0, a0, W[0]);
-                                W[1] = cfma(b0, a1, W[1]);
-                                W[2] = cfma(b1, a0, W[2]);
-                                W[3] = cfma(b1, a1, W[3]);
+                                W[0] = cfma(b0, p0, W[0]);
+                                W[1] = cfma(b0, p1, W[1]);
+                                W[2] = cfma(b1, p0, W[2]);
+                                W[3] = cfma(b1, p1, W[3]);
                             }
                             sb[e0] = cfma(k10, b1, cmul(k00, b0));
                             sb[e1] = cfma(k11, b1, cmul(k01, b0));
@@ -535,7 +553,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                                 sb[addr[ro]] = bacc;
                                 if (has_w && dim == 4) {
 #pragma unroll
-                                    for (int r2 = 0; r2 < 4; ++r2) wl[r2 * 4 + ro] = cfma(bv[r2], acc, wl[r2 * 4 + ro]);
+                                    for (int r2 = 0; r2 < 4; ++r2) wl[r2 * 4 + ro] = cfma(bv[r2], pv[ro], wl[r2 * 4 + ro]);
                                 }
                             }
                         }

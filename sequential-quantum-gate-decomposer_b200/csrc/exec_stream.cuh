@@ -33,42 +33,57 @@ struct StreamGate {
     int q[5];
 };
 
-// every thread: one (row pair, column). Consecutive threads walk along a row -> 16 B x 32 coalesced accesses.
+// every thread: UNROLL (row pair, column) items per grid-stride step, all loads issued before the first FMA so that
+// 2 * UNROLL independent 16 B requests are in flight per thread. Consecutive threads walk along a row -> 16 B x 32
+// coalesced accesses.
 template <bool DERIV>
 __global__ void __launch_bounds__(256) gate1q_stream(const StreamGate G) {
+    constexpr int UNROLL = 4;
     const cplx* __restrict__ K = G.K + (size_t)blockIdx.y * G.k_ystride;
     const cplx k00 = K[0], k01 = K[1], k10 = K[2], k11 = K[3];
     cplx* __restrict__ d = G.data + (size_t)blockIdx.y * G.ystride;
     const int nfix = DERIV ? 1 : G.nfix;
     const long long nitems = (long long)(G.rows >> nfix) * G.cols;
-    const int tbit = 1 << G.target;
-    for (long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x; item < nitems;
-         item += (long long)gridDim.x * blockDim.x) {
-        int g, j;
-        if (G.log_cols >= 0) {
-            g = (int)(item >> G.log_cols);
-            j = (int)(item & (G.cols - 1));
-        } else {
-            g = (int)(item / G.cols);
-            j = (int)(item - (long long)g * G.cols);
+    const size_t tstride = (size_t)(1 << G.target) * G.ld;
+    const int f0 = DERIV ? G.target : G.fix[0], f1 = DERIV ? 30 : G.fix[1], f2 = DERIV ? 30 : G.fix[2];
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long item0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; item0 < nitems; item0 += step * UNROLL) {
+        size_t off[UNROLL];
+        bool ok[UNROLL], act[UNROLL];
+        cplx a0[UNROLL], a1[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const long long item = item0 + u * step;
+            ok[u] = item < nitems;
+            int g = 0, j = 0;
+            if (ok[u]) {
+                if (G.log_cols >= 0) {
+                    g = (int)(item >> G.log_cols);
+                    j = (int)(item & (G.cols - 1));
+                } else {
+                    g = (int)(item / G.cols);
+                    j = (int)(item - (long long)g * G.cols);
+                }
+            }
+            int i0 = insert_zero(insert_zero(insert_zero(g, f0), f1), f2);
+            if (!DERIV) i0 |= G.ctrl_mask;
+            act[u] = !DERIV || (i0 & G.ctrl_mask) == G.ctrl_mask;
+            off[u] = (size_t)i0 * G.ld + j;
+            if (ok[u] && act[u]) {
+                a0[u] = d[off[u]];
+                a1[u] = d[off[u] + tstride];
+            }
         }
-        int i0;
-        if (DERIV) {
-            i0 = insert_zero(g, G.target);
-        } else {
-            i0 = g;
-            for (int f = 0; f < G.nfix; ++f) i0 = insert_zero(i0, G.fix[f]);
-            i0 |= G.ctrl_mask;
-        }
-        cplx* p0 = d + (size_t)i0 * G.ld + j;
-        cplx* p1 = d + (size_t)(i0 | tbit) * G.ld + j;
-        if (!DERIV || (i0 & G.ctrl_mask) == G.ctrl_mask) {
-            const cplx a0 = *p0, a1 = *p1;
-            *p0 = cfma(k01, a1, cmul(k00, a0));
-            *p1 = cfma(k11, a1, cmul(k10, a0));
-        } else {
-            *p0 = czero();
-            *p1 = czero();
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            if (!ok[u]) continue;
+            if (act[u]) {
+                d[off[u]] = cfma(k01, a1[u], cmul(k00, a0[u]));
+                d[off[u] + tstride] = cfma(k11, a1[u], cmul(k10, a0[u]));
+            } else {
+                d[off[u]] = czero();
+                d[off[u] + tstride] = czero();
+            }
         }
     }
 }

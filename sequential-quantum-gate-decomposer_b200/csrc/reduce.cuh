@@ -2,7 +2,9 @@
 //
 //   reduce_partials   : tr_part[y][chunk][6], w_part[y][chunk][w_total]  ->  traces[y][1+P][3][2]
 //                       k = 0: the three trace terms of C(theta) U; k = 1+p: dL_p = sum_{r,c} dK_p[r][c] W[r][c], the
-//                       derivative of the functional L = sum_t omega_t T_t (stored in slot t = 0).
+//                       derivative of the functional L = sum_t omega_t T_t (stored in slot t = 0). The executor stores
+//                       W' = sum beta p^T (p = column after the op), W = W' conj(K), hence
+//                       dL_p = sum_{r,r'} W'[r][r'] (dK_p K^dagger)[r][r'].
 //   cost_from_traces  : calculate_cost_function (decomposition/Optimization_Interface.cpp:677-735) and the gradient
 //                       component formulas (Optimization_Interface.cpp:1397-1458) on (possibly rank-summed) traces.
 //   make_omega        : weights of the second pass for the Hilbert-Schmidt-with-corrections variants.
@@ -17,7 +19,8 @@ __host__ __device__ __forceinline__ size_t tr_index(int y, int k, int n_k, int t
 
 __global__ void reduce_partials(const double* __restrict__ tr_part, int nchunks, const cplx* __restrict__ w_part,
                                 int w_total, const DevOp* __restrict__ ops, const int* __restrict__ param_op,
-                                const int* __restrict__ param_slot, const cplx* __restrict__ dktab, int dkern_total, int n_params, int with_grad,
+                                const int* __restrict__ param_slot, const cplx* __restrict__ dktab, int dkern_total,
+                                const cplx* __restrict__ ktab, int kern_total, int n_params, int with_grad,
                                 double* __restrict__ traces) {
     const int y = blockIdx.x;
     const int n_k = 1 + (with_grad ? n_params : 0);
@@ -31,12 +34,17 @@ __global__ void reduce_partials(const double* __restrict__ tr_part, int nchunks,
         const DevOp op = ops[param_op[p]];
         const int d2 = op.dim * op.dim;
         const cplx* dk = dktab + (size_t)y * dkern_total + op.dkern_off + param_slot[p] * d2;
+        const cplx* kk = ktab + (size_t)y * kern_total + op.kern_off;  // parametric ops always have a table kernel
+        const int dim = op.dim;
         cplx acc = czero();
-        for (int e = 0; e < d2; ++e) {
-            cplx w = czero();
-            for (int ch = 0; ch < nchunks; ++ch) w = cadd(w, w_part[((size_t)y * nchunks + ch) * w_total + op.w_off + e]);
-            acc = cfma(dk[e], w, acc);
-        }
+        for (int r = 0; r < dim; ++r)
+            for (int r2 = 0; r2 < dim; ++r2) {
+                cplx w = czero();
+                for (int ch = 0; ch < nchunks; ++ch) w = cadd(w, w_part[((size_t)y * nchunks + ch) * w_total + op.w_off + r * dim + r2]);
+                cplx dkk = czero();  // (dK K^dagger)[r][r2] = sum_c dK[r][c] conj(K[r2][c])
+                for (int c = 0; c < dim; ++c) dkk = cfmac(kk[r2 * dim + c], dk[r * dim + c], dkk);
+                acc = cfma(dkk, w, acc);
+            }
         double* dst = traces + tr_index(y, 1 + p, n_k, 0);
         dst[0] = acc.x;
         dst[1] = acc.y;

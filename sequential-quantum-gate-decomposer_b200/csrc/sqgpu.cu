@@ -520,7 +520,7 @@ int run_exec_resident(sqgpu_ctx* c, int batch, bool grad, const cplx* d_omega, d
     if (e != cudaSuccess) return fail(SQGPU_ERR_CUDA, "fused_exec launch failed: %s", cudaGetErrorString(e));
     reduce_partials<<<batch, 128, 0, st>>>(c->wTrPart.as<double>(), p.chunks, c->wWPart.as<cplx>(), c->w_total,
                                            c->dOps.as<DevOp>(), c->dParamOp.as<int>(), c->dParamOp.as<int>() + std::max(c->n_params, 1),
-                                           c->wDKtab.as<cplx>(), c->dkern_total, c->n_params, grad ? 1 : 0, d_traces);
+                                           c->wDKtab.as<cplx>(), c->dkern_total, c->wKtab.as<cplx>(), c->kern_total, c->n_params, grad ? 1 : 0, d_traces);
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     return SQGPU_OK;
@@ -623,11 +623,8 @@ StreamGate make_stream_gate(const DevOp& op, cplx* data, long long ystride, int 
         if ((1 << l) == cols) g.log_cols = l;
     g.target = op.target;
     g.ctrl_mask = op.ctrl_mask;
-    unsigned m = op.ctrl_mask;
-    if (op.dim == 2) m |= 1u << op.target;
-    g.nfix = 0;
-    for (int b = 0; b < 31; ++b)
-        if ((m >> b) & 1) g.fix[g.nfix++] = b;
+    g.nfix = op.nfix;
+    for (int f = 0; f < 6; ++f) g.fix[f] = op.fix[f];
     g.K = K;
     g.k_ystride = k_ystride;
     g.nq = op.nq;
@@ -642,7 +639,8 @@ int launch_stream_gate(sqgpu_ctx* c, const DevOp& op, bool deriv, cplx* data, lo
     if (op.dim == 2) {
         const long long items = (long long)(rows >> (deriv ? 1 : g.nfix)) * cols;
         const int thr = 256;
-        const unsigned blocks = (unsigned)std::min<long long>((items + thr - 1) / thr, (long long)c->sm_count * 64);
+        // 4 items per thread and grid-stride step; cap the grid at 8 CTAs per SM worth of waves x 4
+        const unsigned blocks = (unsigned)std::min<long long>((items + 4 * thr - 1) / (4 * thr), (long long)c->sm_count * 32);
         dim3 grid(std::max(1u, blocks), ysets);
         if (deriv) gate1q_stream<true><<<grid, thr, 0, st>>>(g);
         else gate1q_stream<false><<<grid, thr, 0, st>>>(g);

@@ -92,10 +92,10 @@ __global__ void __launch_bounds__(256) adjoint1q_stream(const StreamGate G, cplx
         d[o0] = a0;
         d[o1] = a1;
         if (want_w) {
-            w00 = cfma(b0, a0, w00);
-            w01 = cfma(b0, a1, w01);
-            w10 = cfma(b1, a0, w10);
-            w11 = cfma(b1, a1, w11);
+            w00 = cfma(b0, p0, w00);  // W' = beta p^T (column after the gate), see reduce_partials
+            w01 = cfma(b0, p1, w01);
+            w10 = cfma(b1, p0, w10);
+            w11 = cfma(b1, p1, w11);
         }
         bt[o0] = cfma(k10, b1, cmul(k00, b0));
         bt[o1] = cfma(k11, b1, cmul(k01, b0));
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(128) adjoint2q_stream(const StreamGate G, cplx
 #pragma unroll
             for (int r = 0; r < 4; ++r)
 #pragma unroll
-                for (int cc = 0; cc < 4; ++cc) W[r * 4 + cc] = cfma(b[r], a[cc], W[r * 4 + cc]);
+                for (int cc = 0; cc < 4; ++cc) W[r * 4 + cc] = cfma(b[r], p[cc], W[r * 4 + cc]);
         }
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc)

@@ -85,7 +85,7 @@ static int vqe_dev(sqgpu_ctx* c, const double* d_params, int batch, bool with_gr
         double* dummy_tr = c->wTrPart.as<double>() + (size_t)slice * nblk * 32;  // slice * 6 doubles, content unused
         reduce_partials<<<nb, 128, 0, st>>>(dummy_tr, 1, c->wWPart.as<cplx>(), c->w_total, c->dOps.as<DevOp>(), c->dParamOp.as<int>(),
                                             c->dParamOp.as<int>() + std::max(c->n_params, 1), c->wDKtab.as<cplx>(), c->dkern_total,
-                                            c->n_params, 1, c->wTraces.as<double>());
+                                            c->wKtab.as<cplx>(), c->kern_total, c->n_params, 1, c->wTraces.as<double>());
         grad_from_traces<<<nb, 128, 0, st>>>(c->wTraces.as<double>(), c->n_params, 2.0, d_grad + (size_t)b0 * c->n_params);
         c->launches += 2;
         CUDA_TRY(cudaGetLastError());
