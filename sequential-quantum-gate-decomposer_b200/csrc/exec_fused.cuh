@@ -63,7 +63,7 @@ struct ExecArgs {
 };
 
 static const int FUSED_THREADS = 256;
-static const int DENSE_STAGE = 1024;  // complex elements (32 x 32)
+static const int DENSE_STAGE = 2304;  // complex elements: real embedding of a 32 x 32 complex kernel, 64 x (64+4) doubles, + row patterns
 
 // ---- shared-memory swizzle -------------------------------------------------------------------------------------
 // rows per 128 B wavefront: 8 / ct. The low log2(8/ct) bits of the physical row select the 16 B bank group set; they
@@ -141,6 +141,89 @@ __device__ __forceinline__ void warp_store_w(const cplx* w, double* slot, int la
         }
         warp_reduce8(v, lane);
         if ((lane & 3) == 0) slot[part * 8 + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)] = v[0];
+    }
+}
+
+// ---- dense k-qubit blocks on the FP64 tensor cores ----------------------------------------------------------------
+// A dense 2^k x 2^k complex kernel acting on a group of 2^k amplitudes is a real (2^(k+1)) x (2^(k+1)) matrix acting on
+// the interleaved {re, im} vector:  Kreal[2r+a][2c+b] = { K.re if a == b;  -K.im if (a,b) = (0,1);  +K.im if (1,0) }.
+// One warp transforms 8 (group, column) items per step with mma.sync.m8n8k4.f64 (DMMA): D[8 x 8 items] +=
+// Kreal[8 x 4] * X[4 x 8 items], RT = 2^(k+1)/8 row tiles x KS = 2^(k+1)/4 k-steps. Replaces the reference's gather /
+// dense matvec / scatter loop for 4-5 qubit kernels (apply_large_kernel_to_input.cpp:160-199,
+// apply_large_kernel_to_input_AVX.cpp:90-136).
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+static const int DMMA_PAD = 4;  // doubles of row padding of the staged real kernel (conflict-free 8 x 4 fragment loads)
+
+// forward application of a raw dense op (no controls) on the tile; requires nitems % 8 == 0. skr: staged real kernel
+// [DIMR][DIMR + DMMA_PAD]; spat: row pattern of local index l. All warps of the CTA take part.
+template <int LOG_CT, int KQ>
+__device__ __forceinline__ void dense_dmma_forward(cplx* sa, const double* skr, const int* spat, const DevOp& op, int rows,
+                                                   int tid, int nthr) {
+    constexpr int CT = 1 << LOG_CT;
+    constexpr int DIMR = 2 << KQ, RT = DIMR / 8, KS = DIMR / 4, LD = DIMR + DMMA_PAD;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
+    double* sad = reinterpret_cast<double*>(sa);
+    const int nitems = (rows >> KQ) << LOG_CT;
+    const int m = lane >> 2, kk = lane & 3;
+    int q[KQ];
+#pragma unroll
+    for (int j = 0; j < KQ; ++j) q[j] = op.q[j];
+    auto item_base = [&](int item, int& c) {
+        c = item & (CT - 1);
+        int base = item >> LOG_CT;
+#pragma unroll
+        for (int j = 0; j < KQ; ++j) base = insert_zero(base, q[j]);
+        return base;
+    };
+    // A fragments: in registers when they fit (k <= 4: 32 doubles), else re-read from shared memory per DMMA
+    constexpr bool A_IN_REGS = (RT * KS <= 32);
+    double areg[A_IN_REGS ? RT * KS : 1];
+    if (A_IN_REGS) {
+#pragma unroll
+        for (int rt = 0; rt < RT; ++rt)
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) areg[rt * KS + ks] = skr[(8 * rt + m) * LD + 4 * ks + kk];
+    }
+    for (int b0 = warp * 8; b0 < nitems; b0 += nwarps * 8) {
+        // B operand: lane holds real component 4*ks + kk of item b0 + m
+        double bfrag[KS];
+        {
+            int c;
+            const int base = item_base(b0 + m, c);
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                const int comp = 4 * ks + kk;
+                const int row = base | spat[comp >> 1];
+                bfrag[ks] = sad[(phys_row<LOG_CT>(row) * CT + c) * 2 + (comp & 1)];
+            }
+        }
+        double d[RT][2];
+#pragma unroll
+        for (int rt = 0; rt < RT; ++rt) {
+            d[rt][0] = 0.0;
+            d[rt][1] = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                const double a = A_IN_REGS ? areg[rt * KS + ks] : skr[(8 * rt + m) * LD + 4 * ks + kk];
+                dmma_m8n8k4(d[rt][0], d[rt][1], a, bfrag[ks]);
+            }
+        }
+        __syncwarp();  // every lane has read its inputs of this 8-item batch before anyone overwrites them
+        // D: lane holds output component 8*rt + m of items b0 + 2*kk and b0 + 2*kk + 1
+        int c0, c1;
+        const int base0 = item_base(b0 + 2 * kk, c0), base1 = item_base(b0 + 2 * kk + 1, c1);
+#pragma unroll
+        for (int rt = 0; rt < RT; ++rt) {
+            const int comp = 8 * rt + m;
+            const int pat = spat[comp >> 1];
+            sad[(phys_row<LOG_CT>(base0 | pat) * CT + c0) * 2 + (comp & 1)] = d[rt][0];
+            sad[(phys_row<LOG_CT>(base1 | pat) * CT + c1) * 2 + (comp & 1)] = d[rt][1];
+        }
+        __syncwarp();
     }
 }
 
@@ -306,10 +389,32 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                     }
                 } else {
                     // dense dim x dim kernel on ascending qubits (apply_large_kernel_to_input.cpp:160-199)
-                    for (int e = tid; e < dim * dim; e += nthr) sk[e] = K[e];
-                    __syncthreads();
                     const int nq = op.nq;
                     const int nitems = (rows >> nq) << LOG_CT;
+                    const bool use_dmma = !deriv && op.ctrl_mask == 0 && nq >= 3 && (nitems & 7) == 0;
+                    if (use_dmma) {
+                        // stage the real embedding of K (padded rows) and the local-index -> row-bit pattern
+                        const int dimr = 2 * dim, ld = dimr + DMMA_PAD;
+                        double* skr = reinterpret_cast<double*>(sk);
+                        int* spat = reinterpret_cast<int*>(skr + dimr * ld);
+                        for (int e = tid; e < dimr * dimr; e += nthr) {
+                            const int r = e / dimr, cidx = e - r * dimr;
+                            const cplx kv = K[(r >> 1) * dim + (cidx >> 1)];
+                            const int a = r & 1, b = cidx & 1;
+                            skr[r * ld + cidx] = (a == b) ? kv.x : (a ? kv.y : -kv.y);
+                        }
+                        for (int l = tid; l < dim; l += nthr) {
+                            int r = 0;
+                            for (int j = 0; j < nq; ++j) r |= ((l >> j) & 1) << op.q[j];
+                            spat[l] = r;
+                        }
+                        __syncthreads();
+                        if (nq == 3) dense_dmma_forward<LOG_CT, 3>(sa, skr, spat, op, rows, tid, nthr);
+                        else if (nq == 4) dense_dmma_forward<LOG_CT, 4>(sa, skr, spat, op, rows, tid, nthr);
+                        else dense_dmma_forward<LOG_CT, 5>(sa, skr, spat, op, rows, tid, nthr);
+                    } else {
+                    for (int e = tid; e < dim * dim; e += nthr) sk[e] = K[e];
+                    __syncthreads();
                     for (int item = tid; item < nitems; item += nthr) {
                         const int c = item & (CT - 1);
                         int base = item >> LOG_CT;
@@ -330,6 +435,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                             for (int j = 0; j < nq; ++j) r |= ((ro >> j) & 1) << op.q[j];
                             sa[phys_row<LOG_CT>(r) * CT + c] = acc;
                         }
+                    }
                     }
                 }
             }

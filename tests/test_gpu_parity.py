@@ -375,3 +375,40 @@ def test_vqe_energy_and_gradient(sq, port, n, layers):
         assert close_rel(en[b], e_ref) and close_rel(en2[b], e_ref)
         assert close_rel(gr[b], g_ref)
     e.close()
+
+
+# ---- dense 3-5 qubit blocks on the FP64 tensor cores (DMMA path of the executor) -----------------------------------
+
+@pytest.mark.parametrize("n,cols", [(7, 128), (8, 16), (10, 4), (6, 1)])
+def test_dense_blocks_in_circuit(sq, port, n, cols):
+    """circuits of GENERAL 3/4/5-qubit kernels interleaved with U3 layers (BASELINE configs[3] structure): apply and
+    cost against the oracle; (6, 1) has too few groups for the tensor-core path and exercises the generic one"""
+    rng = np.random.default_rng(n * 7 + cols)
+    c = sq.Circuit(n)
+    for m in range(9):
+        k = 3 + m % 3
+        if k > n:
+            k = n - 1
+        qs = sorted(int(q) for q in rng.choice(n, k, replace=False))
+        c.add_GENERAL(H.random_unitary(1 << k, seed=2000 + m), qs)
+        for q in range(n):
+            c.add_U3(q)
+    d, pool = c.descriptors()
+    P = c.get_Parameter_Num()
+    p = H.random_params(P, seed=31)
+    U = H.random_unitary(1 << n)[:, :cols].copy()
+    e = sq.Engine(0)
+    e.set_circuit(c)
+    got = U.copy()
+    e.apply(p, got)
+    assert np.abs(got - port.apply_circuit(d, p, U, pool)).max() < ENTRY_TOL
+    if cols > 1:
+        e.upload_matrix(U)
+        e.set_cost(0, 0)
+        f = e.cost_batched(np.vstack([p, p]))
+        f_ref = port.cost(d, p, U, n, 0, pool=pool)
+        assert close_rel(f[0], f_ref) and f[0] == f[1]
+        fg, gg = e.cost_grad_batched(p)
+        f_ref2, g_ref = port.cost_grad(d, P, p, U, n, 0, pool=pool)
+        assert close_rel(fg[0], f_ref2) and close_rel(gg[0], g_ref)
+    e.close()
