@@ -181,4 +181,31 @@ __global__ void replicate_matrix(const cplx* __restrict__ src, cplx* __restrict_
         d[i] = src[i];
 }
 
+// dst[y][i][j] = src[i * ld_src + j0 + j]: the column chunk [j0, j0 + cw) of the resident matrix, once per parameter set
+__global__ void copy_chunk(const cplx* __restrict__ src, int ld_src, int j0, int rows, int cw, cplx* __restrict__ dst) {
+    cplx* __restrict__ d = dst + (size_t)blockIdx.y * rows * cw;
+    const long long n = (long long)rows * cw;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(e / cw), j = (int)(e - (long long)i * cw);
+        d[e] = src[(size_t)i * ld_src + j0 + j];
+    }
+}
+
+// beta_N of the adjoint sweep for a column chunk (the chunk is zero-filled first):
+// beta[y][(j0 + j + off) ^ mask][j] = omega[y][t] for every mask of trace type t < n_trace_types
+__global__ void beta_init_stream(cplx* __restrict__ beta, int rows, int cw, int j0, int n, int trace_offset,
+                                 int n_trace_types, const cplx* __restrict__ omega) {
+    cplx* __restrict__ b = beta + (size_t)blockIdx.y * rows * cw;
+    const cplx* w = omega + (size_t)blockIdx.y * 3;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < cw; j += gridDim.x * blockDim.x) {
+        const int r = j0 + j + trace_offset;
+        b[(size_t)r * cw + j] = w[0];
+        if (n_trace_types > 1)
+            for (int q = 0; q < n; ++q) b[(size_t)(r ^ (1 << q)) * cw + j] = w[1];
+        if (n_trace_types > 2)
+            for (int q1 = 0; q1 < n - 1; ++q1)
+                for (int q2 = q1 + 1; q2 < n; ++q2) b[(size_t)(r ^ ((1 << q1) | (1 << q2))) * cw + j] = w[2];
+    }
+}
+
 }  // namespace sq

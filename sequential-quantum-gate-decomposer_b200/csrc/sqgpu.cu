@@ -382,6 +382,10 @@ size_t fused_smem(int mode, int rows, int ct, int threads, bool has_dense, int w
 
 FusedPlan plan_fused(const sqgpu_ctx* c, int mode, int rows, int cols, int ysets) {
     FusedPlan p;
+    {   // test hook: SQGPU_FORCE_STREAM=1 sends cost / gradient evaluations down the chunked streaming executor
+        const char* fs = getenv("SQGPU_FORCE_STREAM");
+        if (fs && fs[0] == '1' && mode != MODE_APPLY) return p;
+    }
     const size_t budget = (size_t)c->smem_optin;
     int max_log = 3;
     while ((1 << max_log) > cols && max_log > 0) --max_log;  // no wider than the matrix (cols = 1: state vector)
@@ -492,14 +496,17 @@ void time_end(sqgpu_ctx* c, cudaStream_t st) {
     c->timer.n++;
 }
 
+int run_exec_streaming(sqgpu_ctx* c, int batch, bool grad, const cplx* d_omega, double* d_traces, cudaStream_t st);
+StreamGate make_stream_gate(const DevOp& op, cplx* data, long long ystride, int rows, int cols, int ld, const cplx* K, long long k_ystride);
+int launch_stream_gate(sqgpu_ctx* c, const DevOp& op, bool deriv, cplx* data, long long ystride, int ysets, int rows, int cols,
+                       int ld, const cplx* K, long long k_ystride, cudaStream_t st);
+
 // one executor pass over the resident matrix for `batch` parameter sets whose kernel tables are already built:
 // fills wTrPart (and wWPart), then reduces into d_traces[batch][1+P or 1][3][2].
 int run_exec_resident(sqgpu_ctx* c, int batch, bool grad, const cplx* d_omega, double* d_traces, cudaStream_t st) {
     const int mode = grad ? MODE_GRAD : MODE_COST;
     FusedPlan p = plan_fused(c, mode, c->rows, c->cols, batch);
-    if (!p.ok)
-        return fail(SQGPU_ERR_UNSUPPORTED, "%d-qubit %s does not fit the shared-memory executor (rows = %d); "
-                    "the streaming executor for this size is not implemented yet", c->qbit_num, grad ? "gradient" : "cost", c->rows);
+    if (!p.ok) return run_exec_streaming(c, batch, grad, d_omega, d_traces, st);  // column too tall for shared memory
     int rc;
     if ((rc = c->wTrPart.ensure((size_t)batch * p.chunks * 6 * sizeof(double)))) return rc;
     if (grad && (rc = c->wWPart.ensure(std::max<size_t>(1, (size_t)batch * p.chunks * c->w_total) * sizeof(cplx)))) return rc;
@@ -538,6 +545,10 @@ int check_ready(const sqgpu_ctx* c, bool need_matrix) {
 
 // max parameter sets per executor launch so that the W partials stay below ~1.5 GiB
 int batch_slice(const sqgpu_ctx* c, int batch, bool grad) {
+    {
+        FusedPlan pf = plan_fused(c, grad ? MODE_GRAD : MODE_COST, c->rows, c->cols, batch);
+        if (!pf.ok) return std::min(batch, 32);  // streaming fallback: bound the replicated chunk workspace
+    }
     if (!grad || c->w_total == 0) return std::min(batch, 65535);
     FusedPlan p = plan_fused(c, MODE_GRAD, c->rows, c->cols, batch);
     const size_t per = (size_t)std::max(1, p.chunks) * c->w_total * sizeof(cplx);
@@ -738,6 +749,87 @@ int apply_program_dev(sqgpu_ctx* c, const cplx* d_in, long long in_ystride, cplx
             y = y1;
         }
     }
+    return SQGPU_OK;
+}
+
+// Fallback for matrices whose columns do not fit shared memory (n >= 13 gradient, n >= 14 cost): column chunks of the
+// resident matrix are replicated per parameter set into an L2-sized workspace and the program runs one op per launch
+// with the streaming kernels; partials have the same layout as the fused executor's, one "chunk" per column chunk.
+int run_exec_streaming(sqgpu_ctx* c, int batch, bool grad, const cplx* d_omega, double* d_traces, cudaStream_t st) {
+    const int rows = c->rows, cols = c->cols;
+    if (grad)
+        for (const DevOp& op : c->ops) {
+            const bool ok = op.dim == 2 || (op.dim == 4 && op.nq == 2 && op.ctrl_mask == 0);
+            if (!ok) return fail(SQGPU_ERR_UNSUPPORTED, "streaming gradient with 3+ qubit dense or controlled two-target gates is not implemented (n = %d)", c->qbit_num);
+        }
+    // chunk width: ~16 MiB of column data per parameter set, at least 1 column
+    int cw = (int)std::max<long long>(1, std::min<long long>(cols, ((long long)16 << 20) / ((long long)rows * (long long)sizeof(cplx))));
+    const int nchunks = (cols + cw - 1) / cw;
+    const size_t chunk_elems = (size_t)rows * cw;
+    const int nblk = std::min(c->sm_count * 8, std::max(1, (int)(chunk_elems / 1024)));
+    int rc;
+    if ((rc = c->wMat.ensure((size_t)(grad ? 2 : 1) * batch * chunk_elems * sizeof(cplx)))) return rc;
+    if ((rc = c->wTrPart.ensure(((size_t)batch * nchunks * 6 + (size_t)batch * nblk * 32) * sizeof(double)))) return rc;
+    if (grad && (rc = c->wWPart.ensure(std::max<size_t>(1, (size_t)batch * nchunks * c->w_total) * sizeof(cplx)))) return rc;
+    cplx* A = c->wMat.as<cplx>();
+    cplx* Bt = A + (size_t)batch * chunk_elems;
+    double* tr_part = c->wTrPart.as<double>();
+    double* wscratch = tr_part + (size_t)batch * nchunks * 6;
+    const int ntt = n_trace_types_of(c->cfg.variant);
+    const int off = effective_offset(c);
+    time_begin(c, "gate_stream (chunked)", st);
+    for (int ch = 0; ch < nchunks; ++ch) {
+        const int j0 = ch * cw, w = std::min(cw, cols - j0);
+        const size_t ce = (size_t)rows * w;
+        copy_chunk<<<dim3(std::min(c->sm_count * 8, std::max(1, (int)(ce / 256))), batch), 256, 0, st>>>(c->U.as<cplx>(), cols, j0, rows, w, A);
+        c->launches++;
+        for (int k = 0; k < c->n_ops; ++k) {
+            const DevOp& op = c->ops[k];
+            const cplx* K = op.kern_off >= 0 ? c->wKtab.as<cplx>() + op.kern_off : c->dPool.as<cplx>() + op.pool_off;
+            const long long kst = op.kern_off >= 0 ? c->kern_total : 0;
+            if ((rc = launch_stream_gate(c, op, false, A, (long long)ce, batch, rows, w, w, K, kst, st))) return rc;
+        }
+        // per-chunk traces land at tr_part[y][ch][6]: launch with out pointing at chunk ch and stride nchunks*6
+        traces_stream<<<batch, 256, 0, st>>>(A, (long long)ce, w, w, c->qbit_num, off + j0, ntt, tr_part + (size_t)ch * 6, nchunks * 6);
+        c->launches++;
+        if (!grad) continue;
+        CUDA_TRY(cudaMemsetAsync(Bt, 0, (size_t)batch * ce * sizeof(cplx), st));
+        beta_init_stream<<<dim3((w + 127) / 128, batch), 128, 0, st>>>(Bt, rows, w, j0, c->qbit_num, off, ntt, d_omega);
+        c->launches++;
+        for (int k = c->n_ops - 1; k >= 0; --k) {
+            const DevOp& op = c->ops[k];
+            const cplx* K = op.kern_off >= 0 ? c->wKtab.as<cplx>() + op.kern_off : c->dPool.as<cplx>() + op.pool_off;
+            const long long kst = op.kern_off >= 0 ? c->kern_total : 0;
+            StreamGate g = make_stream_gate(op, A, (long long)ce, rows, w, w, K, kst);
+            const int want_w = op.n_params > 0 ? 1 : 0;
+            int blocks, width;
+            if (op.dim == 2) {
+                const long long items = (long long)(rows >> g.nfix) * w;
+                blocks = (int)std::max<long long>(1, std::min<long long>((items + 255) / 256, nblk));
+                width = 8;
+                adjoint1q_stream<<<dim3(blocks, batch), 256, 0, st>>>(g, Bt, (long long)ce, wscratch, want_w);
+            } else {
+                const long long items = (long long)(rows >> 2) * w;
+                blocks = (int)std::max<long long>(1, std::min<long long>((items + 127) / 128, nblk));
+                width = 32;
+                adjoint2q_stream<<<dim3(blocks, batch), 128, 0, st>>>(g, Bt, (long long)ce, wscratch, want_w);
+            }
+            c->launches++;
+            if (want_w) {
+                sum_partials<<<batch, 32, 0, st>>>(wscratch, blocks, width, 1.0,
+                                                   reinterpret_cast<double*>(c->wWPart.as<cplx>() + (size_t)ch * c->w_total + op.w_off),
+                                                   2 * nchunks * c->w_total);
+                c->launches++;
+            }
+        }
+    }
+    time_end(c, st);
+    CUDA_TRY(cudaGetLastError());
+    reduce_partials<<<batch, 128, 0, st>>>(tr_part, nchunks, c->wWPart.as<cplx>(), c->w_total, c->dOps.as<DevOp>(), c->dParamOp.as<int>(),
+                                           c->dParamOp.as<int>() + std::max(c->n_params, 1), c->wDKtab.as<cplx>(), c->dkern_total,
+                                           c->wKtab.as<cplx>(), c->kern_total, c->n_params, grad ? 1 : 0, d_traces);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
     return SQGPU_OK;
 }
 

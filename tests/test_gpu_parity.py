@@ -412,3 +412,82 @@ def test_dense_blocks_in_circuit(sq, port, n, cols):
         f_ref2, g_ref = port.cost_grad(d, P, p, U, n, 0, pool=pool)
         assert close_rel(fg[0], f_ref2) and close_rel(gg[0], g_ref)
     e.close()
+
+
+# ---- sizes beyond one column per CTA: the chunked streaming executor -------------------------------------------------
+
+@pytest.mark.parametrize("variant", [0, 2, 3, 5])
+def test_streaming_executor_matches_oracle(sq, port, monkeypatch, variant):
+    """SQGPU_FORCE_STREAM=1 routes cost/gradient through the fallback used when a column does not fit shared memory
+    (n >= 13 gradient, n >= 14 cost); same answers as the oracle, and as the shared-memory executor"""
+    n = 6
+    c = H.random_circuit(n, 40, seed=17, names=["U3", "RY", "CRY", "CNOT", "RZ", "adaptive", "CZ", "RX", "RXX", "H", "CP"])
+    d, pool = c.descriptors()
+    P = c.get_Parameter_Num()
+    U = H.random_unitary(1 << n).conj().T.copy()[:, :37].copy()
+    ps = H.random_params(P, seed=9, batch=3)
+    monkeypatch.setenv("SQGPU_FORCE_STREAM", "1")
+    e = sq.Engine(0)
+    e.upload_matrix(U)
+    e.set_circuit(c)
+    e.set_cost(variant, 0, 0.37)
+    f, g = e.cost_grad_batched(ps)
+    fc = e.cost_batched(ps)
+    assert "stream" in e.last_kernel_time()[0]
+    for b in range(3):
+        f_ref, g_ref = port.cost_grad(d, P, ps[b], U, n, variant, 0, 0.37, pool=pool)
+        assert close_rel(f[b], f_ref) and close_rel(fc[b], f_ref) and close_rel(g[b], g_ref)
+    e.close()
+
+
+def test_n12_gradient_single_column_tiles(sq, port):
+    """n = 12: one column (64 KB) per CTA for the gradient; checked on a 6-column slice against the oracle"""
+    n = 12
+    c = H.adaptive_circuit(n, 1, topology=[(q + 1, q) for q in range(n - 1)])
+    d, pool = c.descriptors()
+    P = c.get_Parameter_Num()
+    rng = np.random.default_rng(5)
+    U = (rng.standard_normal(((1 << n), 6)) + 1j * rng.standard_normal(((1 << n), 6))) / np.sqrt(1 << n)
+    U = np.ascontiguousarray(U)
+    p = H.random_params(P, seed=2)
+    e = sq.Engine(0)
+    e.upload_matrix(U)
+    e.set_circuit(c)
+    for variant in (0, 3):
+        e.set_cost(variant, 0)
+        f, g = e.cost_grad_batched(p)
+        f_ref, g_ref = port.cost_grad(d, P, p, U, n, variant)
+        assert close_rel(f[0], f_ref) and close_rel(g[0], g_ref)
+    e.close()
+
+
+def test_n13_gradient_streams(sq):
+    """n = 13 gradient does not fit shared memory: the engine falls back to the streaming executor by itself. No oracle
+    at this size; checked through size-independent properties: analytic gradient vs central finite difference, and
+    linearity of the trace cost in U."""
+    n = 13
+    c = H.adaptive_circuit(n, 1, topology=[(q + 1, q) for q in range(n - 1)])
+    P = c.get_Parameter_Num()
+    theta = H.random_params(P, seed=8)
+    e = sq.Engine(0)
+    e.set_circuit(c)
+    cols = 3
+    rng = np.random.default_rng(3)
+    U = np.ascontiguousarray((rng.standard_normal((1 << n, cols)) + 1j * rng.standard_normal((1 << n, cols))) / 50.0)
+    e.upload_matrix(U)
+    e.set_cost(0, 0)
+    f, g = e.cost_grad_batched(theta)
+    assert "stream" in e.last_kernel_time()[0]
+    idx = rng.choice(P, 4, replace=False)
+    h = 1e-5
+    sh = np.repeat(theta[None, :], 8, axis=0)
+    for k, i in enumerate(idx):
+        sh[2 * k, i] += h
+        sh[2 * k + 1, i] -= h
+    fs = e.cost_batched(sh)
+    assert np.abs((fs[0::2] - fs[1::2]) / (2 * h) - g[0, idx]).max() < 1e-8
+    # linearity of the trace in U: cost(2U) - 1 = 2 (cost(U) - 1)
+    e.upload_matrix(2 * U)
+    f2 = e.cost_batched(theta)
+    assert abs((f2[0] - 1.0) - 2 * (f[0] - 1.0)) < 1e-12
+    e.close()
