@@ -56,14 +56,15 @@ struct ExecArgs {
     double* tr_part;         // [y][chunks][6]
     cplx* w_part;            // [y][chunks][w_total]
     int w_total;
-    int w_in_smem;           // accumulate W over the CTA's tiles in shared memory (else tiles_per_cta must be 1)
+    int w_in_smem;           // accumulate W over the CTA's tiles in shared memory; else in the CTA's own (zero-initialised)
+                             // slice of w_part with fire-and-forget reductions: one thread owns each address, so the
+                             // summation order stays fixed
     const cplx* omega;       // [y][3] weights of the three trace types in the functional whose gradient is taken
-    int has_dense;           // program contains raw dim > 2 ops (reserves the 16 KB kernel staging buffer)
+    int dense_stage;         // complex elements of kernel staging for the generic dense path (0: none)
     int wmax;                // max dim*dim over parametric ops (complex), >= 4
 };
 
-static const int FUSED_THREADS = 256;
-static const int DENSE_STAGE = 2304;  // complex elements: real embedding of a 32 x 32 complex kernel, 64 x (64+4) doubles, + row patterns
+static const int FUSED_THREADS = 512;
 
 // ---- shared-memory swizzle -------------------------------------------------------------------------------------
 // rows per 128 B wavefront: 8 / ct. The low log2(8/ct) bits of the physical row select the 16 B bank group set; they
@@ -227,15 +228,202 @@ __device__ __forceinline__ void dense_dmma_forward(cplx* sa, const double* skr, 
     }
 }
 
+// ---- fused 2-/3-qubit blocks on the FP64 tensor cores -------------------------------------------------------------
+// The block kernel K (4 x 4 or 8 x 8 complex) sits in shared memory (km); every lane derives the DMMA A-fragments of the
+// real embeddings it needs: mode 0: K, 1: K^dagger, 2: K^T.
+template <int DIM>
+__device__ __forceinline__ double block_frag(const cplx* km, int x, int y, int mode) {
+    const int r = x >> 1, a = x & 1, c = y >> 1, b = y & 1;
+    const cplx e = (mode == 0) ? km[r * DIM + c] : km[c * DIM + r];
+    const double im = (mode == 1) ? -e.y : e.y;
+    return (a == b) ? e.x : (a ? im : -im);
+}
+
+// Addressing of the DMMA block path. phys_row() is GF(2)-linear (x ^ L(x >> s) with L linear), and so are the bit
+// insertions that expand a group index into a row index; hence the shared-memory address of (item, component) splits into
+//     address = B0(batch) ^ slot(lane, access)
+// where B0 is computed once per 8-item batch and `slot` once per op and lane. Units: doubles (2 per complex element).
+template <int LOG_CT, int KQ>
+struct BlockGeom {
+    static constexpr int CT = 1 << LOG_CT;
+    static constexpr int LOGG = 3 - LOG_CT;  // log2(groups per 8-item batch)
+    int q[3];   // block qubits, ascending (unused = 30)
+    int Pq[3];  // address image of row bit q[j]
+    int F[3];   // address image of the j-th lowest row bit that is NOT a block qubit (group-offset bits inside a batch)
+
+    __device__ __forceinline__ void init(int q0, int q1, int q2) {
+        q[0] = q0; q[1] = q1; q[2] = q2;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) Pq[j] = (j < KQ) ? (phys_row<LOG_CT>(1 << q[j]) << (LOG_CT + 1)) : 0;
+        int f = 0;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            while (f == q0 || f == q1 || f == q2) ++f;
+            F[j] = phys_row<LOG_CT>(1 << f) << (LOG_CT + 1);
+            ++f;
+        }
+    }
+    // B0 of the batch starting at item b0 (b0 % 8 == 0)
+    __device__ __forceinline__ int batch_base(int b0) const {
+        int base = b0 >> LOG_CT;
+#pragma unroll
+        for (int j = 0; j < KQ; ++j) base = insert_zero(base, q[j]);
+        return phys_row<LOG_CT>(base) << (LOG_CT + 1);
+    }
+    // lane-constant part of the address of real component `comp` (= 2 * local amplitude + re/im) of batch item `item` (0..7)
+    __device__ __forceinline__ int slot(int item, int comp) const {
+        const int go = item >> LOG_CT, c = item & (CT - 1), amp = comp >> 1;
+        int a = c * 2 + (comp & 1);
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            if (j < LOGG && ((go >> j) & 1)) a ^= F[j];
+#pragma unroll
+        for (int j = 0; j < KQ; ++j)
+            if ((amp >> j) & 1) a ^= Pq[j];
+        return a;
+    }
+};
+
+// forward: x <- K x for every group of the tile. One warp handles 8 (group, column) items per step.
+template <int LOG_CT, int KQ>
+__device__ __forceinline__ void block_dmma_forward(cplx* sa, const cplx* km, const BlockGeom<LOG_CT, KQ>& G, int rows, int tid,
+                                                   int nthr) {
+    constexpr int DIM = 1 << KQ, DIMR = 2 * DIM, RT = DIMR / 8, KS = DIMR / 4;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5, m = lane >> 2, kk = lane & 3;
+    double* sad = reinterpret_cast<double*>(sa);
+    double af[RT][KS];
+    int sl_ld[KS], sl_st0[RT], sl_st1[RT];
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) sl_ld[ks] = G.slot(m, 4 * ks + kk);
+#pragma unroll
+    for (int rt = 0; rt < RT; ++rt) {
+        sl_st0[rt] = G.slot(2 * kk, 8 * rt + m);
+        sl_st1[rt] = G.slot(2 * kk + 1, 8 * rt + m);
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) af[rt][ks] = block_frag<DIM>(km, 8 * rt + m, 4 * ks + kk, 0);
+    }
+    const int nitems = (rows >> KQ) << LOG_CT;
+    for (int b0 = warp * 8; b0 < nitems; b0 += nwarps * 8) {
+        const int B0 = G.batch_base(b0);
+        double xf[KS];
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) xf[ks] = sad[B0 ^ sl_ld[ks]];
+        double d[RT][2];
+#pragma unroll
+        for (int rt = 0; rt < RT; ++rt) {
+            d[rt][0] = d[rt][1] = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) dmma_m8n8k4(d[rt][0], d[rt][1], af[rt][ks], xf[ks]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int rt = 0; rt < RT; ++rt) {
+            sad[B0 ^ sl_st0[rt]] = d[rt][0];
+            sad[B0 ^ sl_st1[rt]] = d[rt][1];
+        }
+        __syncwarp();
+    }
+}
+
+// backward step of the adjoint sweep: a <- K^dagger p, beta <- K^T beta, W' += beta p^T (all on DMMA); the warp's W'
+// (DIM x DIM complex) is written to wslot after the loop.
+template <int LOG_CT, int KQ>
+__device__ __forceinline__ void block_dmma_backward(cplx* sa, cplx* sb, const cplx* km, const BlockGeom<LOG_CT, KQ>& G, int rows,
+                                                    bool has_w, cplx* wslot, int tid, int nthr) {
+    constexpr int DIM = 1 << KQ, DIMR = 2 * DIM, RT = DIMR / 8, KS = DIMR / 4;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5, m = lane >> 2, kk = lane & 3;
+    double* sad = reinterpret_cast<double*>(sa);
+    double* sbd = reinterpret_cast<double*>(sb);
+    double adag[RT][KS], atr[RT][KS];
+    int sl_ld[KS], sl_w[2][RT], sl_st0[RT], sl_st1[RT];
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) sl_ld[ks] = G.slot(m, 4 * ks + kk);
+#pragma unroll
+    for (int rt = 0; rt < RT; ++rt) {
+        sl_w[0][rt] = G.slot(kk, 8 * rt + m);
+        sl_w[1][rt] = G.slot(kk + 4, 8 * rt + m);
+        sl_st0[rt] = G.slot(2 * kk, 8 * rt + m);
+        sl_st1[rt] = G.slot(2 * kk + 1, 8 * rt + m);
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            adag[rt][ks] = block_frag<DIM>(km, 8 * rt + m, 4 * ks + kk, 1);
+            atr[rt][ks] = block_frag<DIM>(km, 8 * rt + m, 4 * ks + kk, 2);
+        }
+    }
+    double pacc[RT][RT][2];
+#pragma unroll
+    for (int tr = 0; tr < RT; ++tr)
+#pragma unroll
+        for (int tc = 0; tc < RT; ++tc) pacc[tr][tc][0] = pacc[tr][tc][1] = 0.0;
+    const int nitems = (rows >> KQ) << LOG_CT;
+    for (int b0 = warp * 8; b0 < nitems; b0 += nwarps * 8) {
+        const int B0 = G.batch_base(b0);
+        double pf[KS], bf[KS];
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            pf[ks] = sad[B0 ^ sl_ld[ks]];
+            bf[ks] = sbd[B0 ^ sl_ld[ks]];
+        }
+        if (has_w) {  // W' operands: component 8t + m of items kk and kk + 4
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                double pw[RT], bw[RT];
+#pragma unroll
+                for (int t = 0; t < RT; ++t) {
+                    pw[t] = sad[B0 ^ sl_w[h][t]];
+                    bw[t] = sbd[B0 ^ sl_w[h][t]];
+                }
+#pragma unroll
+                for (int tr = 0; tr < RT; ++tr)
+#pragma unroll
+                    for (int tc = 0; tc < RT; ++tc) dmma_m8n8k4(pacc[tr][tc][0], pacc[tr][tc][1], bw[tr], pw[tc]);
+            }
+        }
+        double da[RT][2], db[RT][2];
+#pragma unroll
+        for (int rt = 0; rt < RT; ++rt) {
+            da[rt][0] = da[rt][1] = db[rt][0] = db[rt][1] = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                dmma_m8n8k4(da[rt][0], da[rt][1], adag[rt][ks], pf[ks]);
+                dmma_m8n8k4(db[rt][0], db[rt][1], atr[rt][ks], bf[ks]);
+            }
+        }
+        __syncwarp();  // all reads of this batch are done
+#pragma unroll
+        for (int rt = 0; rt < RT; ++rt) {
+            sad[B0 ^ sl_st0[rt]] = da[rt][0];
+            sad[B0 ^ sl_st1[rt]] = da[rt][1];
+            sbd[B0 ^ sl_st0[rt]] = db[rt][0];
+            sbd[B0 ^ sl_st1[rt]] = db[rt][1];
+        }
+        __syncwarp();
+    }
+    if (has_w) {
+        // lane (m, kk) holds P[8tr+m][8tc+2kk], P[8tr+m][8tc+2kk+1]; rows 2r (even m) and 2r+1 (odd m) combine to
+        // W'[r][c] = (P[2r][2c] - P[2r+1][2c+1]) + i (P[2r][2c+1] + P[2r+1][2c]),  r = 4tr + m/2, c = 4tc + kk
+#pragma unroll
+        for (int tr = 0; tr < RT; ++tr)
+#pragma unroll
+            for (int tc = 0; tc < RT; ++tc) {
+                const double o0 = __shfl_xor_sync(0xffffffffu, pacc[tr][tc][0], 4);
+                const double o1 = __shfl_xor_sync(0xffffffffu, pacc[tr][tc][1], 4);
+                if ((m & 1) == 0) wslot[(4 * tr + (m >> 1)) * DIM + 4 * tc + kk] = cmake(pacc[tr][tc][0] - o1, pacc[tr][tc][1] + o0);
+            }
+    }
+}
+
 // compact per-op record staged in shared memory (uniform reads, no global latency on the critical path)
 struct SOp {
-    int32_t dim;       // 2 / 4 for fast ops
-    int32_t q0, q1;    // fast ops: qubit(s) (q0 < q1); raw ops: unused
+    int32_t dim;       // 2 / 4 / 8 for block ops
+    int32_t q0, q1, q2;  // block ops: qubits ascending (unused entries 30)
     int32_t kern_off;  // kernel-table offset, -1: pool
     int32_t w_off;
-    int32_t raw;       // 1: generic path (controls / dense >= 8 / derivative op)
+    int32_t kind;      // 0: scalar 2x2 block, 2: DMMA 4x4 / 8x8 block, 1: generic path (controls, raw dense, derivative op)
     int32_t pool_lo, pool_hi;
 };
+
+static const int KM_ELEMS = 64;  // prefetched block kernel: up to 8 x 8 complex
 
 template <int MODE, int LOG_CT>
 __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A) {
@@ -251,8 +439,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
     cplx* sa = reinterpret_cast<cplx*>(smem_raw);
     cplx* sb = sa + (size_t)rows * CT;                                   // MODE_GRAD only
     cplx* sk = (MODE == MODE_GRAD) ? sb + (size_t)rows * CT : sb;         // raw dense kernel staging
-    cplx* skm = sk + (A.has_dense ? DENSE_STAGE : 0);                     // [2][16] prefetched fast-op kernels
-    cplx* swarp = skm + 32;                                               // [2][nwarps][wmax]
+    cplx* skm = sk + A.dense_stage;                                       // [2][KM_ELEMS] prefetched block kernels
+    cplx* swarp = skm + 2 * KM_ELEMS;                                     // [2][nwarps][wmax]
     cplx* swacc = swarp + ((MODE == MODE_GRAD) ? 2 * nwarps * A.wmax : 0);  // [w_total] if w_in_smem
     double* sred = reinterpret_cast<double*>(swacc + ((MODE == MODE_GRAD && A.w_in_smem) ? A.w_total : 0));  // [nwarps][6]
     SOp* sops = reinterpret_cast<SOp*>(sred + nwarps * 6);               // [n_ops]
@@ -271,10 +459,14 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
         s.w_off = op.w_off;
         s.pool_lo = (int32_t)(op.pool_off & 0xffffffffLL);
         s.pool_hi = (int32_t)(op.pool_off >> 32);
-        const bool fast = op.ctrl_mask == 0 && (op.dim == 2 || (op.dim == 4 && op.nq == 2)) && k != deriv_op;
-        s.raw = fast ? 0 : 1;
+        s.kind = 1;
+        if (op.ctrl_mask == 0 && k != deriv_op) {
+            if (op.dim == 2) s.kind = 0;
+            else if ((op.dim == 4 || op.dim == 8) && ((((rows >> op.nq) << LOG_CT) & 7) == 0) && nthr >= 32) s.kind = 2;
+        }
         s.q0 = op.dim == 2 ? op.target : op.q[0];
         s.q1 = op.dim == 2 ? 30 : op.q[1];
+        s.q2 = op.dim == 8 ? op.q[2] : 30;
         sops[k] = s;
     }
     if (MODE == MODE_GRAD && A.w_in_smem) {
@@ -283,10 +475,10 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
     double tsum[6] = {0, 0, 0, 0, 0, 0};  // running trace sums of this CTA (thread 0)
     __syncthreads();
 
-    // kernel element this thread prefetches for op k (threads 0..15), and the commit into skm[k & 1]
+    // kernel element this thread prefetches for op k (threads 0..63)
     auto kernel_elem = [&](int k) -> cplx {
         const SOp s = sops[k];
-        if (s.raw || tid >= s.dim * s.dim) return czero();
+        if (s.kind == 1 || tid >= s.dim * s.dim) return czero();
         const cplx* K = s.kern_off >= 0 ? ktab + s.kern_off : A.pool + (((long long)s.pool_hi << 32) | (unsigned)s.pool_lo);
         return K[tid];
     };
@@ -306,7 +498,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                 if (c < valid) v = src[(size_t)i * A.ld_in + c];
                 sa[phys_row<LOG_CT>(i) * CT + c] = v;
             }
-            if (A.n_ops > 0 && tid < 16) skm[tid] = kernel_elem(0);
+            if (A.n_ops > 0 && tid < KM_ELEMS) skm[tid] = kernel_elem(0);
         }
         __syncthreads();
 
@@ -315,42 +507,32 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
             const SOp s = sops[k];
             cplx next_elem = czero();
             const bool have_next = k + 1 < A.n_ops;
-            if (have_next && tid < 16) next_elem = kernel_elem(k + 1);
-            if (!s.raw) {
-                const cplx* __restrict__ km = skm + (k & 1) * 16;
-                if (s.dim == 4) {
-                    cplx M[16];
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) M[e] = km[e];
-                    const int b0 = 1 << s.q0, b1 = 1 << s.q1;
-                    const int px0 = __popc(b0 >> 1) & 1, px1 = __popc(b1 >> 1) & 1;
-                    const int nitems = (rows >> 2) << LOG_CT;
-                    for (int item = tid; item < nitems; item += nthr) {
-                        const int c = item & (CT - 1);
-                        const int base = insert_zero(insert_zero(item >> LOG_CT, s.q0), s.q1);
-                        int e0, e1, e2, e3;
-                        group4_addr<LOG_CT>(base, b0, b1, c, px0, px1, e0, e1, e2, e3);
-                        const cplx v0 = sa[e0], v1 = sa[e1], v2 = sa[e2], v3 = sa[e3];
-                        sa[e0] = cfma(M[3], v3, cfma(M[2], v2, cfma(M[1], v1, cmul(M[0], v0))));
-                        sa[e1] = cfma(M[7], v3, cfma(M[6], v2, cfma(M[5], v1, cmul(M[4], v0))));
-                        sa[e2] = cfma(M[11], v3, cfma(M[10], v2, cfma(M[9], v1, cmul(M[8], v0))));
-                        sa[e3] = cfma(M[15], v3, cfma(M[14], v2, cfma(M[13], v1, cmul(M[12], v0))));
-                    }
+            if (have_next && tid < KM_ELEMS) next_elem = kernel_elem(k + 1);
+            const cplx* __restrict__ km = skm + (k & 1) * KM_ELEMS;
+            if (s.kind == 2) {
+                if (s.dim == 8) {
+                    BlockGeom<LOG_CT, 3> G;
+                    G.init(s.q0, s.q1, s.q2);
+                    block_dmma_forward<LOG_CT, 3>(sa, km, G, rows, tid, nthr);
                 } else {
-                    const cplx k00 = km[0], k01 = km[1], k10 = km[2], k11 = km[3];
-                    const int tbit = 1 << s.q0;
-                    const int nitems = (rows >> 1) << LOG_CT;
-                    for (int item = tid; item < nitems; item += nthr) {
-                        const int c = item & (CT - 1);
-                        const int i0 = insert_zero(item >> LOG_CT, s.q0);
-                        const int e0 = phys_row<LOG_CT>(i0) * CT + c, e1 = phys_row<LOG_CT>(i0 | tbit) * CT + c;
-                        const cplx a0 = sa[e0], a1 = sa[e1];
-                        sa[e0] = cfma(k01, a1, cmul(k00, a0));
-                        sa[e1] = cfma(k11, a1, cmul(k10, a0));
-                    }
+                    BlockGeom<LOG_CT, 2> G;
+                    G.init(s.q0, s.q1, 30);
+                    block_dmma_forward<LOG_CT, 2>(sa, km, G, rows, tid, nthr);
+                }
+            } else if (s.kind == 0) {
+                const cplx k00 = km[0], k01 = km[1], k10 = km[2], k11 = km[3];
+                const int tbit = 1 << s.q0;
+                const int nitems = (rows >> 1) << LOG_CT;
+                for (int item = tid; item < nitems; item += nthr) {
+                    const int c = item & (CT - 1);
+                    const int i0 = insert_zero(item >> LOG_CT, s.q0);
+                    const int e0 = phys_row<LOG_CT>(i0) * CT + c, e1 = phys_row<LOG_CT>(i0 | tbit) * CT + c;
+                    const cplx a0 = sa[e0], a1 = sa[e1];
+                    sa[e0] = cfma(k01, a1, cmul(k00, a0));
+                    sa[e1] = cfma(k11, a1, cmul(k10, a0));
                 }
             } else {
-                // ---- generic path: controlled gates, dense 8..32 kernels, derivative kernels ----------------------
+                // ---- generic path: controlled gates, raw dense kernels, derivative kernels ------------------------
                 const DevOp& op = A.ops[k];
                 const bool deriv = (MODE == MODE_APPLY) && (k == deriv_op);
                 const int dim = op.dim;
@@ -413,33 +595,33 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                         else if (nq == 4) dense_dmma_forward<LOG_CT, 4>(sa, skr, spat, op, rows, tid, nthr);
                         else dense_dmma_forward<LOG_CT, 5>(sa, skr, spat, op, rows, tid, nthr);
                     } else {
-                    for (int e = tid; e < dim * dim; e += nthr) sk[e] = K[e];
-                    __syncthreads();
-                    for (int item = tid; item < nitems; item += nthr) {
-                        const int c = item & (CT - 1);
-                        int base = item >> LOG_CT;
-                        for (int j = 0; j < nq; ++j) base = insert_zero(base, op.q[j]);
-                        const bool active = (base & op.ctrl_mask) == op.ctrl_mask;
-                        if (!active && !deriv) continue;
-                        cplx v[32];
-                        for (int l = 0; l < dim; ++l) {
-                            int r = base;
-                            for (int j = 0; j < nq; ++j) r |= ((l >> j) & 1) << op.q[j];
-                            v[l] = active ? sa[phys_row<LOG_CT>(r) * CT + c] : czero();
+                        for (int e = tid; e < dim * dim; e += nthr) sk[e] = K[e];
+                        __syncthreads();
+                        for (int item = tid; item < nitems; item += nthr) {
+                            const int c = item & (CT - 1);
+                            int base = item >> LOG_CT;
+                            for (int j = 0; j < nq; ++j) base = insert_zero(base, op.q[j]);
+                            const bool active = (base & op.ctrl_mask) == op.ctrl_mask;
+                            if (!active && !deriv) continue;
+                            cplx v[32];
+                            for (int l = 0; l < dim; ++l) {
+                                int r = base;
+                                for (int j = 0; j < nq; ++j) r |= ((l >> j) & 1) << op.q[j];
+                                v[l] = active ? sa[phys_row<LOG_CT>(r) * CT + c] : czero();
+                            }
+                            for (int ro = 0; ro < dim; ++ro) {
+                                cplx acc = czero();
+                                if (active)
+                                    for (int l = 0; l < dim; ++l) acc = cfma(sk[ro * dim + l], v[l], acc);
+                                int r = base;
+                                for (int j = 0; j < nq; ++j) r |= ((ro >> j) & 1) << op.q[j];
+                                sa[phys_row<LOG_CT>(r) * CT + c] = acc;
+                            }
                         }
-                        for (int ro = 0; ro < dim; ++ro) {
-                            cplx acc = czero();
-                            if (active)
-                                for (int l = 0; l < dim; ++l) acc = cfma(sk[ro * dim + l], v[l], acc);
-                            int r = base;
-                            for (int j = 0; j < nq; ++j) r |= ((ro >> j) & 1) << op.q[j];
-                            sa[phys_row<LOG_CT>(r) * CT + c] = acc;
-                        }
-                    }
                     }
                 }
             }
-            if (have_next && tid < 16) skm[((k + 1) & 1) * 16 + tid] = next_elem;
+            if (have_next && tid < KM_ELEMS) skm[((k + 1) & 1) * KM_ELEMS + tid] = next_elem;
             __syncthreads();
         }
 
@@ -485,15 +667,15 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
             }
             const int nt = 2 * A.n_trace_types;
             for (int i = 0; i < nt; ++i)
-                for (int s = 16; s > 0; s >>= 1) t[i] += __shfl_xor_sync(0xffffffffu, t[i], s);
+                for (int sft = 16; sft > 0; sft >>= 1) t[i] += __shfl_xor_sync(0xffffffffu, t[i], sft);
             if (lane == 0)
                 for (int i = 0; i < nt; ++i) sred[warp * 6 + i] = t[i];
             __syncthreads();
             if (tid == 0) {
                 for (int i = 0; i < nt; ++i) {
-                    double s = 0;
-                    for (int w = 0; w < nwarps; ++w) s += sred[w * 6 + i];
-                    tsum[i] += s;
+                    double sum = 0;
+                    for (int w = 0; w < nwarps; ++w) sum += sred[w * 6 + i];
+                    tsum[i] += sum;
                 }
             }
         }
@@ -501,7 +683,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
         if (MODE == MODE_GRAD) {
             // ---- beta_N = sum_t omega_t * sum_{masks of type t} e_{(j+off)^mask} per column ---------------------
             for (int e = tid; e < rows * CT; e += nthr) sb[e] = czero();
-            if (A.n_ops > 0 && tid < 16) skm[((A.n_ops - 1) & 1) * 16 + tid] = kernel_elem(A.n_ops - 1);
+            if (A.n_ops > 0 && tid < KM_ELEMS) skm[((A.n_ops - 1) & 1) * KM_ELEMS + tid] = kernel_elem(A.n_ops - 1);
             __syncthreads();
             {
                 const int off = A.trace_offset;
@@ -532,72 +714,44 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                 const SOp s = sops[k];
                 cplx next_elem = czero();
                 const bool have_next = k > 0;
-                if (have_next && tid < 16) next_elem = kernel_elem(k - 1);
+                if (have_next && tid < KM_ELEMS) next_elem = kernel_elem(k - 1);
                 const bool has_w = s.w_off >= 0;
-                double* wslot = reinterpret_cast<double*>(swarp + (size_t)(buf * nwarps + warp) * A.wmax);
+                cplx* wslot_c = swarp + (size_t)(buf * nwarps + warp) * A.wmax;
+                double* wslot = reinterpret_cast<double*>(wslot_c);
+                const cplx* __restrict__ km = skm + (k & 1) * KM_ELEMS;
                 int wdim = s.dim;
-                if (!s.raw) {
-                    const cplx* __restrict__ km = skm + (k & 1) * 16;
-                    if (s.dim == 4) {
-                        cplx M[16], W[16];
-#pragma unroll
-                        for (int e = 0; e < 16; ++e) {
-                            M[e] = km[e];
-                            W[e] = czero();
-                        }
-                        const int b0 = 1 << s.q0, b1 = 1 << s.q1;
-                        const int px0 = __popc(b0 >> 1) & 1, px1 = __popc(b1 >> 1) & 1;
-                        const int nitems = (rows >> 2) << LOG_CT;
-                        for (int item = tid; item < nitems; item += nthr) {
-                            const int c = item & (CT - 1);
-                            const int base = insert_zero(insert_zero(item >> LOG_CT, s.q0), s.q1);
-                            int e0, e1, e2, e3;
-                            group4_addr<LOG_CT>(base, b0, b1, c, px0, px1, e0, e1, e2, e3);
-                            const cplx p[4] = {sa[e0], sa[e1], sa[e2], sa[e3]};  // column after the block
-                            const cplx b[4] = {sb[e0], sb[e1], sb[e2], sb[e3]};  // row functional after the block
-                            if (has_w) {
-#pragma unroll
-                                for (int r = 0; r < 4; ++r)
-#pragma unroll
-                                    for (int cc = 0; cc < 4; ++cc) W[r * 4 + cc] = cfma(b[r], p[cc], W[r * 4 + cc]);
-                            }
-                            // a = M^dagger p
-                            sa[e0] = cfmac(M[12], p[3], cfmac(M[8], p[2], cfmac(M[4], p[1], cfmac(M[0], p[0], czero()))));
-                            sa[e1] = cfmac(M[13], p[3], cfmac(M[9], p[2], cfmac(M[5], p[1], cfmac(M[1], p[0], czero()))));
-                            sa[e2] = cfmac(M[14], p[3], cfmac(M[10], p[2], cfmac(M[6], p[1], cfmac(M[2], p[0], czero()))));
-                            sa[e3] = cfmac(M[15], p[3], cfmac(M[11], p[2], cfmac(M[7], p[1], cfmac(M[3], p[0], czero()))));
-                            // beta' = M^T beta
-                            sb[e0] = cfma(M[12], b[3], cfma(M[8], b[2], cfma(M[4], b[1], cmul(M[0], b[0]))));
-                            sb[e1] = cfma(M[13], b[3], cfma(M[9], b[2], cfma(M[5], b[1], cmul(M[1], b[0]))));
-                            sb[e2] = cfma(M[14], b[3], cfma(M[10], b[2], cfma(M[6], b[1], cmul(M[2], b[0]))));
-                            sb[e3] = cfma(M[15], b[3], cfma(M[11], b[2], cfma(M[7], b[1], cmul(M[3], b[0]))));
-                        }
-                        if (has_w) warp_store_w<16>(W, wslot, lane);
+                if (s.kind == 2) {
+                    if (s.dim == 8) {
+                        BlockGeom<LOG_CT, 3> G;
+                        G.init(s.q0, s.q1, s.q2);
+                        block_dmma_backward<LOG_CT, 3>(sa, sb, km, G, rows, has_w, wslot_c, tid, nthr);
                     } else {
-                        const cplx k00 = km[0], k01 = km[1], k10 = km[2], k11 = km[3];
-                        const int tbit = 1 << s.q0;
-                        cplx W[4] = {czero(), czero(), czero(), czero()};
-                        const int nitems = (rows >> 1) << LOG_CT;
-                        for (int item = tid; item < nitems; item += nthr) {
-                            const int c = item & (CT - 1);
-                            const int i0 = insert_zero(item >> LOG_CT, s.q0);
-                            const int e0 = phys_row<LOG_CT>(i0) * CT + c, e1 = phys_row<LOG_CT>(i0 | tbit) * CT + c;
-                            const cplx p0 = sa[e0], p1 = sa[e1], b0 = sb[e0], b1 = sb[e1];
-                            const cplx a0 = cfmac(k10, p1, cfmac(k00, p0, czero()));
-                            const cplx a1 = cfmac(k11, p1, cfmac(k01, p0, czero()));
-                            sa[e0] = a0;
-                            sa[e1] = a1;
-                            if (has_w) {
-                                W[0] = cfma(b0, p0, W[0]);
-                                W[1] = cfma(b0, p1, W[1]);
-                                W[2] = cfma(b1, p0, W[2]);
-                                W[3] = cfma(b1, p1, W[3]);
-                            }
-                            sb[e0] = cfma(k10, b1, cmul(k00, b0));
-                            sb[e1] = cfma(k11, b1, cmul(k01, b0));
-                        }
-                        if (has_w) warp_store_w<4>(W, wslot, lane);
+                        BlockGeom<LOG_CT, 2> G;
+                        G.init(s.q0, s.q1, 30);
+                        block_dmma_backward<LOG_CT, 2>(sa, sb, km, G, rows, has_w, wslot_c, tid, nthr);
                     }
+                } else if (s.kind == 0) {
+                    const cplx k00 = km[0], k01 = km[1], k10 = km[2], k11 = km[3];
+                    const int tbit = 1 << s.q0;
+                    cplx W[4] = {czero(), czero(), czero(), czero()};
+                    const int nitems = (rows >> 1) << LOG_CT;
+                    for (int item = tid; item < nitems; item += nthr) {
+                        const int c = item & (CT - 1);
+                        const int i0 = insert_zero(item >> LOG_CT, s.q0);
+                        const int e0 = phys_row<LOG_CT>(i0) * CT + c, e1 = phys_row<LOG_CT>(i0 | tbit) * CT + c;
+                        const cplx p0 = sa[e0], p1 = sa[e1], b0 = sb[e0], b1 = sb[e1];
+                        sa[e0] = cfmac(k10, p1, cfmac(k00, p0, czero()));
+                        sa[e1] = cfmac(k11, p1, cfmac(k01, p0, czero()));
+                        if (has_w) {
+                            W[0] = cfma(b0, p0, W[0]);
+                            W[1] = cfma(b0, p1, W[1]);
+                            W[2] = cfma(b1, p0, W[2]);
+                            W[3] = cfma(b1, p1, W[3]);
+                        }
+                        sb[e0] = cfma(k10, b1, cmul(k00, b0));
+                        sb[e1] = cfma(k11, b1, cmul(k01, b0));
+                    }
+                    if (has_w) warp_store_w<4>(W, wslot, lane);
                 } else {
                     const DevOp& op = A.ops[k];
                     const cplx* __restrict__ K = op.kern_off >= 0 ? ktab + op.kern_off : A.pool + op.pool_off;
@@ -614,10 +768,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                             const int i0 = insert_zero(insert_zero(insert_zero(item >> LOG_CT, f0), f1), f2) | cm;
                             const int e0 = phys_row<LOG_CT>(i0) * CT + c, e1 = phys_row<LOG_CT>(i0 | tbit) * CT + c;
                             const cplx p0 = sa[e0], p1 = sa[e1], b0 = sb[e0], b1 = sb[e1];
-                            const cplx a0 = cfmac(k10, p1, cfmac(k00, p0, czero()));
-                            const cplx a1 = cfmac(k11, p1, cfmac(k01, p0, czero()));
-                            sa[e0] = a0;
-                            sa[e1] = a1;
+                            sa[e0] = cfmac(k10, p1, cfmac(k00, p0, czero()));
+                            sa[e1] = cfmac(k11, p1, cfmac(k01, p0, czero()));
                             if (has_w) {
                                 W[0] = cfma(b0, p0, W[0]);
                                 W[1] = cfma(b0, p1, W[1]);
@@ -629,12 +781,15 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                         }
                         if (has_w) warp_store_w<4>(W, wslot, lane);
                     } else {
+                        // raw dense op (controlled two-target gates, GENERAL blocks, or a block too small for the tensor
+                        // path): thread per (group, column), local arrays
                         const int dim = op.dim, nq = op.nq;
                         for (int e = tid; e < dim * dim; e += nthr) sk[e] = K[e];
                         __syncthreads();
                         const int nitems = (rows >> nq) << LOG_CT;
-                        cplx wl[16];  // raw dense parametric ops are 4 x 4 (controlled two-target gates)
-                        for (int e = 0; e < 16; ++e) wl[e] = czero();
+                        cplx wl[64];  // parametric dense ops have dim <= 8
+                        if (has_w)
+                            for (int e = 0; e < dim * dim; ++e) wl[e] = czero();
                         for (int item = tid; item < nitems; item += nthr) {
                             const int c = item & (CT - 1);
                             int base = item >> LOG_CT;
@@ -657,26 +812,34 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                                 }
                                 sa[addr[ro]] = acc;
                                 sb[addr[ro]] = bacc;
-                                if (has_w && dim == 4) {
-#pragma unroll
-                                    for (int r2 = 0; r2 < 4; ++r2) wl[r2 * 4 + ro] = cfma(bv[r2], pv[ro], wl[r2 * 4 + ro]);
-                                }
+                                if (has_w)
+                                    for (int r2 = 0; r2 < dim; ++r2) wl[r2 * dim + ro] = cfma(bv[r2], pv[ro], wl[r2 * dim + ro]);
                             }
                         }
-                        if (has_w) warp_store_w<16>(wl, wslot, lane);
+                        if (has_w) {
+                            for (int part = 0; part < dim * dim / 4; ++part) {
+                                double v[8];
+                                for (int e = 0; e < 4; ++e) {
+                                    v[2 * e] = wl[part * 4 + e].x;
+                                    v[2 * e + 1] = wl[part * 4 + e].y;
+                                }
+                                warp_reduce8(v, lane);
+                                if ((lane & 3) == 0) wslot[part * 8 + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)] = v[0];
+                            }
+                        }
                     }
                 }
-                if (have_next && tid < 16) skm[((k - 1) & 1) * 16 + tid] = next_elem;
+                if (have_next && tid < KM_ELEMS) skm[((k - 1) & 1) * KM_ELEMS + tid] = next_elem;
                 __syncthreads();
                 if (has_w) {
                     const int nd = 2 * wdim * wdim;  // doubles
-                    if (tid < nd) {
+                    for (int e = tid; e < nd; e += nthr) {
                         double sum = 0;
                         for (int w = 0; w < nwarps; ++w)
-                            sum += reinterpret_cast<const double*>(swarp + (size_t)(buf * nwarps + w) * A.wmax)[tid];
-                        if (A.w_in_smem) reinterpret_cast<double*>(swacc + s.w_off)[tid] += sum;
+                            sum += reinterpret_cast<const double*>(swarp + (size_t)(buf * nwarps + w) * A.wmax)[e];
+                        if (A.w_in_smem) reinterpret_cast<double*>(swacc + s.w_off)[e] += sum;
                         else
-                            reinterpret_cast<double*>(A.w_part + ((size_t)y * nchunks + chunk) * A.w_total + s.w_off)[tid] = sum;
+                            atomicAdd(reinterpret_cast<double*>(A.w_part + ((size_t)y * nchunks + chunk) * A.w_total + s.w_off) + e, sum);
                     }
                     buf ^= 1;
                 }

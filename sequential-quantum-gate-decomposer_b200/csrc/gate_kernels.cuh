@@ -126,41 +126,24 @@ __device__ inline int build_gate_kernel(int type, const Trig& t, int which, cplx
 }
 
 // ---- fused blocks ------------------------------------------------------------------------------------------------
+// A block is a run of gates acting inside 1, 2 or 3 qubits (dim = 2, 4, 8). One WARP builds the tables of one
+// (parameter set, block): matrices live in shared memory, every lane owns dim*dim/32 (at most 2) entries.
 
-// c = a * b for dim x dim row-major complex matrices (dim = 2 or 4); c must not alias a or b
-__device__ __forceinline__ void mat_mul(const cplx* a, const cplx* b, cplx* c, int dim) {
-    for (int r = 0; r < dim; ++r)
-        for (int cc = 0; cc < dim; ++cc) {
-            cplx acc = czero();
-            for (int l = 0; l < dim; ++l) acc = cfma(a[r * dim + l], b[l * dim + cc], acc);
-            c[r * dim + cc] = acc;
-        }
-}
-
-__device__ __forceinline__ void mat_identity(cplx* m, int dim) {
-    for (int e = 0; e < dim * dim; ++e) m[e] = czero();
-    for (int r = 0; r < dim; ++r) m[r * dim + r] = cmake(1.0, 0.0);
-}
-
-// Embed a member's kernel into the block's basis (local index = bit0 <-> lower qubit, bit1 <-> higher qubit).
+// element (r, c) of a member's kernel embedded into the block's basis (local index bit j <-> j-th ascending block qubit).
 // `deriv`: derivative kernels of controlled gates are ZERO (not identity) where the control bit is 0 -- the reference's
 // convention for derivative matrices (kernels/apply_kernel_to_input.cpp:93-97).
-__device__ __forceinline__ void embed_member(const DevMember& m, const cplx* k, bool deriv, int bdim, cplx* e) {
-    if (bdim == 2 || m.dim == 4) {
-        for (int i = 0; i < bdim * bdim; ++i) e[i] = k[i];
-        return;
+__device__ __forceinline__ cplx embed_elem(const DevMember& m, const cplx* k, bool deriv, int r, int c) {
+    if (m.dim == 2) {
+        const int tl = m.tl;
+        if ((r & ~(1 << tl)) != (c & ~(1 << tl))) return czero();
+        const int tr = (r >> tl) & 1, tc = (c >> tl) & 1;
+        if (m.cl >= 0 && ((r >> m.cl) & 1) == 0) return (deriv || tr != tc) ? czero() : cmake(1.0, 0.0);
+        return k[tr * 2 + tc];
     }
-    const int tl = m.tl, ol = 1 - m.tl;
-    for (int r = 0; r < 4; ++r)
-        for (int c = 0; c < 4; ++c) {
-            const int tr = (r >> tl) & 1, tc = (c >> tl) & 1, orr = (r >> ol) & 1, oc = (c >> ol) & 1;
-            cplx v = czero();
-            if (orr == oc) {
-                if (m.cl >= 0 && orr == 0) v = (deriv || tr != tc) ? czero() : cmake(1.0, 0.0);
-                else v = k[tr * 2 + tc];
-            }
-            e[r * 4 + c] = v;
-        }
+    const int lo = m.tl, hi = m.tl2, mask = (1 << lo) | (1 << hi);
+    if ((r & ~mask) != (c & ~mask)) return czero();
+    const int kr = ((r >> lo) & 1) | (((r >> hi) & 1) << 1), kc = ((c >> lo) & 1) | (((c >> hi) & 1) << 1);
+    return k[kr * 4 + kc];
 }
 
 __device__ __forceinline__ void member_trig(const DevMember& m, const double* __restrict__ params, Trig& t) {
@@ -181,70 +164,109 @@ __device__ __forceinline__ void member_kernel(const DevMember& m, const Trig& t,
     build_gate_kernel(m.type, t, which, k);
 }
 
+// out = a * b (dim x dim, row-major) by one warp; out must not alias a or b
+__device__ __forceinline__ void warp_mat_mul(const cplx* a, const cplx* b, cplx* out, int dim, int lane) {
+    for (int i = lane; i < dim * dim; i += 32) {
+        const int r = i / dim, c = i - r * dim;
+        cplx acc = czero();
+        for (int l = 0; l < dim; ++l) acc = cfma(a[r * dim + l], b[l * dim + c], acc);
+        out[i] = acc;
+    }
+    __syncwarp();
+}
+
 // Block matrix M = E_{m-1} ... E_0 and, for every parameter p of member j, dM_p = (E_{m-1}..E_{j+1}) dE_{j,p} (E_{j-1}..E_0).
 // This is the product rule the reference evaluates with full-size matrices (Gates_block::apply_derivate_to,
-// Gates_block.cpp:1011-1150), restricted to the 4 x 4 space the run of gates acts on.
-__device__ inline void build_block(const DevOp& op, const DevMember* __restrict__ members, const double* __restrict__ params,
-                                   const cplx* __restrict__ pool, cplx* __restrict__ kdst, cplx* __restrict__ dkdst,
-                                   bool with_deriv) {
+// Gates_block.cpp:1011-1150), restricted to the 2^k-dimensional space the run of gates acts on.
+// Pass 1 walks the members forward and parks the running prefix in each parameter's output slot; pass 2 walks
+// backward with the running suffix and finishes dM_p = suffix * dE * prefix in place.
+// ws: 3 * 64 complex of shared memory owned by the warp.
+__device__ inline void build_block_warp(const DevOp& op, const DevMember* __restrict__ members, const double* __restrict__ params,
+                                        const cplx* __restrict__ pool, cplx* __restrict__ kdst, cplx* __restrict__ dkdst,
+                                        bool with_deriv, cplx* ws, int lane) {
     const int dim = op.dim, d2 = dim * dim, nm = op.n_members;
-    cplx pre[SQ_MAX_MEMBERS + 1][16];  // pre[j] = E_{j-1} ... E_0
-    cplx k[16], e[16], tmp[16];
-    mat_identity(pre[0], dim);
+    cplx* R = ws;        // running prefix / suffix
+    cplx* E = ws + 64;   // embedded member
+    cplx* T = ws + 128;  // product scratch
+    cplx k[16];
+    for (int i = lane; i < d2; i += 32) R[i] = (i / dim == i % dim) ? cmake(1.0, 0.0) : czero();
+    __syncwarp();
     for (int j = 0; j < nm; ++j) {
         const DevMember m = members[op.member_off + j];
+        if (with_deriv)
+            for (int p = 0; p < m.n_params; ++p)
+                for (int i = lane; i < d2; i += 32) dkdst[(size_t)(m.slot0 + p) * d2 + i] = R[i];
         Trig t;
         member_trig(m, params, t);
         member_kernel(m, t, -1, pool, k);
-        embed_member(m, k, false, dim, e);
-        mat_mul(e, pre[j], pre[j + 1], dim);
+        for (int i = lane; i < d2; i += 32) E[i] = embed_elem(m, k, false, i / dim, i % dim);
+        __syncwarp();
+        warp_mat_mul(E, R, T, dim, lane);
+        for (int i = lane; i < d2; i += 32) R[i] = T[i];
+        __syncwarp();
     }
-    for (int i = 0; i < d2; ++i) kdst[i] = pre[nm][i];
+    for (int i = lane; i < d2; i += 32) kdst[i] = R[i];
     if (!with_deriv || op.n_params == 0) return;
-    cplx suf[16];  // E_{m-1} ... E_{j+1}
-    mat_identity(suf, dim);
+    __syncwarp();
+    for (int i = lane; i < d2; i += 32) R[i] = (i / dim == i % dim) ? cmake(1.0, 0.0) : czero();  // suffix
+    __syncwarp();
     for (int j = nm - 1; j >= 0; --j) {
         const DevMember m = members[op.member_off + j];
         Trig t;
         member_trig(m, params, t);
         for (int p = 0; p < m.n_params; ++p) {
+            cplx* dd = dkdst + (size_t)(m.slot0 + p) * d2;  // holds the prefix E_{j-1}..E_0
             member_kernel(m, t, p, pool, k);
-            embed_member(m, k, true, dim, e);
-            mat_mul(e, pre[j], tmp, dim);
-            cplx* dd = dkdst + (size_t)(m.slot0 + p) * d2;
-            // dd = suf * tmp
-            for (int r = 0; r < dim; ++r)
-                for (int cc = 0; cc < dim; ++cc) {
-                    cplx acc = czero();
-                    for (int l = 0; l < dim; ++l) acc = cfma(suf[r * dim + l], tmp[l * dim + cc], acc);
-                    dd[r * dim + cc] = acc;
-                }
+            for (int i = lane; i < d2; i += 32) E[i] = embed_elem(m, k, true, i / dim, i % dim);
+            __syncwarp();
+            // T = dE * prefix (prefix read from global: written by this warp in pass 1)
+            for (int i = lane; i < d2; i += 32) {
+                const int r = i / dim, c = i - r * dim;
+                cplx acc = czero();
+                for (int l = 0; l < dim; ++l) acc = cfma(E[r * dim + l], dd[l * dim + c], acc);
+                T[i] = acc;
+            }
+            __syncwarp();
+            // dd = suffix * T
+            for (int i = lane; i < d2; i += 32) {
+                const int r = i / dim, c = i - r * dim;
+                cplx acc = czero();
+                for (int l = 0; l < dim; ++l) acc = cfma(R[r * dim + l], T[l * dim + c], acc);
+                dd[i] = acc;
+            }
+            __syncwarp();
         }
         member_kernel(m, t, -1, pool, k);
-        embed_member(m, k, false, dim, e);
-        mat_mul(suf, e, tmp, dim);
-        for (int i = 0; i < d2; ++i) suf[i] = tmp[i];
+        for (int i = lane; i < d2; i += 32) E[i] = embed_elem(m, k, false, i / dim, i % dim);
+        __syncwarp();
+        warp_mat_mul(R, E, T, dim, lane);
+        for (int i = lane; i < d2; i += 32) R[i] = T[i];
+        __syncwarp();
     }
 }
 
-// One thread per (parameter set b, op): fills the forward kernel table and the derivative kernel table.
+// One warp per (parameter set b, op): fills the forward kernel table and the derivative kernel table.
 // ktab[b * kern_total + op.kern_off + ...], dktab[b * dkern_total + op.dkern_off + slot * dim*dim + ...].
-__global__ void build_kernel_tables(const DevOp* __restrict__ ops, int n_ops, const DevMember* __restrict__ members,
-                                    const double* __restrict__ params, int n_params, int batch,
-                                    const cplx* __restrict__ pool, cplx* __restrict__ ktab, int kern_total,
-                                    cplx* __restrict__ dktab, int dkern_total, int with_deriv) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= batch * n_ops) return;
-    const int b = idx / n_ops;
-    const DevOp op = ops[idx - b * n_ops];
+static const int TABLE_WARPS = 4;
+__global__ void __launch_bounds__(TABLE_WARPS * 32) build_kernel_tables(
+    const DevOp* __restrict__ ops, int n_ops, const DevMember* __restrict__ members, const double* __restrict__ params,
+    int n_params, int batch, const cplx* __restrict__ pool, cplx* __restrict__ ktab, int kern_total,
+    cplx* __restrict__ dktab, int dkern_total, int with_deriv) {
+    __shared__ cplx ws[TABLE_WARPS][192];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long idx = (long long)blockIdx.x * TABLE_WARPS + warp;
+    if (idx >= (long long)batch * n_ops) return;
+    const int b = (int)(idx / n_ops);
+    const DevOp op = ops[idx - (long long)b * n_ops];
     if (op.kern_off < 0) return;  // constant kernel (raw GENERAL) lives in the pool
     const double* __restrict__ pb = params + (size_t)b * n_params;
     cplx* kdst = ktab + (size_t)b * kern_total + op.kern_off;
     cplx* dkdst = dktab + (size_t)b * dkern_total + (op.dkern_off >= 0 ? op.dkern_off : 0);
     if (op.type == SQ_OP_BLOCK) {
-        build_block(op, members, pb, pool, kdst, dkdst, with_deriv != 0);
+        build_block_warp(op, members, pb, pool, kdst, dkdst, with_deriv != 0, ws[warp], lane);
         return;
     }
+    if (lane != 0) return;
     Trig t;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {

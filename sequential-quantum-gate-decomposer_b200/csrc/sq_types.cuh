@@ -58,17 +58,17 @@ struct DevOp {
 // A gate inside a fused block, in block-local coordinates.
 struct DevMember {
     int32_t type;         // sqgpu_gate_type
-    int32_t dim;          // 2: 1-qubit kernel (optionally controlled by the block's other qubit); 4: two-target kernel
-    int32_t tl;           // dim == 2: local target bit (0/1)
+    int32_t dim;          // 2: 1-qubit kernel (optionally controlled by another block qubit); 4: two-target kernel
+    int32_t tl;           // local bit of the target (dim == 2) / of the lower target (dim == 4)
     int32_t cl;           // dim == 2: local control bit or -1
     int32_t param_start;  // first parameter in the circuit's parameter vector
     int32_t n_params;
     int32_t slot0;        // index of the member's first derivative kernel inside the block's derivative table
-    int32_t pad;
+    int32_t tl2;          // dim == 4: local bit of the higher target
     int64_t pool_off;     // GENERAL members: constant kernel in the pool
 };
 
-static const int SQ_MAX_MEMBERS = 12;  // gates per fused block (local scratch of the table builder)
+static const int SQ_MAX_MEMBERS = 24;  // gates per fused block
 
 // insert a zero bit at position t of idx (all higher bits move up)
 __host__ __device__ __forceinline__ int insert_zero(int idx, int t) {

@@ -101,6 +101,20 @@ struct KernelTimer {  // CUDA-event timing of the dominant kernel on the launchi
 
 }  // namespace
 
+// A lowered device program. Two are kept per circuit: `plan2` fuses gate runs inside at most two qubits (4 x 4 blocks;
+// used by the streaming / apply / VQE paths, whose kernels stop at two-qubit blocks) and `plan3` inside at most three
+// qubits (8 x 8 blocks on the FP64 tensor cores; used by the shared-memory executor).
+struct Plan {
+    std::vector<DevOp> ops;          // device program (fused blocks + raw ops)
+    std::vector<DevMember> members;  // gates inside the fused blocks
+    std::vector<int> param_op;       // parameter -> op that owns it
+    std::vector<int> param_slot;     // parameter -> index of its derivative kernel inside that op
+    DevBuf dOps, dMembers, dParamOp;
+    DevBuf wKtab, wDKtab;            // per-parameter-set kernel tables (workspace)
+    int n_ops = 0, kern_total = 0, dkern_total = 0, w_total = 0, wmax = 4;
+    int dense_stage = 0;             // complex elements of kernel staging the executor's generic dense path needs
+};
+
 struct sqgpu_ctx {
     int device = 0;
     int sm_count = 148;
@@ -113,14 +127,11 @@ struct sqgpu_ctx {
     int rows = 0, cols = 0;
 
     // circuit
-    std::vector<DevOp> ops;          // device program (fused blocks + raw ops)
-    std::vector<DevMember> members;  // gates inside the fused blocks
-    std::vector<int> param_op;       // parameter -> op that owns it
-    std::vector<int> param_slot;     // parameter -> index of its derivative kernel inside that op
-    DevBuf dOps, dMembers, dParamOp, dPool;
-    int n_params = 0, qbit_num = 0, n_ops = 0, n_gates = 0;
-    int kern_total = 0, dkern_total = 0, w_total = 0, wmax = 4;
-    bool has_dense = false, all_unitary = true, circuit_set = false;
+    Plan plan2, plan3;
+    Plan* P = &plan2;                // plan the helpers below operate on (set by the entry point, under the mutex)
+    DevBuf dPool;
+    int n_params = 0, qbit_num = 0, n_gates = 0;
+    bool all_unitary = true, circuit_set = false;
     std::vector<cplx> pool;
 
     // cost configuration
@@ -128,7 +139,7 @@ struct sqgpu_ctx {
     int trace_offset = 0;
 
     // workspaces
-    DevBuf wParams, wKtab, wDKtab, wTrPart, wWPart, wTraces, wOmega, wCost, wGrad, wMat, wDerivIdx, wTraces0;
+    DevBuf wParams, wTrPart, wWPart, wTraces, wOmega, wCost, wGrad, wMat, wDerivIdx, wTraces0;
 
     // Hamiltonian (VQE)
     DevBuf hIndptr, hIndices, hValues;
@@ -366,10 +377,10 @@ struct FusedPlan {
     size_t smem = 0;
 };
 
-size_t fused_smem(int mode, int rows, int ct, int threads, bool has_dense, int wmax, int w_total, bool w_in_smem, int n_ops) {
+size_t fused_smem(int mode, int rows, int ct, int threads, int dense_stage, int wmax, int w_total, bool w_in_smem, int n_ops) {
     size_t s = (size_t)rows * ct * sizeof(cplx) * (mode == MODE_GRAD ? 2 : 1);
-    if (has_dense) s += (size_t)DENSE_STAGE * sizeof(cplx);
-    s += 32 * sizeof(cplx);                  // prefetched block kernels
+    s += (size_t)dense_stage * sizeof(cplx);
+    s += 2 * KM_ELEMS * sizeof(cplx);        // prefetched block kernels
     s += (size_t)n_ops * sizeof(SOp);        // staged op table
     const int nwarps = threads / 32;
     if (mode == MODE_GRAD) {
@@ -389,27 +400,36 @@ FusedPlan plan_fused(const sqgpu_ctx* c, int mode, int rows, int cols, int ysets
     const size_t budget = (size_t)c->smem_optin;
     int max_log = 3;
     while ((1 << max_log) > cols && max_log > 0) --max_log;  // no wider than the matrix (cols = 1: state vector)
-    for (int lc = max_log; lc >= 0; --lc) {
+    const bool grad = mode == MODE_GRAD;
+    auto threads_for = [&](int ct) {
+        const int items = (rows / 4) * ct;  // groups of a two-qubit block
+        return std::min(FUSED_THREADS, std::max(64, (items + 31) / 32 * 32));  // >= 64: the 8 x 8 block kernel prefetch
+    };
+    // widest tile that fits; the W accumulator lives in shared memory when it fits beside that tile, otherwise in the
+    // CTA's own slice of w_part in global memory
+    int pick = -1;
+    bool pick_wsm = false;
+    for (int lc = max_log; lc >= 0 && pick < 0; --lc) {
         const int ct = 1 << lc;
-        int items = (rows / 4) * ct;  // groups of a 4x4 block
-        int threads = std::min(FUSED_THREADS, std::max(32, (items + 31) / 32 * 32));
-        const bool grad = mode == MODE_GRAD;
-        bool wsm = grad && c->w_total > 0;
-        size_t s = fused_smem(mode, rows, ct, threads, c->has_dense, c->wmax, c->w_total, wsm, c->n_ops);
-        if (s > budget && wsm) {
-            wsm = false;
-            s = fused_smem(mode, rows, ct, threads, c->has_dense, c->wmax, c->w_total, false, c->n_ops);
+        const bool can_wsm = grad && c->P->w_total > 0;
+        if (can_wsm && fused_smem(mode, rows, ct, threads_for(ct), c->P->dense_stage, c->P->wmax, c->P->w_total, true, c->P->n_ops) <= budget) {
+            pick = lc;
+            pick_wsm = true;
+        } else if (fused_smem(mode, rows, ct, threads_for(ct), c->P->dense_stage, c->P->wmax, c->P->w_total, false, c->P->n_ops) <= budget) {
+            pick = lc;
+            pick_wsm = false;
         }
-        if (s > budget) continue;
-        // prefer tiles that leave shared memory for the W accumulator: a narrower tile with W in smem beats a wider
-        // one without only when the wider one cannot hold W; keep the first (widest) fit.
+    }
+    if (pick < 0) return p;
+    {
+        const int lc = pick, ct = 1 << lc;
         p.ok = true;
         p.log_ct = lc;
-        p.threads = threads;
-        p.smem = s;
-        p.w_in_smem = wsm;
+        p.threads = threads_for(ct);
+        p.w_in_smem = pick_wsm;
+        p.smem = fused_smem(mode, rows, ct, p.threads, c->P->dense_stage, c->P->wmax, c->P->w_total, pick_wsm, c->P->n_ops);
         p.tiles = (cols + ct - 1) / ct;
-        if (grad && !wsm) {
+        if (mode == MODE_APPLY) {
             p.tiles_per_cta = 1;
             p.chunks = p.tiles;
         } else {
@@ -418,11 +438,6 @@ FusedPlan plan_fused(const sqgpu_ctx* c, int mode, int rows, int cols, int ysets
             p.tiles_per_cta = (p.tiles + chunks - 1) / chunks;
             p.chunks = (p.tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
         }
-        if (mode == MODE_APPLY) {
-            p.tiles_per_cta = 1;
-            p.chunks = p.tiles;
-        }
-        return p;
     }
     return p;
 }
@@ -451,14 +466,14 @@ cudaError_t launch_fused_mode(const ExecArgs& a, const FusedPlan& p, int ysets, 
 
 int run_tables(sqgpu_ctx* c, const double* d_params, int batch, bool with_deriv, cudaStream_t st) {
     int rc;
-    if ((rc = c->wKtab.ensure(std::max<size_t>(1, (size_t)batch * c->kern_total) * sizeof(cplx)))) return rc;
-    if ((rc = c->wDKtab.ensure(std::max<size_t>(1, (size_t)batch * c->dkern_total) * sizeof(cplx)))) return rc;
-    const long long total = (long long)batch * c->n_ops;
+    if ((rc = c->P->wKtab.ensure(std::max<size_t>(1, (size_t)batch * c->P->kern_total) * sizeof(cplx)))) return rc;
+    if ((rc = c->P->wDKtab.ensure(std::max<size_t>(1, (size_t)batch * c->P->dkern_total) * sizeof(cplx)))) return rc;
+    const long long total = (long long)batch * c->P->n_ops;
     if (total == 0) return SQGPU_OK;
-    const int thr = 64;
-    build_kernel_tables<<<(unsigned)((total + thr - 1) / thr), thr, 0, st>>>(
-        c->dOps.as<DevOp>(), c->n_ops, c->dMembers.as<DevMember>(), d_params, c->n_params, batch, c->dPool.as<cplx>(),
-        c->wKtab.as<cplx>(), c->kern_total, c->wDKtab.as<cplx>(), c->dkern_total, with_deriv ? 1 : 0);
+    // one warp per (parameter set, op)
+    build_kernel_tables<<<(unsigned)((total + TABLE_WARPS - 1) / TABLE_WARPS), TABLE_WARPS * 32, 0, st>>>(
+        c->P->dOps.as<DevOp>(), c->P->n_ops, c->P->dMembers.as<DevMember>(), d_params, c->n_params, batch, c->dPool.as<cplx>(),
+        c->P->wKtab.as<cplx>(), c->P->kern_total, c->P->wDKtab.as<cplx>(), c->P->dkern_total, with_deriv ? 1 : 0);
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     return SQGPU_OK;
@@ -473,16 +488,16 @@ void fill_common_args(const sqgpu_ctx* c, const FusedPlan& p, ExecArgs& a, int r
     a.log_ct = p.log_ct;
     a.tiles = p.tiles;
     a.tiles_per_cta = p.tiles_per_cta;
-    a.ops = c->dOps.as<DevOp>();
-    a.n_ops = c->n_ops;
-    a.ktab = c->wKtab.as<cplx>();
-    a.kern_total = c->kern_total;
-    a.dktab = c->wDKtab.as<cplx>();
-    a.dkern_total = c->dkern_total;
+    a.ops = c->P->dOps.as<DevOp>();
+    a.n_ops = c->P->n_ops;
+    a.ktab = c->P->wKtab.as<cplx>();
+    a.kern_total = c->P->kern_total;
+    a.dktab = c->P->wDKtab.as<cplx>();
+    a.dkern_total = c->P->dkern_total;
     a.pool = c->dPool.as<cplx>();
-    a.has_dense = c->has_dense ? 1 : 0;
-    a.wmax = c->wmax;
-    a.w_total = c->w_total;
+    a.dense_stage = c->P->dense_stage;
+    a.wmax = c->P->wmax;
+    a.w_total = c->P->w_total;
     a.w_in_smem = p.w_in_smem ? 1 : 0;
 }
 
@@ -509,7 +524,7 @@ int run_exec_resident(sqgpu_ctx* c, int batch, bool grad, const cplx* d_omega, d
     if (!p.ok) return run_exec_streaming(c, batch, grad, d_omega, d_traces, st);  // column too tall for shared memory
     int rc;
     if ((rc = c->wTrPart.ensure((size_t)batch * p.chunks * 6 * sizeof(double)))) return rc;
-    if (grad && (rc = c->wWPart.ensure(std::max<size_t>(1, (size_t)batch * p.chunks * c->w_total) * sizeof(cplx)))) return rc;
+    if (grad && (rc = c->wWPart.ensure(std::max<size_t>(1, (size_t)batch * p.chunks * c->P->w_total) * sizeof(cplx)))) return rc;
     ExecArgs a;
     fill_common_args(c, p, a, c->rows, c->cols);
     a.in = c->U.as<cplx>();
@@ -520,14 +535,16 @@ int run_exec_resident(sqgpu_ctx* c, int batch, bool grad, const cplx* d_omega, d
     a.tr_part = c->wTrPart.as<double>();
     a.w_part = c->wWPart.as<cplx>();
     a.omega = d_omega;
+    if (grad && !p.w_in_smem && c->P->w_total > 0)
+        CUDA_TRY(cudaMemsetAsync(c->wWPart.p, 0, (size_t)batch * p.chunks * c->P->w_total * sizeof(cplx), st));
     time_begin(c, grad ? "fused_exec<GRAD>" : "fused_exec<COST>", st);
     cudaError_t e = grad ? launch_fused_mode<MODE_GRAD>(a, p, batch, st) : launch_fused_mode<MODE_COST>(a, p, batch, st);
     time_end(c, st);
     c->launches++;
     if (e != cudaSuccess) return fail(SQGPU_ERR_CUDA, "fused_exec launch failed: %s", cudaGetErrorString(e));
-    reduce_partials<<<batch, 128, 0, st>>>(c->wTrPart.as<double>(), p.chunks, c->wWPart.as<cplx>(), c->w_total,
-                                           c->dOps.as<DevOp>(), c->dParamOp.as<int>(), c->dParamOp.as<int>() + std::max(c->n_params, 1),
-                                           c->wDKtab.as<cplx>(), c->dkern_total, c->wKtab.as<cplx>(), c->kern_total, c->n_params, grad ? 1 : 0, d_traces);
+    reduce_partials<<<batch, 128, 0, st>>>(c->wTrPart.as<double>(), p.chunks, c->wWPart.as<cplx>(), c->P->w_total,
+                                           c->P->dOps.as<DevOp>(), c->P->dParamOp.as<int>(), c->P->dParamOp.as<int>() + std::max(c->n_params, 1),
+                                           c->P->wDKtab.as<cplx>(), c->P->dkern_total, c->P->wKtab.as<cplx>(), c->P->kern_total, c->n_params, grad ? 1 : 0, d_traces);
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     return SQGPU_OK;
@@ -549,9 +566,9 @@ int batch_slice(const sqgpu_ctx* c, int batch, bool grad) {
         FusedPlan pf = plan_fused(c, grad ? MODE_GRAD : MODE_COST, c->rows, c->cols, batch);
         if (!pf.ok) return std::min(batch, 32);  // streaming fallback: bound the replicated chunk workspace
     }
-    if (!grad || c->w_total == 0) return std::min(batch, 65535);
+    if (!grad || c->P->w_total == 0) return std::min(batch, 65535);
     FusedPlan p = plan_fused(c, MODE_GRAD, c->rows, c->cols, batch);
-    const size_t per = (size_t)std::max(1, p.chunks) * c->w_total * sizeof(cplx);
+    const size_t per = (size_t)std::max(1, p.chunks) * c->P->w_total * sizeof(cplx);
     const size_t lim = (size_t)1536 << 20;
     return (int)std::max<size_t>(1, std::min<size_t>((size_t)std::min(batch, 65535), lim / std::max<size_t>(per, 1)));
 }
@@ -562,6 +579,9 @@ int traces_dev(sqgpu_ctx* c, const double* d_params, int batch, bool with_grad, 
     int rc = check_ready(c, true);
     if (rc) return rc;
     if (batch <= 0) return SQGPU_OK;
+    // three-qubit blocks for the shared-memory executor, two-qubit blocks for the streaming fallback
+    c->P = &c->plan3;
+    if (!plan_fused(c, with_grad ? MODE_GRAD : MODE_COST, c->rows, c->cols, batch).ok) c->P = &c->plan2;
     if (c->cols + effective_offset(c) > c->rows) return fail(SQGPU_ERR_INVALID, "trace_offset %d + cols %d exceeds rows %d", effective_offset(c), c->cols, c->rows);
     if (with_grad && !c->all_unitary) return fail(SQGPU_ERR_UNSUPPORTED, "gradient with a non-unitary GENERAL gate is not supported (the adjoint sweep needs K^-1 = K^dagger)");
     const bool hs_corr = c->cfg.variant == SQGPU_HILBERT_SCHMIDT_TEST_CORRECTION1 || c->cfg.variant == SQGPU_HILBERT_SCHMIDT_TEST_CORRECTION2;
@@ -730,9 +750,9 @@ int apply_program_dev(sqgpu_ctx* c, const cplx* d_in, long long in_ystride, cplx
         cplx* dst = d_out + (size_t)y * out_ystride;
         if (src != dst) CUDA_TRY(cudaMemcpyAsync(dst, src, n_elem * sizeof(cplx), cudaMemcpyDeviceToDevice, st));
     }
-    for (int k = 0; k < c->n_ops; ++k) {
-        const DevOp& op = c->ops[k];
-        const cplx* Kf = op.kern_off >= 0 ? c->wKtab.as<cplx>() + op.kern_off : c->dPool.as<cplx>() + op.pool_off;
+    for (int k = 0; k < c->P->n_ops; ++k) {
+        const DevOp& op = c->P->ops[k];
+        const cplx* Kf = op.kern_off >= 0 ? c->P->wKtab.as<cplx>() + op.kern_off : c->dPool.as<cplx>() + op.pool_off;
         if (!deriv_op) {
             if ((rc = launch_stream_gate(c, op, false, d_out, out_ystride, ysets, rows, cols, cols, Kf, 0, st))) return rc;
             continue;
@@ -744,7 +764,7 @@ int apply_program_dev(sqgpu_ctx* c, const cplx* d_in, long long in_ystride, cplx
             int y1 = y + 1;
             if (!d)
                 while (y1 < ysets && (*deriv_op)[y1] != k) ++y1;
-            const cplx* K = d ? c->wDKtab.as<cplx>() + op.dkern_off + (size_t)(*deriv_p)[y] * op.dim * op.dim : Kf;
+            const cplx* K = d ? c->P->wDKtab.as<cplx>() + op.dkern_off + (size_t)(*deriv_p)[y] * op.dim * op.dim : Kf;
             if ((rc = launch_stream_gate(c, op, d, d_out + (size_t)y * out_ystride, out_ystride, y1 - y, rows, cols, cols, K, 0, st))) return rc;
             y = y1;
         }
@@ -758,7 +778,7 @@ int apply_program_dev(sqgpu_ctx* c, const cplx* d_in, long long in_ystride, cplx
 int run_exec_streaming(sqgpu_ctx* c, int batch, bool grad, const cplx* d_omega, double* d_traces, cudaStream_t st) {
     const int rows = c->rows, cols = c->cols;
     if (grad)
-        for (const DevOp& op : c->ops) {
+        for (const DevOp& op : c->P->ops) {
             const bool ok = op.dim == 2 || (op.dim == 4 && op.nq == 2 && op.ctrl_mask == 0);
             if (!ok) return fail(SQGPU_ERR_UNSUPPORTED, "streaming gradient with 3+ qubit dense or controlled two-target gates is not implemented (n = %d)", c->qbit_num);
         }
@@ -770,7 +790,7 @@ int run_exec_streaming(sqgpu_ctx* c, int batch, bool grad, const cplx* d_omega, 
     int rc;
     if ((rc = c->wMat.ensure((size_t)(grad ? 2 : 1) * batch * chunk_elems * sizeof(cplx)))) return rc;
     if ((rc = c->wTrPart.ensure(((size_t)batch * nchunks * 6 + (size_t)batch * nblk * 32) * sizeof(double)))) return rc;
-    if (grad && (rc = c->wWPart.ensure(std::max<size_t>(1, (size_t)batch * nchunks * c->w_total) * sizeof(cplx)))) return rc;
+    if (grad && (rc = c->wWPart.ensure(std::max<size_t>(1, (size_t)batch * nchunks * c->P->w_total) * sizeof(cplx)))) return rc;
     cplx* A = c->wMat.as<cplx>();
     cplx* Bt = A + (size_t)batch * chunk_elems;
     double* tr_part = c->wTrPart.as<double>();
@@ -783,10 +803,10 @@ int run_exec_streaming(sqgpu_ctx* c, int batch, bool grad, const cplx* d_omega, 
         const size_t ce = (size_t)rows * w;
         copy_chunk<<<dim3(std::min(c->sm_count * 8, std::max(1, (int)(ce / 256))), batch), 256, 0, st>>>(c->U.as<cplx>(), cols, j0, rows, w, A);
         c->launches++;
-        for (int k = 0; k < c->n_ops; ++k) {
-            const DevOp& op = c->ops[k];
-            const cplx* K = op.kern_off >= 0 ? c->wKtab.as<cplx>() + op.kern_off : c->dPool.as<cplx>() + op.pool_off;
-            const long long kst = op.kern_off >= 0 ? c->kern_total : 0;
+        for (int k = 0; k < c->P->n_ops; ++k) {
+            const DevOp& op = c->P->ops[k];
+            const cplx* K = op.kern_off >= 0 ? c->P->wKtab.as<cplx>() + op.kern_off : c->dPool.as<cplx>() + op.pool_off;
+            const long long kst = op.kern_off >= 0 ? c->P->kern_total : 0;
             if ((rc = launch_stream_gate(c, op, false, A, (long long)ce, batch, rows, w, w, K, kst, st))) return rc;
         }
         // per-chunk traces land at tr_part[y][ch][6]: launch with out pointing at chunk ch and stride nchunks*6
@@ -796,10 +816,10 @@ int run_exec_streaming(sqgpu_ctx* c, int batch, bool grad, const cplx* d_omega, 
         CUDA_TRY(cudaMemsetAsync(Bt, 0, (size_t)batch * ce * sizeof(cplx), st));
         beta_init_stream<<<dim3((w + 127) / 128, batch), 128, 0, st>>>(Bt, rows, w, j0, c->qbit_num, off, ntt, d_omega);
         c->launches++;
-        for (int k = c->n_ops - 1; k >= 0; --k) {
-            const DevOp& op = c->ops[k];
-            const cplx* K = op.kern_off >= 0 ? c->wKtab.as<cplx>() + op.kern_off : c->dPool.as<cplx>() + op.pool_off;
-            const long long kst = op.kern_off >= 0 ? c->kern_total : 0;
+        for (int k = c->P->n_ops - 1; k >= 0; --k) {
+            const DevOp& op = c->P->ops[k];
+            const cplx* K = op.kern_off >= 0 ? c->P->wKtab.as<cplx>() + op.kern_off : c->dPool.as<cplx>() + op.pool_off;
+            const long long kst = op.kern_off >= 0 ? c->P->kern_total : 0;
             StreamGate g = make_stream_gate(op, A, (long long)ce, rows, w, w, K, kst);
             const int want_w = op.n_params > 0 ? 1 : 0;
             int blocks, width;
@@ -817,17 +837,17 @@ int run_exec_streaming(sqgpu_ctx* c, int batch, bool grad, const cplx* d_omega, 
             c->launches++;
             if (want_w) {
                 sum_partials<<<batch, 32, 0, st>>>(wscratch, blocks, width, 1.0,
-                                                   reinterpret_cast<double*>(c->wWPart.as<cplx>() + (size_t)ch * c->w_total + op.w_off),
-                                                   2 * nchunks * c->w_total);
+                                                   reinterpret_cast<double*>(c->wWPart.as<cplx>() + (size_t)ch * c->P->w_total + op.w_off),
+                                                   2 * nchunks * c->P->w_total);
                 c->launches++;
             }
         }
     }
     time_end(c, st);
     CUDA_TRY(cudaGetLastError());
-    reduce_partials<<<batch, 128, 0, st>>>(tr_part, nchunks, c->wWPart.as<cplx>(), c->w_total, c->dOps.as<DevOp>(), c->dParamOp.as<int>(),
-                                           c->dParamOp.as<int>() + std::max(c->n_params, 1), c->wDKtab.as<cplx>(), c->dkern_total,
-                                           c->wKtab.as<cplx>(), c->kern_total, c->n_params, grad ? 1 : 0, d_traces);
+    reduce_partials<<<batch, 128, 0, st>>>(tr_part, nchunks, c->wWPart.as<cplx>(), c->P->w_total, c->P->dOps.as<DevOp>(), c->P->dParamOp.as<int>(),
+                                           c->P->dParamOp.as<int>() + std::max(c->n_params, 1), c->P->wDKtab.as<cplx>(), c->P->dkern_total,
+                                           c->P->wKtab.as<cplx>(), c->P->kern_total, c->n_params, grad ? 1 : 0, d_traces);
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     return SQGPU_OK;
@@ -909,7 +929,7 @@ int sqgpu_destroy(sqgpu_handle_t c) {
         DeviceGuard guard(c->device);
         std::lock_guard<std::mutex> lk(c->mtx);
         cudaStreamSynchronize(c->stream);
-        DevBuf* bufs[] = {&c->U, &c->dOps, &c->dMembers, &c->dParamOp, &c->dPool, &c->wParams, &c->wKtab, &c->wDKtab, &c->wTrPart, &c->wWPart,
+        DevBuf* bufs[] = {&c->U, &c->plan2.dOps, &c->plan2.dMembers, &c->plan2.dParamOp, &c->plan2.wKtab, &c->plan2.wDKtab, &c->plan3.dOps, &c->plan3.dMembers, &c->plan3.dParamOp, &c->plan3.wKtab, &c->plan3.wDKtab, &c->dPool, &c->wParams, &c->wTrPart, &c->wWPart,
                           &c->wTraces, &c->wOmega, &c->wCost, &c->wGrad, &c->wMat, &c->wDerivIdx, &c->wTraces0,
                           &c->hIndptr, &c->hIndices, &c->hValues};
         for (DevBuf* b : bufs) b->release();
@@ -965,128 +985,149 @@ int sqgpu_set_circuit(sqgpu_handle_t c, const sqgpu_gate_desc* gates, int n_gate
     for (int p = 0; p < n_params; ++p)
         if (!param_used[p]) return fail(SQGPU_ERR_INVALID, "parameter %d is not used by any gate", p);
 
-    // 2. plan: fuse runs of consecutive gates whose joint support is at most two qubits into one dense block
+    // 2. plan: fuse runs of consecutive gates whose joint support is at most `max_q` qubits into one dense block
     //    (the device-side analogue of Gates_block's <=2-qubit fusion rule, Gates_block.cpp:632-681, applied to the
-    //    flattened circuit and extended to the gradient by the product rule in build_block)
+    //    flattened circuit and extended to the gradient by the product rule in build_block_warp)
     const char* nf = getenv("SQGPU_NO_FUSE");
     const bool fuse = !(nf && nf[0] == '1');
-    std::vector<DevOp> ops;
-    std::vector<DevMember> members;
-    std::vector<int> param_op(std::max(n_params, 1), -1), param_slot(std::max(n_params, 1), 0);
-    int kern_total = 0, dkern_total = 0, w_total = 0, wmax = 4;
-    bool has_dense = false;
-    std::vector<int> pend;
-    unsigned pend_support = 0;
-
-    auto finish_op = [&](DevOp& op) {
-        const int d2 = op.dim * op.dim;
-        if (!(op.type == SQGPU_GENERAL)) {
-            op.kern_off = kern_total;
-            kern_total += d2;
-        }
-        if (op.dim > 2) has_dense = true;
-        if (op.n_params > 0) {
-            op.dkern_off = dkern_total;
-            dkern_total += d2 * op.n_params;
-            op.w_off = w_total;
-            w_total += d2;
-            wmax = std::max(wmax, d2);
-        }
-        ops.push_back(op);
-    };
-    auto flush = [&]() {
-        if (pend.empty()) return;
-        DevOp b;
-        memset(&b, 0, sizeof(b));
-        b.type = SQ_OP_BLOCK;
-        b.kern_off = b.dkern_off = b.w_off = -1;
-        int qs[2], nqs = 0;
-        for (int q = 0; q < 30; ++q)
-            if ((pend_support >> q) & 1) qs[nqs++] = q;
-        if (nqs == 1) {
-            b.dim = 2;
-            b.target = qs[0];
-        } else {
-            b.dim = 4;
-            b.nq = 2;
-            b.q[0] = qs[0];
-            b.q[1] = qs[1];
-        }
-        b.member_off = (int)members.size();
-        b.n_members = (int)pend.size();
-        int slot = 0;
-        for (int gi : pend) {
-            const DevOp& r = raw[gi];
-            DevMember m;
-            memset(&m, 0, sizeof(m));
-            m.type = r.type;
-            m.dim = r.dim;
-            m.tl = (r.dim == 2 && nqs == 2 && r.target == qs[1]) ? 1 : 0;
-            m.cl = (r.dim == 2 && r.ctrl_mask) ? 1 - m.tl : -1;
-            m.param_start = r.param_start;
-            m.n_params = r.n_params;
-            m.slot0 = slot;
-            m.pool_off = r.pool_off;
-            for (int p = 0; p < r.n_params; ++p) {
-                param_op[r.param_start + p] = (int)ops.size();
-                param_slot[r.param_start + p] = slot + p;
+    auto build_plan = [&](int max_q, Plan& out) {
+        std::vector<DevOp> ops;
+        std::vector<DevMember> members;
+        std::vector<int> param_op(std::max(n_params, 1), -1), param_slot(std::max(n_params, 1), 0);
+        int kern_total = 0, dkern_total = 0, w_total = 0, wmax = 4;
+        int dense_stage = 0;
+        std::vector<int> pend;
+        unsigned pend_support = 0;
+        auto finish_op = [&](DevOp& op) {
+            const int d2 = op.dim * op.dim;
+            if (!(op.type == SQGPU_GENERAL)) {
+                op.kern_off = kern_total;
+                kern_total += d2;
             }
-            slot += r.n_params;
-            members.push_back(m);
-        }
-        b.n_params = slot;
-        fill_fix(b);
-        finish_op(b);
-        pend.clear();
-        pend_support = 0;
-    };
-    for (int i = 0; i < n_gates; ++i) {
-        const DevOp& r = raw[i];
-        const unsigned sup = support_mask(r);
-        const bool fusable = fuse && ((r.dim == 2 && popcount32(r.ctrl_mask) <= 1) || (r.dim == 4 && r.ctrl_mask == 0));
-        if (fusable) {
-            if (!pend.empty() && (popcount32(pend_support | sup) > 2 || (int)pend.size() >= SQ_MAX_MEMBERS)) flush();
-            pend.push_back(i);
-            pend_support |= sup;
-            continue;
+            if (op.dim > 2) {
+                // generic dense path: dim^2 complex; raw 4-5 qubit kernels on the tensor cores: padded real embedding + patterns
+                int need = op.dim * op.dim;
+                if (op.dim > 8) need = (2 * op.dim) * (2 * op.dim + 4) / 2 + op.dim;
+                dense_stage = std::max(dense_stage, need);
+            }
+            if (op.n_params > 0) {
+                op.dkern_off = dkern_total;
+                dkern_total += d2 * op.n_params;
+                op.w_off = w_total;
+                w_total += d2;
+                wmax = std::max(wmax, d2);
+            }
+            ops.push_back(op);
+        };
+        auto flush = [&]() {
+            if (pend.empty()) return;
+            DevOp b;
+            memset(&b, 0, sizeof(b));
+            b.type = SQ_OP_BLOCK;
+            b.kern_off = b.dkern_off = b.w_off = -1;
+            int qs[3] = {0, 0, 0}, nqs = 0;
+            for (int q = 0; q < 30; ++q)
+                if ((pend_support >> q) & 1) qs[nqs++] = q;
+            auto local_bit = [&](int q) { for (int j = 0; j < nqs; ++j) if (qs[j] == q) return j; return 0; };
+            b.dim = 1 << nqs;
+            if (nqs == 1) {
+                b.target = qs[0];
+            } else {
+                b.nq = nqs;
+                for (int j = 0; j < nqs; ++j) b.q[j] = qs[j];
+            }
+            b.member_off = (int)members.size();
+            b.n_members = (int)pend.size();
+            int slot = 0;
+            for (int gi : pend) {
+                const DevOp& r = raw[gi];
+                DevMember m;
+                memset(&m, 0, sizeof(m));
+                m.type = r.type;
+                m.dim = r.dim;
+                m.cl = -1;
+                if (r.dim == 2) {
+                    m.tl = local_bit(r.target);
+                    if (r.ctrl_mask)
+                        for (int q = 0; q < 30; ++q)
+                            if ((r.ctrl_mask >> q) & 1) m.cl = local_bit(q);
+                } else {
+                    m.tl = local_bit(r.q[0]);
+                    m.tl2 = local_bit(r.q[1]);
+                }
+                m.param_start = r.param_start;
+                m.n_params = r.n_params;
+                m.slot0 = slot;
+                m.pool_off = r.pool_off;
+                for (int p = 0; p < r.n_params; ++p) {
+                    param_op[r.param_start + p] = (int)ops.size();
+                    param_slot[r.param_start + p] = slot + p;
+                }
+                slot += r.n_params;
+                members.push_back(m);
+            }
+            b.n_params = slot;
+            fill_fix(b);
+            finish_op(b);
+            pend.clear();
+            pend_support = 0;
+        };
+        for (int i = 0; i < n_gates; ++i) {
+            const DevOp& r = raw[i];
+            const unsigned sup = support_mask(r);
+            const bool fusable = fuse && ((r.dim == 2 && popcount32(r.ctrl_mask) <= 1) || (r.dim == 4 && r.ctrl_mask == 0));
+            if (fusable) {
+                if (!pend.empty() && (popcount32(pend_support | sup) > max_q || (int)pend.size() >= SQ_MAX_MEMBERS)) flush();
+                pend.push_back(i);
+                pend_support |= sup;
+                continue;
+            }
+            flush();
+            DevOp op = r;
+            for (int p = 0; p < op.n_params; ++p) {
+                param_op[op.param_start + p] = (int)ops.size();
+                param_slot[op.param_start + p] = p;
+            }
+            finish_op(op);
         }
         flush();
-        DevOp op = r;
-        for (int p = 0; p < op.n_params; ++p) {
-            param_op[op.param_start + p] = (int)ops.size();
-            param_slot[op.param_start + p] = p;
-        }
-        finish_op(op);
-    }
-    flush();
+        int rc;
+        const size_t np1 = std::max(n_params, 1);
+        if ((rc = out.dOps.ensure(std::max<size_t>(1, ops.size()) * sizeof(DevOp)))) return rc;
+        if ((rc = out.dMembers.ensure(std::max<size_t>(1, members.size()) * sizeof(DevMember)))) return rc;
+        if ((rc = out.dParamOp.ensure(2 * np1 * sizeof(int)))) return rc;
+        if (!ops.empty()) CUDA_TRY(cudaMemcpy(out.dOps.p, ops.data(), ops.size() * sizeof(DevOp), cudaMemcpyHostToDevice));
+        if (!members.empty()) CUDA_TRY(cudaMemcpy(out.dMembers.p, members.data(), members.size() * sizeof(DevMember), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(out.dParamOp.p, param_op.data(), np1 * sizeof(int), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(out.dParamOp.as<int>() + np1, param_slot.data(), np1 * sizeof(int), cudaMemcpyHostToDevice));
+        out.ops.swap(ops);
+        out.members.swap(members);
+        out.param_op.swap(param_op);
+        out.param_slot.swap(param_slot);
+        out.n_ops = (int)out.ops.size();
+        out.kern_total = kern_total;
+        out.dkern_total = dkern_total;
+        out.w_total = w_total;
+        out.wmax = wmax;
+        out.dense_stage = dense_stage;
+        return (int)SQGPU_OK;
+    };
 
     DeviceGuard guard(c->device);
     std::lock_guard<std::mutex> lk(c->mtx);
     int rc;
-    const size_t np1 = std::max(n_params, 1);
-    if ((rc = c->dOps.ensure(std::max<size_t>(1, ops.size()) * sizeof(DevOp)))) return rc;
-    if ((rc = c->dMembers.ensure(std::max<size_t>(1, members.size()) * sizeof(DevMember)))) return rc;
-    if ((rc = c->dParamOp.ensure(2 * np1 * sizeof(int)))) return rc;
     if ((rc = c->dPool.ensure(std::max<size_t>(1, (size_t)pool_len) * sizeof(cplx)))) return rc;
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    if (!ops.empty()) CUDA_TRY(cudaMemcpy(c->dOps.p, ops.data(), ops.size() * sizeof(DevOp), cudaMemcpyHostToDevice));
-    if (!members.empty()) CUDA_TRY(cudaMemcpy(c->dMembers.p, members.data(), members.size() * sizeof(DevMember), cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(c->dParamOp.p, param_op.data(), np1 * sizeof(int), cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(c->dParamOp.as<int>() + np1, param_slot.data(), np1 * sizeof(int), cudaMemcpyHostToDevice));
     if (pool_len > 0) CUDA_TRY(cudaMemcpy(c->dPool.p, matrix_pool, (size_t)pool_len * sizeof(cplx), cudaMemcpyHostToDevice));
-    c->ops.swap(ops);
-    c->members.swap(members);
-    c->param_op.swap(param_op);
-    c->param_slot.swap(param_slot);
-    c->n_ops = (int)c->ops.size();
+    c->circuit_set = false;
+    if ((rc = build_plan(2, c->plan2))) return rc;
+    const char* mq = getenv("SQGPU_MAX_FUSE_QUBITS");
+    const int max_q3 = (mq && mq[0] == '2') ? 2 : 3;
+    if ((rc = build_plan(max_q3, c->plan3))) return rc;
+    c->P = &c->plan2;
     c->n_gates = n_gates;
     c->n_params = n_params;
     c->qbit_num = qbit_num;
-    c->kern_total = kern_total;
-    c->dkern_total = dkern_total;
-    c->w_total = w_total;
-    c->wmax = wmax;
-    c->has_dense = has_dense;
     c->all_unitary = all_unitary;
     c->circuit_set = true;
     return SQGPU_OK;
@@ -1214,6 +1255,7 @@ int sqgpu_apply(sqgpu_handle_t c, const double* params, double* inout, int rows,
     if (!inout || rows <= 0 || cols <= 0 || stride < cols) return fail(SQGPU_ERR_INVALID, "bad matrix arguments");
     DeviceGuard guard(c->device);
     std::lock_guard<std::mutex> lk(c->mtx);
+    c->P = &c->plan2;  // apply paths: two-qubit blocks (the streaming kernels stop there)
     int rc = check_ready(c, false);
     if (rc) return rc;
     if (rows != (1 << c->qbit_num)) return fail(SQGPU_ERR_INVALID, "Wrong input size in Gates_block gate apply: %d rows for %d qubits", rows, c->qbit_num);
@@ -1235,6 +1277,7 @@ int sqgpu_apply_derivative(sqgpu_handle_t c, const double* params, const double*
     if (!in || rows <= 0 || cols <= 0 || stride < cols) return fail(SQGPU_ERR_INVALID, "bad matrix arguments");
     DeviceGuard guard(c->device);
     std::lock_guard<std::mutex> lk(c->mtx);
+    c->P = &c->plan2;  // apply paths: two-qubit blocks (the streaming kernels stop there)
     int rc = check_ready(c, false);
     if (rc) return rc;
     if (rows != (1 << c->qbit_num)) return fail(SQGPU_ERR_INVALID, "Wrong input size in Gates_block gate apply: %d rows for %d qubits", rows, c->qbit_num);
@@ -1255,8 +1298,8 @@ int sqgpu_apply_derivative(sqgpu_handle_t c, const double* params, const double*
         const int np = std::min(slice, P - p0);
         std::vector<int> dop(np), dp(np);
         for (int i = 0; i < np; ++i) {
-            dop[i] = c->param_op[p0 + i];
-            dp[i] = c->param_slot[p0 + i];
+            dop[i] = c->P->param_op[p0 + i];
+            dp[i] = c->P->param_slot[p0 + i];
         }
         if ((rc = apply_program_dev(c, d_in, 0, d_out, (long long)n_elem, np, rows, cols, &dop, &dp, c->stream))) return rc;
         CUDA_TRY(cudaMemcpyAsync(out + 2 * (size_t)p0 * n_elem, d_out, (size_t)np * n_elem * sizeof(cplx), cudaMemcpyDeviceToHost, c->stream));

@@ -4,6 +4,7 @@
 #pragma once
 
 static int vqe_dev(sqgpu_ctx* c, const double* d_params, int batch, bool with_grad, double* d_energy, double* d_grad, cudaStream_t st) {
+    c->P = &c->plan2;
     int rc = check_ready(c, true);
     if (rc) return rc;
     if (batch < 0) return fail(SQGPU_ERR_INVALID, "negative batch");
@@ -11,8 +12,8 @@ static int vqe_dev(sqgpu_ctx* c, const double* d_params, int batch, bool with_gr
     if (c->cols != 1) return fail(SQGPU_ERR_INVALID, "the VQE path needs a state vector (cols = 1), the resident matrix has %d columns", c->cols);
     if (!c->hIndptr.p || c->h_rows != c->rows) return fail(SQGPU_ERR_STATE, "no Hamiltonian of matching size set (call sqgpu_set_hamiltonian_csr)");
     if (!d_energy || (with_grad && !d_grad && c->n_params > 0)) return fail(SQGPU_ERR_INVALID, "NULL buffer");
-    for (int k = 0; k < c->n_ops; ++k) {
-        const DevOp& op = c->ops[k];
+    for (int k = 0; k < c->P->n_ops; ++k) {
+        const DevOp& op = c->P->ops[k];
         const bool ok = op.dim == 2 || (op.dim == 4 && op.nq == 2 && op.ctrl_mask == 0);
         if (with_grad && !ok) return fail(SQGPU_ERR_UNSUPPORTED, "VQE gradient with 3+ qubit dense or multi-controlled gates is not implemented");
     }
@@ -24,7 +25,7 @@ static int vqe_dev(sqgpu_ctx* c, const double* d_params, int batch, bool with_gr
     if ((rc = c->wMat.ensure((size_t)2 * slice * rows * sizeof(cplx)))) return rc;
     if ((rc = c->wTrPart.ensure((size_t)slice * (nblk * 32 + 6) * sizeof(double)))) return rc;
     if (with_grad) {
-        if ((rc = c->wWPart.ensure(std::max<size_t>(1, (size_t)slice * c->w_total) * sizeof(cplx)))) return rc;
+        if ((rc = c->wWPart.ensure(std::max<size_t>(1, (size_t)slice * c->P->w_total) * sizeof(cplx)))) return rc;
         if ((rc = c->wTraces.ensure((size_t)slice * (1 + c->n_params) * 6 * sizeof(double)))) return rc;
     }
     cplx* psi = c->wMat.as<cplx>();
@@ -39,10 +40,10 @@ static int vqe_dev(sqgpu_ctx* c, const double* d_params, int batch, bool with_gr
             c->launches++;
         }
         time_begin(c, "gate1q_stream", st);
-        for (int k = 0; k < c->n_ops; ++k) {
-            const DevOp& op = c->ops[k];
-            const cplx* K = op.kern_off >= 0 ? c->wKtab.as<cplx>() + op.kern_off : c->dPool.as<cplx>() + op.pool_off;
-            const long long kst = op.kern_off >= 0 ? c->kern_total : 0;
+        for (int k = 0; k < c->P->n_ops; ++k) {
+            const DevOp& op = c->P->ops[k];
+            const cplx* K = op.kern_off >= 0 ? c->P->wKtab.as<cplx>() + op.kern_off : c->dPool.as<cplx>() + op.pool_off;
+            const long long kst = op.kern_off >= 0 ? c->P->kern_total : 0;
             if ((rc = launch_stream_gate(c, op, false, psi, rows, nb, rows, 1, 1, K, kst, st))) return rc;
         }
         time_end(c, st);
@@ -56,10 +57,10 @@ static int vqe_dev(sqgpu_ctx* c, const double* d_params, int batch, bool with_gr
             CUDA_TRY(cudaGetLastError());
         }
         if (!with_grad) continue;
-        for (int k = c->n_ops - 1; k >= 0; --k) {
-            const DevOp& op = c->ops[k];
-            const cplx* K = op.kern_off >= 0 ? c->wKtab.as<cplx>() + op.kern_off : c->dPool.as<cplx>() + op.pool_off;
-            const long long kst = op.kern_off >= 0 ? c->kern_total : 0;
+        for (int k = c->P->n_ops - 1; k >= 0; --k) {
+            const DevOp& op = c->P->ops[k];
+            const cplx* K = op.kern_off >= 0 ? c->P->wKtab.as<cplx>() + op.kern_off : c->dPool.as<cplx>() + op.pool_off;
+            const long long kst = op.kern_off >= 0 ? c->P->kern_total : 0;
             StreamGate g = make_stream_gate(op, psi, rows, rows, 1, 1, K, kst);
             const int want_w = op.n_params > 0 ? 1 : 0;
             int blocks, width;
@@ -77,15 +78,15 @@ static int vqe_dev(sqgpu_ctx* c, const double* d_params, int batch, bool with_gr
             c->launches++;
             if (want_w) {
                 sum_partials<<<nb, 32, 0, st>>>(c->wTrPart.as<double>(), blocks, width, 1.0,
-                                                reinterpret_cast<double*>(c->wWPart.as<cplx>() + op.w_off), 2 * c->w_total);
+                                                reinterpret_cast<double*>(c->wWPart.as<cplx>() + op.w_off), 2 * c->P->w_total);
                 c->launches++;
             }
         }
         // dL_p = sum dK_p W  (same contraction as the unitary path), grad_p = 2 Re dL_p  (…Base.cpp:1180-1186)
         double* dummy_tr = c->wTrPart.as<double>() + (size_t)slice * nblk * 32;  // slice * 6 doubles, content unused
-        reduce_partials<<<nb, 128, 0, st>>>(dummy_tr, 1, c->wWPart.as<cplx>(), c->w_total, c->dOps.as<DevOp>(), c->dParamOp.as<int>(),
-                                            c->dParamOp.as<int>() + std::max(c->n_params, 1), c->wDKtab.as<cplx>(), c->dkern_total,
-                                            c->wKtab.as<cplx>(), c->kern_total, c->n_params, 1, c->wTraces.as<double>());
+        reduce_partials<<<nb, 128, 0, st>>>(dummy_tr, 1, c->wWPart.as<cplx>(), c->P->w_total, c->P->dOps.as<DevOp>(), c->P->dParamOp.as<int>(),
+                                            c->P->dParamOp.as<int>() + std::max(c->n_params, 1), c->P->wDKtab.as<cplx>(), c->P->dkern_total,
+                                            c->P->wKtab.as<cplx>(), c->P->kern_total, c->n_params, 1, c->wTraces.as<double>());
         grad_from_traces<<<nb, 128, 0, st>>>(c->wTraces.as<double>(), c->n_params, 2.0, d_grad + (size_t)b0 * c->n_params);
         c->launches += 2;
         CUDA_TRY(cudaGetLastError());
