@@ -32,6 +32,8 @@ namespace sq {
 
 enum { MODE_COST = 0, MODE_GRAD = 1, MODE_APPLY = 2 };
 
+struct OpTab;
+
 struct ExecArgs {
     const cplx* in;          // input matrix (row-major, leading dimension ld_in)
     cplx* out;               // MODE_APPLY: output (may alias in)
@@ -48,6 +50,7 @@ struct ExecArgs {
     const cplx* dktab;       // [ysets][dkern_total]
     int dkern_total;
     const cplx* pool;
+    const struct OpTab* optabs;  // [ysets][n_ops] lookup tables of the DMMA block path (build_optabs)
     int k_shared;            // 1: every blockIdx.y uses kernel-table set 0 (materialised derivative: one parameter set)
     const int* deriv_op;     // MODE_APPLY: per blockIdx.y the op whose derivative kernel is applied (NULL: none)
     const int* deriv_slot;   //             and which of its derivative kernels
@@ -284,9 +287,92 @@ struct BlockGeom {
     }
 };
 
+// Per-op lookup table of the DMMA block path, built in shared memory by all threads while the PREVIOUS op runs
+// (double-buffered): the A fragments of K, K^dagger, K^T in lane order and the lane-constant address slots.
+struct OpTab {
+    double frag[3][8][32];  // [mode][rt * KS + ks][lane]
+    int slot[12][32];       // [0, KS): loads; [KS, KS + 2 RT): W' operands (h * RT + t); then stores (2 * rt + odd)
+};
+
+template <int KQ>
+__device__ __forceinline__ int optab_entries() {
+    constexpr int DIMR = 2 << KQ, RT = DIMR / 8, KS = DIMR / 4;
+    return 3 * RT * KS * 32 + (KS + 4 * RT) * 32;
+}
+
+// which complex element of K entry e of the table needs (-1: none, a slot entry)
+template <int KQ>
+__device__ __forceinline__ int optab_kindex(int e) {
+    constexpr int DIM = 1 << KQ, DIMR = 2 * DIM, RT = DIMR / 8, KS = DIMR / 4, NF = 3 * RT * KS * 32;
+    if (e >= NF) return -1;
+    const int mode = e / (RT * KS * 32), rem = e - mode * (RT * KS * 32), rtks = rem >> 5, lane = rem & 31;
+    const int x = 8 * (rtks / KS) + (lane >> 2), y = 4 * (rtks % KS) + (lane & 3);
+    return (mode == 0) ? (x >> 1) * DIM + (y >> 1) : (y >> 1) * DIM + (x >> 1);
+}
+
+template <int LOG_CT, int KQ>
+__device__ __forceinline__ void optab_store(OpTab* T, int e, cplx kel, const BlockGeom<LOG_CT, KQ>& G) {
+    constexpr int DIM = 1 << KQ, DIMR = 2 * DIM, RT = DIMR / 8, KS = DIMR / 4, NF = 3 * RT * KS * 32;
+    if (e < NF) {
+        const int mode = e / (RT * KS * 32), rem = e - mode * (RT * KS * 32), rtks = rem >> 5, lane = rem & 31;
+        const int x = 8 * (rtks / KS) + (lane >> 2), y = 4 * (rtks % KS) + (lane & 3);
+        const int a = x & 1, b = y & 1;
+        const double im = (mode == 1) ? -kel.y : kel.y;
+        T->frag[mode][rtks][lane] = (a == b) ? kel.x : (a ? im : -im);
+        return;
+    }
+    const int r = e - NF, sidx = r >> 5, lane = r & 31, m = lane >> 2, kk = lane & 3;
+    int v;
+    if (sidx < KS) v = G.slot(m, 4 * sidx + kk);
+    else if (sidx < KS + 2 * RT) {
+        const int j = sidx - KS;
+        v = G.slot(kk + 4 * (j / RT), 8 * (j % RT) + m);
+    } else {
+        const int j = sidx - KS - 2 * RT;
+        v = G.slot(2 * kk + (j & 1), 8 * (j >> 1) + m);
+    }
+    T->slot[sidx][lane] = v;
+}
+
+// One CTA per (parameter set, op): fills the op's lookup table in global memory (ops the DMMA block path cannot take are
+// skipped; their tables are never read).
+template <int LOG_CT>
+__device__ __forceinline__ void fill_optab(OpTab* T, const DevOp& op, const cplx* __restrict__ K) {
+    if (op.dim == 8) {
+        BlockGeom<LOG_CT, 3> G;
+        G.init(op.q[0], op.q[1], op.q[2]);
+        for (int e = threadIdx.x; e < optab_entries<3>(); e += blockDim.x) {
+            const int ki = optab_kindex<3>(e);
+            optab_store<LOG_CT, 3>(T, e, ki >= 0 ? K[ki] : czero(), G);
+        }
+    } else {
+        BlockGeom<LOG_CT, 2> G;
+        G.init(op.q[0], op.q[1], 30);
+        for (int e = threadIdx.x; e < optab_entries<2>(); e += blockDim.x) {
+            const int ki = optab_kindex<2>(e);
+            optab_store<LOG_CT, 2>(T, e, ki >= 0 ? K[ki] : czero(), G);
+        }
+    }
+}
+
+__global__ void build_optabs(const DevOp* __restrict__ ops, int n_ops, const cplx* __restrict__ ktab, int kern_total,
+                             const cplx* __restrict__ pool, int log_ct, OpTab* __restrict__ tabs) {
+    const int b = blockIdx.x / n_ops, k = blockIdx.x - b * n_ops;
+    const DevOp op = ops[k];
+    if (op.ctrl_mask != 0 || (op.dim != 4 && op.dim != 8)) return;
+    const cplx* K = op.kern_off >= 0 ? ktab + (size_t)b * kern_total + op.kern_off : pool + op.pool_off;
+    OpTab* T = tabs + (size_t)b * n_ops + k;
+    switch (log_ct) {
+        case 0: fill_optab<0>(T, op, K); break;
+        case 1: fill_optab<1>(T, op, K); break;
+        case 2: fill_optab<2>(T, op, K); break;
+        default: fill_optab<3>(T, op, K); break;
+    }
+}
+
 // forward: x <- K x for every group of the tile. One warp handles 8 (group, column) items per step.
 template <int LOG_CT, int KQ>
-__device__ __forceinline__ void block_dmma_forward(cplx* sa, const cplx* km, const BlockGeom<LOG_CT, KQ>& G, int rows, int tid,
+__device__ __forceinline__ void block_dmma_forward(cplx* sa, const OpTab* T, const BlockGeom<LOG_CT, KQ>& G, int rows, int tid,
                                                    int nthr) {
     constexpr int DIM = 1 << KQ, DIMR = 2 * DIM, RT = DIMR / 8, KS = DIMR / 4;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5, m = lane >> 2, kk = lane & 3;
@@ -294,14 +380,16 @@ __device__ __forceinline__ void block_dmma_forward(cplx* sa, const cplx* km, con
     double af[RT][KS];
     int sl_ld[KS], sl_st0[RT], sl_st1[RT];
 #pragma unroll
-    for (int ks = 0; ks < KS; ++ks) sl_ld[ks] = G.slot(m, 4 * ks + kk);
+    for (int ks = 0; ks < KS; ++ks) sl_ld[ks] = T->slot[ks][lane];
 #pragma unroll
     for (int rt = 0; rt < RT; ++rt) {
-        sl_st0[rt] = G.slot(2 * kk, 8 * rt + m);
-        sl_st1[rt] = G.slot(2 * kk + 1, 8 * rt + m);
+        sl_st0[rt] = T->slot[KS + 2 * RT + 2 * rt][lane];
+        sl_st1[rt] = T->slot[KS + 2 * RT + 2 * rt + 1][lane];
 #pragma unroll
-        for (int ks = 0; ks < KS; ++ks) af[rt][ks] = block_frag<DIM>(km, 8 * rt + m, 4 * ks + kk, 0);
+        for (int ks = 0; ks < KS; ++ks) af[rt][ks] = T->frag[0][rt * KS + ks][lane];
     }
+    (void)m;
+    (void)kk;
     const int nitems = (rows >> KQ) << LOG_CT;
     for (int b0 = warp * 8; b0 < nitems; b0 += nwarps * 8) {
         const int B0 = G.batch_base(b0);
@@ -328,7 +416,7 @@ __device__ __forceinline__ void block_dmma_forward(cplx* sa, const cplx* km, con
 // backward step of the adjoint sweep: a <- K^dagger p, beta <- K^T beta, W' += beta p^T (all on DMMA); the warp's W'
 // (DIM x DIM complex) is written to wslot after the loop.
 template <int LOG_CT, int KQ>
-__device__ __forceinline__ void block_dmma_backward(cplx* sa, cplx* sb, const cplx* km, const BlockGeom<LOG_CT, KQ>& G, int rows,
+__device__ __forceinline__ void block_dmma_backward(cplx* sa, cplx* sb, const OpTab* T, const BlockGeom<LOG_CT, KQ>& G, int rows,
                                                     bool has_w, cplx* wslot, int tid, int nthr) {
     constexpr int DIM = 1 << KQ, DIMR = 2 * DIM, RT = DIMR / 8, KS = DIMR / 4;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5, m = lane >> 2, kk = lane & 3;
@@ -337,17 +425,17 @@ __device__ __forceinline__ void block_dmma_backward(cplx* sa, cplx* sb, const cp
     double adag[RT][KS], atr[RT][KS];
     int sl_ld[KS], sl_w[2][RT], sl_st0[RT], sl_st1[RT];
 #pragma unroll
-    for (int ks = 0; ks < KS; ++ks) sl_ld[ks] = G.slot(m, 4 * ks + kk);
+    for (int ks = 0; ks < KS; ++ks) sl_ld[ks] = T->slot[ks][lane];
 #pragma unroll
     for (int rt = 0; rt < RT; ++rt) {
-        sl_w[0][rt] = G.slot(kk, 8 * rt + m);
-        sl_w[1][rt] = G.slot(kk + 4, 8 * rt + m);
-        sl_st0[rt] = G.slot(2 * kk, 8 * rt + m);
-        sl_st1[rt] = G.slot(2 * kk + 1, 8 * rt + m);
+        sl_w[0][rt] = T->slot[KS + rt][lane];
+        sl_w[1][rt] = T->slot[KS + RT + rt][lane];
+        sl_st0[rt] = T->slot[KS + 2 * RT + 2 * rt][lane];
+        sl_st1[rt] = T->slot[KS + 2 * RT + 2 * rt + 1][lane];
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) {
-            adag[rt][ks] = block_frag<DIM>(km, 8 * rt + m, 4 * ks + kk, 1);
-            atr[rt][ks] = block_frag<DIM>(km, 8 * rt + m, 4 * ks + kk, 2);
+            adag[rt][ks] = T->frag[1][rt * KS + ks][lane];
+            atr[rt][ks] = T->frag[2][rt * KS + ks][lane];
         }
     }
     double pacc[RT][RT][2];
@@ -440,7 +528,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
     cplx* sb = sa + (size_t)rows * CT;                                   // MODE_GRAD only
     cplx* sk = (MODE == MODE_GRAD) ? sb + (size_t)rows * CT : sb;         // raw dense kernel staging
     cplx* skm = sk + A.dense_stage;                                       // [2][KM_ELEMS] prefetched block kernels
-    cplx* swarp = skm + 2 * KM_ELEMS;                                     // [2][nwarps][wmax]
+    OpTab* stab = reinterpret_cast<OpTab*>(skm + 2 * KM_ELEMS);           // [2] DMMA block lookup tables
+    cplx* swarp = reinterpret_cast<cplx*>(stab + 2);                      // [2][nwarps][wmax]
     cplx* swacc = swarp + ((MODE == MODE_GRAD) ? 2 * nwarps * A.wmax : 0);  // [w_total] if w_in_smem
     double* sred = reinterpret_cast<double*>(swacc + ((MODE == MODE_GRAD && A.w_in_smem) ? A.w_total : 0));  // [nwarps][6]
     SOp* sops = reinterpret_cast<SOp*>(sred + nwarps * 6);               // [n_ops]
@@ -483,6 +572,18 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
         return K[tid];
     };
 
+    // DMMA block table of op k: built per (parameter set, op) by build_optabs; copied global -> shared with cp.async while
+    // the previous op computes (no registers held across the DMMA loops), into stab[k & 1]
+    const OpTab* __restrict__ gtabs = A.optabs + (size_t)kset * A.n_ops;
+    auto tab_prefetch = [&](int k) {
+        if (sops[k].kind != 2) return;
+        const char* src = reinterpret_cast<const char*>(gtabs + k);
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(stab + (k & 1));
+        for (int e = tid; e < (int)(sizeof(OpTab) / 16); e += nthr)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + e * 16), "l"(src + (size_t)e * 16));
+    };
+    auto tab_wait = [&]() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); };
+
     for (int ti = 0; ti < A.tiles_per_cta; ++ti) {
         const int tile = chunk * A.tiles_per_cta + ti;
         if (tile >= A.tiles) break;
@@ -499,6 +600,10 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                 sa[phys_row<LOG_CT>(i) * CT + c] = v;
             }
             if (A.n_ops > 0 && tid < KM_ELEMS) skm[tid] = kernel_elem(0);
+            if (A.n_ops > 0) {
+                tab_prefetch(0);
+                tab_wait();
+            }
         }
         __syncthreads();
 
@@ -508,16 +613,17 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
             cplx next_elem = czero();
             const bool have_next = k + 1 < A.n_ops;
             if (have_next && tid < KM_ELEMS) next_elem = kernel_elem(k + 1);
+            if (have_next) tab_prefetch(k + 1);
             const cplx* __restrict__ km = skm + (k & 1) * KM_ELEMS;
             if (s.kind == 2) {
                 if (s.dim == 8) {
                     BlockGeom<LOG_CT, 3> G;
                     G.init(s.q0, s.q1, s.q2);
-                    block_dmma_forward<LOG_CT, 3>(sa, km, G, rows, tid, nthr);
+                    block_dmma_forward<LOG_CT, 3>(sa, stab + (k & 1), G, rows, tid, nthr);
                 } else {
                     BlockGeom<LOG_CT, 2> G;
                     G.init(s.q0, s.q1, 30);
-                    block_dmma_forward<LOG_CT, 2>(sa, km, G, rows, tid, nthr);
+                    block_dmma_forward<LOG_CT, 2>(sa, stab + (k & 1), G, rows, tid, nthr);
                 }
             } else if (s.kind == 0) {
                 const cplx k00 = km[0], k01 = km[1], k10 = km[2], k11 = km[3];
@@ -622,6 +728,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                 }
             }
             if (have_next && tid < KM_ELEMS) skm[((k + 1) & 1) * KM_ELEMS + tid] = next_elem;
+            tab_wait();
             __syncthreads();
         }
 
@@ -684,6 +791,10 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
             // ---- beta_N = sum_t omega_t * sum_{masks of type t} e_{(j+off)^mask} per column ---------------------
             for (int e = tid; e < rows * CT; e += nthr) sb[e] = czero();
             if (A.n_ops > 0 && tid < KM_ELEMS) skm[((A.n_ops - 1) & 1) * KM_ELEMS + tid] = kernel_elem(A.n_ops - 1);
+            if (A.n_ops > 0) {
+                tab_prefetch(A.n_ops - 1);
+                tab_wait();
+            }
             __syncthreads();
             {
                 const int off = A.trace_offset;
@@ -715,6 +826,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                 cplx next_elem = czero();
                 const bool have_next = k > 0;
                 if (have_next && tid < KM_ELEMS) next_elem = kernel_elem(k - 1);
+                if (have_next) tab_prefetch(k - 1);
                 const bool has_w = s.w_off >= 0;
                 cplx* wslot_c = swarp + (size_t)(buf * nwarps + warp) * A.wmax;
                 double* wslot = reinterpret_cast<double*>(wslot_c);
@@ -724,11 +836,11 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                     if (s.dim == 8) {
                         BlockGeom<LOG_CT, 3> G;
                         G.init(s.q0, s.q1, s.q2);
-                        block_dmma_backward<LOG_CT, 3>(sa, sb, km, G, rows, has_w, wslot_c, tid, nthr);
+                        block_dmma_backward<LOG_CT, 3>(sa, sb, stab + (k & 1), G, rows, has_w, wslot_c, tid, nthr);
                     } else {
                         BlockGeom<LOG_CT, 2> G;
                         G.init(s.q0, s.q1, 30);
-                        block_dmma_backward<LOG_CT, 2>(sa, sb, km, G, rows, has_w, wslot_c, tid, nthr);
+                        block_dmma_backward<LOG_CT, 2>(sa, sb, stab + (k & 1), G, rows, has_w, wslot_c, tid, nthr);
                     }
                 } else if (s.kind == 0) {
                     const cplx k00 = km[0], k01 = km[1], k10 = km[2], k11 = km[3];
@@ -830,6 +942,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                     }
                 }
                 if (have_next && tid < KM_ELEMS) skm[((k - 1) & 1) * KM_ELEMS + tid] = next_elem;
+                tab_wait();
                 __syncthreads();
                 if (has_w) {
                     const int nd = 2 * wdim * wdim;  // doubles

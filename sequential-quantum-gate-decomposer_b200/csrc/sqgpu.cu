@@ -110,7 +110,7 @@ struct Plan {
     std::vector<int> param_op;       // parameter -> op that owns it
     std::vector<int> param_slot;     // parameter -> index of its derivative kernel inside that op
     DevBuf dOps, dMembers, dParamOp;
-    DevBuf wKtab, wDKtab;            // per-parameter-set kernel tables (workspace)
+    DevBuf wKtab, wDKtab, wOpTab;    // per-parameter-set kernel tables and DMMA block lookup tables (workspace)
     int n_ops = 0, kern_total = 0, dkern_total = 0, w_total = 0, wmax = 4;
     int dense_stage = 0;             // complex elements of kernel staging the executor's generic dense path needs
 };
@@ -381,6 +381,7 @@ size_t fused_smem(int mode, int rows, int ct, int threads, int dense_stage, int 
     size_t s = (size_t)rows * ct * sizeof(cplx) * (mode == MODE_GRAD ? 2 : 1);
     s += (size_t)dense_stage * sizeof(cplx);
     s += 2 * KM_ELEMS * sizeof(cplx);        // prefetched block kernels
+    s += 2 * sizeof(OpTab);                  // DMMA block lookup tables (double-buffered)
     s += (size_t)n_ops * sizeof(SOp);        // staged op table
     const int nwarps = threads / 32;
     if (mode == MODE_GRAD) {
@@ -479,6 +480,18 @@ int run_tables(sqgpu_ctx* c, const double* d_params, int batch, bool with_deriv,
     return SQGPU_OK;
 }
 
+// lookup tables of the DMMA block path for `ysets` parameter sets (after run_tables), for tile width 2^log_ct
+int run_optabs(sqgpu_ctx* c, int ysets, int log_ct, cudaStream_t st) {
+    if (c->P->n_ops == 0 || ysets == 0) return SQGPU_OK;
+    int rc;
+    if ((rc = c->P->wOpTab.ensure((size_t)ysets * c->P->n_ops * sizeof(OpTab)))) return rc;
+    build_optabs<<<ysets * c->P->n_ops, 128, 0, st>>>(c->P->dOps.as<DevOp>(), c->P->n_ops, c->P->wKtab.as<cplx>(), c->P->kern_total,
+                                                       c->dPool.as<cplx>(), log_ct, c->P->wOpTab.as<OpTab>());
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return SQGPU_OK;
+}
+
 void fill_common_args(const sqgpu_ctx* c, const FusedPlan& p, ExecArgs& a, int rows, int cols) {
     memset(&a, 0, sizeof(a));
     a.rows = rows;
@@ -495,6 +508,7 @@ void fill_common_args(const sqgpu_ctx* c, const FusedPlan& p, ExecArgs& a, int r
     a.dktab = c->P->wDKtab.as<cplx>();
     a.dkern_total = c->P->dkern_total;
     a.pool = c->dPool.as<cplx>();
+    a.optabs = c->P->wOpTab.as<OpTab>();
     a.dense_stage = c->P->dense_stage;
     a.wmax = c->P->wmax;
     a.w_total = c->P->w_total;
@@ -523,6 +537,7 @@ int run_exec_resident(sqgpu_ctx* c, int batch, bool grad, const cplx* d_omega, d
     FusedPlan p = plan_fused(c, mode, c->rows, c->cols, batch);
     if (!p.ok) return run_exec_streaming(c, batch, grad, d_omega, d_traces, st);  // column too tall for shared memory
     int rc;
+    if ((rc = run_optabs(c, batch, p.log_ct, st))) return rc;
     if ((rc = c->wTrPart.ensure((size_t)batch * p.chunks * 6 * sizeof(double)))) return rc;
     if (grad && (rc = c->wWPart.ensure(std::max<size_t>(1, (size_t)batch * p.chunks * c->P->w_total) * sizeof(cplx)))) return rc;
     ExecArgs a;
@@ -706,6 +721,7 @@ int apply_program_dev(sqgpu_ctx* c, const cplx* d_in, long long in_ystride, cplx
     int rc;
     FusedPlan p = plan_fused(c, MODE_APPLY, rows, cols, ysets);
     if (p.ok) {
+        if ((rc = run_optabs(c, 1, p.log_ct, st))) return rc;
         const int* d_dop = nullptr;
         const int* d_dp = nullptr;
         if (deriv_op) {
@@ -929,7 +945,7 @@ int sqgpu_destroy(sqgpu_handle_t c) {
         DeviceGuard guard(c->device);
         std::lock_guard<std::mutex> lk(c->mtx);
         cudaStreamSynchronize(c->stream);
-        DevBuf* bufs[] = {&c->U, &c->plan2.dOps, &c->plan2.dMembers, &c->plan2.dParamOp, &c->plan2.wKtab, &c->plan2.wDKtab, &c->plan3.dOps, &c->plan3.dMembers, &c->plan3.dParamOp, &c->plan3.wKtab, &c->plan3.wDKtab, &c->dPool, &c->wParams, &c->wTrPart, &c->wWPart,
+        DevBuf* bufs[] = {&c->U, &c->plan2.dOps, &c->plan2.dMembers, &c->plan2.dParamOp, &c->plan2.wKtab, &c->plan2.wDKtab, &c->plan2.wOpTab, &c->plan3.dOps, &c->plan3.dMembers, &c->plan3.dParamOp, &c->plan3.wKtab, &c->plan3.wDKtab, &c->plan3.wOpTab, &c->dPool, &c->wParams, &c->wTrPart, &c->wWPart,
                           &c->wTraces, &c->wOmega, &c->wCost, &c->wGrad, &c->wMat, &c->wDerivIdx, &c->wTraces0,
                           &c->hIndptr, &c->hIndices, &c->hValues};
         for (DevBuf* b : bufs) b->release();
