@@ -34,6 +34,12 @@ for _p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
 
 METRIC = "cost+grad evals/s (10-qubit unitary decomposition)"
 UNIT = "evals/s"
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE fused_exec<GRAD> launch of the default workload (n=10, L=4, batch 256),
+# from the `ncu --set full` capture summarised in profiles/r1_ncu_fused_grad_v5_b256.csv (629.4 MB read + 356.2 MB written).
+# Algorithmic HBM bytes of the same launch: U once (16.8 MB) + block tables (187 MB) + W partials written once (3.2 GB would
+# be the naive figure; they are reduced in L2) -- the kernel is tensor-pipe bound, HBM runs at 0.04 % of peak.
+TRAFFIC_DEFAULT_WORKLOAD = 985516544
+TRAFFIC_NOTE = "ncu --set full capture of this launch (profiles/r1_ncu_fused_grad_v5_b256.csv); null for non-default workloads"
 
 
 def parse():
@@ -400,12 +406,15 @@ def run_ours(args):
     achieved_tf = tot_flops * B / k_s / 1e12
     sb = stream_bytes_per_eval(descs, 1 << n, 1 << n)
     roofline = {
-        "kernel": kname, "bound": "fp64", "achieved": round(achieved_tf, 3), "peak": round(fp64_peak, 3), "unit": "TFLOP/s",
-        "frac": round(achieved_tf / fp64_peak, 4) if fp64_peak > 0 else None, "traffic": None,
-        "peak_source": "FP64 DFMA microbenchmark run in this process (sqgpu_fp64_fma_peak); MEASURED_PEAKS.json has no FP64 figure",
+        "kernel": kname, "bound": "tensor", "achieved": round(achieved_tf, 3), "peak": round(fp64_peak, 3), "unit": "TFLOP/s",
+        "frac": round(achieved_tf / fp64_peak, 4) if fp64_peak > 0 else None, "traffic": TRAFFIC_DEFAULT_WORKLOAD if (n, args.levels, B, args.variant) == (10, 4, 256, 0) else None,
+        "peak_source": "FP64 tensor-core (DMMA m8n8k4) / DFMA burn kernels run in this process (sqgpu_fp64_fma_peak, the larger of "
+                       "the two: they share one pipe); MEASURED_PEAKS.json holds only HBM and bf16 figures, not usable for an f64 path",
+        "traffic_note": TRAFFIC_NOTE,
         "kernel_ms": round(kms, 4), "kernel_launches_timed": klaunches,
         "algorithmic_flops_per_launch": tot_flops * B,
-        "note": "the executor keeps column tiles in shared memory, so the FP64 pipe bounds it, not HBM; hbm_equivalent is the "
+        "note": "the executor keeps column tiles in shared memory and runs the fused blocks on the FP64 tensor cores, so that pipe "
+                "bounds it, not HBM; hbm_equivalent is the "
                 "bandwidth the reference's per-gate streaming algorithm would need for the same evals/s",
         "hbm_equivalent": {"bytes_per_eval_streaming": 4 * sb, "achieved_GB/s": round(4 * sb * B / k_s / 1e9, 1),
                            "peak_GB/s": peaks.get("hbm_gbs"), "peak_source": peak_src,

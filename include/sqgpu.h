@@ -236,8 +236,9 @@ int sqgpu_launch_count(sqgpu_handle_t h, int64_t* count);
  * batched evaluation -- bench.py's roofline numerator. name_len includes the terminating NUL. */
 int sqgpu_last_kernel_time(sqgpu_handle_t h, char* name, int name_len, double* ms, int* launches);
 
-/* measured FP64 FMA throughput of the handle's device (TFLOP/s, 2 flops per DFMA): the roofline denominator of the
- * shared-memory executor, which is bound by the FP64 pipe and not by HBM (MEASURED_PEAKS.json has no FP64 figure). */
+/* measured FP64 throughput of the handle's device in TFLOP/s: the larger of a DFMA and a DMMA (mma.sync m8n8k4.f64, the
+ * instruction the executor's block path issues) burn kernel -- both run on the same pipe. Roofline denominator of the
+ * shared-memory executor, which is bound by the FP64 tensor pipe and not by HBM (MEASURED_PEAKS.json has no FP64 figure). */
 int sqgpu_fp64_fma_peak(sqgpu_handle_t h, double* tflops);
 
 #ifdef __cplusplus
