@@ -69,39 +69,30 @@ struct ExecArgs {
 
 static const int FUSED_THREADS = 512;
 
-// ---- shared-memory swizzle -------------------------------------------------------------------------------------
-// rows per 128 B wavefront: 8 / ct. The low log2(8/ct) bits of the physical row select the 16 B bank group set; they
-// are XORed with images of the higher row bits so that rows differing in any of the lowest free bits do not collide.
-template <int LOG_CT>
-__device__ __forceinline__ int phys_row(int i) {
-    if (LOG_CT >= 3) return i;
-    if (LOG_CT == 2) return i ^ (__popc(i >> 1) & 1);
-    if (LOG_CT == 1) {
-        // image of row bit b: (1, 2, 3)[b % 3]; bits 0 and 1 map to themselves
-        const unsigned m_lo = 0x6DB6DB6Cu;  // bits b >= 2 with b % 3 in {2, 0}
-        const unsigned m_hi = 0x36DB6DB4u;  // bits b >= 2 with b % 3 in {2, 1}
-        return i ^ ((__popc((unsigned)i & m_lo) & 1) | ((__popc((unsigned)i & m_hi) & 1) << 1));
-    }
-    return i ^ (((i >> 3) & 1) * 7);
+// ---- shared-memory layout ----------------------------------------------------------------------------------------
+// Element (row r, tile column c) lives at complex index elem(r, c), a GF(2)-linear bijection of the (row, column) bits: the
+// three address bits that select the 16 B bank group (address mod 8) are XORed with images of the row bits. Row bit k has
+// the image (1, 2, 3)[k % 3] in the two bank bits above tile-column bit 0 (for CT = 1: a 3-bit image), so rows that differ
+// in two block qubits of different residue, and columns that differ in bit 0, fall into 8 different bank groups: the
+// quarter-warp of a 128-bit fragment access of the DMMA block path is conflict-free. Linearity makes every address of that
+// path  B0(batch) ^ slot(lane).
+__host__ __device__ constexpr unsigned bits_mod(int m, unsigned sel, int from) {
+    unsigned r = 0;
+    for (int b = from; b < 31; ++b)
+        if ((sel >> ((b - from) % m)) & 1u) r |= 1u << b;
+    return r;
 }
-
-// shared-memory element indices of the 4 rows of a two-qubit group: base | {0, b0, b1, b0|b1}. For CT = 4 the swizzle
-// parity of (base | x) splits into parity(base) ^ parity(x), so one POPC per group suffices.
 template <int LOG_CT>
-__device__ __forceinline__ void group4_addr(int base, int b0, int b1, int c, int px0, int px1, int& e0, int& e1, int& e2, int& e3) {
-    constexpr int CT = 1 << LOG_CT;
-    if (LOG_CT == 2) {
-        const int pb = __popc(base >> 1) & 1;
-        e0 = ((base) ^ pb) * CT + c;
-        e1 = ((base | b0) ^ (pb ^ px0)) * CT + c;
-        e2 = ((base | b1) ^ (pb ^ px1)) * CT + c;
-        e3 = ((base | b0 | b1) ^ (pb ^ px0 ^ px1)) * CT + c;
-    } else {
-        e0 = phys_row<LOG_CT>(base) * CT + c;
-        e1 = phys_row<LOG_CT>(base | b0) * CT + c;
-        e2 = phys_row<LOG_CT>(base | b1) * CT + c;
-        e3 = phys_row<LOG_CT>(base | b0 | b1) * CT + c;
-    }
+__device__ __forceinline__ int elem(int r, int c) {
+    constexpr unsigned MA = bits_mod(3, 0b101u, 0);  // row bits k with k % 3 in {0, 2}: image bit 0
+    constexpr unsigned MB = bits_mod(3, 0b110u, 0);  // row bits k with k % 3 in {1, 2}: image bit 1
+    const int pa = __popc((unsigned)r & MA) & 1, pb = __popc((unsigned)r & MB) & 1;
+    if (LOG_CT >= 3) return ((r << LOG_CT) | c) ^ ((pa | (pb << 1)) << 1);
+    if (LOG_CT == 2) return ((((r & ~1) | pa) << 2) | c) ^ (pb << 1);
+    if (LOG_CT == 1) return ((((r & ~3) | pa | (pb << 1))) << 1) | c;
+    // CT = 1: bank bits are row bits 0..2; row bit k >= 3 has image (7, 3, 5, 6)[(k - 3) % 4]
+    constexpr unsigned M0 = bits_mod(4, 0b0111u, 3), M1 = bits_mod(4, 0b1011u, 3), M2 = bits_mod(4, 0b1101u, 3);
+    return r ^ ((__popc((unsigned)r & M0) & 1) | ((__popc((unsigned)r & M1) & 1) << 1) | ((__popc((unsigned)r & M2) & 1) << 2));
 }
 
 // reduce 8 per-lane doubles over the warp; lanes with (lane & 3) == 0 end up holding the total of value
@@ -202,7 +193,7 @@ __device__ __forceinline__ void dense_dmma_forward(cplx* sa, const double* skr, 
             for (int ks = 0; ks < KS; ++ks) {
                 const int comp = 4 * ks + kk;
                 const int row = base | spat[comp >> 1];
-                bfrag[ks] = sad[(phys_row<LOG_CT>(row) * CT + c) * 2 + (comp & 1)];
+                bfrag[ks] = sad[(elem<LOG_CT>(row, c)) * 2 + (comp & 1)];
             }
         }
         double d[RT][2];
@@ -224,59 +215,50 @@ __device__ __forceinline__ void dense_dmma_forward(cplx* sa, const double* skr, 
         for (int rt = 0; rt < RT; ++rt) {
             const int comp = 8 * rt + m;
             const int pat = spat[comp >> 1];
-            sad[(phys_row<LOG_CT>(base0 | pat) * CT + c0) * 2 + (comp & 1)] = d[rt][0];
-            sad[(phys_row<LOG_CT>(base1 | pat) * CT + c1) * 2 + (comp & 1)] = d[rt][1];
+            sad[(elem<LOG_CT>(base0 | pat, c0)) * 2 + (comp & 1)] = d[rt][0];
+            sad[(elem<LOG_CT>(base1 | pat, c1)) * 2 + (comp & 1)] = d[rt][1];
         }
         __syncwarp();
     }
 }
 
 // ---- fused 2-/3-qubit blocks on the FP64 tensor cores -------------------------------------------------------------
-// The block kernel K (4 x 4 or 8 x 8 complex) sits in shared memory (km); every lane derives the DMMA A-fragments of the
-// real embeddings it needs: mode 0: K, 1: K^dagger, 2: K^T.
-template <int DIM>
-__device__ __forceinline__ double block_frag(const cplx* km, int x, int y, int mode) {
-    const int r = x >> 1, a = x & 1, c = y >> 1, b = y & 1;
-    const cplx e = (mode == 0) ? km[r * DIM + c] : km[c * DIM + r];
-    const double im = (mode == 1) ? -e.y : e.y;
-    return (a == b) ? e.x : (a ? im : -im);
-}
-
-// Addressing of the DMMA block path. phys_row() is GF(2)-linear (x ^ L(x >> s) with L linear), and so are the bit
-// insertions that expand a group index into a row index; hence the shared-memory address of (item, component) splits into
-//     address = B0(batch) ^ slot(lane, access)
-// where B0 is computed once per 8-item batch and `slot` once per op and lane. Units: doubles (2 per complex element).
+// D[8 items x 8 out comps] += X[8 items x 4 in comps] * KrealT[4 in comps x 8 out comps] with mma.sync.m8n8k4.f64: the DATA
+// is the A operand (lane l supplies item l >> 2, component slot l & 3) and the kernel the B operand. Lane (i, j) loads the
+// complex amplitudes dep(j, u) of item i (one 128-bit load per u; .x feeds k-step 2u, .y k-step 2u + 1) and receives in its
+// D fragment exactly the same amplitudes of the result (out comps 2j, 2j + 1 of n-tile u): loads and stores of a lane hit
+// the same addresses, 16 B wide, and no lane touches another lane's elements.
 template <int LOG_CT, int KQ>
 struct BlockGeom {
     static constexpr int CT = 1 << LOG_CT;
     static constexpr int LOGG = 3 - LOG_CT;  // log2(groups per 8-item batch)
     int q[3];   // block qubits, ascending (unused = 30)
-    int Pq[3];  // address image of row bit q[j]
+    int Pq[3];  // address image (complex units) of row bit q[j]
     int F[3];   // address image of the j-th lowest row bit that is NOT a block qubit (group-offset bits inside a batch)
 
     __device__ __forceinline__ void init(int q0, int q1, int q2) {
         q[0] = q0; q[1] = q1; q[2] = q2;
 #pragma unroll
-        for (int j = 0; j < 3; ++j) Pq[j] = (j < KQ) ? (phys_row<LOG_CT>(1 << q[j]) << (LOG_CT + 1)) : 0;
+        for (int j = 0; j < 3; ++j) Pq[j] = (j < KQ) ? elem<LOG_CT>(1 << q[j], 0) : 0;
         int f = 0;
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
             while (f == q0 || f == q1 || f == q2) ++f;
-            F[j] = phys_row<LOG_CT>(1 << f) << (LOG_CT + 1);
+            F[j] = elem<LOG_CT>(1 << f, 0);
             ++f;
         }
     }
-    // B0 of the batch starting at item b0 (b0 % 8 == 0)
+    // B0 (complex units) of the batch starting at item b0 (b0 % 8 == 0)
     __device__ __forceinline__ int batch_base(int b0) const {
         int base = b0 >> LOG_CT;
 #pragma unroll
         for (int j = 0; j < KQ; ++j) base = insert_zero(base, q[j]);
-        return phys_row<LOG_CT>(base) << (LOG_CT + 1);
+        return elem<LOG_CT>(base, 0);
     }
-    // lane-constant part of the address of real component `comp` (= 2 * local amplitude + re/im) of batch item `item` (0..7)
-    __device__ __forceinline__ int slot(int item, int comp) const {
-        const int go = item >> LOG_CT, c = item & (CT - 1), amp = comp >> 1;
-        int a = c * 2 + (comp & 1);
+    // lane-constant part of the address (complex units) of local amplitude `amp` of batch item `item` (0..7)
+    __device__ __forceinline__ int slot(int item, int amp) const {
+        const int go = item >> LOG_CT;
+        int a = item & (CT - 1);
 #pragma unroll
         for (int j = 0; j < 3; ++j)
             if (j < LOGG && ((go >> j) & 1)) a ^= F[j];
@@ -287,74 +269,86 @@ struct BlockGeom {
     }
 };
 
-// Per-op lookup table of the DMMA block path, built in shared memory by all threads while the PREVIOUS op runs
-// (double-buffered): the A fragments of K, K^dagger, K^T in lane order and the lane-constant address slots.
+// Per-(parameter set, op) lookup table of the DMMA block path, written by build_optabs and prefetched into shared memory
+// with cp.async while the previous op runs (double-buffered).
 struct OpTab {
-    double frag[3][8][32];  // [mode][rt * KS + ks][lane]
-    int slot[12][32];       // [0, KS): loads; [KS, KS + 2 RT): W' operands (h * RT + t); then stores (2 * rt + odd)
+    double frag[3][8][32];  // [mode: K, K^dagger, K^T][t * KS + s][lane]: kernel (B operand) fragments
+    int slot[4][32];        // [u]: load/store slot of amplitude dep(j, u); [2 + h]: W' operand slot of item half h
+    int widx[32];           // 3-qubit blocks: positions of the lane's two W' outputs, idx0 | idx1 << 8
 };
 
-template <int KQ>
-__device__ __forceinline__ int optab_entries() {
-    constexpr int DIMR = 2 << KQ, RT = DIMR / 8, KS = DIMR / 4;
-    return 3 * RT * KS * 32 + (KS + 4 * RT) * 32;
+// local amplitude index from the lane's amplitude slot j (2 bits) and the k-step pair u: block-qubit position ju carries u
+__device__ __forceinline__ int dep3(int j, int u, int ju) {
+    const int ja = (ju == 0) ? 1 : 0, jb = (ju == 2) ? 1 : 2;
+    return ((j & 1) << ja) | (((j >> 1) & 1) << jb) | (u << ju);
+}
+// W' row/column enumeration: bit 0 of rho sits on block-qubit position pa, the others ascend
+__device__ __forceinline__ int permw3(int rho, int pa) {
+    const int pb = (pa == 0) ? 1 : 0, pc = (pa == 2) ? 1 : 2;
+    return ((rho & 1) << pa) | (((rho >> 1) & 1) << pb) | (((rho >> 2) & 1) << pc);
 }
 
-// which complex element of K entry e of the table needs (-1: none, a slot entry)
-template <int KQ>
-__device__ __forceinline__ int optab_kindex(int e) {
-    constexpr int DIM = 1 << KQ, DIMR = 2 * DIM, RT = DIMR / 8, KS = DIMR / 4, NF = 3 * RT * KS * 32;
-    if (e >= NF) return -1;
-    const int mode = e / (RT * KS * 32), rem = e - mode * (RT * KS * 32), rtks = rem >> 5, lane = rem & 31;
-    const int x = 8 * (rtks / KS) + (lane >> 2), y = 4 * (rtks % KS) + (lane & 3);
-    return (mode == 0) ? (x >> 1) * DIM + (y >> 1) : (y >> 1) * DIM + (x >> 1);
+__device__ __forceinline__ double kreal_entry(const cplx* __restrict__ K, int dim, int mode, int amp_out, int a, int amp_in, int b) {
+    const cplx e = (mode == 0) ? K[amp_out * dim + amp_in] : K[amp_in * dim + amp_out];
+    const double im = (mode == 1) ? -e.y : e.y;
+    return (a == b) ? e.x : (a ? im : -im);
 }
 
-template <int LOG_CT, int KQ>
-__device__ __forceinline__ void optab_store(OpTab* T, int e, cplx kel, const BlockGeom<LOG_CT, KQ>& G) {
-    constexpr int DIM = 1 << KQ, DIMR = 2 * DIM, RT = DIMR / 8, KS = DIMR / 4, NF = 3 * RT * KS * 32;
-    if (e < NF) {
-        const int mode = e / (RT * KS * 32), rem = e - mode * (RT * KS * 32), rtks = rem >> 5, lane = rem & 31;
-        const int x = 8 * (rtks / KS) + (lane >> 2), y = 4 * (rtks % KS) + (lane & 3);
-        const int a = x & 1, b = y & 1;
-        const double im = (mode == 1) ? -kel.y : kel.y;
-        T->frag[mode][rtks][lane] = (a == b) ? kel.x : (a ? im : -im);
-        return;
-    }
-    const int r = e - NF, sidx = r >> 5, lane = r & 31, m = lane >> 2, kk = lane & 3;
-    int v;
-    if (sidx < KS) v = G.slot(m, 4 * sidx + kk);
-    else if (sidx < KS + 2 * RT) {
-        const int j = sidx - KS;
-        v = G.slot(kk + 4 * (j / RT), 8 * (j % RT) + m);
-    } else {
-        const int j = sidx - KS - 2 * RT;
-        v = G.slot(2 * kk + (j & 1), 8 * (j >> 1) + m);
-    }
-    T->slot[sidx][lane] = v;
-}
-
-// One CTA per (parameter set, op): fills the op's lookup table in global memory (ops the DMMA block path cannot take are
-// skipped; their tables are never read).
 template <int LOG_CT>
 __device__ __forceinline__ void fill_optab(OpTab* T, const DevOp& op, const cplx* __restrict__ K) {
+    __shared__ int s_choice[2];
+    const int tid = threadIdx.x, nthr = blockDim.x;
     if (op.dim == 8) {
         BlockGeom<LOG_CT, 3> G;
         G.init(op.q[0], op.q[1], op.q[2]);
-        for (int e = threadIdx.x; e < optab_entries<3>(); e += blockDim.x) {
-            const int ki = optab_kindex<3>(e);
-            optab_store<LOG_CT, 3>(T, e, ki >= 0 ? K[ki] : czero(), G);
+        if (tid == 0) {
+            // pick the amplitude-to-lane assignments whose quarter-warp (lanes 0..7) hits the most bank groups
+            int best_ju = 0, best_pa = 0, best_m = -1, best_w = -1;
+            for (int cand = 0; cand < 3; ++cand) {
+                unsigned seen_m = 0, seen_w = 0;
+                for (int l = 0; l < 8; ++l) {
+                    seen_m |= 1u << (G.slot(l >> 2, dep3(l & 3, 0, cand)) & 7);
+                    seen_w |= 1u << (G.slot(l & 3, permw3(l >> 2, cand)) & 7);
+                }
+                if (__popc(seen_m) > best_m) { best_m = __popc(seen_m); best_ju = cand; }
+                if (__popc(seen_w) > best_w) { best_w = __popc(seen_w); best_pa = cand; }
+            }
+            s_choice[0] = best_ju;
+            s_choice[1] = best_pa;
+        }
+        __syncthreads();
+        const int ju = s_choice[0], pa = s_choice[1];
+        for (int e = tid; e < 3 * 8 * 32; e += nthr) {
+            const int mode = e >> 8, ts = (e >> 5) & 7, lane = e & 31, t = ts >> 2, s = ts & 3;
+            const int n = lane >> 2, k = lane & 3;
+            T->frag[mode][ts][lane] = kreal_entry(K, 8, mode, dep3(n >> 1, t, ju), n & 1, dep3(k, s >> 1, ju), s & 1);
+        }
+        for (int e = tid; e < 4 * 32; e += nthr) {
+            const int sidx = e >> 5, lane = e & 31;
+            T->slot[sidx][lane] = (sidx < 2) ? G.slot(lane >> 2, dep3(lane & 3, sidx, ju))
+                                             : G.slot((lane & 3) + 4 * (sidx - 2), permw3(lane >> 2, pa));
+        }
+        for (int lane = tid; lane < 32; lane += nthr) {
+            const int r = permw3(lane >> 2, pa), c0 = permw3(2 * (lane & 3), pa), c1 = permw3(2 * (lane & 3) + 1, pa);
+            T->widx[lane] = (r * 8 + c0) | ((r * 8 + c1) << 8);
         }
     } else {
         BlockGeom<LOG_CT, 2> G;
         G.init(op.q[0], op.q[1], 30);
-        for (int e = threadIdx.x; e < optab_entries<2>(); e += blockDim.x) {
-            const int ki = optab_kindex<2>(e);
-            optab_store<LOG_CT, 2>(T, e, ki >= 0 ? K[ki] : czero(), G);
+        for (int e = tid; e < 3 * 2 * 32; e += nthr) {
+            const int mode = e >> 6, s = (e >> 5) & 1, lane = e & 31;
+            const int n = lane >> 2, k = lane & 3;
+            T->frag[mode][s][lane] = kreal_entry(K, 4, mode, n >> 1, n & 1, k, s);
+        }
+        for (int e = tid; e < 4 * 32; e += nthr) {
+            const int sidx = e >> 5, lane = e & 31, m = lane >> 2, kk = lane & 3;
+            // W' operands of 2-qubit blocks are single doubles: component m of item kk + 4h (double units)
+            T->slot[sidx][lane] = (sidx < 2) ? G.slot(m, kk) : 2 * G.slot(kk + 4 * (sidx - 2), m >> 1) + (m & 1);
         }
     }
 }
 
+// One CTA per (parameter set, op); ops the DMMA block path cannot take are skipped (their tables are never read).
 __global__ void build_optabs(const DevOp* __restrict__ ops, int n_ops, const cplx* __restrict__ ktab, int kern_total,
                              const cplx* __restrict__ pool, int log_ct, OpTab* __restrict__ tabs) {
     const int b = blockIdx.x / n_ops, k = blockIdx.x - b * n_ops;
@@ -374,130 +368,123 @@ __global__ void build_optabs(const DevOp* __restrict__ ops, int n_ops, const cpl
 template <int LOG_CT, int KQ>
 __device__ __forceinline__ void block_dmma_forward(cplx* sa, const OpTab* T, const BlockGeom<LOG_CT, KQ>& G, int rows, int tid,
                                                    int nthr) {
-    constexpr int DIM = 1 << KQ, DIMR = 2 * DIM, RT = DIMR / 8, KS = DIMR / 4;
-    const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5, m = lane >> 2, kk = lane & 3;
-    double* sad = reinterpret_cast<double*>(sa);
-    double af[RT][KS];
-    int sl_ld[KS], sl_st0[RT], sl_st1[RT];
+    constexpr int NT = (KQ == 3) ? 2 : 1, KS = 2 * NT;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
+    double kf[NT][KS];
+    int sl[NT];
 #pragma unroll
-    for (int ks = 0; ks < KS; ++ks) sl_ld[ks] = T->slot[ks][lane];
+    for (int t = 0; t < NT; ++t) {
+        sl[t] = T->slot[t][lane];
 #pragma unroll
-    for (int rt = 0; rt < RT; ++rt) {
-        sl_st0[rt] = T->slot[KS + 2 * RT + 2 * rt][lane];
-        sl_st1[rt] = T->slot[KS + 2 * RT + 2 * rt + 1][lane];
-#pragma unroll
-        for (int ks = 0; ks < KS; ++ks) af[rt][ks] = T->frag[0][rt * KS + ks][lane];
+        for (int s = 0; s < KS; ++s) kf[t][s] = T->frag[0][t * KS + s][lane];
     }
-    (void)m;
-    (void)kk;
     const int nitems = (rows >> KQ) << LOG_CT;
     for (int b0 = warp * 8; b0 < nitems; b0 += nwarps * 8) {
         const int B0 = G.batch_base(b0);
-        double xf[KS];
+        cplx x[NT], d[NT];
 #pragma unroll
-        for (int ks = 0; ks < KS; ++ks) xf[ks] = sad[B0 ^ sl_ld[ks]];
-        double d[RT][2];
-#pragma unroll
-        for (int rt = 0; rt < RT; ++rt) {
-            d[rt][0] = d[rt][1] = 0.0;
-#pragma unroll
-            for (int ks = 0; ks < KS; ++ks) dmma_m8n8k4(d[rt][0], d[rt][1], af[rt][ks], xf[ks]);
+        for (int u = 0; u < NT; ++u) {
+            x[u] = sa[B0 ^ sl[u]];
+            d[u] = czero();
         }
-        __syncwarp();
 #pragma unroll
-        for (int rt = 0; rt < RT; ++rt) {
-            sad[B0 ^ sl_st0[rt]] = d[rt][0];
-            sad[B0 ^ sl_st1[rt]] = d[rt][1];
-        }
-        __syncwarp();
+        for (int u = 0; u < NT; ++u)
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                dmma_m8n8k4(d[t].x, d[t].y, x[u].x, kf[t][2 * u]);
+                dmma_m8n8k4(d[t].x, d[t].y, x[u].y, kf[t][2 * u + 1]);
+            }
+#pragma unroll
+        for (int t = 0; t < NT; ++t) sa[B0 ^ sl[t]] = d[t];
     }
 }
 
-// backward step of the adjoint sweep: a <- K^dagger p, beta <- K^T beta, W' += beta p^T (all on DMMA); the warp's W'
-// (DIM x DIM complex) is written to wslot after the loop.
+// backward step of the adjoint sweep: W' += beta p^T (outer product over items), a <- K^dagger p, beta <- K^T beta, all on
+// DMMA; the warp's W' (DIM x DIM complex) is written to wslot after the loop.
 template <int LOG_CT, int KQ>
 __device__ __forceinline__ void block_dmma_backward(cplx* sa, cplx* sb, const OpTab* T, const BlockGeom<LOG_CT, KQ>& G, int rows,
                                                     bool has_w, cplx* wslot, int tid, int nthr) {
-    constexpr int DIM = 1 << KQ, DIMR = 2 * DIM, RT = DIMR / 8, KS = DIMR / 4;
-    const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5, m = lane >> 2, kk = lane & 3;
-    double* sad = reinterpret_cast<double*>(sa);
-    double* sbd = reinterpret_cast<double*>(sb);
-    double adag[RT][KS], atr[RT][KS];
-    int sl_ld[KS], sl_w[2][RT], sl_st0[RT], sl_st1[RT];
+    constexpr int DIM = 1 << KQ, NT = (KQ == 3) ? 2 : 1, KS = 2 * NT;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
+    double kd[NT][KS], kt[NT][KS];
+    int sl[NT], slw[2];
 #pragma unroll
-    for (int ks = 0; ks < KS; ++ks) sl_ld[ks] = T->slot[ks][lane];
+    for (int t = 0; t < NT; ++t) {
+        sl[t] = T->slot[t][lane];
 #pragma unroll
-    for (int rt = 0; rt < RT; ++rt) {
-        sl_w[0][rt] = T->slot[KS + rt][lane];
-        sl_w[1][rt] = T->slot[KS + RT + rt][lane];
-        sl_st0[rt] = T->slot[KS + 2 * RT + 2 * rt][lane];
-        sl_st1[rt] = T->slot[KS + 2 * RT + 2 * rt + 1][lane];
-#pragma unroll
-        for (int ks = 0; ks < KS; ++ks) {
-            adag[rt][ks] = T->frag[1][rt * KS + ks][lane];
-            atr[rt][ks] = T->frag[2][rt * KS + ks][lane];
+        for (int s = 0; s < KS; ++s) {
+            kd[t][s] = T->frag[1][t * KS + s][lane];
+            kt[t][s] = T->frag[2][t * KS + s][lane];
         }
     }
-    double pacc[RT][RT][2];
+    slw[0] = T->slot[2][lane];
+    slw[1] = T->slot[3][lane];
+    double pacc[NT][NT][2];
 #pragma unroll
-    for (int tr = 0; tr < RT; ++tr)
+    for (int a = 0; a < NT; ++a)
 #pragma unroll
-        for (int tc = 0; tc < RT; ++tc) pacc[tr][tc][0] = pacc[tr][tc][1] = 0.0;
+        for (int b = 0; b < NT; ++b) pacc[a][b][0] = pacc[a][b][1] = 0.0;
     const int nitems = (rows >> KQ) << LOG_CT;
     for (int b0 = warp * 8; b0 < nitems; b0 += nwarps * 8) {
         const int B0 = G.batch_base(b0);
-        double pf[KS], bf[KS];
+        cplx p[NT], be[NT], da[NT], db[NT];
 #pragma unroll
-        for (int ks = 0; ks < KS; ++ks) {
-            pf[ks] = sad[B0 ^ sl_ld[ks]];
-            bf[ks] = sbd[B0 ^ sl_ld[ks]];
+        for (int u = 0; u < NT; ++u) {
+            p[u] = sa[B0 ^ sl[u]];
+            be[u] = sb[B0 ^ sl[u]];
+            da[u] = czero();
+            db[u] = czero();
         }
-        if (has_w) {  // W' operands: component 8t + m of items kk and kk + 4
+        if (has_w) {
+            if (KQ == 3) {
+                // lane (rho, it): amplitude permw(rho) of item it + 4h of beta (A operand, rows = rho, tile = re/im) and of p
+                // (B operand, columns = rho)
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                double pw[RT], bw[RT];
-#pragma unroll
-                for (int t = 0; t < RT; ++t) {
-                    pw[t] = sad[B0 ^ sl_w[h][t]];
-                    bw[t] = sbd[B0 ^ sl_w[h][t]];
+                for (int h = 0; h < 2; ++h) {
+                    const cplx bw = sb[B0 ^ slw[h]], pw = sa[B0 ^ slw[h]];
+                    dmma_m8n8k4(pacc[0][0][0], pacc[0][0][1], bw.x, pw.x);
+                    dmma_m8n8k4(pacc[0][NT - 1][0], pacc[0][NT - 1][1], bw.x, pw.y);
+                    dmma_m8n8k4(pacc[NT - 1][0][0], pacc[NT - 1][0][1], bw.y, pw.x);
+                    dmma_m8n8k4(pacc[NT - 1][NT - 1][0], pacc[NT - 1][NT - 1][1], bw.y, pw.y);
                 }
+            } else {
+                const double* sad = reinterpret_cast<const double*>(sa);
+                const double* sbd = reinterpret_cast<const double*>(sb);
 #pragma unroll
-                for (int tr = 0; tr < RT; ++tr)
-#pragma unroll
-                    for (int tc = 0; tc < RT; ++tc) dmma_m8n8k4(pacc[tr][tc][0], pacc[tr][tc][1], bw[tr], pw[tc]);
+                for (int h = 0; h < 2; ++h) dmma_m8n8k4(pacc[0][0][0], pacc[0][0][1], sbd[(2 * B0) ^ slw[h]], sad[(2 * B0) ^ slw[h]]);
             }
         }
-        double da[RT][2], db[RT][2];
 #pragma unroll
-        for (int rt = 0; rt < RT; ++rt) {
-            da[rt][0] = da[rt][1] = db[rt][0] = db[rt][1] = 0.0;
+        for (int u = 0; u < NT; ++u)
 #pragma unroll
-            for (int ks = 0; ks < KS; ++ks) {
-                dmma_m8n8k4(da[rt][0], da[rt][1], adag[rt][ks], pf[ks]);
-                dmma_m8n8k4(db[rt][0], db[rt][1], atr[rt][ks], bf[ks]);
+            for (int t = 0; t < NT; ++t) {
+                dmma_m8n8k4(da[t].x, da[t].y, p[u].x, kd[t][2 * u]);
+                dmma_m8n8k4(db[t].x, db[t].y, be[u].x, kt[t][2 * u]);
+                dmma_m8n8k4(da[t].x, da[t].y, p[u].y, kd[t][2 * u + 1]);
+                dmma_m8n8k4(db[t].x, db[t].y, be[u].y, kt[t][2 * u + 1]);
             }
-        }
-        __syncwarp();  // all reads of this batch are done
+        if (has_w) __syncwarp();  // the W' operands (other lanes' elements) are read before anybody overwrites them
 #pragma unroll
-        for (int rt = 0; rt < RT; ++rt) {
-            sad[B0 ^ sl_st0[rt]] = da[rt][0];
-            sad[B0 ^ sl_st1[rt]] = da[rt][1];
-            sbd[B0 ^ sl_st0[rt]] = db[rt][0];
-            sbd[B0 ^ sl_st1[rt]] = db[rt][1];
+        for (int t = 0; t < NT; ++t) {
+            sa[B0 ^ sl[t]] = da[t];
+            sb[B0 ^ sl[t]] = db[t];
         }
-        __syncwarp();
     }
     if (has_w) {
-        // lane (m, kk) holds P[8tr+m][8tc+2kk], P[8tr+m][8tc+2kk+1]; rows 2r (even m) and 2r+1 (odd m) combine to
-        // W'[r][c] = (P[2r][2c] - P[2r+1][2c+1]) + i (P[2r][2c+1] + P[2r+1][2c]),  r = 4tr + m/2, c = 4tc + kk
-#pragma unroll
-        for (int tr = 0; tr < RT; ++tr)
-#pragma unroll
-            for (int tc = 0; tc < RT; ++tc) {
-                const double o0 = __shfl_xor_sync(0xffffffffu, pacc[tr][tc][0], 4);
-                const double o1 = __shfl_xor_sync(0xffffffffu, pacc[tr][tc][1], 4);
-                if ((m & 1) == 0) wslot[(4 * tr + (m >> 1)) * DIM + 4 * tc + kk] = cmake(pacc[tr][tc][0] - o1, pacc[tr][tc][1] + o0);
-            }
+        if (KQ == 3) {
+            // lane (rho, jj) holds P[(rho, a)][(2jj + e, b)] in pacc[a][b][e]:
+            // W'[rho][gamma] = (P[re][re] - P[im][im]) + i (P[re][im] + P[im][re])
+            const int wi = T->widx[lane];
+            wslot[wi & 255] = cmake(pacc[0][0][0] - pacc[NT - 1][NT - 1][0], pacc[0][NT - 1][0] + pacc[NT - 1][0][0]);
+            wslot[(wi >> 8) & 255] = cmake(pacc[0][0][1] - pacc[NT - 1][NT - 1][1], pacc[0][NT - 1][1] + pacc[NT - 1][0][1]);
+        } else {
+            // lane (m, kk) holds P[m][2kk], P[m][2kk+1]; rows 2r (even m) and 2r+1 (odd m) combine to
+            // W'[r][c] = (P[2r][2c] - P[2r+1][2c+1]) + i (P[2r][2c+1] + P[2r+1][2c]),  r = m/2, c = kk
+            const int m = lane >> 2, kk = lane & 3;
+            const double o0 = __shfl_xor_sync(0xffffffffu, pacc[0][0][0], 4);
+            const double o1 = __shfl_xor_sync(0xffffffffu, pacc[0][0][1], 4);
+            if ((m & 1) == 0) wslot[(m >> 1) * DIM + kk] = cmake(pacc[0][0][0] - o1, pacc[0][0][1] + o0);
+        }
     }
 }
 
@@ -597,7 +584,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                 const int i = e >> LOG_CT, c = e & (CT - 1);
                 cplx v = czero();
                 if (c < valid) v = src[(size_t)i * A.ld_in + c];
-                sa[phys_row<LOG_CT>(i) * CT + c] = v;
+                sa[elem<LOG_CT>(i, c)] = v;
             }
             if (A.n_ops > 0 && tid < KM_ELEMS) skm[tid] = kernel_elem(0);
             if (A.n_ops > 0) {
@@ -632,7 +619,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                 for (int item = tid; item < nitems; item += nthr) {
                     const int c = item & (CT - 1);
                     const int i0 = insert_zero(item >> LOG_CT, s.q0);
-                    const int e0 = phys_row<LOG_CT>(i0) * CT + c, e1 = phys_row<LOG_CT>(i0 | tbit) * CT + c;
+                    const int e0 = elem<LOG_CT>(i0, c), e1 = elem<LOG_CT>(i0 | tbit, c);
                     const cplx a0 = sa[e0], a1 = sa[e1];
                     sa[e0] = cfma(k01, a1, cmul(k00, a0));
                     sa[e1] = cfma(k11, a1, cmul(k10, a0));
@@ -654,7 +641,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                         for (int item = tid; item < nitems; item += nthr) {
                             const int c = item & (CT - 1);
                             const int i0 = insert_zero(insert_zero(insert_zero(item >> LOG_CT, f0), f1), f2) | cm;
-                            const int e0 = phys_row<LOG_CT>(i0) * CT + c, e1 = phys_row<LOG_CT>(i0 | tbit) * CT + c;
+                            const int e0 = elem<LOG_CT>(i0, c), e1 = elem<LOG_CT>(i0 | tbit, c);
                             const cplx a0 = sa[e0], a1 = sa[e1];
                             sa[e0] = cfma(k01, a1, cmul(k00, a0));
                             sa[e1] = cfma(k11, a1, cmul(k10, a0));
@@ -664,7 +651,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                         for (int item = tid; item < nitems; item += nthr) {
                             const int c = item & (CT - 1);
                             const int i0 = insert_zero(item >> LOG_CT, op.target);
-                            const int e0 = phys_row<LOG_CT>(i0) * CT + c, e1 = phys_row<LOG_CT>(i0 | tbit) * CT + c;
+                            const int e0 = elem<LOG_CT>(i0, c), e1 = elem<LOG_CT>(i0 | tbit, c);
                             if ((i0 & cm) == cm) {
                                 const cplx a0 = sa[e0], a1 = sa[e1];
                                 sa[e0] = cfma(k01, a1, cmul(k00, a0));
@@ -713,7 +700,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                             for (int l = 0; l < dim; ++l) {
                                 int r = base;
                                 for (int j = 0; j < nq; ++j) r |= ((l >> j) & 1) << op.q[j];
-                                v[l] = active ? sa[phys_row<LOG_CT>(r) * CT + c] : czero();
+                                v[l] = active ? sa[elem<LOG_CT>(r, c)] : czero();
                             }
                             for (int ro = 0; ro < dim; ++ro) {
                                 cplx acc = czero();
@@ -721,7 +708,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                                     for (int l = 0; l < dim; ++l) acc = cfma(sk[ro * dim + l], v[l], acc);
                                 int r = base;
                                 for (int j = 0; j < nq; ++j) r |= ((ro >> j) & 1) << op.q[j];
-                                sa[phys_row<LOG_CT>(r) * CT + c] = acc;
+                                sa[elem<LOG_CT>(r, c)] = acc;
                             }
                         }
                     }
@@ -736,7 +723,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
             cplx* __restrict__ dst = A.out + (size_t)y * A.out_ystride + j0;
             for (int e = tid; e < rows * CT; e += nthr) {
                 const int i = e >> LOG_CT, c = e & (CT - 1);
-                if (c < valid) dst[(size_t)i * A.ld_out + c] = sa[phys_row<LOG_CT>(i) * CT + c];
+                if (c < valid) dst[(size_t)i * A.ld_out + c] = sa[elem<LOG_CT>(i, c)];
             }
             __syncthreads();
             continue;
@@ -747,7 +734,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
             double t[6] = {0, 0, 0, 0, 0, 0};
             const int off = A.trace_offset;
             if (tid < valid) {
-                const cplx v = sa[phys_row<LOG_CT>(j0 + tid + off) * CT + tid];
+                const cplx v = sa[elem<LOG_CT>(j0 + tid + off, tid)];
                 t[0] = v.x;
                 t[1] = v.y;
             }
@@ -755,7 +742,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                 for (int e = tid; e < A.n * CT; e += nthr) {
                     const int c = e & (CT - 1), qb = e >> LOG_CT;
                     if (c < valid) {
-                        const cplx v = sa[phys_row<LOG_CT>((j0 + c + off) ^ (1 << qb)) * CT + c];
+                        const cplx v = sa[elem<LOG_CT>((j0 + c + off) ^ (1 << qb), c)];
                         t[2] += v.x;
                         t[3] += v.y;
                     }
@@ -767,7 +754,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                     for (int q2 = q1 + 1; q2 < A.n; ++q2)
                         for (int c = 0; c < valid; ++c, ++e)
                             if (e % nthr == tid) {
-                                const cplx v = sa[phys_row<LOG_CT>((j0 + c + off) ^ ((1 << q1) | (1 << q2))) * CT + c];
+                                const cplx v = sa[elem<LOG_CT>((j0 + c + off) ^ ((1 << q1) | (1 << q2)), c)];
                                 t[4] += v.x;
                                 t[5] += v.y;
                             }
@@ -799,12 +786,12 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
             {
                 const int off = A.trace_offset;
                 const cplx w0 = A.omega[(size_t)y * 3 + 0];
-                if (tid < valid) sb[phys_row<LOG_CT>(j0 + tid + off) * CT + tid] = w0;
+                if (tid < valid) sb[elem<LOG_CT>(j0 + tid + off, tid)] = w0;
                 if (A.n_trace_types > 1) {
                     const cplx w1 = A.omega[(size_t)y * 3 + 1];
                     for (int e = tid; e < A.n * CT; e += nthr) {
                         const int c = e & (CT - 1), qb = e >> LOG_CT;
-                        if (c < valid) sb[phys_row<LOG_CT>((j0 + c + off) ^ (1 << qb)) * CT + c] = w1;
+                        if (c < valid) sb[elem<LOG_CT>((j0 + c + off) ^ (1 << qb), c)] = w1;
                     }
                 }
                 if (A.n_trace_types > 2) {
@@ -814,7 +801,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                         for (int q2 = q1 + 1; q2 < A.n; ++q2)
                             for (int c = 0; c < valid; ++c, ++e)
                                 if (e % nthr == tid)
-                                    sb[phys_row<LOG_CT>((j0 + c + off) ^ ((1 << q1) | (1 << q2))) * CT + c] = w2;
+                                    sb[elem<LOG_CT>((j0 + c + off) ^ ((1 << q1) | (1 << q2)), c)] = w2;
                 }
             }
             __syncthreads();
@@ -850,7 +837,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                     for (int item = tid; item < nitems; item += nthr) {
                         const int c = item & (CT - 1);
                         const int i0 = insert_zero(item >> LOG_CT, s.q0);
-                        const int e0 = phys_row<LOG_CT>(i0) * CT + c, e1 = phys_row<LOG_CT>(i0 | tbit) * CT + c;
+                        const int e0 = elem<LOG_CT>(i0, c), e1 = elem<LOG_CT>(i0 | tbit, c);
                         const cplx p0 = sa[e0], p1 = sa[e1], b0 = sb[e0], b1 = sb[e1];
                         sa[e0] = cfmac(k10, p1, cfmac(k00, p0, czero()));
                         sa[e1] = cfmac(k11, p1, cfmac(k01, p0, czero()));
@@ -878,7 +865,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                         for (int item = tid; item < nitems; item += nthr) {
                             const int c = item & (CT - 1);
                             const int i0 = insert_zero(insert_zero(insert_zero(item >> LOG_CT, f0), f1), f2) | cm;
-                            const int e0 = phys_row<LOG_CT>(i0) * CT + c, e1 = phys_row<LOG_CT>(i0 | tbit) * CT + c;
+                            const int e0 = elem<LOG_CT>(i0, c), e1 = elem<LOG_CT>(i0 | tbit, c);
                             const cplx p0 = sa[e0], p1 = sa[e1], b0 = sb[e0], b1 = sb[e1];
                             sa[e0] = cfmac(k10, p1, cfmac(k00, p0, czero()));
                             sa[e1] = cfmac(k11, p1, cfmac(k01, p0, czero()));
@@ -912,7 +899,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                             for (int l = 0; l < dim; ++l) {
                                 int r = base;
                                 for (int j = 0; j < nq; ++j) r |= ((l >> j) & 1) << op.q[j];
-                                addr[l] = phys_row<LOG_CT>(r) * CT + c;
+                                addr[l] = elem<LOG_CT>(r, c);
                                 pv[l] = sa[addr[l]];
                                 bv[l] = sb[addr[l]];
                             }
