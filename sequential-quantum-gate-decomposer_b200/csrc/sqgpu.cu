@@ -119,6 +119,7 @@ struct sqgpu_ctx {
     int device = 0;
     int sm_count = 148;
     int smem_optin = 0;
+    int smem_per_sm = 0;
     std::mutex mtx;
     cudaStream_t stream = nullptr;
 
@@ -422,11 +423,33 @@ FusedPlan plan_fused(const sqgpu_ctx* c, int mode, int rows, int cols, int ysets
         }
     }
     if (pick < 0) return p;
+    int pick_threads = threads_for(1 << pick);
+    // Columns are independent, so two half-width CTAs per SM do the work of one: while one CTA sits in the barrier /
+    // table prologue between two ops, the other keeps the FP64 tensor pipe busy. Taken when both fit in the SM.
+    {
+        const char* sp = getenv("SQGPU_SPLIT");
+        const int split = sp ? atoi(sp) : 2;
+        int lc = pick, thr = pick_threads, ways = 1;
+        while (ways < split && lc > 0 && thr >= 128) {
+            --lc;
+            thr /= 2;
+            ways *= 2;
+        }
+        if (ways > 1 && mode != MODE_APPLY) {
+            const size_t sm = fused_smem(mode, rows, 1 << lc, thr, c->P->dense_stage, c->P->wmax, c->P->w_total, false, c->P->n_ops);
+            const char* fc = getenv("SQGPU_SPLIT_FORCE");
+            if ((fc && fc[0] == '1') || ((sm + 1024) * ways <= (size_t)c->smem_per_sm && thr * ways * 128 <= 65536)) {
+                pick = lc;
+                pick_threads = thr;
+                pick_wsm = false;
+            }
+        }
+    }
     {
         const int lc = pick, ct = 1 << lc;
         p.ok = true;
         p.log_ct = lc;
-        p.threads = threads_for(ct);
+        p.threads = pick_threads;
         p.w_in_smem = pick_wsm;
         p.smem = fused_smem(mode, rows, ct, p.threads, c->P->dense_stage, c->P->wmax, c->P->w_total, pick_wsm, c->P->n_ops);
         p.tiles = (cols + ct - 1) / ct;
@@ -930,6 +953,7 @@ int sqgpu_create(int device, sqgpu_handle_t* out) {
     c->device = device;
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
     cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    cudaDeviceGetAttribute(&c->smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
     e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         delete c;
