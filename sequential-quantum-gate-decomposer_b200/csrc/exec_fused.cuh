@@ -488,6 +488,108 @@ __device__ __forceinline__ void block_dmma_backward(cplx* sa, cplx* sb, const Op
     }
 }
 
+// Raw dense 3-/4-qubit kernels (GENERAL blocks; no controls) in the same formulation as the fused blocks: data = A operand,
+// 128-bit per-lane loads / stores of the same elements, kernel fragments (NT x KS doubles per lane) in registers. The
+// fragment table is built in shared memory by the CTA (skf: [NT * KS][32] doubles, schoice: 2 ints), the two block-qubit
+// positions that index the lane's amplitude slot are picked for the fewest bank conflicts.
+template <int LOG_CT, int KQ>
+__device__ __forceinline__ void dense_dmma_forward2(cplx* sa, double* skf, int* schoice, const cplx* __restrict__ K, const DevOp& op,
+                                                    int rows, int tid, int nthr) {
+    constexpr int CT = 1 << LOG_CT, LOGG = 3 - LOG_CT, DIM = 1 << KQ, NT = DIM / 4, KS = 2 * NT;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
+    int q[KQ], Pq[KQ], F[3];
+    unsigned qmask = 0;
+#pragma unroll
+    for (int j = 0; j < KQ; ++j) {
+        q[j] = op.q[j];
+        Pq[j] = elem<LOG_CT>(1 << q[j], 0);
+        qmask |= 1u << q[j];
+    }
+    {
+        int f = 0;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            while ((qmask >> f) & 1u) ++f;
+            F[j] = elem<LOG_CT>(1 << f, 0);
+            ++f;
+        }
+    }
+    // amplitude index of lane slot j (2 bits, on positions ja < jb) and k-step group u (the other positions, ascending)
+    auto dep = [&](int j, int u, int ja, int jb) {
+        int amp = ((j & 1) << ja) | (((j >> 1) & 1) << jb), ub = 0;
+#pragma unroll
+        for (int pos = 0; pos < KQ; ++pos)
+            if (pos != ja && pos != jb) {
+                amp |= ((u >> ub) & 1) << pos;
+                ++ub;
+            }
+        return amp;
+    };
+    auto slot = [&](int item, int amp) {
+        const int go = item >> LOG_CT;
+        int a = item & (CT - 1);
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            if (j < LOGG && ((go >> j) & 1)) a ^= F[j];
+#pragma unroll
+        for (int j = 0; j < KQ; ++j)
+            if ((amp >> j) & 1) a ^= Pq[j];
+        return a;
+    };
+    if (tid == 0) {
+        int best = -1, bja = 0, bjb = 1;
+        for (int ja = 0; ja < KQ; ++ja)
+            for (int jb = ja + 1; jb < KQ; ++jb) {
+                unsigned seen = 0;
+                for (int l = 0; l < 8; ++l) seen |= 1u << (slot(l >> 2, dep(l & 3, 0, ja, jb)) & 7);
+                if (__popc(seen) > best) {
+                    best = __popc(seen);
+                    bja = ja;
+                    bjb = jb;
+                }
+            }
+        schoice[0] = bja;
+        schoice[1] = bjb;
+    }
+    __syncthreads();
+    const int ja = schoice[0], jb = schoice[1];
+    for (int e = tid; e < NT * KS * 32; e += nthr) {
+        const int ts = e >> 5, l = e & 31, t = ts / KS, ks = ts - t * KS, n = l >> 2, k = l & 3;
+        skf[e] = kreal_entry(K, DIM, 0, dep(n >> 1, t, ja, jb), n & 1, dep(k, ks >> 1, ja, jb), ks & 1);
+    }
+    __syncthreads();
+    double kf[NT][KS];
+    int sl[NT];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+        sl[t] = slot(lane >> 2, dep(lane & 3, t, ja, jb));
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) kf[t][ks] = skf[(t * KS + ks) * 32 + lane];
+    }
+    const int nitems = (rows >> KQ) << LOG_CT;
+    for (int b0 = warp * 8; b0 < nitems; b0 += nwarps * 8) {
+        int base = b0 >> LOG_CT;
+#pragma unroll
+        for (int j = 0; j < KQ; ++j) base = insert_zero(base, q[j]);
+        const int B0 = elem<LOG_CT>(base, 0);
+        cplx x[NT], d[NT];
+#pragma unroll
+        for (int u = 0; u < NT; ++u) {
+            x[u] = sa[B0 ^ sl[u]];
+            d[u] = czero();
+        }
+#pragma unroll
+        for (int u = 0; u < NT; ++u)
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                dmma_m8n8k4(d[t].x, d[t].y, x[u].x, kf[t][2 * u]);
+                dmma_m8n8k4(d[t].x, d[t].y, x[u].y, kf[t][2 * u + 1]);
+            }
+#pragma unroll
+        for (int t = 0; t < NT; ++t) sa[B0 ^ sl[t]] = d[t];
+    }
+}
+
 // compact per-op record staged in shared memory (uniform reads, no global latency on the critical path)
 struct SOp {
     int32_t dim;       // 2 / 4 / 8 for block ops
@@ -667,8 +769,14 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                     const int nq = op.nq;
                     const int nitems = (rows >> nq) << LOG_CT;
                     const bool use_dmma = !deriv && op.ctrl_mask == 0 && nq >= 3 && (nitems & 7) == 0;
-                    if (use_dmma) {
-                        // stage the real embedding of K (padded rows) and the local-index -> row-bit pattern
+                    if (use_dmma && nq <= 4) {
+                        // fragment table in the staging area: [NT * KS][32] doubles (8 KB for 4 qubits) + 2 ints
+                        double* skf = reinterpret_cast<double*>(sk);
+                        int* schoice = reinterpret_cast<int*>(skf + 4 * dim * dim);
+                        if (nq == 3) dense_dmma_forward2<LOG_CT, 3>(sa, skf, schoice, K, op, rows, tid, nthr);
+                        else dense_dmma_forward2<LOG_CT, 4>(sa, skf, schoice, K, op, rows, tid, nthr);
+                    } else if (use_dmma) {
+                        // 5 qubits: stage the real embedding of K (padded rows) and the local-index -> row-bit pattern
                         const int dimr = 2 * dim, ld = dimr + DMMA_PAD;
                         double* skr = reinterpret_cast<double*>(sk);
                         int* spat = reinterpret_cast<int*>(skr + dimr * ld);
@@ -684,9 +792,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                             spat[l] = r;
                         }
                         __syncthreads();
-                        if (nq == 3) dense_dmma_forward<LOG_CT, 3>(sa, skr, spat, op, rows, tid, nthr);
-                        else if (nq == 4) dense_dmma_forward<LOG_CT, 4>(sa, skr, spat, op, rows, tid, nthr);
-                        else dense_dmma_forward<LOG_CT, 5>(sa, skr, spat, op, rows, tid, nthr);
+                        dense_dmma_forward<LOG_CT, 5>(sa, skr, spat, op, rows, tid, nthr);
                     } else {
                         for (int e = tid; e < dim * dim; e += nthr) sk[e] = K[e];
                         __syncthreads();

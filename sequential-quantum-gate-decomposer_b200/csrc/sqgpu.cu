@@ -1047,7 +1047,8 @@ int sqgpu_set_circuit(sqgpu_handle_t c, const sqgpu_gate_desc* gates, int n_gate
             if (op.dim > 2) {
                 // generic dense path: dim^2 complex; raw 4-5 qubit kernels on the tensor cores: padded real embedding + patterns
                 int need = op.dim * op.dim;
-                if (op.dim > 8) need = (2 * op.dim) * (2 * op.dim + 4) / 2 + op.dim;
+                if (op.dim > 16) need = (2 * op.dim) * (2 * op.dim + 4) / 2 + op.dim;
+                else if (op.type == SQGPU_GENERAL && op.dim >= 8) need = 2 * op.dim * op.dim + 1;  // DMMA fragment table
                 dense_stage = std::max(dense_stage, need);
             }
             if (op.n_params > 0) {
