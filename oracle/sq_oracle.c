@@ -284,6 +284,69 @@ void sqo_apply_large_kernel_to_input(const double* kernel, double* input, int ro
     }
 }
 
+/* SYC (Sycamore fSim(pi/2, pi/6)), kernels/apply_dedicated_gate_kernel_to_input.cpp:582-640: rows with (target, control)
+ * bits (1,0) and (0,1) are exchanged and multiplied by -i, rows with both bits set by exp(-i pi/6); symmetric in the two
+ * qubits. */
+static void sqo_apply_syc(double* input, int rows, int cols, int stride, int target, int control) {
+    cplx* in = (cplx*)input;
+    const int tb = 1 << target, cb = 1 << control;
+    const double pr = sqrt(3.0) / 2.0, pi_ = -0.5;
+    for (int r = 0; r < rows; ++r) {
+        if ((r & tb) || (r & cb)) continue; /* r = the (0,0) row of its group */
+        cplx* r01 = in + (size_t)(r | tb) * stride;
+        cplx* r10 = in + (size_t)(r | cb) * stride;
+        cplx* r11 = in + (size_t)(r | tb | cb) * stride;
+        for (int c = 0; c < cols; ++c) {
+            const cplx e01 = r01[c], e10 = r10[c], e11 = r11[c];
+            r01[c].re = e10.im;  r01[c].im = -e10.re;
+            r10[c].re = e01.im;  r10[c].im = -e01.re;
+            r11[c].re = pr * e11.re - pi_ * e11.im;
+            r11[c].im = pr * e11.im + pi_ * e11.re;
+        }
+    }
+}
+
+/* CROT kernels, gates/include/gate_kernel_templates.h:779-877: the control = 0 branch is U3(theta, phi - pi/2, -phi + pi/2),
+ * the control = 1 branch the same with -theta (Gate.cpp:1568-1580 hands the "inverse" kernel to the control = 1 rows of
+ * apply_crot_kernel_to_matrix_input, kernels/apply_large_kernel_to_input.cpp:436-505). which: -1 forward, 0 d/dtheta
+ * (theta -> theta + pi/2 on both branches), 1 d/dphi (U3(+-theta, phi, -phi) with the diagonal zeroed). */
+static void crot_kernels(const double* p, int which, double* k0, double* k1) {
+    double st, ct, sp, cp;
+    sincos(p[0], &st, &ct);
+    sincos(p[1], &sp, &cp);
+    if (which == 0) { const double t = st; st = ct; ct = -t; }
+    if (which <= 0) {
+        u3_from_trig(k0, st, ct, -cp, sp, cp, sp);
+        u3_from_trig(k1, -st, ct, -cp, sp, cp, sp);
+    } else {
+        u3_from_trig(k0, st, ct, sp, cp, -sp, cp);
+        u3_from_trig(k1, -st, ct, sp, cp, -sp, cp);
+        kset(k0, 0, 0, 0); kset(k0, 3, 0, 0); kset(k1, 0, 0, 0); kset(k1, 3, 0, 0);
+    }
+}
+
+static void sqo_apply_crot(const double* k0, const double* k1, double* input, int rows, int cols, int stride, int target, int control) {
+    cplx* in = (cplx*)input;
+    const int step = 1 << target;
+    for (int base = 0; base < rows; base += (step << 1))
+        for (int idx = 0; idx < step; ++idx) {
+            const int r0 = base + idx, r1 = r0 + step;
+            const cplx* k = (const cplx*)(((r0 >> control) & 1) ? k1 : k0);
+            cplx* row0 = in + (size_t)r0 * stride;
+            cplx* row1 = in + (size_t)r1 * stride;
+            for (int c = 0; c < cols; ++c) {
+                const cplx e0 = row0[c], e1 = row1[c];
+                cplx t1 = cmul(k[0], e0), t2 = cmul(k[1], e1);
+                row0[c].re = t1.re + t2.re;
+                row0[c].im = t1.im + t2.im;
+                t1 = cmul(k[2], e0);
+                t2 = cmul(k[3], e1);
+                row1[c].re = t1.re + t2.re;
+                row1[c].im = t1.im + t2.im;
+            }
+        }
+}
+
 /* Gate::apply_to / apply_to_inner -> gate_kernel_to -> apply_kernel_to (Gate.cpp:432-570, 1477-1768) and
  * Gate::apply_derivative_to_precomputed (Gate.cpp:644-706; deriv == true). */
 int sqo_apply_gate(const sqgpu_gate_desc* g, const double* params, const double* pool, int deriv_param, double* input,
@@ -299,6 +362,17 @@ int sqo_apply_gate(const sqgpu_gate_desc* g, const double* params, const double*
             sqo_apply_large_kernel_to_input(pool + 2 * g->matrix_off, input, rows, cols, stride, g->qubits,
                                             g->n_qubits, -1, 0);
         }
+        return 0;
+    }
+    if (g->type == SQGPU_SYC) {
+        if (deriv) return -1;
+        sqo_apply_syc(input, rows, cols, stride, g->target, g->control);
+        return 0;
+    }
+    if (g->type == SQGPU_CROT) {
+        double k1[8];
+        crot_kernels(gp, deriv ? deriv_param : -1, k, k1);
+        sqo_apply_crot(k, k1, input, rows, cols, stride, g->target, g->control);
         return 0;
     }
     const int dim = deriv ? sqo_gate_derivative_kernel(g->type, gp, deriv_param, k) : sqo_gate_kernel(g->type, gp, k);

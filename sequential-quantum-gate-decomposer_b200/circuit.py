@@ -98,6 +98,8 @@ class Circuit:
     def add_CP(self, target_qbit, control_qbit): self._add_c1q(abi.CP, target_qbit, control_qbit)
     def add_CR(self, target_qbit, control_qbit): self._add_c1q(abi.CR, target_qbit, control_qbit)
     def add_adaptive(self, target_qbit, control_qbit): self._add_c1q(abi.ADAPTIVE, target_qbit, control_qbit)
+    def add_CROT(self, target_qbit, control_qbit): self._add_c1q(abi.CROT, target_qbit, control_qbit)
+    def add_SYC(self, target_qbit, control_qbit): self._add_c1q(abi.SYC, target_qbit, control_qbit)
     def add_RXX(self, target_qbits): self._add_2t(abi.RXX, target_qbits)
     def add_RYY(self, target_qbits): self._add_2t(abi.RYY, target_qbits)
     def add_RZZ(self, target_qbits): self._add_2t(abi.RZZ, target_qbits)

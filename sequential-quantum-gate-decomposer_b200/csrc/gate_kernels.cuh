@@ -121,6 +121,31 @@ __device__ inline int build_gate_kernel(int type, const Trig& t, int which, cplx
             zero16(k);
             k[0] = cmake(1, 0); k[6] = cmake(1, 0); k[9] = cmake(1, 0); k[15] = cmake(1, 0);
             return 4;
+        case SQGPU_SYC:  // fSim(pi/2, pi/6), kernels/apply_dedicated_gate_kernel_to_input.cpp:582-640 (symmetric in its qubits)
+            zero16(k);
+            k[0] = cmake(1, 0); k[6] = cmake(0, -1); k[9] = cmake(0, -1); k[15] = cmake(0.86602540378443864676, -0.5);
+            return 4;
+        case SQGPU_CROT: {
+            // local index = target bit | control bit << 1. control = 0: U3(theta, phi - pi/2, -phi + pi/2), control = 1: the
+            // same with -theta (gate_kernel_templates.h:779-807; Gate.cpp:1568-1580 gives the "inverse" kernel to the
+            // control = 1 rows). d/dtheta: theta -> theta + pi/2 on both branches (:831-842); d/dphi: U3(+-theta, phi, -phi)
+            // with the diagonal zeroed (:866-877). Derivative kernels are NOT zero-filled: both branches carry them.
+            zero16(k);
+            double st = s0, ct = c0;
+            if (which == 0) { st = c0; ct = -s0; }
+            cplx b0[4], b1[4];
+            if (which <= 0) {
+                u3_body(b0, -1, st, ct, -c1, s1, c1, s1);
+                u3_body(b1, -1, -st, ct, -c1, s1, c1, s1);
+            } else {
+                u3_body(b0, -1, st, ct, s1, c1, -s1, c1);
+                u3_body(b1, -1, -st, ct, s1, c1, -s1, c1);
+                b0[0] = b0[3] = b1[0] = b1[3] = czero();
+            }
+            k[0] = b0[0]; k[1] = b0[1]; k[4] = b0[2]; k[5] = b0[3];
+            k[10] = b1[0]; k[11] = b1[1]; k[14] = b1[2]; k[15] = b1[3];
+            return 4;
+        }
         default: return 0;
     }
 }
@@ -276,12 +301,19 @@ __global__ void __launch_bounds__(TABLE_WARPS * 32) build_kernel_tables(
     }
     cplx k[16];
     const int dim = build_gate_kernel(op.type, t, -1, k);
-    for (int i = 0; i < dim * dim; ++i) kdst[i] = k[i];
+    // two-qubit kernels are built with kernel bit 0 = op.target; the op's local bit 0 is its LOWER qubit
+    const bool flip = dim == 4 && op.target == op.q[1];
+    auto src = [&](int i) {
+        if (!flip) return i;
+        const int r = i >> 2, c = i & 3;
+        return ((((r & 1) << 1) | (r >> 1)) << 2) | (((c & 1) << 1) | (c >> 1));
+    };
+    for (int i = 0; i < dim * dim; ++i) kdst[i] = k[src(i)];
     if (with_deriv) {
         for (int p = 0; p < op.n_params; ++p) {
             build_gate_kernel(op.type, t, p, k);
             cplx* dd = dkdst + p * dim * dim;
-            for (int i = 0; i < dim * dim; ++i) dd[i] = k[i];
+            for (int i = 0; i < dim * dim; ++i) dd[i] = k[src(i)];
         }
     }
 }

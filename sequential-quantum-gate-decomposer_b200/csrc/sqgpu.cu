@@ -243,13 +243,13 @@ int param_count_of(int type) {
     switch (type) {
         case SQGPU_U3: return 3;
         case SQGPU_CU: return 4;
-        case SQGPU_U2: case SQGPU_R: case SQGPU_CR: return 2;
+        case SQGPU_U2: case SQGPU_R: case SQGPU_CR: case SQGPU_CROT: return 2;
         case SQGPU_RX: case SQGPU_RY: case SQGPU_RZ: case SQGPU_U1: case SQGPU_CRY: case SQGPU_CRX: case SQGPU_CRZ:
         case SQGPU_CP: case SQGPU_ADAPTIVE: case SQGPU_RXX: case SQGPU_RYY: case SQGPU_RZZ: return 1;
         case SQGPU_GENERAL: case SQGPU_CZ: case SQGPU_CNOT: case SQGPU_CH: case SQGPU_X: case SQGPU_Y: case SQGPU_Z:
         case SQGPU_H: case SQGPU_S: case SQGPU_SDG: case SQGPU_T: case SQGPU_TDG: case SQGPU_SX: case SQGPU_SXDG:
-        case SQGPU_CCX: case SQGPU_SWAP: case SQGPU_CSWAP: return 0;
-        default: return -1;  // CROT, SYC: not on the device path yet
+        case SQGPU_CCX: case SQGPU_SWAP: case SQGPU_CSWAP: case SQGPU_SYC: return 0;
+        default: return -1;
     }
 }
 
@@ -335,6 +335,20 @@ int lower_gate(const sqgpu_gate_desc& g, int qbit_num, const double* pool, int64
         *out = op;
         return SQGPU_OK;
     }
+    if (g.type == SQGPU_SYC || g.type == SQGPU_CROT) {
+        // two-qubit kernels over (target, control): a dense 4 x 4 op on the sorted pair; op.target keeps the qubit that is
+        // kernel bit 0 (build_kernel_tables flips the kernel when that is the higher qubit; block members carry tl / tl2)
+        if (!qok(g.target) || !qok(g.control) || g.control == g.target) return fail(SQGPU_ERR_INVALID, "gate type %d: bad target / control qubits %d / %d", g.type, g.target, g.control);
+        op.dim = 4;
+        op.nq = 2;
+        op.q[0] = std::min(g.target, g.control);
+        op.q[1] = std::max(g.target, g.control);
+        op.target = g.target;
+        op.member_off = -1;
+        fill_fix(op);
+        *out = op;
+        return SQGPU_OK;
+    }
     const bool two_target = g.type == SQGPU_RXX || g.type == SQGPU_RYY || g.type == SQGPU_RZZ || g.type == SQGPU_SWAP || g.type == SQGPU_CSWAP;
     if (!qok(g.target)) return fail(SQGPU_ERR_INVALID, "gate type %d: target qubit %d out of range", g.type, g.target);
     unsigned cm = 0;
@@ -358,6 +372,7 @@ int lower_gate(const sqgpu_gate_desc& g, int qbit_num, const double* pool, int64
         op.nq = 2;
         op.q[0] = std::min(g.target, g.target2);
         op.q[1] = std::max(g.target, g.target2);
+        op.target = op.q[0];
     } else {
         op.dim = 2;
         op.target = g.target;
@@ -1093,8 +1108,9 @@ int sqgpu_set_circuit(sqgpu_handle_t c, const sqgpu_gate_desc* gates, int n_gate
                         for (int q = 0; q < 30; ++q)
                             if ((r.ctrl_mask >> q) & 1) m.cl = local_bit(q);
                 } else {
-                    m.tl = local_bit(r.q[0]);
-                    m.tl2 = local_bit(r.q[1]);
+                    const bool hi_first = r.target == r.q[1];  // kernel bit 0 sits on the higher qubit (CROT with target > control)
+                    m.tl = local_bit(hi_first ? r.q[1] : r.q[0]);
+                    m.tl2 = local_bit(hi_first ? r.q[0] : r.q[1]);
                 }
                 m.param_start = r.param_start;
                 m.n_params = r.n_params;

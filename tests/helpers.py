@@ -6,7 +6,7 @@ import squander_b200 as sq
 abi = sq.abi
 
 ONE_Q = ["U1", "U2", "U3", "RX", "RY", "RZ", "R", "H", "X", "Y", "Z", "S", "Sdg", "T", "Tdg", "SX", "SXdg"]
-CTRL = ["CNOT", "CZ", "CH", "CU", "CRY", "CRX", "CRZ", "CP", "CR", "adaptive"]
+CTRL = ["CNOT", "CZ", "CH", "CU", "CRY", "CRX", "CRZ", "CP", "CR", "adaptive", "CROT", "SYC"]
 TWO_T = ["RXX", "RYY", "RZZ", "SWAP"]
 
 

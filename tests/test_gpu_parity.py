@@ -196,6 +196,33 @@ def test_mixed_gate_circuit_gradient(sq, port, plan_mode):
         assert close_rel(f, f_ref) and close_rel(g, g_ref)
 
 
+def test_crot_and_syc_in_fused_blocks(sq, port, plan_mode):
+    """CROT (both qubit orders: its two branches are not symmetric) and SYC as members of fused blocks, as stand-alone ops,
+    and through the gradient (CROT.cpp, SYC.cpp; kernels/apply_large_kernel_to_input.cpp:436-505)"""
+    n = 5
+    c = sq.Circuit(n)
+    for t, cq in ((0, 3), (3, 0), (4, 1), (1, 2), (2, 1)):
+        c.add_U3(t)
+        c.add_CROT(t, cq)
+        c.add_RY(cq)
+        c.add_SYC(cq, t)
+        c.add_CNOT((t + 1) % n if (t + 1) % n != cq else (t + 2) % n, cq)
+        c.add_CROT(cq, t)
+    d, pool = c.descriptors()
+    P = c.get_Parameter_Num()
+    U = H.random_unitary(1 << n)
+    p = H.random_params(P, seed=21)
+    out = c.apply_to(p, U)
+    assert np.abs(out - port.apply_circuit(d, p, U, pool=pool)).max() < ENTRY_TOL
+    dec = sq.N_Qubit_Decomposition_custom(U)
+    dec.set_Gate_Structure(c)
+    for variant in (0, 3):
+        dec.set_Cost_Function_Variant(variant)
+        f, g = dec.Optimization_Problem_Combined(p)
+        f_ref, g_ref = port.cost_grad(d, P, p, U, n, variant, pool=pool)
+        assert close_rel(f, f_ref) and close_rel(g, g_ref)
+
+
 def test_reference_wrapper_flow(sq, port):
     """the call sequence of the reference's own test (tests/decomposition/test_optmization_problem_combined.py:189-219)"""
     n, levels = 5, 2
