@@ -30,7 +30,10 @@
 
 namespace sq {
 
-enum { MODE_COST = 0, MODE_GRAD = 1, MODE_APPLY = 2 };
+// MODE_COST: forward sweep + trace terms.  MODE_GRAD: + adjoint (backward) sweep.  MODE_APPLY: forward sweep, tile stored.
+// MODE_BWD: one segment of the adjoint sweep over a state vector that lives in HBM -- the column tile `a` (out) and the row
+// functional `beta` are loaded, swept backward through the segment's ops and stored again (windowed VQE executor).
+enum { MODE_COST = 0, MODE_GRAD = 1, MODE_APPLY = 2, MODE_BWD = 3 };
 
 struct OpTab;
 
@@ -50,7 +53,11 @@ struct ExecArgs {
     const cplx* dktab;       // [ysets][dkern_total]
     int dkern_total;
     const cplx* pool;
-    const struct OpTab* optabs;  // [ysets][n_ops] lookup tables of the DMMA block path (build_optabs)
+    const struct OpTab* optabs;  // [ysets][optab_stride] lookup tables of the DMMA block path (build_optabs)
+    int optab_stride;        // tables per parameter set (0: n_ops)
+    unsigned wmask;          // window mode (state vectors): bit mask of the `n_win` qubits that form the tile's rows; element
+                             // (row r, column j) of y lives at in[y * ystride + deposit(r, wmask) | deposit(j, ~wmask)]; 0: matrix
+    cplx* beta;              // MODE_BWD: the row functional, same layout and stride as out
     int k_shared;            // 1: every blockIdx.y uses kernel-table set 0 (materialised derivative: one parameter set)
     const int* deriv_op;     // MODE_APPLY: per blockIdx.y the op whose derivative kernel is applied (NULL: none)
     const int* deriv_slot;   //             and which of its derivative kernels
@@ -614,14 +621,16 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
     const cplx* __restrict__ dktab = A.dktab ? A.dktab + (size_t)kset * A.dkern_total : nullptr;
 
     cplx* sa = reinterpret_cast<cplx*>(smem_raw);
-    cplx* sb = sa + (size_t)rows * CT;                                   // MODE_GRAD only
-    cplx* sk = (MODE == MODE_GRAD) ? sb + (size_t)rows * CT : sb;         // raw dense kernel staging
+    constexpr bool HAS_B = (MODE == MODE_GRAD || MODE == MODE_BWD);
+    cplx* sb = sa + (size_t)rows * CT;                                   // the row functional beta (HAS_B only)
+    cplx* sk = HAS_B ? sb + (size_t)rows * CT : sb;                       // raw dense kernel staging
     cplx* skm = sk + A.dense_stage;                                       // [2][KM_ELEMS] prefetched block kernels
     OpTab* stab = reinterpret_cast<OpTab*>(skm + 2 * KM_ELEMS);           // [2] DMMA block lookup tables
     cplx* swarp = reinterpret_cast<cplx*>(stab + 2);                      // [2][nwarps][wmax]
-    cplx* swacc = swarp + ((MODE == MODE_GRAD) ? 2 * nwarps * A.wmax : 0);  // [w_total] if w_in_smem
-    double* sred = reinterpret_cast<double*>(swacc + ((MODE == MODE_GRAD && A.w_in_smem) ? A.w_total : 0));  // [nwarps][6]
+    cplx* swacc = swarp + (HAS_B ? 2 * nwarps * A.wmax : 0);              // [w_total] if w_in_smem
+    double* sred = reinterpret_cast<double*>(swacc + ((HAS_B && A.w_in_smem) ? A.w_total : 0));  // [nwarps][6]
     SOp* sops = reinterpret_cast<SOp*>(sred + nwarps * 6);               // [n_ops]
+    int* srowpart = reinterpret_cast<int*>(sops + A.n_ops);              // window mode: [rows] deposit(r, wmask)
 
     const int chunk = blockIdx.x;
     const int nchunks = gridDim.x;
@@ -647,8 +656,11 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
         s.q2 = op.dim == 8 ? op.q[2] : 30;
         sops[k] = s;
     }
-    if (MODE == MODE_GRAD && A.w_in_smem) {
+    if (HAS_B && A.w_in_smem) {
         for (int e = tid; e < A.w_total; e += nthr) swacc[e] = czero();
+    }
+    if (A.wmask) {
+        for (int r = tid; r < rows; r += nthr) srowpart[r] = (int)deposit_bits((unsigned)r, A.wmask);
     }
     double tsum[6] = {0, 0, 0, 0, 0, 0};  // running trace sums of this CTA (thread 0)
     __syncthreads();
@@ -663,7 +675,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
 
     // DMMA block table of op k: built per (parameter set, op) by build_optabs; copied global -> shared with cp.async while
     // the previous op computes (no registers held across the DMMA loops), into stab[k & 1]
-    const OpTab* __restrict__ gtabs = A.optabs + (size_t)kset * A.n_ops;
+    const OpTab* __restrict__ gtabs = A.optabs + (size_t)kset * (A.optab_stride ? A.optab_stride : A.n_ops);
     auto tab_prefetch = [&](int k) {
         if (sops[k].kind != 2) return;
         const char* src = reinterpret_cast<const char*>(gtabs + k);
@@ -681,23 +693,36 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
 
         // ---- load the tile ------------------------------------------------------------------------------------
         {
-            const cplx* __restrict__ src = A.in + (size_t)y * A.in_ystride + j0;
-            for (int e = tid; e < rows * CT; e += nthr) {
-                const int i = e >> LOG_CT, c = e & (CT - 1);
-                cplx v = czero();
-                if (c < valid) v = src[(size_t)i * A.ld_in + c];
-                sa[elem<LOG_CT>(i, c)] = v;
+            if (A.wmask) {
+                // window mode: the tile's columns are CT consecutive values of the non-window bits
+                const size_t colbase = (size_t)y * A.in_ystride + deposit_bits((unsigned)j0, ~A.wmask);
+                const cplx* __restrict__ src = (MODE == MODE_BWD ? A.out : A.in) + colbase;
+                for (int e = tid; e < rows * CT; e += nthr) {
+                    const int i = e >> LOG_CT, c = e & (CT - 1);
+                    const size_t off = (size_t)srowpart[i] | deposit_bits((unsigned)c, ~A.wmask);
+                    sa[elem<LOG_CT>(i, c)] = src[off];
+                    if (MODE == MODE_BWD) sb[elem<LOG_CT>(i, c)] = (A.beta + colbase)[off];
+                }
+            } else {
+                const cplx* __restrict__ src = A.in + (size_t)y * A.in_ystride + j0;
+                for (int e = tid; e < rows * CT; e += nthr) {
+                    const int i = e >> LOG_CT, c = e & (CT - 1);
+                    cplx v = czero();
+                    if (c < valid) v = src[(size_t)i * A.ld_in + c];
+                    sa[elem<LOG_CT>(i, c)] = v;
+                }
             }
-            if (A.n_ops > 0 && tid < KM_ELEMS) skm[tid] = kernel_elem(0);
+            const int first_op = (MODE == MODE_BWD) ? A.n_ops - 1 : 0;
+            if (A.n_ops > 0 && tid < KM_ELEMS) skm[(first_op & 1) * KM_ELEMS + tid] = kernel_elem(first_op);
             if (A.n_ops > 0) {
-                tab_prefetch(0);
+                tab_prefetch(first_op);
                 tab_wait();
             }
         }
         __syncthreads();
 
         // ---- forward sweep: op 0 first (Gates_block.cpp:683) ---------------------------------------------------
-        for (int k = 0; k < A.n_ops; ++k) {
+        for (int k = 0; k < (MODE == MODE_BWD ? 0 : A.n_ops); ++k) {
             const SOp s = sops[k];
             cplx next_elem = czero();
             const bool have_next = k + 1 < A.n_ops;
@@ -826,17 +851,25 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
         }
 
         if (MODE == MODE_APPLY) {
-            cplx* __restrict__ dst = A.out + (size_t)y * A.out_ystride + j0;
-            for (int e = tid; e < rows * CT; e += nthr) {
-                const int i = e >> LOG_CT, c = e & (CT - 1);
-                if (c < valid) dst[(size_t)i * A.ld_out + c] = sa[elem<LOG_CT>(i, c)];
+            if (A.wmask) {
+                cplx* __restrict__ dst = A.out + (size_t)y * A.out_ystride + deposit_bits((unsigned)j0, ~A.wmask);
+                for (int e = tid; e < rows * CT; e += nthr) {
+                    const int i = e >> LOG_CT, c = e & (CT - 1);
+                    dst[(size_t)srowpart[i] | deposit_bits((unsigned)c, ~A.wmask)] = sa[elem<LOG_CT>(i, c)];
+                }
+            } else {
+                cplx* __restrict__ dst = A.out + (size_t)y * A.out_ystride + j0;
+                for (int e = tid; e < rows * CT; e += nthr) {
+                    const int i = e >> LOG_CT, c = e & (CT - 1);
+                    if (c < valid) dst[(size_t)i * A.ld_out + c] = sa[elem<LOG_CT>(i, c)];
+                }
             }
             __syncthreads();
             continue;
         }
 
         // ---- trace terms: sum_j M[(j+off) ^ mask, j] (N_Qubit_Decomposition_Cost_Function.cpp:137-160,191-404) ----
-        {
+        if (MODE != MODE_BWD) {
             double t[6] = {0, 0, 0, 0, 0, 0};
             const int off = A.trace_offset;
             if (tid < valid) {
@@ -880,7 +913,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
             }
         }
 
-        if (MODE == MODE_GRAD) {
+        if (HAS_B) {
+          if (MODE == MODE_GRAD) {
             // ---- beta_N = sum_t omega_t * sum_{masks of type t} e_{(j+off)^mask} per column ---------------------
             for (int e = tid; e < rows * CT; e += nthr) sb[e] = czero();
             if (A.n_ops > 0 && tid < KM_ELEMS) skm[((A.n_ops - 1) & 1) * KM_ELEMS + tid] = kernel_elem(A.n_ops - 1);
@@ -911,6 +945,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                 }
             }
             __syncthreads();
+          }
 
             // ---- backward sweep ---------------------------------------------------------------------------------
             int buf = 0;
@@ -1051,10 +1086,22 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                 }
             }
             __syncthreads();
+            if (MODE == MODE_BWD) {
+                const size_t colbase = (size_t)y * A.out_ystride + deposit_bits((unsigned)j0, ~A.wmask);
+                cplx* __restrict__ da = A.out + colbase;
+                cplx* __restrict__ db = A.beta + colbase;
+                for (int e = tid; e < rows * CT; e += nthr) {
+                    const int i = e >> LOG_CT, c = e & (CT - 1);
+                    const size_t off = (size_t)srowpart[i] | deposit_bits((unsigned)c, ~A.wmask);
+                    da[off] = sa[elem<LOG_CT>(i, c)];
+                    db[off] = sb[elem<LOG_CT>(i, c)];
+                }
+                __syncthreads();
+            }
         }
     }
 
-    if (MODE != MODE_APPLY) {
+    if (MODE == MODE_COST || MODE == MODE_GRAD) {
         if (tid == 0) {
             double* dst = A.tr_part + ((size_t)y * nchunks + chunk) * 6;
             for (int i = 0; i < 6; ++i) dst[i] = tsum[i];

@@ -75,4 +75,16 @@ __host__ __device__ __forceinline__ int insert_zero(int idx, int t) {
     return ((idx >> t) << (t + 1)) | (idx & ((1 << t) - 1));
 }
 
+// software PDEP: the bits of v, lowest first, placed on the set bits of mask, lowest first
+__host__ __device__ __forceinline__ unsigned deposit_bits(unsigned v, unsigned mask) {
+    unsigned out = 0;
+    while (mask && v) {
+        const unsigned low = mask & (0u - mask);
+        if (v & 1u) out |= low;
+        v >>= 1;
+        mask ^= low;
+    }
+    return out;
+}
+
 }  // namespace sq

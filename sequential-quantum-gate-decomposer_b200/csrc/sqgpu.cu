@@ -129,6 +129,12 @@ struct sqgpu_ctx {
 
     // circuit
     Plan plan2, plan3;
+    // windowed state-vector executor (VQE): plan3's ops reordered into segments whose joint support fits `win_w` qubits,
+    // qubit indices rewritten to positions inside the segment's window
+    Plan planW;
+    struct Segment { int begin, end; unsigned wmask; };
+    std::vector<Segment> segs;
+    int win_w = 0;
     Plan* P = &plan2;                // plan the helpers below operate on (set by the entry point, under the mutex)
     DevBuf dPool;
     int n_params = 0, qbit_num = 0, n_gates = 0;
@@ -282,6 +288,91 @@ int popcount32(unsigned v) {
     return c;
 }
 
+// Windowed plan for state vectors: the ops of plan3 are scheduled into SEGMENTS whose joint support fits
+// win_w qubits. Inside a segment the executor keeps a 2^win_w x CT tile of the state in shared memory -- rows = the window
+// qubits, columns = values of the other bits -- and runs all of the segment's ops on it, so the state makes one HBM round
+// trip per segment instead of one per gate (the reference streams it once per gate,
+// apply_kernel_to_state_vector_input.cpp:33-229). Ops on disjoint qubits commute: an op may be pulled forward when no
+// earlier unscheduled op shares a qubit with it. Qubit indices are rewritten to positions inside the window.
+int build_window_plan(sqgpu_ctx* c) {
+    const Plan& src = c->plan3;
+    Plan& dst = c->planW;
+    const int N = (int)src.ops.size(), n = c->qbit_num;
+    const char* we = getenv("SQGPU_WINDOW");
+    const int w = std::max(1, std::min(n, we ? atoi(we) : 10));
+    c->win_w = w;
+    c->segs.clear();
+    std::vector<unsigned> sup(N);
+    for (int k = 0; k < N; ++k) sup[k] = support_mask(src.ops[k]);
+    std::vector<char> done(N, 0);
+    std::vector<int> order, newidx(N, -1);
+    int remaining = N, first = 0;
+    while (remaining > 0) {
+        sqgpu_ctx::Segment sg;
+        sg.begin = (int)order.size();
+        unsigned S = 0, blocked = 0;
+        for (int k = first; k < N; ++k) {
+            if (done[k]) continue;
+            if ((sup[k] & blocked) == 0 && popcount32(S | sup[k]) <= w) {
+                done[k] = 1;
+                newidx[k] = (int)order.size();
+                order.push_back(k);
+                S |= sup[k];
+                --remaining;
+            } else {
+                blocked |= sup[k];
+            }
+        }
+        while (first < N && done[first]) ++first;
+        if ((int)order.size() == sg.begin) return fail(SQGPU_ERR_UNSUPPORTED, "window planner made no progress (op support wider than the window)");
+        for (int q = n - 1; q >= 0 && popcount32(S) < w; --q) S |= 1u << q;  // pad the window with the highest free qubits
+        sg.end = (int)order.size();
+        sg.wmask = S;
+        c->segs.push_back(sg);
+    }
+    dst.ops.clear();
+    for (const auto& sg : c->segs)
+        for (int i = sg.begin; i < sg.end; ++i) {
+            DevOp op = src.ops[order[i]];
+            auto loc = [&](int q) { return popcount32(sg.wmask & ((1u << q) - 1u)); };
+            if (op.dim == 2) op.target = loc(op.target);
+            else {
+                const bool hi_first = op.target == op.q[1];
+                for (int j = 0; j < op.nq; ++j) op.q[j] = loc(op.q[j]);
+                op.target = hi_first ? op.q[1] : op.q[0];
+            }
+            unsigned cm = 0;
+            for (int q = 0; q < 30; ++q)
+                if ((op.ctrl_mask >> q) & 1) cm |= 1u << loc(q);
+            op.ctrl_mask = cm;
+            fill_fix(op);
+            dst.ops.push_back(op);
+        }
+    dst.members = src.members;
+    dst.param_slot = src.param_slot;
+    dst.param_op = src.param_op;
+    for (auto& po : dst.param_op)
+        if (po >= 0) po = newidx[po];
+    dst.n_ops = N;
+    dst.kern_total = src.kern_total;
+    dst.dkern_total = src.dkern_total;
+    dst.w_total = src.w_total;
+    dst.wmax = src.wmax;
+    dst.dense_stage = src.dense_stage;
+    int rc;
+    const size_t np1 = std::max<size_t>(dst.param_op.size(), 1);
+    if ((rc = dst.dOps.ensure(std::max<size_t>(1, dst.ops.size()) * sizeof(DevOp)))) return rc;
+    if ((rc = dst.dMembers.ensure(std::max<size_t>(1, dst.members.size()) * sizeof(DevMember)))) return rc;
+    if ((rc = dst.dParamOp.ensure(2 * np1 * sizeof(int)))) return rc;
+    if (!dst.ops.empty()) CUDA_TRY(cudaMemcpy(dst.dOps.p, dst.ops.data(), dst.ops.size() * sizeof(DevOp), cudaMemcpyHostToDevice));
+    if (!dst.members.empty()) CUDA_TRY(cudaMemcpy(dst.dMembers.p, dst.members.data(), dst.members.size() * sizeof(DevMember), cudaMemcpyHostToDevice));
+    if (!dst.param_op.empty()) {
+        CUDA_TRY(cudaMemcpy(dst.dParamOp.p, dst.param_op.data(), dst.param_op.size() * sizeof(int), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(dst.dParamOp.as<int>() + np1, dst.param_slot.data(), dst.param_slot.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    return SQGPU_OK;
+}
+
 // Lower one descriptor to a DevOp (offsets are assigned by the caller). Returns 0 or a status.
 int lower_gate(const sqgpu_gate_desc& g, int qbit_num, const double* pool, int64_t pool_len, DevOp* out, bool* unitary) {
     DevOp op;
@@ -394,17 +485,19 @@ struct FusedPlan {
 };
 
 size_t fused_smem(int mode, int rows, int ct, int threads, int dense_stage, int wmax, int w_total, bool w_in_smem, int n_ops) {
-    size_t s = (size_t)rows * ct * sizeof(cplx) * (mode == MODE_GRAD ? 2 : 1);
+    const bool has_b = mode == MODE_GRAD || mode == MODE_BWD;
+    size_t s = (size_t)rows * ct * sizeof(cplx) * (has_b ? 2 : 1);
     s += (size_t)dense_stage * sizeof(cplx);
     s += 2 * KM_ELEMS * sizeof(cplx);        // prefetched block kernels
     s += 2 * sizeof(OpTab);                  // DMMA block lookup tables (double-buffered)
     s += (size_t)n_ops * sizeof(SOp);        // staged op table
     const int nwarps = threads / 32;
-    if (mode == MODE_GRAD) {
+    if (has_b) {
         s += (size_t)2 * nwarps * wmax * sizeof(cplx);
         if (w_in_smem) s += (size_t)w_total * sizeof(cplx);
     }
     s += (size_t)nwarps * 6 * sizeof(double);
+    s += (size_t)rows * sizeof(int);         // window mode: deposit(r, wmask) per row
     return s;
 }
 
@@ -412,12 +505,12 @@ FusedPlan plan_fused(const sqgpu_ctx* c, int mode, int rows, int cols, int ysets
     FusedPlan p;
     {   // test hook: SQGPU_FORCE_STREAM=1 sends cost / gradient evaluations down the chunked streaming executor
         const char* fs = getenv("SQGPU_FORCE_STREAM");
-        if (fs && fs[0] == '1' && mode != MODE_APPLY) return p;
+        if (fs && fs[0] == '1' && (mode == MODE_COST || mode == MODE_GRAD)) return p;
     }
     const size_t budget = (size_t)c->smem_optin;
     int max_log = 3;
     while ((1 << max_log) > cols && max_log > 0) --max_log;  // no wider than the matrix (cols = 1: state vector)
-    const bool grad = mode == MODE_GRAD;
+    const bool grad = mode == MODE_GRAD || mode == MODE_BWD;
     auto threads_for = [&](int ct) {
         const int items = (rows / 4) * ct;  // groups of a two-qubit block
         return std::min(FUSED_THREADS, std::max(64, (items + 31) / 32 * 32));  // >= 64: the 8 x 8 block kernel prefetch
@@ -428,7 +521,7 @@ FusedPlan plan_fused(const sqgpu_ctx* c, int mode, int rows, int cols, int ysets
     bool pick_wsm = false;
     for (int lc = max_log; lc >= 0 && pick < 0; --lc) {
         const int ct = 1 << lc;
-        const bool can_wsm = grad && c->P->w_total > 0;
+        const bool can_wsm = mode == MODE_GRAD && c->P->w_total > 0;  // MODE_BWD accumulates over several launches: global
         if (can_wsm && fused_smem(mode, rows, ct, threads_for(ct), c->P->dense_stage, c->P->wmax, c->P->w_total, true, c->P->n_ops) <= budget) {
             pick = lc;
             pick_wsm = true;
@@ -984,7 +1077,7 @@ int sqgpu_destroy(sqgpu_handle_t c) {
         DeviceGuard guard(c->device);
         std::lock_guard<std::mutex> lk(c->mtx);
         cudaStreamSynchronize(c->stream);
-        DevBuf* bufs[] = {&c->U, &c->plan2.dOps, &c->plan2.dMembers, &c->plan2.dParamOp, &c->plan2.wKtab, &c->plan2.wDKtab, &c->plan2.wOpTab, &c->plan3.dOps, &c->plan3.dMembers, &c->plan3.dParamOp, &c->plan3.wKtab, &c->plan3.wDKtab, &c->plan3.wOpTab, &c->dPool, &c->wParams, &c->wTrPart, &c->wWPart,
+        DevBuf* bufs[] = {&c->U, &c->plan2.dOps, &c->plan2.dMembers, &c->plan2.dParamOp, &c->plan2.wKtab, &c->plan2.wDKtab, &c->plan2.wOpTab, &c->plan3.dOps, &c->plan3.dMembers, &c->plan3.dParamOp, &c->plan3.wKtab, &c->plan3.wDKtab, &c->plan3.wOpTab, &c->planW.dOps, &c->planW.dMembers, &c->planW.dParamOp, &c->planW.wKtab, &c->planW.wDKtab, &c->planW.wOpTab, &c->dPool, &c->wParams, &c->wTrPart, &c->wWPart,
                           &c->wTraces, &c->wOmega, &c->wCost, &c->wGrad, &c->wMat, &c->wDerivIdx, &c->wTraces0,
                           &c->hIndptr, &c->hIndices, &c->hValues};
         for (DevBuf* b : bufs) b->release();
@@ -1181,6 +1274,8 @@ int sqgpu_set_circuit(sqgpu_handle_t c, const sqgpu_gate_desc* gates, int n_gate
     const char* mq = getenv("SQGPU_MAX_FUSE_QUBITS");
     const int max_q3 = (mq && mq[0] == '2') ? 2 : 3;
     if ((rc = build_plan(max_q3, c->plan3))) return rc;
+    c->qbit_num = qbit_num;
+    if ((rc = build_window_plan(c))) return rc;
     c->P = &c->plan2;
     c->n_gates = n_gates;
     c->n_params = n_params;

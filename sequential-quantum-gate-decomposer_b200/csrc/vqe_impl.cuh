@@ -3,6 +3,92 @@
 // optimization_problem_combined_non_static (:1131-1199), batched over parameter sets.
 #pragma once
 
+// Windowed executor: the state makes one HBM round trip per SEGMENT (build_window_plan) instead of one per gate. Forward:
+// fused_exec<MODE_APPLY> per segment, in place; energy as in the streaming path; gradient: fused_exec<MODE_BWD> per segment
+// in reverse order on (psi, lambda), W' partials per (parameter set, CTA) reduced by reduce_partials.
+// Returns 1 when the shared-memory plan does not fit (caller falls back to the streaming path).
+static int vqe_window_dev(sqgpu_ctx* c, const double* d_params, int batch, bool with_grad, double* d_energy, double* d_grad, cudaStream_t st) {
+    c->P = &c->planW;
+    const int rows = c->rows, w = c->win_w, wr = 1 << w, wc = rows >> w;
+    int rc;
+    const int slice = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::min(batch, 65535), ((size_t)1 << 30) / ((size_t)rows * sizeof(cplx))));
+    const FusedPlan pf = plan_fused(c, MODE_APPLY, wr, wc, std::min(slice, batch));
+    const FusedPlan pb = with_grad ? plan_fused(c, MODE_BWD, wr, wc, std::min(slice, batch)) : pf;
+    if (!pf.ok || !pb.ok) return 1;
+    const int nblk = std::min(c->sm_count * 8, std::max(1, rows / 512));
+    if ((rc = c->wMat.ensure((size_t)2 * slice * rows * sizeof(cplx)))) return rc;
+    if ((rc = c->wTrPart.ensure((size_t)slice * std::max(nblk * 32 + 6, pb.chunks * 6) * sizeof(double)))) return rc;
+    if (with_grad) {
+        if ((rc = c->wWPart.ensure(std::max<size_t>(1, (size_t)slice * pb.chunks * c->P->w_total) * sizeof(cplx)))) return rc;
+        if ((rc = c->wTraces.ensure((size_t)slice * (1 + c->n_params) * 6 * sizeof(double)))) return rc;
+    }
+    cplx* psi = c->wMat.as<cplx>();
+    cplx* lam = psi + (size_t)slice * rows;
+    auto seg_args = [&](const FusedPlan& p, const sqgpu_ctx::Segment& sg, ExecArgs& a) {
+        fill_common_args(c, p, a, wr, wc);
+        a.n = w;
+        a.in = psi;
+        a.out = psi;
+        a.in_ystride = a.out_ystride = rows;
+        a.wmask = sg.wmask;
+        a.ops += sg.begin;
+        a.n_ops = sg.end - sg.begin;
+        a.optabs += sg.begin;
+        a.optab_stride = c->P->n_ops;
+    };
+    for (int b0 = 0; b0 < batch; b0 += slice) {
+        const int nb = std::min(slice, batch - b0);
+        const double* dp = d_params + (size_t)b0 * c->n_params;
+        if ((rc = run_tables(c, dp, nb, with_grad, st))) return rc;
+        {
+            dim3 grid(std::min(c->sm_count * 8, std::max(1, rows / 256)), nb);
+            replicate_matrix<<<grid, 256, 0, st>>>(c->U.as<cplx>(), psi, rows);
+            c->launches++;
+        }
+        if ((rc = run_optabs(c, nb, pf.log_ct, st))) return rc;
+        time_begin(c, "fused_exec<WINDOW_FWD>", st);
+        for (const auto& sg : c->segs) {
+            ExecArgs a;
+            seg_args(pf, sg, a);
+            cudaError_t e = launch_fused_mode<MODE_APPLY>(a, pf, nb, st);
+            c->launches++;
+            if (e != cudaSuccess) return fail(SQGPU_ERR_CUDA, "fused_exec launch failed: %s", cudaGetErrorString(e));
+        }
+        time_end(c, st);
+        {   // beta_N = conj(H psi_N); energy = Re <psi|H psi>
+            dim3 grid((unsigned)(((long long)rows * 32 + 255) / 256), nb);
+            csr_matvec_batched<<<grid, 256, 0, st>>>(rows, c->hIndptr.as<int32_t>(), c->hIndices.as<int32_t>(), c->hValues.as<cplx>(), psi, lam, 1);
+            dim3 g2(nblk, nb);
+            expectation_partial<<<g2, 256, 0, st>>>(rows, psi, lam, -1.0, c->wTrPart.as<double>());
+            sum_partials<<<nb, 32, 0, st>>>(c->wTrPart.as<double>(), nblk, 1, 1.0, d_energy + b0, 1);
+            c->launches += 3;
+            CUDA_TRY(cudaGetLastError());
+        }
+        if (!with_grad) continue;
+        if (pb.log_ct != pf.log_ct && (rc = run_optabs(c, nb, pb.log_ct, st))) return rc;
+        if (c->P->w_total > 0) CUDA_TRY(cudaMemsetAsync(c->wWPart.p, 0, (size_t)nb * pb.chunks * c->P->w_total * sizeof(cplx), st));
+        CUDA_TRY(cudaMemsetAsync(c->wTrPart.p, 0, (size_t)nb * pb.chunks * 6 * sizeof(double), st));
+        time_begin(c, "fused_exec<WINDOW_BWD>", st);
+        for (int si = (int)c->segs.size() - 1; si >= 0; --si) {
+            ExecArgs a;
+            seg_args(pb, c->segs[si], a);
+            a.beta = lam;
+            a.w_part = c->wWPart.as<cplx>();
+            cudaError_t e = launch_fused_mode<MODE_BWD>(a, pb, nb, st);
+            c->launches++;
+            if (e != cudaSuccess) return fail(SQGPU_ERR_CUDA, "fused_exec launch failed: %s", cudaGetErrorString(e));
+        }
+        time_end(c, st);
+        reduce_partials<<<nb, 128, 0, st>>>(c->wTrPart.as<double>(), pb.chunks, c->wWPart.as<cplx>(), c->P->w_total, c->P->dOps.as<DevOp>(),
+                                            c->P->dParamOp.as<int>(), c->P->dParamOp.as<int>() + std::max(c->n_params, 1), c->P->wDKtab.as<cplx>(),
+                                            c->P->dkern_total, c->P->wKtab.as<cplx>(), c->P->kern_total, c->n_params, 1, c->wTraces.as<double>());
+        grad_from_traces<<<nb, 128, 0, st>>>(c->wTraces.as<double>(), c->n_params, 2.0, d_grad + (size_t)b0 * c->n_params);
+        c->launches += 2;
+        CUDA_TRY(cudaGetLastError());
+    }
+    return SQGPU_OK;
+}
+
 static int vqe_dev(sqgpu_ctx* c, const double* d_params, int batch, bool with_grad, double* d_energy, double* d_grad, cudaStream_t st) {
     c->P = &c->plan2;
     int rc = check_ready(c, true);
@@ -12,12 +98,20 @@ static int vqe_dev(sqgpu_ctx* c, const double* d_params, int batch, bool with_gr
     if (c->cols != 1) return fail(SQGPU_ERR_INVALID, "the VQE path needs a state vector (cols = 1), the resident matrix has %d columns", c->cols);
     if (!c->hIndptr.p || c->h_rows != c->rows) return fail(SQGPU_ERR_STATE, "no Hamiltonian of matching size set (call sqgpu_set_hamiltonian_csr)");
     if (!d_energy || (with_grad && !d_grad && c->n_params > 0)) return fail(SQGPU_ERR_INVALID, "NULL buffer");
+    if (with_grad && !c->all_unitary) return fail(SQGPU_ERR_UNSUPPORTED, "gradient with a non-unitary GENERAL gate is not supported");
+    {   // windowed shared-memory executor first; SQGPU_VQE_STREAM=1 (test hook) or a plan that does not fit: one op per launch
+        const char* vs = getenv("SQGPU_VQE_STREAM");
+        if (!(vs && vs[0] == '1')) {
+            rc = vqe_window_dev(c, d_params, batch, with_grad, d_energy, d_grad, st);
+            if (rc != 1) return rc;
+            c->P = &c->plan2;
+        }
+    }
     for (int k = 0; k < c->P->n_ops; ++k) {
         const DevOp& op = c->P->ops[k];
         const bool ok = op.dim == 2 || (op.dim == 4 && op.nq == 2 && op.ctrl_mask == 0);
-        if (with_grad && !ok) return fail(SQGPU_ERR_UNSUPPORTED, "VQE gradient with 3+ qubit dense or multi-controlled gates is not implemented");
+        if (with_grad && !ok) return fail(SQGPU_ERR_UNSUPPORTED, "VQE gradient with 3+ qubit dense or multi-controlled gates is not implemented on the streaming path");
     }
-    if (with_grad && !c->all_unitary) return fail(SQGPU_ERR_UNSUPPORTED, "gradient with a non-unitary GENERAL gate is not supported");
     const int rows = c->rows;
     // parameter sets per slice: two state buffers of <= 1 GiB each
     const int slice = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::min(batch, 65535), ((size_t)1 << 30) / ((size_t)rows * sizeof(cplx))));

@@ -212,7 +212,8 @@ def test_crot_and_syc_in_fused_blocks(sq, port, plan_mode):
     P = c.get_Parameter_Num()
     U = H.random_unitary(1 << n)
     p = H.random_params(P, seed=21)
-    out = c.apply_to(p, U)
+    out = U.copy()
+    c.apply_to(p, out)  # in place, like the reference's Circuit.apply_to
     assert np.abs(out - port.apply_circuit(d, p, U, pool=pool)).max() < ENTRY_TOL
     dec = sq.N_Qubit_Decomposition_custom(U)
     dec.set_Gate_Structure(c)
@@ -221,6 +222,28 @@ def test_crot_and_syc_in_fused_blocks(sq, port, plan_mode):
         f, g = dec.Optimization_Problem_Combined(p)
         f_ref, g_ref = port.cost_grad(d, P, p, U, n, variant, pool=pool)
         assert close_rel(f, f_ref) and close_rel(g, g_ref)
+
+
+def test_vqe_window_with_mixed_gates(sq, port, monkeypatch):
+    """the windowed state-vector executor on a circuit with every gate family (controlled, two-target, GENERAL blocks,
+    CCX/CSWAP): segments are formed by pulling commuting ops forward, so this pins the reordering and the qubit remapping"""
+    n = 7
+    monkeypatch.setenv("SQGPU_WINDOW", "4")
+    indptr, indices, data = H.heisenberg_csr(n, degree=2)
+    c = H.random_circuit(n, 80, seed=5, general_k=(2, 3))
+    d, pool = c.descriptors()
+    P = c.get_Parameter_Num()
+    psi0 = H.random_state(1 << n)
+    e = sq.Engine(0)
+    e.upload_matrix(psi0)
+    e.set_circuit(c)
+    e.set_hamiltonian_csr(indptr, indices, data)
+    ps = H.random_params(P, seed=3, batch=2)
+    en, gr = e.vqe_energy_grad_batched(ps)
+    for b in range(2):
+        e_ref, g_ref = port.vqe_energy_grad(d, P, ps[b], psi0, indptr, indices, data, pool=pool)
+        assert close_rel(en[b], e_ref) and close_rel(gr[b], g_ref)
+    e.close()
 
 
 def test_reference_wrapper_flow(sq, port):
@@ -382,8 +405,15 @@ def test_golden_general_blocks(sq):
 
 # ---- VQE state-vector path (Variational_Quantum_Eigensolver_Base::optimization_problem{,_combined}) ----------------
 
+@pytest.mark.parametrize("path", ["window", "window5", "window3", "stream"])
 @pytest.mark.parametrize("n,layers", [(4, 2), (8, 2), (12, 1)])
-def test_vqe_energy_and_gradient(sq, port, n, layers):
+def test_vqe_energy_and_gradient(sq, port, monkeypatch, n, layers, path):
+    """windowed shared-memory executor (default window of 10 qubits: one segment for n <= 10, several for n = 12), forced
+    narrow windows (many segments, 2^(n-w) tile columns) and the one-op-per-launch streaming path"""
+    if path == "stream":
+        monkeypatch.setenv("SQGPU_VQE_STREAM", "1")
+    elif path != "window":
+        monkeypatch.setenv("SQGPU_WINDOW", path[6:])
     indptr, indices, data = H.heisenberg_csr(n)
     c = H.hea_zyz_circuit(n, layers)
     d, pool = c.descriptors()
