@@ -17,11 +17,23 @@ namespace sq {
 // traces layout helpers
 __host__ __device__ __forceinline__ size_t tr_index(int y, int k, int n_k, int t) { return (((size_t)y * n_k + k) * 3 + t) * 2; }
 
+// w_part[y][0][e] <- sum over chunks of w_part[y][chunk][e], chunks in ascending order (fixed summation order): one
+// coalesced pass over the partials instead of one strided gather per parameter in reduce_partials
+__global__ void fold_w_chunks(cplx* __restrict__ w_part, int nchunks, int w_total) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= w_total) return;
+    cplx* base = w_part + (size_t)blockIdx.y * nchunks * w_total + e;
+    cplx acc = base[0];
+    for (int ch = 1; ch < nchunks; ++ch) acc = cadd(acc, base[(size_t)ch * w_total]);
+    base[0] = acc;
+}
+
+// w_folded: the W partials of chunk 0 already hold the sum over chunks (fold_w_chunks)
 __global__ void reduce_partials(const double* __restrict__ tr_part, int nchunks, const cplx* __restrict__ w_part,
                                 int w_total, const DevOp* __restrict__ ops, const int* __restrict__ param_op,
                                 const int* __restrict__ param_slot, const cplx* __restrict__ dktab, int dkern_total,
                                 const cplx* __restrict__ ktab, int kern_total, int n_params, int with_grad,
-                                double* __restrict__ traces) {
+                                double* __restrict__ traces, int w_folded = 0) {
     const int y = blockIdx.x;
     const int n_k = 1 + (with_grad ? n_params : 0);
     if (threadIdx.x < 6) {
@@ -40,7 +52,8 @@ __global__ void reduce_partials(const double* __restrict__ tr_part, int nchunks,
         for (int r = 0; r < dim; ++r)
             for (int r2 = 0; r2 < dim; ++r2) {
                 cplx w = czero();
-                for (int ch = 0; ch < nchunks; ++ch) w = cadd(w, w_part[((size_t)y * nchunks + ch) * w_total + op.w_off + r * dim + r2]);
+                const int wch = w_folded ? 1 : nchunks;
+                for (int ch = 0; ch < wch; ++ch) w = cadd(w, w_part[((size_t)y * nchunks + ch) * w_total + op.w_off + r * dim + r2]);
                 cplx dkk = czero();  // (dK K^dagger)[r][r2] = sum_c dK[r][c] conj(K[r2][c])
                 for (int c = 0; c < dim; ++c) dkk = cfmac(kk[r2 * dim + c], dk[r * dim + c], dkk);
                 acc = cfma(dkk, w, acc);

@@ -543,7 +543,7 @@ FusedPlan plan_fused(const sqgpu_ctx* c, int mode, int rows, int cols, int ysets
             thr /= 2;
             ways *= 2;
         }
-        if (ways > 1 && mode != MODE_APPLY) {
+        if (ways > 1) {
             const size_t sm = fused_smem(mode, rows, 1 << lc, thr, c->P->dense_stage, c->P->wmax, c->P->w_total, false, c->P->n_ops);
             const char* fc = getenv("SQGPU_SPLIT_FORCE");
             if ((fc && fc[0] == '1') || ((sm + 1024) * ways <= (size_t)c->smem_per_sm && thr * ways * 128 <= 65536)) {
@@ -688,9 +688,13 @@ int run_exec_resident(sqgpu_ctx* c, int batch, bool grad, const cplx* d_omega, d
     time_end(c, st);
     c->launches++;
     if (e != cudaSuccess) return fail(SQGPU_ERR_CUDA, "fused_exec launch failed: %s", cudaGetErrorString(e));
+    if (grad && p.chunks > 1 && c->P->w_total > 0) {
+        fold_w_chunks<<<dim3((c->P->w_total + 255) / 256, batch), 256, 0, st>>>(c->wWPart.as<cplx>(), p.chunks, c->P->w_total);
+        c->launches++;
+    }
     reduce_partials<<<batch, 128, 0, st>>>(c->wTrPart.as<double>(), p.chunks, c->wWPart.as<cplx>(), c->P->w_total,
                                            c->P->dOps.as<DevOp>(), c->P->dParamOp.as<int>(), c->P->dParamOp.as<int>() + std::max(c->n_params, 1),
-                                           c->P->wDKtab.as<cplx>(), c->P->dkern_total, c->P->wKtab.as<cplx>(), c->P->kern_total, c->n_params, grad ? 1 : 0, d_traces);
+                                           c->P->wDKtab.as<cplx>(), c->P->dkern_total, c->P->wKtab.as<cplx>(), c->P->kern_total, c->n_params, grad ? 1 : 0, d_traces, 1);
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     return SQGPU_OK;
@@ -992,9 +996,13 @@ int run_exec_streaming(sqgpu_ctx* c, int batch, bool grad, const cplx* d_omega, 
     }
     time_end(c, st);
     CUDA_TRY(cudaGetLastError());
+    if (grad && nchunks > 1 && c->P->w_total > 0) {
+        fold_w_chunks<<<dim3((c->P->w_total + 255) / 256, batch), 256, 0, st>>>(c->wWPart.as<cplx>(), nchunks, c->P->w_total);
+        c->launches++;
+    }
     reduce_partials<<<batch, 128, 0, st>>>(tr_part, nchunks, c->wWPart.as<cplx>(), c->P->w_total, c->P->dOps.as<DevOp>(), c->P->dParamOp.as<int>(),
                                            c->P->dParamOp.as<int>() + std::max(c->n_params, 1), c->P->wDKtab.as<cplx>(), c->P->dkern_total,
-                                           c->P->wKtab.as<cplx>(), c->P->kern_total, c->n_params, grad ? 1 : 0, d_traces);
+                                           c->P->wKtab.as<cplx>(), c->P->kern_total, c->n_params, grad ? 1 : 0, d_traces, 1);
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     return SQGPU_OK;

@@ -79,9 +79,13 @@ static int vqe_window_dev(sqgpu_ctx* c, const double* d_params, int batch, bool 
             if (e != cudaSuccess) return fail(SQGPU_ERR_CUDA, "fused_exec launch failed: %s", cudaGetErrorString(e));
         }
         time_end(c, st);
+        if (pb.chunks > 1 && c->P->w_total > 0) {
+            fold_w_chunks<<<dim3((c->P->w_total + 255) / 256, nb), 256, 0, st>>>(c->wWPart.as<cplx>(), pb.chunks, c->P->w_total);
+            c->launches++;
+        }
         reduce_partials<<<nb, 128, 0, st>>>(c->wTrPart.as<double>(), pb.chunks, c->wWPart.as<cplx>(), c->P->w_total, c->P->dOps.as<DevOp>(),
                                             c->P->dParamOp.as<int>(), c->P->dParamOp.as<int>() + std::max(c->n_params, 1), c->P->wDKtab.as<cplx>(),
-                                            c->P->dkern_total, c->P->wKtab.as<cplx>(), c->P->kern_total, c->n_params, 1, c->wTraces.as<double>());
+                                            c->P->dkern_total, c->P->wKtab.as<cplx>(), c->P->kern_total, c->n_params, 1, c->wTraces.as<double>(), 1);
         grad_from_traces<<<nb, 128, 0, st>>>(c->wTraces.as<double>(), c->n_params, 2.0, d_grad + (size_t)b0 * c->n_params);
         c->launches += 2;
         CUDA_TRY(cudaGetLastError());
