@@ -622,6 +622,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
 
     cplx* sa = reinterpret_cast<cplx*>(smem_raw);
     constexpr bool HAS_B = (MODE == MODE_GRAD || MODE == MODE_BWD);
+    constexpr bool WIN = (MODE == MODE_APPLY || MODE == MODE_BWD);  // window mode is compiled only where it is used
     cplx* sb = sa + (size_t)rows * CT;                                   // the row functional beta (HAS_B only)
     cplx* sk = HAS_B ? sb + (size_t)rows * CT : sb;                       // raw dense kernel staging
     cplx* skm = sk + A.dense_stage;                                       // [2][KM_ELEMS] prefetched block kernels
@@ -659,7 +660,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
     if (HAS_B && A.w_in_smem) {
         for (int e = tid; e < A.w_total; e += nthr) swacc[e] = czero();
     }
-    if (A.wmask) {
+    if (WIN && A.wmask) {
         for (int r = tid; r < rows; r += nthr) srowpart[r] = (int)deposit_bits((unsigned)r, A.wmask);
     }
     double tsum[6] = {0, 0, 0, 0, 0, 0};  // running trace sums of this CTA (thread 0)
@@ -693,15 +694,32 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
 
         // ---- load the tile ------------------------------------------------------------------------------------
         {
-            if (A.wmask) {
+            if (WIN && A.wmask) {
                 // window mode: the tile's columns are CT consecutive values of the non-window bits
                 const size_t colbase = (size_t)y * A.in_ystride + deposit_bits((unsigned)j0, ~A.wmask);
                 const cplx* __restrict__ src = (MODE == MODE_BWD ? A.out : A.in) + colbase;
-                for (int e = tid; e < rows * CT; e += nthr) {
-                    const int i = e >> LOG_CT, c = e & (CT - 1);
-                    const size_t off = (size_t)srowpart[i] | deposit_bits((unsigned)c, ~A.wmask);
-                    sa[elem<LOG_CT>(i, c)] = src[off];
-                    if (MODE == MODE_BWD) sb[elem<LOG_CT>(i, c)] = (A.beta + colbase)[off];
+                const cplx* __restrict__ srcb = (MODE == MODE_BWD) ? A.beta + colbase : nullptr;
+                // 8 independent 16 B loads in flight per thread (the state comes from HBM / L2: latency-bound otherwise)
+                constexpr int UL = (MODE == MODE_BWD) ? 4 : 8;
+                for (int e0 = tid; e0 < rows * CT; e0 += nthr * UL) {
+                    cplx va[UL], vb[UL];
+#pragma unroll
+                    for (int u = 0; u < UL; ++u) {
+                        const int e = e0 + u * nthr;
+                        if (e < rows * CT) {
+                            const size_t off = (size_t)srowpart[e >> LOG_CT] | deposit_bits((unsigned)(e & (CT - 1)), ~A.wmask);
+                            va[u] = src[off];
+                            if (MODE == MODE_BWD) vb[u] = srcb[off];
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < UL; ++u) {
+                        const int e = e0 + u * nthr;
+                        if (e < rows * CT) {
+                            sa[elem<LOG_CT>(e >> LOG_CT, e & (CT - 1))] = va[u];
+                            if (MODE == MODE_BWD) sb[elem<LOG_CT>(e >> LOG_CT, e & (CT - 1))] = vb[u];
+                        }
+                    }
                 }
             } else {
                 const cplx* __restrict__ src = A.in + (size_t)y * A.in_ystride + j0;
@@ -851,7 +869,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
         }
 
         if (MODE == MODE_APPLY) {
-            if (A.wmask) {
+            if (WIN && A.wmask) {
                 cplx* __restrict__ dst = A.out + (size_t)y * A.out_ystride + deposit_bits((unsigned)j0, ~A.wmask);
                 for (int e = tid; e < rows * CT; e += nthr) {
                     const int i = e >> LOG_CT, c = e & (CT - 1);

@@ -14,21 +14,51 @@
 
 namespace sq {
 
-// y[b][r] = sum_e values[e] * x[b][indices[e]]; one warp per row, lanes over the row's non-zeros
-__global__ void csr_matvec_batched(int n_rows, const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+// y[b][r] = sum_e values[e] * x[b][indices[e]]. G lanes share a row (G = 8 for short rows: a 20-qubit Heisenberg row holds
+// 16 non-zeros on average, a whole warp per row would idle half its lanes), and every group applies the row to YB parameter
+// sets at once so that indices / values are read once per YB states.
+template <int G, int YB>
+__global__ void csr_matvec_batched(int n_rows, int n_sets, const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                                    const cplx* __restrict__ values, const cplx* __restrict__ x, cplx* __restrict__ yv,
                                    int conj_out) {
-    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (row >= n_rows) return;
-    const cplx* __restrict__ xb = x + (size_t)blockIdx.y * n_rows;
-    cplx acc = czero();
-    for (int e = indptr[row] + lane; e < indptr[row + 1]; e += 32) acc = cfma(values[e], xb[indices[e]], acc);
-    for (int s = 16; s > 0; s >>= 1) {
-        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, s);
-        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, s);
+    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int lane = threadIdx.x & (G - 1);
+    if (row >= n_rows) return;  // whole groups leave together (blockDim.x is a multiple of G, shuffles below are per group)
+    const int y0 = blockIdx.y * YB;
+    cplx acc[YB];
+#pragma unroll
+    for (int b = 0; b < YB; ++b) acc[b] = czero();
+    const int e1 = indptr[row + 1];
+    for (int e = indptr[row] + lane; e < e1; e += G) {
+        const cplx v = values[e];
+        const size_t col = (size_t)indices[e];
+#pragma unroll
+        for (int b = 0; b < YB; ++b)
+            if (y0 + b < n_sets) acc[b] = cfma(v, x[(size_t)(y0 + b) * n_rows + col], acc[b]);
     }
-    if (lane == 0) yv[(size_t)blockIdx.y * n_rows + row] = conj_out ? cmake(acc.x, -acc.y) : acc;
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
+#pragma unroll
+    for (int b = 0; b < YB; ++b) {
+        for (int s = G / 2; s > 0; s >>= 1) {
+            acc[b].x += __shfl_xor_sync(gmask, acc[b].x, s);
+            acc[b].y += __shfl_xor_sync(gmask, acc[b].y, s);
+        }
+        if (lane == 0 && y0 + b < n_sets) yv[(size_t)(y0 + b) * n_rows + row] = conj_out ? cmake(acc[b].x, -acc[b].y) : acc[b];
+    }
+}
+
+// host launcher: group width from the average row length
+inline void launch_csr_matvec(int n_rows, long long nnz, int n_sets, const int32_t* indptr, const int32_t* indices, const cplx* values,
+                              const cplx* x, cplx* yv, int conj_out, cudaStream_t st) {
+    constexpr int YB = 4;
+    const long long avg = n_rows > 0 ? nnz / n_rows : 0;
+    if (avg <= 24) {
+        dim3 grid((unsigned)(((long long)n_rows * 8 + 255) / 256), (n_sets + YB - 1) / YB);
+        csr_matvec_batched<8, YB><<<grid, 256, 0, st>>>(n_rows, n_sets, indptr, indices, values, x, yv, conj_out);
+    } else {
+        dim3 grid((unsigned)(((long long)n_rows * 32 + 255) / 256), (n_sets + YB - 1) / YB);
+        csr_matvec_batched<32, YB><<<grid, 256, 0, st>>>(n_rows, n_sets, indptr, indices, values, x, yv, conj_out);
+    }
 }
 
 // part[b][blockIdx.x] = sum_i Re(conj(left_i) * right_i)  (right may be stored conjugated: sign_im = -1)

@@ -56,8 +56,7 @@ static int vqe_window_dev(sqgpu_ctx* c, const double* d_params, int batch, bool 
         }
         time_end(c, st);
         {   // beta_N = conj(H psi_N); energy = Re <psi|H psi>
-            dim3 grid((unsigned)(((long long)rows * 32 + 255) / 256), nb);
-            csr_matvec_batched<<<grid, 256, 0, st>>>(rows, c->hIndptr.as<int32_t>(), c->hIndices.as<int32_t>(), c->hValues.as<cplx>(), psi, lam, 1);
+            launch_csr_matvec(rows, c->h_nnz, nb, c->hIndptr.as<int32_t>(), c->hIndices.as<int32_t>(), c->hValues.as<cplx>(), psi, lam, 1, st);
             dim3 g2(nblk, nb);
             expectation_partial<<<g2, 256, 0, st>>>(rows, psi, lam, -1.0, c->wTrPart.as<double>());
             sum_partials<<<nb, 32, 0, st>>>(c->wTrPart.as<double>(), nblk, 1, 1.0, d_energy + b0, 1);
@@ -146,8 +145,7 @@ static int vqe_dev(sqgpu_ctx* c, const double* d_params, int batch, bool with_gr
         }
         time_end(c, st);
         {   // beta_N = conj(H psi_N); energy = Re <psi|H psi>
-            dim3 grid((unsigned)(((long long)rows * 32 + 255) / 256), nb);
-            csr_matvec_batched<<<grid, 256, 0, st>>>(rows, c->hIndptr.as<int32_t>(), c->hIndices.as<int32_t>(), c->hValues.as<cplx>(), psi, lam, 1);
+            launch_csr_matvec(rows, c->h_nnz, nb, c->hIndptr.as<int32_t>(), c->hIndices.as<int32_t>(), c->hValues.as<cplx>(), psi, lam, 1, st);
             dim3 g2(nblk, nb);
             expectation_partial<<<g2, 256, 0, st>>>(rows, psi, lam, -1.0, c->wTrPart.as<double>());
             sum_partials<<<nb, 32, 0, st>>>(c->wTrPart.as<double>(), nblk, 1, 1.0, d_energy + b0, 1);
