@@ -36,6 +36,7 @@ namespace sq {
 enum { MODE_COST = 0, MODE_GRAD = 1, MODE_APPLY = 2, MODE_BWD = 3 };
 
 struct OpTab;
+struct DenseTab;
 
 struct ExecArgs {
     const cplx* in;          // input matrix (row-major, leading dimension ld_in)
@@ -58,6 +59,7 @@ struct ExecArgs {
     unsigned wmask;          // window mode (state vectors): bit mask of the `n_win` qubits that form the tile's rows; element
                              // (row r, column j) of y lives at in[y * ystride + deposit(r, wmask) | deposit(j, ~wmask)]; 0: matrix
     cplx* beta;              // MODE_BWD: the row functional, same layout and stride as out
+    const struct DenseTab* dense_tabs;  // fragment tables of the raw dense 3-/4-qubit ops (build_dense_tabs), NULL: none
     int k_shared;            // 1: every blockIdx.y uses kernel-table set 0 (materialised derivative: one parameter set)
     const int* deriv_op;     // MODE_APPLY: per blockIdx.y the op whose derivative kernel is applied (NULL: none)
     const int* deriv_slot;   //             and which of its derivative kernels
@@ -496,21 +498,24 @@ __device__ __forceinline__ void block_dmma_backward(cplx* sa, cplx* sb, const Op
 }
 
 // Raw dense 3-/4-qubit kernels (GENERAL blocks; no controls) in the same formulation as the fused blocks: data = A operand,
-// 128-bit per-lane loads / stores of the same elements, kernel fragments (NT x KS doubles per lane) in registers. The
-// fragment table is built in shared memory by the CTA (skf: [NT * KS][32] doubles, schoice: 2 ints), the two block-qubit
-// positions that index the lane's amplitude slot are picked for the fewest bank conflicts.
+// 128-bit per-lane loads / stores of the same elements, kernel fragments (NT x KS doubles per lane) in registers. Their
+// kernels are constants of the circuit, so the lane-ordered fragment table is built once per (circuit, tile width) by
+// build_dense_tabs and read straight from global memory / L2 at the start of the op (32 coalesced 256 B loads per warp);
+// the two block-qubit positions that index the lane's amplitude slot are picked for the fewest bank conflicts.
+struct DenseTab {
+    double frag[1024];  // [t * KS + ks][lane], NT * KS <= 32
+    int sl[4][32];      // [u][lane]: load/store slot (complex units) of amplitude dep(lane & 3, u) of item lane >> 2
+};
+
 template <int LOG_CT, int KQ>
-__device__ __forceinline__ void dense_dmma_forward2(cplx* sa, double* skf, int* schoice, const cplx* __restrict__ K, const DevOp& op,
-                                                    int rows, int tid, int nthr) {
+__device__ __forceinline__ void dense_tab_fill(DenseTab* T, int* schoice, const cplx* __restrict__ K, const DevOp& op, int tid, int nthr) {
     constexpr int CT = 1 << LOG_CT, LOGG = 3 - LOG_CT, DIM = 1 << KQ, NT = DIM / 4, KS = 2 * NT;
-    const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
-    int q[KQ], Pq[KQ], F[3];
+    int Pq[KQ], F[3];
     unsigned qmask = 0;
 #pragma unroll
     for (int j = 0; j < KQ; ++j) {
-        q[j] = op.q[j];
-        Pq[j] = elem<LOG_CT>(1 << q[j], 0);
-        qmask |= 1u << q[j];
+        Pq[j] = elem<LOG_CT>(1 << op.q[j], 0);
+        qmask |= 1u << op.q[j];
     }
     {
         int f = 0;
@@ -562,17 +567,36 @@ __device__ __forceinline__ void dense_dmma_forward2(cplx* sa, double* skf, int* 
     const int ja = schoice[0], jb = schoice[1];
     for (int e = tid; e < NT * KS * 32; e += nthr) {
         const int ts = e >> 5, l = e & 31, t = ts / KS, ks = ts - t * KS, n = l >> 2, k = l & 3;
-        skf[e] = kreal_entry(K, DIM, 0, dep(n >> 1, t, ja, jb), n & 1, dep(k, ks >> 1, ja, jb), ks & 1);
+        T->frag[e] = kreal_entry(K, DIM, 0, dep(n >> 1, t, ja, jb), n & 1, dep(k, ks >> 1, ja, jb), ks & 1);
     }
-    __syncthreads();
+    for (int e = tid; e < NT * 32; e += nthr) T->sl[e >> 5][e & 31] = slot((e & 31) >> 2, dep(e & 3, e >> 5, ja, jb));
+}
+
+template <int LOG_CT>
+__global__ void build_dense_tabs(const DevOp* __restrict__ ops, int n_ops, const cplx* __restrict__ pool, DenseTab* __restrict__ tabs) {
+    __shared__ int schoice[2];
+    const DevOp op = ops[blockIdx.x];
+    if (op.dtab <= 0) return;
+    DenseTab* T = tabs + (op.dtab - 1);
+    if (op.nq == 3) dense_tab_fill<LOG_CT, 3>(T, schoice, pool + op.pool_off, op, threadIdx.x, blockDim.x);
+    else dense_tab_fill<LOG_CT, 4>(T, schoice, pool + op.pool_off, op, threadIdx.x, blockDim.x);
+}
+
+template <int LOG_CT, int KQ>
+__device__ __forceinline__ void dense_dmma_forward2(cplx* sa, const DenseTab* __restrict__ T, const DevOp& op, int rows, int tid, int nthr) {
+    constexpr int DIM = 1 << KQ, NT = DIM / 4, KS = 2 * NT;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
     double kf[NT][KS];
     int sl[NT];
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
-        sl[t] = slot(lane >> 2, dep(lane & 3, t, ja, jb));
+        sl[t] = T->sl[t][lane];
 #pragma unroll
-        for (int ks = 0; ks < KS; ++ks) kf[t][ks] = skf[(t * KS + ks) * 32 + lane];
+        for (int ks = 0; ks < KS; ++ks) kf[t][ks] = T->frag[(t * KS + ks) * 32 + lane];
     }
+    int q[KQ];
+#pragma unroll
+    for (int j = 0; j < KQ; ++j) q[j] = op.q[j];
     const int nitems = (rows >> KQ) << LOG_CT;
     for (int b0 = warp * 8; b0 < nitems; b0 += nwarps * 8) {
         int base = b0 >> LOG_CT;
@@ -813,11 +837,17 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                     const int nitems = (rows >> nq) << LOG_CT;
                     const bool use_dmma = !deriv && op.ctrl_mask == 0 && nq >= 3 && (nitems & 7) == 0;
                     if (use_dmma && nq <= 4) {
-                        // fragment table in the staging area: [NT * KS][32] doubles (8 KB for 4 qubits) + 2 ints
-                        double* skf = reinterpret_cast<double*>(sk);
-                        int* schoice = reinterpret_cast<int*>(skf + 4 * dim * dim);
-                        if (nq == 3) dense_dmma_forward2<LOG_CT, 3>(sa, skf, schoice, K, op, rows, tid, nthr);
-                        else dense_dmma_forward2<LOG_CT, 4>(sa, skf, schoice, K, op, rows, tid, nthr);
+                        const DenseTab* T = (A.dense_tabs && op.dtab > 0) ? A.dense_tabs + (op.dtab - 1) : nullptr;
+                        if (!T) {  // no precomputed table (parametric dense op): build it in the staging area
+                            DenseTab* Ts = reinterpret_cast<DenseTab*>(sk);
+                            int* schoice = reinterpret_cast<int*>(Ts + 1);
+                            if (nq == 3) dense_tab_fill<LOG_CT, 3>(Ts, schoice, K, op, tid, nthr);
+                            else dense_tab_fill<LOG_CT, 4>(Ts, schoice, K, op, tid, nthr);
+                            __syncthreads();
+                            T = Ts;
+                        }
+                        if (nq == 3) dense_dmma_forward2<LOG_CT, 3>(sa, T, op, rows, tid, nthr);
+                        else dense_dmma_forward2<LOG_CT, 4>(sa, T, op, rows, tid, nthr);
                     } else if (use_dmma) {
                         // 5 qubits: stage the real embedding of K (padded rows) and the local-index -> row-bit pattern
                         const int dimr = 2 * dim, ld = dimr + DMMA_PAD;

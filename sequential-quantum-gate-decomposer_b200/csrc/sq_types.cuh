@@ -51,7 +51,7 @@ struct DevOp {
     int32_t n_members;
     int32_t nfix;         // number of fixed row-index bits when enumerating the op's groups (targets + controls)
     int32_t fix[6];       // those bit positions, ascending; unused entries = 30 (insert_zero(.,30) is the identity)
-    int32_t pad;
+    int32_t dtab;         // raw dense 3-/4-qubit ops with a constant kernel: 1 + index of the op's DMMA fragment table, else 0
     int64_t pool_off;     // constant kernel offset (complex) in the pool
 };
 

@@ -111,6 +111,8 @@ struct Plan {
     std::vector<int> param_slot;     // parameter -> index of its derivative kernel inside that op
     DevBuf dOps, dMembers, dParamOp;
     DevBuf wKtab, wDKtab, wOpTab;    // per-parameter-set kernel tables and DMMA block lookup tables (workspace)
+    DevBuf wDenseTab;                // fragment tables of the raw dense 3-/4-qubit ops (constant kernels): per tile width
+    int n_dense = 0, dense_logct = -1;
     int n_ops = 0, kern_total = 0, dkern_total = 0, w_total = 0, wmax = 4;
     int dense_stage = 0;             // complex elements of kernel staging the executor's generic dense path needs
 };
@@ -359,6 +361,8 @@ int build_window_plan(sqgpu_ctx* c) {
     dst.w_total = src.w_total;
     dst.wmax = src.wmax;
     dst.dense_stage = src.dense_stage;
+    dst.n_dense = src.n_dense;
+    dst.dense_logct = -1;
     int rc;
     const size_t np1 = std::max<size_t>(dst.param_op.size(), 1);
     if ((rc = dst.dOps.ensure(std::max<size_t>(1, dst.ops.size()) * sizeof(DevOp)))) return rc;
@@ -510,7 +514,6 @@ FusedPlan plan_fused(const sqgpu_ctx* c, int mode, int rows, int cols, int ysets
     const size_t budget = (size_t)c->smem_optin;
     int max_log = 3;
     while ((1 << max_log) > cols && max_log > 0) --max_log;  // no wider than the matrix (cols = 1: state vector)
-    const bool grad = mode == MODE_GRAD || mode == MODE_BWD;
     auto threads_for = [&](int ct) {
         const int items = (rows / 4) * ct;  // groups of a two-qubit block
         return std::min(FUSED_THREADS, std::max(64, (items + 31) / 32 * 32));  // >= 64: the 8 x 8 block kernel prefetch
@@ -623,6 +626,27 @@ int run_optabs(sqgpu_ctx* c, int ysets, int log_ct, cudaStream_t st) {
     return SQGPU_OK;
 }
 
+// fragment tables of the raw dense 3-/4-qubit ops: constants of (circuit, tile width), rebuilt only when the width changes
+int run_dense_tabs(sqgpu_ctx* c, int log_ct, cudaStream_t st) {
+    Plan* P = c->P;
+    if (P->n_dense == 0 || P->dense_logct == log_ct) return SQGPU_OK;
+    int rc;
+    if ((rc = P->wDenseTab.ensure((size_t)P->n_dense * sizeof(DenseTab)))) return rc;
+    const DevOp* ops = P->dOps.as<DevOp>();
+    const cplx* pool = c->dPool.as<cplx>();
+    DenseTab* tabs = P->wDenseTab.as<DenseTab>();
+    switch (log_ct) {
+        case 0: build_dense_tabs<0><<<P->n_ops, 128, 0, st>>>(ops, P->n_ops, pool, tabs); break;
+        case 1: build_dense_tabs<1><<<P->n_ops, 128, 0, st>>>(ops, P->n_ops, pool, tabs); break;
+        case 2: build_dense_tabs<2><<<P->n_ops, 128, 0, st>>>(ops, P->n_ops, pool, tabs); break;
+        default: build_dense_tabs<3><<<P->n_ops, 128, 0, st>>>(ops, P->n_ops, pool, tabs); break;
+    }
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    P->dense_logct = log_ct;
+    return SQGPU_OK;
+}
+
 void fill_common_args(const sqgpu_ctx* c, const FusedPlan& p, ExecArgs& a, int rows, int cols) {
     memset(&a, 0, sizeof(a));
     a.rows = rows;
@@ -640,6 +664,7 @@ void fill_common_args(const sqgpu_ctx* c, const FusedPlan& p, ExecArgs& a, int r
     a.dkern_total = c->P->dkern_total;
     a.pool = c->dPool.as<cplx>();
     a.optabs = c->P->wOpTab.as<OpTab>();
+    a.dense_tabs = (c->P->n_dense > 0 && c->P->dense_logct == p.log_ct) ? c->P->wDenseTab.as<DenseTab>() : nullptr;
     a.dense_stage = c->P->dense_stage;
     a.wmax = c->P->wmax;
     a.w_total = c->P->w_total;
@@ -669,6 +694,7 @@ int run_exec_resident(sqgpu_ctx* c, int batch, bool grad, const cplx* d_omega, d
     if (!p.ok) return run_exec_streaming(c, batch, grad, d_omega, d_traces, st);  // column too tall for shared memory
     int rc;
     if ((rc = run_optabs(c, batch, p.log_ct, st))) return rc;
+    if ((rc = run_dense_tabs(c, p.log_ct, st))) return rc;
     if ((rc = c->wTrPart.ensure((size_t)batch * p.chunks * 6 * sizeof(double)))) return rc;
     if (grad && (rc = c->wWPart.ensure(std::max<size_t>(1, (size_t)batch * p.chunks * c->P->w_total) * sizeof(cplx)))) return rc;
     ExecArgs a;
@@ -857,6 +883,7 @@ int apply_program_dev(sqgpu_ctx* c, const cplx* d_in, long long in_ystride, cplx
     FusedPlan p = plan_fused(c, MODE_APPLY, rows, cols, ysets);
     if (p.ok) {
         if ((rc = run_optabs(c, 1, p.log_ct, st))) return rc;
+        if ((rc = run_dense_tabs(c, p.log_ct, st))) return rc;
         const int* d_dop = nullptr;
         const int* d_dp = nullptr;
         if (deriv_op) {
@@ -1085,7 +1112,7 @@ int sqgpu_destroy(sqgpu_handle_t c) {
         DeviceGuard guard(c->device);
         std::lock_guard<std::mutex> lk(c->mtx);
         cudaStreamSynchronize(c->stream);
-        DevBuf* bufs[] = {&c->U, &c->plan2.dOps, &c->plan2.dMembers, &c->plan2.dParamOp, &c->plan2.wKtab, &c->plan2.wDKtab, &c->plan2.wOpTab, &c->plan3.dOps, &c->plan3.dMembers, &c->plan3.dParamOp, &c->plan3.wKtab, &c->plan3.wDKtab, &c->plan3.wOpTab, &c->planW.dOps, &c->planW.dMembers, &c->planW.dParamOp, &c->planW.wKtab, &c->planW.wDKtab, &c->planW.wOpTab, &c->dPool, &c->wParams, &c->wTrPart, &c->wWPart,
+        DevBuf* bufs[] = {&c->U, &c->plan2.dOps, &c->plan2.dMembers, &c->plan2.dParamOp, &c->plan2.wKtab, &c->plan2.wDKtab, &c->plan2.wOpTab, &c->plan3.dOps, &c->plan3.dMembers, &c->plan3.dParamOp, &c->plan3.wKtab, &c->plan3.wDKtab, &c->plan3.wOpTab, &c->planW.dOps, &c->planW.dMembers, &c->planW.dParamOp, &c->planW.wKtab, &c->planW.wDKtab, &c->planW.wOpTab, &c->plan2.wDenseTab, &c->plan3.wDenseTab, &c->planW.wDenseTab, &c->dPool, &c->wParams, &c->wTrPart, &c->wWPart,
                           &c->wTraces, &c->wOmega, &c->wCost, &c->wGrad, &c->wMat, &c->wDerivIdx, &c->wTraces0,
                           &c->hIndptr, &c->hIndices, &c->hValues};
         for (DevBuf* b : bufs) b->release();
@@ -1151,7 +1178,7 @@ int sqgpu_set_circuit(sqgpu_handle_t c, const sqgpu_gate_desc* gates, int n_gate
         std::vector<DevMember> members;
         std::vector<int> param_op(std::max(n_params, 1), -1), param_slot(std::max(n_params, 1), 0);
         int kern_total = 0, dkern_total = 0, w_total = 0, wmax = 4;
-        int dense_stage = 0;
+        int dense_stage = 0, n_dense = 0;
         std::vector<int> pend;
         unsigned pend_support = 0;
         auto finish_op = [&](DevOp& op) {
@@ -1164,7 +1191,8 @@ int sqgpu_set_circuit(sqgpu_handle_t c, const sqgpu_gate_desc* gates, int n_gate
                 // generic dense path: dim^2 complex; raw 4-5 qubit kernels on the tensor cores: padded real embedding + patterns
                 int need = op.dim * op.dim;
                 if (op.dim > 16) need = (2 * op.dim) * (2 * op.dim + 4) / 2 + op.dim;
-                else if (op.type == SQGPU_GENERAL && op.dim >= 8) need = 2 * op.dim * op.dim + 1;  // DMMA fragment table
+                else if (op.type == SQGPU_GENERAL && op.dim >= 8) need = (int)(sizeof(DenseTab) / sizeof(cplx)) + 1;  // DMMA fragment table
+                if (op.type == SQGPU_GENERAL && op.ctrl_mask == 0 && (op.nq == 3 || op.nq == 4)) op.dtab = ++n_dense;
                 dense_stage = std::max(dense_stage, need);
             }
             if (op.n_params > 0) {
@@ -1268,6 +1296,8 @@ int sqgpu_set_circuit(sqgpu_handle_t c, const sqgpu_gate_desc* gates, int n_gate
         out.w_total = w_total;
         out.wmax = wmax;
         out.dense_stage = dense_stage;
+        out.n_dense = n_dense;
+        out.dense_logct = -1;
         return (int)SQGPU_OK;
     };
 

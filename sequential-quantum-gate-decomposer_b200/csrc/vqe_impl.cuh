@@ -46,6 +46,7 @@ static int vqe_window_dev(sqgpu_ctx* c, const double* d_params, int batch, bool 
             c->launches++;
         }
         if ((rc = run_optabs(c, nb, pf.log_ct, st))) return rc;
+        if ((rc = run_dense_tabs(c, pf.log_ct, st))) return rc;
         time_begin(c, "fused_exec<WINDOW_FWD>", st);
         for (const auto& sg : c->segs) {
             ExecArgs a;
@@ -65,6 +66,7 @@ static int vqe_window_dev(sqgpu_ctx* c, const double* d_params, int batch, bool 
         }
         if (!with_grad) continue;
         if (pb.log_ct != pf.log_ct && (rc = run_optabs(c, nb, pb.log_ct, st))) return rc;
+        if ((rc = run_dense_tabs(c, pb.log_ct, st))) return rc;
         if (c->P->w_total > 0) CUDA_TRY(cudaMemsetAsync(c->wWPart.p, 0, (size_t)nb * pb.chunks * c->P->w_total * sizeof(cplx), st));
         CUDA_TRY(cudaMemsetAsync(c->wTrPart.p, 0, (size_t)nb * pb.chunks * 6 * sizeof(double), st));
         time_begin(c, "fused_exec<WINDOW_BWD>", st);
