@@ -557,6 +557,10 @@ FusedPlan plan_fused(const sqgpu_ctx* c, int mode, int rows, int cols, int ysets
         }
     }
     {
+        const char* te = getenv("SQGPU_THREADS");  // experiment hook: CTA size of the fused executor
+        if (te && atoi(te) >= 64) pick_threads = std::min(pick_threads, atoi(te));
+    }
+    {
         const int lc = pick, ct = 1 << lc;
         p.ok = true;
         p.log_ct = lc;
@@ -947,6 +951,43 @@ int apply_program_dev(sqgpu_ctx* c, const cplx* d_in, long long in_ystride, cplx
             y = y1;
         }
     }
+    return SQGPU_OK;
+}
+
+// State vectors too long for one shared-memory tile (n >= 14): the windowed executor -- one pass over the state per
+// SEGMENT of the window plan instead of one per gate (build_window_plan). Parameters are in c->wParams. Returns 1 when no
+// window plan fits (caller falls back to one op per launch).
+int apply_window_dev(sqgpu_ctx* c, cplx* d_inout, int rows, cudaStream_t st) {
+    Plan* saved = c->P;
+    c->P = &c->planW;
+    const int w = c->win_w, wr = 1 << w, wc = rows >> w;
+    const FusedPlan pf = plan_fused(c, MODE_APPLY, wr, wc, 1);
+    if (!pf.ok || c->segs.empty()) {
+        c->P = saved;
+        return 1;
+    }
+    int rc;
+    if ((rc = run_tables(c, c->wParams.as<double>(), 1, false, st))) return rc;
+    if ((rc = run_optabs(c, 1, pf.log_ct, st))) return rc;
+    if ((rc = run_dense_tabs(c, pf.log_ct, st))) return rc;
+    time_begin(c, "fused_exec<WINDOW_FWD>", st);
+    for (const auto& sg : c->segs) {
+        ExecArgs a;
+        fill_common_args(c, pf, a, wr, wc);
+        a.n = w;
+        a.in = d_inout;
+        a.out = d_inout;
+        a.wmask = sg.wmask;
+        a.ops += sg.begin;
+        a.n_ops = sg.end - sg.begin;
+        a.optabs += sg.begin;
+        a.optab_stride = c->P->n_ops;
+        a.k_shared = 1;
+        cudaError_t e = launch_fused_mode<MODE_APPLY>(a, pf, 1, st);
+        c->launches++;
+        if (e != cudaSuccess) return fail(SQGPU_ERR_CUDA, "fused_exec launch failed: %s", cudaGetErrorString(e));
+    }
+    time_end(c, st);
     return SQGPU_OK;
 }
 
@@ -1455,8 +1496,15 @@ int sqgpu_apply(sqgpu_handle_t c, const double* params, double* inout, int rows,
     if ((rc = c->wParams.ensure(std::max<size_t>(1, c->n_params) * sizeof(double)))) return rc;
     if (c->n_params) CUDA_TRY(cudaMemcpyAsync(c->wParams.p, params, c->n_params * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(cudaMemcpy2DAsync(c->wMat.p, (size_t)cols * sizeof(cplx), inout, (size_t)stride * sizeof(cplx), (size_t)cols * sizeof(cplx), rows, cudaMemcpyHostToDevice, c->stream));
-    if ((rc = run_tables(c, c->wParams.as<double>(), 1, false, c->stream))) return rc;
-    if ((rc = apply_program_dev(c, c->wMat.as<cplx>(), 0, c->wMat.as<cplx>(), 0, 1, rows, cols, nullptr, nullptr, c->stream))) return rc;
+    rc = 1;
+    if (cols == 1 && !plan_fused(c, MODE_APPLY, rows, 1, 1).ok) rc = apply_window_dev(c, c->wMat.as<cplx>(), rows, c->stream);
+    if (rc == 1) {
+        c->P = &c->plan2;
+        if ((rc = run_tables(c, c->wParams.as<double>(), 1, false, c->stream))) return rc;
+        if ((rc = apply_program_dev(c, c->wMat.as<cplx>(), 0, c->wMat.as<cplx>(), 0, 1, rows, cols, nullptr, nullptr, c->stream))) return rc;
+    } else if (rc) {
+        return rc;
+    }
     CUDA_TRY(cudaMemcpy2DAsync(inout, (size_t)stride * sizeof(cplx), c->wMat.p, (size_t)cols * sizeof(cplx), (size_t)cols * sizeof(cplx), rows, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return SQGPU_OK;

@@ -146,3 +146,54 @@ class ShardedCost:
     def close(self):
         if hasattr(self.engine, "close"):
             self.engine.close()
+
+
+class ShardedVQE:
+    """VQE energy / energy+gradient over ``world`` ranks. A 2^n state vector is never split: the parameter
+    sets are sharded (rank r evaluates a contiguous slice on its own copy of the initial state and Hamiltonian) and one
+    all-gather returns all energies and gradients, as for ``ShardedCost(mode="batch")``."""
+
+    def __init__(self, state0, circuit, indptr, indices, data, engine_factory=None, device=None, group=None):
+        import torch.distributed as dist
+
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.n_params = circuit.get_Parameter_Num()
+        if engine_factory is None:
+            from .engine import Engine
+
+            engine_factory = Engine
+        self.engine = engine_factory(self.rank if device is None else device)
+        self.engine.upload_matrix(np.ascontiguousarray(state0, dtype=np.complex128).reshape(-1))
+        self.engine.set_circuit(circuit)
+        self.engine.set_hamiltonian_csr(indptr, indices, data)
+
+    _tensor = ShardedCost._tensor
+    _all_gather_rows = ShardedCost._all_gather_rows
+
+    def energy_grad(self, params, with_grad=True):
+        p = np.ascontiguousarray(params, dtype=np.float64)
+        if p.ndim == 1:
+            p = p.reshape(1, -1)
+        B = p.shape[0]
+        counts = [batch_shard(B, r, self.world)[1] - batch_shard(B, r, self.world)[0] for r in range(self.world)]
+        b, e = batch_shard(B, self.rank, self.world)
+        if with_grad:
+            if e > b:
+                en, g = self.engine.vqe_energy_grad_batched(p[b:e])
+            else:
+                en, g = np.zeros(0), np.zeros((0, self.n_params))
+            packed = np.concatenate([np.asarray(en).reshape(-1, 1), np.asarray(g).reshape(e - b, self.n_params)], axis=1)
+            allp = self._all_gather_rows(packed, counts)
+            return allp[:, 0].copy(), allp[:, 1:].copy()
+        en = self.engine.vqe_energy_batched(p[b:e]) if e > b else np.zeros(0)
+        return self._all_gather_rows(np.asarray(en).reshape(-1, 1), counts)[:, 0].copy()
+
+    def energy(self, params):
+        return self.energy_grad(params, with_grad=False)
+
+    def close(self):
+        if hasattr(self.engine, "close"):
+            self.engine.close()

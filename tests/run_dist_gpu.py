@@ -46,6 +46,25 @@ for variant in (0, 2, 3, 9):
         if rank == 0:
             print("variant %d mode %-7s world %d max err %.3e %s" % (variant, mode, world, err, "ok" if good else "FAIL"), flush=True)
         sc.close()
+# VQE: parameter sets sharded over the ranks (the partial-sum order may depend on the slice size: 1e-12)
+nv = 10
+vc = H.hea_zyz_circuit(nv, 2)
+psi0 = np.zeros(1 << nv, dtype=np.complex128)
+psi0[0] = 1.0
+ip, ix, dv = H.heisenberg_csr(nv)
+vp = H.random_params(vc.get_Parameter_Num(), seed=3, batch=13)
+single = sq.Engine(local)
+single.upload_matrix(psi0)
+single.set_circuit(vc)
+single.set_hamiltonian_csr(ip, ix, dv)
+e_ref, g_ref = single.vqe_energy_grad_batched(vp)
+sv = sq.dist.ShardedVQE(psi0, vc, ip, ix, dv, device=local)
+e_sh, g_sh = sv.energy_grad(vp)
+err = max(np.abs(e_sh - e_ref).max(), np.abs(g_sh - g_ref).max(), np.abs(sv.energy(vp) - e_ref).max())
+ok = ok and err <= 1e-12
+if rank == 0:
+    print("VQE batch sharding world %d max err %.3e %s" % (world, err, "ok" if err <= 1e-12 else "FAIL"), flush=True)
+sv.close()
 t = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(t, op=dist.ReduceOp.MIN)
 dist.destroy_process_group()

@@ -78,6 +78,40 @@ class OracleEngine:
         return np.array([r[0] for r in res]), np.array([r[1] for r in res])
 
 
+class OracleVQEEngine:
+    """engine double with the Engine methods dist.ShardedVQE uses"""
+
+    def __init__(self, device=0):
+        import pyoracle
+
+        self.port = pyoracle.Port()
+
+    def upload_matrix(self, psi0):
+        self.psi0 = np.ascontiguousarray(psi0)
+
+    def set_circuit(self, circuit):
+        self.descs, self.pool = circuit.descriptors()
+        self.P = circuit.get_Parameter_Num()
+
+    def set_hamiltonian_csr(self, indptr, indices, data):
+        self.H = (indptr, indices, data)
+
+    def vqe_energy_grad_batched(self, params):
+        res = [self.port.vqe_energy_grad(self.descs, self.P, p, self.psi0, *self.H, pool=self.pool) for p in params]
+        return np.array([r[0] for r in res]), np.array([r[1] for r in res])
+
+    def vqe_energy_batched(self, params):
+        return self.vqe_energy_grad_batched(params)[0]
+
+
+def _vqe_problem():
+    n = 4
+    circ = H.hea_zyz_circuit(n, 1)
+    psi0 = np.zeros(1 << n, dtype=np.complex128)
+    psi0[0] = 1.0
+    return n, circ, psi0, H.heisenberg_csr(n), H.random_params(circ.get_Parameter_Num(), seed=9, batch=5)
+
+
 def _worker(rank, world, port_no, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port_no)
@@ -97,6 +131,10 @@ def _worker(rank, world, port_no, q):
                 sc = sq.dist.ShardedCost(U, circ, variant=variant, mode=mode, prev_cost=0.37, engine_factory=OracleEngine)
                 c, g = sc.cost_grad(params)
                 res[(mode, variant)] = (c, g, sc.cost(params))
+        _, vcirc, psi0, (ip, ix, dv), vparams = _vqe_problem()
+        sv = sq.dist.ShardedVQE(psi0, vcirc, ip, ix, dv, engine_factory=OracleVQEEngine)
+        en, gr = sv.energy_grad(vparams)
+        res["vqe"] = (en, gr, sv.energy(vparams))
         q.put((rank, res))
     finally:
         dist.destroy_process_group()
@@ -144,6 +182,14 @@ def test_world2_gloo_matches_single_process(port):
     P = circ.get_Parameter_Num()
     U = H.random_unitary(1 << n).conj().T.copy()
     params = H.random_params(P, batch=5)
+    _, vcirc, psi0, (ip, ix, dv), vparams = _vqe_problem()
+    vd, vpool = vcirc.descriptors()
+    en0, gr0, ee0 = results[0].pop("vqe")
+    en1, gr1, ee1 = results[1].pop("vqe")
+    assert (en0 == en1).all() and (gr0 == gr1).all() and (ee0 == ee1).all()
+    for b in range(len(vparams)):
+        e_ref, g_ref = port.vqe_energy_grad(vd, vcirc.get_Parameter_Num(), vparams[b], psi0, ip, ix, dv, pool=vpool)
+        assert abs(en0[b] - e_ref) < 1e-12 and abs(ee0[b] - e_ref) < 1e-12 and np.abs(gr0[b] - g_ref).max() < 1e-12
     for key, (c0, g0, cc0) in results[0].items():
         mode, variant = key
         c1, g1, cc1 = results[1][key]

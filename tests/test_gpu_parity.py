@@ -224,6 +224,23 @@ def test_crot_and_syc_in_fused_blocks(sq, port, plan_mode):
         assert close_rel(f, f_ref) and close_rel(g, g_ref)
 
 
+def test_long_state_vector_apply_uses_window_plan(sq, port):
+    """Circuit.apply_to on a 2^15 state vector: too long for one shared-memory tile, so sqgpu_apply runs the window plan
+    (segments of commuting ops, one pass over the state per segment) -- every gate family, against the oracle"""
+    n = 15
+    c = H.random_circuit(n, 120, seed=77, general_k=(2, 3, 4))
+    d, pool = c.descriptors()
+    p = H.random_params(c.get_Parameter_Num(), seed=8)
+    psi = H.random_state(1 << n)
+    e = sq.Engine(0)
+    e.set_circuit(c)
+    got = psi.copy()
+    e.apply(p, got)
+    assert e.last_kernel_time()[0] == "fused_exec<WINDOW_FWD>"
+    assert np.abs(got - port.apply_circuit(d, p, psi.reshape(-1, 1), pool).reshape(-1)).max() < ENTRY_TOL
+    e.close()
+
+
 def test_vqe_window_with_mixed_gates(sq, port, monkeypatch):
     """the windowed state-vector executor on a circuit with every gate family (controlled, two-target, GENERAL blocks,
     CCX/CSWAP): segments are formed by pulling commuting ops forward, so this pins the reordering and the qubit remapping"""
