@@ -35,11 +35,11 @@ for _p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
 METRIC = "cost+grad evals/s (10-qubit unitary decomposition)"
 UNIT = "evals/s"
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE fused_exec<GRAD> launch of the default workload (n=10, L=4, batch 256),
-# from the `ncu --set full` capture summarised in profiles/r1_ncu_fused_grad_v5_b256.csv (629.4 MB read + 356.2 MB written).
+# from the `ncu --set full` capture summarised in profiles/r1_ncu_fused_grad_v8_b256.csv (753.9 MB read + 598.9 MB written).
 # Algorithmic HBM bytes of the same launch: U once (16.8 MB) + block tables (187 MB) + W partials written once (3.2 GB would
 # be the naive figure; they are reduced in L2) -- the kernel is tensor-pipe bound, HBM runs at 0.04 % of peak.
-TRAFFIC_DEFAULT_WORKLOAD = 985516544
-TRAFFIC_NOTE = "ncu --set full capture of this launch (profiles/r1_ncu_fused_grad_v5_b256.csv); null for non-default workloads"
+TRAFFIC_DEFAULT_WORKLOAD = 1352835328
+TRAFFIC_NOTE = "ncu --set full capture of this launch (profiles/r1_ncu_fused_grad_v8_b256.csv); null for non-default workloads"
 
 
 def parse():
