@@ -59,6 +59,7 @@ struct ExecArgs {
     unsigned wmask;          // window mode (state vectors): bit mask of the `n_win` qubits that form the tile's rows; element
                              // (row r, column j) of y lives at in[y * ystride + deposit(r, wmask) | deposit(j, ~wmask)]; 0: matrix
     cplx* beta;              // MODE_BWD: the row functional, same layout and stride as out
+    int sum_sq;              // SUM_OF_SQUARES cost: trace slot 0 carries sum |M_ij - delta_ij|^2, beta_N = 2 conj(M - I)
     const struct DenseTab* dense_tabs;  // fragment tables of the raw dense 3-/4-qubit ops (build_dense_tabs), NULL: none
     int k_shared;            // 1: every blockIdx.y uses kernel-table set 0 (materialised derivative: one parameter set)
     const int* deriv_op;     // MODE_APPLY: per blockIdx.y the op whose derivative kernel is applied (NULL: none)
@@ -920,7 +921,17 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
         if (MODE != MODE_BWD) {
             double t[6] = {0, 0, 0, 0, 0, 0};
             const int off = A.trace_offset;
-            if (tid < valid) {
+            if (A.sum_sq) {
+                // get_cost_function_sum_of_squares (N_Qubit_Decomposition_Cost_Function.cpp:443-457): every element of the tile
+                for (int e = tid; e < rows * CT; e += nthr) {
+                    const int i = e >> LOG_CT, c = e & (CT - 1);
+                    if (c < valid) {
+                        const cplx v = sa[elem<LOG_CT>(i, c)];
+                        const double dr = v.x - ((i == j0 + c + off) ? 1.0 : 0.0);
+                        t[0] += dr * dr + v.y * v.y;
+                    }
+                }
+            } else if (tid < valid) {
                 const cplx v = sa[elem<LOG_CT>(j0 + tid + off, tid)];
                 t[0] = v.x;
                 t[1] = v.y;
@@ -971,7 +982,18 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                 tab_wait();
             }
             __syncthreads();
-            {
+            if (A.sum_sq) {
+                // the functional of the gradient is Re sum conj(Upartial_ij) dM_ij with Upartial = 2 (M - I)
+                // (get_deriv_sum_of_squares :459-475, real_trace_conj_dot): beta_N = conj(Upartial) per column
+                const int off = A.trace_offset;
+                for (int e = tid; e < rows * CT; e += nthr) {
+                    const int i = e >> LOG_CT, c = e & (CT - 1);
+                    if (c < valid) {
+                        const cplx v = sa[elem<LOG_CT>(i, c)];
+                        sb[elem<LOG_CT>(i, c)] = cmake(2.0 * (v.x - ((i == j0 + c + off) ? 1.0 : 0.0)), -2.0 * v.y);
+                    }
+                }
+            } else {
                 const int off = A.trace_offset;
                 const cplx w0 = A.omega[(size_t)y * 3 + 0];
                 if (tid < valid) sb[elem<LOG_CT>(j0 + tid + off, tid)] = w0;

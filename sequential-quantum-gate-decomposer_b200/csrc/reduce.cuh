@@ -86,6 +86,7 @@ __device__ __forceinline__ double cost_formula(const CostCfg& c, const double* t
             return 1 - d * d * (t[0] * t[0] + t[1] * t[1] + sp * (c.c1 * (t[2] * t[2] + t[3] * t[3]) + c.c2 * (t[4] * t[4] + t[5] * t[5])));
         }
         case SQGPU_INFIDELITY: return 1.0 - ((t[0] * t[0] + t[1] * t[1]) / n + 1) / (n + 1);
+        case SQGPU_SUM_OF_SQUARES: return t[0];  // slot 0 carries sum |M_ij - delta_ij|^2 (Cost_Function.cpp:443-457)
         default: return nan("");
     }
 }
@@ -106,6 +107,7 @@ __device__ __forceinline__ double grad_formula(const CostCfg& c, const double* t
             return -2.0 * d * d * dl[0];
         }
         case SQGPU_INFIDELITY: return -2.0 / n / (n + 1) * t[0] * dl[0] - 2.0 / n / (n + 1) * t[1] * dl[1];
+        case SQGPU_SUM_OF_SQUARES: return dl[0];  // real_trace_conj_dot(Upartial, dM_p), Optimization_Interface.cpp:1432-1434
         default: return nan("");
     }
 }

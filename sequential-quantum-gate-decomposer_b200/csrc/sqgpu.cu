@@ -241,7 +241,7 @@ int n_trace_types_of(int variant) {
 bool variant_supported(int v) {
     return v == SQGPU_FROBENIUS_NORM || v == SQGPU_FROBENIUS_NORM_CORRECTION1 || v == SQGPU_FROBENIUS_NORM_CORRECTION2 ||
            v == SQGPU_HILBERT_SCHMIDT_TEST || v == SQGPU_HILBERT_SCHMIDT_TEST_CORRECTION1 ||
-           v == SQGPU_HILBERT_SCHMIDT_TEST_CORRECTION2 || v == SQGPU_INFIDELITY;
+           v == SQGPU_HILBERT_SCHMIDT_TEST_CORRECTION2 || v == SQGPU_INFIDELITY || v == SQGPU_SUM_OF_SQUARES;
 }
 
 // the trace offset only enters the Frobenius-family cost functions (get_cost_function*, :73-404); get_trace* ignore it
@@ -708,6 +708,7 @@ int run_exec_resident(sqgpu_ctx* c, int batch, bool grad, const cplx* d_omega, d
     a.ld_in = c->cols;
     a.trace_offset = effective_offset(c);
     a.n_trace_types = n_trace_types_of(c->cfg.variant);
+    a.sum_sq = c->cfg.variant == SQGPU_SUM_OF_SQUARES ? 1 : 0;
     a.tr_part = c->wTrPart.as<double>();
     a.w_part = c->wWPart.as<cplx>();
     a.omega = d_omega;
@@ -996,6 +997,7 @@ int apply_window_dev(sqgpu_ctx* c, cplx* d_inout, int rows, cudaStream_t st) {
 // with the streaming kernels; partials have the same layout as the fused executor's, one "chunk" per column chunk.
 int run_exec_streaming(sqgpu_ctx* c, int batch, bool grad, const cplx* d_omega, double* d_traces, cudaStream_t st) {
     const int rows = c->rows, cols = c->cols;
+    if (c->cfg.variant == SQGPU_SUM_OF_SQUARES) return fail(SQGPU_ERR_UNSUPPORTED, "SUM_OF_SQUARES is not implemented on the streaming executor (n = %d)", c->qbit_num);
     if (grad)
         for (const DevOp& op : c->P->ops) {
             const bool ok = op.dim == 2 || (op.dim == 4 && op.nq == 2 && op.ctrl_mask == 0);

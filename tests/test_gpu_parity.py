@@ -129,7 +129,7 @@ def test_column_subset_invariance(eng):
 
 # ---- cost and gradient (optimization_problem{,_combined,_batched}) ----------------------------------------------
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 9])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 9])
 @pytest.mark.parametrize("n,levels", [(4, 2), (5, 1)])
 def test_cost_and_gradient_match_oracle(sq, port, plan_mode, variant, n, levels):
     c = H.adaptive_circuit(n, levels)
@@ -260,6 +260,27 @@ def test_vqe_window_with_mixed_gates(sq, port, monkeypatch):
     for b in range(2):
         e_ref, g_ref = port.vqe_energy_grad(d, P, ps[b], psi0, indptr, indices, data, pool=pool)
         assert close_rel(en[b], e_ref) and close_rel(gr[b], g_ref)
+    e.close()
+
+
+def test_sum_of_squares_n8_rectangular(sq, port):
+    """SUM_OF_SQUARES (cost = sum |M_ij - delta_ij|^2, gradient through Upartial = 2 (M - I)) on a rectangular 256 x 96
+    matrix: several column tiles per CTA and a diagonal that ends inside the matrix"""
+    n = 8
+    c = H.adaptive_circuit(n, 1)
+    d, pool = c.descriptors()
+    P = c.get_Parameter_Num()
+    U = H.random_unitary(1 << n)[:, :96].copy()
+    e = sq.Engine(0)
+    e.upload_matrix(U)
+    e.set_circuit(c)
+    e.set_cost(6, 0)
+    ps = H.random_params(P, seed=31, batch=2)
+    f, g = e.cost_grad_batched(ps)
+    f2 = e.cost_batched(ps)
+    for b in range(2):
+        f_ref, g_ref = port.cost_grad(d, P, ps[b], U, n, 6)
+        assert close_rel(f[b], f_ref) and close_rel(f2[b], f_ref) and close_rel(g[b], g_ref)
     e.close()
 
 

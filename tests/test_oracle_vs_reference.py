@@ -74,7 +74,7 @@ def test_general_block_placement(port, ref, k):
         assert np.abs(port.apply_circuit(d, [], psi, pool) - rc.apply([], psi)).max() < TOL
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 9])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 9])
 def test_cost_and_gradient_match_reference(port, ref, variant):
     """optimization_problem / optimization_problem_combined on the adaptive structure, n = 4, L = 2"""
     n = 4
