@@ -17,13 +17,19 @@
 // Inactive (control = 0) pairs contribute nothing, which is exactly the reference's "zero rows in the derivative"
 // convention (apply_kernel_to_input.cpp:93-97).
 //
-// The hot ops are the planner's fused blocks: dense 4x4 (two qubits) or 2x2 (one qubit) complex kernels without
-// controls. Each thread keeps the kernel (and, in the backward sweep, the 16 W accumulators) in registers and owns
-// whole amplitude groups, so a block costs one shared-memory round trip and one barrier instead of one per gate.
+// The hot ops are the planner's fused blocks: dense 8x8 (three qubits) or 4x4 (two qubits) complex kernels without
+// controls, run on the FP64 tensor cores (mma.sync m8n8k4.f64 on the real embedding of the kernel, block_dmma_forward /
+// block_dmma_backward); a block costs one shared-memory round trip and one barrier instead of one per gate. Single-qubit
+// blocks, controlled leftovers and derivative ops take scalar paths in the same kernel; raw GENERAL 3-5 qubit kernels the
+// dense DMMA paths.
 //
-// Data layout in shared memory: element (row i, tile column c) at [phys(i) * CT + c], 16 B each, so a quarter-warp
-// (8 lanes, one 128 B shared-memory wavefront) reads whole rows; phys() XOR-swizzles the low row bits so that rows that
-// differ in the lane-varying bits land in different 16 B bank groups for every target qubit.
+// Data layout in shared memory: element (row i, tile column c) at elem(i, c), 16 B each, a GF(2)-linear bijection that
+// XORs images of the row bits into the three bank-group bits (see elem() below), so that the 128-bit fragment accesses of
+// the DMMA paths are conflict-free and every address splits into B0(batch) ^ slot(lane).
+//
+// Window mode (state vectors too long for one tile, VQE): the rows of the tile are the configurations of an arbitrary
+// subset of `n_win` qubits (ExecArgs::wmask), the columns those of the other bits; MODE_APPLY / MODE_BWD run one SEGMENT of
+// the window plan (sqgpu.cu: build_window_plan) per launch.
 #pragma once
 #include "sq_types.cuh"
 #include "../../include/sqgpu.h"
