@@ -505,7 +505,7 @@ size_t fused_smem(int mode, int rows, int ct, int threads, int dense_stage, int 
     return s;
 }
 
-FusedPlan plan_fused(const sqgpu_ctx* c, int mode, int rows, int cols, int ysets) {
+FusedPlan plan_fused(const sqgpu_ctx* c, int mode, int rows, int cols, int ysets, int default_split = 2) {
     FusedPlan p;
     {   // test hook: SQGPU_FORCE_STREAM=1 sends cost / gradient evaluations down the chunked streaming executor
         const char* fs = getenv("SQGPU_FORCE_STREAM");
@@ -539,9 +539,9 @@ FusedPlan plan_fused(const sqgpu_ctx* c, int mode, int rows, int cols, int ysets
     // table prologue between two ops, the other keeps the FP64 tensor pipe busy. Taken when both fit in the SM.
     {
         const char* sp = getenv("SQGPU_SPLIT");
-        const int split = sp ? atoi(sp) : 2;
+        const int split = sp ? atoi(sp) : default_split;
         int lc = pick, thr = pick_threads, ways = 1;
-        while (ways < split && lc > 0 && thr >= 128) {
+        while (ways < split && lc > 0 && thr >= 128 && (thr >= 256 || split > 4)) {
             --lc;
             thr /= 2;
             ways *= 2;
@@ -962,7 +962,7 @@ int apply_window_dev(sqgpu_ctx* c, cplx* d_inout, int rows, cudaStream_t st) {
     Plan* saved = c->P;
     c->P = &c->planW;
     const int w = c->win_w, wr = 1 << w, wc = rows >> w;
-    const FusedPlan pf = plan_fused(c, MODE_APPLY, wr, wc, 1);
+    const FusedPlan pf = plan_fused(c, MODE_APPLY, wr, wc, 1, 4);
     if (!pf.ok || c->segs.empty()) {
         c->P = saved;
         return 1;

@@ -12,8 +12,10 @@ static int vqe_window_dev(sqgpu_ctx* c, const double* d_params, int batch, bool 
     const int rows = c->rows, w = c->win_w, wr = 1 << w, wc = rows >> w;
     int rc;
     const int slice = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::min(batch, 65535), ((size_t)1 << 30) / ((size_t)rows * sizeof(cplx))));
-    const FusedPlan pf = plan_fused(c, MODE_APPLY, wr, wc, std::min(slice, batch));
-    const FusedPlan pb = with_grad ? plan_fused(c, MODE_BWD, wr, wc, std::min(slice, batch)) : pf;
+    // four quarter-width CTAs per SM: with ~5 ops between a tile's load and its store, more independent CTAs in different
+    // phases are what overlaps the HBM round trips with the tensor work (measured: +12 % energy, +7 % gradient over two)
+    const FusedPlan pf = plan_fused(c, MODE_APPLY, wr, wc, std::min(slice, batch), 4);
+    const FusedPlan pb = with_grad ? plan_fused(c, MODE_BWD, wr, wc, std::min(slice, batch), 4) : pf;
     if (!pf.ok || !pb.ok) return 1;
     const int nblk = std::min(c->sm_count * 8, std::max(1, rows / 512));
     if ((rc = c->wMat.ensure((size_t)2 * slice * rows * sizeof(cplx)))) return rc;
