@@ -572,7 +572,8 @@ FusedPlan plan_fused(const sqgpu_ctx* c, int mode, int rows, int cols, int ysets
             p.tiles_per_cta = 1;
             p.chunks = p.tiles;
         } else {
-            const int want_ctas = c->sm_count * 24;
+            const char* wc_env = getenv("SQGPU_CTAS_PER_SM");  // experiment hook: grid granularity
+            const int want_ctas = c->sm_count * (wc_env ? std::max(1, atoi(wc_env)) : 48);
             int chunks = std::min(p.tiles, std::max(1, (want_ctas + ysets - 1) / ysets));
             p.tiles_per_cta = (p.tiles + chunks - 1) / chunks;
             p.chunks = (p.tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
