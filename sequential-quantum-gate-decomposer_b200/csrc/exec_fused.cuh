@@ -293,6 +293,14 @@ struct OpTab {
     int widx[32];           // 3-qubit blocks: positions of the lane's two W' outputs, idx0 | idx1 << 8
 };
 
+// shared-memory copy of the part of an OpTab one sweep direction needs: the forward sweep takes frag[0] (K), the backward
+// sweep frag[1..2] (K^dagger, K^T); both take the slots (4.7 KB instead of 6.8 KB per buffer)
+struct OpTabS {
+    double frag[2][8][32];
+    int slot[4][32];
+    int widx[32];
+};
+
 // local amplitude index from the lane's amplitude slot j (2 bits) and the k-step pair u: block-qubit position ju carries u
 __device__ __forceinline__ int dep3(int j, int u, int ju) {
     const int ja = (ju == 0) ? 1 : 0, jb = (ju == 2) ? 1 : 2;
@@ -382,7 +390,7 @@ __global__ void build_optabs(const DevOp* __restrict__ ops, int n_ops, const cpl
 
 // forward: x <- K x for every group of the tile. One warp handles 8 (group, column) items per step.
 template <int LOG_CT, int KQ>
-__device__ __forceinline__ void block_dmma_forward(cplx* sa, const OpTab* T, const BlockGeom<LOG_CT, KQ>& G, int rows, int tid,
+__device__ __forceinline__ void block_dmma_forward(cplx* sa, const OpTabS* T, const BlockGeom<LOG_CT, KQ>& G, int rows, int tid,
                                                    int nthr) {
     constexpr int NT = (KQ == 3) ? 2 : 1, KS = 2 * NT;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
@@ -418,7 +426,7 @@ __device__ __forceinline__ void block_dmma_forward(cplx* sa, const OpTab* T, con
 // backward step of the adjoint sweep: W' += beta p^T (outer product over items), a <- K^dagger p, beta <- K^T beta, all on
 // DMMA; the warp's W' (DIM x DIM complex) is written to wslot after the loop.
 template <int LOG_CT, int KQ>
-__device__ __forceinline__ void block_dmma_backward(cplx* sa, cplx* sb, const OpTab* T, const BlockGeom<LOG_CT, KQ>& G, int rows,
+__device__ __forceinline__ void block_dmma_backward(cplx* sa, cplx* sb, const OpTabS* T, const BlockGeom<LOG_CT, KQ>& G, int rows,
                                                     bool has_w, cplx* wslot, int tid, int nthr) {
     constexpr int DIM = 1 << KQ, NT = (KQ == 3) ? 2 : 1, KS = 2 * NT;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
@@ -429,8 +437,8 @@ __device__ __forceinline__ void block_dmma_backward(cplx* sa, cplx* sb, const Op
         sl[t] = T->slot[t][lane];
 #pragma unroll
         for (int s = 0; s < KS; ++s) {
-            kd[t][s] = T->frag[1][t * KS + s][lane];
-            kt[t][s] = T->frag[2][t * KS + s][lane];
+            kd[t][s] = T->frag[0][t * KS + s][lane];  // K^dagger
+            kt[t][s] = T->frag[1][t * KS + s][lane];  // K^T
         }
     }
     slw[0] = T->slot[2][lane];
@@ -657,7 +665,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
     cplx* sb = sa + (size_t)rows * CT;                                   // the row functional beta (HAS_B only)
     cplx* sk = HAS_B ? sb + (size_t)rows * CT : sb;                       // raw dense kernel staging
     cplx* skm = sk + A.dense_stage;                                       // [2][KM_ELEMS] prefetched block kernels
-    OpTab* stab = reinterpret_cast<OpTab*>(skm + 2 * KM_ELEMS);           // [2] DMMA block lookup tables
+    OpTabS* stab = reinterpret_cast<OpTabS*>(skm + 2 * KM_ELEMS);         // [2] DMMA block lookup tables (one sweep direction)
     cplx* swarp = reinterpret_cast<cplx*>(stab + 2);                      // [2][nwarps][wmax]
     cplx* swacc = swarp + (HAS_B ? 2 * nwarps * A.wmax : 0);              // [w_total] if w_in_smem
     double* sred = reinterpret_cast<double*>(swacc + ((HAS_B && A.w_in_smem) ? A.w_total : 0));  // [nwarps][6]
@@ -708,12 +716,18 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
     // DMMA block table of op k: built per (parameter set, op) by build_optabs; copied global -> shared with cp.async while
     // the previous op computes (no registers held across the DMMA loops), into stab[k & 1]
     const OpTab* __restrict__ gtabs = A.optabs + (size_t)kset * (A.optab_stride ? A.optab_stride : A.n_ops);
-    auto tab_prefetch = [&](int k) {
+    auto tab_prefetch = [&](int k, bool bwd) {
         if (sops[k].kind != 2) return;
         const char* src = reinterpret_cast<const char*>(gtabs + k);
         const unsigned dst = (unsigned)__cvta_generic_to_shared(stab + (k & 1));
-        for (int e = tid; e < (int)(sizeof(OpTab) / 16); e += nthr)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + e * 16), "l"(src + (size_t)e * 16));
+        constexpr int FRAG = 8 * 32 * 8, TAIL = (int)(sizeof(OpTabS) - 2 * FRAG);  // bytes of one fragment set / of slots + widx
+        const int nfrag = bwd ? 2 * FRAG : FRAG, src_off = bwd ? FRAG : 0;
+        for (int e = tid; e < (nfrag + TAIL) / 16; e += nthr) {
+            const int b = e * 16;
+            const int d_off = (b < nfrag) ? b : 2 * FRAG + (b - nfrag);
+            const int s_off = (b < nfrag) ? src_off + b : 3 * FRAG + (b - nfrag);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + d_off), "l"(src + s_off));
+        }
     };
     auto tab_wait = [&]() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); };
 
@@ -764,7 +778,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
             const int first_op = (MODE == MODE_BWD) ? A.n_ops - 1 : 0;
             if (A.n_ops > 0 && tid < KM_ELEMS) skm[(first_op & 1) * KM_ELEMS + tid] = kernel_elem(first_op);
             if (A.n_ops > 0) {
-                tab_prefetch(first_op);
+                tab_prefetch(first_op, MODE == MODE_BWD);
                 tab_wait();
             }
         }
@@ -776,7 +790,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
             cplx next_elem = czero();
             const bool have_next = k + 1 < A.n_ops;
             if (have_next && tid < KM_ELEMS) next_elem = kernel_elem(k + 1);
-            if (have_next) tab_prefetch(k + 1);
+            if (have_next) tab_prefetch(k + 1, false);
             const cplx* __restrict__ km = skm + (k & 1) * KM_ELEMS;
             if (s.kind == 2) {
                 if (s.dim == 8) {
@@ -984,7 +998,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
             for (int e = tid; e < rows * CT; e += nthr) sb[e] = czero();
             if (A.n_ops > 0 && tid < KM_ELEMS) skm[((A.n_ops - 1) & 1) * KM_ELEMS + tid] = kernel_elem(A.n_ops - 1);
             if (A.n_ops > 0) {
-                tab_prefetch(A.n_ops - 1);
+                tab_prefetch(A.n_ops - 1, true);
                 tab_wait();
             }
             __syncthreads();
@@ -1030,7 +1044,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                 cplx next_elem = czero();
                 const bool have_next = k > 0;
                 if (have_next && tid < KM_ELEMS) next_elem = kernel_elem(k - 1);
-                if (have_next) tab_prefetch(k - 1);
+                if (have_next) tab_prefetch(k - 1, true);
                 const bool has_w = s.w_off >= 0;
                 cplx* wslot_c = swarp + (size_t)(buf * nwarps + warp) * A.wmax;
                 double* wslot = reinterpret_cast<double*>(wslot_c);

@@ -493,7 +493,7 @@ size_t fused_smem(int mode, int rows, int ct, int threads, int dense_stage, int 
     size_t s = (size_t)rows * ct * sizeof(cplx) * (has_b ? 2 : 1);
     s += (size_t)dense_stage * sizeof(cplx);
     s += 2 * KM_ELEMS * sizeof(cplx);        // prefetched block kernels
-    s += 2 * sizeof(OpTab);                  // DMMA block lookup tables (double-buffered)
+    s += 2 * sizeof(OpTabS);                 // DMMA block lookup tables of one sweep direction (double-buffered)
     s += (size_t)n_ops * sizeof(SOp);        // staged op table
     const int nwarps = threads / 32;
     if (has_b) {
