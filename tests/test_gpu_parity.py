@@ -284,6 +284,40 @@ def test_sum_of_squares_n8_rectangular(sq, port):
     e.close()
 
 
+@pytest.mark.parametrize("variant", [0, 3])
+def test_optimizer_trajectory_agreement(sq, port, variant):
+    """the same ADAM iteration driven once by the GPU cost+gradient and once by the oracle's (the reference algorithm):
+    the parameter and cost trajectories stay together within the fp64 tolerance of the gradient (BASELINE north_star:
+    'optimizer trajectory agreement within the stated fp64 tolerance')"""
+    n = 4
+    c = H.adaptive_circuit(n, 2)
+    d, pool = c.descriptors()
+    P = c.get_Parameter_Num()
+    U = H.random_unitary(1 << n).conj().T.copy()
+    dec = sq.N_Qubit_Decomposition_custom(U)
+    dec.set_Gate_Structure(c)
+    dec.set_Cost_Function_Variant(variant)
+
+    def run(cost_grad, steps=40, eta=0.02, b1=0.9, b2=0.999, eps=1e-8):
+        th = H.random_params(P, seed=77).copy()
+        m = np.zeros(P)
+        v = np.zeros(P)
+        traj = []
+        for t in range(1, steps + 1):
+            f, g = cost_grad(th)
+            traj.append(float(f))
+            m = b1 * m + (1 - b1) * g
+            v = b2 * v + (1 - b2) * g * g
+            th = th - eta * (m / (1 - b1 ** t)) / (np.sqrt(v / (1 - b2 ** t)) + eps)
+        return th, np.array(traj)
+
+    th_gpu, f_gpu = run(lambda th: dec.Optimization_Problem_Combined(th))
+    th_ref, f_ref = run(lambda th: port.cost_grad(d, P, th, U, n, variant))
+    assert f_gpu[-1] < f_gpu[0]  # it does optimise
+    assert np.abs(f_gpu - f_ref).max() < 1e-10
+    assert np.abs(th_gpu - th_ref).max() < 1e-8
+
+
 def test_reference_wrapper_flow(sq, port):
     """the call sequence of the reference's own test (tests/decomposition/test_optmization_problem_combined.py:189-219)"""
     n, levels = 5, 2
