@@ -318,6 +318,41 @@ def test_optimizer_trajectory_agreement(sq, port, variant):
     assert np.abs(th_gpu - th_ref).max() < 1e-8
 
 
+def test_reoptimise_19cnot_circuit_with_lbfgs(sq):
+    """BASELINE configs[1] / tests/decomposition/test_parametric_circuit.py:138-210 in miniature: the 19-CNOT circuit of
+    data/19CNOT.qasm (gate list from the golden fixture), target = the circuit at known parameters, start from a perturbed
+    parameter vector, L-BFGS on the GPU cost+gradient (Hilbert-Schmidt test cost) must bring the error below 1e-3 -- the
+    reference test's bar -- and well beyond"""
+    import scipy.optimize
+
+    import golden_cases as G
+
+    g = G.load("C2_19CNOT")
+    e = sq.Engine(0)
+    e.set_circuit_raw(g.descs, g.pool, g.P, g.n)
+    rng = np.random.default_rng(5)
+    theta_true = rng.random(g.P) * 2 * np.pi
+    M = np.eye(1 << g.n, dtype=np.complex128)
+    e.apply(theta_true, M)
+    e.upload_matrix(np.ascontiguousarray(M.conj().T))
+    e.set_cost(3, 0)
+    f_true, _ = e.cost_grad_batched(theta_true.reshape(1, -1))
+    assert abs(f_true[0]) < 1e-12
+    evals = [0]
+
+    def fun(th):
+        evals[0] += 1
+        f, gr = e.cost_grad_batched(th.reshape(1, -1))
+        return float(f[0]), np.asarray(gr[0], dtype=np.float64)
+
+    x0 = theta_true + 0.05 * rng.standard_normal(g.P)
+    f0 = fun(x0)[0]
+    res = scipy.optimize.minimize(fun, x0, jac=True, method="L-BFGS-B", options={"maxiter": 400, "ftol": 1e-15, "gtol": 1e-10})
+    assert f0 > 1e-3 and res.fun < 1e-3, (f0, res.fun, evals[0])
+    assert res.fun < 1e-6, (res.fun, evals[0])
+    e.close()
+
+
 def test_reference_wrapper_flow(sq, port):
     """the call sequence of the reference's own test (tests/decomposition/test_optmization_problem_combined.py:189-219)"""
     n, levels = 5, 2
