@@ -72,6 +72,25 @@ def c4():
             "TFLOP/s_algorithmic": flops / t / 1e12, "kernel": e.last_kernel_time()}
 
 
+def c4q5():
+    """C4 with 5-qubit blocks: 32 x 32 kernels, 256 flop per amplitude"""
+    n, M, B = 12, 64, 32
+    rng = np.random.default_rng(9)
+    c = sq.Circuit(n)
+    for m in range(M):
+        qs = sorted(int(q) for q in rng.choice(n, 5, replace=False))
+        c.add_GENERAL(H.random_unitary(32, seed=2000 + m), qs)
+    e = sq.Engine(0)
+    e.upload_matrix(np.ascontiguousarray(H.random_unitary(1 << n).conj().T))
+    e.set_circuit(c)
+    e.set_cost(0)
+    p = H.random_params(max(c.get_Parameter_Num(), 1), batch=B)[:, : c.get_Parameter_Num()]
+    t = timeit(lambda: e.cost_batched(p), reps=2)
+    flops = B * M * 8.0 * 32 * (1 << n) * (1 << n)
+    return {"config": "C4 variant: n=12, 64 GENERAL 5-qubit blocks, cost only", "batch": B, "evals_per_s": B / t,
+            "TFLOP/s_algorithmic": flops / t / 1e12, "kernel": e.last_kernel_time()}
+
+
 def c5(n=20, layers=10, B=64):
     indptr, indices, data = H.heisenberg_csr(n)
     c = H.hea_zyz_circuit(n, layers)
@@ -91,4 +110,4 @@ def c5(n=20, layers=10, B=64):
 if __name__ == "__main__":
     which = sys.argv[1:] or ["c2", "c3cost", "c4", "c5"]
     for w in which:
-        print(json.dumps({"c2": c2, "c4": c4, "c5": c5, "c3cost": c3cost}[w]()), flush=True)
+        print(json.dumps({"c2": c2, "c4": c4, "c4q5": c4q5, "c5": c5, "c3cost": c3cost}[w]()), flush=True)

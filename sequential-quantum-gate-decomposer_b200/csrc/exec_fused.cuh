@@ -43,6 +43,7 @@ enum { MODE_COST = 0, MODE_GRAD = 1, MODE_APPLY = 2, MODE_BWD = 3 };
 
 struct OpTab;
 struct DenseTab;
+struct DenseTab5;
 
 struct ExecArgs {
     const cplx* in;          // input matrix (row-major, leading dimension ld_in)
@@ -67,6 +68,7 @@ struct ExecArgs {
     cplx* beta;              // MODE_BWD: the row functional, same layout and stride as out
     int sum_sq;              // SUM_OF_SQUARES cost: trace slot 0 carries sum |M_ij - delta_ij|^2, beta_N = 2 conj(M - I)
     const struct DenseTab* dense_tabs;  // fragment tables of the raw dense 3-/4-qubit ops (build_dense_tabs), NULL: none
+    const struct DenseTab5* dense_tabs5;  // ... of the 5-qubit ops
     int k_shared;            // 1: every blockIdx.y uses kernel-table set 0 (materialised derivative: one parameter set)
     const int* deriv_op;     // MODE_APPLY: per blockIdx.y the op whose derivative kernel is applied (NULL: none)
     const int* deriv_slot;   //             and which of its derivative kernels
@@ -521,9 +523,15 @@ struct DenseTab {
     double frag[1024];  // [t * KS + ks][lane], NT * KS <= 32
     int sl[4][32];      // [u][lane]: load/store slot (complex units) of amplitude dep(lane & 3, u) of item lane >> 2
 };
+// 5-qubit kernels: 8 n-tiles x 16 k-steps = 128 fragments per lane do not fit registers; they are read per DMMA from this
+// table through L1 (32 KB, shared by every warp of the SM, coalesced 256 B per warp load)
+struct DenseTab5 {
+    double frag[4096];
+    int sl[8][32];
+};
 
-template <int LOG_CT, int KQ>
-__device__ __forceinline__ void dense_tab_fill(DenseTab* T, int* schoice, const cplx* __restrict__ K, const DevOp& op, int tid, int nthr) {
+template <int LOG_CT, int KQ, typename TAB>
+__device__ __forceinline__ void dense_tab_fill(TAB* T, int* schoice, const cplx* __restrict__ K, const DevOp& op, int tid, int nthr) {
     constexpr int CT = 1 << LOG_CT, LOGG = 3 - LOG_CT, DIM = 1 << KQ, NT = DIM / 4, KS = 2 * NT;
     int Pq[KQ], F[3];
     unsigned qmask = 0;
@@ -587,15 +595,61 @@ __device__ __forceinline__ void dense_tab_fill(DenseTab* T, int* schoice, const 
     for (int e = tid; e < NT * 32; e += nthr) T->sl[e >> 5][e & 31] = slot((e & 31) >> 2, dep(e & 3, e >> 5, ja, jb));
 }
 
+// dtab > 0: 1 + index into the 3-/4-qubit tables; dtab < 0: -1 - index into the 5-qubit tables
 template <int LOG_CT>
-__global__ void build_dense_tabs(const DevOp* __restrict__ ops, int n_ops, const cplx* __restrict__ pool, DenseTab* __restrict__ tabs) {
+__global__ void build_dense_tabs(const DevOp* __restrict__ ops, int n_ops, const cplx* __restrict__ pool, DenseTab* __restrict__ tabs,
+                                 DenseTab5* __restrict__ tabs5) {
     __shared__ int schoice[2];
     const DevOp op = ops[blockIdx.x];
-    if (op.dtab <= 0) return;
+    if (op.dtab == 0) return;
+    if (op.dtab < 0) {
+        dense_tab_fill<LOG_CT, 5>(tabs5 + (-1 - op.dtab), schoice, pool + op.pool_off, op, threadIdx.x, blockDim.x);
+        return;
+    }
     DenseTab* T = tabs + (op.dtab - 1);
     if (op.nq == 3) dense_tab_fill<LOG_CT, 3>(T, schoice, pool + op.pool_off, op, threadIdx.x, blockDim.x);
     else dense_tab_fill<LOG_CT, 4>(T, schoice, pool + op.pool_off, op, threadIdx.x, blockDim.x);
 }
+
+// 5-qubit kernels: 128 DMMA per 8-item batch, kernel fragments streamed from the (L1-resident) table
+template <int LOG_CT>
+__device__ __forceinline__ void dense_dmma_forward5(cplx* sa, const DenseTab5* __restrict__ T, const DevOp& op, int rows, int tid, int nthr) {
+    constexpr int KQ = 5, NT = 8, KS = 16, TH = 4;  // n-tiles are processed in two halves of TH (8 accumulator registers live)
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
+    int sl[NT], q[KQ];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) sl[t] = T->sl[t][lane];
+#pragma unroll
+    for (int j = 0; j < KQ; ++j) q[j] = op.q[j];
+    const int nitems = (rows >> KQ) << LOG_CT;
+    for (int b0 = warp * 8; b0 < nitems; b0 += nwarps * 8) {
+        int base = b0 >> LOG_CT;
+#pragma unroll
+        for (int j = 0; j < KQ; ++j) base = insert_zero(base, q[j]);
+        const int B0 = elem<LOG_CT>(base, 0);
+        cplx x[NT];
+#pragma unroll
+        for (int u = 0; u < NT; ++u) x[u] = sa[B0 ^ sl[u]];
+#pragma unroll 1
+        for (int th = 0; th < NT / TH; ++th) {
+            const double* __restrict__ fr = T->frag + (size_t)th * TH * KS * 32 + lane;
+            cplx d[TH];
+#pragma unroll
+            for (int t = 0; t < TH; ++t) d[t] = czero();
+#pragma unroll
+            for (int u = 0; u < NT; ++u)
+#pragma unroll
+                for (int t = 0; t < TH; ++t) {
+                    dmma_m8n8k4(d[t].x, d[t].y, x[u].x, __ldg(fr + (t * KS + 2 * u) * 32));
+                    dmma_m8n8k4(d[t].x, d[t].y, x[u].y, __ldg(fr + (t * KS + 2 * u + 1) * 32));
+                }
+            // a lane's stores hit the elements it loaded itself (all of them are in x[] by now): no hazard with other lanes
+#pragma unroll
+            for (int t = 0; t < TH; ++t) sa[B0 ^ __ldg(&T->sl[th * TH + t][lane])] = d[t];  // (slot re-read: no dynamic register index)
+        }
+    }
+}
+
 
 template <int LOG_CT, int KQ>
 __device__ __forceinline__ void dense_dmma_forward2(cplx* sa, const DenseTab* __restrict__ T, const DevOp& op, int rows, int tid, int nthr) {
@@ -869,6 +923,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                         }
                         if (nq == 3) dense_dmma_forward2<LOG_CT, 3>(sa, T, op, rows, tid, nthr);
                         else dense_dmma_forward2<LOG_CT, 4>(sa, T, op, rows, tid, nthr);
+                    } else if (use_dmma && A.dense_tabs5 && op.dtab < 0) {
+                        dense_dmma_forward5<LOG_CT>(sa, A.dense_tabs5 + (-1 - op.dtab), op, rows, tid, nthr);
                     } else if (use_dmma) {
                         // 5 qubits: stage the real embedding of K (padded rows) and the local-index -> row-bit pattern
                         const int dimr = 2 * dim, ld = dimr + DMMA_PAD;

@@ -111,8 +111,8 @@ struct Plan {
     std::vector<int> param_slot;     // parameter -> index of its derivative kernel inside that op
     DevBuf dOps, dMembers, dParamOp;
     DevBuf wKtab, wDKtab, wOpTab;    // per-parameter-set kernel tables and DMMA block lookup tables (workspace)
-    DevBuf wDenseTab;                // fragment tables of the raw dense 3-/4-qubit ops (constant kernels): per tile width
-    int n_dense = 0, dense_logct = -1;
+    DevBuf wDenseTab, wDenseTab5;    // fragment tables of the raw dense 3-/4- and 5-qubit ops (constant kernels): per tile width
+    int n_dense = 0, n_dense5 = 0, dense_logct = -1;
     int n_ops = 0, kern_total = 0, dkern_total = 0, w_total = 0, wmax = 4;
     int dense_stage = 0;             // complex elements of kernel staging the executor's generic dense path needs
 };
@@ -362,6 +362,7 @@ int build_window_plan(sqgpu_ctx* c) {
     dst.wmax = src.wmax;
     dst.dense_stage = src.dense_stage;
     dst.n_dense = src.n_dense;
+    dst.n_dense5 = src.n_dense5;
     dst.dense_logct = -1;
     int rc;
     const size_t np1 = std::max<size_t>(dst.param_op.size(), 1);
@@ -634,17 +635,19 @@ int run_optabs(sqgpu_ctx* c, int ysets, int log_ct, cudaStream_t st) {
 // fragment tables of the raw dense 3-/4-qubit ops: constants of (circuit, tile width), rebuilt only when the width changes
 int run_dense_tabs(sqgpu_ctx* c, int log_ct, cudaStream_t st) {
     Plan* P = c->P;
-    if (P->n_dense == 0 || P->dense_logct == log_ct) return SQGPU_OK;
+    if ((P->n_dense == 0 && P->n_dense5 == 0) || P->dense_logct == log_ct) return SQGPU_OK;
     int rc;
-    if ((rc = P->wDenseTab.ensure((size_t)P->n_dense * sizeof(DenseTab)))) return rc;
+    if ((rc = P->wDenseTab.ensure(std::max<size_t>(1, (size_t)P->n_dense) * sizeof(DenseTab)))) return rc;
+    if ((rc = P->wDenseTab5.ensure(std::max<size_t>(1, (size_t)P->n_dense5) * sizeof(DenseTab5)))) return rc;
     const DevOp* ops = P->dOps.as<DevOp>();
     const cplx* pool = c->dPool.as<cplx>();
     DenseTab* tabs = P->wDenseTab.as<DenseTab>();
+    DenseTab5* tabs5 = P->wDenseTab5.as<DenseTab5>();
     switch (log_ct) {
-        case 0: build_dense_tabs<0><<<P->n_ops, 128, 0, st>>>(ops, P->n_ops, pool, tabs); break;
-        case 1: build_dense_tabs<1><<<P->n_ops, 128, 0, st>>>(ops, P->n_ops, pool, tabs); break;
-        case 2: build_dense_tabs<2><<<P->n_ops, 128, 0, st>>>(ops, P->n_ops, pool, tabs); break;
-        default: build_dense_tabs<3><<<P->n_ops, 128, 0, st>>>(ops, P->n_ops, pool, tabs); break;
+        case 0: build_dense_tabs<0><<<P->n_ops, 128, 0, st>>>(ops, P->n_ops, pool, tabs, tabs5); break;
+        case 1: build_dense_tabs<1><<<P->n_ops, 128, 0, st>>>(ops, P->n_ops, pool, tabs, tabs5); break;
+        case 2: build_dense_tabs<2><<<P->n_ops, 128, 0, st>>>(ops, P->n_ops, pool, tabs, tabs5); break;
+        default: build_dense_tabs<3><<<P->n_ops, 128, 0, st>>>(ops, P->n_ops, pool, tabs, tabs5); break;
     }
     c->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -670,6 +673,7 @@ void fill_common_args(const sqgpu_ctx* c, const FusedPlan& p, ExecArgs& a, int r
     a.pool = c->dPool.as<cplx>();
     a.optabs = c->P->wOpTab.as<OpTab>();
     a.dense_tabs = (c->P->n_dense > 0 && c->P->dense_logct == p.log_ct) ? c->P->wDenseTab.as<DenseTab>() : nullptr;
+    a.dense_tabs5 = (c->P->n_dense5 > 0 && c->P->dense_logct == p.log_ct) ? c->P->wDenseTab5.as<DenseTab5>() : nullptr;
     a.dense_stage = c->P->dense_stage;
     a.wmax = c->P->wmax;
     a.w_total = c->P->w_total;
@@ -1156,7 +1160,7 @@ int sqgpu_destroy(sqgpu_handle_t c) {
         DeviceGuard guard(c->device);
         std::lock_guard<std::mutex> lk(c->mtx);
         cudaStreamSynchronize(c->stream);
-        DevBuf* bufs[] = {&c->U, &c->plan2.dOps, &c->plan2.dMembers, &c->plan2.dParamOp, &c->plan2.wKtab, &c->plan2.wDKtab, &c->plan2.wOpTab, &c->plan3.dOps, &c->plan3.dMembers, &c->plan3.dParamOp, &c->plan3.wKtab, &c->plan3.wDKtab, &c->plan3.wOpTab, &c->planW.dOps, &c->planW.dMembers, &c->planW.dParamOp, &c->planW.wKtab, &c->planW.wDKtab, &c->planW.wOpTab, &c->plan2.wDenseTab, &c->plan3.wDenseTab, &c->planW.wDenseTab, &c->dPool, &c->wParams, &c->wTrPart, &c->wWPart,
+        DevBuf* bufs[] = {&c->U, &c->plan2.dOps, &c->plan2.dMembers, &c->plan2.dParamOp, &c->plan2.wKtab, &c->plan2.wDKtab, &c->plan2.wOpTab, &c->plan3.dOps, &c->plan3.dMembers, &c->plan3.dParamOp, &c->plan3.wKtab, &c->plan3.wDKtab, &c->plan3.wOpTab, &c->planW.dOps, &c->planW.dMembers, &c->planW.dParamOp, &c->planW.wKtab, &c->planW.wDKtab, &c->planW.wOpTab, &c->plan2.wDenseTab, &c->plan3.wDenseTab, &c->planW.wDenseTab, &c->plan2.wDenseTab5, &c->plan3.wDenseTab5, &c->planW.wDenseTab5, &c->dPool, &c->wParams, &c->wTrPart, &c->wWPart,
                           &c->wTraces, &c->wOmega, &c->wCost, &c->wGrad, &c->wMat, &c->wDerivIdx, &c->wTraces0,
                           &c->hIndptr, &c->hIndices, &c->hValues};
         for (DevBuf* b : bufs) b->release();
@@ -1222,7 +1226,7 @@ int sqgpu_set_circuit(sqgpu_handle_t c, const sqgpu_gate_desc* gates, int n_gate
         std::vector<DevMember> members;
         std::vector<int> param_op(std::max(n_params, 1), -1), param_slot(std::max(n_params, 1), 0);
         int kern_total = 0, dkern_total = 0, w_total = 0, wmax = 4;
-        int dense_stage = 0, n_dense = 0;
+        int dense_stage = 0, n_dense = 0, n_dense5 = 0;
         std::vector<int> pend;
         unsigned pend_support = 0;
         auto finish_op = [&](DevOp& op) {
@@ -1237,6 +1241,7 @@ int sqgpu_set_circuit(sqgpu_handle_t c, const sqgpu_gate_desc* gates, int n_gate
                 if (op.dim > 16) need = (2 * op.dim) * (2 * op.dim + 4) / 2 + op.dim;
                 else if (op.type == SQGPU_GENERAL && op.dim >= 8) need = (int)(sizeof(DenseTab) / sizeof(cplx)) + 1;  // DMMA fragment table
                 if (op.type == SQGPU_GENERAL && op.ctrl_mask == 0 && (op.nq == 3 || op.nq == 4)) op.dtab = ++n_dense;
+                if (op.type == SQGPU_GENERAL && op.ctrl_mask == 0 && op.nq == 5) op.dtab = -(++n_dense5);
                 dense_stage = std::max(dense_stage, need);
             }
             if (op.n_params > 0) {
@@ -1341,6 +1346,7 @@ int sqgpu_set_circuit(sqgpu_handle_t c, const sqgpu_gate_desc* gates, int n_gate
         out.wmax = wmax;
         out.dense_stage = dense_stage;
         out.n_dense = n_dense;
+        out.n_dense5 = n_dense5;
         out.dense_logct = -1;
         return (int)SQGPU_OK;
     };
