@@ -353,6 +353,46 @@ def test_reoptimise_19cnot_circuit_with_lbfgs(sq):
     e.close()
 
 
+def test_edge_cases_tiny_and_empty(sq, port):
+    """1- and 2-qubit registers, a circuit without gates, a circuit without parameters, a single column, batch of one and
+    an empty batch -- the degenerate shapes of every entry point"""
+    # empty circuit on 2 qubits: cost of U against the identity, no gradient entries
+    U = H.random_unitary(4)
+    e = sq.Engine(0)
+    e.upload_matrix(U)
+    e.set_circuit(sq.Circuit(2))
+    e.set_cost(0, 0)
+    f = e.cost_batched(np.zeros((2, 0)))
+    assert np.allclose(f, 1.0 - np.trace(U).real / 4, rtol=0, atol=1e-14)
+    f2, g2 = e.cost_grad_batched(np.zeros((1, 0)))
+    assert abs(f2[0] - f[0]) < 1e-14 and np.asarray(g2).size == 0
+    assert np.asarray(e.cost_batched(np.zeros((0, 0)))).size == 0
+    e.close()
+    # one qubit, every 1-qubit parametric gate; parameter-free circuit on 2 qubits; single column
+    for n, build in ((1, lambda c: (c.add_U3(0), c.add_RZ(0), c.add_H(0), c.add_RY(0))),
+                     (2, lambda c: (c.add_H(0), c.add_CNOT(1, 0), c.add_SX(1), c.add_SWAP([0, 1]))),
+                     (2, lambda c: (c.add_U3(1), c.add_CRY(0, 1), c.add_RXX([0, 1])))):
+        c = sq.Circuit(n)
+        build(c)
+        d, pool = c.descriptors()
+        P = c.get_Parameter_Num()
+        p = H.random_params(max(P, 1), seed=4)[:P]
+        for cols in (1 << n, 1):
+            Um = H.random_unitary(1 << n)[:, :cols].copy()
+            got = Um.copy()
+            c.apply_to(p, got)
+            assert np.abs(got - port.apply_circuit(d, p, Um, pool)).max() < ENTRY_TOL
+            dec = sq.N_Qubit_Decomposition_custom(Um)
+            dec.set_Gate_Structure(c)
+            for variant in (0, 3):
+                dec.set_Cost_Function_Variant(variant)
+                f, g = dec.Optimization_Problem_Combined(p)
+                f_ref, g_ref = port.cost_grad(d, P, p, Um, n, variant, pool=pool)
+                assert close_rel(f, f_ref)
+                if P:
+                    assert close_rel(g, g_ref)
+
+
 def test_reference_wrapper_flow(sq, port):
     """the call sequence of the reference's own test (tests/decomposition/test_optmization_problem_combined.py:189-219)"""
     n, levels = 5, 2
