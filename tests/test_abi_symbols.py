@@ -91,3 +91,17 @@ def test_circuit_descriptors_and_parameter_layout():
     assert [x for x in dn["type"] if x < 1000] == list(d["type"])
     c10 = H.adaptive_circuit(10, 4)
     assert (len(c10.descriptors()[0]), c10.get_Parameter_Num()) == (550, 1290)
+
+
+def test_plain_c_client_compiles_and_links(tmp_path):
+    """tests/c_abi/abi_client.c is a C11 program that uses nothing but include/sqgpu.h: the boundary carries no C++ or
+    torch types (it is what a reference-side shim would be built against)"""
+    import os
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "sequential-quantum-gate-decomposer_b200", "csrc")
+    exe = str(tmp_path / "abi_client")
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Werror", "-I" + os.path.join(root, "include"), "-o", exe,
+                           os.path.join(root, "tests", "c_abi", "abi_client.c"), "-L" + libdir, "-lsqgpu", "-Wl,-rpath," + libdir])
+    assert os.path.exists(exe)

@@ -393,6 +393,47 @@ def test_edge_cases_tiny_and_empty(sq, port):
                     assert close_rel(g, g_ref)
 
 
+def test_plain_c_client_matches_python_binding(sq, port, tmp_path):
+    """the C program tests/c_abi/abi_client.c (include/sqgpu.h only) evaluates cost+gradient through the shared library; the
+    numbers it prints are those of the Python binding (bit for bit) and of the oracle"""
+    import os
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "sequential-quantum-gate-decomposer_b200", "csrc")
+    exe = str(tmp_path / "abi_client")
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-I" + os.path.join(root, "include"), "-o", exe,
+                           os.path.join(root, "tests", "c_abi", "abi_client.c"), "-L" + libdir, "-lsqgpu", "-Wl,-rpath," + libdir])
+    out = subprocess.check_output([exe], text=True)
+    cost, grad = {}, {}
+    for line in out.splitlines():
+        head, *vals = line.split()
+        b = int(head[head.index("[") + 1:head.index("]")])
+        (cost if head.startswith("cost") else grad)[b] = np.array([float(v) for v in vals])
+    c = sq.Circuit(3)
+    c.add_U3(0)
+    c.add_U3(1)
+    c.add_CRY(0, 1)
+    c.add_U3(2)
+    c.add_CNOT(2, 0)
+    c.add_RZ(1)
+    d, pool = c.descriptors()
+    P = c.get_Parameter_Num()
+    assert P == 11
+    U = np.eye(8, dtype=np.complex128)
+    params = np.array([[0.1 * (p + 1) + 0.37 * b for p in range(P)] for b in range(2)])
+    e = sq.Engine(0)
+    e.upload_matrix(U)
+    e.set_circuit(c)
+    e.set_cost(0, 0)
+    f, g = e.cost_grad_batched(params)
+    for b in range(2):
+        assert cost[b][0] == f[b] and (grad[b] == g[b]).all()
+        f_ref, g_ref = port.cost_grad(d, P, params[b], U, 3, 0)
+        assert close_rel(cost[b][0], f_ref) and close_rel(grad[b], g_ref)
+    e.close()
+
+
 def test_reference_wrapper_flow(sq, port):
     """the call sequence of the reference's own test (tests/decomposition/test_optmization_problem_combined.py:189-219)"""
     n, levels = 5, 2
