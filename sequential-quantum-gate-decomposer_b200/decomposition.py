@@ -45,9 +45,18 @@ class N_Qubit_Decomposition_custom:
         self._prev_cost = 1.0  # Optimization_Interface.cpp:74-76
         self._c1 = 1 / 1.7
         self._c2 = 1 / 2.0
-        self._engine = Engine(device)
-        self._engine.upload_matrix(U)
+        # the device context is created with the first evaluation (the gate-structure methods need no GPU); there is
+        # no CPU evaluation path: without a CUDA device that first evaluation raises SqgpuError
+        self._device = int(device)
+        self._engine_obj = None
         self._dirty = True
+
+    @property
+    def _engine(self):
+        if self._engine_obj is None:
+            self._engine_obj = Engine(self._device)
+            self._engine_obj.upload_matrix(self.Umtx)
+        return self._engine_obj
 
     # ---- gate structure -------------------------------------------------------------------------------------
     def set_Gate_Structure(self, circuit):

@@ -105,3 +105,53 @@ def test_plain_c_client_compiles_and_links(tmp_path):
     subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Werror", "-I" + os.path.join(root, "include"), "-o", exe,
                            os.path.join(root, "tests", "c_abi", "abi_client.c"), "-L" + libdir, "-lsqgpu", "-Wl,-rpath," + libdir])
     assert os.path.exists(exe)
+
+
+def test_adaptive_wrapper_structure_without_gpu():
+    """the gate-structure half of the N_Qubit_Decomposition_adaptive mirror needs no device: same sub-block order, qubit roles
+    and parameter layout as the reference's add_adaptive_layers / add_finalyzing_layer
+    (N_Qubit_Decomposition_adaptive.cpp:1840-1881, 1947-1966) -- helpers.adaptive_circuit is the structure the oracle tests
+    pin against the reference -- and P = 7 n (n - 1) / 2 L + 3 n"""
+    import numpy as np
+
+    import helpers as H
+
+    sq = H.sq
+    for n, levels, topology in ((4, 2, None), (5, 1, None), (4, 3, [(0, 1), (1, 2), (2, 3)])):
+        dec = sq.N_Qubit_Decomposition_adaptive(np.eye(1 << n, dtype=np.complex128), level_limit_max=5, level_limit_min=0,
+                                                topology=topology, accelerator_num=1)
+        for _ in range(levels):
+            dec.add_Adaptive_Layers()
+        dec.add_Finalyzing_Layer_To_Gate_Structure()
+        want = H.adaptive_circuit(n, levels, topology)
+        d0, _ = dec.get_Circuit().descriptors()
+        d1, _ = want.descriptors()
+        assert d0.tobytes() == d1.tobytes()
+        pairs = len(topology) if topology else n * (n - 1) // 2
+        assert dec.get_Parameter_Num() == 7 * pairs * levels + 3 * n
+    with pytest.raises(Exception):
+        sq.N_Qubit_Decomposition_adaptive(np.eye(4, dtype=np.complex128), accelerator_num=0)  # no CPU path in this package
+
+
+def test_evaluation_without_device_fails_loudly():
+    """no CPU fallback: on a box without a CUDA device the first evaluation raises, it does not compute on the host"""
+    import ctypes
+
+    import numpy as np
+
+    import helpers as H
+
+    sq = H.sq
+    lib = sq.abi.load_library()
+    count = ctypes.c_int(0)
+    rc = lib.sqgpu_device_count(ctypes.byref(count))
+    if rc == 0 and count.value > 0:
+        pytest.skip("a CUDA device is present")
+    dec = sq.N_Qubit_Decomposition_custom(np.eye(4, dtype=np.complex128))
+    c = sq.Circuit(2)
+    c.add_U3(0)
+    dec.set_Gate_Structure(c)
+    with pytest.raises(sq.abi.SqgpuError):
+        dec.Optimization_Problem(np.zeros(3))
+    with pytest.raises(sq.abi.SqgpuError):
+        c.apply_to(np.zeros(3), np.eye(4, dtype=np.complex128))
