@@ -81,7 +81,7 @@ out["C2_19CNOT/qasm_params"] = p_qasm
 # C3-small: the C3 structure at n = 6 (same generator, seeds of SURVEY.md §8d), all cost variants
 c3 = H.adaptive_circuit(6, 2)
 U3 = np.ascontiguousarray(H.random_unitary(64, seed=123).conj().T)
-add_case("C3_n6", c3, U3, [H.random_params(c3.get_Parameter_Num(), seed=42)], [0, 1, 2, 3, 4, 5, 9], prev=0.37)
+add_case("C3_n6", c3, U3, [H.random_params(c3.get_Parameter_Num(), seed=42)], [0, 1, 2, 3, 4, 5, 6, 9], prev=0.37)
 
 # trace offset / rectangular U (tests/decomposition/test_optmization_problem_combined.py:123-184 at n = 6)
 c4 = H.adaptive_circuit(6, 1)
@@ -93,7 +93,8 @@ add_case("OFFSET_n6", c4, Urect, [p4, H.random_params(c4.get_Parameter_Num(), se
 # every gate family in one circuit: cost/gradient through the decomposition object (no GENERAL gates there: the
 # reference's Gate::clone drops the target qubits of a GENERAL gate, so set_custom_gate_structure cannot carry them)
 c5 = H.random_circuit(5, 60, seed=11)
-add_case("MIXED_n5", c5, H.random_unitary(32, seed=5), [H.random_params(c5.get_Parameter_Num(), seed=12)], [0, 3], with_matrices=True)
+add_case("MIXED_n5", c5, H.random_unitary(32, seed=5), [H.random_params(c5.get_Parameter_Num(), seed=12)], [0, 3, 6], with_matrices=True)
+assert {int(t) for t in c5.descriptors()[0]["type"]} >= {sq.abi.CROT, sq.abi.SYC}  # the two-branch and Sycamore kernels are in
 
 # GENERAL 2/3-qubit blocks mixed with every gate family through Circuit.apply_to, matrix and state-vector input
 c6 = H.random_circuit(5, 60, seed=13, general_k=(2, 3))
