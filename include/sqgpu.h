@@ -152,6 +152,16 @@ int sqgpu_upload_matrix(sqgpu_handle_t h, const double* data, int rows, int cols
 int sqgpu_set_circuit(sqgpu_handle_t h, const sqgpu_gate_desc* gates, int n_gates, int n_params, int qbit_num,
                       const double* matrix_pool, int64_t pool_len);
 
+/* What the host planner makes of a gate structure, WITHOUT a device (no handle): the same lowering, block fusion
+ * (the device analogue of Gates_block's fusion rule, Gates_block.cpp:632-681) and window scheduling that
+ * sqgpu_set_circuit runs. stats[0..SQGPU_PLAN_STATS): ops of the <=2-qubit plan, ops of the <=3-qubit plan, window
+ * segments, ops of the largest segment, window width, complex elements per parameter set of the kernel / derivative-kernel
+ * / W tables of the 3-qubit plan, raw dense 3-5 qubit ops, gates inside fused blocks. Validation errors are the ones
+ * sqgpu_set_circuit reports. */
+#define SQGPU_PLAN_STATS 10
+int sqgpu_plan_stats(const sqgpu_gate_desc* gates, int n_gates, int n_params, int qbit_num, const double* matrix_pool,
+                     int64_t pool_len, int64_t* stats, int n_stats);
+
 /* replaces Optimization_Interface::set_cost_function_variant / set_trace_offset and the members
  * prev_cost_fnv_val, correction1_scale, correction2_scale (Optimization_Interface.h:83-89, .cpp:74-76,1785-1800). */
 int sqgpu_set_cost(sqgpu_handle_t h, int variant, int trace_offset, double prev_cost_fnv_val,

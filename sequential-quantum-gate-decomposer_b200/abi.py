@@ -140,6 +140,7 @@ PROTOTYPES = {
     "sqgpu_abi_version": (C.c_int, []),
     "sqgpu_upload_matrix": (C.c_int, [_handle, _dp, C.c_int, C.c_int, C.c_int]),
     "sqgpu_set_circuit": (C.c_int, [_handle, C.POINTER(GateDesc), C.c_int, C.c_int, C.c_int, _dp, C.c_int64]),
+    "sqgpu_plan_stats": (C.c_int, [C.POINTER(GateDesc), C.c_int, C.c_int, C.c_int, _dp, C.c_int64, C.POINTER(C.c_int64), C.c_int]),
     "sqgpu_set_cost": (C.c_int, [_handle, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]),
     "sqgpu_cost_batched": (C.c_int, [_handle, _dp, C.c_int, _dp]),
     "sqgpu_cost_grad_batched": (C.c_int, [_handle, _dp, C.c_int, _dp, _dp]),
@@ -202,3 +203,22 @@ def as_dp(a):
 
 def as_ip(a):
     return a.ctypes.data_as(_ip)
+
+
+PLAN_STATS = ("ops_plan2", "ops_plan3", "segments", "max_segment_ops", "window", "kern_total", "dkern_total", "w_total",
+              "dense_ops", "block_members")
+
+
+def plan_stats(circuit):
+    """What the host planner of libsqgpu.so makes of a Circuit (sqgpu_plan_stats): needs no CUDA device."""
+    import numpy as np
+
+    lib = load_library()
+    descs, pool = circuit.descriptors()
+    descs = np.ascontiguousarray(descs, dtype=GATE_DESC_DTYPE)
+    pool = np.ascontiguousarray(pool, dtype=np.complex128)
+    out = (C.c_int64 * len(PLAN_STATS))()
+    check(lib, lib.sqgpu_plan_stats(descs.ctypes.data_as(C.POINTER(GateDesc)), len(descs), circuit.get_Parameter_Num(),
+                                    circuit.qbit_num, as_dp(pool.view(np.float64)) if pool.size else None, pool.size, out,
+                                    len(PLAN_STATS)))
+    return dict(zip(PLAN_STATS, (int(v) for v in out)))

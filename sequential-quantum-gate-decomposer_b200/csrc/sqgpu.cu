@@ -296,7 +296,7 @@ int popcount32(unsigned v) {
 // trip per segment instead of one per gate (the reference streams it once per gate,
 // apply_kernel_to_state_vector_input.cpp:33-229). Ops on disjoint qubits commute: an op may be pulled forward when no
 // earlier unscheduled op shares a qubit with it. Qubit indices are rewritten to positions inside the window.
-int build_window_plan(sqgpu_ctx* c) {
+int build_window_plan(sqgpu_ctx* c, bool upload) {
     const Plan& src = c->plan3;
     Plan& dst = c->planW;
     const int N = (int)src.ops.size(), n = c->qbit_num;
@@ -364,6 +364,7 @@ int build_window_plan(sqgpu_ctx* c) {
     dst.n_dense = src.n_dense;
     dst.n_dense5 = src.n_dense5;
     dst.dense_logct = -1;
+    if (!upload) return SQGPU_OK;  // planning only (sqgpu_plan_stats)
     int rc;
     const size_t np1 = std::max<size_t>(dst.param_op.size(), 1);
     if ((rc = dst.dOps.ensure(std::max<size_t>(1, dst.ops.size()) * sizeof(DevOp)))) return rc;
@@ -1188,9 +1189,9 @@ int sqgpu_upload_matrix(sqgpu_handle_t c, const double* data, int rows, int cols
     return SQGPU_OK;
 }
 
-int sqgpu_set_circuit(sqgpu_handle_t c, const sqgpu_gate_desc* gates, int n_gates, int n_params, int qbit_num,
-                      const double* matrix_pool, int64_t pool_len) {
-    if (!c) return fail(SQGPU_ERR_INVALID, "NULL handle");
+// lowering + planning (host only) and, with `upload`, the transfer of the three plans to the device
+static int set_circuit_impl(sqgpu_ctx* c, const sqgpu_gate_desc* gates, int n_gates, int n_params, int qbit_num,
+                            const double* matrix_pool, int64_t pool_len, bool upload) {
     if (n_gates < 0 || n_params < 0 || qbit_num < 1 || qbit_num > 30) return fail(SQGPU_ERR_INVALID, "bad circuit arguments");
     if (n_gates > 0 && !gates) return fail(SQGPU_ERR_INVALID, "gates is NULL");
     // 1. lower every descriptor to a raw op (validation happens here)
@@ -1326,15 +1327,17 @@ int sqgpu_set_circuit(sqgpu_handle_t c, const sqgpu_gate_desc* gates, int n_gate
             finish_op(op);
         }
         flush();
-        int rc;
-        const size_t np1 = std::max(n_params, 1);
-        if ((rc = out.dOps.ensure(std::max<size_t>(1, ops.size()) * sizeof(DevOp)))) return rc;
-        if ((rc = out.dMembers.ensure(std::max<size_t>(1, members.size()) * sizeof(DevMember)))) return rc;
-        if ((rc = out.dParamOp.ensure(2 * np1 * sizeof(int)))) return rc;
-        if (!ops.empty()) CUDA_TRY(cudaMemcpy(out.dOps.p, ops.data(), ops.size() * sizeof(DevOp), cudaMemcpyHostToDevice));
-        if (!members.empty()) CUDA_TRY(cudaMemcpy(out.dMembers.p, members.data(), members.size() * sizeof(DevMember), cudaMemcpyHostToDevice));
-        CUDA_TRY(cudaMemcpy(out.dParamOp.p, param_op.data(), np1 * sizeof(int), cudaMemcpyHostToDevice));
-        CUDA_TRY(cudaMemcpy(out.dParamOp.as<int>() + np1, param_slot.data(), np1 * sizeof(int), cudaMemcpyHostToDevice));
+        if (upload) {
+            int rc;
+            const size_t np1 = std::max(n_params, 1);
+            if ((rc = out.dOps.ensure(std::max<size_t>(1, ops.size()) * sizeof(DevOp)))) return rc;
+            if ((rc = out.dMembers.ensure(std::max<size_t>(1, members.size()) * sizeof(DevMember)))) return rc;
+            if ((rc = out.dParamOp.ensure(2 * np1 * sizeof(int)))) return rc;
+            if (!ops.empty()) CUDA_TRY(cudaMemcpy(out.dOps.p, ops.data(), ops.size() * sizeof(DevOp), cudaMemcpyHostToDevice));
+            if (!members.empty()) CUDA_TRY(cudaMemcpy(out.dMembers.p, members.data(), members.size() * sizeof(DevMember), cudaMemcpyHostToDevice));
+            CUDA_TRY(cudaMemcpy(out.dParamOp.p, param_op.data(), np1 * sizeof(int), cudaMemcpyHostToDevice));
+            CUDA_TRY(cudaMemcpy(out.dParamOp.as<int>() + np1, param_slot.data(), np1 * sizeof(int), cudaMemcpyHostToDevice));
+        }
         out.ops.swap(ops);
         out.members.swap(members);
         out.param_op.swap(param_op);
@@ -1351,26 +1354,51 @@ int sqgpu_set_circuit(sqgpu_handle_t c, const sqgpu_gate_desc* gates, int n_gate
         return (int)SQGPU_OK;
     };
 
-    DeviceGuard guard(c->device);
-    std::lock_guard<std::mutex> lk(c->mtx);
     int rc;
-    if ((rc = c->dPool.ensure(std::max<size_t>(1, (size_t)pool_len) * sizeof(cplx)))) return rc;
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-    if (pool_len > 0) CUDA_TRY(cudaMemcpy(c->dPool.p, matrix_pool, (size_t)pool_len * sizeof(cplx), cudaMemcpyHostToDevice));
+    if (upload) {
+        if ((rc = c->dPool.ensure(std::max<size_t>(1, (size_t)pool_len) * sizeof(cplx)))) return rc;
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        if (pool_len > 0) CUDA_TRY(cudaMemcpy(c->dPool.p, matrix_pool, (size_t)pool_len * sizeof(cplx), cudaMemcpyHostToDevice));
+    }
     c->circuit_set = false;
     if ((rc = build_plan(2, c->plan2))) return rc;
     const char* mq = getenv("SQGPU_MAX_FUSE_QUBITS");
     const int max_q3 = (mq && mq[0] == '2') ? 2 : 3;
     if ((rc = build_plan(max_q3, c->plan3))) return rc;
     c->qbit_num = qbit_num;
-    if ((rc = build_window_plan(c))) return rc;
+    if ((rc = build_window_plan(c, upload))) return rc;
     c->P = &c->plan2;
     c->n_gates = n_gates;
     c->n_params = n_params;
     c->qbit_num = qbit_num;
     c->all_unitary = all_unitary;
-    c->circuit_set = true;
+    c->circuit_set = upload;
     return SQGPU_OK;
+}
+
+int sqgpu_set_circuit(sqgpu_handle_t c, const sqgpu_gate_desc* gates, int n_gates, int n_params, int qbit_num,
+                      const double* matrix_pool, int64_t pool_len) {
+    if (!c) return fail(SQGPU_ERR_INVALID, "NULL handle");
+    DeviceGuard guard(c->device);
+    std::lock_guard<std::mutex> lk(c->mtx);
+    return set_circuit_impl(c, gates, n_gates, n_params, qbit_num, matrix_pool, pool_len, true);
+}
+
+int sqgpu_plan_stats(const sqgpu_gate_desc* gates, int n_gates, int n_params, int qbit_num, const double* matrix_pool,
+                     int64_t pool_len, int64_t* stats, int n_stats) {
+    if (!stats || n_stats < 0) return fail(SQGPU_ERR_INVALID, "NULL stats");
+    sqgpu_ctx* tmp = new sqgpu_ctx();  // never touches a device: no stream, no allocations
+    const int rc = set_circuit_impl(tmp, gates, n_gates, n_params, qbit_num, matrix_pool, pool_len, false);
+    if (rc == SQGPU_OK) {
+        int max_seg = 0;
+        for (const auto& sg : tmp->segs) max_seg = std::max(max_seg, sg.end - sg.begin);
+        const int64_t v[SQGPU_PLAN_STATS] = {tmp->plan2.n_ops, tmp->plan3.n_ops, (int64_t)tmp->segs.size(), max_seg, tmp->win_w,
+                                             tmp->plan3.kern_total, tmp->plan3.dkern_total, tmp->plan3.w_total,
+                                             tmp->plan3.n_dense + tmp->plan3.n_dense5, (int64_t)tmp->plan3.members.size()};
+        for (int i = 0; i < n_stats && i < SQGPU_PLAN_STATS; ++i) stats[i] = v[i];
+    }
+    delete tmp;
+    return rc;
 }
 
 int sqgpu_set_cost(sqgpu_handle_t c, int variant, int trace_offset, double prev_cost_fnv_val, double correction1_scale,

@@ -155,3 +155,43 @@ def test_evaluation_without_device_fails_loudly():
         dec.Optimization_Problem(np.zeros(3))
     with pytest.raises(sq.abi.SqgpuError):
         c.apply_to(np.zeros(3), np.eye(4, dtype=np.complex128))
+
+
+def test_host_planner_without_gpu(monkeypatch):
+    """sqgpu_plan_stats runs the library's own lowering, block fusion and window scheduling without a device: the numbers
+    DESIGN.md quotes, and the validation errors of sqgpu_set_circuit"""
+    import numpy as np
+
+    import helpers as H
+
+    sq = H.sq
+    st = sq.abi.plan_stats(H.adaptive_circuit(10, 4))  # C3: 550 gates, P = 1290
+    assert st["ops_plan2"] == 185 and st["ops_plan3"] == 100 and st["block_members"] == 550 and st["dense_ops"] == 0
+    assert st["w_total"] == st["kern_total"]  # every op of this structure carries parameters: one W accumulator per kernel
+    assert st["segments"] == 1 and st["window"] == 10
+    st = sq.abi.plan_stats(H.hea_zyz_circuit(20, 10))  # C5: 1330 gates
+    assert st["block_members"] == 1330 and st["window"] == 10 and st["segments"] == 20 and st["ops_plan3"] == 100
+    monkeypatch.setenv("SQGPU_WINDOW", "12")
+    assert sq.abi.plan_stats(H.hea_zyz_circuit(20, 10))["segments"] < 20
+    monkeypatch.setenv("SQGPU_WINDOW", "4")
+    c = H.random_circuit(7, 80, seed=5, general_k=(2, 3))
+    st = sq.abi.plan_stats(c)
+    assert st["segments"] > 1 and st["max_segment_ops"] >= 1 and st["dense_ops"] == 3
+    monkeypatch.setenv("SQGPU_NO_FUSE", "1")
+    st = sq.abi.plan_stats(c)
+    assert st["ops_plan2"] == st["ops_plan3"] == len(c.descriptors()[0]) and st["block_members"] == 0
+    monkeypatch.delenv("SQGPU_NO_FUSE")
+    # validation: the same errors sqgpu_set_circuit raises
+    bad = sq.Circuit(3)
+    bad.add_U3(0)
+    d, pool = bad.descriptors()
+    lib = sq.abi.load_library()
+    import ctypes as C
+
+    out = (C.c_int64 * 10)()
+    d2 = d.copy()
+    d2["target"][0] = 5  # qubit out of range
+    assert lib.sqgpu_plan_stats(d2.ctypes.data_as(C.POINTER(sq.abi.GateDesc)), 1, 3, 3, None, 0, out, 10) == sq.abi.ERR_INVALID
+    assert b"out of range" in lib.sqgpu_last_error()
+    assert lib.sqgpu_plan_stats(d.ctypes.data_as(C.POINTER(sq.abi.GateDesc)), 1, 4, 3, None, 0, out, 10) == sq.abi.ERR_INVALID
+    assert b"not used by any gate" in lib.sqgpu_last_error()
