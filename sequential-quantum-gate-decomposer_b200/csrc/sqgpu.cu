@@ -301,37 +301,97 @@ int build_window_plan(sqgpu_ctx* c, bool upload) {
     Plan& dst = c->planW;
     const int N = (int)src.ops.size(), n = c->qbit_num;
     const char* we = getenv("SQGPU_WINDOW");
-    const int w = std::max(1, std::min(n, we ? atoi(we) : 10));
+    const int w = std::max(1, std::min(n, we ? atoi(we) : 11));
     c->win_w = w;
     c->segs.clear();
     std::vector<unsigned> sup(N);
     for (int k = 0; k < N; ++k) sup[k] = support_mask(src.ops[k]);
-    std::vector<char> done(N, 0);
-    std::vector<int> order, newidx(N, -1);
-    int remaining = N, first = 0;
-    while (remaining > 0) {
-        sqgpu_ctx::Segment sg;
-        sg.begin = (int)order.size();
-        unsigned S = 0, blocked = 0;
-        for (int k = first; k < N; ++k) {
+    // Scheduling. A segment is defined by its window W (w qubits): it takes, in program order, every unscheduled op that
+    // lies inside W and shares no qubit with an earlier op left behind. Two schedules are built and the shorter one kept:
+    //   (a) first fit: W grows with the ops as they come (pads with the highest free qubits);
+    //   (b) best of several candidate windows per segment -- every contiguous range of w qubits (nearest-neighbour
+    //       ansatz circuits: HEA n = 20 needs 15 instead of 20 segments at w = 10), the first-fit set, and first-fit sets
+    //       seeded with each of the first few ready ops -- scored by the number of ops they admit.
+    auto pad = [&](unsigned S) {
+        for (int q = n - 1; q >= 0 && popcount32(S) < w; --q) S |= 1u << q;
+        return S;
+    };
+    auto admitted = [&](unsigned W, const std::vector<char>& done, std::vector<int>* got) {
+        unsigned blocked = 0;
+        int cnt = 0;
+        for (int k = 0; k < N; ++k) {
             if (done[k]) continue;
-            if ((sup[k] & blocked) == 0 && popcount32(S | sup[k]) <= w) {
-                done[k] = 1;
-                newidx[k] = (int)order.size();
-                order.push_back(k);
-                S |= sup[k];
-                --remaining;
+            if ((sup[k] & blocked) == 0 && (sup[k] & ~W) == 0) {
+                ++cnt;
+                if (got) got->push_back(k);
             } else {
                 blocked |= sup[k];
             }
         }
-        while (first < N && done[first]) ++first;
-        if ((int)order.size() == sg.begin) return fail(SQGPU_ERR_UNSUPPORTED, "window planner made no progress (op support wider than the window)");
-        for (int q = n - 1; q >= 0 && popcount32(S) < w; --q) S |= 1u << q;  // pad the window with the highest free qubits
-        sg.end = (int)order.size();
-        sg.wmask = S;
-        c->segs.push_back(sg);
+        return cnt;
+    };
+    auto first_fit_set = [&](const std::vector<char>& done, int seed) {
+        unsigned S = seed >= 0 ? sup[seed] : 0u, blocked = 0;
+        for (int k = 0; k < N; ++k) {
+            if (done[k]) continue;
+            if ((sup[k] & blocked) == 0 && popcount32(S | sup[k]) <= w) S |= sup[k];
+            else blocked |= sup[k];
+        }
+        return pad(S);
+    };
+    auto schedule = [&](bool candidates, std::vector<int>& order, std::vector<sqgpu_ctx::Segment>& segs) {
+        std::vector<char> done(N, 0);
+        int remaining = N;
+        order.clear();
+        segs.clear();
+        while (remaining > 0) {
+            unsigned bestW = first_fit_set(done, -1);
+            int best = admitted(bestW, done, nullptr);
+            if (candidates) {
+                std::vector<unsigned> cand;
+                for (int a = 0; a + w <= n; ++a) cand.push_back(((w >= 32 ? 0u : (1u << w)) - 1u) << a);
+                unsigned blocked = 0;
+                int seeds = 0;
+                for (int k = 0; k < N && seeds < 8; ++k) {
+                    if (done[k]) continue;
+                    if ((sup[k] & blocked) == 0) {
+                        cand.push_back(first_fit_set(done, k));
+                        ++seeds;
+                    }
+                    blocked |= sup[k];
+                }
+                for (unsigned W : cand) {
+                    const int cnt = admitted(W, done, nullptr);
+                    if (cnt > best) {
+                        best = cnt;
+                        bestW = W;
+                    }
+                }
+            }
+            if (best <= 0) return false;
+            sqgpu_ctx::Segment sg;
+            sg.begin = (int)order.size();
+            std::vector<int> got;
+            admitted(bestW, done, &got);
+            for (int k : got) {
+                done[k] = 1;
+                order.push_back(k);
+            }
+            remaining -= (int)got.size();
+            sg.end = (int)order.size();
+            sg.wmask = bestW;
+            segs.push_back(sg);
+        }
+        return true;
+    };
+    std::vector<int> order, order_b, newidx(N, -1);
+    std::vector<sqgpu_ctx::Segment> segs_b;
+    if (!schedule(false, order, c->segs)) return fail(SQGPU_ERR_UNSUPPORTED, "window planner made no progress (op support wider than the window)");
+    if (schedule(true, order_b, segs_b) && segs_b.size() < c->segs.size()) {
+        order.swap(order_b);
+        c->segs.swap(segs_b);
     }
+    for (int i = 0; i < N; ++i) newidx[order[i]] = i;
     dst.ops.clear();
     for (const auto& sg : c->segs)
         for (int i = sg.begin; i < sg.end; ++i) {

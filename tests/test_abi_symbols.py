@@ -169,10 +169,10 @@ def test_host_planner_without_gpu(monkeypatch):
     assert st["ops_plan2"] == 185 and st["ops_plan3"] == 100 and st["block_members"] == 550 and st["dense_ops"] == 0
     assert st["w_total"] == st["kern_total"]  # every op of this structure carries parameters: one W accumulator per kernel
     assert st["segments"] == 1 and st["window"] == 10
-    st = sq.abi.plan_stats(H.hea_zyz_circuit(20, 10))  # C5: 1330 gates
-    assert st["block_members"] == 1330 and st["window"] == 10 and st["segments"] == 20 and st["ops_plan3"] == 100
-    monkeypatch.setenv("SQGPU_WINDOW", "12")
-    assert sq.abi.plan_stats(H.hea_zyz_circuit(20, 10))["segments"] < 20
+    st = sq.abi.plan_stats(H.hea_zyz_circuit(20, 10))  # C5: 1330 gates, default window of 11 qubits
+    assert st["block_members"] == 1330 and st["window"] == 11 and st["segments"] == 9 and st["ops_plan3"] == 100
+    monkeypatch.setenv("SQGPU_WINDOW", "10")  # first fit alone needs 20 segments here; the candidate windows 16
+    assert sq.abi.plan_stats(H.hea_zyz_circuit(20, 10))["segments"] == 16
     monkeypatch.setenv("SQGPU_WINDOW", "4")
     c = H.random_circuit(7, 80, seed=5, general_k=(2, 3))
     st = sq.abi.plan_stats(c)

@@ -596,7 +596,7 @@ def test_golden_general_blocks(sq):
 @pytest.mark.parametrize("path", ["window", "window5", "window3", "stream"])
 @pytest.mark.parametrize("n,layers", [(4, 2), (8, 2), (12, 1)])
 def test_vqe_energy_and_gradient(sq, port, monkeypatch, n, layers, path):
-    """windowed shared-memory executor (default window of 10 qubits: one segment for n <= 10, several for n = 12), forced
+    """windowed shared-memory executor (default window of 11 qubits: one segment for n <= 11, several for n = 12), forced
     narrow windows (many segments, 2^(n-w) tile columns) and the one-op-per-launch streaming path"""
     if path == "stream":
         monkeypatch.setenv("SQGPU_VQE_STREAM", "1")
