@@ -89,7 +89,8 @@ typedef enum sqgpu_gate_type {
 } sqgpu_gate_type;
 
 /* Cost-function variants: numerically identical to the reference enum cost_function_type
- * (squander/src-cpp/decomposition/include/Optimization_Interface.h:43-45). */
+ * (squander/src-cpp/decomposition/include/Optimization_Interface.h:43-45). Every variant listed here is implemented on the
+ * device path; the reference's OSR_ENTANGLEMENT (an SVD per cut) and its VQE / GQML tags are not cost variants of this path. */
 typedef enum sqgpu_cost_variant {
     SQGPU_FROBENIUS_NORM = 0,
     SQGPU_FROBENIUS_NORM_CORRECTION1 = 1,
