@@ -701,6 +701,7 @@ struct SOp {
 };
 
 static const int KM_ELEMS = 64;  // prefetched block kernel: up to 8 x 8 complex
+static const int TAB_RING = 4;   // shared-memory ring of op tables: the table of op k + TAB_RING - 1 is requested when op k starts
 
 template <int MODE, int LOG_CT>
 __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A) {
@@ -719,8 +720,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
     cplx* sb = sa + (size_t)rows * CT;                                   // the row functional beta (HAS_B only)
     cplx* sk = HAS_B ? sb + (size_t)rows * CT : sb;                       // raw dense kernel staging
     cplx* skm = sk + A.dense_stage;                                       // [2][KM_ELEMS] prefetched block kernels
-    OpTabS* stab = reinterpret_cast<OpTabS*>(skm + 2 * KM_ELEMS);         // [2] DMMA block lookup tables (one sweep direction)
-    cplx* swarp = reinterpret_cast<cplx*>(stab + 2);                      // [2][nwarps][wmax]
+    OpTabS* stab = reinterpret_cast<OpTabS*>(skm + 2 * KM_ELEMS);         // [TAB_RING] DMMA block lookup tables (one sweep direction)
+    cplx* swarp = reinterpret_cast<cplx*>(stab + TAB_RING);               // [2][nwarps][wmax]
     cplx* swacc = swarp + (HAS_B ? 2 * nwarps * A.wmax : 0);              // [w_total] if w_in_smem
     double* sred = reinterpret_cast<double*>(swacc + ((HAS_B && A.w_in_smem) ? A.w_total : 0));  // [nwarps][6]
     SOp* sops = reinterpret_cast<SOp*>(sred + nwarps * 6);               // [n_ops]
@@ -771,9 +772,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
     // the previous op computes (no registers held across the DMMA loops), into stab[k & 1]
     const OpTab* __restrict__ gtabs = A.optabs + (size_t)kset * (A.optab_stride ? A.optab_stride : A.n_ops);
     auto tab_prefetch = [&](int k, bool bwd) {
-        if (sops[k].kind != 2) return;
+        if (k < 0 || k >= A.n_ops || sops[k].kind != 2) return;
         const char* src = reinterpret_cast<const char*>(gtabs + k);
-        const unsigned dst = (unsigned)__cvta_generic_to_shared(stab + (k & 1));
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(stab + (k & (TAB_RING - 1)));
         constexpr int FRAG = 8 * 32 * 8, TAIL = (int)(sizeof(OpTabS) - 2 * FRAG);  // bytes of one fragment set / of slots + widx
         const int nfrag = bwd ? 2 * FRAG : FRAG, src_off = bwd ? FRAG : 0;
         for (int e = tid; e < (nfrag + TAIL) / 16; e += nthr) {
@@ -783,7 +784,19 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + d_off), "l"(src + s_off));
         }
     };
-    auto tab_wait = [&]() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); };
+    // One cp.async group per op, committed in sweep order (empty for ops without a table). Tables are requested
+    // TAB_RING - 1 ops ahead: when an op ends, "at most TAB_RING - 2 groups pending" means the NEXT op's table has landed
+    // even when the ops are much shorter than an L2 round trip (small matrices: the latency-bound case).
+    auto tab_commit = [&]() { asm volatile("cp.async.commit_group;" ::: "memory"); };
+    auto tab_wait = [&]() { asm volatile("cp.async.wait_group %0;" ::"n"(TAB_RING - 2) : "memory"); };
+    auto tab_prime = [&](int first, int step, bool bwd) {  // requests for the first TAB_RING - 1 ops of a sweep
+#pragma unroll
+        for (int j = 0; j < TAB_RING - 1; ++j) {
+            tab_prefetch(first + j * step, bwd);
+            tab_commit();
+        }
+        tab_wait();
+    };
 
     for (int ti = 0; ti < A.tiles_per_cta; ++ti) {
         const int tile = chunk * A.tiles_per_cta + ti;
@@ -831,10 +844,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
             }
             const int first_op = (MODE == MODE_BWD) ? A.n_ops - 1 : 0;
             if (A.n_ops > 0 && tid < KM_ELEMS) skm[(first_op & 1) * KM_ELEMS + tid] = kernel_elem(first_op);
-            if (A.n_ops > 0) {
-                tab_prefetch(first_op, MODE == MODE_BWD);
-                tab_wait();
-            }
+            if (A.n_ops > 0) tab_prime(first_op, MODE == MODE_BWD ? -1 : 1, MODE == MODE_BWD);
         }
         __syncthreads();
 
@@ -844,17 +854,18 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
             cplx next_elem = czero();
             const bool have_next = k + 1 < A.n_ops;
             if (have_next && tid < KM_ELEMS) next_elem = kernel_elem(k + 1);
-            if (have_next) tab_prefetch(k + 1, false);
+            tab_prefetch(k + TAB_RING - 1, false);
+            tab_commit();
             const cplx* __restrict__ km = skm + (k & 1) * KM_ELEMS;
             if (s.kind == 2) {
                 if (s.dim == 8) {
                     BlockGeom<LOG_CT, 3> G;
                     G.init(s.q0, s.q1, s.q2);
-                    block_dmma_forward<LOG_CT, 3>(sa, stab + (k & 1), G, rows, tid, nthr);
+                    block_dmma_forward<LOG_CT, 3>(sa, stab + (k & (TAB_RING - 1)), G, rows, tid, nthr);
                 } else {
                     BlockGeom<LOG_CT, 2> G;
                     G.init(s.q0, s.q1, 30);
-                    block_dmma_forward<LOG_CT, 2>(sa, stab + (k & 1), G, rows, tid, nthr);
+                    block_dmma_forward<LOG_CT, 2>(sa, stab + (k & (TAB_RING - 1)), G, rows, tid, nthr);
                 }
             } else if (s.kind == 0) {
                 const cplx k00 = km[0], k01 = km[1], k10 = km[2], k11 = km[3];
@@ -1053,10 +1064,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
             // ---- beta_N = sum_t omega_t * sum_{masks of type t} e_{(j+off)^mask} per column ---------------------
             for (int e = tid; e < rows * CT; e += nthr) sb[e] = czero();
             if (A.n_ops > 0 && tid < KM_ELEMS) skm[((A.n_ops - 1) & 1) * KM_ELEMS + tid] = kernel_elem(A.n_ops - 1);
-            if (A.n_ops > 0) {
-                tab_prefetch(A.n_ops - 1, true);
-                tab_wait();
-            }
+            if (A.n_ops > 0) tab_prime(A.n_ops - 1, -1, true);
             __syncthreads();
             if (A.sum_sq) {
                 // the functional of the gradient is Re sum conj(Upartial_ij) dM_ij with Upartial = 2 (M - I)
@@ -1100,7 +1108,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                 cplx next_elem = czero();
                 const bool have_next = k > 0;
                 if (have_next && tid < KM_ELEMS) next_elem = kernel_elem(k - 1);
-                if (have_next) tab_prefetch(k - 1, true);
+                tab_prefetch(k - (TAB_RING - 1), true);
+                tab_commit();
                 const bool has_w = s.w_off >= 0;
                 cplx* wslot_c = swarp + (size_t)(buf * nwarps + warp) * A.wmax;
                 double* wslot = reinterpret_cast<double*>(wslot_c);
@@ -1110,11 +1119,11 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                     if (s.dim == 8) {
                         BlockGeom<LOG_CT, 3> G;
                         G.init(s.q0, s.q1, s.q2);
-                        block_dmma_backward<LOG_CT, 3>(sa, sb, stab + (k & 1), G, rows, has_w, wslot_c, tid, nthr);
+                        block_dmma_backward<LOG_CT, 3>(sa, sb, stab + (k & (TAB_RING - 1)), G, rows, has_w, wslot_c, tid, nthr);
                     } else {
                         BlockGeom<LOG_CT, 2> G;
                         G.init(s.q0, s.q1, 30);
-                        block_dmma_backward<LOG_CT, 2>(sa, sb, stab + (k & 1), G, rows, has_w, wslot_c, tid, nthr);
+                        block_dmma_backward<LOG_CT, 2>(sa, sb, stab + (k & (TAB_RING - 1)), G, rows, has_w, wslot_c, tid, nthr);
                     }
                 } else if (s.kind == 0) {
                     const cplx k00 = km[0], k01 = km[1], k10 = km[2], k11 = km[3];

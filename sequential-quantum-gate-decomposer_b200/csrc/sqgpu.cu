@@ -555,7 +555,7 @@ size_t fused_smem(int mode, int rows, int ct, int threads, int dense_stage, int 
     size_t s = (size_t)rows * ct * sizeof(cplx) * (has_b ? 2 : 1);
     s += (size_t)dense_stage * sizeof(cplx);
     s += 2 * KM_ELEMS * sizeof(cplx);        // prefetched block kernels
-    s += 2 * sizeof(OpTabS);                 // DMMA block lookup tables of one sweep direction (double-buffered)
+    s += TAB_RING * sizeof(OpTabS);          // ring of DMMA block lookup tables of one sweep direction
     s += (size_t)n_ops * sizeof(SOp);        // staged op table
     const int nwarps = threads / 32;
     if (has_b) {
@@ -602,19 +602,21 @@ FusedPlan plan_fused(const sqgpu_ctx* c, int mode, int rows, int cols, int ysets
     {
         const char* sp = getenv("SQGPU_SPLIT");
         const int split = sp ? atoi(sp) : default_split;
-        int lc = pick, thr = pick_threads, ways = 1;
-        while (ways < split && lc > 0 && thr >= 128 && (thr >= 256 || split > 4)) {
-            --lc;
-            thr /= 2;
-            ways *= 2;
-        }
-        if (ways > 1) {
+        const char* fc = getenv("SQGPU_SPLIT_FORCE");
+        for (int want = split; want >= 2; want /= 2) {  // the most CTAs per SM that fit, then fewer
+            int lc = pick, thr = pick_threads, ways = 1;
+            while (ways < want && lc > 0 && thr >= 128 && (thr >= 256 || want > 4)) {
+                --lc;
+                thr /= 2;
+                ways *= 2;
+            }
+            if (ways < 2) break;
             const size_t sm = fused_smem(mode, rows, 1 << lc, thr, c->P->dense_stage, c->P->wmax, c->P->w_total, false, c->P->n_ops);
-            const char* fc = getenv("SQGPU_SPLIT_FORCE");
             if ((fc && fc[0] == '1') || ((sm + 1024) * ways <= (size_t)c->smem_per_sm && thr * ways * 128 <= 65536)) {
                 pick = lc;
                 pick_threads = thr;
                 pick_wsm = false;
+                break;
             }
         }
     }
