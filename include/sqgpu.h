@@ -17,7 +17,9 @@
  *    (the reference throws std::string, Gate.cpp:435-446; the host shim rethrows it -- see INTEGRATION.md).
  *  - host pointers are borrowed for the duration of the call only; the library owns all device memory.
  *  - a handle is bound to one CUDA device; calls on one handle are serialised by an internal mutex
- *    (the DFE bridge serialises with a rw-mutex, common_DFE.cpp:33,61-68).
+ *    (the DFE bridge serialises with a rw-mutex, common_DFE.cpp:33,61-68), and the work they enqueue is ordered on
+ *    the device too: every call makes its stream wait for the previous call's work, whatever stream that used, so
+ *    the handle's workspaces are never shared by two calls in flight; uploads block until the handle is idle.
  *  - there is NO CPU fallback: without a usable CUDA device every compute entry point fails with
  *    SQGPU_ERR_NO_DEVICE.
  */
@@ -30,7 +32,7 @@
 extern "C" {
 #endif
 
-#define SQGPU_ABI_VERSION 1
+#define SQGPU_ABI_VERSION 2
 
 typedef enum sqgpu_status {
     SQGPU_OK = 0,
@@ -162,6 +164,25 @@ int sqgpu_set_circuit(sqgpu_handle_t h, const sqgpu_gate_desc* gates, int n_gate
 #define SQGPU_PLAN_STATS 10
 int sqgpu_plan_stats(const sqgpu_gate_desc* gates, int n_gates, int n_params, int qbit_num, const double* matrix_pool,
                      int64_t pool_len, int64_t* stats, int n_stats);
+/* the same with planner options, "name=value,name=value" (names of sqgpu_set_option), NULL = defaults */
+int sqgpu_plan_stats_opt(const sqgpu_gate_desc* gates, int n_gates, int n_params, int qbit_num, const double* matrix_pool,
+                         int64_t pool_len, const char* options, int64_t* stats, int n_stats);
+
+/* Per-handle switches; the defaults are the product configuration. They are what the reference keeps in its `config` map
+ * (Decomposition_Base::config, e.g. "use_float", "parallel"; Decomposition_Base.cpp:1115-1190) for this path. Planner
+ * options take effect with the next sqgpu_set_circuit. Names:
+ *   no_fuse (0/1)          every gate stays its own op (parity tests cover the raw-op paths of the executor with it)
+ *   max_fuse_qubits (2/3)  widest fused block of the shared-memory executor
+ *   fuse_consecutive (0/1) fuse runs of consecutive gates only (no commuting reorder)
+ *   force_stream (0/1)     cost / gradient through the one-op-per-launch streaming executor
+ *   vqe_stream (0/1)       VQE through the streaming kernels instead of the windowed executor
+ *   window (1..30)         window width of the state-vector / tall-matrix segment planner (default 11)
+ *   tall_window (0/1)      matrices whose column does not fit shared memory go through the windowed executor (default 1)
+ *   async_tiles (0/1)      windowed executor loads / stores its tiles with the bulk-async (TMA) pipeline (default 1)
+ *   split, split_force, threads, ctas_per_sm   CTA-shape experiments of the launch planner
+ *   verbose (0/1) */
+int sqgpu_set_option(sqgpu_handle_t h, const char* name, int64_t value);
+int sqgpu_get_option(sqgpu_handle_t h, const char* name, int64_t* value);
 
 /* replaces Optimization_Interface::set_cost_function_variant / set_trace_offset and the members
  * prev_cost_fnv_val, correction1_scale, correction2_scale (Optimization_Interface.h:83-89, .cpp:74-76,1785-1800). */
@@ -183,7 +204,7 @@ int sqgpu_cost_grad_batched(sqgpu_handle_t h, const double* params, int batch, d
  * ranks, then calls sqgpu_cost_from_traces). Mirrors the {trace, correction1, correction2} triple calcqgdKernelDFE
  * returns per gate set (Optimization_Interface.cpp:806-832). Layout: traces[b][k][t][2], k = 0 the circuit itself,
  * k = 1..P the P derivatives (only if with_grad), t < 3 = {main diagonal, one-bit-flip, two-bit-flip sums}, {re, im}.
- * `cols_total` written = local column count (the normalisation the cost formulas use is the summed one). */
+ * The normalisation of the cost formulas (the summed column count) is applied by sqgpu_cost_from_traces. */
 int sqgpu_traces_batched(sqgpu_handle_t h, const double* params, int batch, int with_grad, double* traces);
 
 /* cost (and gradient if grad != NULL) from (possibly rank-summed) trace terms; cols_total = summed column count. */
@@ -237,15 +258,20 @@ int sqgpu_apply_gate_dev(sqgpu_handle_t h, const sqgpu_gate_desc* gate, const do
                          const double* matrix_pool, int deriv_param, double* d_inout, int rows, int cols, int stride,
                          void* stream);
 int sqgpu_vqe_energy_batched_dev(sqgpu_handle_t h, const double* d_params, int batch, double* d_energy, void* stream);
+int sqgpu_vqe_energy_grad_batched_dev(sqgpu_handle_t h, const double* d_params, int batch, double* d_energy, double* d_grad,
+                                      void* stream);
 
 /* ---- introspection for bench.py / tests -------------------------------------------------------------------- */
 
 /* number of kernels this library has launched on the handle since creation (bench.py's gpu_launches). */
 int sqgpu_launch_count(sqgpu_handle_t h, int64_t* count);
 
-/* name and average device time (ms, CUDA events on the launching stream) of the dominant kernel of the last
- * batched evaluation -- bench.py's roofline numerator. name_len includes the terminating NUL. */
+/* name and average device time (ms, CUDA events on the launching stream) of the kernel that took the most device time since
+ * the last call -- bench.py's roofline numerator; resets every per-kernel event ring. name_len includes the terminating NUL. */
 int sqgpu_last_kernel_time(sqgpu_handle_t h, char* name, int name_len, double* ms, int* launches);
+/* the same for one kernel by name ("fused_exec<GRAD>", "fused_exec<WINDOW_FWD>", "fused_exec<WINDOW_BWD>", "gate1q_stream", ...);
+ * resets that ring only. launches = 0: the kernel has not run since the last reset. */
+int sqgpu_kernel_time(sqgpu_handle_t h, const char* name, double* ms, int* launches);
 
 /* measured FP64 throughput of the handle's device in TFLOP/s: the larger of a DFMA and a DMMA (mma.sync m8n8k4.f64, the
  * instruction the executor's block path issues) burn kernel -- both run on the same pipe. Roofline denominator of the

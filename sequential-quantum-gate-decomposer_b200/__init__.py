@@ -13,10 +13,13 @@ from . import dist
 from .circuit import Circuit
 from .engine import Engine
 from .decomposition import N_Qubit_Decomposition_adaptive, N_Qubit_Decomposition_custom
+from .vqe import Variational_Quantum_Eigensolver
 
 # the reference exports the circuit class under both names (squander/__init__.py)
 qgd_Circuit = Circuit
+qgd_Variational_Quantum_Eigensolver_Base = Variational_Quantum_Eigensolver
 
 __all__ = [
     "abi", "qasm", "dist", "Circuit", "qgd_Circuit", "Engine", "N_Qubit_Decomposition_adaptive", "N_Qubit_Decomposition_custom",
+    "Variational_Quantum_Eigensolver", "qgd_Variational_Quantum_Eigensolver_Base",
 ]

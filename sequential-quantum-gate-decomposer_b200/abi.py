@@ -141,6 +141,9 @@ PROTOTYPES = {
     "sqgpu_upload_matrix": (C.c_int, [_handle, _dp, C.c_int, C.c_int, C.c_int]),
     "sqgpu_set_circuit": (C.c_int, [_handle, C.POINTER(GateDesc), C.c_int, C.c_int, C.c_int, _dp, C.c_int64]),
     "sqgpu_plan_stats": (C.c_int, [C.POINTER(GateDesc), C.c_int, C.c_int, C.c_int, _dp, C.c_int64, C.POINTER(C.c_int64), C.c_int]),
+    "sqgpu_plan_stats_opt": (C.c_int, [C.POINTER(GateDesc), C.c_int, C.c_int, C.c_int, _dp, C.c_int64, C.c_char_p, C.POINTER(C.c_int64), C.c_int]),
+    "sqgpu_set_option": (C.c_int, [_handle, C.c_char_p, C.c_int64]),
+    "sqgpu_get_option": (C.c_int, [_handle, C.c_char_p, C.POINTER(C.c_int64)]),
     "sqgpu_set_cost": (C.c_int, [_handle, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]),
     "sqgpu_cost_batched": (C.c_int, [_handle, _dp, C.c_int, _dp]),
     "sqgpu_cost_grad_batched": (C.c_int, [_handle, _dp, C.c_int, _dp, _dp]),
@@ -160,12 +163,15 @@ PROTOTYPES = {
     "sqgpu_apply_gate_dev": (C.c_int, [_handle, C.POINTER(GateDesc), _dp, _dp, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                       C.c_int, C.c_void_p]),
     "sqgpu_vqe_energy_batched_dev": (C.c_int, [_handle, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "sqgpu_vqe_energy_grad_batched_dev": (C.c_int, [_handle, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sqgpu_kernel_time": (C.c_int, [_handle, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "sqgpu_launch_count": (C.c_int, [_handle, C.POINTER(C.c_int64)]),
     "sqgpu_last_kernel_time": (C.c_int, [_handle, C.c_char_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "sqgpu_fp64_fma_peak": (C.c_int, [_handle, C.POINTER(C.c_double)]),
 }
 
 _lib = None
+ABI_VERSION = 2
 
 
 def load_library(path=None):
@@ -185,7 +191,7 @@ def load_library(path=None):
         fn = getattr(lib, name)  # AttributeError here == header/library mismatch
         fn.restype = res
         fn.argtypes = args
-    if lib.sqgpu_abi_version() != 1:
+    if lib.sqgpu_abi_version() != ABI_VERSION:
         raise RuntimeError("libsqgpu.so ABI version mismatch")
     if path is None:
         _lib = lib
@@ -209,8 +215,9 @@ PLAN_STATS = ("ops_plan2", "ops_plan3", "segments", "max_segment_ops", "window",
               "dense_ops", "block_members")
 
 
-def plan_stats(circuit):
-    """What the host planner of libsqgpu.so makes of a Circuit (sqgpu_plan_stats): needs no CUDA device."""
+def plan_stats(circuit, **options):
+    """What the host planner of libsqgpu.so makes of a Circuit (sqgpu_plan_stats_opt): needs no CUDA device.
+    Keyword arguments are planner options (names of sqgpu_set_option), e.g. ``plan_stats(c, window=10)``."""
     import numpy as np
 
     lib = load_library()
@@ -218,7 +225,8 @@ def plan_stats(circuit):
     descs = np.ascontiguousarray(descs, dtype=GATE_DESC_DTYPE)
     pool = np.ascontiguousarray(pool, dtype=np.complex128)
     out = (C.c_int64 * len(PLAN_STATS))()
-    check(lib, lib.sqgpu_plan_stats(descs.ctypes.data_as(C.POINTER(GateDesc)), len(descs), circuit.get_Parameter_Num(),
-                                    circuit.qbit_num, as_dp(pool.view(np.float64)) if pool.size else None, pool.size, out,
-                                    len(PLAN_STATS)))
+    opts = ",".join("%s=%d" % (k, int(v)) for k, v in options.items()).encode() or None
+    check(lib, lib.sqgpu_plan_stats_opt(descs.ctypes.data_as(C.POINTER(GateDesc)), len(descs), circuit.get_Parameter_Num(),
+                                        circuit.qbit_num, as_dp(pool.view(np.float64)) if pool.size else None, pool.size,
+                                        opts, out, len(PLAN_STATS)))
     return dict(zip(PLAN_STATS, (int(v) for v in out)))

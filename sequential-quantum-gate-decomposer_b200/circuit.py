@@ -34,15 +34,17 @@ class _Gate:
 class Circuit:
     """Ordered gate structure over ``qbit_num`` qubits; gate 0 is applied first (Gates_block.cpp:683-708)."""
 
-    def __init__(self, qbit_num):
+    def __init__(self, qbit_num, device=0):
         qbit_num = int(qbit_num)
         if qbit_num < 1 or qbit_num > 30:
             raise Exception("Circuit: number of qubits should be between 1 and 30")
         self.qbit_num = qbit_num
         self._items = []  # _Gate or Circuit
         self._min_fusion = 14  # Gates_block.cpp:91,113 (kept for API parity; the engine plans its own windows)
+        self._device = int(device)  # CUDA device of the numerical calls (apply_to, get_Matrix, ...)
         self._engine = None
         self._engine_key = None
+        self._version = 0  # bumped by every structural change of THIS block
 
     # ---- structure ------------------------------------------------------------------------------------------
     def _check_q(self, *qs):
@@ -54,7 +56,17 @@ class Circuit:
 
     def _add(self, gate):
         self._items.append(gate)
-        self._engine_key = None
+        self._version += 1
+
+    def structure_key(self):
+        """Changes whenever the gate structure does, nested blocks included (they stay shared with whoever added them, as
+        in Gates_block::add_gate, which stores the pointer): the versions and identities of all blocks, depth first. The
+        device plan of a circuit is rebuilt when this key differs from the one it was built for."""
+        key = [id(self), self._version, len(self._items)]
+        for it in self._items:
+            if isinstance(it, Circuit):
+                key.append(it.structure_key())
+        return tuple(key)
 
     def _add_1q(self, type_, target_qbit):
         self._check_q(int(target_qbit))
@@ -163,8 +175,9 @@ class Circuit:
 
     def get_Flat_Circuit(self):
         """Un-nested copy (Gates_block::get_flat_circuit, Gates_block.cpp:3827-3856)."""
-        c = Circuit(self.qbit_num)
+        c = Circuit(self.qbit_num, self._device)
         c._items = list(self._flat_gates())
+        c._version = 1
         return c
 
     def descriptors(self, nested=False):
@@ -205,9 +218,9 @@ class Circuit:
     def _get_engine(self):
         from .engine import Engine
 
-        key = (len(self._items), self.get_Parameter_Num(), id(self))
+        key = self.structure_key()
         if self._engine is None:
-            self._engine = Engine(0)
+            self._engine = Engine(self._device)
         if self._engine_key != key:
             self._engine.set_circuit(self)
             self._engine_key = key

@@ -75,29 +75,117 @@ struct DevBuf {
     T* as() const { return reinterpret_cast<T*>(p); }
 };
 
-struct KernelTimer {  // CUDA-event timing of the dominant kernel on the launching stream
-    static const int RING = 64;
-    cudaEvent_t e0[RING], e1[RING];
-    int n = 0;
-    bool init = false;
-    std::string name;
-    void ensure() {
-        if (init) return;
-        for (int i = 0; i < RING; ++i) {
-            cudaEventCreate(&e0[i]);
-            cudaEventCreate(&e1[i]);
+struct KernelTimer {  // CUDA-event timing of the library's dominant kernels on the launching stream, one ring per kernel name
+    static const int RING = 64, NAMES = 8;
+    struct Ring {
+        std::string name;
+        cudaEvent_t e0[RING], e1[RING];
+        int n = 0;
+        bool init = false;
+    } rings[NAMES];
+    Ring* cur = nullptr;  // ring of the last time_begin
+    Ring* get(const char* name) {
+        int free_slot = -1;
+        for (int i = 0; i < NAMES; ++i) {
+            if (rings[i].init && rings[i].name == name) return &rings[i];
+            if (!rings[i].init && free_slot < 0) free_slot = i;
         }
-        init = true;
+        if (free_slot < 0) free_slot = 0;  // more names than rings: recycle the first
+        Ring& r = rings[free_slot];
+        if (!r.init) {
+            for (int i = 0; i < RING; ++i) {
+                cudaEventCreate(&r.e0[i]);
+                cudaEventCreate(&r.e1[i]);
+            }
+            r.init = true;
+        }
+        if (r.name != name) {
+            r.name = name;
+            r.n = 0;
+        }
+        return &r;
     }
     void destroy() {
-        if (!init) return;
-        for (int i = 0; i < RING; ++i) {
-            cudaEventDestroy(e0[i]);
-            cudaEventDestroy(e1[i]);
+        for (auto& r : rings) {
+            if (!r.init) continue;
+            for (int i = 0; i < RING; ++i) {
+                cudaEventDestroy(r.e0[i]);
+                cudaEventDestroy(r.e1[i]);
+            }
+            r.init = false;
         }
-        init = false;
     }
 };
+
+// Per-handle switches (sqgpu_set_option). Defaults are the product configuration; the others exist for the parity tests
+// (both executor paths are covered) and for kernel experiments. They replace the environment variables of round 1: a
+// setenv in some host thread can no longer change the numerics path of a running handle.
+struct Options {
+    int no_fuse = 0;           // every gate is its own op
+    int max_fuse_qubits = 3;   // widest fused block of plan3 (2 or 3)
+    int fuse_consecutive = 0;  // runs of consecutive gates only (no commuting reorder)
+    int force_stream = 0;      // cost / gradient through the one-op-per-launch streaming executor
+    int vqe_stream = 0;        // VQE through the streaming path instead of the windowed executor
+    int window = 11;           // window width of the state-vector segment planner
+    int split = 0;             // CTAs per SM the fused executor aims for (0: default of the call site)
+    int split_force = 0;
+    int threads = 0;           // cap of the fused executor's CTA size (0: none)
+    int ctas_per_sm = 48;      // grid granularity of the cost / gradient executor
+    int verbose = 0;
+    int tall_window = 1;       // matrices whose column does not fit shared memory: windowed executor (0: streaming fallback)
+    int async_tiles = 1;       // windowed executor: bulk-async (TMA) tile pipeline
+};
+
+typedef int Options::*OptionField;
+struct OptionName { const char* name; OptionField field; long long lo, hi; };
+const OptionName kOptionNames[] = {
+    {"no_fuse", &Options::no_fuse, 0, 1},
+    {"max_fuse_qubits", &Options::max_fuse_qubits, 2, 3},
+    {"fuse_consecutive", &Options::fuse_consecutive, 0, 1},
+    {"force_stream", &Options::force_stream, 0, 1},
+    {"vqe_stream", &Options::vqe_stream, 0, 1},
+    {"window", &Options::window, 1, 30},
+    {"split", &Options::split, 0, 16},
+    {"split_force", &Options::split_force, 0, 1},
+    {"threads", &Options::threads, 0, 1024},
+    {"ctas_per_sm", &Options::ctas_per_sm, 1, 1024},
+    {"verbose", &Options::verbose, 0, 1},
+    {"tall_window", &Options::tall_window, 0, 1},
+    {"async_tiles", &Options::async_tiles, 0, 1},
+};
+
+int option_set(Options& o, const char* name, long long value) {
+    if (!name) return fail(SQGPU_ERR_INVALID, "option name is NULL");
+    for (const auto& on : kOptionNames)
+        if (!strcmp(on.name, name)) {
+            if (value < on.lo || value > on.hi) return fail(SQGPU_ERR_INVALID, "option %s: value %lld outside [%lld, %lld]", name, value, on.lo, on.hi);
+            o.*(on.field) = (int)value;
+            return SQGPU_OK;
+        }
+    return fail(SQGPU_ERR_INVALID, "unknown option '%s'", name);
+}
+
+// "name=value,name=value" (sqgpu_plan_stats_opt)
+int options_parse(Options& o, const char* text) {
+    if (!text) return SQGPU_OK;
+    std::string t(text);
+    size_t pos = 0;
+    while (pos < t.size()) {
+        size_t end = t.find(',', pos);
+        if (end == std::string::npos) end = t.size();
+        const std::string item = t.substr(pos, end - pos);
+        pos = end + 1;
+        if (item.empty()) continue;
+        const size_t eq = item.find('=');
+        if (eq == std::string::npos) return fail(SQGPU_ERR_INVALID, "option '%s': expected name=value", item.c_str());
+        char* endp = nullptr;
+        const long long v = strtoll(item.c_str() + eq + 1, &endp, 10);
+        if (!endp || *endp) return fail(SQGPU_ERR_INVALID, "option '%s': value is not an integer", item.c_str());
+        int rc = option_set(o, item.substr(0, eq).c_str(), v);
+        if (rc) return rc;
+    }
+    return SQGPU_OK;
+}
 
 }  // namespace
 
@@ -157,6 +245,13 @@ struct sqgpu_ctx {
 
     long long launches = 0;
     KernelTimer timer;
+    Options opt;
+
+    // Every entry point that enqueues work records `last_done` on its stream when it returns; the next entry point makes its
+    // own stream wait for it first, so calls on DIFFERENT streams cannot race on the handle's shared workspaces (the mutex
+    // only serialises the host side), and the blocking uploads wait for it before they overwrite device data.
+    cudaEvent_t last_done = nullptr;
+    bool last_valid = false;
 };
 
 namespace {
@@ -172,6 +267,32 @@ struct DeviceGuard {
         cudaGetDevice(&cur);
         if (prev >= 0 && cur != prev) cudaSetDevice(prev);
     }
+};
+
+// Orders this call after the previous one on the handle, whatever streams the two use (see sqgpu_ctx::last_done).
+struct CallScope {
+    sqgpu_ctx* c;
+    cudaStream_t st;
+    CallScope(sqgpu_ctx* c_, cudaStream_t st_) : c(c_), st(st_) {
+        if (c->last_valid) cudaStreamWaitEvent(st, c->last_done, 0);
+    }
+    ~CallScope() {
+        if (c->last_done && cudaEventRecord(c->last_done, st) == cudaSuccess) c->last_valid = true;
+    }
+};
+
+// before a blocking upload overwrites device data: everything enqueued on the handle so far has finished
+void wait_idle(sqgpu_ctx* c) {
+    if (c->last_valid) cudaEventSynchronize(c->last_done);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+}
+
+// restores the handle's current plan when a helper that switches it returns (also on its error paths)
+struct PlanScope {
+    sqgpu_ctx* c;
+    Plan* saved;
+    explicit PlanScope(sqgpu_ctx* c_) : c(c_), saved(c_->P) {}
+    ~PlanScope() { c->P = saved; }
 };
 
 // 16 independent DFMA chains per thread: measures the FP64 pipe, nothing else
@@ -300,8 +421,7 @@ int build_window_plan(sqgpu_ctx* c, bool upload) {
     const Plan& src = c->plan3;
     Plan& dst = c->planW;
     const int N = (int)src.ops.size(), n = c->qbit_num;
-    const char* we = getenv("SQGPU_WINDOW");
-    const int w = std::max(1, std::min(n, we ? atoi(we) : 11));
+    const int w = std::max(1, std::min(n, c->opt.window));
     c->win_w = w;
     c->segs.clear();
     std::vector<unsigned> sup(N);
@@ -569,10 +689,8 @@ size_t fused_smem(int mode, int rows, int ct, int threads, int dense_stage, int 
 
 FusedPlan plan_fused(const sqgpu_ctx* c, int mode, int rows, int cols, int ysets, int default_split = 2) {
     FusedPlan p;
-    {   // test hook: SQGPU_FORCE_STREAM=1 sends cost / gradient evaluations down the chunked streaming executor
-        const char* fs = getenv("SQGPU_FORCE_STREAM");
-        if (fs && fs[0] == '1' && (mode == MODE_COST || mode == MODE_GRAD)) return p;
-    }
+    // test hook (option force_stream): cost / gradient evaluations go down the chunked streaming executor
+    if (c->opt.force_stream && (mode == MODE_COST || mode == MODE_GRAD)) return p;
     const size_t budget = (size_t)c->smem_optin;
     int max_log = 3;
     while ((1 << max_log) > cols && max_log > 0) --max_log;  // no wider than the matrix (cols = 1: state vector)
@@ -600,9 +718,8 @@ FusedPlan plan_fused(const sqgpu_ctx* c, int mode, int rows, int cols, int ysets
     // Columns are independent, so two half-width CTAs per SM do the work of one: while one CTA sits in the barrier /
     // table prologue between two ops, the other keeps the FP64 tensor pipe busy. Taken when both fit in the SM.
     {
-        const char* sp = getenv("SQGPU_SPLIT");
-        const int split = sp ? atoi(sp) : default_split;
-        const char* fc = getenv("SQGPU_SPLIT_FORCE");
+        const int split = c->opt.split > 0 ? c->opt.split : default_split;
+        const bool fc = c->opt.split_force != 0;
         for (int want = split; want >= 2; want /= 2) {  // the most CTAs per SM that fit, then fewer
             int lc = pick, thr = pick_threads, ways = 1;
             while (ways < want && lc > 0 && thr >= 128 && (thr >= 256 || want > 4)) {
@@ -612,7 +729,7 @@ FusedPlan plan_fused(const sqgpu_ctx* c, int mode, int rows, int cols, int ysets
             }
             if (ways < 2) break;
             const size_t sm = fused_smem(mode, rows, 1 << lc, thr, c->P->dense_stage, c->P->wmax, c->P->w_total, false, c->P->n_ops);
-            if ((fc && fc[0] == '1') || ((sm + 1024) * ways <= (size_t)c->smem_per_sm && thr * ways * 128 <= 65536)) {
+            if (fc || ((sm + 1024) * ways <= (size_t)c->smem_per_sm && thr * ways * 128 <= 65536)) {
                 pick = lc;
                 pick_threads = thr;
                 pick_wsm = false;
@@ -620,10 +737,7 @@ FusedPlan plan_fused(const sqgpu_ctx* c, int mode, int rows, int cols, int ysets
             }
         }
     }
-    {
-        const char* te = getenv("SQGPU_THREADS");  // experiment hook: CTA size of the fused executor
-        if (te && atoi(te) >= 64) pick_threads = std::min(pick_threads, atoi(te));
-    }
+    if (c->opt.threads >= 64) pick_threads = std::min(pick_threads, c->opt.threads);  // experiment hook: CTA size
     {
         const int lc = pick, ct = 1 << lc;
         p.ok = true;
@@ -636,8 +750,7 @@ FusedPlan plan_fused(const sqgpu_ctx* c, int mode, int rows, int cols, int ysets
             p.tiles_per_cta = 1;
             p.chunks = p.tiles;
         } else {
-            const char* wc_env = getenv("SQGPU_CTAS_PER_SM");  // experiment hook: grid granularity
-            const int want_ctas = c->sm_count * (wc_env ? std::max(1, atoi(wc_env)) : 48);
+            const int want_ctas = c->sm_count * std::max(1, c->opt.ctas_per_sm);  // grid granularity
             int chunks = std::min(p.tiles, std::max(1, (want_ctas + ysets - 1) / ysets));
             p.tiles_per_cta = (p.tiles + chunks - 1) / chunks;
             p.chunks = (p.tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
@@ -744,13 +857,14 @@ void fill_common_args(const sqgpu_ctx* c, const FusedPlan& p, ExecArgs& a, int r
 }
 
 void time_begin(sqgpu_ctx* c, const char* name, cudaStream_t st) {
-    c->timer.ensure();
-    c->timer.name = name;
-    cudaEventRecord(c->timer.e0[c->timer.n % KernelTimer::RING], st);
+    KernelTimer::Ring* r = c->timer.cur = c->timer.get(name);
+    cudaEventRecord(r->e0[r->n % KernelTimer::RING], st);
 }
 void time_end(sqgpu_ctx* c, cudaStream_t st) {
-    cudaEventRecord(c->timer.e1[c->timer.n % KernelTimer::RING], st);
-    c->timer.n++;
+    KernelTimer::Ring* r = c->timer.cur;
+    if (!r) return;
+    cudaEventRecord(r->e1[r->n % KernelTimer::RING], st);
+    r->n++;
 }
 
 int run_exec_streaming(sqgpu_ctx* c, int batch, bool grad, const cplx* d_omega, double* d_traces, cudaStream_t st);
@@ -816,10 +930,17 @@ int batch_slice(const sqgpu_ctx* c, int batch, bool grad) {
         if (!pf.ok) return std::min(batch, 32);  // streaming fallback: bound the replicated chunk workspace
     }
     if (!grad || c->P->w_total == 0) return std::min(batch, 65535);
-    FusedPlan p = plan_fused(c, MODE_GRAD, c->rows, c->cols, batch);
-    const size_t per = (size_t)std::max(1, p.chunks) * c->P->w_total * sizeof(cplx);
+    // a smaller slice is planned with more chunks per parameter set (the grid is filled either way): iterate to a fixed point
     const size_t lim = (size_t)1536 << 20;
-    return (int)std::max<size_t>(1, std::min<size_t>((size_t)std::min(batch, 65535), lim / std::max<size_t>(per, 1)));
+    int slice = std::min(batch, 65535);
+    for (int it = 0; it < 16; ++it) {
+        const FusedPlan p = plan_fused(c, MODE_GRAD, c->rows, c->cols, slice);
+        const size_t per = (size_t)std::max(1, p.chunks) * c->P->w_total * sizeof(cplx);
+        const int fit = (int)std::max<size_t>(1, std::min<size_t>((size_t)slice, lim / std::max<size_t>(per, 1)));
+        if (fit >= slice) break;
+        slice = fit;
+    }
+    return slice;
 }
 
 // traces for a batch (device pointers). Layout d_traces[batch][n_k][3][2], n_k = 1 + (with_grad ? P : 0).
@@ -1027,14 +1148,11 @@ int apply_program_dev(sqgpu_ctx* c, const cplx* d_in, long long in_ystride, cplx
 // SEGMENT of the window plan instead of one per gate (build_window_plan). Parameters are in c->wParams. Returns 1 when no
 // window plan fits (caller falls back to one op per launch).
 int apply_window_dev(sqgpu_ctx* c, cplx* d_inout, int rows, cudaStream_t st) {
-    Plan* saved = c->P;
+    PlanScope keep(c);
     c->P = &c->planW;
     const int w = c->win_w, wr = 1 << w, wc = rows >> w;
     const FusedPlan pf = plan_fused(c, MODE_APPLY, wr, wc, 1, 4);
-    if (!pf.ok || c->segs.empty()) {
-        c->P = saved;
-        return 1;
-    }
+    if (!pf.ok || c->segs.empty()) return 1;
     int rc;
     if ((rc = run_tables(c, c->wParams.as<double>(), 1, false, st))) return rc;
     if ((rc = run_optabs(c, 1, pf.log_ct, st))) return rc;
@@ -1213,6 +1331,12 @@ int sqgpu_create(int device, sqgpu_handle_t* out) {
         delete c;
         return fail(SQGPU_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
     }
+    e = cudaEventCreateWithFlags(&c->last_done, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        cudaStreamDestroy(c->stream);
+        delete c;
+        return fail(SQGPU_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e));
+    }
     *out = c;
     return SQGPU_OK;
 }
@@ -1222,12 +1346,13 @@ int sqgpu_destroy(sqgpu_handle_t c) {
     {
         DeviceGuard guard(c->device);
         std::lock_guard<std::mutex> lk(c->mtx);
-        cudaStreamSynchronize(c->stream);
+        wait_idle(c);
         DevBuf* bufs[] = {&c->U, &c->plan2.dOps, &c->plan2.dMembers, &c->plan2.dParamOp, &c->plan2.wKtab, &c->plan2.wDKtab, &c->plan2.wOpTab, &c->plan3.dOps, &c->plan3.dMembers, &c->plan3.dParamOp, &c->plan3.wKtab, &c->plan3.wDKtab, &c->plan3.wOpTab, &c->planW.dOps, &c->planW.dMembers, &c->planW.dParamOp, &c->planW.wKtab, &c->planW.wDKtab, &c->planW.wOpTab, &c->plan2.wDenseTab, &c->plan3.wDenseTab, &c->planW.wDenseTab, &c->plan2.wDenseTab5, &c->plan3.wDenseTab5, &c->planW.wDenseTab5, &c->dPool, &c->wParams, &c->wTrPart, &c->wWPart,
                           &c->wTraces, &c->wOmega, &c->wCost, &c->wGrad, &c->wMat, &c->wDerivIdx, &c->wTraces0,
                           &c->hIndptr, &c->hIndices, &c->hValues};
         for (DevBuf* b : bufs) b->release();
         c->timer.destroy();
+        if (c->last_done) cudaEventDestroy(c->last_done);
         cudaStreamDestroy(c->stream);
     }
     delete c;
@@ -1241,6 +1366,7 @@ int sqgpu_upload_matrix(sqgpu_handle_t c, const double* data, int rows, int cols
     if (cols > rows) return fail(SQGPU_ERR_INVALID, "cols (%d) cannot exceed rows (%d)", cols, rows);
     DeviceGuard guard(c->device);
     std::lock_guard<std::mutex> lk(c->mtx);
+    wait_idle(c);
     int rc = c->U.ensure((size_t)rows * cols * sizeof(cplx));
     if (rc) return rc;
     CUDA_TRY(cudaMemcpy2DAsync(c->U.p, (size_t)cols * sizeof(cplx), data, (size_t)stride * sizeof(cplx), (size_t)cols * sizeof(cplx),
@@ -1282,8 +1408,7 @@ static int set_circuit_impl(sqgpu_ctx* c, const sqgpu_gate_desc* gates, int n_ga
     // 2. plan: fuse runs of consecutive gates whose joint support is at most `max_q` qubits into one dense block
     //    (the device-side analogue of Gates_block's <=2-qubit fusion rule, Gates_block.cpp:632-681, applied to the
     //    flattened circuit and extended to the gradient by the product rule in build_block_warp)
-    const char* nf = getenv("SQGPU_NO_FUSE");
-    const bool fuse = !(nf && nf[0] == '1');
+    const bool fuse = !c->opt.no_fuse;
     auto build_plan = [&](int max_q, Plan& out) {
         std::vector<DevOp> ops;
         std::vector<DevMember> members;
@@ -1375,9 +1500,8 @@ static int set_circuit_impl(sqgpu_ctx* c, const sqgpu_gate_desc* gates, int n_ga
         // commute with everything in between, so pulling them forward is a valid reordering; inside a block the program
         // order is kept). The all-pairs adaptive structure closes its triangles this way -- (0,1), (0,2) and the later
         // (1,2) become one 8x8 block -- n = 10, L = 4: 84 ops instead of the 100 of consecutive-run fusion, 17 % fewer
-        // flops per amplitude. SQGPU_FUSE_CONSECUTIVE=1 restores runs of consecutive gates only.
-        const char* fc = getenv("SQGPU_FUSE_CONSECUTIVE");
-        const bool consecutive_only = fc && fc[0] == '1';
+        // flops per amplitude. Option fuse_consecutive restores runs of consecutive gates only.
+        const bool consecutive_only = c->opt.fuse_consecutive != 0;
         const unsigned all_qubits = qbit_num >= 32 ? 0xffffffffu : ((1u << qbit_num) - 1u);
         auto fusable_op = [&](const DevOp& r) {
             return fuse && ((r.dim == 2 && popcount32(r.ctrl_mask) <= 1) || (r.dim == 4 && r.ctrl_mask == 0));
@@ -1450,8 +1574,7 @@ static int set_circuit_impl(sqgpu_ctx* c, const sqgpu_gate_desc* gates, int n_ga
     }
     c->circuit_set = false;
     if ((rc = build_plan(2, c->plan2))) return rc;
-    const char* mq = getenv("SQGPU_MAX_FUSE_QUBITS");
-    const int max_q3 = (mq && mq[0] == '2') ? 2 : 3;
+    const int max_q3 = c->opt.max_fuse_qubits == 2 ? 2 : 3;
     if ((rc = build_plan(max_q3, c->plan3))) return rc;
     c->qbit_num = qbit_num;
     if ((rc = build_window_plan(c, upload))) return rc;
@@ -1469,14 +1592,21 @@ int sqgpu_set_circuit(sqgpu_handle_t c, const sqgpu_gate_desc* gates, int n_gate
     if (!c) return fail(SQGPU_ERR_INVALID, "NULL handle");
     DeviceGuard guard(c->device);
     std::lock_guard<std::mutex> lk(c->mtx);
+    wait_idle(c);
     return set_circuit_impl(c, gates, n_gates, n_params, qbit_num, matrix_pool, pool_len, true);
 }
 
 int sqgpu_plan_stats(const sqgpu_gate_desc* gates, int n_gates, int n_params, int qbit_num, const double* matrix_pool,
                      int64_t pool_len, int64_t* stats, int n_stats) {
+    return sqgpu_plan_stats_opt(gates, n_gates, n_params, qbit_num, matrix_pool, pool_len, nullptr, stats, n_stats);
+}
+
+int sqgpu_plan_stats_opt(const sqgpu_gate_desc* gates, int n_gates, int n_params, int qbit_num, const double* matrix_pool,
+                         int64_t pool_len, const char* options, int64_t* stats, int n_stats) {
     if (!stats || n_stats < 0) return fail(SQGPU_ERR_INVALID, "NULL stats");
     sqgpu_ctx* tmp = new sqgpu_ctx();  // never touches a device: no stream, no allocations
-    const int rc = set_circuit_impl(tmp, gates, n_gates, n_params, qbit_num, matrix_pool, pool_len, false);
+    int rc = options_parse(tmp->opt, options);
+    if (rc == SQGPU_OK) rc = set_circuit_impl(tmp, gates, n_gates, n_params, qbit_num, matrix_pool, pool_len, false);
     if (rc == SQGPU_OK) {
         int max_seg = 0;
         for (const auto& sg : tmp->segs) max_seg = std::max(max_seg, sg.end - sg.begin);
@@ -1503,6 +1633,7 @@ int sqgpu_cost_batched_dev(sqgpu_handle_t c, const double* d_params, int batch, 
     if (batch < 0 || (batch > 0 && (!d_params && c->n_params > 0)) || (batch > 0 && !d_cost)) return fail(SQGPU_ERR_INVALID, "bad arguments");
     DeviceGuard guard(c->device);
     std::lock_guard<std::mutex> lk(c->mtx);
+    CallScope cs(c, (cudaStream_t)stream);
     return eval_dev(c, d_params, batch, false, d_cost, nullptr, (cudaStream_t)stream);
 }
 
@@ -1511,6 +1642,7 @@ int sqgpu_cost_grad_batched_dev(sqgpu_handle_t c, const double* d_params, int ba
     if (batch < 0 || (batch > 0 && (!d_params && c->n_params > 0)) || (batch > 0 && (!d_cost || (!d_grad && c->n_params > 0)))) return fail(SQGPU_ERR_INVALID, "bad arguments");
     DeviceGuard guard(c->device);
     std::lock_guard<std::mutex> lk(c->mtx);
+    CallScope cs(c, (cudaStream_t)stream);
     return eval_dev(c, d_params, batch, true, d_cost, d_grad, (cudaStream_t)stream);
 }
 
@@ -1519,6 +1651,7 @@ int sqgpu_traces_batched_dev(sqgpu_handle_t c, const double* d_params, int batch
     if (batch < 0 || (batch > 0 && !d_traces)) return fail(SQGPU_ERR_INVALID, "bad arguments");
     DeviceGuard guard(c->device);
     std::lock_guard<std::mutex> lk(c->mtx);
+    CallScope cs(c, (cudaStream_t)stream);
     return traces_dev(c, d_params, batch, with_grad != 0, d_traces, (cudaStream_t)stream, false);
 }
 
@@ -1528,6 +1661,7 @@ int sqgpu_cost_from_traces_dev(sqgpu_handle_t c, const double* d_traces, int bat
     if (batch < 0 || cols_total <= 0 || (batch > 0 && (!d_traces || !d_cost))) return fail(SQGPU_ERR_INVALID, "bad arguments");
     DeviceGuard guard(c->device);
     std::lock_guard<std::mutex> lk(c->mtx);
+    CallScope cs(c, (cudaStream_t)stream);
     if (!c->circuit_set) return fail(SQGPU_ERR_STATE, "no circuit set");
     return cost_from_traces_dev(c, d_traces, batch, with_grad != 0, cols_total, d_cost, d_grad, (cudaStream_t)stream);
 }
@@ -1541,6 +1675,7 @@ static int host_eval(sqgpu_handle_t c, const double* params, int batch, bool wit
     if ((!params && c->n_params > 0) || !cost || (with_grad && !grad && c->n_params > 0)) return fail(SQGPU_ERR_INVALID, "NULL buffer");
     DeviceGuard guard(c->device);
     std::lock_guard<std::mutex> lk(c->mtx);
+    CallScope cs(c, c->stream);
     int rc = check_ready(c, true);
     if (rc) return rc;
     const size_t np = (size_t)batch * c->n_params;
@@ -1570,6 +1705,7 @@ int sqgpu_traces_batched(sqgpu_handle_t c, const double* params, int batch, int 
     if ((!params && c->n_params > 0) || !traces) return fail(SQGPU_ERR_INVALID, "NULL buffer");
     DeviceGuard guard(c->device);
     std::lock_guard<std::mutex> lk(c->mtx);
+    CallScope cs(c, c->stream);
     int rc = check_ready(c, true);
     if (rc) return rc;
     const size_t np = (size_t)batch * c->n_params;
@@ -1590,6 +1726,7 @@ int sqgpu_cost_from_traces(sqgpu_handle_t c, const double* traces, int batch, in
     if (!traces || !cost || (with_grad && !grad && c->n_params > 0)) return fail(SQGPU_ERR_INVALID, "NULL buffer");
     DeviceGuard guard(c->device);
     std::lock_guard<std::mutex> lk(c->mtx);
+    CallScope cs(c, c->stream);
     if (!c->circuit_set) return fail(SQGPU_ERR_STATE, "no circuit set");
     int rc;
     const size_t np = (size_t)batch * c->n_params;
@@ -1611,6 +1748,7 @@ int sqgpu_apply(sqgpu_handle_t c, const double* params, double* inout, int rows,
     if (!inout || rows <= 0 || cols <= 0 || stride < cols) return fail(SQGPU_ERR_INVALID, "bad matrix arguments");
     DeviceGuard guard(c->device);
     std::lock_guard<std::mutex> lk(c->mtx);
+    CallScope cs(c, c->stream);
     c->P = &c->plan2;  // apply paths: two-qubit blocks (the streaming kernels stop there)
     int rc = check_ready(c, false);
     if (rc) return rc;
@@ -1640,6 +1778,7 @@ int sqgpu_apply_derivative(sqgpu_handle_t c, const double* params, const double*
     if (!in || rows <= 0 || cols <= 0 || stride < cols) return fail(SQGPU_ERR_INVALID, "bad matrix arguments");
     DeviceGuard guard(c->device);
     std::lock_guard<std::mutex> lk(c->mtx);
+    CallScope cs(c, c->stream);
     c->P = &c->plan2;  // apply paths: two-qubit blocks (the streaming kernels stop there)
     int rc = check_ready(c, false);
     if (rc) return rc;
@@ -1726,6 +1865,7 @@ int sqgpu_apply_gate(sqgpu_handle_t c, const sqgpu_gate_desc* gate, const double
     if (!gate || !inout || rows <= 0 || cols <= 0 || stride < cols) return fail(SQGPU_ERR_INVALID, "bad arguments");
     DeviceGuard guard(c->device);
     std::lock_guard<std::mutex> lk(c->mtx);
+    CallScope cs(c, c->stream);
     int rc;
     if ((rc = c->wMat.ensure((size_t)rows * cols * sizeof(cplx)))) return rc;
     CUDA_TRY(cudaMemcpy2DAsync(c->wMat.p, (size_t)cols * sizeof(cplx), inout, (size_t)stride * sizeof(cplx), (size_t)cols * sizeof(cplx), rows, cudaMemcpyHostToDevice, c->stream));
@@ -1741,6 +1881,7 @@ int sqgpu_apply_gate_dev(sqgpu_handle_t c, const sqgpu_gate_desc* gate, const do
     if (!gate || !d_inout || rows <= 0 || cols <= 0 || stride < cols) return fail(SQGPU_ERR_INVALID, "bad arguments");
     DeviceGuard guard(c->device);
     std::lock_guard<std::mutex> lk(c->mtx);
+    CallScope cs(c, (cudaStream_t)stream);
     return apply_gate_on_device(c, gate, gate_params, matrix_pool, deriv_param, reinterpret_cast<cplx*>(d_inout), rows, cols, stride, (cudaStream_t)stream);
 }
 
@@ -1756,7 +1897,7 @@ int sqgpu_set_hamiltonian_csr(sqgpu_handle_t c, int n_rows, int64_t nnz, const i
     if ((rc = c->hIndptr.ensure((size_t)(n_rows + 1) * sizeof(int32_t)))) return rc;
     if ((rc = c->hIndices.ensure(std::max<size_t>(1, (size_t)nnz) * sizeof(int32_t)))) return rc;
     if ((rc = c->hValues.ensure(std::max<size_t>(1, (size_t)nnz) * sizeof(cplx)))) return rc;
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    wait_idle(c);
     CUDA_TRY(cudaMemcpy(c->hIndptr.p, indptr, (size_t)(n_rows + 1) * sizeof(int32_t), cudaMemcpyHostToDevice));
     if (nnz) {
         CUDA_TRY(cudaMemcpy(c->hIndices.p, indices, (size_t)nnz * sizeof(int32_t), cudaMemcpyHostToDevice));
@@ -1773,7 +1914,16 @@ int sqgpu_vqe_energy_batched_dev(sqgpu_handle_t c, const double* d_params, int b
     if (!c) return fail(SQGPU_ERR_INVALID, "NULL handle");
     DeviceGuard guard(c->device);
     std::lock_guard<std::mutex> lk(c->mtx);
+    CallScope cs(c, (cudaStream_t)stream);
     return vqe_dev(c, d_params, batch, false, d_energy, nullptr, (cudaStream_t)stream);
+}
+
+int sqgpu_vqe_energy_grad_batched_dev(sqgpu_handle_t c, const double* d_params, int batch, double* d_energy, double* d_grad, void* stream) {
+    if (!c) return fail(SQGPU_ERR_INVALID, "NULL handle");
+    DeviceGuard guard(c->device);
+    std::lock_guard<std::mutex> lk(c->mtx);
+    CallScope cs(c, (cudaStream_t)stream);
+    return vqe_dev(c, d_params, batch, true, d_energy, d_grad, (cudaStream_t)stream);
 }
 
 static int vqe_host(sqgpu_handle_t c, const double* params, int batch, bool with_grad, double* energy, double* grad) {
@@ -1783,6 +1933,7 @@ static int vqe_host(sqgpu_handle_t c, const double* params, int batch, bool with
     if ((!params && c->n_params > 0) || !energy || (with_grad && !grad && c->n_params > 0)) return fail(SQGPU_ERR_INVALID, "NULL buffer");
     DeviceGuard guard(c->device);
     std::lock_guard<std::mutex> lk(c->mtx);
+    CallScope cs(c, c->stream);
     int rc;
     const size_t np = (size_t)batch * c->n_params;
     if ((rc = c->wParams.ensure(std::max<size_t>(1, np) * sizeof(double)))) return rc;
@@ -1813,36 +1964,87 @@ int sqgpu_launch_count(sqgpu_handle_t c, int64_t* count) {
     return SQGPU_OK;
 }
 
+// average of the events of one ring (the last RING brackets); resets the ring
+static int ring_average(KernelTimer::Ring& r, double* ms, int* launches) {
+    *ms = 0;
+    *launches = 0;
+    if (!r.init || r.n == 0) return SQGPU_OK;
+    const int cnt = std::min(r.n, (int)KernelTimer::RING);
+    double tot = 0;
+    for (int i = 0; i < cnt; ++i) {
+        const int slot = (r.n - 1 - i) % KernelTimer::RING;
+        CUDA_TRY(cudaEventSynchronize(r.e1[slot]));
+        float t = 0;
+        CUDA_TRY(cudaEventElapsedTime(&t, r.e0[slot], r.e1[slot]));
+        tot += t;
+    }
+    *ms = tot / cnt;
+    *launches = cnt;
+    r.n = 0;
+    return SQGPU_OK;
+}
+
 int sqgpu_last_kernel_time(sqgpu_handle_t c, char* name, int name_len, double* ms, int* launches) {
     if (!c || !ms || !launches) return fail(SQGPU_ERR_INVALID, "NULL argument");
     DeviceGuard guard(c->device);
     std::lock_guard<std::mutex> lk(c->mtx);
     *ms = 0;
     *launches = 0;
-    if (name && name_len > 0) {
-        strncpy(name, c->timer.name.c_str(), name_len - 1);
-        name[name_len - 1] = 0;
+    if (name && name_len > 0) name[0] = 0;
+    // the ring with the largest accumulated time since the last call is "the dominant kernel"; all rings are reset
+    double best_total = -1;
+    for (auto& r : c->timer.rings) {
+        if (!r.init || r.n == 0) continue;
+        double m = 0;
+        int n = 0;
+        int rc = ring_average(r, &m, &n);
+        if (rc) return rc;
+        if (m * n > best_total) {
+            best_total = m * n;
+            *ms = m;
+            *launches = n;
+            if (name && name_len > 0) {
+                strncpy(name, r.name.c_str(), name_len - 1);
+                name[name_len - 1] = 0;
+            }
+        }
     }
-    if (!c->timer.init || c->timer.n == 0) return SQGPU_OK;
-    const int cnt = std::min(c->timer.n, (int)KernelTimer::RING);
-    double tot = 0;
-    for (int i = 0; i < cnt; ++i) {
-        const int slot = (c->timer.n - 1 - i) % KernelTimer::RING;
-        CUDA_TRY(cudaEventSynchronize(c->timer.e1[slot]));
-        float t = 0;
-        CUDA_TRY(cudaEventElapsedTime(&t, c->timer.e0[slot], c->timer.e1[slot]));
-        tot += t;
-    }
-    *ms = tot / cnt;
-    *launches = cnt;
-    c->timer.n = 0;
     return SQGPU_OK;
+}
+
+int sqgpu_kernel_time(sqgpu_handle_t c, const char* name, double* ms, int* launches) {
+    if (!c || !name || !ms || !launches) return fail(SQGPU_ERR_INVALID, "NULL argument");
+    DeviceGuard guard(c->device);
+    std::lock_guard<std::mutex> lk(c->mtx);
+    *ms = 0;
+    *launches = 0;
+    for (auto& r : c->timer.rings)
+        if (r.init && r.name == name) return ring_average(r, ms, launches);
+    return SQGPU_OK;
+}
+
+int sqgpu_set_option(sqgpu_handle_t c, const char* name, int64_t value) {
+    if (!c) return fail(SQGPU_ERR_INVALID, "NULL handle");
+    std::lock_guard<std::mutex> lk(c->mtx);
+    return option_set(c->opt, name, value);
+}
+
+int sqgpu_get_option(sqgpu_handle_t c, const char* name, int64_t* value) {
+    if (!c || !name || !value) return fail(SQGPU_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(c->mtx);
+    for (const auto& on : kOptionNames)
+        if (!strcmp(on.name, name)) {
+            *value = c->opt.*(on.field);
+            return SQGPU_OK;
+        }
+    return fail(SQGPU_ERR_INVALID, "unknown option '%s'", name);
 }
 
 int sqgpu_fp64_fma_peak(sqgpu_handle_t c, double* tflops) {
     if (!c || !tflops) return fail(SQGPU_ERR_INVALID, "NULL argument");
     DeviceGuard guard(c->device);
     std::lock_guard<std::mutex> lk(c->mtx);
+    CallScope cs(c, c->stream);
     int rc;
     const int blocks = c->sm_count * 8, thr = 256, iters = 4096;
     if ((rc = c->wCost.ensure((size_t)blocks * thr * sizeof(double)))) return rc;
@@ -1863,7 +2065,7 @@ int sqgpu_fp64_fma_peak(sqgpu_handle_t c, double* tflops) {
     }
     // the FP64 tensor-core rate (DMMA m8n8k4, the instruction the executor's block path issues) and, for the record, DFMA and
     // DMMA mixed: all three share one pipe on B200; the reported peak is the larger of the DFMA and DMMA figures
-    const char* vb = getenv("SQGPU_VERBOSE");
+    const bool vb = c->opt.verbose != 0;
     {
         double best_mma = 0, best_mix = 0;
         for (int rep = 0; rep < 4; ++rep) {
@@ -1883,7 +2085,7 @@ int sqgpu_fp64_fma_peak(sqgpu_handle_t c, double* tflops) {
             const double fl2 = (2.0 * 256 * 2 * (thr / 32) + 2.0 * 16 * thr) * (double)iters * blocks;
             if (rep > 0) best_mix = std::max(best_mix, fl2 / (ms * 1e-3) * 1e-12);
         }
-        if (vb && vb[0] == '1')
+        if (vb)
             fprintf(stderr, "[sqgpu] FP64 peaks: DFMA %.2f TFLOP/s, DMMA m8n8k4 %.2f TFLOP/s, DFMA+DMMA mixed %.2f TFLOP/s\n", best, best_mma, best_mix);
         best = std::max(best, best_mma);
     }

@@ -8,6 +8,7 @@
 // in reverse order on (psi, lambda), W' partials per (parameter set, CTA) reduced by reduce_partials.
 // Returns 1 when the shared-memory plan does not fit (caller falls back to the streaming path).
 static int vqe_window_dev(sqgpu_ctx* c, const double* d_params, int batch, bool with_grad, double* d_energy, double* d_grad, cudaStream_t st) {
+    PlanScope keep(c);
     c->P = &c->planW;
     const int rows = c->rows, w = c->win_w, wr = 1 << w, wc = rows >> w;
     int rc;
@@ -106,9 +107,8 @@ static int vqe_dev(sqgpu_ctx* c, const double* d_params, int batch, bool with_gr
     if (!c->hIndptr.p || c->h_rows != c->rows) return fail(SQGPU_ERR_STATE, "no Hamiltonian of matching size set (call sqgpu_set_hamiltonian_csr)");
     if (!d_energy || (with_grad && !d_grad && c->n_params > 0)) return fail(SQGPU_ERR_INVALID, "NULL buffer");
     if (with_grad && !c->all_unitary) return fail(SQGPU_ERR_UNSUPPORTED, "gradient with a non-unitary GENERAL gate is not supported");
-    {   // windowed shared-memory executor first; SQGPU_VQE_STREAM=1 (test hook) or a plan that does not fit: one op per launch
-        const char* vs = getenv("SQGPU_VQE_STREAM");
-        if (!(vs && vs[0] == '1')) {
+    {   // windowed shared-memory executor first; option vqe_stream (test hook) or a plan that does not fit: one op per launch
+        if (!c->opt.vqe_stream) {
             rc = vqe_window_dev(c, d_params, batch, with_grad, d_energy, d_grad, st);
             if (rc != 1) return rc;
             c->P = &c->plan2;

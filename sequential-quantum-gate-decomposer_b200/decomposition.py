@@ -39,7 +39,8 @@ class N_Qubit_Decomposition_custom:
         self.Umtx = U
         self.config = dict(config or {})
         self.accelerator_num = int(accelerator_num)
-        self._circuit = Circuit(n)
+        self._circuit = Circuit(n, device)
+        self._circuit_key = None
         self._variant = abi.FROBENIUS_NORM
         self._trace_offset = 0
         self._prev_cost = 1.0  # Optimization_Interface.cpp:74-76
@@ -63,8 +64,9 @@ class N_Qubit_Decomposition_custom:
         """Optimization_Interface::set_custom_gate_structure (Optimization_Interface.cpp:1770-1778)."""
         if circuit.qbit_num != self.qbit_num:
             raise Exception("set_Gate_Structure: qubit count mismatch")
-        self._circuit = Circuit(self.qbit_num)
+        self._circuit = Circuit(self.qbit_num, self._device)
         self._circuit._items = list(circuit._items)  # release_gates(); combine(gate_structure_in)
+        self._circuit._version = 1
         self._dirty = True
 
     def get_Circuit(self):
@@ -94,8 +96,13 @@ class N_Qubit_Decomposition_custom:
         self._dirty = True
 
     def _sync(self):
-        if self._dirty:
+        # the structure can also change behind our back -- get_Circuit() hands out the live object and set_Gate_Structure
+        # shares nested blocks with the caller -- so the plan is keyed on the recursive structure key, not on a flag
+        key = self._circuit.structure_key()
+        if key != self._circuit_key:
             self._engine.set_circuit(self._circuit)
+            self._circuit_key = key
+        if self._dirty:
             self._engine.set_cost(self._variant, self._trace_offset, self._prev_cost, self._c1, self._c2)
             self._dirty = False
         return self._engine

@@ -17,11 +17,17 @@ def _f64(a):
 class Engine:
     """One context on one CUDA device (sqgpu_create / sqgpu_destroy)."""
 
-    def __init__(self, device=0):
+    # options every new Engine starts with (sqgpu_set_option names); the parity tests set e.g. {"no_fuse": 1} here so that
+    # engines created deep inside the wrapper classes pick the executor path under test. Empty = product configuration.
+    default_options = {}
+
+    def __init__(self, device=0, options=None):
         self.lib = abi.load_library()
         self._h = abi._handle()
         abi.check(self.lib, self.lib.sqgpu_create(int(device), C.byref(self._h)))
         self.device = int(device)
+        for k, v in dict(Engine.default_options, **(options or {})).items():
+            self.set_option(k, v)
         self.n_params = 0
         self.n_gates = 0
         self.qbit_num = 0
@@ -38,6 +44,15 @@ class Engine:
             self.close()
         except Exception:
             pass
+
+    def set_option(self, name, value):
+        """sqgpu_set_option: planner options take effect with the next set_circuit"""
+        abi.check(self.lib, self.lib.sqgpu_set_option(self._h, name.encode(), int(value)))
+
+    def get_option(self, name):
+        v = C.c_int64(0)
+        abi.check(self.lib, self.lib.sqgpu_get_option(self._h, name.encode(), C.byref(v)))
+        return v.value
 
     # ---- inputs ---------------------------------------------------------------------------------------------
     def upload_matrix(self, umtx):
@@ -185,6 +200,10 @@ class Engine:
     def vqe_energy_batched_dev(self, d_params, batch, d_energy, stream=0):
         abi.check(self.lib, self.lib.sqgpu_vqe_energy_batched_dev(self._h, d_params, int(batch), d_energy, stream))
 
+    def vqe_energy_grad_batched_dev(self, d_params, batch, d_energy, d_grad, stream=0):
+        abi.check(self.lib, self.lib.sqgpu_vqe_energy_grad_batched_dev(self._h, d_params, int(batch), d_energy, d_grad,
+                                                                       stream))
+
     # ---- introspection --------------------------------------------------------------------------------------
     def launch_count(self):
         n = C.c_int64(0)
@@ -197,6 +216,13 @@ class Engine:
         n = C.c_int(0)
         abi.check(self.lib, self.lib.sqgpu_last_kernel_time(self._h, buf, 128, C.byref(ms), C.byref(n)))
         return buf.value.decode(), ms.value, n.value
+
+    def kernel_time(self, name):
+        """(ms, launches) of one kernel by name since its ring was last reset (sqgpu_kernel_time)"""
+        ms = C.c_double(0)
+        n = C.c_int(0)
+        abi.check(self.lib, self.lib.sqgpu_kernel_time(self._h, name.encode(), C.byref(ms), C.byref(n)))
+        return ms.value, n.value
 
     def fp64_fma_peak(self):
         t = C.c_double(0)

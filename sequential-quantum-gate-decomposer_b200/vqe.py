@@ -1,0 +1,168 @@
+"""Host-side mirror of the cost path of the reference's VQE class.
+
+``Variational_Quantum_Eigensolver`` keeps the constructor and method names of
+``qgd_Variational_Quantum_Eigensolver_Base`` (squander/VQA/qgd_Variational_Quantum_Eigensolver_Base.py:145-420) for the calls
+on the hot path: ``set_Ansatz``, ``Generate_Circuit``, ``set_Gate_Structure``, ``set_Initial_State``, ``get_Parameter_Num``,
+``Optimization_Problem``, ``Optimization_Problem_Grad``, ``Optimization_Problem_Combined``, ``Optimization_Problem_Batch``,
+``apply_to``. Every evaluation runs on the GPU through the C-ABI (sqgpu_vqe_energy[_grad]_batched): there is no CPU path.
+
+The state-vector backend only; the density-matrix backend, the optimizers and the entropy helpers are outside the hot path
+(SURVEY.md §2.3).
+"""
+import numpy as np
+
+from . import abi
+from .circuit import Circuit
+from .engine import Engine
+
+
+class Variational_Quantum_Eigensolver:
+    """E(theta) = Re <psi(theta)| H |psi(theta)>, psi = C(theta) |initial state>
+    (Variational_Quantum_Eigensolver_Base::optimization_problem, ...Base.cpp:1088-1121)."""
+
+    def __init__(self, Hamiltonian, qbit_num, config=None, accelerator_num=1, device=0, backend=None):
+        if backend not in (None, "state_vector"):
+            raise Exception("Unsupported backend '%s': the device path implements the state-vector backend" % backend)
+        if accelerator_num < 1:
+            raise Exception("accelerator_num should be >= 1: this package only provides the GPU path")
+        self.qbit_num = int(qbit_num)
+        rows = 1 << self.qbit_num
+        # a scipy.sparse CSR matrix (the reference takes .data / .indices / .indptr of one) or an (indptr, indices, data) triple
+        if hasattr(Hamiltonian, "indptr"):
+            H = Hamiltonian.tocsr() if hasattr(Hamiltonian, "tocsr") else Hamiltonian
+            indptr, indices, data = H.indptr, H.indices, H.data
+        else:
+            indptr, indices, data = Hamiltonian
+        self._indptr = np.ascontiguousarray(indptr, dtype=np.int32)
+        self._indices = np.ascontiguousarray(indices, dtype=np.int32)
+        self._data = np.ascontiguousarray(data, dtype=np.complex128)
+        if len(self._indptr) != rows + 1:
+            raise Exception("Hamiltonian should be a 2^qbit_num x 2^qbit_num sparse matrix")
+        self.config = dict(config or {})
+        self.accelerator_num = int(accelerator_num)
+        self.backend = "state_vector"
+        self._device = int(device)
+        self._ansatz = "HEA"  # Variational_Quantum_Eigensolver_Base.cpp: ansatz = HEA by default
+        self._circuit = Circuit(self.qbit_num, device)
+        self._state0 = np.zeros(rows, dtype=np.complex128)
+        self._state0[0] = 1.0  # initialize_zero_state
+        self._engine_obj = None
+        self._circuit_key = None
+        self._state_dirty = True
+
+    # ---- structure -------------------------------------------------------------------------------------------------------
+    def set_Ansatz(self, ansatz_new):
+        if ansatz_new not in ("HEA", "HEA_ZYZ"):
+            raise Exception("Variational_Quantum_Eigensolver: ansatz not implemented")
+        self._ansatz = ansatz_new
+
+    def Generate_Circuit(self, layers, inner_blocks=1):
+        """generate_circuit (...Base.cpp:1299-1437): HEA = [U3, U3, CNOT] per pair, HEA_ZYZ = [RZ RY RZ] blocks + CNOT;
+        pairs (1, 0), then for odd control c: (c + 2, c + 1) if it exists, then (c + 1, c)."""
+        n = self.qbit_num
+        c = Circuit(n, self._device)
+        zyz = self._ansatz == "HEA_ZYZ"
+        if n < (2 if zyz else 1):
+            raise Exception("Variational_Quantum_Eigensolver_Base::generate_initial_circuit: number of qubits should be at least %d" % (2 if zyz else 1))
+
+        def single(q):
+            if zyz:
+                b = Circuit(n, self._device)
+                b.add_RZ(q)
+                b.add_RY(q)
+                b.add_RZ(q)
+                c.add_Circuit(b)
+            else:
+                c.add_U3(q)
+
+        def pair(first, second, tgt, ctl):
+            for _ in range(inner_blocks):
+                single(first)
+                single(second)
+                c.add_CNOT(tgt, ctl)
+
+        for _ in range(layers):
+            if n == 1:
+                for _ in range(inner_blocks):
+                    c.add_U3(0)
+                continue
+            pair(1, 0, 1, 0)
+            for cq in range(1, n - 1, 2):
+                if cq + 2 < n:
+                    pair(cq + 1, cq + 2, cq + 2, cq + 1)
+                pair(cq + 1, cq, cq + 1, cq)
+        self._circuit = c
+
+    def set_Gate_Structure(self, Gate_structure):
+        if Gate_structure.qbit_num != self.qbit_num:
+            raise Exception("set_Gate_Structure: qubit count mismatch")
+        self._circuit = Circuit(self.qbit_num, self._device)
+        self._circuit._items = list(Gate_structure._items)
+        self._circuit._version = 1
+
+    def set_Gate_Structure_from_Binary(self, filename):
+        from . import gate_io
+
+        circ, params = gate_io.import_gate_list_from_binary(filename)
+        self.set_Gate_Structure(circ)
+        self._optimized_parameters = params
+
+    def set_Initial_State(self, initial_state):
+        s = np.ascontiguousarray(initial_state, dtype=np.complex128).reshape(-1)
+        if s.size != (1 << self.qbit_num):
+            raise Exception("Initial state should have 2^qbit_num elements")
+        self._state0 = s
+        self._state_dirty = True
+
+    def get_Circuit(self):
+        return self._circuit
+
+    def get_Qbit_Num(self):
+        return self.qbit_num
+
+    def get_Parameter_Num(self):
+        return self._circuit.get_Parameter_Num()
+
+    # ---- engine ----------------------------------------------------------------------------------------------------------
+    @property
+    def _engine(self):
+        if self._engine_obj is None:
+            self._engine_obj = Engine(self._device)
+            self._engine_obj.set_hamiltonian_csr(self._indptr, self._indices, self._data)
+        return self._engine_obj
+
+    def _sync(self):
+        eng = self._engine
+        if self._state_dirty:
+            eng.upload_matrix(self._state0)
+            self._state_dirty = False
+        key = self._circuit.structure_key()
+        if key != self._circuit_key:
+            eng.set_circuit(self._circuit)
+            self._circuit_key = key
+        return eng
+
+    # ---- the hot path ----------------------------------------------------------------------------------------------------
+    def Optimization_Problem(self, parameters):
+        return float(self._sync().vqe_energy_batched(np.asarray(parameters, dtype=np.float64).reshape(1, -1))[0])
+
+    def Optimization_Problem_Batch(self, parameters):
+        p = np.asarray(parameters, dtype=np.float64)
+        if p.ndim != 2:
+            raise Exception("Optimization_Problem_Batch: parameters should be a 2 dimensional array")
+        return self._sync().vqe_energy_batched(p)
+
+    def Optimization_Problem_Combined(self, parameters):
+        """optimization_problem_combined_non_static (...Base.cpp:1131-1199): (E, grad)"""
+        e, g = self._sync().vqe_energy_grad_batched(np.asarray(parameters, dtype=np.float64).reshape(1, -1))
+        return float(e[0]), g[0]
+
+    def Optimization_Problem_Combined_Batch(self, parameters):
+        return self._sync().vqe_energy_grad_batched(np.asarray(parameters, dtype=np.float64))
+
+    def Optimization_Problem_Grad(self, parameters):
+        return self.Optimization_Problem_Combined(parameters)[1]
+
+    def apply_to(self, parameters_mtx, state_to_be_transformed):
+        """in place: state <- C(parameters) state"""
+        self._circuit.apply_to(parameters_mtx, state_to_be_transformed)

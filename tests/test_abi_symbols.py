@@ -37,7 +37,20 @@ def test_header_symbols_are_exported_and_bound(lib):
         assert hasattr(lib, s), "libsqgpu.so does not export %s" % s
         assert s in abi.PROTOTYPES, "abi.PROTOTYPES has no prototype for %s" % s
     assert sorted(abi.PROTOTYPES) == syms
-    assert lib.sqgpu_abi_version() == 1
+    assert lib.sqgpu_abi_version() == abi.ABI_VERSION == 2
+
+
+def test_library_does_not_read_the_environment():
+    """round 1 read SQGPU_* variables with getenv on every plan; the switches are per-handle options now
+    (sqgpu_set_option): none of the old variable names is left in the binary (the statically linked CUDA runtime still
+    imports getenv for its own CUDA_* variables, so the symbol itself cannot be the check)"""
+    blob = open(abi.LIB_PATH, "rb").read()
+    for name in (b"SQGPU_NO_FUSE", b"SQGPU_WINDOW", b"SQGPU_FORCE_STREAM", b"SQGPU_VQE_STREAM", b"SQGPU_SPLIT", b"SQGPU_THREADS",
+                 b"SQGPU_CTAS_PER_SM", b"SQGPU_FUSE_CONSECUTIVE", b"SQGPU_MAX_FUSE_QUBITS", b"SQGPU_VERBOSE"):
+        assert name not in blob, name
+    src = "".join(open(os.path.join(os.path.dirname(abi.LIB_PATH), f)).read() for f in os.listdir(os.path.dirname(abi.LIB_PATH))
+                  if f.endswith((".cu", ".cuh")))
+    assert "getenv" not in src
 
 
 def test_descriptor_struct_layout_matches_c(tmp_path):
@@ -167,24 +180,26 @@ def test_host_planner_without_gpu(monkeypatch):
     sq = H.sq
     st = sq.abi.plan_stats(H.adaptive_circuit(10, 4))  # C3: 550 gates, P = 1290
     assert st["ops_plan2"] == 180 and st["ops_plan3"] == 84 and st["block_members"] == 550 and st["dense_ops"] == 0
-    monkeypatch.setenv("SQGPU_FUSE_CONSECUTIVE", "1")  # runs of consecutive gates only: more, emptier blocks
-    st_c = sq.abi.plan_stats(H.adaptive_circuit(10, 4))
+    st_c = sq.abi.plan_stats(H.adaptive_circuit(10, 4), fuse_consecutive=1)  # runs of consecutive gates only: more, emptier blocks
     assert st_c["ops_plan2"] == 185 and st_c["ops_plan3"] == 100 and st_c["kern_total"] > st["kern_total"]
-    monkeypatch.delenv("SQGPU_FUSE_CONSECUTIVE")
     assert st["w_total"] == st["kern_total"]  # every op of this structure carries parameters: one W accumulator per kernel
     assert st["segments"] == 1 and st["window"] == 10
     st = sq.abi.plan_stats(H.hea_zyz_circuit(20, 10))  # C5: 1330 gates, default window of 11 qubits
     assert st["block_members"] == 1330 and st["window"] == 11 and st["segments"] == 9 and st["ops_plan3"] == 99
-    monkeypatch.setenv("SQGPU_WINDOW", "10")  # a narrower window needs more segments (first fit alone: 20)
-    assert 9 < sq.abi.plan_stats(H.hea_zyz_circuit(20, 10))["segments"] <= 16
-    monkeypatch.setenv("SQGPU_WINDOW", "4")
+    # a narrower window needs more segments (first fit alone: 20)
+    assert 9 < sq.abi.plan_stats(H.hea_zyz_circuit(20, 10), window=10)["segments"] <= 16
     c = H.random_circuit(7, 80, seed=5, general_k=(2, 3))
-    st = sq.abi.plan_stats(c)
+    st = sq.abi.plan_stats(c, window=4)
     assert st["segments"] > 1 and st["max_segment_ops"] >= 1 and st["dense_ops"] == 3
-    monkeypatch.setenv("SQGPU_NO_FUSE", "1")
-    st = sq.abi.plan_stats(c)
+    st = sq.abi.plan_stats(c, window=4, no_fuse=1)
     assert st["ops_plan2"] == st["ops_plan3"] == len(c.descriptors()[0]) and st["block_members"] == 0
-    monkeypatch.delenv("SQGPU_NO_FUSE")
+    with pytest.raises(sq.abi.SqgpuError):
+        sq.abi.plan_stats(c, no_such_option=1)
+    with pytest.raises(sq.abi.SqgpuError):
+        sq.abi.plan_stats(c, window=99)
+    # the library no longer reads the process environment: an exported variable of round 1 changes nothing
+    monkeypatch.setenv("SQGPU_NO_FUSE", "1")
+    assert sq.abi.plan_stats(c, window=4) == sq.abi.plan_stats(c, window=4, no_fuse=0)
     # validation: the same errors sqgpu_set_circuit raises
     bad = sq.Circuit(3)
     bad.add_U3(0)
@@ -199,3 +214,48 @@ def test_host_planner_without_gpu(monkeypatch):
     assert b"out of range" in lib.sqgpu_last_error()
     assert lib.sqgpu_plan_stats(d.ctypes.data_as(C.POINTER(sq.abi.GateDesc)), 1, 4, 3, None, 0, out, 10) == sq.abi.ERR_INVALID
     assert b"not used by any gate" in lib.sqgpu_last_error()
+
+
+def test_structure_key_tracks_nested_mutations():
+    """the device plan is keyed on a recursive structure key (a sub-circuit mutated after add_Circuit, with the
+    parameter count unchanged, used to keep a stale plan)"""
+    sq = H.sq
+    inner = sq.Circuit(3)
+    inner.add_U3(0)
+    outer = sq.Circuit(3)
+    outer.add_Circuit(inner)
+    outer.add_CNOT(1, 0)
+    k0 = outer.structure_key()
+    assert outer.structure_key() == k0
+    inner.add_CNOT(2, 1)  # no new parameters, same number of top-level items
+    k1 = outer.structure_key()
+    assert k1 != k0
+    dec = sq.N_Qubit_Decomposition_custom(np.eye(8, dtype=np.complex128))
+    dec.set_Gate_Structure(outer)
+    k2 = dec.get_Circuit().structure_key()
+    inner.add_H(0)  # shared nested block, mutated through the caller's reference
+    assert dec.get_Circuit().structure_key() != k2
+    dec.get_Circuit().add_X(1)  # the live object handed out by get_Circuit
+    assert len(dec.get_Circuit().descriptors()[0]) == 5
+
+
+def test_vqe_wrapper_structure_without_gpu():
+    """Generate_Circuit reproduces generate_circuit (Variational_Quantum_Eigensolver_Base.cpp:1299-1437): the HEA_ZYZ
+    structure equals helpers.hea_zyz_circuit, which the oracle tests pin against the reference class itself"""
+    sq = H.sq
+    n = 6
+    Hm = H.heisenberg_csr(n)
+    vqe = sq.Variational_Quantum_Eigensolver(Hm, n, accelerator_num=1)
+    vqe.set_Ansatz("HEA_ZYZ")
+    vqe.Generate_Circuit(3, 2)
+    assert vqe.get_Circuit().descriptors()[0].tobytes() == H.hea_zyz_circuit(n, 3, 2).descriptors()[0].tobytes()
+    vqe.set_Ansatz("HEA")
+    vqe.Generate_Circuit(2, 1)
+    d = vqe.get_Circuit().descriptors()[0]
+    assert list(d["type"][:3]) == [sq.abi.U3, sq.abi.U3, sq.abi.CNOT] and vqe.get_Parameter_Num() == 6 * 5 * 2
+    with pytest.raises(Exception):
+        vqe.set_Ansatz("UCC")
+    with pytest.raises(Exception):
+        sq.Variational_Quantum_Eigensolver(Hm, n, accelerator_num=0)
+    with pytest.raises(Exception):
+        sq.Variational_Quantum_Eigensolver(Hm, n + 1)

@@ -31,12 +31,11 @@ def eng(sq):
 
 @pytest.fixture(params=["fused", "raw"])
 def plan_mode(request, monkeypatch):
-    """run with the block planner (default) and with SQGPU_NO_FUSE=1 (every gate stays a raw op), so both the fused
+    """run with the block planner (default) and with option no_fuse (every gate stays a raw op), so both the fused
     4x4/2x2 block path and the generic controlled / dense path of the executor are checked against the oracle"""
-    if request.param == "raw":
-        monkeypatch.setenv("SQGPU_NO_FUSE", "1")
-    else:
-        monkeypatch.delenv("SQGPU_NO_FUSE", raising=False)
+    import squander_b200
+
+    monkeypatch.setattr(squander_b200.Engine, "default_options", {"no_fuse": 1} if request.param == "raw" else {})
     return request.param
 
 
@@ -245,7 +244,7 @@ def test_vqe_window_with_mixed_gates(sq, port, monkeypatch):
     """the windowed state-vector executor on a circuit with every gate family (controlled, two-target, GENERAL blocks,
     CCX/CSWAP): segments are formed by pulling commuting ops forward, so this pins the reordering and the qubit remapping"""
     n = 7
-    monkeypatch.setenv("SQGPU_WINDOW", "4")
+    monkeypatch.setattr(sq.Engine, "default_options", {"window": 4})
     indptr, indices, data = H.heisenberg_csr(n, degree=2)
     c = H.random_circuit(n, 80, seed=5, general_k=(2, 3))
     d, pool = c.descriptors()
@@ -599,9 +598,9 @@ def test_vqe_energy_and_gradient(sq, port, monkeypatch, n, layers, path):
     """windowed shared-memory executor (default window of 11 qubits: one segment for n <= 11, several for n = 12), forced
     narrow windows (many segments, 2^(n-w) tile columns) and the one-op-per-launch streaming path"""
     if path == "stream":
-        monkeypatch.setenv("SQGPU_VQE_STREAM", "1")
+        monkeypatch.setattr(sq.Engine, "default_options", {"vqe_stream": 1})
     elif path != "window":
-        monkeypatch.setenv("SQGPU_WINDOW", path[6:])
+        monkeypatch.setattr(sq.Engine, "default_options", {"window": int(path[6:])})
     indptr, indices, data = H.heisenberg_csr(n)
     c = H.hea_zyz_circuit(n, layers)
     d, pool = c.descriptors()
@@ -663,7 +662,7 @@ def test_dense_blocks_in_circuit(sq, port, n, cols):
 
 @pytest.mark.parametrize("variant", [0, 2, 3, 5])
 def test_streaming_executor_matches_oracle(sq, port, monkeypatch, variant):
-    """SQGPU_FORCE_STREAM=1 routes cost/gradient through the fallback used when a column does not fit shared memory
+    """option force_stream routes cost/gradient through the fallback used when a column does not fit shared memory
     (n >= 13 gradient, n >= 14 cost); same answers as the oracle, and as the shared-memory executor"""
     n = 6
     c = H.random_circuit(n, 40, seed=17, names=["U3", "RY", "CRY", "CNOT", "RZ", "adaptive", "CZ", "RX", "RXX", "H", "CP"])
@@ -671,8 +670,7 @@ def test_streaming_executor_matches_oracle(sq, port, monkeypatch, variant):
     P = c.get_Parameter_Num()
     U = H.random_unitary(1 << n).conj().T.copy()[:, :37].copy()
     ps = H.random_params(P, seed=9, batch=3)
-    monkeypatch.setenv("SQGPU_FORCE_STREAM", "1")
-    e = sq.Engine(0)
+    e = sq.Engine(0, options={"force_stream": 1})
     e.upload_matrix(U)
     e.set_circuit(c)
     e.set_cost(variant, 0, 0.37)
