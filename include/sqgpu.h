@@ -273,6 +273,11 @@ int sqgpu_last_kernel_time(sqgpu_handle_t h, char* name, int name_len, double* m
  * resets that ring only. launches = 0: the kernel has not run since the last reset. */
 int sqgpu_kernel_time(sqgpu_handle_t h, const char* name, double* ms, int* launches);
 
+/* launch geometry of the fused executor in the last cost / gradient evaluation: shape[0..6) = log2(tile columns), threads per
+ * CTA, column chunks (grid.x), tiles per CTA, dynamic shared memory bytes, cluster size. shape[0] = -1: it has not run (the
+ * evaluation went down the streaming path). The parity tests use it to prove they exercise the instantiation bench.py times. */
+int sqgpu_last_launch_shape(sqgpu_handle_t h, int* shape, int n_shape);
+
 /* measured FP64 throughput of the handle's device in TFLOP/s: the larger of a DFMA and a DMMA (mma.sync m8n8k4.f64, the
  * instruction the executor's block path issues) burn kernel -- both run on the same pipe. Roofline denominator of the
  * shared-memory executor, which is bound by the FP64 tensor pipe and not by HBM (MEASURED_PEAKS.json has no FP64 figure). */

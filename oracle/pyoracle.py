@@ -81,6 +81,7 @@ class Port:
         L.sqo_csr_matvec.argtypes = [C.c_int, _ip, _ip, _dp, _dp, _dp]
         L.sqo_vqe_energy.argtypes = [_gp, C.c_int, _dp, _dp, _dp, C.c_int, _ip, _ip, _dp, _dp]
         L.sqo_vqe_energy_grad.argtypes = [_gp, C.c_int, C.c_int, _dp, _dp, _dp, C.c_int, _ip, _ip, _dp, _dp, _dp]
+        L.sqo_vqe_energy_grad_sampled.argtypes = [_gp, C.c_int, _dp, _dp, _dp, C.c_int, _ip, _ip, _dp, _ip, C.c_int, _dp, _dp]
 
     def gate_kernel(self, type_, gate_params):
         k = np.zeros(16, dtype=np.complex128)
@@ -208,6 +209,27 @@ class Port:
         if rc:
             raise Exception("port: vqe_energy_grad failed")
         return float(out[0]), grad[:n_params]
+
+
+    def vqe_energy_grad_sampled(self, descs, params, state0, indptr, indices, data, sample, pool=None):
+        """(energy, grad[sample]): only the listed parameters' derivative states are formed"""
+        d, dptr = _descs(descs)
+        p = _f64(params)
+        s0 = _c128(state0).reshape(-1)
+        ip = np.ascontiguousarray(indptr, dtype=np.int32)
+        ix = np.ascontiguousarray(indices, dtype=np.int32)
+        v = _c128(data)
+        sm = np.ascontiguousarray(sample, dtype=np.int32)
+        pl = _c128(pool) if pool is not None else np.zeros(0, dtype=np.complex128)
+        out = np.zeros(1)
+        grad = np.zeros(max(sm.size, 1))
+        rc = self.lib.sqo_vqe_energy_grad_sampled(dptr, len(d), _dptr(p), _dptr(pl.view(np.float64)),
+                                                  _dptr(s0.view(np.float64)), s0.size, ip.ctypes.data_as(_ip),
+                                                  ix.ctypes.data_as(_ip), _dptr(v.view(np.float64)),
+                                                  sm.ctypes.data_as(_ip), sm.size, _dptr(out), _dptr(grad))
+        if rc:
+            raise Exception("port: vqe_energy_grad_sampled failed")
+        return float(out[0]), grad[: sm.size]
 
 
 class Ref:

@@ -647,3 +647,39 @@ int sqo_vqe_energy_grad(const sqgpu_gate_desc* gates, int n_gates, int n_params,
     free(d);
     return rc;
 }
+
+/* The same gradient restricted to a sample of parameters: the derivative state of parameter p is the prefix state, the
+ * derivative kernel of p's gate, then the remaining gates (the prefix-only route of sqo_apply_derivate), evaluated only for
+ * p in sample[0..n_sample). Used at sizes where all P derivative states are out of reach (n = 20: P = 1140 passes over
+ * 2^20 amplitudes). grad[i] belongs to sample[i]. */
+int sqo_vqe_energy_grad_sampled(const sqgpu_gate_desc* gates, int n_gates, const double* params, const double* pool,
+                                const double* state0, int n_rows, const int32_t* indptr, const int32_t* indices,
+                                const double* values, const int32_t* sample, int n_sample, double* energy, double* grad) {
+    const size_t vsz = 2 * (size_t)n_rows;
+    double* prefix = copy_compact(state0, n_rows, 1, 1);
+    double* hpsi = (double*)malloc(sizeof(double) * vsz);
+    double* d = (double*)malloc(sizeof(double) * vsz * (size_t)(n_sample > 0 ? n_sample : 1));
+    if (!prefix || !hpsi || !d) { free(prefix); free(hpsi); free(d); return -1; }
+    int rc = 0;
+    for (int gi = 0; gi < n_gates && !rc; ++gi) {
+        const sqgpu_gate_desc* g = &gates[gi];
+        for (int s = 0; s < n_sample && !rc; ++s) {
+            const int p = sample[s] - g->param_start;
+            if (p < 0 || p >= g->n_params) continue;
+            double* ds = d + vsz * (size_t)s;
+            memcpy(ds, prefix, sizeof(double) * vsz);
+            rc = sqo_apply_gate(g, params, pool, p, ds, n_rows, 1, 1);
+            for (int gj = gi + 1; gj < n_gates && !rc; ++gj) rc = sqo_apply_gate(&gates[gj], params, pool, -1, ds, n_rows, 1, 1);
+        }
+        if (!rc) rc = sqo_apply_gate(g, params, pool, -1, prefix, n_rows, 1, 1);
+    }
+    if (!rc) {
+        sqo_csr_matvec(n_rows, indptr, indices, values, prefix, hpsi);
+        *energy = expectation(n_rows, prefix, hpsi);
+        for (int s = 0; s < n_sample; ++s) grad[s] = 2 * expectation(n_rows, d + vsz * (size_t)s, hpsi);
+    }
+    free(prefix);
+    free(hpsi);
+    free(d);
+    return rc;
+}

@@ -91,6 +91,11 @@ int sqo_vqe_energy_grad(const sqgpu_gate_desc* gates, int n_gates, int n_params,
                         const double* pool, const double* state0, int n_rows, const int32_t* indptr,
                         const int32_t* indices, const double* values, double* energy, double* grad);
 
+/* energy and the gradient entries of the parameters in sample[0..n_sample) only (same derivative route) */
+int sqo_vqe_energy_grad_sampled(const sqgpu_gate_desc* gates, int n_gates, const double* params, const double* pool,
+                                const double* state0, int n_rows, const int32_t* indptr, const int32_t* indices,
+                                const double* values, const int32_t* sample, int n_sample, double* energy, double* grad);
+
 #ifdef __cplusplus
 }
 #endif

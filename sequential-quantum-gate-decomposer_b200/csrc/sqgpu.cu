@@ -246,6 +246,7 @@ struct sqgpu_ctx {
     long long launches = 0;
     KernelTimer timer;
     Options opt;
+    int last_shape[6] = {-1, 0, 0, 0, 0, 0};  // fused executor launch of the last evaluation: log_ct, threads, chunks, tiles per CTA, smem, cluster size
 
     // Every entry point that enqueues work records `last_done` on its stream when it returns; the next entry point makes its
     // own stream wait for it first, so calls on DIFFERENT streams cannot race on the handle's shared workspaces (the mutex
@@ -896,6 +897,8 @@ int run_exec_resident(sqgpu_ctx* c, int batch, bool grad, const cplx* d_omega, d
     a.omega = d_omega;
     if (grad && !p.w_in_smem && c->P->w_total > 0)
         CUDA_TRY(cudaMemsetAsync(c->wWPart.p, 0, (size_t)batch * p.chunks * c->P->w_total * sizeof(cplx), st));
+    c->last_shape[0] = p.log_ct; c->last_shape[1] = p.threads; c->last_shape[2] = p.chunks; c->last_shape[3] = p.tiles_per_cta;
+    c->last_shape[4] = (int)p.smem; c->last_shape[5] = 1;
     time_begin(c, grad ? "fused_exec<GRAD>" : "fused_exec<COST>", st);
     cudaError_t e = grad ? launch_fused_mode<MODE_GRAD>(a, p, batch, st) : launch_fused_mode<MODE_COST>(a, p, batch, st);
     time_end(c, st);
@@ -2020,6 +2023,13 @@ int sqgpu_kernel_time(sqgpu_handle_t c, const char* name, double* ms, int* launc
     *launches = 0;
     for (auto& r : c->timer.rings)
         if (r.init && r.name == name) return ring_average(r, ms, launches);
+    return SQGPU_OK;
+}
+
+int sqgpu_last_launch_shape(sqgpu_handle_t c, int* shape, int n_shape) {
+    if (!c || !shape || n_shape < 0) return fail(SQGPU_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(c->mtx);
+    for (int i = 0; i < n_shape && i < 6; ++i) shape[i] = c->last_shape[i];
     return SQGPU_OK;
 }
 

@@ -217,6 +217,12 @@ class Engine:
         abi.check(self.lib, self.lib.sqgpu_last_kernel_time(self._h, buf, 128, C.byref(ms), C.byref(n)))
         return buf.value.decode(), ms.value, n.value
 
+    def last_launch_shape(self):
+        """dict of the fused executor's last launch geometry (sqgpu_last_launch_shape)"""
+        a = (C.c_int * 6)()
+        abi.check(self.lib, self.lib.sqgpu_last_launch_shape(self._h, a, 6))
+        return dict(zip(("log_ct", "threads", "chunks", "tiles_per_cta", "smem", "cluster"), (int(v) for v in a)))
+
     def kernel_time(self, name):
         """(ms, launches) of one kernel by name since its ring was last reset (sqgpu_kernel_time)"""
         ms = C.c_double(0)

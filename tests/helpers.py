@@ -134,6 +134,53 @@ def heisenberg_csr(n, seed=31415, degree=3):
     return Hm.indptr.astype(np.int32), Hm.indices.astype(np.int32), Hm.data.astype(np.complex128)
 
 
+def _regular_graph_edges(n, seed, degree):
+    rng = np.random.default_rng(seed)
+    while True:
+        stubs = np.repeat(np.arange(n), degree)
+        rng.shuffle(stubs)
+        edges = set()
+        ok = True
+        for a, b in stubs.reshape(-1, 2):
+            if a == b or (min(a, b), max(a, b)) in edges:
+                ok = False
+                break
+            edges.add((int(min(a, b)), int(max(a, b))))
+        if ok:
+            return sorted(edges)
+
+
+def heisenberg_csr_fast(n, seed=31415, degree=3):
+    """the same matrix as heisenberg_csr (identical indptr / indices / data; checked in tests/test_oracle_golden.py), built
+    from bit arithmetic instead of 2^n-dimensional Kronecker products (n = 20: 1 s instead of 30 s).
+    Row i: diagonal sum_edges (+1 if bits equal else -1) + sum_q (1 - 2 bit_q); for every edge whose bits differ an entry 2
+    at column i ^ (1 << a | 1 << b) (XX + YY = 2 there, 0 where the bits are equal); zeros are not stored (scipy prunes them)."""
+    edges = _regular_graph_edges(n, seed, degree)
+    dim = 1 << n
+    idx = np.arange(dim, dtype=np.int64)
+    diag = np.zeros(dim, dtype=np.float64)
+    for q in range(n):
+        diag += 1.0 - 2.0 * ((idx >> q) & 1)
+    cols = [idx]
+    vals = [diag]
+    for a, b in edges:
+        differ = ((idx >> a) ^ (idx >> b)) & 1
+        diag += 1.0 - 2.0 * differ
+        cols.append(np.where(differ == 1, idx ^ ((1 << a) | (1 << b)), -1))
+        vals.append(np.full(dim, 2.0))
+    vals[0] = diag
+    cols[0] = np.where(diag != 0.0, idx, -1)
+    C = np.stack(cols, axis=1)
+    V = np.stack(vals, axis=1)
+    order = np.argsort(np.where(C < 0, np.int64(1) << 40, C), axis=1, kind="stable")
+    C = np.take_along_axis(C, order, axis=1)
+    V = np.take_along_axis(V, order, axis=1)
+    keep = C >= 0
+    indptr = np.zeros(dim + 1, dtype=np.int64)
+    np.cumsum(keep.sum(axis=1), out=indptr[1:])
+    return indptr.astype(np.int32), C[keep].astype(np.int32), V[keep].astype(np.complex128)
+
+
 def hea_zyz_circuit(n, layers, inner_blocks=1):
     """HEA_ZYZ ansatz exactly as generate_initial_circuit builds it
     (Variational_Quantum_Eigensolver_Base.cpp:1358-1416): blocks [RZ,RY,RZ] on both qubits of a pair + CNOT,

@@ -56,3 +56,40 @@ def test_qasm_importer_matches_fixture(sq):
         sq.qasm.loads("qreg q[1];\nmeasure q[0];")
     with pytest.raises(ValueError):
         sq.qasm.loads("qreg q[1];\nrx(__import__('os')) q[0];")
+
+
+# ---- round 2: the benchmarked configurations (outputs of the reference's own code, tests/golden/make_golden_r2.py) ----------
+
+def test_c3_benchmark_configuration_golden(port):
+    """n = 10, L = 4 (550 gates, P = 1290), 8-column slice with trace_offset = 80: cost and all 1290 gradient entries of the
+    C port against the reference's optimization_problem_combined (which takes the zgemm suffix route at this size)"""
+    circ, Us, params, off, variants, cost, grad = G.c3_n10_slice()
+    d, pool = circ.descriptors()
+    for vi, v in enumerate(variants):
+        f, g = port.cost_grad(d, circ.get_Parameter_Num(), params, Us, 10, v, off)
+        assert abs(f - cost[vi]) <= 1e-12 * max(1.0, abs(cost[vi]))
+        assert np.abs(g - grad[vi]).max() <= 1e-12 * max(1.0, np.abs(grad[vi]).max())
+
+
+def test_c5_recipe_golden(port):
+    """Heisenberg VQE (C5 recipe): energy + gradient at n = 10 and energy at n = 16 of the C port against
+    Variational_Quantum_Eigensolver_Base; the sampled-gradient entry point equals the full one"""
+    n, circ, p, (ip, ix, dat), e_ref, g_ref = G.c5_vqe("C5_n10_vqe")
+    d, pool = circ.descriptors()
+    psi0 = np.zeros(1 << n, dtype=np.complex128)
+    psi0[0] = 1.0
+    e, g = port.vqe_energy_grad(d, circ.get_Parameter_Num(), p, psi0, ip, ix, dat)
+    assert abs(e - e_ref) < 1e-12 and np.abs(g - g_ref).max() < 1e-12
+    sample = [0, 3, 17, 100, len(p) - 1]
+    e2, gs = port.vqe_energy_grad_sampled(d, p, psi0, ip, ix, dat, sample)
+    assert e2 == e and np.abs(gs - g[sample]).max() < 1e-14
+    n, circ, p, (ip, ix, dat), e_ref, _ = G.c5_vqe("C5_n16_vqe")
+    psi0 = np.zeros(1 << n, dtype=np.complex128)
+    psi0[0] = 1.0
+    assert abs(port.vqe_energy(circ.descriptors()[0], p, psi0, ip, ix, dat) - e_ref) < 1e-12
+
+
+def test_fast_heisenberg_builder_is_identical():
+    for n, deg in ((4, 3), (7, 2), (10, 3)):
+        a, b = H.heisenberg_csr(n, degree=deg), H.heisenberg_csr_fast(n, degree=deg)
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
