@@ -278,6 +278,12 @@ int sqgpu_kernel_time(sqgpu_handle_t h, const char* name, double* ms, int* launc
  * evaluation went down the streaming path). The parity tests use it to prove they exercise the instantiation bench.py times. */
 int sqgpu_last_launch_shape(sqgpu_handle_t h, int* shape, int n_shape);
 
+/* FP64 flops the fused executor issued in its last cost / gradient launch (whole batch), split into tensor-pipe (DMMA m8n8k4,
+ * 512 flops each) and scalar (DFMA) work: counted from the launch's own op list, i.e. what the kernel EXECUTES, not the
+ * per-gate algorithmic figure. bench.py's roofline.frac uses this; profiles/ holds the ncu sm__ops_path_tensor_src_fp64
+ * capture that validates the count. */
+int sqgpu_last_exec_flops(sqgpu_handle_t h, double* tensor_flops, double* scalar_flops);
+
 /* measured FP64 throughput of the handle's device in TFLOP/s: the larger of a DFMA and a DMMA (mma.sync m8n8k4.f64, the
  * instruction the executor's block path issues) burn kernel -- both run on the same pipe. Roofline denominator of the
  * shared-memory executor, which is bound by the FP64 tensor pipe and not by HBM (MEASURED_PEAKS.json has no FP64 figure). */

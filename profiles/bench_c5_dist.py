@@ -29,7 +29,7 @@ if world > 1:
 
 n, layers, per_gpu = 20, 10, 128
 steps, warmup = 2, 1
-indptr, indices, data = H.heisenberg_csr(n)
+indptr, indices, data = H.heisenberg_csr_fast(n)
 c = H.hea_zyz_circuit(n, layers)
 psi0 = np.zeros(1 << n, dtype=np.complex128)
 psi0[0] = 1

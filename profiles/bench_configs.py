@@ -92,7 +92,7 @@ def c4q5():
 
 
 def c5(n=20, layers=10, B=64):
-    indptr, indices, data = H.heisenberg_csr(n)
+    indptr, indices, data = H.heisenberg_csr_fast(n)
     c = H.hea_zyz_circuit(n, layers)
     psi0 = np.zeros(1 << n, dtype=np.complex128)
     psi0[0] = 1

@@ -13,7 +13,7 @@ import squander_b200 as sq
 batch = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 mode = sys.argv[2] if len(sys.argv) > 2 else "grad"
 n, layers = 20, 10
-indptr, indices, data = H.heisenberg_csr(n)
+indptr, indices, data = H.heisenberg_csr_fast(n)
 c = H.hea_zyz_circuit(n, layers)
 psi0 = np.zeros(1 << n, dtype=np.complex128)
 psi0[0] = 1

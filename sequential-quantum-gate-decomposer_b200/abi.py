@@ -166,6 +166,7 @@ PROTOTYPES = {
     "sqgpu_vqe_energy_grad_batched_dev": (C.c_int, [_handle, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sqgpu_kernel_time": (C.c_int, [_handle, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "sqgpu_last_launch_shape": (C.c_int, [_handle, C.POINTER(C.c_int), C.c_int]),
+    "sqgpu_last_exec_flops": (C.c_int, [_handle, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "sqgpu_launch_count": (C.c_int, [_handle, C.POINTER(C.c_int64)]),
     "sqgpu_last_kernel_time": (C.c_int, [_handle, C.c_char_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "sqgpu_fp64_fma_peak": (C.c_int, [_handle, C.POINTER(C.c_double)]),

@@ -246,6 +246,7 @@ struct sqgpu_ctx {
     long long launches = 0;
     KernelTimer timer;
     Options opt;
+    double last_flops[2] = {0, 0};  // FP64 flops the last cost / gradient executor launch issues: tensor (DMMA), scalar (DFMA)
     int last_shape[6] = {-1, 0, 0, 0, 0, 0};  // fused executor launch of the last evaluation: log_ct, threads, chunks, tiles per CTA, smem, cluster size
 
     // Every entry point that enqueues work records `last_done` on its stream when it returns; the next entry point makes its
@@ -899,6 +900,7 @@ int run_exec_resident(sqgpu_ctx* c, int batch, bool grad, const cplx* d_omega, d
         CUDA_TRY(cudaMemsetAsync(c->wWPart.p, 0, (size_t)batch * p.chunks * c->P->w_total * sizeof(cplx), st));
     c->last_shape[0] = p.log_ct; c->last_shape[1] = p.threads; c->last_shape[2] = p.chunks; c->last_shape[3] = p.tiles_per_cta;
     c->last_shape[4] = (int)p.smem; c->last_shape[5] = 1;
+    exec_flops(*c->P, c->rows, c->cols, p.log_ct, grad, batch, &c->last_flops[0], &c->last_flops[1]);
     time_begin(c, grad ? "fused_exec<GRAD>" : "fused_exec<COST>", st);
     cudaError_t e = grad ? launch_fused_mode<MODE_GRAD>(a, p, batch, st) : launch_fused_mode<MODE_COST>(a, p, batch, st);
     time_end(c, st);
@@ -914,6 +916,38 @@ int run_exec_resident(sqgpu_ctx* c, int batch, bool grad, const cplx* d_omega, d
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     return SQGPU_OK;
+}
+
+// FP64 flops the fused executor ISSUES for one launch over `ysets` parameter sets (a model of its instruction stream, to be
+// checked against ncu's sm__ops_path_tensor_src_fp64): a DMMA m8n8k4 is 512 flops; per batch of 8 (group, column) items a
+// 3-qubit block issues 8 DMMA forward and 16 (+ 8 for W') backward, a 2-qubit block 2 and 4 (+ 2); the scalar paths issue
+// 4 complex multiply-adds (32 flops) per row pair forward and 8 (+ 4 for W) backward; raw dense 2^k kernels (2^k/4)^2 * 2
+// DMMA per batch (3-5 qubits) forward.
+void exec_flops(const Plan& P, int rows, int cols, int log_ct, bool grad, int ysets, double* tensor, double* scalar) {
+    double t = 0, sc = 0;
+    const double colsd = (double)cols;
+    for (const DevOp& op : P.ops) {
+        const bool has_w = op.w_off >= 0;
+        if (op.dim == 2) {
+            const double pairs = (double)(rows >> (op.ctrl_mask ? op.nfix : 1)) * colsd;
+            sc += pairs * (32.0 + (grad ? 64.0 + (has_w ? 32.0 : 0.0) : 0.0));
+            continue;
+        }
+        const double items = (double)(rows >> op.nq) * colsd;
+        const bool dmma_block = op.ctrl_mask == 0 && (op.dim == 4 || op.dim == 8) && ((((rows >> op.nq) << log_ct) & 7) == 0);
+        if (dmma_block) {
+            const double per8 = op.dim == 8 ? (8.0 + (grad ? 16.0 + (has_w ? 8.0 : 0.0) : 0.0)) : (2.0 + (grad ? 4.0 + (has_w ? 2.0 : 0.0) : 0.0));
+            t += items / 8.0 * per8 * 512.0;
+        } else if (op.ctrl_mask == 0 && op.nq >= 3 && op.type == SQGPU_GENERAL && !grad) {
+            const double nt = op.dim / 4.0;
+            t += items / 8.0 * (nt * nt * 2.0) * 512.0;
+        } else {
+            const double act = items / (double)(1 << popcount32(op.ctrl_mask));
+            sc += act * 8.0 * op.dim * op.dim * (grad ? 3.0 : 1.0);
+        }
+    }
+    *tensor = t * ysets;
+    *scalar = sc * ysets;
 }
 
 int check_ready(const sqgpu_ctx* c, bool need_matrix) {
@@ -2023,6 +2057,14 @@ int sqgpu_kernel_time(sqgpu_handle_t c, const char* name, double* ms, int* launc
     *launches = 0;
     for (auto& r : c->timer.rings)
         if (r.init && r.name == name) return ring_average(r, ms, launches);
+    return SQGPU_OK;
+}
+
+int sqgpu_last_exec_flops(sqgpu_handle_t c, double* tensor_flops, double* scalar_flops) {
+    if (!c || !tensor_flops || !scalar_flops) return fail(SQGPU_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(c->mtx);
+    *tensor_flops = c->last_flops[0];
+    *scalar_flops = c->last_flops[1];
     return SQGPU_OK;
 }
 

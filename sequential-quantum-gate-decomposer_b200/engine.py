@@ -223,6 +223,12 @@ class Engine:
         abi.check(self.lib, self.lib.sqgpu_last_launch_shape(self._h, a, 6))
         return dict(zip(("log_ct", "threads", "chunks", "tiles_per_cta", "smem", "cluster"), (int(v) for v in a)))
 
+    def last_exec_flops(self):
+        """(tensor, scalar) FP64 flops issued by the fused executor's last cost / gradient launch"""
+        t, sc = C.c_double(0), C.c_double(0)
+        abi.check(self.lib, self.lib.sqgpu_last_exec_flops(self._h, C.byref(t), C.byref(sc)))
+        return t.value, sc.value
+
     def kernel_time(self, name):
         """(ms, launches) of one kernel by name since its ring was last reset (sqgpu_kernel_time)"""
         ms = C.c_double(0)
