@@ -870,6 +870,7 @@ void time_end(sqgpu_ctx* c, cudaStream_t st) {
 }
 
 int run_exec_streaming(sqgpu_ctx* c, int batch, bool grad, const cplx* d_omega, double* d_traces, cudaStream_t st);
+void exec_flops(const Plan& P, int rows, int cols, int log_ct, bool grad, int ysets, double* tensor, double* scalar);
 StreamGate make_stream_gate(const DevOp& op, cplx* data, long long ystride, int rows, int cols, int ld, const cplx* K, long long k_ystride);
 int launch_stream_gate(sqgpu_ctx* c, const DevOp& op, bool deriv, cplx* data, long long ystride, int ysets, int rows, int cols,
                        int ld, const cplx* K, long long k_ystride, cudaStream_t st);
