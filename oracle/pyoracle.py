@@ -412,3 +412,126 @@ class RefVQE:
         if self.ref.lib.sqref_vqe_energy_grad(self.h, _dptr(p), p.size, _dptr(out), _dptr(g)):
             raise Exception("ref: vqe_energy_grad failed: " + self.ref._err())
         return float(out[0]), g[: p.size]
+
+
+REF_GPU_PATH = os.path.join(HERE, "_ref", "libsqref_gpu.so")
+
+
+class RefGpu:
+    """oracle/_ref/libsqref_gpu.so: the reference's own classes and optimizers with the drop-in of integration/ compiled in
+    (oracle/ref_gpu_harness.cpp). ``session(use_gpu=...)`` gives the reference's N_Qubit_Decomposition_custom either as it is
+    (CPU cost path) or as With_GPU_Cost_Path<N_Qubit_Decomposition_custom> (every cost / gradient call served by libsqgpu.so)."""
+
+    @staticmethod
+    def available():
+        return os.path.exists(REF_GPU_PATH)
+
+    def __init__(self):
+        if not os.path.exists(REF_GPU_PATH):
+            if os.path.isdir("/root/reference"):
+                subprocess.check_call(["make", "-s", "-j8", "-C", HERE, "ref_gpu"])
+            else:
+                raise FileNotFoundError(REF_GPU_PATH + " missing and /root/reference not present to build it")
+        L = self.lib = C.CDLL(REF_GPU_PATH)
+        L.sqrefgpu_last_error.restype = C.c_char_p
+        L.sqrefgpu_set_library_path.argtypes = [C.c_char_p]
+        L.sqrefgpu_session_create.restype = C.c_void_p
+        L.sqrefgpu_session_create.argtypes = [C.c_int, _dp, C.c_int, C.c_int, C.c_int, _gp, C.c_int, _dp]
+        L.sqrefgpu_session_free.argtypes = [C.c_void_p]
+        L.sqrefgpu_param_num.argtypes = [C.c_void_p]
+        L.sqrefgpu_set_cost.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]
+        L.sqrefgpu_cost_grad.argtypes = [C.c_void_p, _dp, C.c_int, _dp, _dp]
+        L.sqrefgpu_cost.argtypes = [C.c_void_p, _dp, C.c_int, _dp]
+        L.sqrefgpu_cost_batched.argtypes = [C.c_void_p, _dp, C.c_int, C.c_int, _dp]
+        L.sqrefgpu_optimize.argtypes = [C.c_void_p, C.c_int, _dp, C.c_int, C.c_longlong, C.c_double, _dp, _dp]
+        L.sqrefgpu_get_log.argtypes = [C.c_void_p, _dp, _dp, _dp]
+        L.sqrefgpu_gpu_evaluations.argtypes = [C.c_void_p]
+        L.sqrefgpu_gpu_evaluations.restype = C.c_longlong
+        L.sqrefgpu_flatten.argtypes = [C.c_int, _gp, C.c_int, _dp, _gp, C.c_int, _dp, C.c_longlong, C.POINTER(C.c_longlong)]
+        L.sqrefgpu_set_library_path(abi.LIB_PATH.encode())
+
+    def _err(self):
+        return self.lib.sqrefgpu_last_error().decode("utf-8", "replace")
+
+    def available_gpus(self):
+        return int(self.lib.sqrefgpu_available_gpus())
+
+    def flatten(self, qbit_num, descs_nested, pool=None):
+        """(flat descs, pool) as integration/common_GPU.cpp: to_gpu_gates makes them from the reference's Gates_block"""
+        d, dptr = _descs(descs_nested)
+        pl = _c128(pool) if pool is not None else np.zeros(0, dtype=np.complex128)
+        out = np.zeros(len(d) + 1, dtype=abi.GATE_DESC_DTYPE)
+        pool_out = np.zeros(max(pl.size, 1), dtype=np.complex128)
+        plen = C.c_longlong(0)
+        n = self.lib.sqrefgpu_flatten(qbit_num, dptr, len(d), _dptr(pl.view(np.float64)), out.ctypes.data_as(_gp), len(out),
+                                      _dptr(pool_out.view(np.float64)), pool_out.size, C.byref(plen))
+        if n < 0:
+            raise Exception("ref_gpu: flatten failed: " + self._err())
+        return out[:n].copy(), pool_out[: plen.value].copy()
+
+    def session(self, use_gpu, umtx, qbit_num, descs_nested, pool=None):
+        return RefGpuSession(self, use_gpu, umtx, qbit_num, descs_nested, pool)
+
+
+class RefGpuSession:
+    ADAM, BFGS = 0, 1  # enum optimization_aglorithms (Optimization_Interface.h:50)
+
+    def __init__(self, ref, use_gpu, umtx, qbit_num, descs, pool=None):
+        self.ref = ref
+        U = _c128(umtx)
+        d, dptr = _descs(descs)
+        pl = _c128(pool) if pool is not None else np.zeros(0, dtype=np.complex128)
+        self.h = ref.lib.sqrefgpu_session_create(1 if use_gpu else 0, _dptr(U.view(np.float64)), U.shape[0], U.shape[1], qbit_num,
+                                                 dptr, len(d), _dptr(pl.view(np.float64)))
+        if not self.h:
+            raise Exception("ref_gpu: session_create failed: " + ref._err())
+        self.n_params = ref.lib.sqrefgpu_param_num(self.h)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.ref.lib.sqrefgpu_session_free(self.h)
+            self.h = None
+
+    def set_cost(self, variant=0, trace_offset=0, prev=1.0, c1=1 / 1.7, c2=0.5):
+        if self.ref.lib.sqrefgpu_set_cost(self.h, variant, trace_offset, prev, c1, c2):
+            raise Exception("ref_gpu: set_cost failed: " + self.ref._err())
+
+    def cost_grad(self, params):
+        p = _f64(params)
+        out = np.zeros(1)
+        g = np.zeros(max(p.size, 1))
+        if self.ref.lib.sqrefgpu_cost_grad(self.h, _dptr(p), p.size, _dptr(out), _dptr(g)):
+            raise Exception("ref_gpu: cost_grad failed: " + self.ref._err())
+        return float(out[0]), g[: p.size]
+
+    def cost(self, params):
+        p = _f64(params)
+        out = np.zeros(1)
+        if self.ref.lib.sqrefgpu_cost(self.h, _dptr(p), p.size, _dptr(out)):
+            raise Exception("ref_gpu: cost failed: " + self.ref._err())
+        return float(out[0])
+
+    def cost_batched(self, params):
+        p = _f64(params)
+        out = np.zeros(p.shape[0])
+        if self.ref.lib.sqrefgpu_cost_batched(self.h, _dptr(p), p.shape[1], p.shape[0], _dptr(out)):
+            raise Exception("ref_gpu: cost_batched failed: " + self.ref._err())
+        return out
+
+    def optimize(self, alg, x0, max_inner_iterations, eta=1e-3):
+        """run the reference's optimizer; returns (x_final, f_min, log) with log = dict(params [n, P], cost [n], grad [n, P]) of
+        every cost+gradient evaluation it made, in order"""
+        x0 = _f64(x0)
+        x = np.zeros_like(x0)
+        f = np.zeros(1)
+        n = self.ref.lib.sqrefgpu_optimize(self.h, int(alg), _dptr(x0), x0.size, int(max_inner_iterations), float(eta), _dptr(x), _dptr(f))
+        if n < 0:
+            raise Exception("ref_gpu: optimize failed: " + self.ref._err())
+        P = x0.size
+        lp, lc, lg = np.zeros((n, P)), np.zeros(n), np.zeros((n, P))
+        if n and self.ref.lib.sqrefgpu_get_log(self.h, _dptr(lp), _dptr(lc), _dptr(lg)):
+            raise Exception("ref_gpu: get_log failed: " + self.ref._err())
+        return x, float(f[0]), {"params": lp, "cost": lc, "grad": lg}
+
+    def gpu_evaluations(self):
+        return int(self.ref.lib.sqrefgpu_gpu_evaluations(self.h))
