@@ -168,6 +168,11 @@ int sqgpu_plan_stats(const sqgpu_gate_desc* gates, int n_gates, int n_params, in
 int sqgpu_plan_stats_opt(const sqgpu_gate_desc* gates, int n_gates, int n_params, int qbit_num, const double* matrix_pool,
                          int64_t pool_len, const char* options, int64_t* stats, int n_stats);
 
+/* The op list the planner produces, for inspection (docs, tests): ops[i*8 .. i*8+8) = {dim, q0..q4 (-1: unused), n_params,
+ * n_members} of op i; which = 2 / 3: the <=2- / <=3-qubit block plans, 0: the window plan in segment order. No device needed. */
+int sqgpu_plan_ops(const sqgpu_gate_desc* gates, int n_gates, int n_params, int qbit_num, const double* matrix_pool,
+                   int64_t pool_len, const char* options, int which, int32_t* ops, int cap, int* n_ops);
+
 /* Per-handle switches; the defaults are the product configuration. They are what the reference keeps in its `config` map
  * (Decomposition_Base::config, e.g. "use_float", "parallel"; Decomposition_Base.cpp:1115-1190) for this path. Planner
  * options take effect with the next sqgpu_set_circuit. Names:

@@ -142,6 +142,8 @@ PROTOTYPES = {
     "sqgpu_set_circuit": (C.c_int, [_handle, C.POINTER(GateDesc), C.c_int, C.c_int, C.c_int, _dp, C.c_int64]),
     "sqgpu_plan_stats": (C.c_int, [C.POINTER(GateDesc), C.c_int, C.c_int, C.c_int, _dp, C.c_int64, C.POINTER(C.c_int64), C.c_int]),
     "sqgpu_plan_stats_opt": (C.c_int, [C.POINTER(GateDesc), C.c_int, C.c_int, C.c_int, _dp, C.c_int64, C.c_char_p, C.POINTER(C.c_int64), C.c_int]),
+    "sqgpu_plan_ops": (C.c_int, [C.POINTER(GateDesc), C.c_int, C.c_int, C.c_int, _dp, C.c_int64, C.c_char_p, C.c_int, _ip, C.c_int,
+                                 C.POINTER(C.c_int)]),
     "sqgpu_set_option": (C.c_int, [_handle, C.c_char_p, C.c_int64]),
     "sqgpu_get_option": (C.c_int, [_handle, C.c_char_p, C.POINTER(C.c_int64)]),
     "sqgpu_set_cost": (C.c_int, [_handle, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]),
@@ -232,3 +234,19 @@ def plan_stats(circuit, **options):
                                         circuit.qbit_num, as_dp(pool.view(np.float64)) if pool.size else None, pool.size,
                                         opts, out, len(PLAN_STATS)))
     return dict(zip(PLAN_STATS, (int(v) for v in out)))
+
+
+def plan_ops(circuit, which=3, **options):
+    """[(dim, [qubits], n_params, n_members)] of the planner's op list (sqgpu_plan_ops); which = 2, 3 or 0 (window plan)"""
+    lib = load_library()
+    descs, pool = circuit.descriptors()
+    descs = np.ascontiguousarray(descs, dtype=GATE_DESC_DTYPE)
+    pool = np.ascontiguousarray(pool, dtype=np.complex128)
+    cap = len(descs) + 1
+    out = np.zeros((cap, 8), dtype=np.int32)
+    n = C.c_int(0)
+    opts = ",".join("%s=%d" % (k, int(v)) for k, v in options.items()).encode() or None
+    check(lib, lib.sqgpu_plan_ops(descs.ctypes.data_as(C.POINTER(GateDesc)), len(descs), circuit.get_Parameter_Num(),
+                                  circuit.qbit_num, as_dp(pool.view(np.float64)) if pool.size else None, pool.size, opts,
+                                  int(which), as_ip(out), cap, C.byref(n)))
+    return [(int(r[0]), [int(q) for q in r[1:6] if q >= 0], int(r[6]), int(r[7])) for r in out[: n.value]]

@@ -289,10 +289,13 @@ struct BlockGeom {
 
 // Per-(parameter set, op) lookup table of the DMMA block path, written by build_optabs and prefetched into shared memory
 // with cp.async while the previous op runs (double-buffered).
+static const int B0TAB = 64;  // batch bases precomputed per op (tiles with more batches fall back to the index arithmetic)
+
 struct OpTab {
     double frag[3][8][32];  // [mode: K, K^dagger, K^T][t * KS + s][lane]: kernel (B operand) fragments
     int slot[4][32];        // [u]: load/store slot of amplitude dep(j, u); [2 + h]: W' operand slot of item half h
     int widx[32];           // 3-qubit blocks: positions of the lane's two W' outputs, idx0 | idx1 << 8
+    int b0[B0TAB];          // B0 (complex units) of the batch of items [8 i, 8 i + 8): the op's qubits inserted as zeros, then elem()
 };
 
 // shared-memory copy of the part of an OpTab one sweep direction needs: the forward sweep takes frag[0] (K), the backward
@@ -301,7 +304,9 @@ struct OpTabS {
     double frag[2][8][32];
     int slot[4][32];
     int widx[32];
+    int b0[B0TAB];
 };
+static_assert(sizeof(OpTab) % 16 == 0 && sizeof(OpTabS) % 16 == 0, "bulk copies move multiples of 16 bytes");
 
 // local amplitude index from the lane's amplitude slot j (2 bits) and the k-step pair u: block-qubit position ju carries u
 __device__ __forceinline__ int dep3(int j, int u, int ju) {
@@ -358,6 +363,7 @@ __device__ __forceinline__ void fill_optab(OpTab* T, const DevOp& op, const cplx
             const int r = permw3(lane >> 2, pa), c0 = permw3(2 * (lane & 3), pa), c1 = permw3(2 * (lane & 3) + 1, pa);
             T->widx[lane] = (r * 8 + c0) | ((r * 8 + c1) << 8);
         }
+        for (int i = tid; i < B0TAB; i += nthr) T->b0[i] = G.batch_base(8 * i);
     } else {
         BlockGeom<LOG_CT, 2> G;
         G.init(op.q[0], op.q[1], 30);
@@ -371,6 +377,7 @@ __device__ __forceinline__ void fill_optab(OpTab* T, const DevOp& op, const cplx
             // W' operands of 2-qubit blocks are single doubles: component m of item kk + 4h (double units)
             T->slot[sidx][lane] = (sidx < 2) ? G.slot(m, kk) : 2 * G.slot(kk + 4 * (sidx - 2), m >> 1) + (m & 1);
         }
+        for (int i = tid; i < B0TAB; i += nthr) T->b0[i] = G.batch_base(8 * i);
     }
 }
 
@@ -392,8 +399,7 @@ __global__ void build_optabs(const DevOp* __restrict__ ops, int n_ops, const cpl
 
 // forward: x <- K x for every group of the tile. One warp handles 8 (group, column) items per step.
 template <int LOG_CT, int KQ>
-__device__ __forceinline__ void block_dmma_forward(cplx* sa, const OpTabS* T, const BlockGeom<LOG_CT, KQ>& G, int rows, int tid,
-                                                   int nthr) {
+__device__ __forceinline__ void block_dmma_forward(cplx* sa, const OpTabS* T, int q0, int q1, int q2, int rows, int tid, int nthr) {
     constexpr int NT = (KQ == 3) ? 2 : 1, KS = 2 * NT;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
     double kf[NT][KS];
@@ -405,8 +411,11 @@ __device__ __forceinline__ void block_dmma_forward(cplx* sa, const OpTabS* T, co
         for (int s = 0; s < KS; ++s) kf[t][s] = T->frag[0][t * KS + s][lane];
     }
     const int nitems = (rows >> KQ) << LOG_CT;
+    const bool tab_b0 = nitems <= 8 * B0TAB;  // batch bases from the op table: no index arithmetic in the loop
+    BlockGeom<LOG_CT, KQ> G;
+    if (!tab_b0) G.init(q0, q1, q2);
     for (int b0 = warp * 8; b0 < nitems; b0 += nwarps * 8) {
-        const int B0 = G.batch_base(b0);
+        const int B0 = tab_b0 ? T->b0[b0 >> 3] : G.batch_base(b0);
         cplx x[NT], d[NT];
 #pragma unroll
         for (int u = 0; u < NT; ++u) {
@@ -428,7 +437,7 @@ __device__ __forceinline__ void block_dmma_forward(cplx* sa, const OpTabS* T, co
 // backward step of the adjoint sweep: W' += beta p^T (outer product over items), a <- K^dagger p, beta <- K^T beta, all on
 // DMMA; the warp's W' (DIM x DIM complex) is written to wslot after the loop.
 template <int LOG_CT, int KQ>
-__device__ __forceinline__ void block_dmma_backward(cplx* sa, cplx* sb, const OpTabS* T, const BlockGeom<LOG_CT, KQ>& G, int rows,
+__device__ __forceinline__ void block_dmma_backward(cplx* sa, cplx* sb, const OpTabS* T, int q0, int q1, int q2, int rows,
                                                     bool has_w, cplx* wslot, int tid, int nthr) {
     constexpr int DIM = 1 << KQ, NT = (KQ == 3) ? 2 : 1, KS = 2 * NT;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
@@ -451,8 +460,11 @@ __device__ __forceinline__ void block_dmma_backward(cplx* sa, cplx* sb, const Op
 #pragma unroll
         for (int b = 0; b < NT; ++b) pacc[a][b][0] = pacc[a][b][1] = 0.0;
     const int nitems = (rows >> KQ) << LOG_CT;
+    const bool tab_b0 = nitems <= 8 * B0TAB;
+    BlockGeom<LOG_CT, KQ> G;
+    if (!tab_b0) G.init(q0, q1, q2);
     for (int b0 = warp * 8; b0 < nitems; b0 += nwarps * 8) {
-        const int B0 = G.batch_base(b0);
+        const int B0 = tab_b0 ? T->b0[b0 >> 3] : G.batch_base(b0);
         cplx p[NT], be[NT], da[NT], db[NT];
 #pragma unroll
         for (int u = 0; u < NT; ++u) {
@@ -721,7 +733,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
     cplx* sk = HAS_B ? sb + (size_t)rows * CT : sb;                       // raw dense kernel staging
     cplx* skm = sk + A.dense_stage;                                       // [2][KM_ELEMS] prefetched block kernels
     OpTabS* stab = reinterpret_cast<OpTabS*>(skm + 2 * KM_ELEMS);         // [TAB_RING] DMMA block lookup tables (one sweep direction)
-    cplx* swarp = reinterpret_cast<cplx*>(stab + TAB_RING);               // [2][nwarps][wmax]
+    unsigned long long* tbar = reinterpret_cast<unsigned long long*>(stab + TAB_RING);  // [TAB_RING] mbarriers of the table ring
+    cplx* swarp = reinterpret_cast<cplx*>(tbar + TAB_RING);               // [2][nwarps][wmax]
     cplx* swacc = swarp + (HAS_B ? 2 * nwarps * A.wmax : 0);              // [w_total] if w_in_smem
     double* sred = reinterpret_cast<double*>(swacc + ((HAS_B && A.w_in_smem) ? A.w_total : 0));  // [nwarps][6]
     SOp* sops = reinterpret_cast<SOp*>(sred + nwarps * 6);               // [n_ops]
@@ -763,39 +776,53 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
     // kernel element this thread prefetches for op k (threads 0..63)
     auto kernel_elem = [&](int k) -> cplx {
         const SOp s = sops[k];
-        if (s.kind == 1 || tid >= s.dim * s.dim) return czero();
+        if (s.kind != 0 || tid >= s.dim * s.dim) return czero();  // only the scalar 2 x 2 path reads the staged kernel
         const cplx* K = s.kern_off >= 0 ? ktab + s.kern_off : A.pool + (((long long)s.pool_hi << 32) | (unsigned)s.pool_lo);
         return K[tid];
     };
 
-    // DMMA block table of op k: built per (parameter set, op) by build_optabs; copied global -> shared with cp.async while
-    // the previous op computes (no registers held across the DMMA loops), into stab[k & 1]
+    // DMMA block table of op k: built per (parameter set, op) by build_optabs. ONE thread requests it with two bulk-async
+    // copies (cp.async.bulk, the TMA engine: no registers, no per-thread address arithmetic, no instruction issue in the
+    // other 255 threads) into ring slot k % TAB_RING while earlier ops compute; completion is signalled on the slot's
+    // mbarrier (expect_tx / complete_tx), which every thread waits on (tab_acquire) right before it reads the table. Tables
+    // are requested TAB_RING - 1 ops ahead; a slot is rewritten only after the end-of-op barrier of its previous user.
     const OpTab* __restrict__ gtabs = A.optabs + (size_t)kset * (A.optab_stride ? A.optab_stride : A.n_ops);
+    if (tid == 0) {
+        for (int i = 0; i < TAB_RING; ++i)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(tbar + i)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    unsigned tab_parity = 0;  // bit s: phase parity the next wait on ring slot s expects (identical in every thread)
     auto tab_prefetch = [&](int k, bool bwd) {
-        if (k < 0 || k >= A.n_ops || sops[k].kind != 2) return;
+        if (tid != 0 || k < 0 || k >= A.n_ops || sops[k].kind != 2) return;
         const char* src = reinterpret_cast<const char*>(gtabs + k);
-        const unsigned dst = (unsigned)__cvta_generic_to_shared(stab + (k & (TAB_RING - 1)));
-        constexpr int FRAG = 8 * 32 * 8, TAIL = (int)(sizeof(OpTabS) - 2 * FRAG);  // bytes of one fragment set / of slots + widx
+        const int slot = k & (TAB_RING - 1);
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(stab + slot);
+        const unsigned bar = (unsigned)__cvta_generic_to_shared(tbar + slot);
+        constexpr int FRAG = 8 * 32 * 8, TAIL = (int)(sizeof(OpTabS) - 2 * FRAG);  // bytes of one fragment set / of slots + widx + b0
         const int nfrag = bwd ? 2 * FRAG : FRAG, src_off = bwd ? FRAG : 0;
-        for (int e = tid; e < (nfrag + TAIL) / 16; e += nthr) {
-            const int b = e * 16;
-            const int d_off = (b < nfrag) ? b : 2 * FRAG + (b - nfrag);
-            const int s_off = (b < nfrag) ? src_off + b : 3 * FRAG + (b - nfrag);
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + d_off), "l"(src + s_off));
-        }
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(nfrag + TAIL) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                     "l"(src + src_off), "r"(nfrag), "r"(bar)
+                     : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + 2 * FRAG),
+                     "l"(src + 3 * FRAG), "r"(TAIL), "r"(bar)
+                     : "memory");
     };
-    // One cp.async group per op, committed in sweep order (empty for ops without a table). Tables are requested
-    // TAB_RING - 1 ops ahead: when an op ends, "at most TAB_RING - 2 groups pending" means the NEXT op's table has landed
-    // even when the ops are much shorter than an L2 round trip (small matrices: the latency-bound case).
-    auto tab_commit = [&]() { asm volatile("cp.async.commit_group;" ::: "memory"); };
-    auto tab_wait = [&]() { asm volatile("cp.async.wait_group %0;" ::"n"(TAB_RING - 2) : "memory"); };
+    auto tab_acquire = [&](int k) {  // the table of op k (a DMMA block op) has landed in its ring slot
+        const int slot = k & (TAB_RING - 1);
+        const unsigned bar = (unsigned)__cvta_generic_to_shared(tbar + slot);
+        const unsigned parity = (tab_parity >> slot) & 1u;
+        unsigned done;
+        do {
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        } while (!done);
+        tab_parity ^= 1u << slot;
+    };
     auto tab_prime = [&](int first, int step, bool bwd) {  // requests for the first TAB_RING - 1 ops of a sweep
 #pragma unroll
-        for (int j = 0; j < TAB_RING - 1; ++j) {
-            tab_prefetch(first + j * step, bwd);
-            tab_commit();
-        }
-        tab_wait();
+        for (int j = 0; j < TAB_RING - 1; ++j) tab_prefetch(first + j * step, bwd);
     };
 
     for (int ti = 0; ti < A.tiles_per_cta; ++ti) {
@@ -855,18 +882,11 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
             const bool have_next = k + 1 < A.n_ops;
             if (have_next && tid < KM_ELEMS) next_elem = kernel_elem(k + 1);
             tab_prefetch(k + TAB_RING - 1, false);
-            tab_commit();
             const cplx* __restrict__ km = skm + (k & 1) * KM_ELEMS;
             if (s.kind == 2) {
-                if (s.dim == 8) {
-                    BlockGeom<LOG_CT, 3> G;
-                    G.init(s.q0, s.q1, s.q2);
-                    block_dmma_forward<LOG_CT, 3>(sa, stab + (k & (TAB_RING - 1)), G, rows, tid, nthr);
-                } else {
-                    BlockGeom<LOG_CT, 2> G;
-                    G.init(s.q0, s.q1, 30);
-                    block_dmma_forward<LOG_CT, 2>(sa, stab + (k & (TAB_RING - 1)), G, rows, tid, nthr);
-                }
+                tab_acquire(k);
+                if (s.dim == 8) block_dmma_forward<LOG_CT, 3>(sa, stab + (k & (TAB_RING - 1)), s.q0, s.q1, s.q2, rows, tid, nthr);
+                else block_dmma_forward<LOG_CT, 2>(sa, stab + (k & (TAB_RING - 1)), s.q0, s.q1, 30, rows, tid, nthr);
             } else if (s.kind == 0) {
                 const cplx k00 = km[0], k01 = km[1], k10 = km[2], k11 = km[3];
                 const int tbit = 1 << s.q0;
@@ -982,7 +1002,6 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                 }
             }
             if (have_next && tid < KM_ELEMS) skm[((k + 1) & 1) * KM_ELEMS + tid] = next_elem;
-            tab_wait();
             __syncthreads();
         }
 
@@ -1109,22 +1128,15 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                 const bool have_next = k > 0;
                 if (have_next && tid < KM_ELEMS) next_elem = kernel_elem(k - 1);
                 tab_prefetch(k - (TAB_RING - 1), true);
-                tab_commit();
                 const bool has_w = s.w_off >= 0;
                 cplx* wslot_c = swarp + (size_t)(buf * nwarps + warp) * A.wmax;
                 double* wslot = reinterpret_cast<double*>(wslot_c);
                 const cplx* __restrict__ km = skm + (k & 1) * KM_ELEMS;
                 int wdim = s.dim;
                 if (s.kind == 2) {
-                    if (s.dim == 8) {
-                        BlockGeom<LOG_CT, 3> G;
-                        G.init(s.q0, s.q1, s.q2);
-                        block_dmma_backward<LOG_CT, 3>(sa, sb, stab + (k & (TAB_RING - 1)), G, rows, has_w, wslot_c, tid, nthr);
-                    } else {
-                        BlockGeom<LOG_CT, 2> G;
-                        G.init(s.q0, s.q1, 30);
-                        block_dmma_backward<LOG_CT, 2>(sa, sb, stab + (k & (TAB_RING - 1)), G, rows, has_w, wslot_c, tid, nthr);
-                    }
+                    tab_acquire(k);
+                    if (s.dim == 8) block_dmma_backward<LOG_CT, 3>(sa, sb, stab + (k & (TAB_RING - 1)), s.q0, s.q1, s.q2, rows, has_w, wslot_c, tid, nthr);
+                    else block_dmma_backward<LOG_CT, 2>(sa, sb, stab + (k & (TAB_RING - 1)), s.q0, s.q1, 30, rows, has_w, wslot_c, tid, nthr);
                 } else if (s.kind == 0) {
                     const cplx k00 = km[0], k01 = km[1], k10 = km[2], k11 = km[3];
                     const int tbit = 1 << s.q0;
@@ -1225,17 +1237,31 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                     }
                 }
                 if (have_next && tid < KM_ELEMS) skm[((k - 1) & 1) * KM_ELEMS + tid] = next_elem;
-                tab_wait();
                 __syncthreads();
                 if (has_w) {
                     const int nd = 2 * wdim * wdim;  // doubles
-                    for (int e = tid; e < nd; e += nthr) {
-                        double sum = 0;
-                        for (int w = 0; w < nwarps; ++w)
-                            sum += reinterpret_cast<const double*>(swarp + (size_t)(buf * nwarps + w) * A.wmax)[e];
-                        if (A.w_in_smem) reinterpret_cast<double*>(swacc + s.w_off)[e] += sum;
-                        else
-                            atomicAdd(reinterpret_cast<double*>(A.w_part + ((size_t)y * nchunks + chunk) * A.w_total + s.w_off) + e, sum);
+                    if (A.w_in_smem) {
+                        for (int e = tid; e < nd; e += nthr) {
+                            double sum = 0;
+                            for (int w = 0; w < nwarps; ++w)
+                                sum += reinterpret_cast<const double*>(swarp + (size_t)(buf * nwarps + w) * A.wmax)[e];
+                            reinterpret_cast<double*>(swacc + s.w_off)[e] += sum;
+                        }
+                    } else {
+                        // every thread takes part: the warps' partials of one element are split over `parts` threads (a power
+                        // of two), each of which folds its share in a fixed order and issues one fire-and-forget reduction;
+                        // the reductions of one address are issued in thread order by one CTA, and each CTA owns its slice
+                        int parts = 1;
+                        while (2 * parts * nd <= nthr && 2 * parts <= nwarps) parts *= 2;
+                        const int per = nwarps / parts;
+                        double* dst = reinterpret_cast<double*>(A.w_part + ((size_t)y * nchunks + chunk) * A.w_total + s.w_off);
+                        for (int e2 = tid; e2 < nd * parts; e2 += nthr) {
+                            const int e = e2 % nd, part = e2 / nd;
+                            double sum = 0;
+                            for (int w = part * per; w < (part + 1) * per; ++w)
+                                sum += reinterpret_cast<const double*>(swarp + (size_t)(buf * nwarps + w) * A.wmax)[e];
+                            atomicAdd(dst + e, sum);
+                        }
                     }
                     buf ^= 1;
                 }

@@ -678,6 +678,7 @@ size_t fused_smem(int mode, int rows, int ct, int threads, int dense_stage, int 
     s += (size_t)dense_stage * sizeof(cplx);
     s += 2 * KM_ELEMS * sizeof(cplx);        // prefetched block kernels
     s += TAB_RING * sizeof(OpTabS);          // ring of DMMA block lookup tables of one sweep direction
+    s += TAB_RING * sizeof(unsigned long long);  // ... and their mbarriers
     s += (size_t)n_ops * sizeof(SOp);        // staged op table
     const int nwarps = threads / 32;
     if (has_b) {
@@ -1652,6 +1653,33 @@ int sqgpu_plan_stats_opt(const sqgpu_gate_desc* gates, int n_gates, int n_params
                                              tmp->plan3.kern_total, tmp->plan3.dkern_total, tmp->plan3.w_total,
                                              tmp->plan3.n_dense + tmp->plan3.n_dense5, (int64_t)tmp->plan3.members.size()};
         for (int i = 0; i < n_stats && i < SQGPU_PLAN_STATS; ++i) stats[i] = v[i];
+    }
+    delete tmp;
+    return rc;
+}
+
+// ops[i*8 .. i*8+8) = {dim, q0, q1, q2, q3, q4, n_params, n_members} of op i of the chosen plan (2: <=2-qubit blocks, 3: <=3-qubit
+// blocks, 0: the window plan in segment order); unused qubit slots are -1. Returns the number of ops through *n_ops.
+int sqgpu_plan_ops(const sqgpu_gate_desc* gates, int n_gates, int n_params, int qbit_num, const double* matrix_pool,
+                   int64_t pool_len, const char* options, int which, int32_t* ops, int cap, int* n_ops) {
+    if (!n_ops) return fail(SQGPU_ERR_INVALID, "NULL n_ops");
+    sqgpu_ctx* tmp = new sqgpu_ctx();
+    int rc = options_parse(tmp->opt, options);
+    if (rc == SQGPU_OK) rc = set_circuit_impl(tmp, gates, n_gates, n_params, qbit_num, matrix_pool, pool_len, false);
+    if (rc == SQGPU_OK) {
+        const Plan& P = which == 2 ? tmp->plan2 : (which == 3 ? tmp->plan3 : tmp->planW);
+        *n_ops = (int)P.ops.size();
+        for (int i = 0; i < (int)P.ops.size() && i < cap; ++i) {
+            const DevOp& op = P.ops[i];
+            int32_t* o = ops + (size_t)i * 8;
+            o[0] = op.dim;
+            for (int j = 0; j < 5; ++j) o[1 + j] = -1;
+            if (op.dim == 2) o[1] = op.target;
+            else
+                for (int j = 0; j < op.nq && j < 5; ++j) o[1 + j] = op.q[j];
+            o[6] = op.n_params;
+            o[7] = op.n_members;
+        }
     }
     delete tmp;
     return rc;
