@@ -137,6 +137,21 @@ int sqgpu_create(int device, sqgpu_handle_t* out);
 /* replaces releive_DFE (common_DFE.cpp:49,110-113). */
 int sqgpu_destroy(sqgpu_handle_t h);
 
+/* replaces initialize_DFE(accelerator_num) for accelerator_num = G > 1 and the reference's split of the batched cost path over
+ * accelerators / MPI ranks (Optimization_Interface.cpp:806-832, 962-1004): ONE handle over n_devices GPUs of this process
+ * (devices = NULL: 0 .. n_devices-1). The handle takes the same calls as a single-device one -- sqgpu_upload_matrix,
+ * sqgpu_set_circuit, sqgpu_set_cost, sqgpu_set_option, sqgpu_cost_batched, sqgpu_cost_grad_batched, sqgpu_set_hamiltonian_csr,
+ * sqgpu_vqe_energy[_grad]_batched, sqgpu_destroy -- and shards the work itself:
+ *   SQGPU_SHARD_BATCH    parameter vectors over the devices, results written straight into the caller's arrays;
+ *   SQGPU_SHARD_COLUMNS  columns of the matrix over the devices, one ncclAllReduce of the raw trace terms per evaluation on
+ *                        the devices' compute streams (two for the Hilbert-Schmidt correction variants);
+ *   SQGPU_SHARD_AUTO     columns for matrices with >= 2048 columns (n >= 11), batch otherwise (and for state vectors).
+ * The device-pointer (_dev), apply and raw-trace entry points are per device: they fail with SQGPU_ERR_UNSUPPORTED here. */
+typedef enum sqgpu_shard_mode { SQGPU_SHARD_AUTO = 0, SQGPU_SHARD_BATCH = 1, SQGPU_SHARD_COLUMNS = 2 } sqgpu_shard_mode;
+int sqgpu_create_multi(int n_devices, const int* devices, int mode, sqgpu_handle_t* out);
+/* number of devices behind a handle (1 for sqgpu_create) and the sharding mode in force after the last upload */
+int sqgpu_multi_info(sqgpu_handle_t h, int* n_devices, int* mode);
+
 /* text of the last failure on the calling thread ("" if none). Never NULL. */
 const char* sqgpu_last_error(void);
 
@@ -259,6 +274,17 @@ int sqgpu_traces_batched_dev(sqgpu_handle_t h, const double* d_params, int batch
                              void* stream);
 int sqgpu_cost_from_traces_dev(sqgpu_handle_t h, const double* d_traces, int batch, int with_grad, int cols_total,
                                double* d_cost, double* d_grad, void* stream);
+/* Column sharding driven from OUTSIDE the library (one process per GPU, torch.distributed / MPI for the exchange; the
+ * reference's rectangular-Umtx + trace_offset semantics, N_Qubit_Decomposition_Cost_Function.cpp:147-153): the resident matrix
+ * of this handle is U[:, col_begin : col_begin + cols) of a matrix with cols_total columns. The shard's row offset then enters
+ * the trace terms of EVERY cost variant (the user's trace_offset keeps entering the Frobenius family only, as in the
+ * reference). col_begin = 0, cols_total = 0 switches sharding off. */
+int sqgpu_set_shard(sqgpu_handle_t h, int col_begin, int cols_total);
+/* gradient traces of a column shard for the Hilbert-Schmidt correction variants (4, 5), whose gradient functional takes its
+ * weights from the traces of the circuit itself: d_global_traces0 [batch][3][2] = sqgpu_traces_batched_dev(with_grad = 0)
+ * summed over all shards. For every other variant sqgpu_traces_batched_dev(with_grad = 1) is enough. */
+int sqgpu_grad_traces_with_global_dev(sqgpu_handle_t h, const double* d_params, int batch, const double* d_global_traces0,
+                                      double* d_traces, void* stream);
 int sqgpu_apply_gate_dev(sqgpu_handle_t h, const sqgpu_gate_desc* gate, const double* gate_params,
                          const double* matrix_pool, int deriv_param, double* d_inout, int rows, int cols, int stride,
                          void* stream);

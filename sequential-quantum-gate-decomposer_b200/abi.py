@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "csrc", "libsqgpu.so")
+# SQGPU_LIB selects another build of the same library (kernel-experiment variants, profiles/variants.py); host-side only
+LIB_PATH = os.environ.get("SQGPU_LIB") or os.path.join(PKG_DIR, "csrc", "libsqgpu.so")
 
 # ---- enum sqgpu_gate_type -------------------------------------------------------------------------------------
 GENERAL = 1
@@ -78,6 +79,11 @@ HILBERT_SCHMIDT_TEST_CORRECTION2 = 5
 SUM_OF_SQUARES = 6
 INFIDELITY = 9
 
+# ---- enum sqgpu_shard_mode ------------------------------------------------------------------------------------
+SHARD_AUTO = 0
+SHARD_BATCH = 1
+SHARD_COLUMNS = 2
+
 # ---- enum sqgpu_status ----------------------------------------------------------------------------------------
 OK = 0
 ERR_NO_DEVICE = -1
@@ -136,6 +142,10 @@ PROTOTYPES = {
     "sqgpu_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "sqgpu_create": (C.c_int, [C.c_int, C.POINTER(_handle)]),
     "sqgpu_destroy": (C.c_int, [_handle]),
+    "sqgpu_create_multi": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(_handle)]),
+    "sqgpu_multi_info": (C.c_int, [_handle, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "sqgpu_set_shard": (C.c_int, [_handle, C.c_int, C.c_int]),
+    "sqgpu_grad_traces_with_global_dev": (C.c_int, [_handle, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sqgpu_last_error": (C.c_char_p, []),
     "sqgpu_abi_version": (C.c_int, []),
     "sqgpu_upload_matrix": (C.c_int, [_handle, _dp, C.c_int, C.c_int, C.c_int]),

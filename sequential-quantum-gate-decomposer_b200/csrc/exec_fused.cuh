@@ -290,6 +290,21 @@ struct BlockGeom {
 // Per-(parameter set, op) lookup table of the DMMA block path, written by build_optabs and prefetched into shared memory
 // with cp.async while the previous op runs (double-buffered).
 static const int B0TAB = 64;  // batch bases precomputed per op (tiles with more batches fall back to the index arithmetic)
+// Where the DMMA loops get the base address of a batch from (compile-time switch; measured on B200, C3 / C5 energy,
+// profiles/r2_variants.jsonl):
+//   0: index arithmetic at the top of every iteration (1 245 evals/s / 2 458);  1: the per-op table b0[] in shared memory
+//   (1 243 / 2 534, the default);  2: index arithmetic for the NEXT batch issued before the current batch's DMMAs (1 228 / 2 429)
+#ifndef SQ_B0_MODE
+#define SQ_B0_MODE 1
+#endif
+// How the op tables travel to shared memory: 0 (default): per-thread cp.async (LDGSTS) groups; 1: bulk-async copies issued by
+// one thread (cp.async.bulk, the TMA engine: UBLKCP in SASS) with mbarrier completion. Measured: the bulk ring is 2.2 % SLOWER
+// on C3 (1 217 vs 1 245 evals/s) and 1.5 % on C5 -- a 4.9 KB table per ~3 us op is too small for the TMA engine to beat 1.2
+// LDGSTS per thread, and the mbarrier try_wait (60-90 cycles) lands on every warp's critical path once per op. Kept as a
+// switch with its measurement; not the product configuration.
+#ifndef SQ_TAB_BULK
+#define SQ_TAB_BULK 0
+#endif
 
 struct OpTab {
     double frag[3][8][32];  // [mode: K, K^dagger, K^T][t * KS + s][lane]: kernel (B operand) fragments
@@ -411,11 +426,13 @@ __device__ __forceinline__ void block_dmma_forward(cplx* sa, const OpTabS* T, in
         for (int s = 0; s < KS; ++s) kf[t][s] = T->frag[0][t * KS + s][lane];
     }
     const int nitems = (rows >> KQ) << LOG_CT;
-    const bool tab_b0 = nitems <= 8 * B0TAB;  // batch bases from the op table: no index arithmetic in the loop
+    const bool tab_b0 = (SQ_B0_MODE == 1) && nitems <= 8 * B0TAB;
     BlockGeom<LOG_CT, KQ> G;
     if (!tab_b0) G.init(q0, q1, q2);
+    int B0next = (SQ_B0_MODE == 2) ? G.batch_base(warp * 8) : 0;
     for (int b0 = warp * 8; b0 < nitems; b0 += nwarps * 8) {
-        const int B0 = tab_b0 ? T->b0[b0 >> 3] : G.batch_base(b0);
+        const int B0 = (SQ_B0_MODE == 2) ? B0next : (tab_b0 ? T->b0[b0 >> 3] : G.batch_base(b0));
+        if (SQ_B0_MODE == 2) B0next = G.batch_base(b0 + nwarps * 8);
         cplx x[NT], d[NT];
 #pragma unroll
         for (int u = 0; u < NT; ++u) {
@@ -460,11 +477,13 @@ __device__ __forceinline__ void block_dmma_backward(cplx* sa, cplx* sb, const Op
 #pragma unroll
         for (int b = 0; b < NT; ++b) pacc[a][b][0] = pacc[a][b][1] = 0.0;
     const int nitems = (rows >> KQ) << LOG_CT;
-    const bool tab_b0 = nitems <= 8 * B0TAB;
+    const bool tab_b0 = (SQ_B0_MODE == 1) && nitems <= 8 * B0TAB;
     BlockGeom<LOG_CT, KQ> G;
     if (!tab_b0) G.init(q0, q1, q2);
+    int B0next = (SQ_B0_MODE == 2) ? G.batch_base(warp * 8) : 0;
     for (int b0 = warp * 8; b0 < nitems; b0 += nwarps * 8) {
-        const int B0 = tab_b0 ? T->b0[b0 >> 3] : G.batch_base(b0);
+        const int B0 = (SQ_B0_MODE == 2) ? B0next : (tab_b0 ? T->b0[b0 >> 3] : G.batch_base(b0));
+        if (SQ_B0_MODE == 2) B0next = G.batch_base(b0 + nwarps * 8);
         cplx p[NT], be[NT], da[NT], db[NT];
 #pragma unroll
         for (int u = 0; u < NT; ++u) {
@@ -787,6 +806,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
     // mbarrier (expect_tx / complete_tx), which every thread waits on (tab_acquire) right before it reads the table. Tables
     // are requested TAB_RING - 1 ops ahead; a slot is rewritten only after the end-of-op barrier of its previous user.
     const OpTab* __restrict__ gtabs = A.optabs + (size_t)kset * (A.optab_stride ? A.optab_stride : A.n_ops);
+#if SQ_TAB_BULK
     if (tid == 0) {
         for (int i = 0; i < TAB_RING; ++i)
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(tbar + i)));
@@ -809,7 +829,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                      "l"(src + 3 * FRAG), "r"(TAIL), "r"(bar)
                      : "memory");
     };
-    auto tab_acquire = [&](int k) {  // the table of op k (a DMMA block op) has landed in its ring slot
+    auto tab_acquire = [&](int k) {  // the table of op k (if it has one) has landed in its ring slot
+        if (k < 0 || k >= A.n_ops || sops[k].kind != 2) return;
         const int slot = k & (TAB_RING - 1);
         const unsigned bar = (unsigned)__cvta_generic_to_shared(tbar + slot);
         const unsigned parity = (tab_parity >> slot) & 1u;
@@ -820,10 +841,41 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
         } while (!done);
         tab_parity ^= 1u << slot;
     };
+    // the wait for the NEXT op's table sits in front of the end-of-op barrier, where its latency overlaps the wait for the
+    // slowest warp (the table was requested TAB_RING - 1 ops ago and has long landed)
+    auto tab_end_of_op = [&](int next_k) { tab_acquire(next_k); };
     auto tab_prime = [&](int first, int step, bool bwd) {  // requests for the first TAB_RING - 1 ops of a sweep
 #pragma unroll
         for (int j = 0; j < TAB_RING - 1; ++j) tab_prefetch(first + j * step, bwd);
+        tab_acquire(first);
     };
+#else
+    // per-thread cp.async (LDGSTS) copies, one commit group per op in sweep order (empty for ops without a table): when an op
+    // ends, "at most TAB_RING - 2 groups pending" means the NEXT op's table has landed; the end-of-op barrier publishes it
+    auto tab_prefetch_raw = [&](int k, bool bwd) {
+        if (k < 0 || k >= A.n_ops || sops[k].kind != 2) return;
+        const char* src = reinterpret_cast<const char*>(gtabs + k);
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(stab + (k & (TAB_RING - 1)));
+        constexpr int FRAG = 8 * 32 * 8, TAIL = (int)(sizeof(OpTabS) - 2 * FRAG);
+        const int nfrag = bwd ? 2 * FRAG : FRAG, src_off = bwd ? FRAG : 0;
+        for (int e = tid; e < (nfrag + TAIL) / 16; e += nthr) {
+            const int b = e * 16;
+            const int d_off = (b < nfrag) ? b : 2 * FRAG + (b - nfrag);
+            const int s_off = (b < nfrag) ? src_off + b : 3 * FRAG + (b - nfrag);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + d_off), "l"(src + s_off));
+        }
+    };
+    auto tab_prefetch = [&](int k, bool bwd) {
+        tab_prefetch_raw(k, bwd);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto tab_end_of_op = [&](int) { asm volatile("cp.async.wait_group %0;" ::"n"(TAB_RING - 2) : "memory"); };
+    auto tab_prime = [&](int first, int step, bool bwd) {
+#pragma unroll
+        for (int j = 0; j < TAB_RING - 1; ++j) tab_prefetch(first + j * step, bwd);
+        tab_end_of_op(first);
+    };
+#endif
 
     for (int ti = 0; ti < A.tiles_per_cta; ++ti) {
         const int tile = chunk * A.tiles_per_cta + ti;
@@ -884,7 +936,6 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
             tab_prefetch(k + TAB_RING - 1, false);
             const cplx* __restrict__ km = skm + (k & 1) * KM_ELEMS;
             if (s.kind == 2) {
-                tab_acquire(k);
                 if (s.dim == 8) block_dmma_forward<LOG_CT, 3>(sa, stab + (k & (TAB_RING - 1)), s.q0, s.q1, s.q2, rows, tid, nthr);
                 else block_dmma_forward<LOG_CT, 2>(sa, stab + (k & (TAB_RING - 1)), s.q0, s.q1, 30, rows, tid, nthr);
             } else if (s.kind == 0) {
@@ -1002,6 +1053,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                 }
             }
             if (have_next && tid < KM_ELEMS) skm[((k + 1) & 1) * KM_ELEMS + tid] = next_elem;
+            tab_end_of_op(k + 1);
             __syncthreads();
         }
 
@@ -1134,7 +1186,6 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                 const cplx* __restrict__ km = skm + (k & 1) * KM_ELEMS;
                 int wdim = s.dim;
                 if (s.kind == 2) {
-                    tab_acquire(k);
                     if (s.dim == 8) block_dmma_backward<LOG_CT, 3>(sa, sb, stab + (k & (TAB_RING - 1)), s.q0, s.q1, s.q2, rows, has_w, wslot_c, tid, nthr);
                     else block_dmma_backward<LOG_CT, 2>(sa, sb, stab + (k & (TAB_RING - 1)), s.q0, s.q1, 30, rows, has_w, wslot_c, tid, nthr);
                 } else if (s.kind == 0) {
@@ -1237,31 +1288,19 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                     }
                 }
                 if (have_next && tid < KM_ELEMS) skm[((k - 1) & 1) * KM_ELEMS + tid] = next_elem;
+                tab_end_of_op(k - 1);
                 __syncthreads();
                 if (has_w) {
                     const int nd = 2 * wdim * wdim;  // doubles
-                    if (A.w_in_smem) {
-                        for (int e = tid; e < nd; e += nthr) {
-                            double sum = 0;
-                            for (int w = 0; w < nwarps; ++w)
-                                sum += reinterpret_cast<const double*>(swarp + (size_t)(buf * nwarps + w) * A.wmax)[e];
-                            reinterpret_cast<double*>(swacc + s.w_off)[e] += sum;
-                        }
-                    } else {
-                        // every thread takes part: the warps' partials of one element are split over `parts` threads (a power
-                        // of two), each of which folds its share in a fixed order and issues one fire-and-forget reduction;
-                        // the reductions of one address are issued in thread order by one CTA, and each CTA owns its slice
-                        int parts = 1;
-                        while (2 * parts * nd <= nthr && 2 * parts <= nwarps) parts *= 2;
-                        const int per = nwarps / parts;
-                        double* dst = reinterpret_cast<double*>(A.w_part + ((size_t)y * nchunks + chunk) * A.w_total + s.w_off);
-                        for (int e2 = tid; e2 < nd * parts; e2 += nthr) {
-                            const int e = e2 % nd, part = e2 / nd;
-                            double sum = 0;
-                            for (int w = part * per; w < (part + 1) * per; ++w)
-                                sum += reinterpret_cast<const double*>(swarp + (size_t)(buf * nwarps + w) * A.wmax)[e];
-                            atomicAdd(dst + e, sum);
-                        }
+                    // one thread per element folds the warps' partials in a fixed order and issues ONE fire-and-forget reduction:
+                    // each address of the CTA's slice has a single writer, so the sums are bit-reproducible
+                    for (int e = tid; e < nd; e += nthr) {
+                        double sum = 0;
+                        for (int w = 0; w < nwarps; ++w)
+                            sum += reinterpret_cast<const double*>(swarp + (size_t)(buf * nwarps + w) * A.wmax)[e];
+                        if (A.w_in_smem) reinterpret_cast<double*>(swacc + s.w_off)[e] += sum;
+                        else
+                            atomicAdd(reinterpret_cast<double*>(A.w_part + ((size_t)y * nchunks + chunk) * A.w_total + s.w_off) + e, sum);
                     }
                     buf ^= 1;
                 }

@@ -234,6 +234,10 @@ struct sqgpu_ctx {
     // cost configuration
     CostCfg cfg{SQGPU_FROBENIUS_NORM, 1.0, 1.0 / 1.7, 0.5};
     int trace_offset = 0;
+    // column sharding (sqgpu_set_shard / multi-device handles): the resident matrix is U[:, shard_offset : shard_offset + cols]
+    // of a matrix with shard_cols_total columns; diagonal element j of the shard sits in row j + shard_offset for EVERY variant
+    int shard_offset = 0, shard_cols_total = 0;
+    struct MultiGpu* multi = nullptr;  // non-null: this handle is the front of a multi-device group (multi.cuh)
 
     // workspaces
     DevBuf wParams, wTrPart, wWPart, wTraces, wOmega, wCost, wGrad, wMat, wDerivIdx, wTraces0;
@@ -368,7 +372,9 @@ bool variant_supported(int v) {
 }
 
 // the trace offset only enters the Frobenius-family cost functions (get_cost_function*, :73-404); get_trace* ignore it
-int effective_offset(const sqgpu_ctx* c) { return c->cfg.variant <= SQGPU_FROBENIUS_NORM_CORRECTION2 ? c->trace_offset : 0; }
+int effective_offset(const sqgpu_ctx* c) {
+    return (c->cfg.variant <= SQGPU_FROBENIUS_NORM_CORRECTION2 ? c->trace_offset : 0) + c->shard_offset;
+}
 
 int param_count_of(int type) {
     switch (type) {
@@ -983,8 +989,10 @@ int batch_slice(const sqgpu_ctx* c, int batch, bool grad) {
 }
 
 // traces for a batch (device pointers). Layout d_traces[batch][n_k][3][2], n_k = 1 + (with_grad ? P : 0).
+// d_global_traces0 (optional, [batch][3][2]): the traces of the circuit itself already summed over all column shards -- the
+// Hilbert-Schmidt correction variants take the weights of their gradient functional from them (omega_t = w_t conj(T_t))
 int traces_dev(sqgpu_ctx* c, const double* d_params, int batch, bool with_grad, double* d_traces, cudaStream_t st,
-               bool allow_two_pass) {
+               bool allow_two_pass, const double* d_global_traces0 = nullptr) {
     int rc = check_ready(c, true);
     if (rc) return rc;
     if (batch <= 0) return SQGPU_OK;
@@ -994,7 +1002,7 @@ int traces_dev(sqgpu_ctx* c, const double* d_params, int batch, bool with_grad, 
     if (c->cols + effective_offset(c) > c->rows) return fail(SQGPU_ERR_INVALID, "trace_offset %d + cols %d exceeds rows %d", effective_offset(c), c->cols, c->rows);
     if (with_grad && !c->all_unitary) return fail(SQGPU_ERR_UNSUPPORTED, "gradient with a non-unitary GENERAL gate is not supported (the adjoint sweep needs K^-1 = K^dagger)");
     const bool hs_corr = c->cfg.variant == SQGPU_HILBERT_SCHMIDT_TEST_CORRECTION1 || c->cfg.variant == SQGPU_HILBERT_SCHMIDT_TEST_CORRECTION2;
-    if (with_grad && hs_corr && !allow_two_pass)
+    if (with_grad && hs_corr && !allow_two_pass && !d_global_traces0)
         return fail(SQGPU_ERR_UNSUPPORTED, "raw gradient traces for the Hilbert-Schmidt correction variants need the globally summed traces first");
     const int n_k = 1 + (with_grad ? c->n_params : 0);
     const int slice = batch_slice(c, batch, with_grad);
@@ -1010,7 +1018,9 @@ int traces_dev(sqgpu_ctx* c, const double* d_params, int batch, bool with_grad, 
         if ((rc = c->wOmega.ensure((size_t)nb * 3 * sizeof(cplx)))) return rc;
         const double* tr_for_omega = nullptr;
         int nk_for_omega = 1;
-        if (hs_corr) {  // pass 1: traces of the circuit itself, pass 2 uses omega_t = w_t conj(T_t)
+        if (hs_corr && d_global_traces0) {
+            tr_for_omega = d_global_traces0 + (size_t)b0 * 6;
+        } else if (hs_corr) {  // pass 1: traces of the circuit itself, pass 2 uses omega_t = w_t conj(T_t)
             if ((rc = c->wTraces0.ensure((size_t)nb * 6 * sizeof(double)))) return rc;
             if ((rc = run_exec_resident(c, nb, false, nullptr, c->wTraces0.as<double>(), st))) return rc;
             tr_for_omega = c->wTraces0.as<double>();
@@ -1045,7 +1055,7 @@ int eval_dev(sqgpu_ctx* c, const double* d_params, int batch, bool with_grad, do
     const int n_k = 1 + (with_grad ? c->n_params : 0);
     if ((rc = c->wTraces.ensure(std::max<size_t>(1, (size_t)batch * n_k * 6) * sizeof(double)))) return rc;
     if ((rc = traces_dev(c, d_params, batch, with_grad, c->wTraces.as<double>(), st, true))) return rc;
-    return cost_from_traces_dev(c, c->wTraces.as<double>(), batch, with_grad, c->cols, d_cost, d_grad, st);
+    return cost_from_traces_dev(c, c->wTraces.as<double>(), batch, with_grad, c->cols, d_cost, d_grad, st);  // a single, unsharded handle
 }
 
 // ---- apply paths -------------------------------------------------------------------------------------------------
@@ -1317,6 +1327,23 @@ int set_cost_checked(sqgpu_ctx* c, int variant, int trace_offset, double prev, d
 
 }  // namespace
 
+namespace {
+int multi_upload(sqgpu_ctx* front, const double* data, int rows, int cols, int stride);
+int multi_eval(sqgpu_ctx* front, const double* params, int batch, bool with_grad, double* cost, double* grad);
+int multi_vqe(sqgpu_ctx* front, const double* params, int batch, bool with_grad, double* energy, double* grad);
+int multi_apply_cost(struct MultiGpu* m);
+int multi_destroy(sqgpu_ctx* front);
+int multi_set_circuit(sqgpu_ctx* front, const sqgpu_gate_desc* gates, int n_gates, int n_params, int qbit_num, const double* matrix_pool, int64_t pool_len);
+int multi_set_cost(sqgpu_ctx* front, int variant, int trace_offset, double prev, double c1, double c2);
+int multi_set_option(sqgpu_ctx* front, const char* name, int64_t value);
+int multi_set_hamiltonian(sqgpu_ctx* front, int n_rows, int64_t nnz, const int32_t* indptr, const int32_t* indices, const double* values);
+long long multi_launches(sqgpu_ctx* front);
+sqgpu_ctx* multi_first(sqgpu_ctx* front);
+}  // namespace
+
+#define SQ_NOT_ON_MULTI(c) \
+    if ((c) && (c)->multi) return fail(SQGPU_ERR_UNSUPPORTED, "%s is not available on a multi-device handle", __func__)
+
 // =====================================================================================================================
 // extern "C" entry points
 // =====================================================================================================================
@@ -1382,6 +1409,7 @@ int sqgpu_create(int device, sqgpu_handle_t* out) {
 
 int sqgpu_destroy(sqgpu_handle_t c) {
     if (!c) return SQGPU_OK;
+    if (c->multi) return multi_destroy(c);
     {
         DeviceGuard guard(c->device);
         std::lock_guard<std::mutex> lk(c->mtx);
@@ -1403,6 +1431,10 @@ int sqgpu_upload_matrix(sqgpu_handle_t c, const double* data, int rows, int cols
     if (!data || rows <= 0 || cols <= 0 || stride < cols) return fail(SQGPU_ERR_INVALID, "bad matrix arguments");
     if (rows & (rows - 1)) return fail(SQGPU_ERR_INVALID, "rows must be a power of two, got %d", rows);
     if (cols > rows) return fail(SQGPU_ERR_INVALID, "cols (%d) cannot exceed rows (%d)", cols, rows);
+    if (c->multi) {
+        std::lock_guard<std::mutex> lk(c->mtx);
+        return multi_upload(c, data, rows, cols, stride);
+    }
     DeviceGuard guard(c->device);
     std::lock_guard<std::mutex> lk(c->mtx);
     wait_idle(c);
@@ -1629,6 +1661,10 @@ static int set_circuit_impl(sqgpu_ctx* c, const sqgpu_gate_desc* gates, int n_ga
 int sqgpu_set_circuit(sqgpu_handle_t c, const sqgpu_gate_desc* gates, int n_gates, int n_params, int qbit_num,
                       const double* matrix_pool, int64_t pool_len) {
     if (!c) return fail(SQGPU_ERR_INVALID, "NULL handle");
+    if (c->multi) {
+        std::lock_guard<std::mutex> lk(c->mtx);
+        return multi_set_circuit(c, gates, n_gates, n_params, qbit_num, matrix_pool, pool_len);
+    }
     DeviceGuard guard(c->device);
     std::lock_guard<std::mutex> lk(c->mtx);
     wait_idle(c);
@@ -1689,6 +1725,7 @@ int sqgpu_set_cost(sqgpu_handle_t c, int variant, int trace_offset, double prev_
                    double correction2_scale) {
     if (!c) return fail(SQGPU_ERR_INVALID, "NULL handle");
     std::lock_guard<std::mutex> lk(c->mtx);
+    if (c->multi) return multi_set_cost(c, variant, trace_offset, prev_cost_fnv_val, correction1_scale, correction2_scale);
     return set_cost_checked(c, variant, trace_offset, prev_cost_fnv_val, correction1_scale, correction2_scale);
 }
 
@@ -1696,6 +1733,7 @@ int sqgpu_set_cost(sqgpu_handle_t c, int variant, int trace_offset, double prev_
 
 int sqgpu_cost_batched_dev(sqgpu_handle_t c, const double* d_params, int batch, double* d_cost, void* stream) {
     if (!c) return fail(SQGPU_ERR_INVALID, "NULL handle");
+    SQ_NOT_ON_MULTI(c);
     if (batch < 0 || (batch > 0 && (!d_params && c->n_params > 0)) || (batch > 0 && !d_cost)) return fail(SQGPU_ERR_INVALID, "bad arguments");
     DeviceGuard guard(c->device);
     std::lock_guard<std::mutex> lk(c->mtx);
@@ -1705,6 +1743,7 @@ int sqgpu_cost_batched_dev(sqgpu_handle_t c, const double* d_params, int batch, 
 
 int sqgpu_cost_grad_batched_dev(sqgpu_handle_t c, const double* d_params, int batch, double* d_cost, double* d_grad, void* stream) {
     if (!c) return fail(SQGPU_ERR_INVALID, "NULL handle");
+    SQ_NOT_ON_MULTI(c);
     if (batch < 0 || (batch > 0 && (!d_params && c->n_params > 0)) || (batch > 0 && (!d_cost || (!d_grad && c->n_params > 0)))) return fail(SQGPU_ERR_INVALID, "bad arguments");
     DeviceGuard guard(c->device);
     std::lock_guard<std::mutex> lk(c->mtx);
@@ -1714,6 +1753,7 @@ int sqgpu_cost_grad_batched_dev(sqgpu_handle_t c, const double* d_params, int ba
 
 int sqgpu_traces_batched_dev(sqgpu_handle_t c, const double* d_params, int batch, int with_grad, double* d_traces, void* stream) {
     if (!c) return fail(SQGPU_ERR_INVALID, "NULL handle");
+    SQ_NOT_ON_MULTI(c);
     if (batch < 0 || (batch > 0 && !d_traces)) return fail(SQGPU_ERR_INVALID, "bad arguments");
     DeviceGuard guard(c->device);
     std::lock_guard<std::mutex> lk(c->mtx);
@@ -1724,6 +1764,7 @@ int sqgpu_traces_batched_dev(sqgpu_handle_t c, const double* d_params, int batch
 int sqgpu_cost_from_traces_dev(sqgpu_handle_t c, const double* d_traces, int batch, int with_grad, int cols_total,
                                double* d_cost, double* d_grad, void* stream) {
     if (!c) return fail(SQGPU_ERR_INVALID, "NULL handle");
+    SQ_NOT_ON_MULTI(c);
     if (batch < 0 || cols_total <= 0 || (batch > 0 && (!d_traces || !d_cost))) return fail(SQGPU_ERR_INVALID, "bad arguments");
     DeviceGuard guard(c->device);
     std::lock_guard<std::mutex> lk(c->mtx);
@@ -1736,6 +1777,10 @@ int sqgpu_cost_from_traces_dev(sqgpu_handle_t c, const double* d_traces, int bat
 
 static int host_eval(sqgpu_handle_t c, const double* params, int batch, bool with_grad, double* cost, double* grad) {
     if (!c) return fail(SQGPU_ERR_INVALID, "NULL handle");
+    if (c->multi) {
+        std::lock_guard<std::mutex> lk(c->mtx);
+        return multi_eval(c, params, batch, with_grad, cost, grad);
+    }
     if (batch < 0) return fail(SQGPU_ERR_INVALID, "negative batch");
     if (batch == 0) return SQGPU_OK;
     if ((!params && c->n_params > 0) || !cost || (with_grad && !grad && c->n_params > 0)) return fail(SQGPU_ERR_INVALID, "NULL buffer");
@@ -1766,6 +1811,7 @@ int sqgpu_cost_grad_batched(sqgpu_handle_t c, const double* params, int batch, d
 
 int sqgpu_traces_batched(sqgpu_handle_t c, const double* params, int batch, int with_grad, double* traces) {
     if (!c) return fail(SQGPU_ERR_INVALID, "NULL handle");
+    SQ_NOT_ON_MULTI(c);
     if (batch < 0) return fail(SQGPU_ERR_INVALID, "negative batch");
     if (batch == 0) return SQGPU_OK;
     if ((!params && c->n_params > 0) || !traces) return fail(SQGPU_ERR_INVALID, "NULL buffer");
@@ -1787,6 +1833,7 @@ int sqgpu_traces_batched(sqgpu_handle_t c, const double* params, int batch, int 
 
 int sqgpu_cost_from_traces(sqgpu_handle_t c, const double* traces, int batch, int with_grad, int cols_total, double* cost, double* grad) {
     if (!c) return fail(SQGPU_ERR_INVALID, "NULL handle");
+    SQ_NOT_ON_MULTI(c);
     if (batch < 0 || cols_total <= 0) return fail(SQGPU_ERR_INVALID, "bad arguments");
     if (batch == 0) return SQGPU_OK;
     if (!traces || !cost || (with_grad && !grad && c->n_params > 0)) return fail(SQGPU_ERR_INVALID, "NULL buffer");
@@ -1811,6 +1858,7 @@ int sqgpu_cost_from_traces(sqgpu_handle_t c, const double* traces, int batch, in
 
 int sqgpu_apply(sqgpu_handle_t c, const double* params, double* inout, int rows, int cols, int stride) {
     if (!c) return fail(SQGPU_ERR_INVALID, "NULL handle");
+    SQ_NOT_ON_MULTI(c);
     if (!inout || rows <= 0 || cols <= 0 || stride < cols) return fail(SQGPU_ERR_INVALID, "bad matrix arguments");
     DeviceGuard guard(c->device);
     std::lock_guard<std::mutex> lk(c->mtx);
@@ -1841,6 +1889,7 @@ int sqgpu_apply(sqgpu_handle_t c, const double* params, double* inout, int rows,
 
 int sqgpu_apply_derivative(sqgpu_handle_t c, const double* params, const double* in, int rows, int cols, int stride, double* out) {
     if (!c) return fail(SQGPU_ERR_INVALID, "NULL handle");
+    SQ_NOT_ON_MULTI(c);
     if (!in || rows <= 0 || cols <= 0 || stride < cols) return fail(SQGPU_ERR_INVALID, "bad matrix arguments");
     DeviceGuard guard(c->device);
     std::lock_guard<std::mutex> lk(c->mtx);
@@ -1928,6 +1977,7 @@ static int apply_gate_on_device(sqgpu_ctx* c, const sqgpu_gate_desc* gate, const
 int sqgpu_apply_gate(sqgpu_handle_t c, const sqgpu_gate_desc* gate, const double* gate_params, const double* matrix_pool,
                      int deriv_param, double* inout, int rows, int cols, int stride) {
     if (!c) return fail(SQGPU_ERR_INVALID, "NULL handle");
+    SQ_NOT_ON_MULTI(c);
     if (!gate || !inout || rows <= 0 || cols <= 0 || stride < cols) return fail(SQGPU_ERR_INVALID, "bad arguments");
     DeviceGuard guard(c->device);
     std::lock_guard<std::mutex> lk(c->mtx);
@@ -1944,6 +1994,7 @@ int sqgpu_apply_gate(sqgpu_handle_t c, const sqgpu_gate_desc* gate, const double
 int sqgpu_apply_gate_dev(sqgpu_handle_t c, const sqgpu_gate_desc* gate, const double* gate_params, const double* matrix_pool,
                          int deriv_param, double* d_inout, int rows, int cols, int stride, void* stream) {
     if (!c) return fail(SQGPU_ERR_INVALID, "NULL handle");
+    SQ_NOT_ON_MULTI(c);
     if (!gate || !d_inout || rows <= 0 || cols <= 0 || stride < cols) return fail(SQGPU_ERR_INVALID, "bad arguments");
     DeviceGuard guard(c->device);
     std::lock_guard<std::mutex> lk(c->mtx);
@@ -1957,6 +2008,10 @@ int sqgpu_set_hamiltonian_csr(sqgpu_handle_t c, int n_rows, int64_t nnz, const i
     if (!c) return fail(SQGPU_ERR_INVALID, "NULL handle");
     if (n_rows <= 0 || nnz < 0 || !indptr || (nnz > 0 && (!indices || !values))) return fail(SQGPU_ERR_INVALID, "bad CSR arguments");
     if (indptr[0] != 0 || indptr[n_rows] != nnz) return fail(SQGPU_ERR_INVALID, "inconsistent CSR indptr");
+    if (c->multi) {
+        std::lock_guard<std::mutex> lk(c->mtx);
+        return multi_set_hamiltonian(c, n_rows, nnz, indptr, indices, values);
+    }
     DeviceGuard guard(c->device);
     std::lock_guard<std::mutex> lk(c->mtx);
     int rc;
@@ -1978,6 +2033,7 @@ static int vqe_dev(sqgpu_ctx* c, const double* d_params, int batch, bool with_gr
 
 int sqgpu_vqe_energy_batched_dev(sqgpu_handle_t c, const double* d_params, int batch, double* d_energy, void* stream) {
     if (!c) return fail(SQGPU_ERR_INVALID, "NULL handle");
+    SQ_NOT_ON_MULTI(c);
     DeviceGuard guard(c->device);
     std::lock_guard<std::mutex> lk(c->mtx);
     CallScope cs(c, (cudaStream_t)stream);
@@ -1986,6 +2042,7 @@ int sqgpu_vqe_energy_batched_dev(sqgpu_handle_t c, const double* d_params, int b
 
 int sqgpu_vqe_energy_grad_batched_dev(sqgpu_handle_t c, const double* d_params, int batch, double* d_energy, double* d_grad, void* stream) {
     if (!c) return fail(SQGPU_ERR_INVALID, "NULL handle");
+    SQ_NOT_ON_MULTI(c);
     DeviceGuard guard(c->device);
     std::lock_guard<std::mutex> lk(c->mtx);
     CallScope cs(c, (cudaStream_t)stream);
@@ -1994,6 +2051,10 @@ int sqgpu_vqe_energy_grad_batched_dev(sqgpu_handle_t c, const double* d_params, 
 
 static int vqe_host(sqgpu_handle_t c, const double* params, int batch, bool with_grad, double* energy, double* grad) {
     if (!c) return fail(SQGPU_ERR_INVALID, "NULL handle");
+    if (c->multi) {
+        std::lock_guard<std::mutex> lk(c->mtx);
+        return multi_vqe(c, params, batch, with_grad, energy, grad);
+    }
     if (batch < 0) return fail(SQGPU_ERR_INVALID, "negative batch");
     if (batch == 0) return SQGPU_OK;
     if ((!params && c->n_params > 0) || !energy || (with_grad && !grad && c->n_params > 0)) return fail(SQGPU_ERR_INVALID, "NULL buffer");
@@ -2026,7 +2087,7 @@ int sqgpu_vqe_energy_grad_batched(sqgpu_handle_t c, const double* params, int ba
 int sqgpu_launch_count(sqgpu_handle_t c, int64_t* count) {
     if (!c || !count) return fail(SQGPU_ERR_INVALID, "NULL argument");
     std::lock_guard<std::mutex> lk(c->mtx);
-    *count = c->launches;
+    *count = c->multi ? multi_launches(c) : c->launches;
     return SQGPU_OK;
 }
 
@@ -2052,6 +2113,7 @@ static int ring_average(KernelTimer::Ring& r, double* ms, int* launches) {
 
 int sqgpu_last_kernel_time(sqgpu_handle_t c, char* name, int name_len, double* ms, int* launches) {
     if (!c || !ms || !launches) return fail(SQGPU_ERR_INVALID, "NULL argument");
+    if (c->multi) c = multi_first(c);  // introspection of a multi-device handle reports its first device
     DeviceGuard guard(c->device);
     std::lock_guard<std::mutex> lk(c->mtx);
     *ms = 0;
@@ -2080,6 +2142,7 @@ int sqgpu_last_kernel_time(sqgpu_handle_t c, char* name, int name_len, double* m
 
 int sqgpu_kernel_time(sqgpu_handle_t c, const char* name, double* ms, int* launches) {
     if (!c || !name || !ms || !launches) return fail(SQGPU_ERR_INVALID, "NULL argument");
+    if (c->multi) c = multi_first(c);  // introspection of a multi-device handle reports its first device
     DeviceGuard guard(c->device);
     std::lock_guard<std::mutex> lk(c->mtx);
     *ms = 0;
@@ -2091,6 +2154,7 @@ int sqgpu_kernel_time(sqgpu_handle_t c, const char* name, double* ms, int* launc
 
 int sqgpu_last_exec_flops(sqgpu_handle_t c, double* tensor_flops, double* scalar_flops) {
     if (!c || !tensor_flops || !scalar_flops) return fail(SQGPU_ERR_INVALID, "NULL argument");
+    if (c->multi) c = multi_first(c);  // introspection of a multi-device handle reports its first device
     std::lock_guard<std::mutex> lk(c->mtx);
     *tensor_flops = c->last_flops[0];
     *scalar_flops = c->last_flops[1];
@@ -2099,6 +2163,7 @@ int sqgpu_last_exec_flops(sqgpu_handle_t c, double* tensor_flops, double* scalar
 
 int sqgpu_last_launch_shape(sqgpu_handle_t c, int* shape, int n_shape) {
     if (!c || !shape || n_shape < 0) return fail(SQGPU_ERR_INVALID, "NULL argument");
+    if (c->multi) c = multi_first(c);  // introspection of a multi-device handle reports its first device
     std::lock_guard<std::mutex> lk(c->mtx);
     for (int i = 0; i < n_shape && i < 6; ++i) shape[i] = c->last_shape[i];
     return SQGPU_OK;
@@ -2107,6 +2172,7 @@ int sqgpu_last_launch_shape(sqgpu_handle_t c, int* shape, int n_shape) {
 int sqgpu_set_option(sqgpu_handle_t c, const char* name, int64_t value) {
     if (!c) return fail(SQGPU_ERR_INVALID, "NULL handle");
     std::lock_guard<std::mutex> lk(c->mtx);
+    if (c->multi) return multi_set_option(c, name, value);
     return option_set(c->opt, name, value);
 }
 
@@ -2123,6 +2189,7 @@ int sqgpu_get_option(sqgpu_handle_t c, const char* name, int64_t* value) {
 
 int sqgpu_fp64_fma_peak(sqgpu_handle_t c, double* tflops) {
     if (!c || !tflops) return fail(SQGPU_ERR_INVALID, "NULL argument");
+    if (c->multi) c = multi_first(c);  // introspection of a multi-device handle reports its first device
     DeviceGuard guard(c->device);
     std::lock_guard<std::mutex> lk(c->mtx);
     CallScope cs(c, c->stream);
@@ -2180,3 +2247,5 @@ int sqgpu_fp64_fma_peak(sqgpu_handle_t c, double* tflops) {
 
 // VQE device path (defined after the C block so it can use the static helpers above)
 #include "vqe_impl.cuh"
+// several devices behind one handle
+#include "multi.cuh"

@@ -55,7 +55,12 @@ class N_Qubit_Decomposition_custom:
     @property
     def _engine(self):
         if self._engine_obj is None:
-            self._engine_obj = Engine(self._device)
+            # accelerator_num = G > 1: one handle over GPUs device .. device + G - 1, sharded inside the library
+            # (the reference splits its batched cost path over accelerators the same way, Optimization_Interface.cpp:806-832)
+            if self.accelerator_num > 1:
+                self._engine_obj = Engine(devices=list(range(self._device, self._device + self.accelerator_num)))
+            else:
+                self._engine_obj = Engine(self._device)
             self._engine_obj.upload_matrix(self.Umtx)
         return self._engine_obj
 
@@ -107,6 +112,13 @@ class N_Qubit_Decomposition_custom:
             self._dirty = False
         return self._engine
 
+    def _apply_engine(self):
+        """engine of the matrix-valued calls (apply_to, derivative matrices): they run on one device; a multi-device handle
+        only shards the cost path, so those calls go through the circuit's own single-device engine"""
+        if self.accelerator_num > 1:
+            return self._circuit._get_engine()
+        return self._sync()
+
     # ---- the hot path ---------------------------------------------------------------------------------------
     def Optimization_Problem(self, parameters):
         """Optimization_Interface::optimization_problem (Optimization_Interface.cpp:634-668)."""
@@ -135,7 +147,7 @@ class N_Qubit_Decomposition_custom:
 
     def Optimization_Problem_Combined_Unitary(self, parameters):
         """optimization_problem_combined_unitary (Optimization_Interface.cpp:1525-1547): (C Umtx, [d_i C Umtx])."""
-        eng = self._sync()
+        eng = self._apply_engine()
         derivs = eng.apply_derivative(parameters, self.Umtx)
         m = self.Umtx.copy()
         eng.apply(parameters, m)
@@ -143,9 +155,8 @@ class N_Qubit_Decomposition_custom:
 
     def get_Matrix(self, parameters):
         """Unitary of the gate structure itself (Gates_block::get_matrix)."""
-        self._sync()
         m = np.eye(1 << self.qbit_num, dtype=np.complex128)
-        self._engine.apply(parameters, m)
+        self._apply_engine().apply(parameters, m)
         return m
 
 

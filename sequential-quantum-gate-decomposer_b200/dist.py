@@ -33,15 +33,7 @@ def batch_shard(batch, rank, world):
     return begin, begin + base + (1 if rank < rem else 0)
 
 
-def trace_pass_variant(variant):
-    """cost variant the shard engines run for the TRACE pass: the Frobenius family keeps its own variant (it fixes how
-    many trace types are needed and the real weights of the functional); the trace-modulus variants (3, 9) need the
-    shard's row offset, which only the Frobenius family honours, with the same single trace type."""
-    if variant in (abi.FROBENIUS_NORM, abi.FROBENIUS_NORM_CORRECTION1, abi.FROBENIUS_NORM_CORRECTION2):
-        return variant
-    if variant in (abi.HILBERT_SCHMIDT_TEST, abi.INFIDELITY):
-        return abi.FROBENIUS_NORM
-    raise Exception("cost variant %d is not supported with column sharding" % variant)
+HS_CORRECTION = (abi.HILBERT_SCHMIDT_TEST_CORRECTION1, abi.HILBERT_SCHMIDT_TEST_CORRECTION2)
 
 
 class ShardedCost:
@@ -76,7 +68,10 @@ class ShardedCost:
             self.col_begin = b
             self.engine.upload_matrix(np.ascontiguousarray(U[:, b:e]))
             self.engine.set_circuit(circuit)
-            self._trace_variant = trace_pass_variant(self.variant)
+            # the shard's row offset enters the trace terms of every cost variant (sqgpu_set_shard); the cost formulas run on
+            # the summed traces with the full column count
+            self.engine.set_shard(b, self.cols)
+            self.engine.set_cost(self.variant, 0, *self.cfg)
         else:
             self.engine.upload_matrix(U)
             self.engine.set_circuit(circuit)
@@ -123,6 +118,8 @@ class ShardedCost:
         if self.mode == "batch":
             counts = [batch_shard(B, r, self.world)[1] - batch_shard(B, r, self.world)[0] for r in range(self.world)]
             b, e = batch_shard(B, self.rank, self.world)
+            if self._on_device() and self.world > 1:
+                return self._batch_on_device(p, b, e, counts, with_grad)
             if with_grad:
                 if e > b:
                     c, g = self.engine.cost_grad_batched(p[b:e])
@@ -133,12 +130,75 @@ class ShardedCost:
                 return allp[:, 0].copy(), allp[:, 1:].copy()
             c = self.engine.cost_batched(p[b:e]) if e > b else np.zeros(0)
             return self._all_gather_rows(c.reshape(-1, 1), counts)[:, 0].copy()
-        # columns: shard traces -> one all-reduce -> cost formulas on the summed traces
-        self.engine.set_cost(self._trace_variant, self.col_begin, *self.cfg)
-        tr = self.engine.traces_batched(p, with_grad)
+        # columns: shard traces -> one all-reduce -> cost formulas on the summed traces. The Hilbert-Schmidt correction
+        # variants take the weights of their gradient functional from the summed traces of the circuit itself: one more,
+        # small all-reduce in front of the gradient pass.
+        hs_corr = with_grad and self.variant in HS_CORRECTION
+        if self._on_device():
+            return self._columns_on_device(p, with_grad, hs_corr)
+        if hs_corr:
+            tr0 = self._all_reduce_sum(self.engine.traces_batched(p, False))
+            tr = self.engine.grad_traces_with_global(p, tr0)
+        else:
+            tr = self.engine.traces_batched(p, with_grad)
         tr = self._all_reduce_sum(tr)
-        self.engine.set_cost(self.variant, 0, *self.cfg)
         return self.engine.cost_from_traces(tr, with_grad, self.cols)
+
+    def _on_device(self):
+        """NCCL backend + the CUDA engine: parameters, traces and results stay in device tensors, the all-reduce runs on the
+        compute stream between the executor and the cost formulas (no host round trip before the final read-back)"""
+        return (self.dist.is_initialized() and self.dist.get_backend(self.group) == "nccl"
+                and hasattr(self.engine, "traces_batched_dev"))
+
+    def _columns_on_device(self, p, with_grad, hs_corr):
+        import torch
+
+        B, P = p.shape
+        n_k = 1 + (P if with_grad else 0)
+        st = torch.cuda.current_stream().cuda_stream
+        d_p = torch.from_numpy(p).cuda()
+        tr = torch.empty(B * n_k * 6, dtype=torch.float64, device="cuda")
+        if hs_corr:
+            tr0 = torch.empty(B * 6, dtype=torch.float64, device="cuda")
+            self.engine.traces_batched_dev(d_p.data_ptr(), B, False, tr0.data_ptr(), st)
+            if self.world > 1:
+                self.dist.all_reduce(tr0, op=self.dist.ReduceOp.SUM, group=self.group)
+            self.engine.grad_traces_with_global_dev(d_p.data_ptr(), B, tr0.data_ptr(), tr.data_ptr(), st)
+        else:
+            self.engine.traces_batched_dev(d_p.data_ptr(), B, with_grad, tr.data_ptr(), st)
+        if self.world > 1:
+            self.dist.all_reduce(tr, op=self.dist.ReduceOp.SUM, group=self.group)
+        cost = torch.empty(B, dtype=torch.float64, device="cuda")
+        grad = torch.empty(B * P, dtype=torch.float64, device="cuda") if with_grad else None
+        self.engine.cost_from_traces_dev(tr.data_ptr(), B, with_grad, self.cols, cost.data_ptr(), grad.data_ptr() if with_grad else 0, st)
+        if with_grad:
+            return cost.cpu().numpy(), grad.cpu().numpy().reshape(B, P)
+        return cost.cpu().numpy()
+
+    def _batch_on_device(self, p, b, e, counts, with_grad):
+        """batch sharding with device tensors end to end: one all-gather of [max slice x (1 + P)] per evaluation"""
+        import torch
+
+        B, P = p.shape
+        width = 1 + (P if with_grad else 0)
+        mx = max(counts)
+        st = torch.cuda.current_stream().cuda_stream
+        packed = torch.zeros(mx * width, dtype=torch.float64, device="cuda")  # [cost(mx) | grad(mx * P)], zero padded
+        nb = e - b
+        if nb:
+            d_p = torch.from_numpy(np.ascontiguousarray(p[b:e])).cuda()
+            if with_grad:
+                self.engine.cost_grad_batched_dev(d_p.data_ptr(), nb, packed.data_ptr(), packed.data_ptr() + 8 * mx, st)
+            else:
+                self.engine.cost_batched_dev(d_p.data_ptr(), nb, packed.data_ptr(), st)
+        gathered = torch.empty(self.world * mx * width, dtype=torch.float64, device="cuda")
+        self.dist.all_gather_into_tensor(gathered, packed, group=self.group)
+        g = gathered.cpu().numpy().reshape(self.world, mx * width)
+        cost = np.concatenate([g[r, : counts[r]] for r in range(self.world)])
+        if not with_grad:
+            return cost
+        grad = np.concatenate([g[r, mx: mx + counts[r] * P].reshape(counts[r], P) for r in range(self.world)], axis=0)
+        return cost, grad
 
     def cost(self, params):
         return self.cost_grad(params, with_grad=False)

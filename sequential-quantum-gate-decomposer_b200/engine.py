@@ -21,10 +21,20 @@ class Engine:
     # engines created deep inside the wrapper classes pick the executor path under test. Empty = product configuration.
     default_options = {}
 
-    def __init__(self, device=0, options=None):
+    def __init__(self, device=0, options=None, devices=None, shard_mode=abi.SHARD_AUTO):
+        """``devices`` (a list of CUDA device indices, or an int n for devices 0..n-1) makes ONE handle over several GPUs
+        (sqgpu_create_multi): the batch or the columns of the matrix are sharded inside the library (``shard_mode``)."""
         self.lib = abi.load_library()
         self._h = abi._handle()
-        abi.check(self.lib, self.lib.sqgpu_create(int(device), C.byref(self._h)))
+        if devices is not None:
+            devs = list(range(devices)) if isinstance(devices, int) else [int(d) for d in devices]
+            arr = (C.c_int * len(devs))(*devs)
+            abi.check(self.lib, self.lib.sqgpu_create_multi(len(devs), arr, int(shard_mode), C.byref(self._h)))
+            self.devices = devs
+            device = devs[0] if devs else 0
+        else:
+            abi.check(self.lib, self.lib.sqgpu_create(int(device), C.byref(self._h)))
+            self.devices = [int(device)]
         self.device = int(device)
         for k, v in dict(Engine.default_options, **(options or {})).items():
             self.set_option(k, v)
@@ -77,6 +87,16 @@ class Engine:
                                        int(n_params), int(qbit_num), pd, pool.size),
         )
         self.n_params, self.n_gates, self.qbit_num = int(n_params), len(descs), int(qbit_num)
+
+    def multi_info(self):
+        """(number of devices behind the handle, sharding mode in force)"""
+        n, m = C.c_int(0), C.c_int(0)
+        abi.check(self.lib, self.lib.sqgpu_multi_info(self._h, C.byref(n), C.byref(m)))
+        return n.value, m.value
+
+    def set_shard(self, col_begin, cols_total):
+        """sqgpu_set_shard: the resident matrix is U[:, col_begin : col_begin + cols) of a cols_total-column matrix"""
+        abi.check(self.lib, self.lib.sqgpu_set_shard(self._h, int(col_begin), int(cols_total)))
 
     def set_cost(self, variant=abi.FROBENIUS_NORM, trace_offset=0, prev_cost=1.0, c1=1 / 1.7, c2=1 / 2.0):
         # defaults: Optimization_Interface.cpp:74-76
@@ -192,6 +212,10 @@ class Engine:
     def traces_batched_dev(self, d_params, batch, with_grad, d_traces, stream=0):
         abi.check(self.lib, self.lib.sqgpu_traces_batched_dev(self._h, d_params, int(batch), int(bool(with_grad)),
                                                               d_traces, stream))
+
+    def grad_traces_with_global_dev(self, d_params, batch, d_global_traces0, d_traces, stream=0):
+        abi.check(self.lib, self.lib.sqgpu_grad_traces_with_global_dev(self._h, d_params, int(batch), d_global_traces0, d_traces,
+                                                                       stream))
 
     def cost_from_traces_dev(self, d_traces, batch, with_grad, cols_total, d_cost, d_grad, stream=0):
         abi.check(self.lib, self.lib.sqgpu_cost_from_traces_dev(self._h, d_traces, int(batch), int(bool(with_grad)),

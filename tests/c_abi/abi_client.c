@@ -1,7 +1,8 @@
 /* A plain-C client of include/sqgpu.h: what a reference-side shim does, without Python or torch.
  * Builds the 3-qubit structure [U3(0) U3(1) CRY(0,1) U3(2) CNOT(2,0) RZ(1)], evaluates cost + gradient for two parameter
  * vectors on U = identity and prints them; tests/test_gpu_parity.py compares the numbers with the Python binding and the
- * oracle. Usage: abi_client <path-to-libsqgpu.so is linked>, prints "cost[b] ..." and "grad[b] ..." lines. */
+ * oracle. Usage: abi_client [n_devices [mode]] -- n_devices > 1 (accelerator_num = G) makes ONE handle over G GPUs with
+ * sqgpu_create_multi (mode: 0 auto, 1 batch, 2 columns); every other call is the same. Prints "cost[b] ..." / "grad[b] ..." lines. */
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -29,15 +30,23 @@ static sqgpu_gate_desc gate(int type, int target, int control, int param_start, 
     return g;
 }
 
-int main(void) {
+int main(int argc, char** argv) {
     int ndev = 0;
+    const int want = argc > 1 ? atoi(argv[1]) : 1, mode = argc > 2 ? atoi(argv[2]) : SQGPU_SHARD_AUTO;
     CHECK(sqgpu_device_count(&ndev));
-    if (ndev < 1) {
-        fprintf(stderr, "no device\n");
+    if (ndev < want || want < 1) {
+        fprintf(stderr, "%d device(s) visible, %d wanted\n", ndev, want);
         return 2;
     }
     sqgpu_handle_t h;
-    CHECK(sqgpu_create(0, &h));
+    if (want > 1) {
+        int n_in_handle = 0, mode_in_force = -1;
+        CHECK(sqgpu_create_multi(want, NULL, mode, &h));
+        CHECK(sqgpu_multi_info(h, &n_in_handle, &mode_in_force));
+        if (n_in_handle != want) return 3;
+    } else {
+        CHECK(sqgpu_create(0, &h));
+    }
     const int n = 3, dim = 8, P = 11, B = 2;
     sqgpu_gate_desc gates[6];
     gates[0] = gate(SQGPU_U3, 0, -1, 0, 3);

@@ -43,7 +43,7 @@ ref = sq.Engine(local)
 ref.upload_matrix(U)
 ref.set_circuit(circ)
 ok = True
-for variant in (0, 2, 3, 9):
+for variant in (0, 2, 3, 4, 5, 6, 9):
     ref.set_cost(variant, 0, 0.37)
     c_ref, g_ref = ref.cost_grad_batched(params)
     oracle = [port.cost_grad(descs, P, params[b], U, n, variant, 0, 0.37) for b in range(len(params))]

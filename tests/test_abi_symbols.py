@@ -259,3 +259,18 @@ def test_vqe_wrapper_structure_without_gpu():
         sq.Variational_Quantum_Eigensolver(Hm, n, accelerator_num=0)
     with pytest.raises(Exception):
         sq.Variational_Quantum_Eigensolver(Hm, n + 1)
+
+
+def test_multi_handle_argument_checks(lib):
+    """sqgpu_create_multi validates before it touches a device; without one it fails like sqgpu_create (no CPU fallback)"""
+    h = abi._handle()
+    assert lib.sqgpu_create_multi(0, None, abi.SHARD_AUTO, C.byref(h)) == abi.ERR_INVALID
+    assert lib.sqgpu_create_multi(2, None, 7, C.byref(h)) == abi.ERR_INVALID and b"sharding mode" in lib.sqgpu_last_error()
+    twice = (C.c_int * 2)(0, 0)
+    assert lib.sqgpu_create_multi(2, twice, abi.SHARD_BATCH, C.byref(h)) == abi.ERR_INVALID and b"twice" in lib.sqgpu_last_error()
+    n = C.c_int(-1)
+    if lib.sqgpu_device_count(C.byref(n)) == abi.OK and n.value > 0:
+        pytest.skip("a GPU is visible; the multi-device handle is covered by the -m gpu tests")
+    assert lib.sqgpu_create_multi(2, None, abi.SHARD_AUTO, C.byref(h)) == abi.ERR_NO_DEVICE
+    with pytest.raises(abi.SqgpuError):
+        H.sq.Engine(devices=2)

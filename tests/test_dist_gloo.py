@@ -21,6 +21,14 @@ class OracleEngine:
 
         self.port = pyoracle.Port()
         self.variant, self.off, self.cfg = 0, 0, (1.0, 1 / 1.7, 0.5)
+        self.shard = 0
+
+    def set_shard(self, col_begin, cols_total):
+        self.shard = col_begin
+
+    def _off(self):
+        # sqgpu_set_shard: the shard's row offset enters every variant; the user's trace_offset the Frobenius family only
+        return (self.off if self.variant <= 2 else 0) + self.shard
 
     def upload_matrix(self, U):
         self.U = np.ascontiguousarray(U)
@@ -33,23 +41,32 @@ class OracleEngine:
     def set_cost(self, variant, trace_offset, prev, c1, c2):
         self.variant, self.off, self.cfg = variant, trace_offset, (prev, c1, c2)
 
-    def _omega(self):
+    def _omega(self, tr0=None):
+        """complex weights of the three trace types in the functional whose gradient is taken (reduce.cuh: make_omega)"""
         prev, c1, c2 = self.cfg
         sp = np.sqrt(prev)
-        return {0: (1, 0, 0), 1: (1, sp * c1, 0), 2: (1, sp * c1, sp * c2)}[self.variant]
+        if self.variant in (4, 5):
+            T = tr0[:, 0] - 1j * tr0[:, 1]  # conj of the summed traces of the circuit itself
+            return (T[0], sp * c1 * T[1], sp * c2 * T[2] if self.variant == 5 else 0)
+        return {0: (1, 0, 0), 1: (1, sp * c1, 0), 2: (1, sp * c1, sp * c2), 3: (1, 0, 0), 9: (1, 0, 0), 6: (1, 0, 0)}[self.variant]
 
-    def traces_batched(self, params, with_grad):
+    def traces_batched(self, params, with_grad, tr0=None):
         out = np.zeros((len(params), 1 + (self.P if with_grad else 0), 3, 2))
-        w = self._omega()
         for b, p in enumerate(params):
             m = self.port.apply_circuit(self.descs, p, self.U, self.pool)
-            out[b, 0] = self.port.traces(m, self.n, self.off).reshape(3, 2)
+            out[b, 0] = self.port.traces(m, self.n, self._off()).reshape(3, 2)
             if with_grad:
+                w = self._omega(None if tr0 is None else tr0[b, 0])
                 d = self.port.apply_derivate(self.descs, self.P, p, self.U, self.pool)
                 for k in range(self.P):
-                    t = self.port.traces(d[k], self.n, self.off).reshape(3, 2)
-                    out[b, 1 + k, 0] = w[0] * t[0] + w[1] * t[1] + w[2] * t[2]
+                    t = self.port.traces(d[k], self.n, self._off()).reshape(3, 2)
+                    tc = t[:, 0] + 1j * t[:, 1]
+                    dl = w[0] * tc[0] + w[1] * tc[1] + w[2] * tc[2]
+                    out[b, 1 + k, 0] = (dl.real, dl.imag)
         return out
+
+    def grad_traces_with_global(self, params, tr0):
+        return self.traces_batched(params, True, tr0)
 
     def cost_from_traces(self, tr, with_grad, cols_total):
         prev, c1, c2 = self.cfg
@@ -64,6 +81,8 @@ class OracleEngine:
                 grad[b] = (1.0 - dl[:, 0] / n) - 1.0
             elif self.variant == 3:
                 grad[b] = -2.0 / n / n * (T[0] * dl[:, 0] + T[1] * dl[:, 1])
+            elif self.variant in (4, 5):
+                grad[b] = -2.0 / n / n * dl[:, 0]
             else:
                 grad[b] = -2.0 / n / (n + 1) * (T[0] * dl[:, 0] + T[1] * dl[:, 1])
         return cost, grad
@@ -71,6 +90,7 @@ class OracleEngine:
     def cost_batched(self, params):
         prev, c1, c2 = self.cfg
         return np.array([self.port.cost(self.descs, p, self.U, self.n, self.variant, self.off, prev, c1, c2, self.pool) for p in params])
+
 
     def cost_grad_batched(self, params):
         prev, c1, c2 = self.cfg
@@ -127,7 +147,7 @@ def _worker(rank, world, port_no, q):
         params = H.random_params(P, batch=5)
         res = {}
         for mode in ("batch", "columns"):
-            for variant in (0, 2, 3, 9):
+            for variant in (0, 2, 3, 4, 5, 9):
                 sc = sq.dist.ShardedCost(U, circ, variant=variant, mode=mode, prev_cost=0.37, engine_factory=OracleEngine)
                 c, g = sc.cost_grad(params)
                 res[(mode, variant)] = (c, g, sc.cost(params))
@@ -156,10 +176,7 @@ def test_shard_plans():
         assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
         sizes = [e - b for b, e in blocks]
         assert max(sizes) - min(sizes) <= 1
-    assert d.trace_pass_variant(abi.HILBERT_SCHMIDT_TEST) == abi.FROBENIUS_NORM
-    assert d.trace_pass_variant(abi.FROBENIUS_NORM_CORRECTION2) == abi.FROBENIUS_NORM_CORRECTION2
-    with pytest.raises(Exception):
-        d.trace_pass_variant(abi.HILBERT_SCHMIDT_TEST_CORRECTION1)
+    assert d.HS_CORRECTION == (abi.HILBERT_SCHMIDT_TEST_CORRECTION1, abi.HILBERT_SCHMIDT_TEST_CORRECTION2)
 
 
 def test_world2_gloo_matches_single_process(port):

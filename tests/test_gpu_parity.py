@@ -840,3 +840,30 @@ def test_multi_gpu_sharding_matches_oracle():
                         "127.0.0.1", "--master-port", str(port_no), os.path.join(root, "tests", "run_dist_gpu.py")],
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "DIST_GPU_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_multi_device_handle(tmp_path):
+    """multi-GPU INSIDE the library (sqgpu_create_multi): tests/run_multi_handle.py checks one handle over two devices -- batch
+    and column sharding, all cost variants, VQE, the wrapper's accelerator_num -- against the oracle, and the plain-C client
+    runs with accelerator_num = 2. Needs two visible devices (gpurun --gpus 2); the single-GPU driver run skips it."""
+    import os
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 CUDA devices")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "run_multi_handle.py"), "2"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "MULTI_HANDLE_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+    libdir = os.path.join(root, "sequential-quantum-gate-decomposer_b200", "csrc")
+    exe = str(tmp_path / "abi_client")
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-I" + os.path.join(root, "include"), "-o", exe,
+                           os.path.join(root, "tests", "c_abi", "abi_client.c"), "-L" + libdir, "-lsqgpu", "-Wl,-rpath," + libdir])
+    one = subprocess.check_output([exe], text=True)
+    for mode in ("1", "2"):
+        two = subprocess.check_output([exe, "2", mode], text=True)
+        a = np.array([float(v) for ln in one.splitlines() for v in ln.split()[1:]])
+        b = np.array([float(v) for ln in two.splitlines() for v in ln.split()[1:]])
+        assert np.abs(a - b).max() <= 1e-12
