@@ -292,6 +292,32 @@ int sqgpu_vqe_energy_batched_dev(sqgpu_handle_t h, const double* d_params, int b
 int sqgpu_vqe_energy_grad_batched_dev(sqgpu_handle_t h, const double* d_params, int batch, double* d_energy, double* d_grad,
                                       void* stream);
 
+/* ---- device-resident optimizer inner loops ------------------------------------------------------------ */
+
+/* replaces the per-iteration host round trip of solve_layer_optimization_problem_ADAM (optimization_engines/ADAM.cpp:199-330:
+ * optimization_problem_combined on the accelerator, Adam::update on the host): `batch` independent ADAM trajectories whose
+ * parameters, moments and scalar optimizer state stay on the device. The update is Adam::update (common/Adam.cpp:120-262) in
+ * its sequential semantics -- the bias-correction products advance once per parameter, as the reference's loop does -- without
+ * FMA contraction, so a trajectory equals the host-driven loop (evaluate, read back, update on the host) bit for bit.
+ * Defaults of the reference: eta 1e-3, beta1 0.68, beta2 0.8, epsilon 1e-4 (Adam::Adam, Adam.cpp:31-36).
+ * The randomisation / restart policy of ADAM.cpp stays with the caller: sqgpu_adam_steps returns the cost of every step and
+ * sqgpu_adam_get the local-minimum flag Adam::update returns, so the host applies it between calls. */
+int sqgpu_adam_init(sqgpu_handle_t h, const double* theta0 /* [batch][P] */, int batch, double eta, double beta1, double beta2,
+                    double epsilon);
+/* n_steps iterations of { f, g = cost+gradient(theta); best = min(best, f); theta = adam_update(theta, g, f) } enqueued on the
+ * device without a host synchronisation (one CUDA graph replay per step after the first). cost_history (NULL or
+ * [n_steps][batch]): f of every step, i.e. the cost BEFORE that step's update. */
+int sqgpu_adam_steps(sqgpu_handle_t h, int n_steps, double* cost_history);
+/* current parameters, lowest cost seen and the parameters that gave it (ADAM.cpp:219-222), Adam::update's status flag
+ * (1: converged to a local minimum); any pointer may be NULL */
+int sqgpu_adam_get(sqgpu_handle_t h, double* theta, double* best_cost, double* best_theta, int* status);
+
+/* replaces the one-evaluation-per-trial-point line search of BFGS_Powell (common/BFGS_Powell.cpp:70-200) by ONE batch: the k
+ * points x + alphas[j] * dir are formed on the device, cost[j] = f(x + alphas[j] dir) and, if dphi != NULL, the directional
+ * derivatives dphi[j] = grad f(x + alphas[j] dir) . dir come back (2 P + k doubles up, k or 2 k doubles down). */
+int sqgpu_line_search_batched(sqgpu_handle_t h, const double* x, const double* dir, const double* alphas, int k, double* cost,
+                              double* dphi);
+
 /* ---- introspection for bench.py / tests -------------------------------------------------------------------- */
 
 /* number of kernels this library has launched on the handle since creation (bench.py's gpu_launches). */

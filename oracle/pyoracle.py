@@ -211,6 +211,10 @@ class Port:
         return float(out[0]), grad[:n_params]
 
 
+    def adam(self, n_params, eta=1e-3, beta1=0.68, beta2=0.8, epsilon=1e-4):
+        """host mirror of Adam::update (sequential semantics): object with .update(params, grad, f0) -> status, in place"""
+        return PortAdam(self.lib, n_params, eta, beta1, beta2, epsilon)
+
     def vqe_energy_grad_sampled(self, descs, params, state0, indptr, indices, data, sample, pool=None):
         """(energy, grad[sample]): only the listed parameters' derivative states are formed"""
         d, dptr = _descs(descs)
@@ -230,6 +234,29 @@ class Port:
         if rc:
             raise Exception("port: vqe_energy_grad_sampled failed")
         return float(out[0]), grad[: sm.size]
+
+
+class PortAdam:
+    class State(C.Structure):
+        _fields_ = [("beta1_t", C.c_double), ("beta2_t", C.c_double), ("f0_mean", C.c_double), ("decreasing_test", C.c_double),
+                    ("f0_prev", C.c_double), ("f0_idx", C.c_int), ("decreasing_idx", C.c_int), ("iter_t", C.c_int),
+                    ("f0_vec", C.c_double * 100), ("decreasing_vec", C.c_int * 20)]
+
+    def __init__(self, lib, n, eta, beta1, beta2, epsilon):
+        self.lib, self.n, self.cfg = lib, n, (eta, beta1, beta2, epsilon)
+        self.state = PortAdam.State()
+        lib.sqo_adam_reset.argtypes = [C.POINTER(PortAdam.State)]
+        lib.sqo_adam_update.argtypes = [C.POINTER(PortAdam.State), _dp, _dp, _dp, _dp, C.c_int, C.c_double, C.c_double, C.c_double,
+                                        C.c_double, C.c_double]
+        lib.sqo_adam_reset(C.byref(self.state))
+        self.mom = np.zeros(n)
+        self.var = np.zeros(n)
+
+    def update(self, params, grad, f0):
+        g = _f64(grad)
+        assert params.dtype == np.float64 and params.flags["C_CONTIGUOUS"] and params.size == self.n
+        return self.lib.sqo_adam_update(C.byref(self.state), _dptr(params), _dptr(g), _dptr(self.mom), _dptr(self.var), self.n,
+                                        float(f0), *self.cfg)
 
 
 class Ref:
@@ -448,6 +475,10 @@ class RefGpu:
         L.sqrefgpu_gpu_evaluations.argtypes = [C.c_void_p]
         L.sqrefgpu_gpu_evaluations.restype = C.c_longlong
         L.sqrefgpu_flatten.argtypes = [C.c_int, _gp, C.c_int, _dp, _gp, C.c_int, _dp, C.c_longlong, C.POINTER(C.c_longlong)]
+        L.sqrefgpu_adam_create.restype = C.c_void_p
+        L.sqrefgpu_adam_create.argtypes = [C.c_double, C.c_double, C.c_double, C.c_double, C.c_int]
+        L.sqrefgpu_adam_free.argtypes = [C.c_void_p]
+        L.sqrefgpu_adam_update.argtypes = [C.c_void_p, _dp, _dp, C.c_int, C.c_double]
         L.sqrefgpu_set_library_path(abi.LIB_PATH.encode())
 
     def _err(self):
@@ -455,6 +486,25 @@ class RefGpu:
 
     def available_gpus(self):
         return int(self.lib.sqrefgpu_available_gpus())
+
+    def adam(self, n_params, eta=1e-3, beta1=0.68, beta2=0.8, epsilon=1e-4):
+        """the reference's own Adam object: .update(params, grad, f0) -> status, params updated in place"""
+        ref = self
+
+        class _A:
+            def __init__(self):
+                self.h = ref.lib.sqrefgpu_adam_create(beta1, beta2, epsilon, eta, n_params)
+
+            def update(self, params, grad, f0):
+                g = _f64(grad)
+                return ref.lib.sqrefgpu_adam_update(self.h, _dptr(params), _dptr(g), n_params, float(f0))
+
+            def __del__(self):
+                if self.h:
+                    ref.lib.sqrefgpu_adam_free(self.h)
+                    self.h = None
+
+        return _A()
 
     def flatten(self, qbit_num, descs_nested, pool=None):
         """(flat descs, pool) as integration/common_GPU.cpp: to_gpu_gates makes them from the reference's Gates_block"""

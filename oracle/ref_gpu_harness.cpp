@@ -14,6 +14,7 @@
 #include "../include/sqgpu.h"
 #include "../integration/GPU_Cost_Path_Mixin.h"
 
+#include "Adam.h"
 #include "Gates_block.h"
 #include "N_Qubit_Decomposition_custom.h"
 
@@ -260,6 +261,31 @@ int sqrefgpu_flatten(int qbit_num, const sqgpu_gate_desc* descs, int n_descs, co
         n = (int)flat.size();
     });
     return rc ? -1 : n;
+}
+
+// ---- the reference's own Adam class (common/Adam.cpp), to pin the host mirror sqo_adam_update and the device kernel ------------
+// (run with SQREF_SERIAL=1: the reference advances its bias-correction members inside a TBB parallel_for, Adam.cpp:219-245, which
+// is only deterministic when that loop runs on one thread)
+void* sqrefgpu_adam_create(double beta1, double beta2, double epsilon, double eta, int n_params) {
+    Adam* a = nullptr;
+    guarded([&] {
+        a = new Adam(beta1, beta2, epsilon, eta);
+        a->initialize_moment_and_variance(n_params);
+    });
+    return a;
+}
+
+void sqrefgpu_adam_free(void* a) { delete reinterpret_cast<Adam*>(a); }
+
+int sqrefgpu_adam_update(void* a, double* params, const double* grad, int n_params, double f0) {
+    int status = -1;
+    guarded([&] {
+        Matrix_real p(params, n_params, 1);  // wraps the caller's buffer: updated in place
+        Matrix_real g(n_params, 1);
+        memcpy(g.get_data(), grad, sizeof(double) * n_params);
+        status = reinterpret_cast<Adam*>(a)->update(p, g, f0);
+    });
+    return status;
 }
 
 long long sqrefgpu_gpu_evaluations(void* h) {

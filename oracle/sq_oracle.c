@@ -683,3 +683,52 @@ int sqo_vqe_energy_grad_sampled(const sqgpu_gate_desc* gates, int n_gates, const
     free(d);
     return rc;
 }
+
+/* ------------------------------------------------------------------------------------------------------------ */
+/* Adam::update, common/Adam.cpp:120-262, in its SEQUENTIAL semantics: the bias-correction products beta1_t / beta2_t */
+/* are class members that the reference advances inside the per-parameter loop (Adam.cpp:226-229), i.e. once per     */
+/* parameter and update (under TBB that loop is racy; one thread, ascending idx, is the deterministic reading).      */
+/* Host mirror of csrc/optim.cuh: adam_update_kernel for the trajectory tests. state = sqo_adam_state.               */
+/* ------------------------------------------------------------------------------------------------------------ */
+void sqo_adam_reset(sqo_adam_state* s) {
+    memset(s, 0, sizeof(*s));
+    s->beta1_t = 1.0;
+    s->beta2_t = 1.0;
+    s->decreasing_test = -1.0;
+    s->f0_prev = 1.7976931348623157e308;
+    for (int i = 0; i < 20; ++i) s->decreasing_vec[i] = -1;
+}
+
+int sqo_adam_update(sqo_adam_state* s, double* params, const double* grad, double* mom, double* var, int n, double f0,
+                    double eta, double beta1, double beta2, double epsilon) {
+    s->f0_mean = s->f0_mean + (f0 - s->f0_vec[s->f0_idx]) / 100.0;
+    s->f0_vec[s->f0_idx] = f0;
+    s->f0_idx = (s->f0_idx + 1) % 100;
+    double var_f0 = 0.0;
+    for (int i = 0; i < 100; ++i) var_f0 = var_f0 + (s->f0_vec[i] - s->f0_mean) * (s->f0_vec[i] - s->f0_mean);
+    var_f0 = sqrt(var_f0) / 100.0;
+    if (f0 < s->f0_prev) {
+        if (s->decreasing_vec[s->decreasing_idx] != 1) s->decreasing_test = s->decreasing_test + 2.0 / 20.0;
+        s->decreasing_vec[s->decreasing_idx] = 1;
+    } else {
+        if (s->decreasing_vec[s->decreasing_idx] == 1) s->decreasing_test = s->decreasing_test - 2.0 / 20.0;
+        s->decreasing_vec[s->decreasing_idx] = -1;
+    }
+    s->decreasing_idx = (s->decreasing_idx + 1) % 20;
+    s->f0_prev = f0;
+    double grad_var = 0.0;
+    for (int i = 0; i < n; ++i) grad_var += var[i];
+    const int barren_plateau = (grad_var < epsilon && s->decreasing_test > 0.7) ? 1 : 0;
+    for (int i = 0; i < n; ++i) {
+        mom[i] = beta1 * mom[i] + (1 - beta1) * grad[i];
+        var[i] = beta2 * var[i] + (1 - beta2) * grad[i] * grad[i];
+        s->beta1_t = s->beta1_t * beta1;
+        const double mom_bias_corr = mom[i] / (1 - s->beta1_t);
+        s->beta2_t = s->beta2_t * beta2;
+        const double var_bias_corr = var[i] / (1 - s->beta2_t);
+        if (barren_plateau) params[i] = params[i] - eta * mom_bias_corr / (sqrt(var_bias_corr) + epsilon / 100);
+        else params[i] = params[i] - eta * mom_bias_corr / (sqrt(var_bias_corr) + epsilon);
+    }
+    s->iter_t++;
+    return (fabs(s->f0_mean - f0) < 1e-6 && s->decreasing_test <= 0.7 && var_f0 / s->f0_mean < 1e-6) ? 1 : 0;
+}

@@ -96,6 +96,17 @@ int sqo_vqe_energy_grad_sampled(const sqgpu_gate_desc* gates, int n_gates, const
                                 const double* state0, int n_rows, const int32_t* indptr, const int32_t* indices,
                                 const double* values, const int32_t* sample, int n_sample, double* energy, double* grad);
 
+/* Adam::update (common/Adam.cpp:120-262), sequential semantics; host mirror of the device-resident ADAM loop */
+typedef struct sqo_adam_state {
+    double beta1_t, beta2_t, f0_mean, decreasing_test, f0_prev;
+    int f0_idx, decreasing_idx, iter_t;
+    double f0_vec[100];
+    int decreasing_vec[20];
+} sqo_adam_state;
+void sqo_adam_reset(sqo_adam_state* s);
+int sqo_adam_update(sqo_adam_state* s, double* params, const double* grad, double* mom, double* var, int n, double f0,
+                    double eta, double beta1, double beta2, double epsilon);
+
 #ifdef __cplusplus
 }
 #endif

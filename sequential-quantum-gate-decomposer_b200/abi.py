@@ -179,6 +179,10 @@ PROTOTYPES = {
     "sqgpu_kernel_time": (C.c_int, [_handle, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "sqgpu_last_launch_shape": (C.c_int, [_handle, C.POINTER(C.c_int), C.c_int]),
     "sqgpu_last_exec_flops": (C.c_int, [_handle, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "sqgpu_adam_init": (C.c_int, [_handle, _dp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double]),
+    "sqgpu_adam_steps": (C.c_int, [_handle, C.c_int, _dp]),
+    "sqgpu_adam_get": (C.c_int, [_handle, _dp, _dp, _dp, C.POINTER(C.c_int)]),
+    "sqgpu_line_search_batched": (C.c_int, [_handle, _dp, _dp, _dp, C.c_int, _dp, _dp]),
     "sqgpu_launch_count": (C.c_int, [_handle, C.POINTER(C.c_int64)]),
     "sqgpu_last_kernel_time": (C.c_int, [_handle, C.c_char_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "sqgpu_fp64_fma_peak": (C.c_int, [_handle, C.POINTER(C.c_double)]),

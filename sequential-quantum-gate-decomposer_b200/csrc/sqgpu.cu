@@ -132,6 +132,7 @@ struct Options {
     int threads = 0;           // cap of the fused executor's CTA size (0: none)
     int ctas_per_sm = 48;      // grid granularity of the cost / gradient executor
     int verbose = 0;
+    int no_graph = 0;          // device-resident optimizer loops: plain launches instead of one CUDA graph replay per step
     int tall_window = 1;       // matrices whose column does not fit shared memory: windowed executor (0: streaming fallback)
     int async_tiles = 1;       // windowed executor: bulk-async (TMA) tile pipeline
 };
@@ -150,6 +151,7 @@ const OptionName kOptionNames[] = {
     {"threads", &Options::threads, 0, 1024},
     {"ctas_per_sm", &Options::ctas_per_sm, 1, 1024},
     {"verbose", &Options::verbose, 0, 1},
+    {"no_graph", &Options::no_graph, 0, 1},
     {"tall_window", &Options::tall_window, 0, 1},
     {"async_tiles", &Options::async_tiles, 0, 1},
 };
@@ -238,6 +240,8 @@ struct sqgpu_ctx {
     // of a matrix with shard_cols_total columns; diagonal element j of the shard sits in row j + shard_offset for EVERY variant
     int shard_offset = 0, shard_cols_total = 0;
     struct MultiGpu* multi = nullptr;  // non-null: this handle is the front of a multi-device group (multi.cuh)
+    struct AdamRun* adam = nullptr;    // device-resident ADAM trajectories (optim.cuh)
+    bool capturing = false;            // a CUDA graph capture is in progress on the handle's stream: no event timers
 
     // workspaces
     DevBuf wParams, wTrPart, wWPart, wTraces, wOmega, wCost, wGrad, wMat, wDerivIdx, wTraces0;
@@ -866,12 +870,13 @@ void fill_common_args(const sqgpu_ctx* c, const FusedPlan& p, ExecArgs& a, int r
 }
 
 void time_begin(sqgpu_ctx* c, const char* name, cudaStream_t st) {
+    if (c->capturing) return;
     KernelTimer::Ring* r = c->timer.cur = c->timer.get(name);
     cudaEventRecord(r->e0[r->n % KernelTimer::RING], st);
 }
 void time_end(sqgpu_ctx* c, cudaStream_t st) {
     KernelTimer::Ring* r = c->timer.cur;
-    if (!r) return;
+    if (!r || c->capturing) return;
     cudaEventRecord(r->e1[r->n % KernelTimer::RING], st);
     r->n++;
 }
@@ -1328,6 +1333,7 @@ int set_cost_checked(sqgpu_ctx* c, int variant, int trace_offset, double prev, d
 }  // namespace
 
 namespace {
+void release_adam(sqgpu_ctx* c);
 int multi_upload(sqgpu_ctx* front, const double* data, int rows, int cols, int stride);
 int multi_eval(sqgpu_ctx* front, const double* params, int batch, bool with_grad, double* cost, double* grad);
 int multi_vqe(sqgpu_ctx* front, const double* params, int batch, bool with_grad, double* energy, double* grad);
@@ -1418,6 +1424,7 @@ int sqgpu_destroy(sqgpu_handle_t c) {
                           &c->wTraces, &c->wOmega, &c->wCost, &c->wGrad, &c->wMat, &c->wDerivIdx, &c->wTraces0,
                           &c->hIndptr, &c->hIndices, &c->hValues};
         for (DevBuf* b : bufs) b->release();
+        release_adam(c);
         c->timer.destroy();
         if (c->last_done) cudaEventDestroy(c->last_done);
         cudaStreamDestroy(c->stream);
@@ -2249,3 +2256,5 @@ int sqgpu_fp64_fma_peak(sqgpu_handle_t c, double* tflops) {
 #include "vqe_impl.cuh"
 // several devices behind one handle
 #include "multi.cuh"
+// device-resident optimizer inner loops
+#include "optim.cuh"

@@ -228,6 +228,41 @@ class Engine:
         abi.check(self.lib, self.lib.sqgpu_vqe_energy_grad_batched_dev(self._h, d_params, int(batch), d_energy, d_grad,
                                                                        stream))
 
+    # ---- device-resident optimizer loops (N1) -----------------------------------------------------------------
+    def adam_init(self, theta0, eta=1e-3, beta1=0.68, beta2=0.8, epsilon=1e-4):
+        """``theta0`` [batch, P] (or [P]): independent ADAM trajectories kept on the device (sqgpu_adam_init)"""
+        t = self._params(theta0)
+        self._adam_batch = t.shape[0]
+        abi.check(self.lib, self.lib.sqgpu_adam_init(self._h, abi.as_dp(t), t.shape[0], float(eta), float(beta1), float(beta2),
+                                                     float(epsilon)))
+
+    def adam_steps(self, n_steps):
+        """run n_steps on the device; returns the cost history [n_steps, batch] (cost before each step's update)"""
+        hist = np.empty((int(n_steps), self._adam_batch), dtype=np.float64)
+        abi.check(self.lib, self.lib.sqgpu_adam_steps(self._h, int(n_steps), abi.as_dp(hist) if hist.size else None))
+        return hist
+
+    def adam_get(self):
+        """(theta, best_cost, best_theta, status)"""
+        B, P = self._adam_batch, self.n_params
+        theta, best = np.empty((B, P)), np.empty((B, P))
+        bc = np.empty(B)
+        st = np.zeros(B, dtype=np.int32)
+        abi.check(self.lib, self.lib.sqgpu_adam_get(self._h, abi.as_dp(theta), abi.as_dp(bc), abi.as_dp(best),
+                                                    st.ctypes.data_as(C.POINTER(C.c_int))))
+        return theta, bc, best, st
+
+    def line_search_batched(self, x, direction, alphas, with_derivative=True):
+        """cost (and directional derivative) at x + alpha_j * direction for all alphas as one batch (sqgpu_line_search_batched)"""
+        x, d, a = _f64(x).reshape(-1), _f64(direction).reshape(-1), _f64(alphas).reshape(-1)
+        if x.size != self.n_params or d.size != self.n_params:
+            raise Exception("Number of free parameters should be %d" % self.n_params)
+        cost = np.empty(a.size)
+        dphi = np.empty(a.size) if with_derivative else None
+        abi.check(self.lib, self.lib.sqgpu_line_search_batched(self._h, abi.as_dp(x), abi.as_dp(d), abi.as_dp(a), a.size,
+                                                               abi.as_dp(cost), abi.as_dp(dphi) if with_derivative else None))
+        return (cost, dphi) if with_derivative else cost
+
     # ---- introspection --------------------------------------------------------------------------------------
     def launch_count(self):
         n = C.c_int64(0)

@@ -171,3 +171,38 @@ def test_gpu_flavour_batched_and_scalar_hooks(refgpu):
         fg, gg = gpu.cost_grad(ps[1])
         fc, gc = cpu.cost_grad(ps[1])
         assert close_rel(fg, fc) and close_rel(gg, gc)
+
+
+def test_adam_mirror_matches_reference_class():
+    """oracle/sq_oracle.c: sqo_adam_update (the host mirror of the device-resident ADAM loop) against the reference's own Adam
+    class (common/Adam.cpp) over 300 updates of a quadratic: parameters within 1e-14, identical status flags. Run in a
+    subprocess with SQREF_SERIAL=1: the reference advances its bias-correction members inside a TBB parallel_for, which is
+    deterministic only on one thread."""
+    import subprocess
+    import sys
+
+    import pyoracle
+
+    if not pyoracle.RefGpu.available() and not os.path.isdir("/root/reference"):
+        pytest.skip("oracle/_ref/libsqref_gpu.so not built and /root/reference absent")
+    code = r'''
+import sys
+sys.path[:0] = [%r, %r, %r]
+import numpy as np, pyoracle
+port, rg = pyoracle.Port(), pyoracle.RefGpu()
+n = 37
+rng = np.random.default_rng(0)
+a, b = port.adam(n), rg.adam(n)
+x1 = rng.normal(size=n); x2 = x1.copy()
+A = rng.normal(size=(n, n)); A = A @ A.T / n
+worst = 0.0
+for it in range(300):
+    s1 = a.update(x1, A @ x1, float(0.5 * x1 @ A @ x1))
+    s2 = b.update(x2, A @ x2, float(0.5 * x2 @ A @ x2))
+    assert s1 == s2, (it, s1, s2)
+    worst = max(worst, float(np.abs(x1 - x2).max()))
+assert worst < 1e-14, worst
+print("ADAM_MIRROR_OK", worst)
+''' % tuple(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), d) for d in ("", "oracle", "tests"))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, SQREF_SERIAL="1"), timeout=300)
+    assert r.returncode == 0 and "ADAM_MIRROR_OK" in r.stdout, r.stdout + r.stderr
