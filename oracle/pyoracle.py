@@ -479,6 +479,7 @@ class RefGpu:
         L.sqrefgpu_adam_create.argtypes = [C.c_double, C.c_double, C.c_double, C.c_double, C.c_int]
         L.sqrefgpu_adam_free.argtypes = [C.c_void_p]
         L.sqrefgpu_adam_update.argtypes = [C.c_void_p, _dp, _dp, C.c_int, C.c_double]
+        L.sqrefgpu_export_binary.argtypes = [C.c_int, _gp, C.c_int, _dp, C.c_int, C.c_char_p]
         L.sqrefgpu_set_library_path(abi.LIB_PATH.encode())
 
     def _err(self):
@@ -505,6 +506,13 @@ class RefGpu:
                     self.h = None
 
         return _A()
+
+    def export_binary(self, qbit_num, descs_nested, params, filename):
+        """export_gate_list_to_binary of the reference on the structure given by a nested descriptor stream"""
+        d, dptr = _descs(descs_nested)
+        p = _f64(params)
+        if self.lib.sqrefgpu_export_binary(qbit_num, dptr, len(d), _dptr(p), p.size, str(filename).encode()):
+            raise Exception("ref_gpu: export_binary failed: " + self._err())
 
     def flatten(self, qbit_num, descs_nested, pool=None):
         """(flat descs, pool) as integration/common_GPU.cpp: to_gpu_gates makes them from the reference's Gates_block"""

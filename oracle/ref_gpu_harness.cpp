@@ -288,6 +288,21 @@ int sqrefgpu_adam_update(void* a, double* params, const double* grad, int n_para
     return status;
 }
 
+// ---- the reference's binary gate-list format (Gates_block.cpp:4807-5330), for the round-trip tests of gate_io.py --------------
+int sqrefgpu_export_binary(int qbit_num, const sqgpu_gate_desc* descs, int n_descs, const double* params, int n_params, const char* filename) {
+    return guarded([&] {
+        Gates_block* blk = reinterpret_cast<Gates_block*>(sqref_circuit_create(qbit_num, descs, n_descs, nullptr));
+        if (!blk) throw std::string("ref_gpu_harness: cannot build the gate structure");
+        Matrix_real p(1, n_params);
+        memcpy(p.get_data(), params, sizeof(double) * n_params);
+        export_gate_list_to_binary(p, blk, std::string(filename), 0);
+        sqref_circuit_free(blk);
+    });
+}
+
+// (the reference's own import_gate_list_from_binary is not exposed: it indexes gate_block_levels[-1] when the top-level block
+// completes, Gates_block.cpp:5296-5303, and crashes on files its own exporter wrote -- reference defect 7 in DESIGN.md)
+
 long long sqrefgpu_gpu_evaluations(void* h) {
     Session* s = reinterpret_cast<Session*>(h);
     return s->gpu ? s->dev->gpu_evaluations() : 0;

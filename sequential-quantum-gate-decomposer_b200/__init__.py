@@ -10,6 +10,8 @@ handle) and ``Variational_Quantum_Eigensolver`` (state-vector cost path).
 from . import abi
 from . import qasm
 from . import dist
+from . import gate_io
+from . import optimize
 from .circuit import Circuit
 from .engine import Engine
 from .decomposition import N_Qubit_Decomposition_adaptive, N_Qubit_Decomposition_custom
@@ -20,6 +22,6 @@ qgd_Circuit = Circuit
 qgd_Variational_Quantum_Eigensolver_Base = Variational_Quantum_Eigensolver
 
 __all__ = [
-    "abi", "qasm", "dist", "Circuit", "qgd_Circuit", "Engine", "N_Qubit_Decomposition_adaptive", "N_Qubit_Decomposition_custom",
+    "abi", "qasm", "dist", "gate_io", "optimize", "Circuit", "qgd_Circuit", "Engine", "N_Qubit_Decomposition_adaptive", "N_Qubit_Decomposition_custom",
     "Variational_Quantum_Eigensolver", "qgd_Variational_Quantum_Eigensolver_Base",
 ]

@@ -9,7 +9,11 @@ hot path: ``add_Adaptive_Layers``, ``add_Finalyzing_Layer_To_Gate_Structure``, `
 kwarg the reference reserves for accelerators (Optimization_Interface.cpp:189-197); it must be >= 1 here --
 the CPU path belongs to the reference, not to this package.
 
-The optimizers / synthesis strategies above these calls are out of scope and not mirrored.
+``Start_Decomposition`` / ``set_Optimizer`` / ``get_Optimized_Parameters`` are a THIN control loop over that cost path
+(SURVEY.md §8f N4): the level search of determine_initial_gate_structure (N_Qubit_Decomposition_adaptive.cpp:786-1037) with
+this package's own optimizer loops (optimize.py: L-BFGS with a device-batched line search, device-resident ADAM). The
+reference's full control plane -- its optimizer engines, compression, CRY -> CNOT finalisation -- is not
+mirrored here; it runs unchanged over the GPU cost path through the drop-in of integration/.
 """
 import numpy as np
 
@@ -51,6 +55,11 @@ class N_Qubit_Decomposition_custom:
         self._device = int(device)
         self._engine_obj = None
         self._dirty = True
+        self._optimizer = "BFGS"  # Optimization_Interface: set_optimizer(BFGS) is the constructors' default for small problems
+        self._optimization_tolerance = float(self.config.get("optimization_tolerance", 1e-4))  # ..._adaptive.cpp:539-544
+        self._optimized_parameters = None
+        self._current_minimum = None
+        self._num_evaluations = 0
 
     @property
     def _engine(self):
@@ -82,6 +91,71 @@ class N_Qubit_Decomposition_custom:
 
     def get_Qbit_Num(self):
         return self.qbit_num
+
+    # ---- optimisation over the GPU cost path (thin; see the module docstring) ------------------------------------
+    def set_Optimizer(self, optimizer="BFGS"):
+        """"BFGS": L-BFGS with a device-batched line search; "ADAM": device-resident ADAM trajectories. The reference's other
+        engines (AGENTS, COSINE, BAYES_OPT ...) stay with the reference: they run over this cost path through integration/."""
+        if optimizer not in ("BFGS", "ADAM"):
+            raise Exception("set_Optimizer: '%s' is not provided by this package (BFGS, ADAM); use the reference's engines over the "
+                            "GPU cost path through the drop-in of integration/" % optimizer)
+        self._optimizer = optimizer
+
+    def set_Optimization_Tolerance(self, tolerance):
+        self._optimization_tolerance = float(tolerance)
+
+    def get_Optimized_Parameters(self):
+        if self._optimized_parameters is None:
+            raise Exception("get_Optimized_Parameters: no optimisation has been run")
+        return self._optimized_parameters.copy()
+
+    def set_Optimized_Parameters(self, parameters):
+        p = np.ascontiguousarray(parameters, dtype=np.float64).reshape(-1)
+        if p.size != self.get_Parameter_Num():
+            raise Exception("Number of free parameters should be %d, but got %d" % (self.get_Parameter_Num(), p.size))
+        self._optimized_parameters = p.copy()
+
+    def get_Decomposition_Error(self):
+        return self._current_minimum
+
+    def get_Num_of_Iters(self):
+        return self._num_evaluations
+
+    def _optimize_structure(self, rng):
+        """minimise the cost over the current gate structure; returns (parameters, cost)"""
+        from . import optimize
+
+        eng = self._sync()
+        P = self.get_Parameter_Num()
+        tol = self._optimization_tolerance
+        if P == 0:
+            return np.zeros(0), float(eng.cost_batched(np.zeros((1, 0)))[0])
+        if self._optimizer == "ADAM":
+            starts = int(self.config.get("adam_trajectories", 16))
+            steps_max = int(self.config.get("max_inner_iterations", 4000))
+            X0 = rng.random((starts, P)) * 2 * np.pi
+            X0[0] = 0.0
+            eng.adam_init(X0, eta=float(self.config.get("eta", 1e-2)))
+            done = 0
+            while done < steps_max:
+                hist = eng.adam_steps(200)
+                done += 200
+                self._num_evaluations += 200 * starts
+                if hist.min() < tol:
+                    break
+            _, best_cost, best_theta, _ = eng.adam_get()
+            b = int(np.argmin(best_cost))
+            return best_theta[b], float(best_cost[b])
+
+        def cost_grad(x):
+            f, g = eng.cost_grad_batched(x.reshape(1, -1))
+            return float(f[0]), g[0]
+
+        x, f, _, ne = optimize.multistart_lbfgs(eng.cost_batched, cost_grad, eng.line_search_batched, P, rng,
+                                                starts=int(self.config.get("initial_points", 64)), keep=int(self.config.get("restarts", 4)),
+                                                max_iter=int(self.config.get("max_inner_iterations", 2000)), tol=tol * 1e-2)
+        self._num_evaluations += ne
+        return x, f
 
     # ---- cost configuration ---------------------------------------------------------------------------------
     def set_Cost_Function_Variant(self, costfnc=0):
@@ -199,3 +273,25 @@ class N_Qubit_Decomposition_adaptive(N_Qubit_Decomposition_custom):
             block.add_U3(q)
         self._circuit.add_Circuit(block)
         self._dirty = True
+
+    def Start_Decomposition(self):
+        """The level search of determine_initial_gate_structure (N_Qubit_Decomposition_adaptive.cpp:786-1037): for
+        level = level_limit_min .. level_limit_max build `level` adaptive layers + the finalizing layer, minimise the cost from
+        random starts, stop at the first level whose minimum is below the optimization tolerance, keep the best level otherwise.
+        Compression and the CRY -> CNOT finalisation of the reference (compress_circuit / finalize_circuit, :372-686) are not
+        part of this thin loop. Afterwards: get_Circuit(), get_Optimized_Parameters(), get_Decomposition_Error()."""
+        rng = np.random.default_rng(int(self.config.get("seed", 0)))
+        best = None
+        for level in range(self.level_limit_min, self.level_limit + 1):
+            self._circuit = Circuit(self.qbit_num, self._device)
+            for _ in range(level):
+                self.add_Adaptive_Layers()
+            self.add_Finalyzing_Layer_To_Gate_Structure()
+            x, f = self._optimize_structure(rng)
+            if best is None or f < best[2]:
+                best = (self._circuit, x, f, level)
+            if f < self._optimization_tolerance:
+                break
+        self._circuit, self._optimized_parameters, self._current_minimum, self.decomposition_level = best
+        self._dirty = True
+        return self._current_minimum

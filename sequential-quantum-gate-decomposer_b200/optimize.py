@@ -1,0 +1,100 @@
+"""Host-side optimizer loops over the engine's cost path: the thin layer that turns the batched
+cost+gradient entry points into ``Start_Decomposition``.
+
+Not a port of the reference's optimizers (optimization_engines/*.cpp are out of the hot-path scope and stay usable unchanged
+through the drop-in of integration/): a limited-memory BFGS whose line search evaluates ALL trial step lengths of an iteration
+as one batch on the device (sqgpu_line_search_batched; the reference's BFGS_Powell evaluates them one by one,
+common/BFGS_Powell.cpp:70-200), and a driver for the device-resident ADAM trajectories (sqgpu_adam_steps).
+
+Everything numerical happens in the two callables handed in -- in the product they are Engine.cost_grad_batched and
+Engine.line_search_batched -- so the host logic is testable on CPU against the oracle.
+"""
+import numpy as np
+
+
+def lbfgs(cost_grad, line_search, x0, max_iter=500, tol=1e-10, gtol=1e-9, history=12, alphas=None, callback=None):
+    """Minimise f from x0. ``cost_grad(x) -> (f, g)``; ``line_search(x, d, alphas) -> (costs, dphis)`` evaluates
+    f(x + a d) and d/da f(x + a d) for every a in ``alphas`` at once (one device batch).
+
+    Per iteration: two-loop recursion for the direction, ONE batched line-search call over a geometric ladder of step lengths,
+    the best point that satisfies the Armijo condition (preferring one that also satisfies the curvature condition), then one
+    cost+gradient evaluation at the accepted point. Returns (x, f, n_iterations, n_evaluations)."""
+    x = np.array(x0, dtype=np.float64).reshape(-1)
+    if alphas is None:
+        alphas = np.array([2.0 ** k for k in range(3, -14, -1)])  # 8, 4, 2, 1, 1/2, ... 2^-13
+    f, g = cost_grad(x)
+    n_eval = 1
+    S, Y = [], []
+    it = 0
+    for it in range(1, max_iter + 1):
+        if f < tol or np.abs(g).max() < gtol:
+            break
+        # two-loop recursion
+        q = g.copy()
+        al = []
+        for s, y in zip(reversed(S), reversed(Y)):
+            a = (s @ q) / (y @ s)
+            al.append(a)
+            q -= a * y
+        if S:
+            q *= (S[-1] @ Y[-1]) / (Y[-1] @ Y[-1])
+        for (s, y), a in zip(zip(S, Y), reversed(al)):
+            b = (y @ q) / (y @ s)
+            q += (a - b) * s
+        d = -q
+        dphi0 = g @ d
+        if not (dphi0 < 0):  # not a descent direction: restart from steepest descent
+            S, Y = [], []
+            d = -g
+            dphi0 = g @ d
+        scale = 1.0 if S else min(1.0, 1.0 / max(np.abs(g).max(), 1e-300))
+        trial = alphas * scale
+        costs, dphis = line_search(x, d, trial)
+        n_eval += len(trial)
+        armijo = costs <= f + 1e-4 * trial * dphi0
+        wolfe = armijo & (np.abs(dphis) <= 0.9 * abs(dphi0))
+        pick = None
+        if wolfe.any():
+            idx = np.flatnonzero(wolfe)
+            pick = idx[np.argmin(costs[idx])]
+        elif armijo.any():
+            idx = np.flatnonzero(armijo)
+            pick = idx[np.argmin(costs[idx])]
+        if pick is None:
+            if S:  # the quasi-Newton model is bad here: drop it and retry along the gradient
+                S, Y = [], []
+                continue
+            break  # no decrease even along the gradient at step 2^-13 / |g|: converged to rounding
+        x_new = x + trial[pick] * d
+        f_new, g_new = cost_grad(x_new)
+        n_eval += 1
+        s, y = x_new - x, g_new - g
+        if s @ y > 1e-14 * np.sqrt((s @ s) * (y @ y)):
+            S.append(s)
+            Y.append(y)
+            if len(S) > history:
+                S.pop(0)
+                Y.pop(0)
+        x, f, g = x_new, f_new, g_new
+        if callback is not None:
+            callback(it, x, f)
+    return x, float(f), it, n_eval
+
+
+def multistart_lbfgs(cost_batched, cost_grad, line_search, n_params, rng, starts=64, keep=4, **kw):
+    """``starts`` random initial points are scored with ONE batched cost call; L-BFGS runs from the ``keep`` best, best first,
+    and stops at the first run that reaches kw['tol'] (the reference restarts BFGS from perturbed points one run after the
+    other, optimization_engines/BFGS.cpp:124-150)."""
+    X0 = rng.random((starts, n_params)) * 2 * np.pi
+    X0[0] = 0.0  # the reference's other initial guess (guess_type ZEROS / CLOSE_TO_ZERO)
+    scores = np.asarray(cost_batched(X0))
+    best = (None, np.inf, 0, 0)
+    total_eval = starts
+    for i in np.argsort(scores)[:keep]:
+        x, f, it, ne = lbfgs(cost_grad, line_search, X0[i], **kw)
+        total_eval += ne
+        if f < best[1]:
+            best = (x, f, it, total_eval)
+        if f < kw.get("tol", 1e-10):
+            break
+    return best[0], best[1], best[2], total_eval

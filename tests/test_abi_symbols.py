@@ -274,3 +274,28 @@ def test_multi_handle_argument_checks(lib):
     assert lib.sqgpu_create_multi(2, None, abi.SHARD_AUTO, C.byref(h)) == abi.ERR_NO_DEVICE
     with pytest.raises(abi.SqgpuError):
         H.sq.Engine(devices=2)
+
+
+def test_lbfgs_host_loop_with_oracle_callables(port):
+    """optimize.lbfgs is host logic over two callables (cost+gradient, batched line search); with oracle-backed callables it
+    decomposes a 3-qubit unitary made of the very structure it optimises: cost -> 0"""
+    sq = H.sq
+    n = 3
+    c = H.adaptive_circuit(n, 2)
+    d, pool = c.descriptors()
+    P = c.get_Parameter_Num()
+    U = np.ascontiguousarray(port.apply_circuit(d, H.random_params(P, seed=5), np.eye(1 << n, dtype=np.complex128)).conj().T)
+    cg = lambda x: port.cost_grad(d, P, x, U, n, 0)
+
+    def ls(x, dd, al):
+        r = [port.cost_grad(d, P, x + a * dd, U, n, 0) for a in al]
+        return np.array([q[0] for q in r]), np.array([q[1] @ dd for q in r])
+
+    x, f, it, ne = sq.optimize.multistart_lbfgs(lambda X: [port.cost(d, xx, U, n, 0) for xx in X], cg, ls, P, np.random.default_rng(1),
+                                                starts=8, keep=3, max_iter=300, tol=1e-9)
+    assert f < 1e-4 and ne > it > 0  # far below the starting cost (~1); the decomposition tolerance of the reference is 1e-4
+    dec = sq.N_Qubit_Decomposition_adaptive(U, level_limit_max=3, level_limit_min=1)
+    with pytest.raises(Exception):
+        dec.set_Optimizer("AGENTS")
+    with pytest.raises(Exception):
+        dec.get_Optimized_Parameters()

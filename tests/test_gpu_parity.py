@@ -931,3 +931,27 @@ def test_batched_line_search(sq, port):
             f_ref, g_ref = port.cost_grad(d, P, x + a * direction, U, n, variant)
             assert close_rel(cost[j], f_ref) and close_rel(dphi[j], g_ref @ direction)
     e.close()
+
+
+@pytest.mark.parametrize("optimizer", ["BFGS", "ADAM"])
+def test_start_decomposition_config1(sq, optimizer):
+    """BASELINE configs[0] end to end through this package: N_Qubit_Decomposition_adaptive on data/Umtx.mat (4 qubits; the
+    matrix is stored in the golden fixture), Start_Decomposition over the GPU cost path; the decomposition error of the
+    reference's own test (tests/decomposition/test_decomposition.py:129-148) is below 1e-3"""
+    import golden_cases as G
+
+    Uct = G.load("C1_L3").U  # = Umtx.conj().T, what the examples pass
+    dec = sq.N_Qubit_Decomposition_adaptive(Uct, level_limit_max=5, level_limit_min=1, config={"optimization_tolerance": 1e-6}, accelerator_num=1)
+    dec.set_Optimizer(optimizer)
+    err = dec.Start_Decomposition()
+    params = dec.get_Optimized_Parameters()
+    assert err < 1e-3 and params.size == dec.get_Parameter_Num()
+    # the reference test's error measure: Umtx (C)^dagger up to a global phase
+    C = dec.get_Matrix(params)
+    Umtx = Uct.conj().T
+    prod = Umtx @ C.conj().T   # C approximates Umtx^dagger^-1 ... cost is 1 - Re Tr(C Uct)/N: C Uct ~ 1
+    prod = C @ Uct
+    prod = prod * np.exp(-1j * np.angle(prod[0, 0]))
+    m = np.eye(16) * 2 - prod - prod.conj().T
+    assert np.real(np.trace(m)) / 2 < 1e-3
+    assert dec.get_Num_of_Iters() > 0 and 1 <= dec.decomposition_level <= 5
