@@ -297,6 +297,17 @@ static const int B0TAB = 64;  // batch bases precomputed per op (tiles with more
 #ifndef SQ_B0_MODE
 #define SQ_B0_MODE 1
 #endif
+// Complex arithmetic of the 3-qubit blocks on the tensor cores (compile-time switch):
+//   0: the real embedding -- an 8 x 8 complex block is a 16 x 16 real matrix, 8 DMMA per 8 items forward, 24 backward;
+//   1 (default): three real products per complex product ("3M": with K = C + iD and x = u + iv,
+//      t1 = C u, t2 = D v, t3 = (C + D)(u + v);  Re = t1 - t2,  Im = t3 - t1 - t2), each an 8 x 8 real matrix-vector product =
+//      2 DMMA per 8 items: 6 DMMA forward, 18 backward (K^dagger p, K^T beta and the W' outer products each drop from 8 to 6),
+//      plus 8 / 20 DADD for the sums and differences -- 12-15 % fewer FP64-pipe cycles, and 6 / 12 kernel-fragment registers
+//      instead of 16 / 32. The rounding differs from the 4-product form by O(eps) per product (normwise; the parity tests hold
+//      the 1e-12 / 1e-10 bars for both settings).
+#ifndef SQ_BLOCK_3M
+#define SQ_BLOCK_3M 1
+#endif
 // How the op tables travel to shared memory: 0 (default): per-thread cp.async (LDGSTS) groups; 1: bulk-async copies issued by
 // one thread (cp.async.bulk, the TMA engine: UBLKCP in SASS) with mbarrier completion. Measured: the bulk ring is 2.2 % SLOWER
 // on C3 (1 217 vs 1 245 evals/s) and 1.5 % on C5 -- a 4.9 KB table per ~3 us op is too small for the TMA engine to beat 1.2
@@ -364,11 +375,26 @@ __device__ __forceinline__ void fill_optab(OpTab* T, const DevOp& op, const cplx
         }
         __syncthreads();
         const int ju = s_choice[0], pa = s_choice[1];
+#if SQ_BLOCK_3M
+        // frag[mode][m * 2 + s][lane]: B-operand fragment (lane = (k = lane & 3, n = lane >> 2)) of k-step s of the REAL 8 x 8
+        // matrix m in {0: C, 1: D, 2: C + D} of the mode's kernel C + iD (mode 0: K, 1: K^dagger, 2: K^T):
+        // entry [out amplitude o(n)][in amplitude c(4 s + k)] with o(n) = dep3(n >> 1, n & 1), c(4 s + k) = dep3(k, s) -- the
+        // lane's two inputs c(j), c(4 + j) are its two outputs o(2 j), o(2 j + 1): loads and stores hit the same elements
+        for (int e = tid; e < 3 * 6 * 32; e += nthr) {
+            const int mode = e / (6 * 32), ms = (e / 32) % 6, lane = e & 31, m = ms >> 1, st = ms & 1;
+            const int n = lane >> 2, k = lane & 3;
+            const int ao = dep3(n >> 1, n & 1, ju), ai = dep3(k, st, ju);
+            const cplx kv = (mode == 0) ? K[ao * 8 + ai] : K[ai * 8 + ao];
+            const double cre = kv.x, dim_ = (mode == 1) ? -kv.y : kv.y;
+            T->frag[mode][ms][lane] = (m == 0) ? cre : (m == 1 ? dim_ : cre + dim_);
+        }
+#else
         for (int e = tid; e < 3 * 8 * 32; e += nthr) {
             const int mode = e >> 8, ts = (e >> 5) & 7, lane = e & 31, t = ts >> 2, s = ts & 3;
             const int n = lane >> 2, k = lane & 3;
             T->frag[mode][ts][lane] = kreal_entry(K, 8, mode, dep3(n >> 1, t, ju), n & 1, dep3(k, s >> 1, ju), s & 1);
         }
+#endif
         for (int e = tid; e < 4 * 32; e += nthr) {
             const int sidx = e >> 5, lane = e & 31;
             T->slot[sidx][lane] = (sidx < 2) ? G.slot(lane >> 2, dep3(lane & 3, sidx, ju))
@@ -416,6 +442,7 @@ __global__ void build_optabs(const DevOp* __restrict__ ops, int n_ops, const cpl
 template <int LOG_CT, int KQ>
 __device__ __forceinline__ void block_dmma_forward(cplx* sa, const OpTabS* T, int q0, int q1, int q2, int rows, int tid, int nthr) {
     constexpr int NT = (KQ == 3) ? 2 : 1, KS = 2 * NT;
+    constexpr bool M3 = (KQ == 3) && (SQ_BLOCK_3M != 0);
     const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
     double kf[NT][KS];
     int sl[NT];
@@ -423,7 +450,8 @@ __device__ __forceinline__ void block_dmma_forward(cplx* sa, const OpTabS* T, in
     for (int t = 0; t < NT; ++t) {
         sl[t] = T->slot[t][lane];
 #pragma unroll
-        for (int s = 0; s < KS; ++s) kf[t][s] = T->frag[0][t * KS + s][lane];
+        for (int s = 0; s < KS; ++s)
+            if (!M3 || t * KS + s < 6) kf[t][s] = T->frag[0][t * KS + s][lane];  // 3M: kf[0][0..3] = C0 C1 D0 D1, kf[1][0..1] = S0 S1
     }
     const int nitems = (rows >> KQ) << LOG_CT;
     const bool tab_b0 = (SQ_B0_MODE == 1) && nitems <= 8 * B0TAB;
@@ -439,13 +467,27 @@ __device__ __forceinline__ void block_dmma_forward(cplx* sa, const OpTabS* T, in
             x[u] = sa[B0 ^ sl[u]];
             d[u] = czero();
         }
+        if (M3) {
+            // t1 = C u, t2 = D v, t3 = (C + D)(u + v) over the two k-steps; the D fragment pair holds outputs o(2j), o(2j+1),
+            // which are the amplitudes the lane loaded as x[0], x[1]
+            double t1[2] = {0.0, 0.0}, t2[2] = {0.0, 0.0}, t3[2] = {0.0, 0.0};
+            dmma_m8n8k4(t1[0], t1[1], x[0].x, kf[0][0]);
+            dmma_m8n8k4(t2[0], t2[1], x[0].y, kf[0][2]);
+            dmma_m8n8k4(t3[0], t3[1], x[0].x + x[0].y, kf[NT - 1][0]);
+            dmma_m8n8k4(t1[0], t1[1], x[NT - 1].x, kf[0][1]);
+            dmma_m8n8k4(t2[0], t2[1], x[NT - 1].y, kf[0][3]);
+            dmma_m8n8k4(t3[0], t3[1], x[NT - 1].x + x[NT - 1].y, kf[NT - 1][1]);
+            d[0] = cmake(t1[0] - t2[0], t3[0] - t1[0] - t2[0]);
+            d[NT - 1] = cmake(t1[1] - t2[1], t3[1] - t1[1] - t2[1]);
+        } else {
 #pragma unroll
-        for (int u = 0; u < NT; ++u)
+            for (int u = 0; u < NT; ++u)
 #pragma unroll
-            for (int t = 0; t < NT; ++t) {
-                dmma_m8n8k4(d[t].x, d[t].y, x[u].x, kf[t][2 * u]);
-                dmma_m8n8k4(d[t].x, d[t].y, x[u].y, kf[t][2 * u + 1]);
-            }
+                for (int t = 0; t < NT; ++t) {
+                    dmma_m8n8k4(d[t].x, d[t].y, x[u].x, kf[t][2 * u]);
+                    dmma_m8n8k4(d[t].x, d[t].y, x[u].y, kf[t][2 * u + 1]);
+                }
+        }
 #pragma unroll
         for (int t = 0; t < NT; ++t) sa[B0 ^ sl[t]] = d[t];
     }
@@ -457,6 +499,7 @@ template <int LOG_CT, int KQ>
 __device__ __forceinline__ void block_dmma_backward(cplx* sa, cplx* sb, const OpTabS* T, int q0, int q1, int q2, int rows,
                                                     bool has_w, cplx* wslot, int tid, int nthr) {
     constexpr int DIM = 1 << KQ, NT = (KQ == 3) ? 2 : 1, KS = 2 * NT;
+    constexpr bool M3 = (KQ == 3) && (SQ_BLOCK_3M != 0);
     const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
     double kd[NT][KS], kt[NT][KS];
     int sl[NT], slw[2];
@@ -464,10 +507,11 @@ __device__ __forceinline__ void block_dmma_backward(cplx* sa, cplx* sb, const Op
     for (int t = 0; t < NT; ++t) {
         sl[t] = T->slot[t][lane];
 #pragma unroll
-        for (int s = 0; s < KS; ++s) {
-            kd[t][s] = T->frag[0][t * KS + s][lane];  // K^dagger
-            kt[t][s] = T->frag[1][t * KS + s][lane];  // K^T
-        }
+        for (int s = 0; s < KS; ++s)
+            if (!M3 || t * KS + s < 6) {  // 3M: [0][0..3] = C0 C1 D0 D1, [1][0..1] = S0 S1 of K^dagger / K^T
+                kd[t][s] = T->frag[0][t * KS + s][lane];  // K^dagger
+                kt[t][s] = T->frag[1][t * KS + s][lane];  // K^T
+            }
     }
     slw[0] = T->slot[2][lane];
     slw[1] = T->slot[3][lane];
@@ -493,7 +537,17 @@ __device__ __forceinline__ void block_dmma_backward(cplx* sa, cplx* sb, const Op
             db[u] = czero();
         }
         if (has_w) {
-            if (KQ == 3) {
+            if (M3) {
+                // three real outer products per half: T1 += br pr^T, T2 += bi pi^T, T3 += (br + bi)(pr + pi)^T
+                // (pacc[0][0] = T1, pacc[NT-1][NT-1] = T2, pacc[0][NT-1] = T3)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const cplx bw = sb[B0 ^ slw[h]], pw = sa[B0 ^ slw[h]];
+                    dmma_m8n8k4(pacc[0][0][0], pacc[0][0][1], bw.x, pw.x);
+                    dmma_m8n8k4(pacc[NT - 1][NT - 1][0], pacc[NT - 1][NT - 1][1], bw.y, pw.y);
+                    dmma_m8n8k4(pacc[0][NT - 1][0], pacc[0][NT - 1][1], bw.x + bw.y, pw.x + pw.y);
+                }
+            } else if (KQ == 3) {
                 // lane (rho, it): amplitude permw(rho) of item it + 4h of beta (A operand, rows = rho, tile = re/im) and of p
                 // (B operand, columns = rho)
 #pragma unroll
@@ -511,15 +565,33 @@ __device__ __forceinline__ void block_dmma_backward(cplx* sa, cplx* sb, const Op
                 for (int h = 0; h < 2; ++h) dmma_m8n8k4(pacc[0][0][0], pacc[0][0][1], sbd[(2 * B0) ^ slw[h]], sad[(2 * B0) ^ slw[h]]);
             }
         }
+        if (M3) {
+            double a1[2] = {0.0, 0.0}, a2[2] = {0.0, 0.0}, a3[2] = {0.0, 0.0}, b1[2] = {0.0, 0.0}, b2[2] = {0.0, 0.0}, b3[2] = {0.0, 0.0};
 #pragma unroll
-        for (int u = 0; u < NT; ++u)
-#pragma unroll
-            for (int t = 0; t < NT; ++t) {
-                dmma_m8n8k4(da[t].x, da[t].y, p[u].x, kd[t][2 * u]);
-                dmma_m8n8k4(db[t].x, db[t].y, be[u].x, kt[t][2 * u]);
-                dmma_m8n8k4(da[t].x, da[t].y, p[u].y, kd[t][2 * u + 1]);
-                dmma_m8n8k4(db[t].x, db[t].y, be[u].y, kt[t][2 * u + 1]);
+            for (int st = 0; st < 2; ++st) {
+                const cplx pp = p[st == 0 ? 0 : NT - 1], bb = be[st == 0 ? 0 : NT - 1];
+                dmma_m8n8k4(a1[0], a1[1], pp.x, kd[0][st]);
+                dmma_m8n8k4(b1[0], b1[1], bb.x, kt[0][st]);
+                dmma_m8n8k4(a2[0], a2[1], pp.y, kd[0][2 + st]);
+                dmma_m8n8k4(b2[0], b2[1], bb.y, kt[0][2 + st]);
+                dmma_m8n8k4(a3[0], a3[1], pp.x + pp.y, kd[NT - 1][st]);
+                dmma_m8n8k4(b3[0], b3[1], bb.x + bb.y, kt[NT - 1][st]);
             }
+            da[0] = cmake(a1[0] - a2[0], a3[0] - a1[0] - a2[0]);
+            da[NT - 1] = cmake(a1[1] - a2[1], a3[1] - a1[1] - a2[1]);
+            db[0] = cmake(b1[0] - b2[0], b3[0] - b1[0] - b2[0]);
+            db[NT - 1] = cmake(b1[1] - b2[1], b3[1] - b1[1] - b2[1]);
+        } else {
+#pragma unroll
+            for (int u = 0; u < NT; ++u)
+#pragma unroll
+                for (int t = 0; t < NT; ++t) {
+                    dmma_m8n8k4(da[t].x, da[t].y, p[u].x, kd[t][2 * u]);
+                    dmma_m8n8k4(db[t].x, db[t].y, be[u].x, kt[t][2 * u]);
+                    dmma_m8n8k4(da[t].x, da[t].y, p[u].y, kd[t][2 * u + 1]);
+                    dmma_m8n8k4(db[t].x, db[t].y, be[u].y, kt[t][2 * u + 1]);
+                }
+        }
         if (has_w) __syncwarp();  // the W' operands (other lanes' elements) are read before anybody overwrites them
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
@@ -532,8 +604,13 @@ __device__ __forceinline__ void block_dmma_backward(cplx* sa, cplx* sb, const Op
             // lane (rho, jj) holds P[(rho, a)][(2jj + e, b)] in pacc[a][b][e]:
             // W'[rho][gamma] = (P[re][re] - P[im][im]) + i (P[re][im] + P[im][re])
             const int wi = T->widx[lane];
-            wslot[wi & 255] = cmake(pacc[0][0][0] - pacc[NT - 1][NT - 1][0], pacc[0][NT - 1][0] + pacc[NT - 1][0][0]);
-            wslot[(wi >> 8) & 255] = cmake(pacc[0][0][1] - pacc[NT - 1][NT - 1][1], pacc[0][NT - 1][1] + pacc[NT - 1][0][1]);
+            if (M3) {  // W' = (T1 - T2) + i (T3 - T1 - T2)
+                wslot[wi & 255] = cmake(pacc[0][0][0] - pacc[NT - 1][NT - 1][0], pacc[0][NT - 1][0] - pacc[0][0][0] - pacc[NT - 1][NT - 1][0]);
+                wslot[(wi >> 8) & 255] = cmake(pacc[0][0][1] - pacc[NT - 1][NT - 1][1], pacc[0][NT - 1][1] - pacc[0][0][1] - pacc[NT - 1][NT - 1][1]);
+            } else {
+                wslot[wi & 255] = cmake(pacc[0][0][0] - pacc[NT - 1][NT - 1][0], pacc[0][NT - 1][0] + pacc[NT - 1][0][0]);
+                wslot[(wi >> 8) & 255] = cmake(pacc[0][0][1] - pacc[NT - 1][NT - 1][1], pacc[0][NT - 1][1] + pacc[NT - 1][0][1]);
+            }
         } else {
             // lane (m, kk) holds P[m][2kk], P[m][2kk+1]; rows 2r (even m) and 2r+1 (odd m) combine to
             // W'[r][c] = (P[2r][2c] - P[2r+1][2c+1]) + i (P[2r][2c+1] + P[2r+1][2c]),  r = m/2, c = kk

@@ -933,7 +933,8 @@ int run_exec_resident(sqgpu_ctx* c, int batch, bool grad, const cplx* d_omega, d
 
 // FP64 flops the fused executor ISSUES for one launch over `ysets` parameter sets (a model of its instruction stream, to be
 // checked against ncu's sm__ops_path_tensor_src_fp64): a DMMA m8n8k4 is 512 flops; per batch of 8 (group, column) items a
-// 3-qubit block issues 8 DMMA forward and 16 (+ 8 for W') backward, a 2-qubit block 2 and 4 (+ 2); the scalar paths issue
+// 3-qubit block issues 6 DMMA forward and 12 (+ 6 for W') backward in the 3M formulation (8 and 16 (+ 8) in the real
+// embedding, SQ_BLOCK_3M = 0), a 2-qubit block 2 and 4 (+ 2); the scalar paths issue
 // 4 complex multiply-adds (32 flops) per row pair forward and 8 (+ 4 for W) backward; raw dense 2^k kernels (2^k/4)^2 * 2
 // DMMA per batch (3-5 qubits) forward.
 void exec_flops(const Plan& P, int rows, int cols, int log_ct, bool grad, int ysets, double* tensor, double* scalar) {
@@ -949,7 +950,15 @@ void exec_flops(const Plan& P, int rows, int cols, int log_ct, bool grad, int ys
         const double items = (double)(rows >> op.nq) * colsd;
         const bool dmma_block = op.ctrl_mask == 0 && (op.dim == 4 || op.dim == 8) && ((((rows >> op.nq) << log_ct) & 7) == 0);
         if (dmma_block) {
-            const double per8 = op.dim == 8 ? (8.0 + (grad ? 16.0 + (has_w ? 8.0 : 0.0) : 0.0)) : (2.0 + (grad ? 4.0 + (has_w ? 2.0 : 0.0) : 0.0));
+            double per8;  // DMMA per batch of 8 items
+            if (op.dim == 8 && SQ_BLOCK_3M) {
+                // three real products per complex product: 6 DMMA forward, 12 (+ 6 for W') backward, and per lane and batch
+                // 8 DADD forward, 16 (+ 4) backward for the sums and differences
+                per8 = 6.0 + (grad ? 12.0 + (has_w ? 6.0 : 0.0) : 0.0);
+                sc += items / 8.0 * 32.0 * (8.0 + (grad ? 16.0 + (has_w ? 4.0 : 0.0) : 0.0));
+            } else {
+                per8 = op.dim == 8 ? (8.0 + (grad ? 16.0 + (has_w ? 8.0 : 0.0) : 0.0)) : (2.0 + (grad ? 4.0 + (has_w ? 2.0 : 0.0) : 0.0));
+            }
             t += items / 8.0 * per8 * 512.0;
         } else if (op.ctrl_mask == 0 && op.nq >= 3 && op.type == SQGPU_GENERAL && !grad) {
             const double nt = op.dim / 4.0;
