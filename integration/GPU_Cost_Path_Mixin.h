@@ -17,6 +17,7 @@
 // adds at .cpp:944 next to the __DFE__ / __GROQ__ ones.
 #pragma once
 #include <cstring>
+#include <functional>
 #include <memory>
 #include <vector>
 
@@ -85,6 +86,15 @@ public:
     long long gpu_evaluations() { return gpu ? gpu->evaluations() : 0; }
 
 protected:
+#ifdef __GPU__
+    // with gpu_hooks.patch applied (-D__GPU__) the reference's own non-virtual optimization_problem_batched forwards to the
+    // engine through this hook: AGENTS, COSINE and the parameter-shift descent then run their batches on the GPU unchanged
+    bool install_batched_hook() {
+        this->gpu_batched_hook = [this](std::vector<Matrix_real>& v) { return this->optimization_problem_batched_GPU(v); };
+        return true;
+    }
+    bool batched_hook_installed = install_batched_hook();
+#endif
     GPU_Cost_Path& engine() {
         if (!gpu) gpu.reset(new GPU_Cost_Path(1));
         return *gpu;
