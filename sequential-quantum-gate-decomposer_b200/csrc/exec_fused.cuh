@@ -81,6 +81,7 @@ struct ExecArgs {
                              // slice of w_part with fire-and-forget reductions: one thread owns each address, so the
                              // summation order stays fixed
     const cplx* omega;       // [y][3] weights of the three trace types in the functional whose gradient is taken
+    int w_direct;            // (not w_in_smem) 1: one slice of w_part per (parameter set, CTA, warp), written by that warp alone
     int dense_stage;         // complex elements of kernel staging for the generic dense path (0: none)
     int wmax;                // max dim*dim over parametric ops (complex), >= 4
 };
@@ -143,7 +144,7 @@ __device__ __forceinline__ void warp_reduce8(double* v, int lane) {
 
 // per-warp W partial (complex w[n]) -> swarp slot; n = 4 or 16
 template <int N>
-__device__ __forceinline__ void warp_store_w(const cplx* w, double* slot, int lane) {
+__device__ __forceinline__ void warp_store_w(const cplx* w, double* slot, int lane, bool direct = false) {
 #pragma unroll
     for (int part = 0; part < N / 4; ++part) {
         double v[8];
@@ -153,7 +154,11 @@ __device__ __forceinline__ void warp_store_w(const cplx* w, double* slot, int la
             v[2 * e + 1] = w[part * 4 + e].y;
         }
         warp_reduce8(v, lane);
-        if ((lane & 3) == 0) slot[part * 8 + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)] = v[0];
+        if ((lane & 3) == 0) {
+            double* dst = slot + part * 8 + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+            if (direct) atomicAdd(dst, v[0]);  // the warp's own slice of w_part (global): fire-and-forget reduction
+            else *dst = v[0];
+        }
     }
 }
 
@@ -316,6 +321,34 @@ static const int B0TAB = 64;  // batch bases precomputed per op (tiles with more
 #ifndef SQ_TAB_BULK
 #define SQ_TAB_BULK 0
 #endif
+// 1: the per-lane operands of the next DMMA block op (BlkPre) are loaded BEFORE the end-of-op barrier of the current one, which
+// needs the next op's table one barrier earlier (tables are waited for two ops ahead instead of one); 0 (default): after the
+// barrier, at the top of the op. Measured (profiles/r2_variants_exec.jsonl): the early load keeps ~50 more registers alive
+// across the barrier (spills at the 128-register cap) and loses 11 % on C3.
+#ifndef SQ_PRELOAD
+#define SQ_PRELOAD 0
+#endif
+// How the batches of a block op are dealt to the warps: 1 (default): contiguous runs (a run of exactly four comes with ONE
+// 128-bit load of its four bases); 0: round robin (round-1 behaviour, one table read per batch).
+#ifndef SQ_BATCH_CONTIG
+#define SQ_BATCH_CONTIG 1
+#endif
+// Experiment: the CTA that arrives second on an SM starts SQ_STAGGER nanoseconds late, so that the two resident CTAs do not
+// run their per-op phases (tensor loop / barrier + operand prologue) in lock-step.
+#ifndef SQ_STAGGER
+#define SQ_STAGGER 0
+#endif
+// Where a warp's W' partial of an op goes: 0: into the warp's shared-memory slot; after the end-of-op barrier the CTA folds the
+// slots and issues one reduction per element into ITS slice of w_part (round-1 scheme: half of the warps spend ~600 cycles per
+// op in that fold while the others are already in the next op -- the phase trace shows them finishing last every time);
+// 1: every warp owns a slice of w_part and adds its partial straight from the accumulator registers with fire-and-forget
+// reductions (RED.ADD.F64): no shared-memory slots, no fold, nothing of W' behind the barrier; each address still has exactly
+// one writer (bit-reproducible). Measured (profiles/r2_variants_exec.jsonl): 8x the reduction traffic and an L2 working set
+// of 196 MB instead of 25 MB cost more than the fold: C3 1 211 against 1 339 evals/s, batch-1 latency 2.7 against 1.7 ms.
+// 0 (default): the shared-memory slots, with the fold spread over ALL warps (see the fold below).
+#ifndef SQ_W_DIRECT
+#define SQ_W_DIRECT 0
+#endif
 
 struct OpTab {
     double frag[3][8][32];  // [mode: K, K^dagger, K^T][t * KS + s][lane]: kernel (B operand) fragments
@@ -438,45 +471,109 @@ __global__ void build_optabs(const DevOp* __restrict__ ops, int n_ops, const cpl
     }
 }
 
-// forward: x <- K x for every group of the tile. One warp handles 8 (group, column) items per step.
-template <int LOG_CT, int KQ>
-__device__ __forceinline__ void block_dmma_forward(cplx* sa, const OpTabS* T, int q0, int q1, int q2, int rows, int tid, int nthr) {
+// Per-lane operands of one DMMA block op, read from the op's table in shared memory: kernel fragments, load/store slots, the
+// W' operand slots and output positions and -- when the warp's share of the tile is exactly four batches -- the four batch
+// bases. The executor loads them for the NEXT op while it waits at the end-of-op barrier of the current one (blk_preload
+// below, called between the last store of the loop and the barrier): warps finish their loops at different times, so these
+// ~20 shared-memory loads and their latency overlap with the other warps' tensor work instead of following the barrier,
+// where all warps of the CTA would sit in them at the same time with the tensor pipe idle.
+struct BlkPre {
+    double kd[2][4];  // forward: fragments of K; backward: of K^dagger   (3M: [0][0..3] = C0 C1 D0 D1, [1][0..1] = S0 S1)
+    double kt[2][4];  // backward: fragments of K^T
+    int sl[2], slw[2], widx;
+    int b0v[4];
+    bool ok, have_b0;
+};
+
+template <int KQ, bool BWD>
+__device__ __forceinline__ void blk_preload(BlkPre& R, const OpTabS* T, int nitems, int lane, int warp, int nwarps) {
     constexpr int NT = (KQ == 3) ? 2 : 1, KS = 2 * NT;
     constexpr bool M3 = (KQ == 3) && (SQ_BLOCK_3M != 0);
-    const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
-    double kf[NT][KS];
-    int sl[NT];
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
-        sl[t] = T->slot[t][lane];
+        R.sl[t] = T->slot[t][lane];
 #pragma unroll
         for (int s = 0; s < KS; ++s)
-            if (!M3 || t * KS + s < 6) kf[t][s] = T->frag[0][t * KS + s][lane];  // 3M: kf[0][0..3] = C0 C1 D0 D1, kf[1][0..1] = S0 S1
+            if (!M3 || t * KS + s < 6) {
+                R.kd[t][s] = T->frag[0][t * KS + s][lane];
+                if (BWD) R.kt[t][s] = T->frag[1][t * KS + s][lane];
+            }
     }
-    const int nitems = (rows >> KQ) << LOG_CT;
-    const bool tab_b0 = (SQ_B0_MODE == 1) && nitems <= 8 * B0TAB;
+    if (BWD) {
+        R.slw[0] = T->slot[2][lane];
+        R.slw[1] = T->slot[3][lane];
+        if (KQ == 3) R.widx = T->widx[lane];
+    }
+    // batches are dealt to the warps in contiguous runs; a run of exactly four comes with one 128-bit load of its bases
+    R.have_b0 = (SQ_B0_MODE == 1) && (nitems >> 3) == 4 * nwarps && (nitems >> 3) <= B0TAB;
+    if (R.have_b0) {
+        if (SQ_BATCH_CONTIG) {
+            const int4 v = *reinterpret_cast<const int4*>(&T->b0[4 * warp]);
+            R.b0v[0] = v.x; R.b0v[1] = v.y; R.b0v[2] = v.z; R.b0v[3] = v.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) R.b0v[i] = T->b0[warp + i * nwarps];
+        }
+    }
+    R.ok = true;
+}
+
+// Called at the end of the executor's non-block branches: a preloaded BlkPre is never consumed there (the preload happens only
+// when the next op is a block), but the compiler cannot know that and would keep ~50 operand registers alive (spilled)
+// through those register-hungry paths. Overwriting them with constants ends their live ranges.
+__device__ __forceinline__ void blk_kill(BlkPre& R) {
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+#pragma unroll
+        for (int s = 0; s < 4; ++s) R.kd[t][s] = R.kt[t][s] = 0.0;
+    R.sl[0] = R.sl[1] = R.slw[0] = R.slw[1] = R.widx = 0;
+    R.b0v[0] = R.b0v[1] = R.b0v[2] = R.b0v[3] = 0;
+    R.ok = R.have_b0 = false;
+}
+
+// runs body(B0) for every batch of this warp: contiguous runs of ceil(nb / nwarps) batches per warp
+template <int LOG_CT, int KQ, typename BODY>
+__device__ __forceinline__ void blk_for_batches(const BlkPre& R, const OpTabS* T, int q0, int q1, int q2, int nitems, int warp,
+                                                int nwarps, BODY&& body) {
+    if (R.have_b0) {
+        // not unrolled: four copies of the body would hoist four batches' worth of addresses (register pressure)
+#pragma unroll 1
+        for (int i = 0; i < 4; ++i) body(i < 2 ? (i == 0 ? R.b0v[0] : R.b0v[1]) : (i == 2 ? R.b0v[2] : R.b0v[3]));
+        return;
+    }
+    const int nb = nitems >> 3, nbw = (nb + nwarps - 1) / nwarps;
+    const int i0 = SQ_BATCH_CONTIG ? warp * nbw : warp, i1 = SQ_BATCH_CONTIG ? min(nb, i0 + nbw) : nb, di = SQ_BATCH_CONTIG ? 1 : nwarps;
+    const bool tab_b0 = (SQ_B0_MODE == 1) && nb <= B0TAB;
     BlockGeom<LOG_CT, KQ> G;
     if (!tab_b0) G.init(q0, q1, q2);
-    int B0next = (SQ_B0_MODE == 2) ? G.batch_base(warp * 8) : 0;
-    for (int b0 = warp * 8; b0 < nitems; b0 += nwarps * 8) {
-        const int B0 = (SQ_B0_MODE == 2) ? B0next : (tab_b0 ? T->b0[b0 >> 3] : G.batch_base(b0));
-        if (SQ_B0_MODE == 2) B0next = G.batch_base(b0 + nwarps * 8);
+    for (int i = i0; i < i1; i += di) body(tab_b0 ? T->b0[i] : G.batch_base(8 * i));
+}
+
+// forward: x <- K x for every group of the tile. One warp handles 8 (group, column) items per step.
+template <int LOG_CT, int KQ>
+__device__ __forceinline__ void block_dmma_forward(cplx* sa, const OpTabS* T, BlkPre& R, int q0, int q1, int q2, int rows, int tid, int nthr) {
+    constexpr int NT = (KQ == 3) ? 2 : 1;
+    constexpr bool M3 = (KQ == 3) && (SQ_BLOCK_3M != 0);
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
+    const int nitems = (rows >> KQ) << LOG_CT;
+    if (!R.ok) blk_preload<KQ, false>(R, T, nitems, lane, warp, nwarps);
+    blk_for_batches<LOG_CT, KQ>(R, T, q0, q1, q2, nitems, warp, nwarps, [&](int B0) {
         cplx x[NT], d[NT];
 #pragma unroll
         for (int u = 0; u < NT; ++u) {
-            x[u] = sa[B0 ^ sl[u]];
+            x[u] = sa[B0 ^ R.sl[u]];
             d[u] = czero();
         }
         if (M3) {
             // t1 = C u, t2 = D v, t3 = (C + D)(u + v) over the two k-steps; the D fragment pair holds outputs o(2j), o(2j+1),
             // which are the amplitudes the lane loaded as x[0], x[1]
             double t1[2] = {0.0, 0.0}, t2[2] = {0.0, 0.0}, t3[2] = {0.0, 0.0};
-            dmma_m8n8k4(t1[0], t1[1], x[0].x, kf[0][0]);
-            dmma_m8n8k4(t2[0], t2[1], x[0].y, kf[0][2]);
-            dmma_m8n8k4(t3[0], t3[1], x[0].x + x[0].y, kf[NT - 1][0]);
-            dmma_m8n8k4(t1[0], t1[1], x[NT - 1].x, kf[0][1]);
-            dmma_m8n8k4(t2[0], t2[1], x[NT - 1].y, kf[0][3]);
-            dmma_m8n8k4(t3[0], t3[1], x[NT - 1].x + x[NT - 1].y, kf[NT - 1][1]);
+            dmma_m8n8k4(t1[0], t1[1], x[0].x, R.kd[0][0]);
+            dmma_m8n8k4(t2[0], t2[1], x[0].y, R.kd[0][2]);
+            dmma_m8n8k4(t3[0], t3[1], x[0].x + x[0].y, R.kd[NT - 1][0]);
+            dmma_m8n8k4(t1[0], t1[1], x[NT - 1].x, R.kd[0][1]);
+            dmma_m8n8k4(t2[0], t2[1], x[NT - 1].y, R.kd[0][3]);
+            dmma_m8n8k4(t3[0], t3[1], x[NT - 1].x + x[NT - 1].y, R.kd[NT - 1][1]);
             d[0] = cmake(t1[0] - t2[0], t3[0] - t1[0] - t2[0]);
             d[NT - 1] = cmake(t1[1] - t2[1], t3[1] - t1[1] - t2[1]);
         } else {
@@ -484,55 +581,37 @@ __device__ __forceinline__ void block_dmma_forward(cplx* sa, const OpTabS* T, in
             for (int u = 0; u < NT; ++u)
 #pragma unroll
                 for (int t = 0; t < NT; ++t) {
-                    dmma_m8n8k4(d[t].x, d[t].y, x[u].x, kf[t][2 * u]);
-                    dmma_m8n8k4(d[t].x, d[t].y, x[u].y, kf[t][2 * u + 1]);
+                    dmma_m8n8k4(d[t].x, d[t].y, x[u].x, R.kd[t][2 * u]);
+                    dmma_m8n8k4(d[t].x, d[t].y, x[u].y, R.kd[t][2 * u + 1]);
                 }
         }
 #pragma unroll
-        for (int t = 0; t < NT; ++t) sa[B0 ^ sl[t]] = d[t];
-    }
+        for (int t = 0; t < NT; ++t) sa[B0 ^ R.sl[t]] = d[t];
+    });
+    R.ok = false;
 }
 
 // backward step of the adjoint sweep: W' += beta p^T (outer product over items), a <- K^dagger p, beta <- K^T beta, all on
 // DMMA; the warp's W' (DIM x DIM complex) is written to wslot after the loop.
 template <int LOG_CT, int KQ>
-__device__ __forceinline__ void block_dmma_backward(cplx* sa, cplx* sb, const OpTabS* T, int q0, int q1, int q2, int rows,
-                                                    bool has_w, cplx* wslot, int tid, int nthr) {
-    constexpr int DIM = 1 << KQ, NT = (KQ == 3) ? 2 : 1, KS = 2 * NT;
+__device__ __forceinline__ void block_dmma_backward(cplx* sa, cplx* sb, const OpTabS* T, BlkPre& R, int q0, int q1, int q2, int rows,
+                                                    bool has_w, cplx* wslot, bool wdirect, int tid, int nthr) {
+    constexpr int DIM = 1 << KQ, NT = (KQ == 3) ? 2 : 1;
     constexpr bool M3 = (KQ == 3) && (SQ_BLOCK_3M != 0);
     const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
-    double kd[NT][KS], kt[NT][KS];
-    int sl[NT], slw[2];
-#pragma unroll
-    for (int t = 0; t < NT; ++t) {
-        sl[t] = T->slot[t][lane];
-#pragma unroll
-        for (int s = 0; s < KS; ++s)
-            if (!M3 || t * KS + s < 6) {  // 3M: [0][0..3] = C0 C1 D0 D1, [1][0..1] = S0 S1 of K^dagger / K^T
-                kd[t][s] = T->frag[0][t * KS + s][lane];  // K^dagger
-                kt[t][s] = T->frag[1][t * KS + s][lane];  // K^T
-            }
-    }
-    slw[0] = T->slot[2][lane];
-    slw[1] = T->slot[3][lane];
+    const int nitems = (rows >> KQ) << LOG_CT;
+    if (!R.ok) blk_preload<KQ, true>(R, T, nitems, lane, warp, nwarps);
     double pacc[NT][NT][2];
 #pragma unroll
     for (int a = 0; a < NT; ++a)
 #pragma unroll
         for (int b = 0; b < NT; ++b) pacc[a][b][0] = pacc[a][b][1] = 0.0;
-    const int nitems = (rows >> KQ) << LOG_CT;
-    const bool tab_b0 = (SQ_B0_MODE == 1) && nitems <= 8 * B0TAB;
-    BlockGeom<LOG_CT, KQ> G;
-    if (!tab_b0) G.init(q0, q1, q2);
-    int B0next = (SQ_B0_MODE == 2) ? G.batch_base(warp * 8) : 0;
-    for (int b0 = warp * 8; b0 < nitems; b0 += nwarps * 8) {
-        const int B0 = (SQ_B0_MODE == 2) ? B0next : (tab_b0 ? T->b0[b0 >> 3] : G.batch_base(b0));
-        if (SQ_B0_MODE == 2) B0next = G.batch_base(b0 + nwarps * 8);
+    blk_for_batches<LOG_CT, KQ>(R, T, q0, q1, q2, nitems, warp, nwarps, [&](int B0) {
         cplx p[NT], be[NT], da[NT], db[NT];
 #pragma unroll
         for (int u = 0; u < NT; ++u) {
-            p[u] = sa[B0 ^ sl[u]];
-            be[u] = sb[B0 ^ sl[u]];
+            p[u] = sa[B0 ^ R.sl[u]];
+            be[u] = sb[B0 ^ R.sl[u]];
             da[u] = czero();
             db[u] = czero();
         }
@@ -542,7 +621,7 @@ __device__ __forceinline__ void block_dmma_backward(cplx* sa, cplx* sb, const Op
                 // (pacc[0][0] = T1, pacc[NT-1][NT-1] = T2, pacc[0][NT-1] = T3)
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    const cplx bw = sb[B0 ^ slw[h]], pw = sa[B0 ^ slw[h]];
+                    const cplx bw = sb[B0 ^ R.slw[h]], pw = sa[B0 ^ R.slw[h]];
                     dmma_m8n8k4(pacc[0][0][0], pacc[0][0][1], bw.x, pw.x);
                     dmma_m8n8k4(pacc[NT - 1][NT - 1][0], pacc[NT - 1][NT - 1][1], bw.y, pw.y);
                     dmma_m8n8k4(pacc[0][NT - 1][0], pacc[0][NT - 1][1], bw.x + bw.y, pw.x + pw.y);
@@ -552,7 +631,7 @@ __device__ __forceinline__ void block_dmma_backward(cplx* sa, cplx* sb, const Op
                 // (B operand, columns = rho)
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    const cplx bw = sb[B0 ^ slw[h]], pw = sa[B0 ^ slw[h]];
+                    const cplx bw = sb[B0 ^ R.slw[h]], pw = sa[B0 ^ R.slw[h]];
                     dmma_m8n8k4(pacc[0][0][0], pacc[0][0][1], bw.x, pw.x);
                     dmma_m8n8k4(pacc[0][NT - 1][0], pacc[0][NT - 1][1], bw.x, pw.y);
                     dmma_m8n8k4(pacc[NT - 1][0][0], pacc[NT - 1][0][1], bw.y, pw.x);
@@ -562,7 +641,7 @@ __device__ __forceinline__ void block_dmma_backward(cplx* sa, cplx* sb, const Op
                 const double* sad = reinterpret_cast<const double*>(sa);
                 const double* sbd = reinterpret_cast<const double*>(sb);
 #pragma unroll
-                for (int h = 0; h < 2; ++h) dmma_m8n8k4(pacc[0][0][0], pacc[0][0][1], sbd[(2 * B0) ^ slw[h]], sad[(2 * B0) ^ slw[h]]);
+                for (int h = 0; h < 2; ++h) dmma_m8n8k4(pacc[0][0][0], pacc[0][0][1], sbd[(2 * B0) ^ R.slw[h]], sad[(2 * B0) ^ R.slw[h]]);
             }
         }
         if (M3) {
@@ -570,12 +649,12 @@ __device__ __forceinline__ void block_dmma_backward(cplx* sa, cplx* sb, const Op
 #pragma unroll
             for (int st = 0; st < 2; ++st) {
                 const cplx pp = p[st == 0 ? 0 : NT - 1], bb = be[st == 0 ? 0 : NT - 1];
-                dmma_m8n8k4(a1[0], a1[1], pp.x, kd[0][st]);
-                dmma_m8n8k4(b1[0], b1[1], bb.x, kt[0][st]);
-                dmma_m8n8k4(a2[0], a2[1], pp.y, kd[0][2 + st]);
-                dmma_m8n8k4(b2[0], b2[1], bb.y, kt[0][2 + st]);
-                dmma_m8n8k4(a3[0], a3[1], pp.x + pp.y, kd[NT - 1][st]);
-                dmma_m8n8k4(b3[0], b3[1], bb.x + bb.y, kt[NT - 1][st]);
+                dmma_m8n8k4(a1[0], a1[1], pp.x, R.kd[0][st]);
+                dmma_m8n8k4(b1[0], b1[1], bb.x, R.kt[0][st]);
+                dmma_m8n8k4(a2[0], a2[1], pp.y, R.kd[0][2 + st]);
+                dmma_m8n8k4(b2[0], b2[1], bb.y, R.kt[0][2 + st]);
+                dmma_m8n8k4(a3[0], a3[1], pp.x + pp.y, R.kd[NT - 1][st]);
+                dmma_m8n8k4(b3[0], b3[1], bb.x + bb.y, R.kt[NT - 1][st]);
             }
             da[0] = cmake(a1[0] - a2[0], a3[0] - a1[0] - a2[0]);
             da[NT - 1] = cmake(a1[1] - a2[1], a3[1] - a1[1] - a2[1]);
@@ -586,30 +665,41 @@ __device__ __forceinline__ void block_dmma_backward(cplx* sa, cplx* sb, const Op
             for (int u = 0; u < NT; ++u)
 #pragma unroll
                 for (int t = 0; t < NT; ++t) {
-                    dmma_m8n8k4(da[t].x, da[t].y, p[u].x, kd[t][2 * u]);
-                    dmma_m8n8k4(db[t].x, db[t].y, be[u].x, kt[t][2 * u]);
-                    dmma_m8n8k4(da[t].x, da[t].y, p[u].y, kd[t][2 * u + 1]);
-                    dmma_m8n8k4(db[t].x, db[t].y, be[u].y, kt[t][2 * u + 1]);
+                    dmma_m8n8k4(da[t].x, da[t].y, p[u].x, R.kd[t][2 * u]);
+                    dmma_m8n8k4(db[t].x, db[t].y, be[u].x, R.kt[t][2 * u]);
+                    dmma_m8n8k4(da[t].x, da[t].y, p[u].y, R.kd[t][2 * u + 1]);
+                    dmma_m8n8k4(db[t].x, db[t].y, be[u].y, R.kt[t][2 * u + 1]);
                 }
         }
         if (has_w) __syncwarp();  // the W' operands (other lanes' elements) are read before anybody overwrites them
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
-            sa[B0 ^ sl[t]] = da[t];
-            sb[B0 ^ sl[t]] = db[t];
+            sa[B0 ^ R.sl[t]] = da[t];
+            sb[B0 ^ R.sl[t]] = db[t];
         }
-    }
+    });
     if (has_w) {
         if (KQ == 3) {
             // lane (rho, jj) holds P[(rho, a)][(2jj + e, b)] in pacc[a][b][e]:
             // W'[rho][gamma] = (P[re][re] - P[im][im]) + i (P[re][im] + P[im][re])
-            const int wi = T->widx[lane];
+            const int wi = R.widx;
+            cplx w0, w1;
             if (M3) {  // W' = (T1 - T2) + i (T3 - T1 - T2)
-                wslot[wi & 255] = cmake(pacc[0][0][0] - pacc[NT - 1][NT - 1][0], pacc[0][NT - 1][0] - pacc[0][0][0] - pacc[NT - 1][NT - 1][0]);
-                wslot[(wi >> 8) & 255] = cmake(pacc[0][0][1] - pacc[NT - 1][NT - 1][1], pacc[0][NT - 1][1] - pacc[0][0][1] - pacc[NT - 1][NT - 1][1]);
+                w0 = cmake(pacc[0][0][0] - pacc[NT - 1][NT - 1][0], pacc[0][NT - 1][0] - pacc[0][0][0] - pacc[NT - 1][NT - 1][0]);
+                w1 = cmake(pacc[0][0][1] - pacc[NT - 1][NT - 1][1], pacc[0][NT - 1][1] - pacc[0][0][1] - pacc[NT - 1][NT - 1][1]);
             } else {
-                wslot[wi & 255] = cmake(pacc[0][0][0] - pacc[NT - 1][NT - 1][0], pacc[0][NT - 1][0] + pacc[NT - 1][0][0]);
-                wslot[(wi >> 8) & 255] = cmake(pacc[0][0][1] - pacc[NT - 1][NT - 1][1], pacc[0][NT - 1][1] + pacc[NT - 1][0][1]);
+                w0 = cmake(pacc[0][0][0] - pacc[NT - 1][NT - 1][0], pacc[0][NT - 1][0] + pacc[NT - 1][0][0]);
+                w1 = cmake(pacc[0][0][1] - pacc[NT - 1][NT - 1][1], pacc[0][NT - 1][1] + pacc[NT - 1][0][1]);
+            }
+            if (wdirect) {
+                double* wd = reinterpret_cast<double*>(wslot);
+                atomicAdd(wd + 2 * (wi & 255), w0.x);
+                atomicAdd(wd + 2 * (wi & 255) + 1, w0.y);
+                atomicAdd(wd + 2 * ((wi >> 8) & 255), w1.x);
+                atomicAdd(wd + 2 * ((wi >> 8) & 255) + 1, w1.y);
+            } else {
+                wslot[wi & 255] = w0;
+                wslot[(wi >> 8) & 255] = w1;
             }
         } else {
             // lane (m, kk) holds P[m][2kk], P[m][2kk+1]; rows 2r (even m) and 2r+1 (odd m) combine to
@@ -617,9 +707,18 @@ __device__ __forceinline__ void block_dmma_backward(cplx* sa, cplx* sb, const Op
             const int m = lane >> 2, kk = lane & 3;
             const double o0 = __shfl_xor_sync(0xffffffffu, pacc[0][0][0], 4);
             const double o1 = __shfl_xor_sync(0xffffffffu, pacc[0][0][1], 4);
-            if ((m & 1) == 0) wslot[(m >> 1) * DIM + kk] = cmake(pacc[0][0][0] - o1, pacc[0][0][1] + o0);
+            if ((m & 1) == 0) {
+                if (wdirect) {
+                    double* wd = reinterpret_cast<double*>(wslot + (m >> 1) * DIM + kk);
+                    atomicAdd(wd, pacc[0][0][0] - o1);
+                    atomicAdd(wd + 1, pacc[0][0][1] + o0);
+                } else {
+                    wslot[(m >> 1) * DIM + kk] = cmake(pacc[0][0][0] - o1, pacc[0][0][1] + o0);
+                }
+            }
         }
     }
+    R.ok = false;
 }
 
 // Raw dense 3-/4-qubit kernels (GENERAL blocks; no controls) in the same formulation as the fused blocks: data = A operand,
@@ -808,8 +907,27 @@ struct SOp {
     int32_t pool_lo, pool_hi;
 };
 
-static const int KM_ELEMS = 64;  // prefetched block kernel: up to 8 x 8 complex
 static const int TAB_RING = 4;   // shared-memory ring of op tables: the table of op k + TAB_RING - 1 is requested when op k starts
+
+#if SQ_STAGGER
+__device__ int g_sm_arrivals[256];
+#endif
+// Profiling build (-DSQ_TRACE=events): the first two CTAs that land on SM 0 record, per op and warp, the SM clock at the start
+// and at the end of the op's work loop (profiles/trace_phases.py reads them through sqgpu_debug_trace and computes how much
+// the two CTAs' tensor phases overlap).
+#ifndef SQ_TRACE
+#define SQ_TRACE 0
+#endif
+#if SQ_TRACE
+__device__ long long g_trace[2][SQ_TRACE][16][2];
+__device__ int g_trace_arrivals;
+#define SQ_TRACE_MARK(which)                                                                          \
+    if (trace_slot >= 0 && trace_ev < SQ_TRACE && lane == 0 && warp < 16) g_trace[trace_slot][trace_ev][warp][which] = clock64();
+#define SQ_TRACE_NEXT() ++trace_ev;
+#else
+#define SQ_TRACE_MARK(which)
+#define SQ_TRACE_NEXT()
+#endif
 
 template <int MODE, int LOG_CT>
 __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A) {
@@ -827,17 +945,48 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
     constexpr bool WIN = (MODE == MODE_APPLY || MODE == MODE_BWD);  // window mode is compiled only where it is used
     cplx* sb = sa + (size_t)rows * CT;                                   // the row functional beta (HAS_B only)
     cplx* sk = HAS_B ? sb + (size_t)rows * CT : sb;                       // raw dense kernel staging
-    cplx* skm = sk + A.dense_stage;                                       // [2][KM_ELEMS] prefetched block kernels
-    OpTabS* stab = reinterpret_cast<OpTabS*>(skm + 2 * KM_ELEMS);         // [TAB_RING] DMMA block lookup tables (one sweep direction)
+    OpTabS* stab = reinterpret_cast<OpTabS*>(sk + A.dense_stage);         // [TAB_RING] DMMA block lookup tables (one sweep direction);
+                                                                          // the 2 x 2 kernel of a single-qubit block travels in the same ring
     unsigned long long* tbar = reinterpret_cast<unsigned long long*>(stab + TAB_RING);  // [TAB_RING] mbarriers of the table ring
-    cplx* swarp = reinterpret_cast<cplx*>(tbar + TAB_RING);               // [2][nwarps][wmax]
-    cplx* swacc = swarp + (HAS_B ? 2 * nwarps * A.wmax : 0);              // [w_total] if w_in_smem
+    const bool wdirect = HAS_B && SQ_W_DIRECT && A.w_direct;              // W' partials go from the registers to the warp's own global slice
+    cplx* swarp = reinterpret_cast<cplx*>(tbar + TAB_RING);               // [2][nwarps][wmax] (not with wdirect)
+    cplx* swacc = swarp + ((HAS_B && !wdirect) ? 2 * nwarps * A.wmax : 0);  // [w_total] if w_in_smem
     double* sred = reinterpret_cast<double*>(swacc + ((HAS_B && A.w_in_smem) ? A.w_total : 0));  // [nwarps][6]
-    SOp* sops = reinterpret_cast<SOp*>(sred + nwarps * 6);               // [n_ops]
+    double* stsum = sred + nwarps * 6;                                   // [6] running trace sums of this CTA over its tiles
+    SOp* sops = reinterpret_cast<SOp*>(stsum + 6);                       // [n_ops]
     int* srowpart = reinterpret_cast<int*>(sops + A.n_ops);              // window mode: [rows] deposit(r, wmask)
 
     const int chunk = blockIdx.x;
     const int nchunks = gridDim.x;
+#if SQ_TRACE
+    int trace_slot = -1, trace_ev = 0;
+    {
+        __shared__ int s_trace_slot;
+        if (tid == 0) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            s_trace_slot = -1;
+            if (smid == 0 && (MODE == MODE_GRAD || MODE == MODE_BWD)) {
+                const int a = atomicAdd(&g_trace_arrivals, 1);
+                if (a < 2) s_trace_slot = a;
+            }
+        }
+        __syncthreads();
+        trace_slot = s_trace_slot;
+    }
+#endif
+#if SQ_STAGGER
+    if (MODE == MODE_GRAD || MODE == MODE_BWD || MODE == MODE_COST) {
+        __shared__ int s_arrival;
+        if (tid == 0) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            s_arrival = atomicAdd(&g_sm_arrivals[smid & 255], 1);
+        }
+        __syncthreads();
+        if (s_arrival & 1) __nanosleep(SQ_STAGGER);
+    }
+#endif
     const int deriv_op = (MODE == MODE_APPLY && A.deriv_op) ? A.deriv_op[y] : -1;
     const int deriv_slot = (MODE == MODE_APPLY && A.deriv_slot) ? A.deriv_slot[y] : 0;
 
@@ -866,15 +1015,13 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
     if (WIN && A.wmask) {
         for (int r = tid; r < rows; r += nthr) srowpart[r] = (int)deposit_bits((unsigned)r, A.wmask);
     }
-    double tsum[6] = {0, 0, 0, 0, 0, 0};  // running trace sums of this CTA (thread 0)
+    if (tid < 6) stsum[tid] = 0.0;
     __syncthreads();
 
-    // kernel element this thread prefetches for op k (threads 0..63)
-    auto kernel_elem = [&](int k) -> cplx {
+    // the 2 x 2 kernel of single-qubit block k (kind 0): 64 bytes that take the place of the table in the op's ring slot
+    auto kernel_of = [&](int k) -> const cplx* {
         const SOp s = sops[k];
-        if (s.kind != 0 || tid >= s.dim * s.dim) return czero();  // only the scalar 2 x 2 path reads the staged kernel
-        const cplx* K = s.kern_off >= 0 ? ktab + s.kern_off : A.pool + (((long long)s.pool_hi << 32) | (unsigned)s.pool_lo);
-        return K[tid];
+        return s.kern_off >= 0 ? ktab + s.kern_off : A.pool + (((long long)s.pool_hi << 32) | (unsigned)s.pool_lo);
     };
 
     // DMMA block table of op k: built per (parameter set, op) by build_optabs. ONE thread requests it with two bulk-async
@@ -891,11 +1038,18 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
     }
     unsigned tab_parity = 0;  // bit s: phase parity the next wait on ring slot s expects (identical in every thread)
     auto tab_prefetch = [&](int k, bool bwd) {
-        if (tid != 0 || k < 0 || k >= A.n_ops || sops[k].kind != 2) return;
+        if (tid != 0 || k < 0 || k >= A.n_ops || sops[k].kind == 1) return;
         const char* src = reinterpret_cast<const char*>(gtabs + k);
         const int slot = k & (TAB_RING - 1);
         const unsigned dst = (unsigned)__cvta_generic_to_shared(stab + slot);
         const unsigned bar = (unsigned)__cvta_generic_to_shared(tbar + slot);
+        if (sops[k].kind == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(64) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                         "l"(kernel_of(k)), "r"(64), "r"(bar)
+                         : "memory");
+            return;
+        }
         constexpr int FRAG = 8 * 32 * 8, TAIL = (int)(sizeof(OpTabS) - 2 * FRAG);  // bytes of one fragment set / of slots + widx + b0
         const int nfrag = bwd ? 2 * FRAG : FRAG, src_off = bwd ? FRAG : 0;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(nfrag + TAIL) : "memory");
@@ -907,7 +1061,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                      : "memory");
     };
     auto tab_acquire = [&](int k) {  // the table of op k (if it has one) has landed in its ring slot
-        if (k < 0 || k >= A.n_ops || sops[k].kind != 2) return;
+        if (k < 0 || k >= A.n_ops || sops[k].kind == 1) return;
         const int slot = k & (TAB_RING - 1);
         const unsigned bar = (unsigned)__cvta_generic_to_shared(tbar + slot);
         const unsigned parity = (tab_parity >> slot) & 1u;
@@ -920,7 +1074,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
     };
     // the wait for the NEXT op's table sits in front of the end-of-op barrier, where its latency overlaps the wait for the
     // slowest warp (the table was requested TAB_RING - 1 ops ago and has long landed)
-    auto tab_end_of_op = [&](int next_k) { tab_acquire(next_k); };
+    auto tab_ready = [&](int next_k) { tab_acquire(next_k); };  // before the next op's operands are read (any thread, no barrier needed)
+    auto tab_end_of_op = [&]() {};
     auto tab_prime = [&](int first, int step, bool bwd) {  // requests for the first TAB_RING - 1 ops of a sweep
 #pragma unroll
         for (int j = 0; j < TAB_RING - 1; ++j) tab_prefetch(first + j * step, bwd);
@@ -928,11 +1083,18 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
     };
 #else
     // per-thread cp.async (LDGSTS) copies, one commit group per op in sweep order (empty for ops without a table): when an op
-    // ends, "at most TAB_RING - 2 groups pending" means the NEXT op's table has landed; the end-of-op barrier publishes it
+    // ends, "at most TAB_RING - 2 groups pending" means the NEXT op's table has landed; the end-of-op barrier publishes it.
+    // With SQ_PRELOAD the operands of the next op are read BEFORE that barrier, so tables are waited for one op earlier
+    // ("at most TAB_RING - 3 pending": the table of the op after the next has landed) and every table is published by the
+    // barrier one op before its first reader.
     auto tab_prefetch_raw = [&](int k, bool bwd) {
-        if (k < 0 || k >= A.n_ops || sops[k].kind != 2) return;
+        if (k < 0 || k >= A.n_ops || sops[k].kind == 1) return;
         const char* src = reinterpret_cast<const char*>(gtabs + k);
         const unsigned dst = (unsigned)__cvta_generic_to_shared(stab + (k & (TAB_RING - 1)));
+        if (sops[k].kind == 0) {
+            if (tid < 4) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * tid), "l"(kernel_of(k) + tid));
+            return;
+        }
         constexpr int FRAG = 8 * 32 * 8, TAIL = (int)(sizeof(OpTabS) - 2 * FRAG);
         const int nfrag = bwd ? 2 * FRAG : FRAG, src_off = bwd ? FRAG : 0;
         for (int e = tid; e < (nfrag + TAIL) / 16; e += nthr) {
@@ -946,11 +1108,12 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
         tab_prefetch_raw(k, bwd);
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    auto tab_end_of_op = [&](int) { asm volatile("cp.async.wait_group %0;" ::"n"(TAB_RING - 2) : "memory"); };
+    auto tab_ready = [&](int) {};
+    auto tab_end_of_op = [&]() { asm volatile("cp.async.wait_group %0;" ::"n"(TAB_RING - 2 - (SQ_PRELOAD ? 1 : 0)) : "memory"); };
     auto tab_prime = [&](int first, int step, bool bwd) {
 #pragma unroll
         for (int j = 0; j < TAB_RING - 1; ++j) tab_prefetch(first + j * step, bwd);
-        tab_end_of_op(first);
+        tab_end_of_op();
     };
 #endif
 
@@ -999,22 +1162,22 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                 }
             }
             const int first_op = (MODE == MODE_BWD) ? A.n_ops - 1 : 0;
-            if (A.n_ops > 0 && tid < KM_ELEMS) skm[(first_op & 1) * KM_ELEMS + tid] = kernel_elem(first_op);
             if (A.n_ops > 0) tab_prime(first_op, MODE == MODE_BWD ? -1 : 1, MODE == MODE_BWD);
         }
         __syncthreads();
 
         // ---- forward sweep: op 0 first (Gates_block.cpp:683) ---------------------------------------------------
+        BlkPre R;  // operands of the next DMMA block op, loaded ahead of the barrier (SQ_PRELOAD)
+        R.ok = false;
         for (int k = 0; k < (MODE == MODE_BWD ? 0 : A.n_ops); ++k) {
             const SOp s = sops[k];
-            cplx next_elem = czero();
             const bool have_next = k + 1 < A.n_ops;
-            if (have_next && tid < KM_ELEMS) next_elem = kernel_elem(k + 1);
             tab_prefetch(k + TAB_RING - 1, false);
-            const cplx* __restrict__ km = skm + (k & 1) * KM_ELEMS;
+            const cplx* __restrict__ km = reinterpret_cast<const cplx*>(stab + (k & (TAB_RING - 1)));
+            SQ_TRACE_MARK(0)
             if (s.kind == 2) {
-                if (s.dim == 8) block_dmma_forward<LOG_CT, 3>(sa, stab + (k & (TAB_RING - 1)), s.q0, s.q1, s.q2, rows, tid, nthr);
-                else block_dmma_forward<LOG_CT, 2>(sa, stab + (k & (TAB_RING - 1)), s.q0, s.q1, 30, rows, tid, nthr);
+                if (s.dim == 8) block_dmma_forward<LOG_CT, 3>(sa, stab + (k & (TAB_RING - 1)), R, s.q0, s.q1, s.q2, rows, tid, nthr);
+                else block_dmma_forward<LOG_CT, 2>(sa, stab + (k & (TAB_RING - 1)), R, s.q0, s.q1, 30, rows, tid, nthr);
             } else if (s.kind == 0) {
                 const cplx k00 = km[0], k01 = km[1], k10 = km[2], k11 = km[3];
                 const int tbit = 1 << s.q0;
@@ -1129,8 +1292,15 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                     }
                 }
             }
-            if (have_next && tid < KM_ELEMS) skm[((k + 1) & 1) * KM_ELEMS + tid] = next_elem;
-            tab_end_of_op(k + 1);
+            SQ_TRACE_MARK(1)
+            SQ_TRACE_NEXT()
+            if (SQ_PRELOAD && s.kind != 2) blk_kill(R);
+            tab_ready(k + 1);
+            if (SQ_PRELOAD && have_next) {
+                const SOp sn = sops[k + 1];
+                if (sn.kind == 2 && sn.dim == 8) blk_preload<3, false>(R, stab + ((k + 1) & (TAB_RING - 1)), (rows >> 3) << LOG_CT, lane, warp, nwarps);
+            }
+            tab_end_of_op();
             __syncthreads();
         }
 
@@ -1202,7 +1372,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                 for (int i = 0; i < nt; ++i) {
                     double sum = 0;
                     for (int w = 0; w < nwarps; ++w) sum += sred[w * 6 + i];
-                    tsum[i] += sum;
+                    stsum[i] += sum;
                 }
             }
         }
@@ -1211,7 +1381,6 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
           if (MODE == MODE_GRAD) {
             // ---- beta_N = sum_t omega_t * sum_{masks of type t} e_{(j+off)^mask} per column ---------------------
             for (int e = tid; e < rows * CT; e += nthr) sb[e] = czero();
-            if (A.n_ops > 0 && tid < KM_ELEMS) skm[((A.n_ops - 1) & 1) * KM_ELEMS + tid] = kernel_elem(A.n_ops - 1);
             if (A.n_ops > 0) tab_prime(A.n_ops - 1, -1, true);
             __syncthreads();
             if (A.sum_sq) {
@@ -1253,18 +1422,18 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
             int buf = 0;
             for (int k = A.n_ops - 1; k >= 0; --k) {
                 const SOp s = sops[k];
-                cplx next_elem = czero();
                 const bool have_next = k > 0;
-                if (have_next && tid < KM_ELEMS) next_elem = kernel_elem(k - 1);
                 tab_prefetch(k - (TAB_RING - 1), true);
                 const bool has_w = s.w_off >= 0;
-                cplx* wslot_c = swarp + (size_t)(buf * nwarps + warp) * A.wmax;
+                cplx* wslot_c = wdirect ? A.w_part + (((size_t)y * nchunks + chunk) * nwarps + warp) * A.w_total + max(s.w_off, 0)
+                                        : swarp + (size_t)(buf * nwarps + warp) * A.wmax;
                 double* wslot = reinterpret_cast<double*>(wslot_c);
-                const cplx* __restrict__ km = skm + (k & 1) * KM_ELEMS;
+                const cplx* __restrict__ km = reinterpret_cast<const cplx*>(stab + (k & (TAB_RING - 1)));
                 int wdim = s.dim;
+                SQ_TRACE_MARK(0)
                 if (s.kind == 2) {
-                    if (s.dim == 8) block_dmma_backward<LOG_CT, 3>(sa, sb, stab + (k & (TAB_RING - 1)), s.q0, s.q1, s.q2, rows, has_w, wslot_c, tid, nthr);
-                    else block_dmma_backward<LOG_CT, 2>(sa, sb, stab + (k & (TAB_RING - 1)), s.q0, s.q1, 30, rows, has_w, wslot_c, tid, nthr);
+                    if (s.dim == 8) block_dmma_backward<LOG_CT, 3>(sa, sb, stab + (k & (TAB_RING - 1)), R, s.q0, s.q1, s.q2, rows, has_w, wslot_c, wdirect, tid, nthr);
+                    else block_dmma_backward<LOG_CT, 2>(sa, sb, stab + (k & (TAB_RING - 1)), R, s.q0, s.q1, 30, rows, has_w, wslot_c, wdirect, tid, nthr);
                 } else if (s.kind == 0) {
                     const cplx k00 = km[0], k01 = km[1], k10 = km[2], k11 = km[3];
                     const int tbit = 1 << s.q0;
@@ -1286,7 +1455,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                         sb[e0] = cfma(k10, b1, cmul(k00, b0));
                         sb[e1] = cfma(k11, b1, cmul(k01, b0));
                     }
-                    if (has_w) warp_store_w<4>(W, wslot, lane);
+                    if (has_w) warp_store_w<4>(W, wslot, lane, wdirect);
                 } else {
                     const DevOp& op = A.ops[k];
                     const cplx* __restrict__ K = op.kern_off >= 0 ? ktab + op.kern_off : A.pool + op.pool_off;
@@ -1314,7 +1483,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                             sb[e0] = cfma(k10, b1, cmul(k00, b0));
                             sb[e1] = cfma(k11, b1, cmul(k01, b0));
                         }
-                        if (has_w) warp_store_w<4>(W, wslot, lane);
+                        if (has_w) warp_store_w<4>(W, wslot, lane, wdirect);
                     } else {
                         // raw dense op (controlled two-target gates, GENERAL blocks, or a block too small for the tensor
                         // path): thread per (group, column), local arrays
@@ -1359,22 +1528,45 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                                     v[2 * e + 1] = wl[part * 4 + e].y;
                                 }
                                 warp_reduce8(v, lane);
-                                if ((lane & 3) == 0) wslot[part * 8 + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)] = v[0];
+                                if ((lane & 3) == 0) {
+                                    double* dst = wslot + part * 8 + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+                                    if (wdirect) atomicAdd(dst, v[0]);
+                                    else *dst = v[0];
+                                }
                             }
                         }
                     }
                 }
-                if (have_next && tid < KM_ELEMS) skm[((k - 1) & 1) * KM_ELEMS + tid] = next_elem;
-                tab_end_of_op(k - 1);
+                SQ_TRACE_MARK(1)
+                SQ_TRACE_NEXT()
+                if (SQ_PRELOAD && s.kind != 2) blk_kill(R);
+                tab_ready(k - 1);
+                if (SQ_PRELOAD && have_next) {
+                    const SOp sn = sops[k - 1];
+                    if (sn.kind == 2 && sn.dim == 8) blk_preload<3, true>(R, stab + ((k - 1) & (TAB_RING - 1)), (rows >> 3) << LOG_CT, lane, warp, nwarps);
+                }
+                tab_end_of_op();
                 __syncthreads();
-                if (has_w) {
+                if (has_w && !wdirect) {
                     const int nd = 2 * wdim * wdim;  // doubles
-                    // one thread per element folds the warps' partials in a fixed order and issues ONE fire-and-forget reduction:
-                    // each address of the CTA's slice has a single writer, so the sums are bit-reproducible
+                    // One thread per element folds the warps' partials in a fixed order (a pairwise tree: three dependent DADDs
+                    // instead of seven -- the fold shares the FP64 pipe with the other warps' queued DMMAs, so every dependent
+                    // add waits its turn) and issues ONE fire-and-forget reduction: each address of the CTA's slice has a single
+                    // writer, so the sums are bit-reproducible. Only the first nd / 32 warps fold; the others are already in the
+                    // next op and keep the tensor pipe fed (spreading the fold over all warps was measured slower: 1 282
+                    // against 1 339 evals/s on C3, profiles/r2_variants_exec.jsonl).
                     for (int e = tid; e < nd; e += nthr) {
-                        double sum = 0;
-                        for (int w = 0; w < nwarps; ++w)
-                            sum += reinterpret_cast<const double*>(swarp + (size_t)(buf * nwarps + w) * A.wmax)[e];
+                        const double* base = reinterpret_cast<const double*>(swarp + (size_t)buf * nwarps * A.wmax) + e;
+                        const size_t wstride = (size_t)A.wmax * 2;
+                        double sum;
+                        if (nwarps == 8) {
+                            const double a0 = base[0], a1 = base[wstride], a2 = base[2 * wstride], a3 = base[3 * wstride];
+                            const double a4 = base[4 * wstride], a5 = base[5 * wstride], a6 = base[6 * wstride], a7 = base[7 * wstride];
+                            sum = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+                        } else {
+                            sum = 0;
+                            for (int w = 0; w < nwarps; ++w) sum += base[w * wstride];
+                        }
                         if (A.w_in_smem) reinterpret_cast<double*>(swacc + s.w_off)[e] += sum;
                         else
                             atomicAdd(reinterpret_cast<double*>(A.w_part + ((size_t)y * nchunks + chunk) * A.w_total + s.w_off) + e, sum);
@@ -1401,7 +1593,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
     if (MODE == MODE_COST || MODE == MODE_GRAD) {
         if (tid == 0) {
             double* dst = A.tr_part + ((size_t)y * nchunks + chunk) * 6;
-            for (int i = 0; i < 6; ++i) dst[i] = tsum[i];
+            for (int i = 0; i < 6; ++i) dst[i] = stsum[i];
         }
         if (MODE == MODE_GRAD && A.w_in_smem) {
             __syncthreads();

@@ -33,7 +33,8 @@ __global__ void reduce_partials(const double* __restrict__ tr_part, int nchunks,
                                 int w_total, const DevOp* __restrict__ ops, const int* __restrict__ param_op,
                                 const int* __restrict__ param_slot, const cplx* __restrict__ dktab, int dkern_total,
                                 const cplx* __restrict__ ktab, int kern_total, int n_params, int with_grad,
-                                double* __restrict__ traces, int w_folded = 0) {
+                                double* __restrict__ traces, int w_folded = 0, int w_slices = 0) {
+    if (w_slices <= 0) w_slices = nchunks;  // slices of w_part per parameter set (chunks x warps with per-warp slices)
     const int y = blockIdx.x;
     const int n_k = 1 + (with_grad ? n_params : 0);
     if (threadIdx.x < 6) {
@@ -52,8 +53,8 @@ __global__ void reduce_partials(const double* __restrict__ tr_part, int nchunks,
         for (int r = 0; r < dim; ++r)
             for (int r2 = 0; r2 < dim; ++r2) {
                 cplx w = czero();
-                const int wch = w_folded ? 1 : nchunks;
-                for (int ch = 0; ch < wch; ++ch) w = cadd(w, w_part[((size_t)y * nchunks + ch) * w_total + op.w_off + r * dim + r2]);
+                const int wch = w_folded ? 1 : w_slices;
+                for (int ch = 0; ch < wch; ++ch) w = cadd(w, w_part[((size_t)y * w_slices + ch) * w_total + op.w_off + r * dim + r2]);
                 cplx dkk = czero();  // (dK K^dagger)[r][r2] = sum_c dK[r][c] conj(K[r2][c])
                 for (int c = 0; c < dim; ++c) dkk = cfmac(kk[r2 * dim + c], dk[r * dim + c], dkk);
                 acc = cfma(dkk, w, acc);

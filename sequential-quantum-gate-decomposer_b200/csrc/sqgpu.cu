@@ -679,23 +679,25 @@ struct FusedPlan {
     int log_ct = 0, threads = 32;
     int tiles = 0, tiles_per_cta = 1, chunks = 1;
     bool w_in_smem = false;
+    bool w_direct = false;  // W' partials: one global slice per (parameter set, CTA, warp), see SQ_W_DIRECT
+    int w_slices = 1;       // slices of w_part per parameter set = chunks * (w_direct ? warps per CTA : 1)
     size_t smem = 0;
 };
 
 size_t fused_smem(int mode, int rows, int ct, int threads, int dense_stage, int wmax, int w_total, bool w_in_smem, int n_ops) {
     const bool has_b = mode == MODE_GRAD || mode == MODE_BWD;
+    const bool w_direct = SQ_W_DIRECT && has_b && !w_in_smem;
     size_t s = (size_t)rows * ct * sizeof(cplx) * (has_b ? 2 : 1);
     s += (size_t)dense_stage * sizeof(cplx);
-    s += 2 * KM_ELEMS * sizeof(cplx);        // prefetched block kernels
     s += TAB_RING * sizeof(OpTabS);          // ring of DMMA block lookup tables of one sweep direction
     s += TAB_RING * sizeof(unsigned long long);  // ... and their mbarriers
     s += (size_t)n_ops * sizeof(SOp);        // staged op table
     const int nwarps = threads / 32;
     if (has_b) {
-        s += (size_t)2 * nwarps * wmax * sizeof(cplx);
+        if (!w_direct) s += (size_t)2 * nwarps * wmax * sizeof(cplx);
         if (w_in_smem) s += (size_t)w_total * sizeof(cplx);
     }
-    s += (size_t)nwarps * 6 * sizeof(double);
+    s += (size_t)(nwarps + 1) * 6 * sizeof(double);  // trace partials per warp + the CTA's running sums
     s += (size_t)rows * sizeof(int);         // window mode: deposit(r, wmask) per row
     return s;
 }
@@ -757,17 +759,21 @@ FusedPlan plan_fused(const sqgpu_ctx* c, int mode, int rows, int cols, int ysets
         p.log_ct = lc;
         p.threads = pick_threads;
         p.w_in_smem = pick_wsm;
+        p.w_direct = SQ_W_DIRECT && (mode == MODE_GRAD || mode == MODE_BWD) && !pick_wsm;
         p.smem = fused_smem(mode, rows, ct, p.threads, c->P->dense_stage, c->P->wmax, c->P->w_total, pick_wsm, c->P->n_ops);
         p.tiles = (cols + ct - 1) / ct;
         if (mode == MODE_APPLY) {
             p.tiles_per_cta = 1;
             p.chunks = p.tiles;
         } else {
-            const int want_ctas = c->sm_count * std::max(1, c->opt.ctas_per_sm);  // grid granularity
+            // grid granularity; the windowed backward pass keeps one W' slice per (CTA, warp) alive across all segment launches,
+            // so it takes fewer, longer-lived CTAs (8 per SM: eight even waves)
+            const int want_ctas = c->sm_count * std::max(1, mode == MODE_BWD ? std::min(c->opt.ctas_per_sm, 8) : c->opt.ctas_per_sm);
             int chunks = std::min(p.tiles, std::max(1, (want_ctas + ysets - 1) / ysets));
             p.tiles_per_cta = (p.tiles + chunks - 1) / chunks;
             p.chunks = (p.tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
         }
+        p.w_slices = p.chunks * (p.w_direct ? p.threads / 32 : 1);
     }
     return p;
 }
@@ -867,6 +873,7 @@ void fill_common_args(const sqgpu_ctx* c, const FusedPlan& p, ExecArgs& a, int r
     a.wmax = c->P->wmax;
     a.w_total = c->P->w_total;
     a.w_in_smem = p.w_in_smem ? 1 : 0;
+    a.w_direct = p.w_direct ? 1 : 0;
 }
 
 void time_begin(sqgpu_ctx* c, const char* name, cudaStream_t st) {
@@ -897,7 +904,7 @@ int run_exec_resident(sqgpu_ctx* c, int batch, bool grad, const cplx* d_omega, d
     if ((rc = run_optabs(c, batch, p.log_ct, st))) return rc;
     if ((rc = run_dense_tabs(c, p.log_ct, st))) return rc;
     if ((rc = c->wTrPart.ensure((size_t)batch * p.chunks * 6 * sizeof(double)))) return rc;
-    if (grad && (rc = c->wWPart.ensure(std::max<size_t>(1, (size_t)batch * p.chunks * c->P->w_total) * sizeof(cplx)))) return rc;
+    if (grad && (rc = c->wWPart.ensure(std::max<size_t>(1, (size_t)batch * p.w_slices * c->P->w_total) * sizeof(cplx)))) return rc;
     ExecArgs a;
     fill_common_args(c, p, a, c->rows, c->cols);
     a.in = c->U.as<cplx>();
@@ -910,7 +917,7 @@ int run_exec_resident(sqgpu_ctx* c, int batch, bool grad, const cplx* d_omega, d
     a.w_part = c->wWPart.as<cplx>();
     a.omega = d_omega;
     if (grad && !p.w_in_smem && c->P->w_total > 0)
-        CUDA_TRY(cudaMemsetAsync(c->wWPart.p, 0, (size_t)batch * p.chunks * c->P->w_total * sizeof(cplx), st));
+        CUDA_TRY(cudaMemsetAsync(c->wWPart.p, 0, (size_t)batch * p.w_slices * c->P->w_total * sizeof(cplx), st));
     c->last_shape[0] = p.log_ct; c->last_shape[1] = p.threads; c->last_shape[2] = p.chunks; c->last_shape[3] = p.tiles_per_cta;
     c->last_shape[4] = (int)p.smem; c->last_shape[5] = 1;
     exec_flops(*c->P, c->rows, c->cols, p.log_ct, grad, batch, &c->last_flops[0], &c->last_flops[1]);
@@ -919,13 +926,14 @@ int run_exec_resident(sqgpu_ctx* c, int batch, bool grad, const cplx* d_omega, d
     time_end(c, st);
     c->launches++;
     if (e != cudaSuccess) return fail(SQGPU_ERR_CUDA, "fused_exec launch failed: %s", cudaGetErrorString(e));
-    if (grad && p.chunks > 1 && c->P->w_total > 0) {
-        fold_w_chunks<<<dim3((c->P->w_total + 255) / 256, batch), 256, 0, st>>>(c->wWPart.as<cplx>(), p.chunks, c->P->w_total);
+    if (grad && p.w_slices > 1 && c->P->w_total > 0) {
+        fold_w_chunks<<<dim3((c->P->w_total + 255) / 256, batch), 256, 0, st>>>(c->wWPart.as<cplx>(), p.w_slices, c->P->w_total);
         c->launches++;
     }
     reduce_partials<<<batch, 128, 0, st>>>(c->wTrPart.as<double>(), p.chunks, c->wWPart.as<cplx>(), c->P->w_total,
                                            c->P->dOps.as<DevOp>(), c->P->dParamOp.as<int>(), c->P->dParamOp.as<int>() + std::max(c->n_params, 1),
-                                           c->P->wDKtab.as<cplx>(), c->P->dkern_total, c->P->wKtab.as<cplx>(), c->P->kern_total, c->n_params, grad ? 1 : 0, d_traces, 1);
+                                           c->P->wDKtab.as<cplx>(), c->P->dkern_total, c->P->wKtab.as<cplx>(), c->P->kern_total, c->n_params, grad ? 1 : 0, d_traces, 1,
+                                           p.w_slices);
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     return SQGPU_OK;
@@ -990,11 +998,11 @@ int batch_slice(const sqgpu_ctx* c, int batch, bool grad) {
     }
     if (!grad || c->P->w_total == 0) return std::min(batch, 65535);
     // a smaller slice is planned with more chunks per parameter set (the grid is filled either way): iterate to a fixed point
-    const size_t lim = (size_t)1536 << 20;
+    const size_t lim = (size_t)(SQ_W_DIRECT ? 8192 : 1536) << 20;  // B200: 180 GB of HBM
     int slice = std::min(batch, 65535);
     for (int it = 0; it < 16; ++it) {
         const FusedPlan p = plan_fused(c, MODE_GRAD, c->rows, c->cols, slice);
-        const size_t per = (size_t)std::max(1, p.chunks) * c->P->w_total * sizeof(cplx);
+        const size_t per = (size_t)std::max(1, p.w_slices) * c->P->w_total * sizeof(cplx);
         const int fit = (int)std::max<size_t>(1, std::min<size_t>((size_t)slice, lim / std::max<size_t>(per, 1)));
         if (fit >= slice) break;
         slice = fit;
@@ -2267,3 +2275,20 @@ int sqgpu_fp64_fma_peak(sqgpu_handle_t c, double* tflops) {
 #include "multi.cuh"
 // device-resident optimizer inner loops
 #include "optim.cuh"
+
+// Profiling builds only (-DSQ_TRACE=events, see exec_fused.cuh): copies the phase trace of the two CTAs on SM 0 to the host and
+// re-arms it. Returns the number of long longs written (0 in product builds).
+extern "C" long long sqgpu_debug_trace(long long* out, long long max_elems) {
+#if SQ_TRACE
+    const long long n = (long long)2 * SQ_TRACE * 16 * 2;
+    if (!out || max_elems < n) return -n;
+    cudaDeviceSynchronize();
+    if (cudaMemcpyFromSymbol(out, sq::g_trace, n * sizeof(long long)) != cudaSuccess) return -1;
+    const int zero = 0;
+    cudaMemcpyToSymbol(sq::g_trace_arrivals, &zero, sizeof(int));
+    return n;
+#else
+    (void)out; (void)max_elems;
+    return 0;
+#endif
+}

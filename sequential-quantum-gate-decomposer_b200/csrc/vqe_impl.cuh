@@ -16,13 +16,15 @@ static int vqe_window_dev(sqgpu_ctx* c, const double* d_params, int batch, bool 
     // four quarter-width CTAs per SM: with ~5 ops between a tile's load and its store, more independent CTAs in different
     // phases are what overlaps the HBM round trips with the tensor work (measured: +12 % energy, +7 % gradient over two)
     const FusedPlan pf = plan_fused(c, MODE_APPLY, wr, wc, std::min(slice, batch), 4);
-    const FusedPlan pb = with_grad ? plan_fused(c, MODE_BWD, wr, wc, std::min(slice, batch), 4) : pf;
+    // backward segments: ONE 512-thread CTA per SM with a two-column tile (measured on C5: 55 ms per 64 sets against 65 ms for
+    // two 256-thread CTAs with single-column tiles, whose layout conflicts more and whose HBM accesses are 16 B wide)
+    const FusedPlan pb = with_grad ? plan_fused(c, MODE_BWD, wr, wc, std::min(slice, batch), 1) : pf;
     if (!pf.ok || !pb.ok) return 1;
     const int nblk = std::min(c->sm_count * 8, std::max(1, rows / 512));
     if ((rc = c->wMat.ensure((size_t)2 * slice * rows * sizeof(cplx)))) return rc;
     if ((rc = c->wTrPart.ensure((size_t)slice * std::max(nblk * 32 + 6, pb.chunks * 6) * sizeof(double)))) return rc;
     if (with_grad) {
-        if ((rc = c->wWPart.ensure(std::max<size_t>(1, (size_t)slice * pb.chunks * c->P->w_total) * sizeof(cplx)))) return rc;
+        if ((rc = c->wWPart.ensure(std::max<size_t>(1, (size_t)slice * pb.w_slices * c->P->w_total) * sizeof(cplx)))) return rc;
         if ((rc = c->wTraces.ensure((size_t)slice * (1 + c->n_params) * 6 * sizeof(double)))) return rc;
     }
     cplx* psi = c->wMat.as<cplx>();
@@ -70,7 +72,7 @@ static int vqe_window_dev(sqgpu_ctx* c, const double* d_params, int batch, bool 
         if (!with_grad) continue;
         if (pb.log_ct != pf.log_ct && (rc = run_optabs(c, nb, pb.log_ct, st))) return rc;
         if ((rc = run_dense_tabs(c, pb.log_ct, st))) return rc;
-        if (c->P->w_total > 0) CUDA_TRY(cudaMemsetAsync(c->wWPart.p, 0, (size_t)nb * pb.chunks * c->P->w_total * sizeof(cplx), st));
+        if (c->P->w_total > 0) CUDA_TRY(cudaMemsetAsync(c->wWPart.p, 0, (size_t)nb * pb.w_slices * c->P->w_total * sizeof(cplx), st));
         CUDA_TRY(cudaMemsetAsync(c->wTrPart.p, 0, (size_t)nb * pb.chunks * 6 * sizeof(double), st));
         time_begin(c, "fused_exec<WINDOW_BWD>", st);
         for (int si = (int)c->segs.size() - 1; si >= 0; --si) {
@@ -83,13 +85,13 @@ static int vqe_window_dev(sqgpu_ctx* c, const double* d_params, int batch, bool 
             if (e != cudaSuccess) return fail(SQGPU_ERR_CUDA, "fused_exec launch failed: %s", cudaGetErrorString(e));
         }
         time_end(c, st);
-        if (pb.chunks > 1 && c->P->w_total > 0) {
-            fold_w_chunks<<<dim3((c->P->w_total + 255) / 256, nb), 256, 0, st>>>(c->wWPart.as<cplx>(), pb.chunks, c->P->w_total);
+        if (pb.w_slices > 1 && c->P->w_total > 0) {
+            fold_w_chunks<<<dim3((c->P->w_total + 255) / 256, nb), 256, 0, st>>>(c->wWPart.as<cplx>(), pb.w_slices, c->P->w_total);
             c->launches++;
         }
         reduce_partials<<<nb, 128, 0, st>>>(c->wTrPart.as<double>(), pb.chunks, c->wWPart.as<cplx>(), c->P->w_total, c->P->dOps.as<DevOp>(),
                                             c->P->dParamOp.as<int>(), c->P->dParamOp.as<int>() + std::max(c->n_params, 1), c->P->wDKtab.as<cplx>(),
-                                            c->P->dkern_total, c->P->wKtab.as<cplx>(), c->P->kern_total, c->n_params, 1, c->wTraces.as<double>(), 1);
+                                            c->P->dkern_total, c->P->wKtab.as<cplx>(), c->P->kern_total, c->n_params, 1, c->wTraces.as<double>(), 1, pb.w_slices);
         grad_from_traces<<<nb, 128, 0, st>>>(c->wTraces.as<double>(), c->n_params, 2.0, d_grad + (size_t)b0 * c->n_params);
         c->launches += 2;
         CUDA_TRY(cudaGetLastError());
