@@ -1012,8 +1012,17 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
     if (HAS_B && A.w_in_smem) {
         for (int e = tid; e < A.w_total; e += nthr) swacc[e] = czero();
     }
+    int* scolpart = srowpart + rows;                                     // window mode: [8] deposit(c, ~wmask) of the tile's column offsets
     if (WIN && A.wmask) {
-        for (int r = tid; r < rows; r += nthr) srowpart[r] = (int)deposit_bits((unsigned)r, A.wmask);
+        // deposit(r, wmask) = deposit(r & 63, wmask) | deposit(r & ~63, wmask): two small tables (built with the software PDEP
+        // loop by 64 + rows / 64 threads, in the not yet loaded tile area) instead of one loop per row
+        int* slo = reinterpret_cast<int*>(sa);
+        int* shi = slo + 64;
+        for (int t = tid; t < 64 + (rows >> 6); t += nthr)
+            slo[t] = (int)deposit_bits(t < 64 ? (unsigned)t : (unsigned)(t - 64) << 6, A.wmask);
+        if (tid < 8) scolpart[tid] = (int)deposit_bits((unsigned)tid, ~A.wmask);
+        __syncthreads();
+        for (int r = tid; r < rows; r += nthr) srowpart[r] = slo[r & 63] | ((r >> 6) ? shi[r >> 6] : 0);
     }
     if (tid < 6) stsum[tid] = 0.0;
     __syncthreads();
@@ -1125,33 +1134,25 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
 
         // ---- load the tile ------------------------------------------------------------------------------------
         {
+            bool win_loaded = false;
             if (WIN && A.wmask) {
                 // window mode: the tile's columns are CT consecutive values of the non-window bits
                 const size_t colbase = (size_t)y * A.in_ystride + deposit_bits((unsigned)j0, ~A.wmask);
                 const cplx* __restrict__ src = (MODE == MODE_BWD ? A.out : A.in) + colbase;
                 const cplx* __restrict__ srcb = (MODE == MODE_BWD) ? A.beta + colbase : nullptr;
-                // 8 independent 16 B loads in flight per thread (the state comes from HBM / L2: latency-bound otherwise)
-                constexpr int UL = (MODE == MODE_BWD) ? 4 : 8;
-                for (int e0 = tid; e0 < rows * CT; e0 += nthr * UL) {
-                    cplx va[UL], vb[UL];
-#pragma unroll
-                    for (int u = 0; u < UL; ++u) {
-                        const int e = e0 + u * nthr;
-                        if (e < rows * CT) {
-                            const size_t off = (size_t)srowpart[e >> LOG_CT] | deposit_bits((unsigned)(e & (CT - 1)), ~A.wmask);
-                            va[u] = src[off];
-                            if (MODE == MODE_BWD) vb[u] = srcb[off];
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < UL; ++u) {
-                        const int e = e0 + u * nthr;
-                        if (e < rows * CT) {
-                            sa[elem<LOG_CT>(e >> LOG_CT, e & (CT - 1))] = va[u];
-                            if (MODE == MODE_BWD) sb[elem<LOG_CT>(e >> LOG_CT, e & (CT - 1))] = vb[u];
-                        }
-                    }
+                // every element travels as one 16 B asynchronous copy (LDGSTS) straight into its swizzled shared-memory slot: no
+                // staging registers, so the WHOLE tile is in flight at once (the state comes from HBM / L2: the gather is
+                // latency-bound otherwise) -- committed as one cp.async group ahead of the op tables of this tile
+                for (int e = tid; e < rows * CT; e += nthr) {
+                    const int r = e >> LOG_CT, cc = e & (CT - 1);
+                    const size_t off = (size_t)(unsigned)(srowpart[r] | scolpart[cc]);
+                    const int se = elem<LOG_CT>(r, cc);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(sa + se)), "l"(src + off));
+                    if (MODE == MODE_BWD)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(sb + se)), "l"(srcb + off));
                 }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                win_loaded = true;
             } else {
                 const cplx* __restrict__ src = A.in + (size_t)y * A.in_ystride + j0;
                 for (int e = tid; e < rows * CT; e += nthr) {
@@ -1163,6 +1164,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
             }
             const int first_op = (MODE == MODE_BWD) ? A.n_ops - 1 : 0;
             if (A.n_ops > 0) tab_prime(first_op, MODE == MODE_BWD ? -1 : 1, MODE == MODE_BWD);
+            // the tile's group is older than the table groups tab_prime leaves pending; without tables (or with the bulk ring,
+            // which does not use groups) wait for it explicitly
+            if (win_loaded && (A.n_ops == 0 || SQ_TAB_BULK)) asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncthreads();
 
@@ -1309,7 +1313,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                 cplx* __restrict__ dst = A.out + (size_t)y * A.out_ystride + deposit_bits((unsigned)j0, ~A.wmask);
                 for (int e = tid; e < rows * CT; e += nthr) {
                     const int i = e >> LOG_CT, c = e & (CT - 1);
-                    dst[(size_t)srowpart[i] | deposit_bits((unsigned)c, ~A.wmask)] = sa[elem<LOG_CT>(i, c)];
+                    dst[(size_t)(unsigned)(srowpart[i] | scolpart[c])] = sa[elem<LOG_CT>(i, c)];
                 }
             } else {
                 cplx* __restrict__ dst = A.out + (size_t)y * A.out_ystride + j0;
@@ -1581,7 +1585,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                 cplx* __restrict__ db = A.beta + colbase;
                 for (int e = tid; e < rows * CT; e += nthr) {
                     const int i = e >> LOG_CT, c = e & (CT - 1);
-                    const size_t off = (size_t)srowpart[i] | deposit_bits((unsigned)c, ~A.wmask);
+                    const size_t off = (size_t)(unsigned)(srowpart[i] | scolpart[c]);
                     da[off] = sa[elem<LOG_CT>(i, c)];
                     db[off] = sb[elem<LOG_CT>(i, c)];
                 }

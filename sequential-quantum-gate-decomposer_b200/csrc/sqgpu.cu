@@ -698,11 +698,11 @@ size_t fused_smem(int mode, int rows, int ct, int threads, int dense_stage, int 
         if (w_in_smem) s += (size_t)w_total * sizeof(cplx);
     }
     s += (size_t)(nwarps + 1) * 6 * sizeof(double);  // trace partials per warp + the CTA's running sums
-    s += (size_t)rows * sizeof(int);         // window mode: deposit(r, wmask) per row
+    s += (size_t)(rows + 8) * sizeof(int);   // window mode: deposit(r, wmask) per row, deposit(c, ~wmask) per tile column
     return s;
 }
 
-FusedPlan plan_fused(const sqgpu_ctx* c, int mode, int rows, int cols, int ysets, int default_split = 2) {
+FusedPlan plan_fused(const sqgpu_ctx* c, int mode, int rows, int cols, int ysets, int default_split = 2, bool window = false) {
     FusedPlan p;
     // test hook (option force_stream): cost / gradient evaluations go down the chunked streaming executor
     if (c->opt.force_stream && (mode == MODE_COST || mode == MODE_GRAD)) return p;
@@ -762,9 +762,16 @@ FusedPlan plan_fused(const sqgpu_ctx* c, int mode, int rows, int cols, int ysets
         p.w_direct = SQ_W_DIRECT && (mode == MODE_GRAD || mode == MODE_BWD) && !pick_wsm;
         p.smem = fused_smem(mode, rows, ct, p.threads, c->P->dense_stage, c->P->wmax, c->P->w_total, pick_wsm, c->P->n_ops);
         p.tiles = (cols + ct - 1) / ct;
-        if (mode == MODE_APPLY) {
+        if (mode == MODE_APPLY && !window) {
             p.tiles_per_cta = 1;
             p.chunks = p.tiles;
+        } else if (mode == MODE_APPLY) {
+            // window segments: a few long-lived CTAs per SM slot, so that the per-CTA prologue (op staging, the deposit
+            // tables of the window) is paid once per ~10 tiles instead of once per tile
+            const int want_ctas = c->sm_count * std::max(1, std::min(c->opt.ctas_per_sm, 16));
+            int chunks = std::min(p.tiles, std::max(1, (want_ctas + ysets - 1) / ysets));
+            p.tiles_per_cta = (p.tiles + chunks - 1) / chunks;
+            p.chunks = (p.tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
         } else {
             // grid granularity; the windowed backward pass keeps one W' slice per (CTA, warp) alive across all segment launches,
             // so it takes fewer, longer-lived CTAs (8 per SM: eight even waves)
@@ -889,6 +896,8 @@ void time_end(sqgpu_ctx* c, cudaStream_t st) {
 }
 
 int run_exec_streaming(sqgpu_ctx* c, int batch, bool grad, const cplx* d_omega, double* d_traces, cudaStream_t st);
+int run_exec_tall_window(sqgpu_ctx* c, int batch, bool grad, const cplx* d_omega, double* d_traces, cudaStream_t st);
+bool tall_window_fits(sqgpu_ctx* c, bool grad);
 void exec_flops(const Plan& P, int rows, int cols, int log_ct, bool grad, int ysets, double* tensor, double* scalar);
 StreamGate make_stream_gate(const DevOp& op, cplx* data, long long ystride, int rows, int cols, int ld, const cplx* K, long long k_ystride);
 int launch_stream_gate(sqgpu_ctx* c, const DevOp& op, bool deriv, cplx* data, long long ystride, int ysets, int rows, int cols,
@@ -899,7 +908,8 @@ int launch_stream_gate(sqgpu_ctx* c, const DevOp& op, bool deriv, cplx* data, lo
 int run_exec_resident(sqgpu_ctx* c, int batch, bool grad, const cplx* d_omega, double* d_traces, cudaStream_t st) {
     const int mode = grad ? MODE_GRAD : MODE_COST;
     FusedPlan p = plan_fused(c, mode, c->rows, c->cols, batch);
-    if (!p.ok) return run_exec_streaming(c, batch, grad, d_omega, d_traces, st);  // column too tall for shared memory
+    if (!p.ok)  // column too tall for shared memory: windowed executor (planW) or one op per launch (plan2)
+        return c->P == &c->planW ? run_exec_tall_window(c, batch, grad, d_omega, d_traces, st) : run_exec_streaming(c, batch, grad, d_omega, d_traces, st);
     int rc;
     if ((rc = run_optabs(c, batch, p.log_ct, st))) return rc;
     if ((rc = run_dense_tabs(c, p.log_ct, st))) return rc;
@@ -1020,7 +1030,7 @@ int traces_dev(sqgpu_ctx* c, const double* d_params, int batch, bool with_grad, 
     if (batch <= 0) return SQGPU_OK;
     // three-qubit blocks for the shared-memory executor, two-qubit blocks for the streaming fallback
     c->P = &c->plan3;
-    if (!plan_fused(c, with_grad ? MODE_GRAD : MODE_COST, c->rows, c->cols, batch).ok) c->P = &c->plan2;
+    if (!plan_fused(c, with_grad ? MODE_GRAD : MODE_COST, c->rows, c->cols, batch).ok) c->P = tall_window_fits(c, with_grad) ? &c->planW : &c->plan2;
     if (c->cols + effective_offset(c) > c->rows) return fail(SQGPU_ERR_INVALID, "trace_offset %d + cols %d exceeds rows %d", effective_offset(c), c->cols, c->rows);
     if (with_grad && !c->all_unitary) return fail(SQGPU_ERR_UNSUPPORTED, "gradient with a non-unitary GENERAL gate is not supported (the adjoint sweep needs K^-1 = K^dagger)");
     const bool hs_corr = c->cfg.variant == SQGPU_HILBERT_SCHMIDT_TEST_CORRECTION1 || c->cfg.variant == SQGPU_HILBERT_SCHMIDT_TEST_CORRECTION2;
@@ -1222,7 +1232,7 @@ int apply_window_dev(sqgpu_ctx* c, cplx* d_inout, int rows, cudaStream_t st) {
     PlanScope keep(c);
     c->P = &c->planW;
     const int w = c->win_w, wr = 1 << w, wc = rows >> w;
-    const FusedPlan pf = plan_fused(c, MODE_APPLY, wr, wc, 1, 4);
+    const FusedPlan pf = plan_fused(c, MODE_APPLY, wr, wc, 1, 4, true);
     if (!pf.ok || c->segs.empty()) return 1;
     int rc;
     if ((rc = run_tables(c, c->wParams.as<double>(), 1, false, st))) return rc;
@@ -1246,6 +1256,117 @@ int apply_window_dev(sqgpu_ctx* c, cplx* d_inout, int rows, cudaStream_t st) {
         if (e != cudaSuccess) return fail(SQGPU_ERR_CUDA, "fused_exec launch failed: %s", cudaGetErrorString(e));
     }
     time_end(c, st);
+    return SQGPU_OK;
+}
+
+// Matrices whose column does not fit shared memory (gradient n >= 13, cost n >= 14), first choice: the WINDOWED executor
+// of the state-vector path. A chunk of 2^m columns of the matrix, stored row-major [2^n][2^m], is a vector over n + m index
+// bits whose upper n bits are the qubits; the segments of the window plan (build_window_plan) apply to it with their masks
+// shifted by m, the tile's columns being the values of all other bits (the non-window qubits AND the matrix columns). The
+// chunk makes one HBM round trip per SEGMENT (fused_exec<MODE_APPLY>, then fused_exec<MODE_BWD> on (a, beta) in reverse)
+// instead of one per gate as in run_exec_streaming below, and the ops are the 3-qubit DMMA blocks of plan3.
+// tall_window_fits: the decision (before the kernel tables are built for the plan); c->P is left untouched.
+bool tall_window_fits(sqgpu_ctx* c, bool grad) {
+    if (!c->opt.tall_window || c->segs.empty() || c->cfg.variant == SQGPU_SUM_OF_SQUARES) return false;
+    if (c->win_w >= c->qbit_num) return false;  // a single tile would hold the column: the resident executor's case
+    PlanScope keep(c);
+    c->P = &c->planW;
+    const int wr = 1 << c->win_w, wc = 1 << (c->qbit_num - c->win_w);
+    if (!plan_fused(c, MODE_APPLY, wr, wc, 1, 4).ok) return false;
+    if (grad && !plan_fused(c, MODE_BWD, wr, wc, 1, 1).ok) return false;
+    return true;
+}
+
+int run_exec_tall_window(sqgpu_ctx* c, int batch, bool grad, const cplx* d_omega, double* d_traces, cudaStream_t st) {
+    const int rows = c->rows, cols = c->cols, n = c->qbit_num, w = c->win_w, wr = 1 << w;
+    // chunk width: a power of two that divides cols (every chunk has the same shape), at most 64 MiB of column data per set
+    int m = 0;
+    while (((cols >> (m + 1)) << (m + 1)) == cols && ((size_t)rows << (m + 1)) * sizeof(cplx) <= ((size_t)64 << 20)) ++m;
+    const int cw = 1 << m, nchunks = cols / cw;
+    const size_t ce = (size_t)rows * cw;
+    const int wc = (int)(ce >> w);
+    const FusedPlan pf = plan_fused(c, MODE_APPLY, wr, wc, batch, 4, true);
+    const FusedPlan pb = grad ? plan_fused(c, MODE_BWD, wr, wc, batch, 1) : pf;
+    if (!pf.ok || !pb.ok) return fail(SQGPU_ERR_STATE, "windowed executor: no shared-memory plan for a %d-qubit window", w);
+    int rc;
+    if ((rc = c->wMat.ensure((size_t)(grad ? 2 : 1) * batch * ce * sizeof(cplx)))) return rc;
+    if ((rc = c->wTrPart.ensure((size_t)batch * nchunks * 6 * sizeof(double)))) return rc;
+    if (grad && (rc = c->wWPart.ensure(std::max<size_t>(1, (size_t)batch * pb.w_slices * c->P->w_total) * sizeof(cplx)))) return rc;
+    cplx* A = c->wMat.as<cplx>();
+    cplx* Bt = A + (size_t)batch * ce;
+    double* tr_part = c->wTrPart.as<double>();
+    const int ntt = n_trace_types_of(c->cfg.variant);
+    const int off = effective_offset(c);
+    auto seg_args = [&](const FusedPlan& p, const sqgpu_ctx::Segment& sg, ExecArgs& a) {
+        fill_common_args(c, p, a, wr, wc);
+        a.n = w;
+        a.in = A;
+        a.out = A;
+        a.in_ystride = a.out_ystride = (long long)ce;
+        a.wmask = sg.wmask << m;
+        a.ops += sg.begin;
+        a.n_ops = sg.end - sg.begin;
+        a.optabs += sg.begin;
+        a.optab_stride = c->P->n_ops;
+    };
+    if ((rc = run_optabs(c, batch, pf.log_ct, st))) return rc;
+    if ((rc = run_dense_tabs(c, pf.log_ct, st))) return rc;
+    int tab_log_ct = pf.log_ct;
+    if (grad && c->P->w_total > 0) CUDA_TRY(cudaMemsetAsync(c->wWPart.p, 0, (size_t)batch * pb.w_slices * c->P->w_total * sizeof(cplx), st));
+    c->last_shape[0] = pb.log_ct; c->last_shape[1] = pb.threads; c->last_shape[2] = pb.chunks; c->last_shape[3] = pb.tiles_per_cta;
+    c->last_shape[4] = (int)pb.smem; c->last_shape[5] = 1;
+    exec_flops(*c->P, rows, cols, pb.log_ct, grad, batch, &c->last_flops[0], &c->last_flops[1]);
+    for (int ch = 0; ch < nchunks; ++ch) {
+        const int j0 = ch * cw;
+        copy_chunk<<<dim3(std::min(c->sm_count * 8, std::max(1, (int)(ce / 256))), batch), 256, 0, st>>>(c->U.as<cplx>(), cols, j0, rows, cw, A);
+        c->launches++;
+        if (tab_log_ct != pf.log_ct) {
+            if ((rc = run_optabs(c, batch, pf.log_ct, st))) return rc;
+            if ((rc = run_dense_tabs(c, pf.log_ct, st))) return rc;
+            tab_log_ct = pf.log_ct;
+        }
+        time_begin(c, "fused_exec<WINDOW_FWD>", st);
+        for (const auto& sg : c->segs) {
+            ExecArgs a;
+            seg_args(pf, sg, a);
+            cudaError_t e = launch_fused_mode<MODE_APPLY>(a, pf, batch, st);
+            c->launches++;
+            if (e != cudaSuccess) return fail(SQGPU_ERR_CUDA, "fused_exec launch failed: %s", cudaGetErrorString(e));
+        }
+        time_end(c, st);
+        traces_stream<<<batch, 256, 0, st>>>(A, (long long)ce, cw, cw, n, off + j0, ntt, tr_part + (size_t)ch * 6, nchunks * 6);
+        c->launches++;
+        if (!grad) continue;
+        CUDA_TRY(cudaMemsetAsync(Bt, 0, (size_t)batch * ce * sizeof(cplx), st));
+        beta_init_stream<<<dim3((cw + 127) / 128, batch), 128, 0, st>>>(Bt, rows, cw, j0, n, off, ntt, d_omega);
+        c->launches++;
+        if (tab_log_ct != pb.log_ct) {
+            if ((rc = run_optabs(c, batch, pb.log_ct, st))) return rc;
+            if ((rc = run_dense_tabs(c, pb.log_ct, st))) return rc;
+            tab_log_ct = pb.log_ct;
+        }
+        time_begin(c, "fused_exec<WINDOW_BWD>", st);
+        for (int si = (int)c->segs.size() - 1; si >= 0; --si) {
+            ExecArgs a;
+            seg_args(pb, c->segs[si], a);
+            a.beta = Bt;
+            a.w_part = c->wWPart.as<cplx>();  // the CTAs' slices accumulate over segments and chunks (one writer per address per launch)
+            cudaError_t e = launch_fused_mode<MODE_BWD>(a, pb, batch, st);
+            c->launches++;
+            if (e != cudaSuccess) return fail(SQGPU_ERR_CUDA, "fused_exec launch failed: %s", cudaGetErrorString(e));
+        }
+        time_end(c, st);
+    }
+    CUDA_TRY(cudaGetLastError());
+    if (grad && pb.w_slices > 1 && c->P->w_total > 0) {
+        fold_w_chunks<<<dim3((c->P->w_total + 255) / 256, batch), 256, 0, st>>>(c->wWPart.as<cplx>(), pb.w_slices, c->P->w_total);
+        c->launches++;
+    }
+    reduce_partials<<<batch, 128, 0, st>>>(tr_part, nchunks, c->wWPart.as<cplx>(), c->P->w_total, c->P->dOps.as<DevOp>(), c->P->dParamOp.as<int>(),
+                                           c->P->dParamOp.as<int>() + std::max(c->n_params, 1), c->P->wDKtab.as<cplx>(), c->P->dkern_total,
+                                           c->P->wKtab.as<cplx>(), c->P->kern_total, c->n_params, grad ? 1 : 0, d_traces, 1, pb.w_slices);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
     return SQGPU_OK;
 }
 

@@ -15,7 +15,7 @@ static int vqe_window_dev(sqgpu_ctx* c, const double* d_params, int batch, bool 
     const int slice = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::min(batch, 65535), ((size_t)1 << 30) / ((size_t)rows * sizeof(cplx))));
     // four quarter-width CTAs per SM: with ~5 ops between a tile's load and its store, more independent CTAs in different
     // phases are what overlaps the HBM round trips with the tensor work (measured: +12 % energy, +7 % gradient over two)
-    const FusedPlan pf = plan_fused(c, MODE_APPLY, wr, wc, std::min(slice, batch), 4);
+    const FusedPlan pf = plan_fused(c, MODE_APPLY, wr, wc, std::min(slice, batch), 4, true);
     // backward segments: ONE 512-thread CTA per SM with a two-column tile (measured on C5: 55 ms per 64 sets against 65 ms for
     // two 256-thread CTAs with single-column tiles, whose layout conflicts more and whose HBM accesses are 16 B wide)
     const FusedPlan pb = with_grad ? plan_fused(c, MODE_BWD, wr, wc, std::min(slice, batch), 1) : pf;

@@ -704,35 +704,68 @@ def test_n12_gradient_single_column_tiles(sq, port):
     e.close()
 
 
-def test_n13_gradient_streams(sq):
-    """n = 13 gradient does not fit shared memory: the engine falls back to the streaming executor by itself. No oracle
-    at this size; checked through size-independent properties: analytic gradient vs central finite difference, and
-    linearity of the trace cost in U."""
+@pytest.mark.parametrize("cols", [3, 4])
+def test_n13_gradient_windowed_executor(sq, port, cols):
+    """n = 13 gradient: one column + its row functional (256 KB) do not fit shared memory. The engine runs the WINDOWED
+    executor on column chunks (segments of an 11-qubit window, fused 3-qubit DMMA blocks, one HBM round trip per segment) --
+    asserted from the kernel name -- instead of one streaming launch per gate. Checked against the oracle on a column slice
+    (variants 0 and 3, all parameters), against the streaming fallback (option tall_window = 0), and through linearity.
+    cols = 3: chunks of one column (tile columns = the non-window qubits only); cols = 4: one chunk of four columns."""
     n = 13
     c = H.adaptive_circuit(n, 1, topology=[(q + 1, q) for q in range(n - 1)])
+    d, pool = c.descriptors()
     P = c.get_Parameter_Num()
-    theta = H.random_params(P, seed=8)
-    e = sq.Engine(0)
-    e.set_circuit(c)
-    cols = 3
+    theta = H.random_params(P, seed=8, batch=2)
     rng = np.random.default_rng(3)
     U = np.ascontiguousarray((rng.standard_normal((1 << n, cols)) + 1j * rng.standard_normal((1 << n, cols))) / 50.0)
+    e = sq.Engine(0)
+    e.set_circuit(c)
     e.upload_matrix(U)
-    e.set_cost(0, 0)
-    f, g = e.cost_grad_batched(theta)
-    assert "stream" in e.last_kernel_time()[0]
-    idx = rng.choice(P, 4, replace=False)
-    h = 1e-5
-    sh = np.repeat(theta[None, :], 8, axis=0)
-    for k, i in enumerate(idx):
-        sh[2 * k, i] += h
-        sh[2 * k + 1, i] -= h
-    fs = e.cost_batched(sh)
-    assert np.abs((fs[0::2] - fs[1::2]) / (2 * h) - g[0, idx]).max() < 1e-8
+    for variant in (0, 3):
+        e.set_cost(variant, 0)
+        f, g = e.cost_grad_batched(theta)
+        assert e.last_kernel_time()[0] == "fused_exec<WINDOW_BWD>", e.last_kernel_time()
+        for b in range(2):
+            f_ref, g_ref = port.cost_grad(d, P, theta[b], U, n, variant)
+            assert close_rel(f[b], f_ref) and close_rel(g[b], g_ref)
+    # the one-op-per-launch fallback gives the same numbers
+    es = sq.Engine(0, options={"tall_window": 0})
+    es.set_circuit(c)
+    es.upload_matrix(U)
+    es.set_cost(3, 0)
+    fs, gs = es.cost_grad_batched(theta)
+    assert "stream" in es.last_kernel_time()[0]
+    assert close_rel(fs, f) and close_rel(gs, g)
+    es.close()
     # linearity of the trace in U: cost(2U) - 1 = 2 (cost(U) - 1)
+    e.set_cost(0, 0)
+    f1 = e.cost_batched(theta)
     e.upload_matrix(2 * U)
     f2 = e.cost_batched(theta)
-    assert abs((f2[0] - 1.0) - 2 * (f[0] - 1.0)) < 1e-12
+    assert np.abs((f2 - 1.0) - 2 * (f1 - 1.0)).max() < 1e-12
+    e.close()
+
+
+def test_n14_cost_windowed_executor(sq, port):
+    """n = 14 cost: a 256 KB column does not fit shared memory either; the forward sweep runs in window segments. All trace
+    variants against the oracle on a two-column slice with a trace offset."""
+    n = 14
+    c = H.random_circuit(n, 60, seed=23, names=["U3", "RY", "CRY", "CNOT", "RZ", "adaptive", "CZ", "RX", "H"])
+    d, pool = c.descriptors()
+    P = c.get_Parameter_Num()
+    theta = H.random_params(P, seed=4, batch=2)
+    rng = np.random.default_rng(6)
+    U = np.ascontiguousarray((rng.standard_normal((1 << n, 2)) + 1j * rng.standard_normal((1 << n, 2))) / 70.0)
+    e = sq.Engine(0)
+    e.set_circuit(c)
+    e.upload_matrix(U)
+    for variant in (0, 1, 2, 3, 5):
+        e.set_cost(variant, 5 if variant <= 2 else 0, 0.41)
+        f = e.cost_batched(theta)
+        assert e.last_kernel_time()[0] == "fused_exec<WINDOW_FWD>", e.last_kernel_time()
+        for b in range(2):
+            f_ref = port.cost(d, theta[b], U, n, variant, 5 if variant <= 2 else 0, 0.41, pool=pool)
+            assert close_rel(f[b], f_ref)
     e.close()
 
 
