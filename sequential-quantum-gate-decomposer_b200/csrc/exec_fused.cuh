@@ -1127,7 +1127,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
 #endif
 
     for (int ti = 0; ti < A.tiles_per_cta; ++ti) {
-        const int tile = chunk * A.tiles_per_cta + ti;
+        // window mode deals the tiles round robin: the CTAs of a wave then work on neighbouring tiles at the same time, and the
+        // 32 B / 64 B pieces of one DRAM burst that belong to different tiles meet in L2 instead of being fetched twice
+        const int tile = (WIN && A.wmask) ? ti * nchunks + chunk : chunk * A.tiles_per_cta + ti;
         if (tile >= A.tiles) break;
         const int j0 = tile * CT;
         const int valid = min(CT, A.cols - j0);

@@ -765,19 +765,32 @@ FusedPlan plan_fused(const sqgpu_ctx* c, int mode, int rows, int cols, int ysets
         if (mode == MODE_APPLY && !window) {
             p.tiles_per_cta = 1;
             p.chunks = p.tiles;
-        } else if (mode == MODE_APPLY) {
-            // window segments: a few long-lived CTAs per SM slot, so that the per-CTA prologue (op staging, the deposit
-            // tables of the window) is paid once per ~10 tiles instead of once per tile
-            const int want_ctas = c->sm_count * std::max(1, std::min(c->opt.ctas_per_sm, 16));
-            int chunks = std::min(p.tiles, std::max(1, (want_ctas + ysets - 1) / ysets));
-            p.tiles_per_cta = (p.tiles + chunks - 1) / chunks;
-            p.chunks = (p.tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
         } else {
-            // grid granularity; the windowed backward pass keeps one W' slice per (CTA, warp) alive across all segment launches,
-            // so it takes fewer, longer-lived CTAs (8 per SM: eight even waves)
-            const int want_ctas = c->sm_count * std::max(1, mode == MODE_BWD ? std::min(c->opt.ctas_per_sm, 8) : c->opt.ctas_per_sm);
-            int chunks = std::min(p.tiles, std::max(1, (want_ctas + ysets - 1) / ysets));
-            p.tiles_per_cta = (p.tiles + chunks - 1) / chunks;
+            // Grid granularity: chunks CTAs per parameter set, each with tiles_per_cta tiles. The target is ctas_per_sm CTAs per
+            // SM (window segments: a few long-lived ones, so that the per-CTA prologue is paid once per ~10 tiles; the windowed
+            // backward pass keeps one W' slice per CTA alive across all segment launches); around that target the chunk count
+            // with the shortest schedule is taken -- waves x tiles per CTA, the CTAs of a wave running side by side on
+            // `slots` = SMs x resident CTAs -- so that the last wave is full (C5 backward: 19 chunks of 14 tiles need 9 waves for
+            // 8.2 waves of work; 37 chunks of 7 tiles fill 16 waves exactly).
+            const int per_sm = mode == MODE_BWD ? std::min(c->opt.ctas_per_sm, 8) : (mode == MODE_APPLY ? std::min(c->opt.ctas_per_sm, 16) : c->opt.ctas_per_sm);
+            const int want_ctas = c->sm_count * std::max(1, per_sm);
+            const int target = std::min(p.tiles, std::max(1, (want_ctas + ysets - 1) / ysets));
+            const int resident = std::max(1, std::min((int)((size_t)c->smem_per_sm / (p.smem + 1024)), 65536 / (128 * std::max(p.threads, 32))));  // shared memory, 128 registers per thread
+            const long long slots = (long long)c->sm_count * resident;
+            long long best_cost = -1;
+            int best_chunks = target;
+            for (int ch = std::max(1, target / 2); ch <= std::min(p.tiles, 2 * target + 1); ++ch) {
+                const int tpc = (p.tiles + ch - 1) / ch;
+                const int used = (p.tiles + tpc - 1) / tpc;  // chunks that actually get tiles
+                const long long waves = ((long long)used * ysets + slots - 1) / slots;
+                const long long cost = waves * tpc;
+                // ties: the count nearest to the target
+                if (best_cost < 0 || cost < best_cost || (cost == best_cost && std::abs(used - target) < std::abs(best_chunks - target))) {
+                    best_cost = cost;
+                    best_chunks = used;
+                }
+            }
+            p.tiles_per_cta = (p.tiles + best_chunks - 1) / best_chunks;
             p.chunks = (p.tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
         }
         p.w_slices = p.chunks * (p.w_direct ? p.threads / 32 : 1);
@@ -1286,7 +1299,7 @@ int run_exec_tall_window(sqgpu_ctx* c, int batch, bool grad, const cplx* d_omega
     const size_t ce = (size_t)rows * cw;
     const int wc = (int)(ce >> w);
     const FusedPlan pf = plan_fused(c, MODE_APPLY, wr, wc, batch, 4, true);
-    const FusedPlan pb = grad ? plan_fused(c, MODE_BWD, wr, wc, batch, 1) : pf;
+    const FusedPlan pb = grad ? plan_fused(c, MODE_BWD, wr, wc, batch, 2) : pf;
     if (!pf.ok || !pb.ok) return fail(SQGPU_ERR_STATE, "windowed executor: no shared-memory plan for a %d-qubit window", w);
     int rc;
     if ((rc = c->wMat.ensure((size_t)(grad ? 2 : 1) * batch * ce * sizeof(cplx)))) return rc;

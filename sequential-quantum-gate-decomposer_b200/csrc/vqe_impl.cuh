@@ -16,9 +16,11 @@ static int vqe_window_dev(sqgpu_ctx* c, const double* d_params, int batch, bool 
     // four quarter-width CTAs per SM: with ~5 ops between a tile's load and its store, more independent CTAs in different
     // phases are what overlaps the HBM round trips with the tensor work (measured: +12 % energy, +7 % gradient over two)
     const FusedPlan pf = plan_fused(c, MODE_APPLY, wr, wc, std::min(slice, batch), 4, true);
-    // backward segments: ONE 512-thread CTA per SM with a two-column tile (measured on C5: 55 ms per 64 sets against 65 ms for
-    // two 256-thread CTAs with single-column tiles, whose layout conflicts more and whose HBM accesses are 16 B wide)
-    const FusedPlan pb = with_grad ? plan_fused(c, MODE_BWD, wr, wc, std::min(slice, batch), 1) : pf;
+    // backward segments: two 256-thread CTAs per SM with single-column tiles (a + beta: 64 KB each). With the tiles loaded by
+    // asynchronous copies and dealt round robin (neighbouring tiles in flight together), two CTAs in different phases beat ONE
+    // 512-thread CTA with a two-column tile: 46.7 against 51.7 ms per 64 sets on C5 (profiles/r2_variants_win2.jsonl; round 1
+    // had it the other way round with register-staged loads)
+    const FusedPlan pb = with_grad ? plan_fused(c, MODE_BWD, wr, wc, std::min(slice, batch), 2) : pf;
     if (!pf.ok || !pb.ok) return 1;
     const int nblk = std::min(c->sm_count * 8, std::max(1, rows / 512));
     if ((rc = c->wMat.ensure((size_t)2 * slice * rows * sizeof(cplx)))) return rc;
