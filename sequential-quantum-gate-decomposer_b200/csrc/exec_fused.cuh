@@ -84,6 +84,7 @@ struct ExecArgs {
     int w_direct;            // (not w_in_smem) 1: one slice of w_part per (parameter set, CTA, warp), written by that warp alone
     int dense_stage;         // complex elements of kernel staging for the generic dense path (0: none)
     int wmax;                // max dim*dim over parametric ops (complex), >= 4
+    int dbuf;                // window forward segments: two tile buffers, the next tile streams in while this one is computed
 };
 
 static const int FUSED_THREADS = 512;
@@ -305,11 +306,14 @@ static const int B0TAB = 64;  // batch bases precomputed per op (tiles with more
 // Complex arithmetic of the 3-qubit blocks on the tensor cores (compile-time switch):
 //   0: the real embedding -- an 8 x 8 complex block is a 16 x 16 real matrix, 8 DMMA per 8 items forward, 24 backward;
 //   1 (default): three real products per complex product ("3M": with K = C + iD and x = u + iv,
-//      t1 = C u, t2 = D v, t3 = (C + D)(u + v);  Re = t1 - t2,  Im = t3 - t1 - t2), each an 8 x 8 real matrix-vector product =
-//      2 DMMA per 8 items: 6 DMMA forward, 18 backward (K^dagger p, K^T beta and the W' outer products each drop from 8 to 6),
-//      plus 8 / 20 DADD for the sums and differences -- 12-15 % fewer FP64-pipe cycles, and 6 / 12 kernel-fragment registers
-//      instead of 16 / 32. The rounding differs from the 4-product form by O(eps) per product (normwise; the parity tests hold
-//      the 1e-12 / 1e-10 bars for both settings).
+//      k1 = C (u + v),  Re = k1 - (C + D) v,  Im = k1 + (D - C) u), each an 8 x 8 real matrix-vector product = 2 DMMA per 8
+//      items: 6 DMMA forward, 18 backward (K^dagger p, K^T beta and the W' outer products each drop from 8 to 6). The second
+//      and third product accumulate on top of register copies of k1 (the DMMA's addend; the table holds C, D - C and -(C + D)),
+//      so the only FP64 additions left are the operand sums u + v: 2 / 8 DADD per batch instead of the 8 / 20 of the first 3M
+//      form (t1 = C u, t2 = D v, t3 = (C + D)(u + v), Re = t1 - t2, Im = t3 - t1 - t2), whose DADDs held 30 % of the warp
+//      samples of the gradient kernel and ~20 % of its FP64-pipe cycles (DADD and DMMA share one pipe,
+//      profiles/r2_dmma_dadd_mix.txt). 6 / 12 kernel-fragment registers instead of 16 / 32. The rounding differs from the
+//      4-product form by O(eps) per product (normwise; the parity tests hold the 1e-12 / 1e-10 bars for both settings).
 #ifndef SQ_BLOCK_3M
 #define SQ_BLOCK_3M 1
 #endif
@@ -320,6 +324,15 @@ static const int B0TAB = 64;  // batch bases precomputed per op (tiles with more
 // switch with its measurement; not the product configuration.
 #ifndef SQ_TAB_BULK
 #define SQ_TAB_BULK 0
+#endif
+// Window modes only: 1: the op tables use the bulk-async / mbarrier ring there, which frees the cp.async groups for a
+// double-buffered tile pipeline in the forward segments (two single-column tile buffers, tile t + 1 requested before tile t is
+// computed: option async_tiles). Measured on C5 (profiles/r2_variants_win3.jsonl): forward sweep 20.2 ms per 64 sets against
+// 17.6 ms for the default -- the mbarrier polls cost 6.7 % of the warp samples (profiles/r2_ncu_vqe_window_src.md), the
+// narrower tiles conflict more, and the tile round trips it hides were not the limiter: 73-79 % of the samples sit inside the
+// DMMA loops, which run the FP64 pipe at ~80 %. 0 (default): LDGSTS ring, one tile buffer, whole tile requested at once.
+#ifndef SQ_WIN_BULK
+#define SQ_WIN_BULK 0
 #endif
 // 1: the per-lane operands of the next DMMA block op (BlkPre) are loaded BEFORE the end-of-op barrier of the current one, which
 // needs the next op's table one barrier earlier (tables are waited for two ops ahead instead of one); 0 (default): after the
@@ -410,7 +423,7 @@ __device__ __forceinline__ void fill_optab(OpTab* T, const DevOp& op, const cplx
         const int ju = s_choice[0], pa = s_choice[1];
 #if SQ_BLOCK_3M
         // frag[mode][m * 2 + s][lane]: B-operand fragment (lane = (k = lane & 3, n = lane >> 2)) of k-step s of the REAL 8 x 8
-        // matrix m in {0: C, 1: D, 2: C + D} of the mode's kernel C + iD (mode 0: K, 1: K^dagger, 2: K^T):
+        // matrix m in {0: C, 1: D - C, 2: -(C + D)} of the mode's kernel C + iD (mode 0: K, 1: K^dagger, 2: K^T):
         // entry [out amplitude o(n)][in amplitude c(4 s + k)] with o(n) = dep3(n >> 1, n & 1), c(4 s + k) = dep3(k, s) -- the
         // lane's two inputs c(j), c(4 + j) are its two outputs o(2 j), o(2 j + 1): loads and stores hit the same elements
         for (int e = tid; e < 3 * 6 * 32; e += nthr) {
@@ -419,7 +432,7 @@ __device__ __forceinline__ void fill_optab(OpTab* T, const DevOp& op, const cplx
             const int ao = dep3(n >> 1, n & 1, ju), ai = dep3(k, st, ju);
             const cplx kv = (mode == 0) ? K[ao * 8 + ai] : K[ai * 8 + ao];
             const double cre = kv.x, dim_ = (mode == 1) ? -kv.y : kv.y;
-            T->frag[mode][ms][lane] = (m == 0) ? cre : (m == 1 ? dim_ : cre + dim_);
+            T->frag[mode][ms][lane] = (m == 0) ? cre : (m == 1 ? dim_ - cre : -(cre + dim_));
         }
 #else
         for (int e = tid; e < 3 * 8 * 32; e += nthr) {
@@ -550,8 +563,10 @@ __device__ __forceinline__ void blk_for_batches(const BlkPre& R, const OpTabS* T
 }
 
 // forward: x <- K x for every group of the tile. One warp handles 8 (group, column) items per step.
-template <int LOG_CT, int KQ>
-__device__ __forceinline__ void block_dmma_forward(cplx* sa, const OpTabS* T, BlkPre& R, int q0, int q1, int q2, int rows, int tid, int nthr) {
+// GST: the results are written to the state in HBM (gdst[sglob[slot]], window segments' last op) instead of the tile.
+template <int LOG_CT, int KQ, bool GST>
+__device__ __forceinline__ void block_dmma_forward(cplx* sa, const OpTabS* T, BlkPre& R, int q0, int q1, int q2, int rows, int tid, int nthr,
+                                                   cplx* __restrict__ gdst, const int* sglob) {
     constexpr int NT = (KQ == 3) ? 2 : 1;
     constexpr bool M3 = (KQ == 3) && (SQ_BLOCK_3M != 0);
     const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
@@ -565,17 +580,19 @@ __device__ __forceinline__ void block_dmma_forward(cplx* sa, const OpTabS* T, Bl
             d[u] = czero();
         }
         if (M3) {
-            // t1 = C u, t2 = D v, t3 = (C + D)(u + v) over the two k-steps; the D fragment pair holds outputs o(2j), o(2j+1),
-            // which are the amplitudes the lane loaded as x[0], x[1]
-            double t1[2] = {0.0, 0.0}, t2[2] = {0.0, 0.0}, t3[2] = {0.0, 0.0};
-            dmma_m8n8k4(t1[0], t1[1], x[0].x, R.kd[0][0]);
-            dmma_m8n8k4(t2[0], t2[1], x[0].y, R.kd[0][2]);
-            dmma_m8n8k4(t3[0], t3[1], x[0].x + x[0].y, R.kd[NT - 1][0]);
-            dmma_m8n8k4(t1[0], t1[1], x[NT - 1].x, R.kd[0][1]);
-            dmma_m8n8k4(t2[0], t2[1], x[NT - 1].y, R.kd[0][3]);
-            dmma_m8n8k4(t3[0], t3[1], x[NT - 1].x + x[NT - 1].y, R.kd[NT - 1][1]);
-            d[0] = cmake(t1[0] - t2[0], t3[0] - t1[0] - t2[0]);
-            d[NT - 1] = cmake(t1[1] - t2[1], t3[1] - t1[1] - t2[1]);
+            // k1 = C (u + v) over the two k-steps, then Re = k1 - (C + D) v and Im = k1 + (D - C) u accumulate ON TOP of copies of
+            // k1 (the DMMA's addend): no additions after the products. The D fragment pair holds outputs o(2j), o(2j+1), which
+            // are the amplitudes the lane loaded as x[0], x[1].
+            double k1[2] = {0.0, 0.0};
+            dmma_m8n8k4(k1[0], k1[1], x[0].x + x[0].y, R.kd[0][0]);
+            dmma_m8n8k4(k1[0], k1[1], x[NT - 1].x + x[NT - 1].y, R.kd[0][1]);
+            double re[2] = {k1[0], k1[1]}, im[2] = {k1[0], k1[1]};
+            dmma_m8n8k4(re[0], re[1], x[0].y, R.kd[NT - 1][0]);
+            dmma_m8n8k4(im[0], im[1], x[0].x, R.kd[0][2]);
+            dmma_m8n8k4(re[0], re[1], x[NT - 1].y, R.kd[NT - 1][1]);
+            dmma_m8n8k4(im[0], im[1], x[NT - 1].x, R.kd[0][3]);
+            d[0] = cmake(re[0], im[0]);
+            d[NT - 1] = cmake(re[1], im[1]);
         } else {
 #pragma unroll
             for (int u = 0; u < NT; ++u)
@@ -586,16 +603,20 @@ __device__ __forceinline__ void block_dmma_forward(cplx* sa, const OpTabS* T, Bl
                 }
         }
 #pragma unroll
-        for (int t = 0; t < NT; ++t) sa[B0 ^ R.sl[t]] = d[t];
+        for (int t = 0; t < NT; ++t) {
+            if (GST) gdst[(size_t)(unsigned)sglob[B0 ^ R.sl[t]]] = d[t];
+            else sa[B0 ^ R.sl[t]] = d[t];
+        }
     });
     R.ok = false;
 }
 
 // backward step of the adjoint sweep: W' += beta p^T (outer product over items), a <- K^dagger p, beta <- K^T beta, all on
 // DMMA; the warp's W' (DIM x DIM complex) is written to wslot after the loop.
-template <int LOG_CT, int KQ>
+template <int LOG_CT, int KQ, bool GST>
 __device__ __forceinline__ void block_dmma_backward(cplx* sa, cplx* sb, const OpTabS* T, BlkPre& R, int q0, int q1, int q2, int rows,
-                                                    bool has_w, cplx* wslot, bool wdirect, int tid, int nthr) {
+                                                    bool has_w, cplx* wslot, bool wdirect, int tid, int nthr,
+                                                    cplx* __restrict__ ga, cplx* __restrict__ gb, const int* sglob) {
     constexpr int DIM = 1 << KQ, NT = (KQ == 3) ? 2 : 1;
     constexpr bool M3 = (KQ == 3) && (SQ_BLOCK_3M != 0);
     const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
@@ -645,21 +666,28 @@ __device__ __forceinline__ void block_dmma_backward(cplx* sa, cplx* sb, const Op
             }
         }
         if (M3) {
-            double a1[2] = {0.0, 0.0}, a2[2] = {0.0, 0.0}, a3[2] = {0.0, 0.0}, b1[2] = {0.0, 0.0}, b2[2] = {0.0, 0.0}, b3[2] = {0.0, 0.0};
+            // as in the forward step: k1 = C (u + v), Re = k1 - (C + D) v, Im = k1 + (D - C) u, for a <- K^dagger p (fragments kd)
+            // and beta <- K^T beta (fragments kt), the two chains interleaved
+            double ka[2] = {0.0, 0.0}, kb[2] = {0.0, 0.0};
 #pragma unroll
             for (int st = 0; st < 2; ++st) {
                 const cplx pp = p[st == 0 ? 0 : NT - 1], bb = be[st == 0 ? 0 : NT - 1];
-                dmma_m8n8k4(a1[0], a1[1], pp.x, R.kd[0][st]);
-                dmma_m8n8k4(b1[0], b1[1], bb.x, R.kt[0][st]);
-                dmma_m8n8k4(a2[0], a2[1], pp.y, R.kd[0][2 + st]);
-                dmma_m8n8k4(b2[0], b2[1], bb.y, R.kt[0][2 + st]);
-                dmma_m8n8k4(a3[0], a3[1], pp.x + pp.y, R.kd[NT - 1][st]);
-                dmma_m8n8k4(b3[0], b3[1], bb.x + bb.y, R.kt[NT - 1][st]);
+                dmma_m8n8k4(ka[0], ka[1], pp.x + pp.y, R.kd[0][st]);
+                dmma_m8n8k4(kb[0], kb[1], bb.x + bb.y, R.kt[0][st]);
             }
-            da[0] = cmake(a1[0] - a2[0], a3[0] - a1[0] - a2[0]);
-            da[NT - 1] = cmake(a1[1] - a2[1], a3[1] - a1[1] - a2[1]);
-            db[0] = cmake(b1[0] - b2[0], b3[0] - b1[0] - b2[0]);
-            db[NT - 1] = cmake(b1[1] - b2[1], b3[1] - b1[1] - b2[1]);
+            double are[2] = {ka[0], ka[1]}, aim[2] = {ka[0], ka[1]}, bre[2] = {kb[0], kb[1]}, bim[2] = {kb[0], kb[1]};
+#pragma unroll
+            for (int st = 0; st < 2; ++st) {
+                const cplx pp = p[st == 0 ? 0 : NT - 1], bb = be[st == 0 ? 0 : NT - 1];
+                dmma_m8n8k4(are[0], are[1], pp.y, R.kd[NT - 1][st]);
+                dmma_m8n8k4(bre[0], bre[1], bb.y, R.kt[NT - 1][st]);
+                dmma_m8n8k4(aim[0], aim[1], pp.x, R.kd[0][2 + st]);
+                dmma_m8n8k4(bim[0], bim[1], bb.x, R.kt[0][2 + st]);
+            }
+            da[0] = cmake(are[0], aim[0]);
+            da[NT - 1] = cmake(are[1], aim[1]);
+            db[0] = cmake(bre[0], bim[0]);
+            db[NT - 1] = cmake(bre[1], bim[1]);
         } else {
 #pragma unroll
             for (int u = 0; u < NT; ++u)
@@ -674,8 +702,14 @@ __device__ __forceinline__ void block_dmma_backward(cplx* sa, cplx* sb, const Op
         if (has_w) __syncwarp();  // the W' operands (other lanes' elements) are read before anybody overwrites them
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
-            sa[B0 ^ R.sl[t]] = da[t];
-            sb[B0 ^ R.sl[t]] = db[t];
+            if (GST) {
+                const size_t off = (size_t)(unsigned)sglob[B0 ^ R.sl[t]];
+                ga[off] = da[t];
+                gb[off] = db[t];
+            } else {
+                sa[B0 ^ R.sl[t]] = da[t];
+                sb[B0 ^ R.sl[t]] = db[t];
+            }
         }
     });
     if (has_w) {
@@ -943,7 +977,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
     cplx* sa = reinterpret_cast<cplx*>(smem_raw);
     constexpr bool HAS_B = (MODE == MODE_GRAD || MODE == MODE_BWD);
     constexpr bool WIN = (MODE == MODE_APPLY || MODE == MODE_BWD);  // window mode is compiled only where it is used
-    cplx* sb = sa + (size_t)rows * CT;                                   // the row functional beta (HAS_B only)
+    const bool dbuf = (MODE == MODE_APPLY) && A.dbuf && A.wmask;        // two tile buffers (window forward segments)
+    cplx* const sa0 = sa;
+    cplx* sb = sa + (size_t)rows * CT * (dbuf ? 2 : 1);                  // the row functional beta (HAS_B only)
     cplx* sk = HAS_B ? sb + (size_t)rows * CT : sb;                       // raw dense kernel staging
     OpTabS* stab = reinterpret_cast<OpTabS*>(sk + A.dense_stage);         // [TAB_RING] DMMA block lookup tables (one sweep direction);
                                                                           // the 2 x 2 kernel of a single-qubit block travels in the same ring
@@ -954,7 +990,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
     double* sred = reinterpret_cast<double*>(swacc + ((HAS_B && A.w_in_smem) ? A.w_total : 0));  // [nwarps][6]
     double* stsum = sred + nwarps * 6;                                   // [6] running trace sums of this CTA over its tiles
     SOp* sops = reinterpret_cast<SOp*>(stsum + 6);                       // [n_ops]
-    int* srowpart = reinterpret_cast<int*>(sops + A.n_ops);              // window mode: [rows] deposit(r, wmask)
+    int* sglob = reinterpret_cast<int*>(sops + A.n_ops);                 // window mode: [rows * CT] element offset in the state of the
+                                                                         // amplitude stored in shared-memory slot e (elem() order)
 
     const int chunk = blockIdx.x;
     const int nchunks = gridDim.x;
@@ -1012,17 +1049,23 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
     if (HAS_B && A.w_in_smem) {
         for (int e = tid; e < A.w_total; e += nthr) swacc[e] = czero();
     }
-    int* scolpart = srowpart + rows;                                     // window mode: [8] deposit(c, ~wmask) of the tile's column offsets
     if (WIN && A.wmask) {
-        // deposit(r, wmask) = deposit(r & 63, wmask) | deposit(r & ~63, wmask): two small tables (built with the software PDEP
-        // loop by 64 + rows / 64 threads, in the not yet loaded tile area) instead of one loop per row
+        // offset of (row r, tile column c) = deposit(r, wmask) | deposit(c, ~wmask); deposit(r) = deposit(r & 63) | deposit(r & ~63):
+        // two small tables (built with the software PDEP loop by 64 + rows / 64 threads, in the not yet loaded tile area),
+        // then one scatter into slot order -- the tile loads, the stores and the fused store of a segment's last op all index
+        // by shared-memory slot
         int* slo = reinterpret_cast<int*>(sa);
         int* shi = slo + 64;
-        for (int t = tid; t < 64 + (rows >> 6); t += nthr)
+        int* scol = shi + max(rows >> 6, 1);
+        for (int t = tid; t < 64 + max(rows >> 6, 1); t += nthr)
             slo[t] = (int)deposit_bits(t < 64 ? (unsigned)t : (unsigned)(t - 64) << 6, A.wmask);
-        if (tid < 8) scolpart[tid] = (int)deposit_bits((unsigned)tid, ~A.wmask);
+        if (tid < CT) scol[tid] = (int)deposit_bits((unsigned)tid, ~A.wmask);
         __syncthreads();
-        for (int r = tid; r < rows; r += nthr) srowpart[r] = slo[r & 63] | ((r >> 6) ? shi[r >> 6] : 0);
+        for (int e = tid; e < rows * CT; e += nthr) {
+            const int r = e >> LOG_CT, cc = e & (CT - 1);
+            sglob[elem<LOG_CT>(r, cc)] = slo[r & 63] | shi[r >> 6] | scol[cc];
+        }
+        __syncthreads();
     }
     if (tid < 6) stsum[tid] = 0.0;
     __syncthreads();
@@ -1039,37 +1082,67 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
     // mbarrier (expect_tx / complete_tx), which every thread waits on (tab_acquire) right before it reads the table. Tables
     // are requested TAB_RING - 1 ops ahead; a slot is rewritten only after the end-of-op barrier of its previous user.
     const OpTab* __restrict__ gtabs = A.optabs + (size_t)kset * (A.optab_stride ? A.optab_stride : A.n_ops);
-#if SQ_TAB_BULK
-    if (tid == 0) {
+    // The ring comes in two flavours. TAB_BULK (window modes, or -DSQ_TAB_BULK=1): ONE thread requests a table with two
+    // bulk-async copies (cp.async.bulk, the TMA engine; UBLKCP in SASS) and every thread waits on the slot's mbarrier right
+    // before the op -- this leaves the per-thread cp.async groups to the TILE pipeline of the window modes, whose prefetch of the
+    // next tile must stay in flight across several ops. Otherwise (cost / gradient over a resident matrix): per-thread cp.async
+    // (LDGSTS) copies, one commit group per op, 2 % faster on C3 (profiles/r2_variants.jsonl) because no mbarrier try_wait sits
+    // on every warp's path once per op.
+    constexpr bool TAB_BULK = (SQ_TAB_BULK != 0) || ((SQ_WIN_BULK != 0) && WIN);
+    if (TAB_BULK && tid == 0) {
         for (int i = 0; i < TAB_RING; ++i)
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(tbar + i)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (TAB_BULK) __syncthreads();  // nobody polls a barrier before it is initialised
     unsigned tab_parity = 0;  // bit s: phase parity the next wait on ring slot s expects (identical in every thread)
     auto tab_prefetch = [&](int k, bool bwd) {
-        if (tid != 0 || k < 0 || k >= A.n_ops || sops[k].kind == 1) return;
-        const char* src = reinterpret_cast<const char*>(gtabs + k);
-        const int slot = k & (TAB_RING - 1);
-        const unsigned dst = (unsigned)__cvta_generic_to_shared(stab + slot);
-        const unsigned bar = (unsigned)__cvta_generic_to_shared(tbar + slot);
-        if (sops[k].kind == 0) {
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(64) : "memory");
+        constexpr int FRAG = 8 * 32 * 8, TAIL = (int)(sizeof(OpTabS) - 2 * FRAG);  // bytes of one fragment set / of slots + widx + b0
+        if (TAB_BULK) {
+            if (tid != 0 || k < 0 || k >= A.n_ops || sops[k].kind == 1) return;
+            const char* src = reinterpret_cast<const char*>(gtabs + k);
+            const int slot = k & (TAB_RING - 1);
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(stab + slot);
+            const unsigned bar = (unsigned)__cvta_generic_to_shared(tbar + slot);
+            if (sops[k].kind == 0) {
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(64) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                             "l"(kernel_of(k)), "r"(64), "r"(bar)
+                             : "memory");
+                return;
+            }
+            const int nfrag = bwd ? 2 * FRAG : FRAG, src_off = bwd ? FRAG : 0;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(nfrag + TAIL) : "memory");
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                         "l"(kernel_of(k)), "r"(64), "r"(bar)
+                         "l"(src + src_off), "r"(nfrag), "r"(bar)
+                         : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + 2 * FRAG),
+                         "l"(src + 3 * FRAG), "r"(TAIL), "r"(bar)
                          : "memory");
             return;
         }
-        constexpr int FRAG = 8 * 32 * 8, TAIL = (int)(sizeof(OpTabS) - 2 * FRAG);  // bytes of one fragment set / of slots + widx + b0
-        const int nfrag = bwd ? 2 * FRAG : FRAG, src_off = bwd ? FRAG : 0;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(nfrag + TAIL) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                     "l"(src + src_off), "r"(nfrag), "r"(bar)
-                     : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + 2 * FRAG),
-                     "l"(src + 3 * FRAG), "r"(TAIL), "r"(bar)
-                     : "memory");
+        // per-thread cp.async (LDGSTS) copies, one commit group per op in sweep order (empty for ops without a table): when an
+        // op ends, "at most TAB_RING - 2 groups pending" means the NEXT op's table has landed; the end-of-op barrier publishes
+        // it. With SQ_PRELOAD the operands of the next op are read BEFORE that barrier, so tables are waited for one op
+        // earlier ("at most TAB_RING - 3 pending") and every table is published by the barrier one op before its first reader.
+        if (!(k < 0 || k >= A.n_ops || sops[k].kind == 1)) {
+            const char* src = reinterpret_cast<const char*>(gtabs + k);
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(stab + (k & (TAB_RING - 1)));
+            if (sops[k].kind == 0) {
+                if (tid < 4) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * tid), "l"(kernel_of(k) + tid));
+            } else {
+                const int nfrag = bwd ? 2 * FRAG : FRAG, src_off = bwd ? FRAG : 0;
+                for (int e = tid; e < (nfrag + TAIL) / 16; e += nthr) {
+                    const int b = e * 16;
+                    const int d_off = (b < nfrag) ? b : 2 * FRAG + (b - nfrag);
+                    const int s_off = (b < nfrag) ? src_off + b : 3 * FRAG + (b - nfrag);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + d_off), "l"(src + s_off));
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    auto tab_acquire = [&](int k) {  // the table of op k (if it has one) has landed in its ring slot
+    auto tab_acquire = [&](int k) {  // bulk ring: the table of op k (if it has one) has landed in its ring slot
         if (k < 0 || k >= A.n_ops || sops[k].kind == 1) return;
         const int slot = k & (TAB_RING - 1);
         const unsigned bar = (unsigned)__cvta_generic_to_shared(tbar + slot);
@@ -1081,80 +1154,66 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
         } while (!done);
         tab_parity ^= 1u << slot;
     };
-    // the wait for the NEXT op's table sits in front of the end-of-op barrier, where its latency overlaps the wait for the
-    // slowest warp (the table was requested TAB_RING - 1 ops ago and has long landed)
-    auto tab_ready = [&](int next_k) { tab_acquire(next_k); };  // before the next op's operands are read (any thread, no barrier needed)
-    auto tab_end_of_op = [&]() {};
+    // bulk ring: the wait for the NEXT op's table sits in front of the end-of-op barrier, where its latency overlaps the wait
+    // for the slowest warp (the table was requested TAB_RING - 1 ops ago and has long landed)
+    auto tab_ready = [&](int next_k) {
+        if (TAB_BULK) tab_acquire(next_k);
+    };
+    auto tab_end_of_op = [&]() {
+        if (!TAB_BULK) asm volatile("cp.async.wait_group %0;" ::"n"(TAB_RING - 2 - (SQ_PRELOAD ? 1 : 0)) : "memory");
+    };
     auto tab_prime = [&](int first, int step, bool bwd) {  // requests for the first TAB_RING - 1 ops of a sweep
 #pragma unroll
         for (int j = 0; j < TAB_RING - 1; ++j) tab_prefetch(first + j * step, bwd);
-        tab_acquire(first);
+        if (TAB_BULK) tab_acquire(first);
+        else tab_end_of_op();
     };
-#else
-    // per-thread cp.async (LDGSTS) copies, one commit group per op in sweep order (empty for ops without a table): when an op
-    // ends, "at most TAB_RING - 2 groups pending" means the NEXT op's table has landed; the end-of-op barrier publishes it.
-    // With SQ_PRELOAD the operands of the next op are read BEFORE that barrier, so tables are waited for one op earlier
-    // ("at most TAB_RING - 3 pending": the table of the op after the next has landed) and every table is published by the
-    // barrier one op before its first reader.
-    auto tab_prefetch_raw = [&](int k, bool bwd) {
-        if (k < 0 || k >= A.n_ops || sops[k].kind == 1) return;
-        const char* src = reinterpret_cast<const char*>(gtabs + k);
-        const unsigned dst = (unsigned)__cvta_generic_to_shared(stab + (k & (TAB_RING - 1)));
-        if (sops[k].kind == 0) {
-            if (tid < 4) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * tid), "l"(kernel_of(k) + tid));
-            return;
+
+    // Window mode, tile pipeline: every element of a tile travels as one 16 B asynchronous copy (LDGSTS) straight into its
+    // swizzled shared-memory slot -- no staging registers, so the WHOLE tile is in flight at once (the state comes from HBM /
+    // L2: a register-staged gather is latency-bound) -- as one cp.async group per tile (the op tables use the mbarrier ring in
+    // these modes, so the groups belong to the tiles alone). Forward segments with two tile buffers (A.dbuf) request tile
+    // t + 1 before they start on tile t; the last op of a segment writes its results straight to the state in HBM
+    // (block_dmma_forward / block_dmma_backward with GST), so a tile has no separate store phase either.
+    auto tile_request = [&](int t, cplx* bufa) {
+        const size_t colbase = (size_t)y * A.in_ystride + deposit_bits((unsigned)(t * CT), ~A.wmask);
+        const cplx* __restrict__ src = (MODE == MODE_BWD ? A.out : A.in) + colbase;
+        const cplx* __restrict__ srcb = (MODE == MODE_BWD) ? A.beta + colbase : nullptr;
+        for (int e = tid; e < rows * CT; e += nthr) {
+            const size_t off = (size_t)(unsigned)sglob[e];
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(bufa + e)), "l"(src + off));
+            if (MODE == MODE_BWD)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(sb + e)), "l"(srcb + off));
         }
-        constexpr int FRAG = 8 * 32 * 8, TAIL = (int)(sizeof(OpTabS) - 2 * FRAG);
-        const int nfrag = bwd ? 2 * FRAG : FRAG, src_off = bwd ? FRAG : 0;
-        for (int e = tid; e < (nfrag + TAIL) / 16; e += nthr) {
-            const int b = e * 16;
-            const int d_off = (b < nfrag) ? b : 2 * FRAG + (b - nfrag);
-            const int s_off = (b < nfrag) ? src_off + b : 3 * FRAG + (b - nfrag);
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + d_off), "l"(src + s_off));
-        }
-    };
-    auto tab_prefetch = [&](int k, bool bwd) {
-        tab_prefetch_raw(k, bwd);
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    auto tab_ready = [&](int) {};
-    auto tab_end_of_op = [&]() { asm volatile("cp.async.wait_group %0;" ::"n"(TAB_RING - 2 - (SQ_PRELOAD ? 1 : 0)) : "memory"); };
-    auto tab_prime = [&](int first, int step, bool bwd) {
-#pragma unroll
-        for (int j = 0; j < TAB_RING - 1; ++j) tab_prefetch(first + j * step, bwd);
-        tab_end_of_op();
-    };
-#endif
+    auto tile_of = [&](int ti) { return (WIN && A.wmask) ? ti * nchunks + chunk : chunk * A.tiles_per_cta + ti; };
+    if (WIN && dbuf && A.tiles_per_cta > 0 && tile_of(0) < A.tiles) tile_request(tile_of(0), sa0);
 
     for (int ti = 0; ti < A.tiles_per_cta; ++ti) {
         // window mode deals the tiles round robin: the CTAs of a wave then work on neighbouring tiles at the same time, and the
         // 32 B / 64 B pieces of one DRAM burst that belong to different tiles meet in L2 instead of being fetched twice
-        const int tile = (WIN && A.wmask) ? ti * nchunks + chunk : chunk * A.tiles_per_cta + ti;
+        const int tile = tile_of(ti);
         if (tile >= A.tiles) break;
         const int j0 = tile * CT;
         const int valid = min(CT, A.cols - j0);
 
         // ---- load the tile ------------------------------------------------------------------------------------
         {
-            bool win_loaded = false;
+            const int first_op = (MODE == MODE_BWD) ? A.n_ops - 1 : 0;
             if (WIN && A.wmask) {
-                // window mode: the tile's columns are CT consecutive values of the non-window bits
-                const size_t colbase = (size_t)y * A.in_ystride + deposit_bits((unsigned)j0, ~A.wmask);
-                const cplx* __restrict__ src = (MODE == MODE_BWD ? A.out : A.in) + colbase;
-                const cplx* __restrict__ srcb = (MODE == MODE_BWD) ? A.beta + colbase : nullptr;
-                // every element travels as one 16 B asynchronous copy (LDGSTS) straight into its swizzled shared-memory slot: no
-                // staging registers, so the WHOLE tile is in flight at once (the state comes from HBM / L2: the gather is
-                // latency-bound otherwise) -- committed as one cp.async group ahead of the op tables of this tile
-                for (int e = tid; e < rows * CT; e += nthr) {
-                    const int r = e >> LOG_CT, cc = e & (CT - 1);
-                    const size_t off = (size_t)(unsigned)(srowpart[r] | scolpart[cc]);
-                    const int se = elem<LOG_CT>(r, cc);
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(sa + se)), "l"(src + off));
-                    if (MODE == MODE_BWD)
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(sb + se)), "l"(srcb + off));
+                if (dbuf) {
+                    sa = sa0 + (size_t)(ti & 1) * rows * CT;
+                    const bool more = ti + 1 < A.tiles_per_cta && tile_of(ti + 1) < A.tiles;
+                    if (more) tile_request(tile_of(ti + 1), sa0 + (size_t)((ti + 1) & 1) * rows * CT);
+                    if (A.n_ops > 0) tab_prime(first_op, 1, false);
+                    if (more) asm volatile("cp.async.wait_group 1;" ::: "memory");
+                    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+                } else {
+                    tile_request(tile, sa);
+                    if (A.n_ops > 0) tab_prime(first_op, MODE == MODE_BWD ? -1 : 1, MODE == MODE_BWD);
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
                 }
-                asm volatile("cp.async.commit_group;" ::: "memory");
-                win_loaded = true;
             } else {
                 const cplx* __restrict__ src = A.in + (size_t)y * A.in_ystride + j0;
                 for (int e = tid; e < rows * CT; e += nthr) {
@@ -1163,14 +1222,19 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                     if (c < valid) v = src[(size_t)i * A.ld_in + c];
                     sa[elem<LOG_CT>(i, c)] = v;
                 }
+                if (A.n_ops > 0) tab_prime(first_op, MODE == MODE_BWD ? -1 : 1, MODE == MODE_BWD);
             }
-            const int first_op = (MODE == MODE_BWD) ? A.n_ops - 1 : 0;
-            if (A.n_ops > 0) tab_prime(first_op, MODE == MODE_BWD ? -1 : 1, MODE == MODE_BWD);
-            // the tile's group is older than the table groups tab_prime leaves pending; without tables (or with the bulk ring,
-            // which does not use groups) wait for it explicitly
-            if (win_loaded && (A.n_ops == 0 || SQ_TAB_BULK)) asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncthreads();
+        // window mode: the state in HBM that the last op of the segment writes to (fused store)
+        cplx* __restrict__ gst_a = nullptr;
+        cplx* __restrict__ gst_b = nullptr;
+        if (WIN && A.wmask) {
+            const size_t colbase = (size_t)y * A.out_ystride + deposit_bits((unsigned)j0, ~A.wmask);
+            gst_a = A.out + colbase;
+            if (MODE == MODE_BWD) gst_b = A.beta + colbase;
+        }
+        bool stored = false;
 
         // ---- forward sweep: op 0 first (Gates_block.cpp:683) ---------------------------------------------------
         BlkPre R;  // operands of the next DMMA block op, loaded ahead of the barrier (SQ_PRELOAD)
@@ -1182,8 +1246,18 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
             const cplx* __restrict__ km = reinterpret_cast<const cplx*>(stab + (k & (TAB_RING - 1)));
             SQ_TRACE_MARK(0)
             if (s.kind == 2) {
-                if (s.dim == 8) block_dmma_forward<LOG_CT, 3>(sa, stab + (k & (TAB_RING - 1)), R, s.q0, s.q1, s.q2, rows, tid, nthr);
-                else block_dmma_forward<LOG_CT, 2>(sa, stab + (k & (TAB_RING - 1)), R, s.q0, s.q1, 30, rows, tid, nthr);
+                bool fused = false;
+                if constexpr (MODE == MODE_APPLY) {
+                    if (gst_a && k == A.n_ops - 1) {  // last op of a window segment: results go straight to the state in HBM
+                        if (s.dim == 8) block_dmma_forward<LOG_CT, 3, true>(sa, stab + (k & (TAB_RING - 1)), R, s.q0, s.q1, s.q2, rows, tid, nthr, gst_a, sglob);
+                        else block_dmma_forward<LOG_CT, 2, true>(sa, stab + (k & (TAB_RING - 1)), R, s.q0, s.q1, 30, rows, tid, nthr, gst_a, sglob);
+                        fused = stored = true;
+                    }
+                }
+                if (!fused) {
+                    if (s.dim == 8) block_dmma_forward<LOG_CT, 3, false>(sa, stab + (k & (TAB_RING - 1)), R, s.q0, s.q1, s.q2, rows, tid, nthr, nullptr, nullptr);
+                    else block_dmma_forward<LOG_CT, 2, false>(sa, stab + (k & (TAB_RING - 1)), R, s.q0, s.q1, 30, rows, tid, nthr, nullptr, nullptr);
+                }
             } else if (s.kind == 0) {
                 const cplx k00 = km[0], k01 = km[1], k10 = km[2], k11 = km[3];
                 const int tbit = 1 << s.q0;
@@ -1312,11 +1386,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
 
         if (MODE == MODE_APPLY) {
             if (WIN && A.wmask) {
-                cplx* __restrict__ dst = A.out + (size_t)y * A.out_ystride + deposit_bits((unsigned)j0, ~A.wmask);
-                for (int e = tid; e < rows * CT; e += nthr) {
-                    const int i = e >> LOG_CT, c = e & (CT - 1);
-                    dst[(size_t)(unsigned)(srowpart[i] | scolpart[c])] = sa[elem<LOG_CT>(i, c)];
-                }
+                if (stored) continue;  // the segment's last op wrote the tile (its end-of-op barrier frees the buffer)
+                for (int e = tid; e < rows * CT; e += nthr) gst_a[(size_t)(unsigned)sglob[e]] = sa[e];
             } else {
                 cplx* __restrict__ dst = A.out + (size_t)y * A.out_ystride + j0;
                 for (int e = tid; e < rows * CT; e += nthr) {
@@ -1438,8 +1509,18 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                 int wdim = s.dim;
                 SQ_TRACE_MARK(0)
                 if (s.kind == 2) {
-                    if (s.dim == 8) block_dmma_backward<LOG_CT, 3>(sa, sb, stab + (k & (TAB_RING - 1)), R, s.q0, s.q1, s.q2, rows, has_w, wslot_c, wdirect, tid, nthr);
-                    else block_dmma_backward<LOG_CT, 2>(sa, sb, stab + (k & (TAB_RING - 1)), R, s.q0, s.q1, 30, rows, has_w, wslot_c, wdirect, tid, nthr);
+                    bool fused = false;
+                    if constexpr (MODE == MODE_BWD) {
+                        if (gst_a && k == 0) {  // last op of the segment's backward sweep: a and beta go straight to HBM
+                            if (s.dim == 8) block_dmma_backward<LOG_CT, 3, true>(sa, sb, stab + (k & (TAB_RING - 1)), R, s.q0, s.q1, s.q2, rows, has_w, wslot_c, wdirect, tid, nthr, gst_a, gst_b, sglob);
+                            else block_dmma_backward<LOG_CT, 2, true>(sa, sb, stab + (k & (TAB_RING - 1)), R, s.q0, s.q1, 30, rows, has_w, wslot_c, wdirect, tid, nthr, gst_a, gst_b, sglob);
+                            fused = stored = true;
+                        }
+                    }
+                    if (!fused) {
+                        if (s.dim == 8) block_dmma_backward<LOG_CT, 3, false>(sa, sb, stab + (k & (TAB_RING - 1)), R, s.q0, s.q1, s.q2, rows, has_w, wslot_c, wdirect, tid, nthr, nullptr, nullptr, nullptr);
+                        else block_dmma_backward<LOG_CT, 2, false>(sa, sb, stab + (k & (TAB_RING - 1)), R, s.q0, s.q1, 30, rows, has_w, wslot_c, wdirect, tid, nthr, nullptr, nullptr, nullptr);
+                    }
                 } else if (s.kind == 0) {
                     const cplx k00 = km[0], k01 = km[1], k10 = km[2], k11 = km[3];
                     const int tbit = 1 << s.q0;
@@ -1581,15 +1662,11 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                 }
             }
             __syncthreads();
-            if (MODE == MODE_BWD) {
-                const size_t colbase = (size_t)y * A.out_ystride + deposit_bits((unsigned)j0, ~A.wmask);
-                cplx* __restrict__ da = A.out + colbase;
-                cplx* __restrict__ db = A.beta + colbase;
+            if (MODE == MODE_BWD && !stored) {
                 for (int e = tid; e < rows * CT; e += nthr) {
-                    const int i = e >> LOG_CT, c = e & (CT - 1);
-                    const size_t off = (size_t)(unsigned)(srowpart[i] | scolpart[c]);
-                    da[off] = sa[elem<LOG_CT>(i, c)];
-                    db[off] = sb[elem<LOG_CT>(i, c)];
+                    const size_t off = (size_t)(unsigned)sglob[e];
+                    gst_a[off] = sa[e];
+                    gst_b[off] = sb[e];
                 }
                 __syncthreads();
             }

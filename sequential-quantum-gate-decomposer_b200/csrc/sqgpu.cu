@@ -679,15 +679,17 @@ struct FusedPlan {
     int log_ct = 0, threads = 32;
     int tiles = 0, tiles_per_cta = 1, chunks = 1;
     bool w_in_smem = false;
+    bool dbuf = false;      // window forward segments: two tile buffers
     bool w_direct = false;  // W' partials: one global slice per (parameter set, CTA, warp), see SQ_W_DIRECT
     int w_slices = 1;       // slices of w_part per parameter set = chunks * (w_direct ? warps per CTA : 1)
     size_t smem = 0;
 };
 
-size_t fused_smem(int mode, int rows, int ct, int threads, int dense_stage, int wmax, int w_total, bool w_in_smem, int n_ops) {
+size_t fused_smem(int mode, int rows, int ct, int threads, int dense_stage, int wmax, int w_total, bool w_in_smem, int n_ops, bool window = false,
+                  bool dbuf = false) {
     const bool has_b = mode == MODE_GRAD || mode == MODE_BWD;
     const bool w_direct = SQ_W_DIRECT && has_b && !w_in_smem;
-    size_t s = (size_t)rows * ct * sizeof(cplx) * (has_b ? 2 : 1);
+    size_t s = (size_t)rows * ct * sizeof(cplx) * ((has_b || (dbuf && mode == MODE_APPLY)) ? 2 : 1);  // a + beta, or two tile buffers
     s += (size_t)dense_stage * sizeof(cplx);
     s += TAB_RING * sizeof(OpTabS);          // ring of DMMA block lookup tables of one sweep direction
     s += TAB_RING * sizeof(unsigned long long);  // ... and their mbarriers
@@ -698,12 +700,14 @@ size_t fused_smem(int mode, int rows, int ct, int threads, int dense_stage, int 
         if (w_in_smem) s += (size_t)w_total * sizeof(cplx);
     }
     s += (size_t)(nwarps + 1) * 6 * sizeof(double);  // trace partials per warp + the CTA's running sums
-    s += (size_t)(rows + 8) * sizeof(int);   // window mode: deposit(r, wmask) per row, deposit(c, ~wmask) per tile column
+    if (window || mode == MODE_BWD) s += (size_t)rows * ct * sizeof(int);  // window mode: offset in the state of every tile slot
     return s;
 }
 
 FusedPlan plan_fused(const sqgpu_ctx* c, int mode, int rows, int cols, int ysets, int default_split = 2, bool window = false) {
     FusedPlan p;
+    // window forward segments: two tile buffers, the next tile streams in while the current one is computed (option async_tiles)
+    const bool dbuf = (SQ_WIN_BULK != 0) && window && mode == MODE_APPLY && c->opt.async_tiles != 0;
     // test hook (option force_stream): cost / gradient evaluations go down the chunked streaming executor
     if (c->opt.force_stream && (mode == MODE_COST || mode == MODE_GRAD)) return p;
     const size_t budget = (size_t)c->smem_optin;
@@ -720,10 +724,10 @@ FusedPlan plan_fused(const sqgpu_ctx* c, int mode, int rows, int cols, int ysets
     for (int lc = max_log; lc >= 0 && pick < 0; --lc) {
         const int ct = 1 << lc;
         const bool can_wsm = mode == MODE_GRAD && c->P->w_total > 0;  // MODE_BWD accumulates over several launches: global
-        if (can_wsm && fused_smem(mode, rows, ct, threads_for(ct), c->P->dense_stage, c->P->wmax, c->P->w_total, true, c->P->n_ops) <= budget) {
+        if (can_wsm && fused_smem(mode, rows, ct, threads_for(ct), c->P->dense_stage, c->P->wmax, c->P->w_total, true, c->P->n_ops, window, dbuf) <= budget) {
             pick = lc;
             pick_wsm = true;
-        } else if (fused_smem(mode, rows, ct, threads_for(ct), c->P->dense_stage, c->P->wmax, c->P->w_total, false, c->P->n_ops) <= budget) {
+        } else if (fused_smem(mode, rows, ct, threads_for(ct), c->P->dense_stage, c->P->wmax, c->P->w_total, false, c->P->n_ops, window, dbuf) <= budget) {
             pick = lc;
             pick_wsm = false;
         }
@@ -743,7 +747,7 @@ FusedPlan plan_fused(const sqgpu_ctx* c, int mode, int rows, int cols, int ysets
                 ways *= 2;
             }
             if (ways < 2) break;
-            const size_t sm = fused_smem(mode, rows, 1 << lc, thr, c->P->dense_stage, c->P->wmax, c->P->w_total, false, c->P->n_ops);
+            const size_t sm = fused_smem(mode, rows, 1 << lc, thr, c->P->dense_stage, c->P->wmax, c->P->w_total, false, c->P->n_ops, window, dbuf);
             if (fc || ((sm + 1024) * ways <= (size_t)c->smem_per_sm && thr * ways * 128 <= 65536)) {
                 pick = lc;
                 pick_threads = thr;
@@ -760,7 +764,8 @@ FusedPlan plan_fused(const sqgpu_ctx* c, int mode, int rows, int cols, int ysets
         p.threads = pick_threads;
         p.w_in_smem = pick_wsm;
         p.w_direct = SQ_W_DIRECT && (mode == MODE_GRAD || mode == MODE_BWD) && !pick_wsm;
-        p.smem = fused_smem(mode, rows, ct, p.threads, c->P->dense_stage, c->P->wmax, c->P->w_total, pick_wsm, c->P->n_ops);
+        p.smem = fused_smem(mode, rows, ct, p.threads, c->P->dense_stage, c->P->wmax, c->P->w_total, pick_wsm, c->P->n_ops, window, dbuf);
+        p.dbuf = dbuf;
         p.tiles = (cols + ct - 1) / ct;
         if (mode == MODE_APPLY && !window) {
             p.tiles_per_cta = 1;
@@ -894,6 +899,7 @@ void fill_common_args(const sqgpu_ctx* c, const FusedPlan& p, ExecArgs& a, int r
     a.w_total = c->P->w_total;
     a.w_in_smem = p.w_in_smem ? 1 : 0;
     a.w_direct = p.w_direct ? 1 : 0;
+    a.dbuf = p.dbuf ? 1 : 0;
 }
 
 void time_begin(sqgpu_ctx* c, const char* name, cudaStream_t st) {
@@ -1285,7 +1291,7 @@ bool tall_window_fits(sqgpu_ctx* c, bool grad) {
     PlanScope keep(c);
     c->P = &c->planW;
     const int wr = 1 << c->win_w, wc = 1 << (c->qbit_num - c->win_w);
-    if (!plan_fused(c, MODE_APPLY, wr, wc, 1, 4).ok) return false;
+    if (!plan_fused(c, MODE_APPLY, wr, wc, 1, 4, true).ok) return false;
     if (grad && !plan_fused(c, MODE_BWD, wr, wc, 1, 1).ok) return false;
     return true;
 }

@@ -724,7 +724,7 @@ def test_n13_gradient_windowed_executor(sq, port, cols):
     for variant in (0, 3):
         e.set_cost(variant, 0)
         f, g = e.cost_grad_batched(theta)
-        assert e.last_kernel_time()[0] == "fused_exec<WINDOW_BWD>", e.last_kernel_time()
+        assert e.last_kernel_time()[0].startswith("fused_exec<WINDOW_"), "not the windowed executor"
         for b in range(2):
             f_ref, g_ref = port.cost_grad(d, P, theta[b], U, n, variant)
             assert close_rel(f[b], f_ref) and close_rel(g[b], g_ref)
