@@ -363,6 +363,13 @@ static const int B0TAB = 64;  // batch bases precomputed per op (tiles with more
 #define SQ_W_DIRECT 0
 #endif
 
+// Raw dense 3-/4-qubit kernels (GENERAL blocks): 1 (default): the same three-product form as the fused blocks -- 24 instead of
+// 32 DMMA per 8 items for a 16 x 16 kernel, 6 instead of 8 for an 8 x 8 one, and 24 / 6 kernel-fragment registers per lane
+// instead of 32 / 8 doubles; 0: the real embedding. 5-qubit kernels keep the real embedding (their fragments stream from L1).
+#ifndef SQ_DENSE_3M
+#define SQ_DENSE_3M 1
+#endif
+
 struct OpTab {
     double frag[3][8][32];  // [mode: K, K^dagger, K^T][t * KS + s][lane]: kernel (B operand) fragments
     int slot[4][32];        // [u]: load/store slot of amplitude dep(j, u); [2 + h]: W' operand slot of item half h
@@ -829,9 +836,22 @@ __device__ __forceinline__ void dense_tab_fill(TAB* T, int* schoice, const cplx*
     }
     __syncthreads();
     const int ja = schoice[0], jb = schoice[1];
-    for (int e = tid; e < NT * KS * 32; e += nthr) {
-        const int ts = e >> 5, l = e & 31, t = ts / KS, ks = ts - t * KS, n = l >> 2, k = l & 3;
-        T->frag[e] = kreal_entry(K, DIM, 0, dep(n >> 1, t, ja, jb), n & 1, dep(k, ks >> 1, ja, jb), ks & 1);
+    if (SQ_DENSE_3M && KQ <= 4) {
+        // three-product form: frag[(m * NTL + nt) * NT + ks][lane], m in {0: C, 1: D - C, 2: -(C + D)} of K = C + iD, n-tile nt
+        // (8 output amplitudes), k-step ks (4 input amplitudes). Lane (k = lane & 3, n = lane >> 2) holds the entry
+        // [out amplitude dep(n >> 1, (n & 1) | 2 nt)][in amplitude dep(k, ks)]: the lane's inputs dep(j, u), u < NT, are its outputs
+        constexpr int NTL = DIM / 8;
+        for (int e = tid; e < 3 * NTL * NT * 32; e += nthr) {
+            const int l = e & 31, idx = e >> 5, m = idx / (NTL * NT), rem = idx - m * NTL * NT, nt = rem / NT, ks = rem - nt * NT;
+            const int n = l >> 2, k = l & 3;
+            const cplx kv = K[dep(n >> 1, (n & 1) | (nt << 1), ja, jb) * DIM + dep(k, ks, ja, jb)];
+            T->frag[e] = (m == 0) ? kv.x : (m == 1 ? kv.y - kv.x : -(kv.x + kv.y));
+        }
+    } else {
+        for (int e = tid; e < NT * KS * 32; e += nthr) {
+            const int ts = e >> 5, l = e & 31, t = ts / KS, ks = ts - t * KS, n = l >> 2, k = l & 3;
+            T->frag[e] = kreal_entry(K, DIM, 0, dep(n >> 1, t, ja, jb), n & 1, dep(k, ks >> 1, ja, jb), ks & 1);
+        }
     }
     for (int e = tid; e < NT * 32; e += nthr) T->sl[e >> 5][e & 31] = slot((e & 31) >> 2, dep(e & 3, e >> 5, ja, jb));
 }
@@ -896,38 +916,86 @@ template <int LOG_CT, int KQ>
 __device__ __forceinline__ void dense_dmma_forward2(cplx* sa, const DenseTab* __restrict__ T, const DevOp& op, int rows, int tid, int nthr) {
     constexpr int DIM = 1 << KQ, NT = DIM / 4, KS = 2 * NT;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
-    double kf[NT][KS];
-    int sl[NT];
+    if constexpr (SQ_DENSE_3M != 0) {
+        // k1 = C (u + v), Re = k1 - (C + D) v, Im = k1 + (D - C) u per n-tile (see block_dmma_forward): 3 * NTL * NT DMMA per batch
+        constexpr int NTL = DIM / 8;
+        double f[3][NTL][NT];
+        int sl[NT];
 #pragma unroll
-    for (int t = 0; t < NT; ++t) {
-        sl[t] = T->sl[t][lane];
+        for (int u = 0; u < NT; ++u) sl[u] = T->sl[u][lane];
 #pragma unroll
-        for (int ks = 0; ks < KS; ++ks) kf[t][ks] = T->frag[(t * KS + ks) * 32 + lane];
-    }
-    int q[KQ];
+        for (int m = 0; m < 3; ++m)
 #pragma unroll
-    for (int j = 0; j < KQ; ++j) q[j] = op.q[j];
-    const int nitems = (rows >> KQ) << LOG_CT;
-    for (int b0 = warp * 8; b0 < nitems; b0 += nwarps * 8) {
-        int base = b0 >> LOG_CT;
+            for (int nt = 0; nt < NTL; ++nt)
 #pragma unroll
-        for (int j = 0; j < KQ; ++j) base = insert_zero(base, q[j]);
-        const int B0 = elem<LOG_CT>(base, 0);
-        cplx x[NT], d[NT];
+                for (int ks = 0; ks < NT; ++ks) f[m][nt][ks] = T->frag[((m * NTL + nt) * NT + ks) * 32 + lane];
+        int q[KQ];
 #pragma unroll
-        for (int u = 0; u < NT; ++u) {
-            x[u] = sa[B0 ^ sl[u]];
-            d[u] = czero();
-        }
+        for (int j = 0; j < KQ; ++j) q[j] = op.q[j];
+        const int nitems = (rows >> KQ) << LOG_CT;
+        for (int b0 = warp * 8; b0 < nitems; b0 += nwarps * 8) {
+            int base = b0 >> LOG_CT;
 #pragma unroll
-        for (int u = 0; u < NT; ++u)
+            for (int j = 0; j < KQ; ++j) base = insert_zero(base, q[j]);
+            const int B0 = elem<LOG_CT>(base, 0);
+            cplx x[NT], d[NT];
+            double sm[NT];
 #pragma unroll
-            for (int t = 0; t < NT; ++t) {
-                dmma_m8n8k4(d[t].x, d[t].y, x[u].x, kf[t][2 * u]);
-                dmma_m8n8k4(d[t].x, d[t].y, x[u].y, kf[t][2 * u + 1]);
+            for (int u = 0; u < NT; ++u) {
+                x[u] = sa[B0 ^ sl[u]];
+                sm[u] = x[u].x + x[u].y;
             }
 #pragma unroll
-        for (int t = 0; t < NT; ++t) sa[B0 ^ sl[t]] = d[t];
+            for (int nt = 0; nt < NTL; ++nt) {
+                double k1[2] = {0.0, 0.0};
+#pragma unroll
+                for (int ks = 0; ks < NT; ++ks) dmma_m8n8k4(k1[0], k1[1], sm[ks], f[0][nt][ks]);
+                double re[2] = {k1[0], k1[1]}, im[2] = {k1[0], k1[1]};
+#pragma unroll
+                for (int ks = 0; ks < NT; ++ks) {
+                    dmma_m8n8k4(re[0], re[1], x[ks].y, f[2][nt][ks]);
+                    dmma_m8n8k4(im[0], im[1], x[ks].x, f[1][nt][ks]);
+                }
+                d[2 * nt] = cmake(re[0], im[0]);
+                d[2 * nt + 1] = cmake(re[1], im[1]);
+            }
+#pragma unroll
+            for (int t = 0; t < NT; ++t) sa[B0 ^ sl[t]] = d[t];
+        }
+    } else {
+        double kf[NT][KS];
+        int sl[NT];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            sl[t] = T->sl[t][lane];
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) kf[t][ks] = T->frag[(t * KS + ks) * 32 + lane];
+        }
+        int q[KQ];
+#pragma unroll
+        for (int j = 0; j < KQ; ++j) q[j] = op.q[j];
+        const int nitems = (rows >> KQ) << LOG_CT;
+        for (int b0 = warp * 8; b0 < nitems; b0 += nwarps * 8) {
+            int base = b0 >> LOG_CT;
+#pragma unroll
+            for (int j = 0; j < KQ; ++j) base = insert_zero(base, q[j]);
+            const int B0 = elem<LOG_CT>(base, 0);
+            cplx x[NT], d[NT];
+#pragma unroll
+            for (int u = 0; u < NT; ++u) {
+                x[u] = sa[B0 ^ sl[u]];
+                d[u] = czero();
+            }
+#pragma unroll
+            for (int u = 0; u < NT; ++u)
+#pragma unroll
+                for (int t = 0; t < NT; ++t) {
+                    dmma_m8n8k4(d[t].x, d[t].y, x[u].x, kf[t][2 * u]);
+                    dmma_m8n8k4(d[t].x, d[t].y, x[u].y, kf[t][2 * u + 1]);
+                }
+#pragma unroll
+            for (int t = 0; t < NT; ++t) sa[B0 ^ sl[t]] = d[t];
+        }
     }
 }
 

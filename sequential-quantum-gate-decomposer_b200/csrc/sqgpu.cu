@@ -990,16 +990,21 @@ void exec_flops(const Plan& P, int rows, int cols, int log_ct, bool grad, int ys
             double per8;  // DMMA per batch of 8 items
             if (op.dim == 8 && SQ_BLOCK_3M) {
                 // three real products per complex product: 6 DMMA forward, 12 (+ 6 for W') backward, and per lane and batch
-                // 8 DADD forward, 16 (+ 4) backward for the sums and differences
+                // 2 DADD forward, 4 (+ 4) backward for the operand sums
                 per8 = 6.0 + (grad ? 12.0 + (has_w ? 6.0 : 0.0) : 0.0);
-                sc += items / 8.0 * 32.0 * (8.0 + (grad ? 16.0 + (has_w ? 4.0 : 0.0) : 0.0));
+                sc += items / 8.0 * 32.0 * (2.0 + (grad ? 4.0 + (has_w ? 4.0 : 0.0) : 0.0));  // the operand sums u + v
             } else {
                 per8 = op.dim == 8 ? (8.0 + (grad ? 16.0 + (has_w ? 8.0 : 0.0) : 0.0)) : (2.0 + (grad ? 4.0 + (has_w ? 2.0 : 0.0) : 0.0));
             }
             t += items / 8.0 * per8 * 512.0;
         } else if (op.ctrl_mask == 0 && op.nq >= 3 && op.type == SQGPU_GENERAL && !grad) {
             const double nt = op.dim / 4.0;
-            t += items / 8.0 * (nt * nt * 2.0) * 512.0;
+            if (SQ_DENSE_3M && op.nq <= 4) {  // three-product form: 3 x (dim / 8) x (dim / 4) DMMA and dim / 4 DADD per batch
+                t += items / 8.0 * (nt * nt * 1.5) * 512.0;
+                sc += items / 8.0 * 32.0 * nt;
+            } else {
+                t += items / 8.0 * (nt * nt * 2.0) * 512.0;
+            }
         } else {
             const double act = items / (double)(1 << popcount32(op.ctrl_mask));
             sc += act * 8.0 * op.dim * op.dim * (grad ? 3.0 : 1.0);
