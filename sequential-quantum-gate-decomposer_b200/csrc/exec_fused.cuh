@@ -328,9 +328,10 @@ static const int B0TAB = 64;  // batch bases precomputed per op (tiles with more
 // Window modes only: 1: the op tables use the bulk-async / mbarrier ring there, which frees the cp.async groups for a
 // double-buffered tile pipeline in the forward segments (two single-column tile buffers, tile t + 1 requested before tile t is
 // computed: option async_tiles). Measured on C5 (profiles/r2_variants_win3.jsonl): forward sweep 20.2 ms per 64 sets against
-// 17.6 ms for the default -- the mbarrier polls cost 6.7 % of the warp samples (profiles/r2_ncu_vqe_window_src.md), the
-// narrower tiles conflict more, and the tile round trips it hides were not the limiter: 73-79 % of the samples sit inside the
-// DMMA loops, which run the FP64 pipe at ~80 %. 0 (default): LDGSTS ring, one tile buffer, whole tile requested at once.
+// 17.6 ms for the default (the bulk ring alone: 18.9 ms). The tile round trips it hides were not the limiter: 73-79 % of
+// the warp samples sit inside the DMMA loops, which run the FP64 pipe at ~80 %, and waits for global loads are 6 %
+// (profiles/r2_ncu_vqe_window_src.md); the narrower single-column tiles conflict more in shared memory.
+// 0 (default): LDGSTS ring, one tile buffer, whole tile requested at once.
 #ifndef SQ_WIN_BULK
 #define SQ_WIN_BULK 0
 #endif
@@ -914,7 +915,7 @@ __device__ __forceinline__ void dense_dmma_forward5(cplx* sa, const DenseTab5* _
 
 template <int LOG_CT, int KQ>
 __device__ __forceinline__ void dense_dmma_forward2(cplx* sa, const DenseTab* __restrict__ T, const DevOp& op, int rows, int tid, int nthr) {
-    constexpr int DIM = 1 << KQ, NT = DIM / 4, KS = 2 * NT;
+    constexpr int DIM = 1 << KQ, NT = DIM / 4;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
     if constexpr (SQ_DENSE_3M != 0) {
         // k1 = C (u + v), Re = k1 - (C + D) v, Im = k1 + (D - C) u per n-tile (see block_dmma_forward): 3 * NTL * NT DMMA per batch
@@ -963,6 +964,7 @@ __device__ __forceinline__ void dense_dmma_forward2(cplx* sa, const DenseTab* __
             for (int t = 0; t < NT; ++t) sa[B0 ^ sl[t]] = d[t];
         }
     } else {
+        constexpr int KS = 2 * NT;
         double kf[NT][KS];
         int sl[NT];
 #pragma unroll
