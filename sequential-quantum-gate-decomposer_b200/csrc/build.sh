@@ -5,5 +5,5 @@ set -e
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 $NVCC -std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo \
-      -Xcompiler -fPIC,-O3,-Wall,-Wno-unused-function -shared -cudart static \
+      -Xcompiler -fPIC,-O3,-Wall,-Wno-unused-function,-Wno-unknown-pragmas -shared -cudart static \
       -ccbin /usr/bin/g++ "$@" -o "${OUT:-libsqgpu.so}" sqgpu.cu

@@ -17,7 +17,7 @@ struct Trig {
     double s[4], c[4];
 };
 
-__device__ __forceinline__ void k2(cplx* k, double r0, double i0, double r1, double i1, double r2, double i2, double r3,
+__host__ __device__ __forceinline__ void k2(cplx* k, double r0, double i0, double r1, double i1, double r2, double i2, double r3,
                                    double i3) {
     k[0] = cmake(r0, i0);
     k[1] = cmake(r1, i1);
@@ -25,13 +25,13 @@ __device__ __forceinline__ void k2(cplx* k, double r0, double i0, double r1, dou
     k[3] = cmake(r3, i3);
 }
 
-__device__ __forceinline__ void rot_phase(cplx* k, double sg, double cg) {  // multiply_2x2_by_phase :611-619
+__host__ __device__ __forceinline__ void rot_phase(cplx* k, double sg, double cg) {  // multiply_2x2_by_phase :611-619
 #pragma unroll
     for (int i = 0; i < 4; ++i) k[i] = cmake(k[i].x * cg - k[i].y * sg, k[i].x * sg + k[i].y * cg);
 }
 
 // U3 body shared by U3 and CU. which: -1 forward, 0/1/2 derivative wrt theta/phi/lambda.
-__device__ __forceinline__ void u3_body(cplx* k, int which, double st, double ct, double sp, double cp, double sl,
+__host__ __device__ __forceinline__ void u3_body(cplx* k, int which, double st, double ct, double sp, double cp, double sl,
                                         double cl) {
     const double spl = sp * cl + cp * sl;
     const double cpl = cp * cl - sp * sl;
@@ -41,13 +41,13 @@ __device__ __forceinline__ void u3_body(cplx* k, int which, double st, double ct
     else k2(k, 0.0, 0.0, st * sl, -st * cl, 0.0, 0.0, -ct * spl, ct * cpl);
 }
 
-__device__ __forceinline__ void zero16(cplx* k) {
+__host__ __device__ __forceinline__ void zero16(cplx* k) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) k[i] = czero();
 }
 
 // Writes the dim x dim kernel of `type` (which < 0) or its derivative wrt parameter `which`. Returns dim (0: unknown).
-__device__ inline int build_gate_kernel(int type, const Trig& t, int which, cplx* k) {
+__host__ __device__ inline int build_gate_kernel(int type, const Trig& t, int which, cplx* k) {
     const double s0 = t.s[0], c0 = t.c[0], s1 = t.s[1], c1 = t.c[1], s2 = t.s[2], c2 = t.c[2], s3 = t.s[3], c3 = t.c[3];
     const double sq2 = 0.70710678118654752440;  // M_SQRT1_2
     const bool fwd = which < 0;

@@ -26,7 +26,7 @@ __device__ __forceinline__ cplx cfmac(cplx a, cplx b, cplx acc) {
     return acc;
 }
 __device__ __forceinline__ cplx cadd(cplx a, cplx b) { return make_double2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ cplx czero() { return make_double2(0.0, 0.0); }
+__host__ __device__ __forceinline__ cplx czero() { return make_double2(0.0, 0.0); }
 
 // One operation of the device program. The host planner (sqgpu.cu: plan_blocks) fuses runs of consecutive gates that act
 // inside one or two qubits into a single dense 2x2 / 4x4 "block" op (type == SQ_OP_BLOCK) whose matrix -- and the

@@ -134,7 +134,8 @@ struct Options {
     int verbose = 0;
     int no_graph = 0;          // device-resident optimizer loops: plain launches instead of one CUDA graph replay per step
     int tall_window = 1;       // matrices whose column does not fit shared memory: windowed executor (0: streaming fallback)
-    int async_tiles = 1;       // windowed executor: bulk-async (TMA) tile pipeline
+    int async_tiles = 1;       // windowed executor (SQ_WIN_BULK builds): double-buffered tiles in the forward segments
+    int const_fuse_qubits = 4; // constant sub-circuits are multiplied out on the host into dense blocks of up to this many qubits (0: off)
 };
 
 typedef int Options::*OptionField;
@@ -154,6 +155,7 @@ const OptionName kOptionNames[] = {
     {"no_graph", &Options::no_graph, 0, 1},
     {"tall_window", &Options::tall_window, 0, 1},
     {"async_tiles", &Options::async_tiles, 0, 1},
+    {"const_fuse_qubits", &Options::const_fuse_qubits, 0, 5},
 };
 
 int option_set(Options& o, const char* name, long long value) {
@@ -229,7 +231,7 @@ struct sqgpu_ctx {
     int win_w = 0;
     Plan* P = &plan2;                // plan the helpers below operate on (set by the entry point, under the mutex)
     DevBuf dPool;
-    int n_params = 0, qbit_num = 0, n_gates = 0;
+    int n_params = 0, qbit_num = 0, n_gates = 0, n_const_fused = 0;
     bool all_unitary = true, circuit_set = false;
     std::vector<cplx> pool;
 
@@ -1618,6 +1620,142 @@ int sqgpu_upload_matrix(sqgpu_handle_t c, const double* data, int rows, int cols
 }
 
 // lowering + planning (host only) and, with `upload`, the transfer of the three plans to the device
+// N3, constant sub-circuits (the reference multiplies gates out into <= 5-qubit kernels in
+// Gates_block::apply_to's fusion rule, gates/Gates_block.cpp:632-681, and in squander/partitioning/partition.py:50-93): gates
+// WITHOUT parameters whose joint support fits `max_q` qubits are multiplied out ON THE HOST, once per sqgpu_set_circuit, into
+// one constant dense kernel that the executor runs as a raw GENERAL op on the tensor cores (dense_dmma_forward2 / 5). The
+// grouping is the same dependency-aware first fit as the block planner's: a group starts at the first constant gate not yet
+// placed and takes, in program order, every later constant gate that fits its qubit set and shares no qubit with a gate that
+// was passed over. A group is only replaced when that pays by the flop model: by itself it would need MORE 3-qubit blocks
+// than the dense kernel costs (a 2^k x 2^k kernel costs 2^(k-3) block units per amplitude), so the parametric layers of the
+// decomposition circuits, whose CNOTs ride along in neighbouring blocks for free, are left alone.
+// `pool` is the matrix pool of the circuit; new kernels are appended to it.
+static void host_apply_const_gate(const DevOp& r, const std::vector<cplx>& pool, const int* qs, int nqs, std::vector<cplx>& M) {
+    const int D = 1 << nqs;
+    auto local_bit = [&](int q) { for (int j = 0; j < nqs; ++j) if (qs[j] == q) return j; return -1; };
+    const int dim = r.dim, nq = r.dim == 2 ? 1 : r.nq;
+    std::vector<cplx> K((size_t)std::max(dim * dim, 16));
+    if (r.type == SQGPU_GENERAL) {
+        for (int e = 0; e < dim * dim; ++e) K[e] = pool[(size_t)r.pool_off + e];
+    } else {
+        Trig t;
+        memset(&t, 0, sizeof(t));
+        build_gate_kernel(r.type, t, -1, K.data());
+    }
+    int pos[5] = {0, 0, 0, 0, 0};
+    if (r.dim == 2) pos[0] = local_bit(r.target);
+    else
+        for (int j = 0; j < nq; ++j) pos[j] = local_bit(r.q[j]);
+    unsigned tmask = 0, cmask = 0;
+    for (int j = 0; j < nq; ++j) tmask |= 1u << pos[j];
+    for (int q = 0; q < 30; ++q)
+        if ((r.ctrl_mask >> q) & 1) cmask |= 1u << local_bit(q);
+    std::vector<cplx> v(dim), o(dim);
+    for (int col = 0; col < D; ++col)
+        for (int base = 0; base < D; ++base) {
+            if ((base & tmask) != 0 || ((unsigned)base & cmask) != cmask) continue;
+            for (int l = 0; l < dim; ++l) {
+                int row = base;
+                for (int j = 0; j < nq; ++j) row |= ((l >> j) & 1) << pos[j];
+                v[l] = M[(size_t)row * D + col];
+            }
+            for (int lo = 0; lo < dim; ++lo) {
+                double re = 0, im = 0;
+                for (int l = 0; l < dim; ++l) {
+                    const cplx k = K[lo * dim + l];
+                    re += k.x * v[l].x - k.y * v[l].y;
+                    im += k.x * v[l].y + k.y * v[l].x;
+                }
+                o[lo] = cmake(re, im);
+            }
+            for (int l = 0; l < dim; ++l) {
+                int row = base;
+                for (int j = 0; j < nq; ++j) row |= ((l >> j) & 1) << pos[j];
+                M[(size_t)row * D + col] = o[l];
+            }
+        }
+}
+
+static int fuse_constant_runs(const std::vector<DevOp>& raw, int qbit_num, int max_q, std::vector<cplx>& pool, std::vector<DevOp>& out) {
+    const int N = (int)raw.size();
+    out.clear();
+    int n_fused = 0;
+    auto is_const = [&](const DevOp& r) { return r.n_params == 0 && popcount32(support_mask(r)) <= max_q; };
+    const unsigned all_qubits = qbit_num >= 32 ? 0xffffffffu : ((1u << qbit_num) - 1u);
+    std::vector<char> placed(std::max(N, 1), 0);
+    for (int first = 0; first < N; ++first) {
+        if (placed[first]) continue;
+        placed[first] = 1;
+        if (max_q < 4 || !is_const(raw[first])) {
+            out.push_back(raw[first]);
+            continue;
+        }
+        std::vector<int> group(1, first);
+        unsigned support = support_mask(raw[first]), blocked = 0;
+        const int scan_end = std::min(N, first + 8192);
+        for (int i = first + 1; i < scan_end; ++i) {
+            if (placed[i]) continue;
+            const unsigned sup = support_mask(raw[i]);
+            if (is_const(raw[i]) && (sup & blocked) == 0 && popcount32(support | sup) <= max_q) {
+                group.push_back(i);
+                support |= sup;
+            } else {
+                blocked |= sup;
+                if ((blocked & all_qubits) == all_qubits) break;
+            }
+        }
+        const int nqs = popcount32(support);
+        // 3-qubit blocks the group would need by itself (the block planner's first fit, restricted to the group)
+        int blocks3 = 0;
+        {
+            std::vector<char> done(group.size(), 0);
+            for (size_t a = 0; a < group.size(); ++a) {
+                if (done[a]) continue;
+                unsigned bs = 0, blk = 0;
+                for (size_t b = a; b < group.size(); ++b) {
+                    if (done[b]) continue;
+                    const unsigned sup = support_mask(raw[group[b]]);
+                    if ((sup & blk) == 0 && popcount32(bs | sup) <= 3) {
+                        bs |= sup;
+                        done[b] = 1;
+                    } else {
+                        blk |= sup;
+                    }
+                }
+                ++blocks3;
+            }
+        }
+        if (nqs < 4 || blocks3 <= (1 << (nqs - 3))) {  // not worth a dense kernel: leave the gates to the block planner
+            out.push_back(raw[first]);
+            continue;
+        }
+        int qs[5] = {0, 0, 0, 0, 0}, nq = 0;
+        for (int q = 0; q < 30; ++q)
+            if ((support >> q) & 1) qs[nq++] = q;
+        const int D = 1 << nqs;
+        std::vector<cplx> M((size_t)D * D, cmake(0, 0));
+        for (int i = 0; i < D; ++i) M[(size_t)i * D + i] = cmake(1, 0);
+        for (int gi : group) {
+            host_apply_const_gate(raw[gi], pool, qs, nqs, M);
+            placed[gi] = 1;
+        }
+        DevOp op;
+        memset(&op, 0, sizeof(op));
+        op.type = SQGPU_GENERAL;
+        op.kern_off = op.dkern_off = op.w_off = -1;
+        op.member_off = -1;
+        op.dim = D;
+        op.nq = nqs;
+        for (int j = 0; j < nqs; ++j) op.q[j] = qs[j];
+        op.pool_off = (int64_t)pool.size();
+        pool.insert(pool.end(), M.begin(), M.end());
+        fill_fix(op);
+        out.push_back(op);
+        ++n_fused;
+    }
+    return n_fused;
+}
+
 static int set_circuit_impl(sqgpu_ctx* c, const sqgpu_gate_desc* gates, int n_gates, int n_params, int qbit_num,
                             const double* matrix_pool, int64_t pool_len, bool upload) {
     if (n_gates < 0 || n_params < 0 || qbit_num < 1 || qbit_num > 30) return fail(SQGPU_ERR_INVALID, "bad circuit arguments");
@@ -1649,7 +1787,16 @@ static int set_circuit_impl(sqgpu_ctx* c, const sqgpu_gate_desc* gates, int n_ga
     //    (the device-side analogue of Gates_block's <=2-qubit fusion rule, Gates_block.cpp:632-681, applied to the
     //    flattened circuit and extended to the gradient by the product rule in build_block_warp)
     const bool fuse = !c->opt.no_fuse;
-    auto build_plan = [&](int max_q, Plan& out) {
+    // plan2 (streaming fallback) keeps the gates as they are; plan3 (shared-memory / windowed executor) sees constant
+    // sub-circuits multiplied out into dense kernels (fuse_constant_runs)
+    std::vector<cplx> pool_ext;
+    if (matrix_pool && pool_len > 0) pool_ext.assign(reinterpret_cast<const cplx*>(matrix_pool), reinterpret_cast<const cplx*>(matrix_pool) + pool_len);
+    std::vector<DevOp> raw_fused;
+    int n_const_fused = 0;
+    if (fuse && c->opt.const_fuse_qubits >= 4) n_const_fused = fuse_constant_runs(raw, qbit_num, c->opt.const_fuse_qubits, pool_ext, raw_fused);
+    const std::vector<DevOp> raw_plain = raw;
+    auto build_plan = [&](int max_q, const std::vector<DevOp>& raw, Plan& out) {
+        const int n_gates = (int)raw.size();
         std::vector<DevOp> ops;
         std::vector<DevMember> members;
         std::vector<int> param_op(std::max(n_params, 1), -1), param_slot(std::max(n_params, 1), 0);
@@ -1808,14 +1955,15 @@ static int set_circuit_impl(sqgpu_ctx* c, const sqgpu_gate_desc* gates, int n_ga
 
     int rc;
     if (upload) {
-        if ((rc = c->dPool.ensure(std::max<size_t>(1, (size_t)pool_len) * sizeof(cplx)))) return rc;
+        if ((rc = c->dPool.ensure(std::max<size_t>(1, pool_ext.size()) * sizeof(cplx)))) return rc;
         CUDA_TRY(cudaStreamSynchronize(c->stream));
-        if (pool_len > 0) CUDA_TRY(cudaMemcpy(c->dPool.p, matrix_pool, (size_t)pool_len * sizeof(cplx), cudaMemcpyHostToDevice));
+        if (!pool_ext.empty()) CUDA_TRY(cudaMemcpy(c->dPool.p, pool_ext.data(), pool_ext.size() * sizeof(cplx), cudaMemcpyHostToDevice));
     }
     c->circuit_set = false;
-    if ((rc = build_plan(2, c->plan2))) return rc;
+    if ((rc = build_plan(2, raw_plain, c->plan2))) return rc;
     const int max_q3 = c->opt.max_fuse_qubits == 2 ? 2 : 3;
-    if ((rc = build_plan(max_q3, c->plan3))) return rc;
+    if ((rc = build_plan(max_q3, n_const_fused > 0 ? raw_fused : raw_plain, c->plan3))) return rc;
+    c->n_const_fused = n_const_fused;
     c->qbit_num = qbit_num;
     if ((rc = build_window_plan(c, upload))) return rc;
     c->P = &c->plan2;

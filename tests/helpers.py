@@ -245,3 +245,28 @@ def pauli_exponent_circuit(alpha=0.6217 * np.pi):
     rx(-np.pi / 2, 0); h(2); cx(0, 1)
     rx(-np.pi / 2, 0); rx(-np.pi / 2, 1); cx(2, 4); cx(1, 2); h(1)
     return c, np.array(p, dtype=np.float64)
+
+
+CONST_NAMES = ["CNOT", "CZ", "CH", "H", "X", "Y", "Z", "S", "Sdg", "T", "Tdg", "SX", "SXdg", "SWAP", "CCX", "CSWAP", "SYC"]
+
+
+def const_heavy_circuit(n, stretches, gates_per_stretch, seed, support=4, general_k=()):
+    """U3 layers with parameter-free stretches in between: every stretch is `gates_per_stretch` random constant gates on a
+    random set of `support` qubits (N3: the planner multiplies such sub-circuits out into dense kernels)"""
+    rng = np.random.default_rng(seed)
+    c = sq.Circuit(n)
+    for s in range(stretches):
+        for q in range(n):
+            c.add_U3(q)
+        sub = sorted(int(q) for q in rng.choice(n, support, replace=False))
+        for g in range(gates_per_stretch):
+            qs = [sub[i] for i in rng.permutation(support)]
+            r = int(rng.integers(0, len(CONST_NAMES) + len(general_k)))
+            if r >= len(CONST_NAMES):
+                k = general_k[r - len(CONST_NAMES)]
+                c.add_GENERAL(random_unitary(1 << k, seed=5000 + 37 * s + g), qs[:k])
+            else:
+                add_named(c, CONST_NAMES[r], qs)
+    for q in range(n):
+        c.add_RY(q)
+    return c

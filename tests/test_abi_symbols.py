@@ -299,3 +299,30 @@ def test_lbfgs_host_loop_with_oracle_callables(port):
         dec.set_Optimizer("AGENTS")
     with pytest.raises(Exception):
         dec.get_Optimized_Parameters()
+
+
+def test_constant_subcircuits_become_dense_kernels():
+    """N3: parameter-free stretches whose support fits 4 qubits are multiplied out on the host into one dense kernel when
+    that needs fewer flops than the 3-qubit blocks they would occupy; the parametric decomposition structures are left alone.
+    Planner only (no device)."""
+    import helpers as H
+
+    sq = H.sq
+    c = H.const_heavy_circuit(8, 3, 40, seed=11)
+    ops = sq.abi.plan_ops(c, which=3)
+    dense = [o for o in ops if o[0] == 16 and o[2] == 0 and o[3] == 0]
+    assert len(dense) == 3 and all(len(o[1]) == 4 for o in dense)
+    ops_off = sq.abi.plan_ops(c, which=3, const_fuse_qubits=0)
+    assert not [o for o in ops_off if o[0] == 16] and len(ops_off) > len(ops)
+    # the <= 2-qubit plan of the streaming fallback keeps the gates as they are
+    assert sq.abi.plan_ops(c, which=2) == sq.abi.plan_ops(c, which=2, const_fuse_qubits=0)
+    # up to five qubits on request
+    c5 = H.const_heavy_circuit(8, 2, 80, seed=12, support=5)
+    assert [o for o in sq.abi.plan_ops(c5, which=3, const_fuse_qubits=5) if o[0] == 32]
+    assert not [o for o in sq.abi.plan_ops(c5, which=3) if o[0] == 32]
+    # a short constant stretch is cheaper inside the neighbouring blocks: nothing changes
+    short = H.const_heavy_circuit(8, 3, 4, seed=13)
+    assert sq.abi.plan_ops(short, which=3) == sq.abi.plan_ops(short, which=3, const_fuse_qubits=0)
+    # C3 / C5 structures: every CNOT-like gate sits between parametric ones, the plans are what they were
+    assert sq.abi.plan_stats(H.adaptive_circuit(10, 4))["ops_plan3"] == 84
+    assert sq.abi.plan_stats(H.hea_zyz_circuit(20, 10)) == sq.abi.plan_stats(H.hea_zyz_circuit(20, 10), const_fuse_qubits=0)

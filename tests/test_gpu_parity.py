@@ -988,3 +988,32 @@ def test_start_decomposition_config1(sq, optimizer):
     m = np.eye(16) * 2 - prod - prod.conj().T
     assert np.real(np.trace(m)) / 2 < 1e-3
     assert dec.get_Num_of_Iters() > 0 and 1 <= dec.decomposition_level <= 5
+
+
+# ---- N3: constant sub-circuits multiplied out into dense kernels -----------------------------------------------------
+
+@pytest.mark.parametrize("n,support,opt", [(6, 4, {}), (7, 5, {"const_fuse_qubits": 5}), (6, 4, {"const_fuse_qubits": 0})])
+def test_constant_subcircuit_fusion_matches_oracle(sq, port, n, support, opt):
+    """parameter-free stretches (every constant gate family, GENERAL kernels included) fused on the host into 16 x 16 / 32 x 32
+    kernels: apply, cost and gradient against the oracle, which applies the original gates one by one"""
+    c = H.const_heavy_circuit(n, 3, 40 if support == 4 else 80, seed=21, support=support, general_k=(2, 3))
+    d, pool = c.descriptors()
+    P = c.get_Parameter_Num()
+    dims = [o[0] for o in sq.abi.plan_ops(c, which=3, **opt)]
+    assert ((1 << support) in dims) == (opt.get("const_fuse_qubits", 4) >= support)
+    U = H.random_unitary(1 << n, seed=4).conj().T.copy()
+    ps = H.random_params(P, seed=6, batch=2)
+    e = sq.Engine(0, options=opt)
+    e.upload_matrix(U)
+    e.set_circuit(c)
+    got = U.copy()
+    e.apply(ps[0], got)
+    assert np.abs(got - port.apply_circuit(d, ps[0], U, pool)).max() < ENTRY_TOL
+    for variant in (0, 3):
+        e.set_cost(variant, 0)
+        f, g = e.cost_grad_batched(ps)
+        fc = e.cost_batched(ps)
+        for b in range(2):
+            f_ref, g_ref = port.cost_grad(d, P, ps[b], U, n, variant, pool=pool)
+            assert close_rel(f[b], f_ref) and close_rel(fc[b], f_ref) and close_rel(g[b], g_ref)
+    e.close()
