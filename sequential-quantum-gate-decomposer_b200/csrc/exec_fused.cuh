@@ -780,7 +780,7 @@ struct DenseTab5 {
 };
 
 template <int LOG_CT, int KQ, typename TAB>
-__device__ __forceinline__ void dense_tab_fill(TAB* T, int* schoice, const cplx* __restrict__ K, const DevOp& op, int tid, int nthr) {
+__device__ __forceinline__ void dense_tab_fill(TAB* T, int* schoice, const cplx* __restrict__ K, const DevOp& op, int tid, int nthr, int mode = 0) {
     constexpr int CT = 1 << LOG_CT, LOGG = 3 - LOG_CT, DIM = 1 << KQ, NT = DIM / 4, KS = 2 * NT;
     int Pq[KQ], F[3];
     unsigned qmask = 0;
@@ -845,13 +845,15 @@ __device__ __forceinline__ void dense_tab_fill(TAB* T, int* schoice, const cplx*
         for (int e = tid; e < 3 * NTL * NT * 32; e += nthr) {
             const int l = e & 31, idx = e >> 5, m = idx / (NTL * NT), rem = idx - m * NTL * NT, nt = rem / NT, ks = rem - nt * NT;
             const int n = l >> 2, k = l & 3;
-            const cplx kv = K[dep(n >> 1, (n & 1) | (nt << 1), ja, jb) * DIM + dep(k, ks, ja, jb)];
-            T->frag[e] = (m == 0) ? kv.x : (m == 1 ? kv.y - kv.x : -(kv.x + kv.y));
+            const int ao = dep(n >> 1, (n & 1) | (nt << 1), ja, jb), ai = dep(k, ks, ja, jb);
+            const cplx kv = (mode == 0) ? K[ao * DIM + ai] : K[ai * DIM + ao];  // mode 1: K^dagger, 2: K^T
+            const double cre = kv.x, dim_ = (mode == 1) ? -kv.y : kv.y;
+            T->frag[e] = (m == 0) ? cre : (m == 1 ? dim_ - cre : -(cre + dim_));
         }
     } else {
         for (int e = tid; e < NT * KS * 32; e += nthr) {
             const int ts = e >> 5, l = e & 31, t = ts / KS, ks = ts - t * KS, n = l >> 2, k = l & 3;
-            T->frag[e] = kreal_entry(K, DIM, 0, dep(n >> 1, t, ja, jb), n & 1, dep(k, ks >> 1, ja, jb), ks & 1);
+            T->frag[e] = kreal_entry(K, DIM, mode, dep(n >> 1, t, ja, jb), n & 1, dep(k, ks >> 1, ja, jb), ks & 1);
         }
     }
     for (int e = tid; e < NT * 32; e += nthr) T->sl[e >> 5][e & 31] = slot((e & 31) >> 2, dep(e & 3, e >> 5, ja, jb));
@@ -868,9 +870,13 @@ __global__ void build_dense_tabs(const DevOp* __restrict__ ops, int n_ops, const
         dense_tab_fill<LOG_CT, 5>(tabs5 + (-1 - op.dtab), schoice, pool + op.pool_off, op, threadIdx.x, blockDim.x);
         return;
     }
-    DenseTab* T = tabs + (op.dtab - 1);
-    if (op.nq == 3) dense_tab_fill<LOG_CT, 3>(T, schoice, pool + op.pool_off, op, threadIdx.x, blockDim.x);
-    else dense_tab_fill<LOG_CT, 4>(T, schoice, pool + op.pool_off, op, threadIdx.x, blockDim.x);
+    // three tables per op: K (forward sweep), K^dagger and K^T (adjoint sweep: a <- K^dagger a, beta <- K^T beta)
+    for (int mode = 0; mode < 3; ++mode) {
+        DenseTab* T = tabs + 3 * (op.dtab - 1) + mode;
+        if (op.nq == 3) dense_tab_fill<LOG_CT, 3>(T, schoice, pool + op.pool_off, op, threadIdx.x, blockDim.x, mode);
+        else dense_tab_fill<LOG_CT, 4>(T, schoice, pool + op.pool_off, op, threadIdx.x, blockDim.x, mode);
+        __syncthreads();
+    }
 }
 
 // 5-qubit kernels: 128 DMMA per 8-item batch, kernel fragments streamed from the (L1-resident) table
@@ -1384,7 +1390,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                     const int nitems = (rows >> nq) << LOG_CT;
                     const bool use_dmma = !deriv && op.ctrl_mask == 0 && nq >= 3 && (nitems & 7) == 0;
                     if (use_dmma && nq <= 4) {
-                        const DenseTab* T = (A.dense_tabs && op.dtab > 0) ? A.dense_tabs + (op.dtab - 1) : nullptr;
+                        const DenseTab* T = (A.dense_tabs && op.dtab > 0) ? A.dense_tabs + 3 * (op.dtab - 1) : nullptr;
                         if (!T) {  // no precomputed table (parametric dense op): build it in the staging area
                             DenseTab* Ts = reinterpret_cast<DenseTab*>(sk);
                             int* schoice = reinterpret_cast<int*>(Ts + 1);
@@ -1641,6 +1647,17 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                             sb[e1] = cfma(k11, b1, cmul(k01, b0));
                         }
                         if (has_w) warp_store_w<4>(W, wslot, lane, wdirect);
+                    } else if (A.dense_tabs && op.dtab > 0 && !has_w && op.ctrl_mask == 0 && ((((rows >> op.nq) << LOG_CT) & 7) == 0)) {
+                        // constant dense 3-/4-qubit kernel (GENERAL blocks, multiplied-out constant sub-circuits): the adjoint
+                        // step is two forward-style products on the tensor cores with the op's K^dagger and K^T tables
+                        const DenseTab* T = A.dense_tabs + 3 * (op.dtab - 1);
+                        if (op.nq == 3) {
+                            dense_dmma_forward2<LOG_CT, 3>(sa, T + 1, op, rows, tid, nthr);
+                            dense_dmma_forward2<LOG_CT, 3>(sb, T + 2, op, rows, tid, nthr);
+                        } else {
+                            dense_dmma_forward2<LOG_CT, 4>(sa, T + 1, op, rows, tid, nthr);
+                            dense_dmma_forward2<LOG_CT, 4>(sb, T + 2, op, rows, tid, nthr);
+                        }
                     } else {
                         // raw dense op (controlled two-target gates, GENERAL blocks, or a block too small for the tensor
                         // path): thread per (group, column), local arrays

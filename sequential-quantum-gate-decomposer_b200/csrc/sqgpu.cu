@@ -859,7 +859,7 @@ int run_dense_tabs(sqgpu_ctx* c, int log_ct, cudaStream_t st) {
     Plan* P = c->P;
     if ((P->n_dense == 0 && P->n_dense5 == 0) || P->dense_logct == log_ct) return SQGPU_OK;
     int rc;
-    if ((rc = P->wDenseTab.ensure(std::max<size_t>(1, (size_t)P->n_dense) * sizeof(DenseTab)))) return rc;
+    if ((rc = P->wDenseTab.ensure(std::max<size_t>(1, (size_t)3 * P->n_dense) * sizeof(DenseTab)))) return rc;  // K, K^dagger, K^T per op
     if ((rc = P->wDenseTab5.ensure(std::max<size_t>(1, (size_t)P->n_dense5) * sizeof(DenseTab5)))) return rc;
     const DevOp* ops = P->dOps.as<DevOp>();
     const cplx* pool = c->dPool.as<cplx>();
@@ -999,13 +999,14 @@ void exec_flops(const Plan& P, int rows, int cols, int log_ct, bool grad, int ys
                 per8 = op.dim == 8 ? (8.0 + (grad ? 16.0 + (has_w ? 8.0 : 0.0) : 0.0)) : (2.0 + (grad ? 4.0 + (has_w ? 2.0 : 0.0) : 0.0));
             }
             t += items / 8.0 * per8 * 512.0;
-        } else if (op.ctrl_mask == 0 && op.nq >= 3 && op.type == SQGPU_GENERAL && !grad) {
+        } else if (op.ctrl_mask == 0 && op.nq >= 3 && op.type == SQGPU_GENERAL && (!grad || op.dtab > 0) && ((((rows >> op.nq) << log_ct) & 7) == 0)) {
             const double nt = op.dim / 4.0;
+            const double passes = grad ? 3.0 : 1.0;  // forward, and in the adjoint sweep K^dagger a and K^T beta (constant kernels: no W')
             if (SQ_DENSE_3M && op.nq <= 4) {  // three-product form: 3 x (dim / 8) x (dim / 4) DMMA and dim / 4 DADD per batch
-                t += items / 8.0 * (nt * nt * 1.5) * 512.0;
-                sc += items / 8.0 * 32.0 * nt;
+                t += passes * items / 8.0 * (nt * nt * 1.5) * 512.0;
+                sc += passes * items / 8.0 * 32.0 * nt;
             } else {
-                t += items / 8.0 * (nt * nt * 2.0) * 512.0;
+                t += passes * items / 8.0 * (nt * nt * 2.0) * 512.0;
             }
         } else {
             const double act = items / (double)(1 << popcount32(op.ctrl_mask));
