@@ -17,17 +17,34 @@ namespace sq {
 // traces layout helpers
 __host__ __device__ __forceinline__ size_t tr_index(int y, int k, int n_k, int t) { return (((size_t)y * n_k + k) * 3 + t) * 2; }
 
-// w_part[y][0][e] <- sum over chunks of w_part[y][chunk][e], chunks in ascending order (fixed summation order): one
-// coalesced pass over the partials instead of one strided gather per parameter in reduce_partials
-__global__ void fold_w_chunks(cplx* __restrict__ w_part, int nchunks, int w_total) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= w_total) return;
-    cplx* base = w_part + (size_t)blockIdx.y * nchunks * w_total + e;
-    cplx acc = base[0];
-    for (int ch = 1; ch < nchunks; ++ch) acc = cadd(acc, base[(size_t)ch * w_total]);
-    base[0] = acc;
+// w_part[y][0][e] <- sum over chunks of w_part[y][chunk][e] in a fixed order: one coalesced pass over the partials instead of
+// one strided gather per parameter in reduce_partials. A block folds 32 consecutive elements; its 8 warps each sum every 8th
+// chunk (512 B per warp load), then warp 0 adds the 8 group sums in ascending order -- a single parameter set (BFGS: batch 1
+// with 512 chunks) keeps w_total / 32 blocks busy instead of w_total / 256 threads walking 512 chunks each.
+__global__ void __launch_bounds__(256) fold_w_chunks(cplx* __restrict__ w_part, int nchunks, int w_total) {
+    __shared__ cplx sgrp[8][32];
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int e = blockIdx.x * 32 + lane;
+    cplx acc = czero();
+    if (e < w_total) {
+        const cplx* base = w_part + (size_t)blockIdx.y * nchunks * w_total + e;
+        for (int ch = grp; ch < nchunks; ch += 8) acc = cadd(acc, base[(size_t)ch * w_total]);
+    }
+    sgrp[grp][lane] = acc;
+    __syncthreads();
+    if (grp == 0 && e < w_total) {
+        cplx t = sgrp[0][lane];
+#pragma unroll
+        for (int g = 1; g < 8; ++g) t = cadd(t, sgrp[g][lane]);
+        w_part[(size_t)blockIdx.y * nchunks * w_total + e] = t;
+    }
 }
+static inline unsigned fold_grid_x(int w_total) { return (unsigned)((w_total + 31) / 32); }
 
+// traces[y][0] <- sum of the trace partials; traces[y][1 + p] <- sum_{r, r2} (dK_p K^dagger)[r][r2] W'[r][r2] per parameter.
+// grid = (parameter sets, parameter blocks); ONE WARP per parameter: its lanes take the dim^2 entries (coalesced reads of the
+// derivative kernel, the kernel and W'), then a shuffle reduction in a fixed order. (Round 1 ran one thread per parameter in
+// one block per set: 0.7 ms for the 1290 parameters of C3 at batch 1 -- 40 % of a single evaluation's latency.)
 // w_folded: the W partials of chunk 0 already hold the sum over chunks (fold_w_chunks)
 __global__ void reduce_partials(const double* __restrict__ tr_part, int nchunks, const cplx* __restrict__ w_part,
                                 int w_total, const DevOp* __restrict__ ops, const int* __restrict__ param_op,
@@ -37,34 +54,43 @@ __global__ void reduce_partials(const double* __restrict__ tr_part, int nchunks,
     if (w_slices <= 0) w_slices = nchunks;  // slices of w_part per parameter set (chunks x warps with per-warp slices)
     const int y = blockIdx.x;
     const int n_k = 1 + (with_grad ? n_params : 0);
-    if (threadIdx.x < 6) {
+    if (blockIdx.y == 0 && threadIdx.x < 6) {
         double s = 0;
         for (int ch = 0; ch < nchunks; ++ch) s += tr_part[((size_t)y * nchunks + ch) * 6 + threadIdx.x];
         traces[tr_index(y, 0, n_k, 0) + threadIdx.x] = s;
     }
     if (!with_grad) return;
-    for (int p = threadIdx.x; p < n_params; p += blockDim.x) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int wch = w_folded ? 1 : w_slices;
+    for (int p = blockIdx.y * wpb + warp; p < n_params; p += gridDim.y * wpb) {
         const DevOp op = ops[param_op[p]];
-        const int d2 = op.dim * op.dim;
+        const int dim = op.dim, d2 = dim * dim;
         const cplx* dk = dktab + (size_t)y * dkern_total + op.dkern_off + param_slot[p] * d2;
         const cplx* kk = ktab + (size_t)y * kern_total + op.kern_off;  // parametric ops always have a table kernel
-        const int dim = op.dim;
         cplx acc = czero();
-        for (int r = 0; r < dim; ++r)
-            for (int r2 = 0; r2 < dim; ++r2) {
-                cplx w = czero();
-                const int wch = w_folded ? 1 : w_slices;
-                for (int ch = 0; ch < wch; ++ch) w = cadd(w, w_part[((size_t)y * w_slices + ch) * w_total + op.w_off + r * dim + r2]);
-                cplx dkk = czero();  // (dK K^dagger)[r][r2] = sum_c dK[r][c] conj(K[r2][c])
-                for (int c = 0; c < dim; ++c) dkk = cfmac(kk[r2 * dim + c], dk[r * dim + c], dkk);
-                acc = cfma(dkk, w, acc);
-            }
-        double* dst = traces + tr_index(y, 1 + p, n_k, 0);
-        dst[0] = acc.x;
-        dst[1] = acc.y;
-        dst[2] = dst[3] = dst[4] = dst[5] = 0.0;
+        for (int e = lane; e < d2; e += 32) {
+            const int r = e / dim, r2 = e - r * dim;
+            cplx w = czero();
+            for (int ch = 0; ch < wch; ++ch) w = cadd(w, w_part[((size_t)y * w_slices + ch) * w_total + op.w_off + e]);
+            cplx dkk = czero();  // (dK K^dagger)[r][r2] = sum_c dK[r][c] conj(K[r2][c])
+            for (int c = 0; c < dim; ++c) dkk = cfmac(kk[r2 * dim + c], dk[r * dim + c], dkk);
+            acc = cfma(dkk, w, acc);
+        }
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) {
+            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, sft);
+            acc.y += __shfl_xor_sync(0xffffffffu, acc.y, sft);
+        }
+        if (lane == 0) {
+            double* dst = traces + tr_index(y, 1 + p, n_k, 0);
+            dst[0] = acc.x;
+            dst[1] = acc.y;
+            dst[2] = dst[3] = dst[4] = dst[5] = 0.0;
+        }
     }
 }
+// parameter blocks per set: four warps (= four parameters at a time) per block, at most 64 blocks
+static inline unsigned reduce_grid_y(int n_params) { return (unsigned)std::max(1, std::min(64, (n_params + 3) / 4)); }
 
 struct CostCfg {
     int variant;

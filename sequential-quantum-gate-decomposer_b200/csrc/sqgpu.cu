@@ -958,10 +958,10 @@ int run_exec_resident(sqgpu_ctx* c, int batch, bool grad, const cplx* d_omega, d
     c->launches++;
     if (e != cudaSuccess) return fail(SQGPU_ERR_CUDA, "fused_exec launch failed: %s", cudaGetErrorString(e));
     if (grad && p.w_slices > 1 && c->P->w_total > 0) {
-        fold_w_chunks<<<dim3((c->P->w_total + 255) / 256, batch), 256, 0, st>>>(c->wWPart.as<cplx>(), p.w_slices, c->P->w_total);
+        fold_w_chunks<<<dim3(fold_grid_x(c->P->w_total), batch), 256, 0, st>>>(c->wWPart.as<cplx>(), p.w_slices, c->P->w_total);
         c->launches++;
     }
-    reduce_partials<<<batch, 128, 0, st>>>(c->wTrPart.as<double>(), p.chunks, c->wWPart.as<cplx>(), c->P->w_total,
+    reduce_partials<<<dim3(batch, reduce_grid_y(c->n_params)), 128, 0, st>>>(c->wTrPart.as<double>(), p.chunks, c->wWPart.as<cplx>(), c->P->w_total,
                                            c->P->dOps.as<DevOp>(), c->P->dParamOp.as<int>(), c->P->dParamOp.as<int>() + std::max(c->n_params, 1),
                                            c->P->wDKtab.as<cplx>(), c->P->dkern_total, c->P->wKtab.as<cplx>(), c->P->kern_total, c->n_params, grad ? 1 : 0, d_traces, 1,
                                            p.w_slices);
@@ -1386,10 +1386,10 @@ int run_exec_tall_window(sqgpu_ctx* c, int batch, bool grad, const cplx* d_omega
     }
     CUDA_TRY(cudaGetLastError());
     if (grad && pb.w_slices > 1 && c->P->w_total > 0) {
-        fold_w_chunks<<<dim3((c->P->w_total + 255) / 256, batch), 256, 0, st>>>(c->wWPart.as<cplx>(), pb.w_slices, c->P->w_total);
+        fold_w_chunks<<<dim3(fold_grid_x(c->P->w_total), batch), 256, 0, st>>>(c->wWPart.as<cplx>(), pb.w_slices, c->P->w_total);
         c->launches++;
     }
-    reduce_partials<<<batch, 128, 0, st>>>(tr_part, nchunks, c->wWPart.as<cplx>(), c->P->w_total, c->P->dOps.as<DevOp>(), c->P->dParamOp.as<int>(),
+    reduce_partials<<<dim3(batch, reduce_grid_y(c->n_params)), 128, 0, st>>>(tr_part, nchunks, c->wWPart.as<cplx>(), c->P->w_total, c->P->dOps.as<DevOp>(), c->P->dParamOp.as<int>(),
                                            c->P->dParamOp.as<int>() + std::max(c->n_params, 1), c->P->wDKtab.as<cplx>(), c->P->dkern_total,
                                            c->P->wKtab.as<cplx>(), c->P->kern_total, c->n_params, grad ? 1 : 0, d_traces, 1, pb.w_slices);
     c->launches++;
@@ -1472,10 +1472,10 @@ int run_exec_streaming(sqgpu_ctx* c, int batch, bool grad, const cplx* d_omega, 
     time_end(c, st);
     CUDA_TRY(cudaGetLastError());
     if (grad && nchunks > 1 && c->P->w_total > 0) {
-        fold_w_chunks<<<dim3((c->P->w_total + 255) / 256, batch), 256, 0, st>>>(c->wWPart.as<cplx>(), nchunks, c->P->w_total);
+        fold_w_chunks<<<dim3(fold_grid_x(c->P->w_total), batch), 256, 0, st>>>(c->wWPart.as<cplx>(), nchunks, c->P->w_total);
         c->launches++;
     }
-    reduce_partials<<<batch, 128, 0, st>>>(tr_part, nchunks, c->wWPart.as<cplx>(), c->P->w_total, c->P->dOps.as<DevOp>(), c->P->dParamOp.as<int>(),
+    reduce_partials<<<dim3(batch, reduce_grid_y(c->n_params)), 128, 0, st>>>(tr_part, nchunks, c->wWPart.as<cplx>(), c->P->w_total, c->P->dOps.as<DevOp>(), c->P->dParamOp.as<int>(),
                                            c->P->dParamOp.as<int>() + std::max(c->n_params, 1), c->P->wDKtab.as<cplx>(), c->P->dkern_total,
                                            c->P->wKtab.as<cplx>(), c->P->kern_total, c->n_params, grad ? 1 : 0, d_traces, 1);
     c->launches++;

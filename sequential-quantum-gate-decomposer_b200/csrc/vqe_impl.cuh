@@ -88,10 +88,10 @@ static int vqe_window_dev(sqgpu_ctx* c, const double* d_params, int batch, bool 
         }
         time_end(c, st);
         if (pb.w_slices > 1 && c->P->w_total > 0) {
-            fold_w_chunks<<<dim3((c->P->w_total + 255) / 256, nb), 256, 0, st>>>(c->wWPart.as<cplx>(), pb.w_slices, c->P->w_total);
+            fold_w_chunks<<<dim3(fold_grid_x(c->P->w_total), nb), 256, 0, st>>>(c->wWPart.as<cplx>(), pb.w_slices, c->P->w_total);
             c->launches++;
         }
-        reduce_partials<<<nb, 128, 0, st>>>(c->wTrPart.as<double>(), pb.chunks, c->wWPart.as<cplx>(), c->P->w_total, c->P->dOps.as<DevOp>(),
+        reduce_partials<<<dim3(nb, reduce_grid_y(c->n_params)), 128, 0, st>>>(c->wTrPart.as<double>(), pb.chunks, c->wWPart.as<cplx>(), c->P->w_total, c->P->dOps.as<DevOp>(),
                                             c->P->dParamOp.as<int>(), c->P->dParamOp.as<int>() + std::max(c->n_params, 1), c->P->wDKtab.as<cplx>(),
                                             c->P->dkern_total, c->P->wKtab.as<cplx>(), c->P->kern_total, c->n_params, 1, c->wTraces.as<double>(), 1, pb.w_slices);
         grad_from_traces<<<nb, 128, 0, st>>>(c->wTraces.as<double>(), c->n_params, 2.0, d_grad + (size_t)b0 * c->n_params);
@@ -188,7 +188,7 @@ static int vqe_dev(sqgpu_ctx* c, const double* d_params, int batch, bool with_gr
         }
         // dL_p = sum dK_p W  (same contraction as the unitary path), grad_p = 2 Re dL_p  (…Base.cpp:1180-1186)
         double* dummy_tr = c->wTrPart.as<double>() + (size_t)slice * nblk * 32;  // slice * 6 doubles, content unused
-        reduce_partials<<<nb, 128, 0, st>>>(dummy_tr, 1, c->wWPart.as<cplx>(), c->P->w_total, c->P->dOps.as<DevOp>(), c->P->dParamOp.as<int>(),
+        reduce_partials<<<dim3(nb, reduce_grid_y(c->n_params)), 128, 0, st>>>(dummy_tr, 1, c->wWPart.as<cplx>(), c->P->w_total, c->P->dOps.as<DevOp>(), c->P->dParamOp.as<int>(),
                                             c->P->dParamOp.as<int>() + std::max(c->n_params, 1), c->P->wDKtab.as<cplx>(), c->P->dkern_total,
                                             c->P->wKtab.as<cplx>(), c->P->kern_total, c->n_params, 1, c->wTraces.as<double>());
         grad_from_traces<<<nb, 128, 0, st>>>(c->wTraces.as<double>(), c->n_params, 2.0, d_grad + (size_t)b0 * c->n_params);
