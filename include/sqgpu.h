@@ -198,7 +198,9 @@ int sqgpu_plan_ops(const sqgpu_gate_desc* gates, int n_gates, int n_params, int 
  *   vqe_stream (0/1)       VQE through the streaming kernels instead of the windowed executor
  *   window (1..30)         window width of the state-vector / tall-matrix segment planner (default 11)
  *   tall_window (0/1)      matrices whose column does not fit shared memory go through the windowed executor (default 1)
- *   async_tiles (0/1)      windowed executor loads / stores its tiles with the bulk-async (TMA) pipeline (default 1)
+ *   async_tiles (0/1)      windowed executor, -DSQ_WIN_BULK=1 builds only: double-buffered tiles in the forward segments
+ *   const_fuse_qubits (0, 4, 5)  constant sub-circuits (gates without parameters) are multiplied out on the host into dense
+ *                          kernels of up to this many qubits where that needs fewer flops than 3-qubit blocks (default 4; 0: off)
  *   split, split_force, threads, ctas_per_sm   CTA-shape experiments of the launch planner
  *   verbose (0/1) */
 int sqgpu_set_option(sqgpu_handle_t h, const char* name, int64_t value);
