@@ -56,8 +56,8 @@ METRIC = "cost+grad evals/s (10-qubit unitary decomposition)"
 UNIT = "evals/s"
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE fused_exec<GRAD> launch of the default workload (n=10, L=4, batch 256):
 # an OFFLINE ncu capture, not measured in this run -- see TRAFFIC_SOURCE. null for every other workload.
-TRAFFIC_DEFAULT_WORKLOAD = 1376906752
-TRAFFIC_SOURCE = {"kind": "offline_capture", "file": "profiles/r1_ncu_fused_grad_v10_b256.csv", "commit": "2e0f9aa",
+TRAFFIC_DEFAULT_WORKLOAD = 762308352 + 537867264
+TRAFFIC_SOURCE = {"kind": "offline_capture", "file": "profiles/r2_ncu_fused_grad_b256.csv", "commit": "4edd65a",
                   "note": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one launch; refreshed per round when the kernel changes"}
 
 

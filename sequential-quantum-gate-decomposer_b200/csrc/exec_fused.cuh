@@ -837,7 +837,7 @@ __device__ __forceinline__ void dense_tab_fill(TAB* T, int* schoice, const cplx*
     }
     __syncthreads();
     const int ja = schoice[0], jb = schoice[1];
-    if (SQ_DENSE_3M && KQ <= 4) {
+    if (SQ_DENSE_3M) {
         // three-product form: frag[(m * NTL + nt) * NT + ks][lane], m in {0: C, 1: D - C, 2: -(C + D)} of K = C + iD, n-tile nt
         // (8 output amplitudes), k-step ks (4 input amplitudes). Lane (k = lane & 3, n = lane >> 2) holds the entry
         // [out amplitude dep(n >> 1, (n & 1) | 2 nt)][in amplitude dep(k, ks)]: the lane's inputs dep(j, u), u < NT, are its outputs
@@ -879,11 +879,53 @@ __global__ void build_dense_tabs(const DevOp* __restrict__ ops, int n_ops, const
     }
 }
 
-// 5-qubit kernels: 128 DMMA per 8-item batch, kernel fragments streamed from the (L1-resident) table
+// 5-qubit kernels: 96 DMMA per 8-item batch in the three-product form (128 in the real embedding), kernel fragments streamed
+// from the (L1-resident) table
 template <int LOG_CT>
 __device__ __forceinline__ void dense_dmma_forward5(cplx* sa, const DenseTab5* __restrict__ T, const DevOp& op, int rows, int tid, int nthr) {
-    constexpr int KQ = 5, NT = 8, KS = 16, TH = 4;  // n-tiles are processed in two halves of TH (8 accumulator registers live)
+    constexpr int KQ = 5, NT = 8;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
+    if constexpr (SQ_DENSE_3M != 0) {
+        // per n-tile (8 output amplitudes): k1 = C (u + v) over the 8 k-steps, then Re = k1 - (C + D) v and Im = k1 + (D - C) u on
+        // copies of k1; the lane's outputs of n-tile nt are the amplitudes it loaded as x[2 nt], x[2 nt + 1]
+        constexpr int NTL = 4;
+        int sl3[NT], q3[KQ];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) sl3[t] = T->sl[t][lane];
+#pragma unroll
+        for (int j = 0; j < KQ; ++j) q3[j] = op.q[j];
+        const double* __restrict__ fr = T->frag + lane;
+        const int nitems3 = (rows >> KQ) << LOG_CT;
+        for (int b0 = warp * 8; b0 < nitems3; b0 += nwarps * 8) {
+            int base = b0 >> LOG_CT;
+#pragma unroll
+            for (int j = 0; j < KQ; ++j) base = insert_zero(base, q3[j]);
+            const int B0 = elem<LOG_CT>(base, 0);
+            cplx x[NT];
+            double sm[NT];
+#pragma unroll
+            for (int u = 0; u < NT; ++u) {
+                x[u] = sa[B0 ^ sl3[u]];
+                sm[u] = x[u].x + x[u].y;
+            }
+#pragma unroll
+            for (int nt = 0; nt < NTL; ++nt) {
+                double k1[2] = {0.0, 0.0};
+#pragma unroll
+                for (int ks = 0; ks < NT; ++ks) dmma_m8n8k4(k1[0], k1[1], sm[ks], __ldg(fr + ((0 * NTL + nt) * NT + ks) * 32));
+                double re[2] = {k1[0], k1[1]}, im[2] = {k1[0], k1[1]};
+#pragma unroll
+                for (int ks = 0; ks < NT; ++ks) {
+                    dmma_m8n8k4(re[0], re[1], x[ks].y, __ldg(fr + ((2 * NTL + nt) * NT + ks) * 32));
+                    dmma_m8n8k4(im[0], im[1], x[ks].x, __ldg(fr + ((1 * NTL + nt) * NT + ks) * 32));
+                }
+                // a lane's stores hit elements it loaded itself (all of them are in x[] by now): no hazard with other lanes
+                sa[B0 ^ sl3[2 * nt]] = cmake(re[0], im[0]);
+                sa[B0 ^ sl3[2 * nt + 1]] = cmake(re[1], im[1]);
+            }
+        }
+    } else {
+    constexpr int KS = 16, TH = 4;  // real embedding: n-tiles are processed in two halves of TH (8 accumulator registers live)
     int sl[NT], q[KQ];
 #pragma unroll
     for (int t = 0; t < NT; ++t) sl[t] = T->sl[t][lane];
@@ -916,6 +958,7 @@ __device__ __forceinline__ void dense_dmma_forward5(cplx* sa, const DenseTab5* _
             for (int t = 0; t < TH; ++t) sa[B0 ^ __ldg(&T->sl[th * TH + t][lane])] = d[t];  // (slot re-read: no dynamic register index)
         }
     }
+}
 }
 
 

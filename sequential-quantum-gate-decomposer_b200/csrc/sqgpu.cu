@@ -1002,7 +1002,7 @@ void exec_flops(const Plan& P, int rows, int cols, int log_ct, bool grad, int ys
         } else if (op.ctrl_mask == 0 && op.nq >= 3 && op.type == SQGPU_GENERAL && (!grad || op.dtab > 0) && ((((rows >> op.nq) << log_ct) & 7) == 0)) {
             const double nt = op.dim / 4.0;
             const double passes = grad ? 3.0 : 1.0;  // forward, and in the adjoint sweep K^dagger a and K^T beta (constant kernels: no W')
-            if (SQ_DENSE_3M && op.nq <= 4) {  // three-product form: 3 x (dim / 8) x (dim / 4) DMMA and dim / 4 DADD per batch
+            if (SQ_DENSE_3M) {  // three-product form: 3 x (dim / 8) x (dim / 4) DMMA and dim / 4 DADD per batch
                 t += passes * items / 8.0 * (nt * nt * 1.5) * 512.0;
                 sc += passes * items / 8.0 * 32.0 * nt;
             } else {
