@@ -184,7 +184,9 @@ int sqgpu_plan_stats_opt(const sqgpu_gate_desc* gates, int n_gates, int n_params
                          int64_t pool_len, const char* options, int64_t* stats, int n_stats);
 
 /* The op list the planner produces, for inspection (docs, tests): ops[i*8 .. i*8+8) = {dim, q0..q4 (-1: unused), n_params,
- * n_members} of op i; which = 2 / 3: the <=2- / <=3-qubit block plans, 0: the window plan in segment order. No device needed. */
+ * n_members} of op i; which = 2 / 3: the <=2- / <=3-qubit block plans, 0: the window plan in segment order, 11 / 12 / 13: the
+ * cluster plans for 2 / 4 / 8 CTAs (qubits are row-bit positions there; a RESPLIT op has dim 0 and {local row bit, cluster-rank
+ * bit}; *n_ops = 0: the circuit has no cluster plan). No device needed. */
 int sqgpu_plan_ops(const sqgpu_gate_desc* gates, int n_gates, int n_params, int qbit_num, const double* matrix_pool,
                    int64_t pool_len, const char* options, int which, int32_t* ops, int cap, int* n_ops);
 
@@ -199,6 +201,9 @@ int sqgpu_plan_ops(const sqgpu_gate_desc* gates, int n_gates, int n_params, int 
  *   window (1..30)         window width of the state-vector / tall-matrix segment planner (default 11)
  *   tall_window (0/1)      matrices whose column does not fit shared memory go through the windowed executor (default 1)
  *   async_tiles (0/1)      windowed executor, -DSQ_WIN_BULK=1 builds only: double-buffered tiles in the forward segments
+ *   cluster (0/1/2)        thread-block-cluster executor (2 / 4 / 8 CTAs share a column over distributed shared memory): 0 off,
+ *                          1 (default) where a column fits one CTA only once per SM (n = 12 gradient) or no window plan exists,
+ *                          2 also instead of the windowed executor (gradient n >= 13, cost n >= 14)
  *   const_fuse_qubits (0, 4, 5)  constant sub-circuits (gates without parameters) are multiplied out on the host into dense
  *                          kernels of up to this many qubits where that needs fewer flops than 3-qubit blocks (default 4; 0: off)
  *   split, split_force, threads, ctas_per_sm   CTA-shape experiments of the launch planner

@@ -256,7 +256,7 @@ def plan_ops(circuit, which=3, **options):
     descs, pool = circuit.descriptors()
     descs = np.ascontiguousarray(descs, dtype=GATE_DESC_DTYPE)
     pool = np.ascontiguousarray(pool, dtype=np.complex128)
-    cap = len(descs) + 1
+    cap = 2 * len(descs) + 1  # (cluster plans add RESPLIT ops)
     out = np.zeros((cap, 8), dtype=np.int32)
     n = C.c_int(0)
     opts = ",".join("%s=%d" % (k, int(v)) for k, v in options.items()).encode() or None

@@ -31,6 +31,7 @@
 // subset of `n_win` qubits (ExecArgs::wmask), the columns those of the other bits; MODE_APPLY / MODE_BWD run one SEGMENT of
 // the window plan (sqgpu.cu: build_window_plan) per launch.
 #pragma once
+#include <cooperative_groups.h>
 #include "sq_types.cuh"
 #include "../../include/sqgpu.h"
 
@@ -85,6 +86,9 @@ struct ExecArgs {
     int dense_stage;         // complex elements of kernel staging for the generic dense path (0: none)
     int wmax;                // max dim*dim over parametric ops (complex), >= 4
     int dbuf;                // window forward segments: two tile buffers, the next tile streams in while this one is computed
+    int rho;                 // cluster executor: log2(CTAs per cluster); `rows` is then the rows ONE CTA holds (2^(n - rho))
+    signed char fin_pos[32]; // cluster executor: where logical qubit q sits after the forward sweep: local row bit p (p < 32) or
+                             // cluster-rank bit p - 32
 };
 
 static const int FUSED_THREADS = 512;
@@ -256,12 +260,20 @@ template <int LOG_CT, int KQ>
 struct BlockGeom {
     static constexpr int CT = 1 << LOG_CT;
     static constexpr int LOGG = 3 - LOG_CT;  // log2(groups per 8-item batch)
-    int q[3];   // block qubits, ascending (unused = 30)
+    int q[3];   // block qubits in kernel order: amplitude bit j <-> q[j] (unused = 30)
+    int qs[3];  // the same, ascending (where zero bits are inserted)
     int Pq[3];  // address image (complex units) of row bit q[j]
     int F[3];   // address image of the j-th lowest row bit that is NOT a block qubit (group-offset bits inside a batch)
 
     __device__ __forceinline__ void init(int q0, int q1, int q2) {
         q[0] = q0; q[1] = q1; q[2] = q2;
+        {
+            int s0 = q0, s1 = KQ > 1 ? q1 : 30, s2 = KQ > 2 ? q2 : 30;
+            if (s0 > s1) { const int t = s0; s0 = s1; s1 = t; }
+            if (s1 > s2) { const int t = s1; s1 = s2; s2 = t; }
+            if (s0 > s1) { const int t = s0; s0 = s1; s1 = t; }
+            qs[0] = s0; qs[1] = s1; qs[2] = s2;
+        }
 #pragma unroll
         for (int j = 0; j < 3; ++j) Pq[j] = (j < KQ) ? elem<LOG_CT>(1 << q[j], 0) : 0;
         int f = 0;
@@ -272,11 +284,12 @@ struct BlockGeom {
             ++f;
         }
     }
-    // B0 (complex units) of the batch starting at item b0 (b0 % 8 == 0)
+    // B0 (complex units) of the batch starting at item b0 (b0 % 8 == 0). The block qubits are in KERNEL order (amplitude bit
+    // j <-> q[j]); the cluster planner's row-bit relabelling can leave them unsorted, the zero bits go in ascending order.
     __device__ __forceinline__ int batch_base(int b0) const {
         int base = b0 >> LOG_CT;
 #pragma unroll
-        for (int j = 0; j < KQ; ++j) base = insert_zero(base, q[j]);
+        for (int j = 0; j < KQ; ++j) base = insert_zero(base, qs[j]);
         return elem<LOG_CT>(base, 0);
     }
     // lane-constant part of the address (complex units) of local amplitude `amp` of batch item `item` (0..7)
@@ -369,6 +382,12 @@ static const int B0TAB = 64;  // batch bases precomputed per op (tiles with more
 // instead of 32 / 8 doubles; 0: the real embedding. 5-qubit kernels keep the real embedding (their fragments stream from L1).
 #ifndef SQ_DENSE_3M
 #define SQ_DENSE_3M 1
+#endif
+// The same for 5-qubit kernels (32 x 32): 96 instead of 128 DMMA per batch, but 16 more live operand registers -- measured: the
+// kernel spills (820 B at the 128-register cap), 64 5-qubit blocks at n = 12 run at 67.4 instead of 93.1 evals/s, and the extra
+// code costs the C3 gradient kernel 1.3 % (1 479 against 1 498 evals/s). 0 (default): 5-qubit kernels keep the real embedding.
+#ifndef SQ_DENSE5_3M
+#define SQ_DENSE5_3M 0
 #endif
 
 struct OpTab {
@@ -837,7 +856,7 @@ __device__ __forceinline__ void dense_tab_fill(TAB* T, int* schoice, const cplx*
     }
     __syncthreads();
     const int ja = schoice[0], jb = schoice[1];
-    if (SQ_DENSE_3M) {
+    if ((KQ <= 4 && SQ_DENSE_3M) || (KQ == 5 && SQ_DENSE5_3M)) {
         // three-product form: frag[(m * NTL + nt) * NT + ks][lane], m in {0: C, 1: D - C, 2: -(C + D)} of K = C + iD, n-tile nt
         // (8 output amplitudes), k-step ks (4 input amplitudes). Lane (k = lane & 3, n = lane >> 2) holds the entry
         // [out amplitude dep(n >> 1, (n & 1) | 2 nt)][in amplitude dep(k, ks)]: the lane's inputs dep(j, u), u < NT, are its outputs
@@ -879,13 +898,13 @@ __global__ void build_dense_tabs(const DevOp* __restrict__ ops, int n_ops, const
     }
 }
 
-// 5-qubit kernels: 96 DMMA per 8-item batch in the three-product form (128 in the real embedding), kernel fragments streamed
-// from the (L1-resident) table
+// 5-qubit kernels: 128 DMMA per 8-item batch in the real embedding (96 in the three-product form, SQ_DENSE5_3M), kernel
+// fragments streamed from the (L1-resident) table
 template <int LOG_CT>
 __device__ __forceinline__ void dense_dmma_forward5(cplx* sa, const DenseTab5* __restrict__ T, const DevOp& op, int rows, int tid, int nthr) {
     constexpr int KQ = 5, NT = 8;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
-    if constexpr (SQ_DENSE_3M != 0) {
+    if constexpr (SQ_DENSE5_3M != 0) {
         // per n-tile (8 output amplitudes): k1 = C (u + v) over the 8 k-steps, then Re = k1 - (C + D) v and Im = k1 + (D - C) u on
         // copies of k1; the lane's outputs of n-tile nt are the amplitudes it loaded as x[2 nt], x[2 nt + 1]
         constexpr int NTL = 4;
@@ -1082,7 +1101,13 @@ __device__ int g_trace_arrivals;
 #define SQ_TRACE_NEXT()
 #endif
 
-template <int MODE, int LOG_CT>
+// CLU: cluster executor (cost / gradient of matrices whose column -- or column + row functional -- does not fit ONE CTA's
+// shared memory, n = 12...15): the 2^rho CTAs of a thread-block cluster share a column tile, CTA `rank` holding the rows whose
+// `rho` SPLIT qubits spell its rank. Ops never touch a split qubit: the host planner (build_cluster_plan) inserts RESPLIT ops
+// that exchange a split qubit with a local one through distributed shared memory (each CTA swaps half of its tile with ONE
+// partner) before an op needs it, and rewrites every op's qubits to the row-bit positions they have at that point. Everything
+// else -- block path, tables, W' slices, trace partials (one chunk per CTA) -- is the single-CTA executor.
+template <int MODE, int LOG_CT, bool CLU = false>
 __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int CT = 1 << LOG_CT;
@@ -1114,6 +1139,18 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
 
     const int chunk = blockIdx.x;
     const int nchunks = gridDim.x;
+    // cluster executor: rank of this CTA inside its cluster, cluster index (tiles are dealt to clusters)
+    unsigned crank = 0;
+    int tile_owner = chunk;
+    __shared__ signed char sfin[CLU ? 32 : 1];  // cluster executor: A.fin_pos (indexed dynamically: kept out of the parameter space)
+    if constexpr (CLU) {
+        crank = cooperative_groups::this_cluster().block_rank();
+        tile_owner = chunk >> A.rho;
+        if (tid == 0) {
+#pragma unroll
+            for (int qb = 0; qb < 32; ++qb) sfin[qb] = A.fin_pos[qb];
+        }
+    }
 #if SQ_TRACE
     int trace_slot = -1, trace_ev = 0;
     {
@@ -1163,6 +1200,11 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
         s.q0 = op.dim == 2 ? op.target : op.q[0];
         s.q1 = op.dim == 2 ? 30 : op.q[1];
         s.q2 = op.dim == 8 ? op.q[2] : 30;
+        if (CLU && op.type == SQ_OP_RESPLIT) {  // cluster executor: q0 = local row bit, q1 = cluster-rank bit
+            s.kind = 3;
+            s.q0 = op.target;
+            s.q1 = op.nq;
+        }
         sops[k] = s;
     }
     if (HAS_B && A.w_in_smem) {
@@ -1218,7 +1260,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
     auto tab_prefetch = [&](int k, bool bwd) {
         constexpr int FRAG = 8 * 32 * 8, TAIL = (int)(sizeof(OpTabS) - 2 * FRAG);  // bytes of one fragment set / of slots + widx + b0
         if (TAB_BULK) {
-            if (tid != 0 || k < 0 || k >= A.n_ops || sops[k].kind == 1) return;
+            if (tid != 0 || k < 0 || k >= A.n_ops || sops[k].kind == 1 || (CLU && sops[k].kind == 3)) return;
             const char* src = reinterpret_cast<const char*>(gtabs + k);
             const int slot = k & (TAB_RING - 1);
             const unsigned dst = (unsigned)__cvta_generic_to_shared(stab + slot);
@@ -1244,7 +1286,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
         // op ends, "at most TAB_RING - 2 groups pending" means the NEXT op's table has landed; the end-of-op barrier publishes
         // it. With SQ_PRELOAD the operands of the next op are read BEFORE that barrier, so tables are waited for one op
         // earlier ("at most TAB_RING - 3 pending") and every table is published by the barrier one op before its first reader.
-        if (!(k < 0 || k >= A.n_ops || sops[k].kind == 1)) {
+        if (!(k < 0 || k >= A.n_ops || sops[k].kind == 1 || (CLU && sops[k].kind == 3))) {
             const char* src = reinterpret_cast<const char*>(gtabs + k);
             const unsigned dst = (unsigned)__cvta_generic_to_shared(stab + (k & (TAB_RING - 1)));
             if (sops[k].kind == 0) {
@@ -1262,7 +1304,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
     auto tab_acquire = [&](int k) {  // bulk ring: the table of op k (if it has one) has landed in its ring slot
-        if (k < 0 || k >= A.n_ops || sops[k].kind == 1) return;
+        if (k < 0 || k >= A.n_ops || sops[k].kind == 1 || (CLU && sops[k].kind == 3)) return;
         const int slot = k & (TAB_RING - 1);
         const unsigned bar = (unsigned)__cvta_generic_to_shared(tbar + slot);
         const unsigned parity = (tab_parity >> slot) & 1u;
@@ -1306,7 +1348,55 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    auto tile_of = [&](int ti) { return (WIN && A.wmask) ? ti * nchunks + chunk : chunk * A.tiles_per_cta + ti; };
+    auto tile_of = [&](int ti) { return (WIN && A.wmask) ? ti * nchunks + chunk : tile_owner * A.tiles_per_cta + ti; };
+    // logical row -> (owning rank, local row) under the layout the forward sweep ends in (cluster executor)
+    auto locate = [&](int lrow_logical, int& local) -> bool {
+        if constexpr (CLU) {
+            unsigned rk = 0;
+            int loc = 0;
+            for (int qb = 0; qb < A.n; ++qb)
+                if ((lrow_logical >> qb) & 1) {
+                    const int ps = sfin[qb];
+                    if (ps >= 32) rk |= 1u << (ps - 32);
+                    else loc |= 1 << ps;
+                }
+            local = loc;
+            return rk == crank;
+        } else {
+            local = lrow_logical;
+            return true;
+        }
+    };
+    // cluster executor, RESPLIT: exchange local row bit j with rank bit i. The elements of this CTA whose bit j differs from
+    // its rank bit i trade places with the partner's elements whose bit j equals it (same pair index = row with bit j removed);
+    // each CTA of the pair performs half of the swaps (pair parity), reading and writing the partner's tile through
+    // distributed shared memory.
+    auto resplit = [&](int j, int i, bool with_b) {
+        if constexpr (CLU) {
+            auto cluster = cooperative_groups::this_cluster();
+            cluster.sync();  // every CTA of the cluster has finished the previous op
+            const unsigned partner = crank ^ (1u << i);
+            const int my_bit = (crank >> i) & 1;
+            cplx* pa = cluster.map_shared_rank(sa, partner);
+            cplx* pb = cluster.map_shared_rank(sb, partner);
+            const int npairs = (rows >> 1) << LOG_CT;
+            for (int t = tid; 2 * t + my_bit < npairs; t += nthr) {
+                const int pid = 2 * t + my_bit;
+                const int cc = pid & (CT - 1);
+                const int x0 = insert_zero(pid >> LOG_CT, j);
+                const int em = elem<LOG_CT>(x0 | ((my_bit ^ 1) << j), cc), ep = elem<LOG_CT>(x0 | (my_bit << j), cc);
+                const cplx vm = sa[em], vp = pa[ep];
+                sa[em] = vp;
+                pa[ep] = vm;
+                if (HAS_B && with_b) {
+                    const cplx bm = sb[em], bp = pb[ep];
+                    sb[em] = bp;
+                    pb[ep] = bm;
+                }
+            }
+            cluster.sync();  // the exchange is complete before anyone touches the tiles again
+        }
+    };
     if (WIN && dbuf && A.tiles_per_cta > 0 && tile_of(0) < A.tiles) tile_request(tile_of(0), sa0);
 
     for (int ti = 0; ti < A.tiles_per_cta; ++ti) {
@@ -1334,7 +1424,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                     asm volatile("cp.async.wait_group 0;" ::: "memory");
                 }
             } else {
-                const cplx* __restrict__ src = A.in + (size_t)y * A.in_ystride + j0;
+                // cluster executor: the sweep starts with the top rho qubits as split qubits: CTA `crank` loads rows [crank * rows, ...)
+                const cplx* __restrict__ src = A.in + (size_t)y * A.in_ystride + j0 + (CLU ? (size_t)crank * rows * A.ld_in : 0);
                 for (int e = tid; e < rows * CT; e += nthr) {
                     const int i = e >> LOG_CT, c = e & (CT - 1);
                     cplx v = czero();
@@ -1364,7 +1455,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
             tab_prefetch(k + TAB_RING - 1, false);
             const cplx* __restrict__ km = reinterpret_cast<const cplx*>(stab + (k & (TAB_RING - 1)));
             SQ_TRACE_MARK(0)
-            if (s.kind == 2) {
+            if (CLU && s.kind == 3) {
+                resplit(s.q0, s.q1, false);
+            } else if (s.kind == 2) {
                 bool fused = false;
                 if constexpr (MODE == MODE_APPLY) {
                     if (gst_a && k == A.n_ops - 1) {  // last op of a window segment: results go straight to the state in HBM
@@ -1533,15 +1626,19 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                     }
                 }
             } else if (tid < valid) {
-                const cplx v = sa[elem<LOG_CT>(j0 + tid + off, tid)];
-                t[0] = v.x;
-                t[1] = v.y;
+                int lr;
+                if (locate(j0 + tid + off, lr)) {
+                    const cplx v = sa[elem<LOG_CT>(lr, tid)];
+                    t[0] = v.x;
+                    t[1] = v.y;
+                }
             }
             if (A.n_trace_types > 1) {
                 for (int e = tid; e < A.n * CT; e += nthr) {
                     const int c = e & (CT - 1), qb = e >> LOG_CT;
-                    if (c < valid) {
-                        const cplx v = sa[elem<LOG_CT>((j0 + c + off) ^ (1 << qb), c)];
+                    int lr;
+                    if (c < valid && locate((j0 + c + off) ^ (1 << qb), lr)) {
+                        const cplx v = sa[elem<LOG_CT>(lr, c)];
                         t[2] += v.x;
                         t[3] += v.y;
                     }
@@ -1553,9 +1650,12 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                     for (int q2 = q1 + 1; q2 < A.n; ++q2)
                         for (int c = 0; c < valid; ++c, ++e)
                             if (e % nthr == tid) {
-                                const cplx v = sa[elem<LOG_CT>((j0 + c + off) ^ ((1 << q1) | (1 << q2)), c)];
-                                t[4] += v.x;
-                                t[5] += v.y;
+                                int lr;
+                                if (locate((j0 + c + off) ^ ((1 << q1) | (1 << q2)), lr)) {
+                                    const cplx v = sa[elem<LOG_CT>(lr, c)];
+                                    t[4] += v.x;
+                                    t[5] += v.y;
+                                }
                             }
             }
             const int nt = 2 * A.n_trace_types;
@@ -1593,12 +1693,16 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
             } else {
                 const int off = A.trace_offset;
                 const cplx w0 = A.omega[(size_t)y * 3 + 0];
-                if (tid < valid) sb[elem<LOG_CT>(j0 + tid + off, tid)] = w0;
+                {
+                    int lr;
+                    if (tid < valid && locate(j0 + tid + off, lr)) sb[elem<LOG_CT>(lr, tid)] = w0;
+                }
                 if (A.n_trace_types > 1) {
                     const cplx w1 = A.omega[(size_t)y * 3 + 1];
                     for (int e = tid; e < A.n * CT; e += nthr) {
                         const int c = e & (CT - 1), qb = e >> LOG_CT;
-                        if (c < valid) sb[elem<LOG_CT>((j0 + c + off) ^ (1 << qb), c)] = w1;
+                        int lr;
+                        if (c < valid && locate((j0 + c + off) ^ (1 << qb), lr)) sb[elem<LOG_CT>(lr, c)] = w1;
                     }
                 }
                 if (A.n_trace_types > 2) {
@@ -1607,8 +1711,10 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                     for (int q1 = 0; q1 < A.n - 1; ++q1)
                         for (int q2 = q1 + 1; q2 < A.n; ++q2)
                             for (int c = 0; c < valid; ++c, ++e)
-                                if (e % nthr == tid)
-                                    sb[elem<LOG_CT>((j0 + c + off) ^ ((1 << q1) | (1 << q2)), c)] = w2;
+                                if (e % nthr == tid) {
+                                    int lr;
+                                    if (locate((j0 + c + off) ^ ((1 << q1) | (1 << q2)), lr)) sb[elem<LOG_CT>(lr, c)] = w2;
+                                }
                 }
             }
             __syncthreads();
@@ -1627,7 +1733,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                 const cplx* __restrict__ km = reinterpret_cast<const cplx*>(stab + (k & (TAB_RING - 1)));
                 int wdim = s.dim;
                 SQ_TRACE_MARK(0)
-                if (s.kind == 2) {
+                if (CLU && s.kind == 3) {
+                    resplit(s.q0, s.q1, true);
+                } else if (s.kind == 2) {
                     bool fused = false;
                     if constexpr (MODE == MODE_BWD) {
                         if (gst_a && k == 0) {  // last op of the segment's backward sweep: a and beta go straight to HBM
@@ -1803,6 +1911,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
         }
     }
 
+    if constexpr (CLU) cooperative_groups::this_cluster().sync();  // no CTA leaves while a partner may still touch its tile
     if (MODE == MODE_COST || MODE == MODE_GRAD) {
         if (tid == 0) {
             double* dst = A.tr_part + ((size_t)y * nchunks + chunk) * 6;

@@ -33,7 +33,9 @@ __host__ __device__ __forceinline__ cplx czero() { return make_double2(0.0, 0.0)
 // derivative of that matrix with respect to every parameter of its member gates -- is built per parameter set by
 // build_kernel_tables. Gates that cannot be fused (controls outside the pair, 3+ qubit dense kernels) stay "raw":
 // a 1-qubit gate with a control bit mask (dim == 2) or a dense dim x dim kernel on ascending qubits.
-enum { SQ_OP_BLOCK = 2000 };
+enum { SQ_OP_BLOCK = 2000,
+       // cluster executor only: exchange local row bit `target` with cluster-rank bit `nq` (no arithmetic), see exec_fused.cuh
+       SQ_OP_RESPLIT = 2001 };
 
 struct DevOp {
     int32_t type;         // sqgpu_gate_type of a raw op, or SQ_OP_BLOCK

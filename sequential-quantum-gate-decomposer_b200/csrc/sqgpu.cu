@@ -135,6 +135,8 @@ struct Options {
     int no_graph = 0;          // device-resident optimizer loops: plain launches instead of one CUDA graph replay per step
     int tall_window = 1;       // matrices whose column does not fit shared memory: windowed executor (0: streaming fallback)
     int async_tiles = 1;       // windowed executor (SQ_WIN_BULK builds): double-buffered tiles in the forward segments
+    int cluster = 1;           // thread-block-cluster executor: 0 off; 1 (default) where it is the measured winner (a column that
+                               // fits one CTA only once per SM) or the only fused option; 2: also instead of the windowed executor
     int const_fuse_qubits = 4; // constant sub-circuits are multiplied out on the host into dense blocks of up to this many qubits (0: off)
 };
 
@@ -156,6 +158,7 @@ const OptionName kOptionNames[] = {
     {"tall_window", &Options::tall_window, 0, 1},
     {"async_tiles", &Options::async_tiles, 0, 1},
     {"const_fuse_qubits", &Options::const_fuse_qubits, 0, 5},
+    {"cluster", &Options::cluster, 0, 2},
 };
 
 int option_set(Options& o, const char* name, long long value) {
@@ -226,6 +229,14 @@ struct sqgpu_ctx {
     // windowed state-vector executor (VQE): plan3's ops reordered into segments whose joint support fits `win_w` qubits,
     // qubit indices rewritten to positions inside the segment's window
     Plan planW;
+    // cluster executor (n >= 12): plan3 with RESPLIT ops inserted and qubits rewritten to row-bit positions, for clusters of
+    // 2^rho CTAs (index rho - 1); cl_fin[rho - 1][q] = where logical qubit q sits after the forward sweep
+    static const int MAX_RHO = 3;
+    Plan planC[MAX_RHO];
+    bool cl_ok[MAX_RHO] = {false, false, false};
+    signed char cl_fin[MAX_RHO][32];
+    int cl_resplits[MAX_RHO] = {0, 0, 0};
+    int use_rho = 0;                 // cluster size (log2) of the evaluation in progress; 0: single-CTA tiles
     struct Segment { int begin, end; unsigned wmask; };
     std::vector<Segment> segs;
     int win_w = 0;
@@ -573,6 +584,120 @@ int build_window_plan(sqgpu_ctx* c, bool upload) {
     return SQGPU_OK;
 }
 
+// Cluster plan (n >= 12; SURVEY a9/a10 for columns that do not fit ONE CTA's shared memory): plan3 for a thread-block cluster
+// of 2^rho CTAs that share a column tile. rho SPLIT qubits select the CTA, the other n - rho qubits the row inside it; an op
+// may only touch local qubits. The sweep starts with the top rho qubits split (CTA r loads rows [r 2^(n-rho), ...)). Before an
+// op that touches a split qubit s, a RESPLIT op exchanges s with a local qubit t that the op does not touch -- the one whose
+// next use lies farthest ahead (Belady) -- through distributed shared memory; from then on t selects the CTA and s sits on
+// t's old row bit. Every op's qubits are rewritten to the row-bit positions they have when it runs (kernel bit order is kept,
+// so a block's positions need not ascend: BlockGeom sorts them where it inserts zero bits). The backward sweep runs the same
+// list in reverse (a RESPLIT is its own inverse). Not available with raw dense / two-target ops (their generic paths want
+// ascending positions): returns false and the caller keeps the windowed executor.
+bool build_cluster_plan(sqgpu_ctx* c, int rho, bool upload, int* rc_out) {
+    *rc_out = SQGPU_OK;
+    const Plan& src = c->plan3;
+    Plan& dst = c->planC[rho - 1];
+    const int N = (int)src.ops.size(), n = c->qbit_num, L = n - rho;
+    c->cl_ok[rho - 1] = false;
+    if (L < 6) return false;
+    for (const DevOp& op : src.ops)
+        if (op.dim > 2 && op.type != SQ_OP_BLOCK) return false;
+    // next use of every qubit at or after op k
+    std::vector<int> nxt((size_t)(N + 1) * n, N + n);
+    for (int k = N - 1; k >= 0; --k) {
+        const unsigned sup = support_mask(src.ops[k]);
+        for (int q = 0; q < n; ++q) nxt[(size_t)k * n + q] = ((sup >> q) & 1) ? k : nxt[(size_t)(k + 1) * n + q];
+    }
+    std::vector<int> pos(n), inv_local(L), rank_q(rho);
+    for (int q = 0; q < n; ++q) pos[q] = q < L ? q : 32 + (q - L);
+    for (int q = 0; q < L; ++q) inv_local[q] = q;
+    for (int i = 0; i < rho; ++i) rank_q[i] = L + i;
+    dst.ops.clear();
+    std::vector<int> newidx(N, -1);
+    int n_resplit = 0;
+    for (int k = 0; k < N; ++k) {
+        DevOp op = src.ops[k];
+        const unsigned sup = support_mask(op);
+        for (int i = 0; i < rho; ++i) {
+            const int s = rank_q[i];
+            if (!((sup >> s) & 1)) continue;
+            int best_j = -1, best_next = -1;
+            for (int j = 0; j < L; ++j) {
+                const int t = inv_local[j];
+                if ((sup >> t) & 1) continue;
+                const int nu = nxt[(size_t)k * n + t];
+                if (nu > best_next) { best_next = nu; best_j = j; }
+            }
+            if (best_j < 0) return false;
+            const int t = inv_local[best_j];
+            DevOp r;
+            memset(&r, 0, sizeof(r));
+            r.type = SQ_OP_RESPLIT;
+            r.kern_off = r.dkern_off = r.w_off = -1;
+            r.member_off = -1;
+            r.target = best_j;
+            r.nq = i;
+            for (int f = 0; f < 6; ++f) r.fix[f] = 30;
+            dst.ops.push_back(r);
+            ++n_resplit;
+            rank_q[i] = t;
+            inv_local[best_j] = s;
+            pos[t] = 32 + i;
+            pos[s] = best_j;
+        }
+        if (op.dim == 2) op.target = pos[op.target];
+        else {
+            const bool hi_first = op.target == op.q[1];
+            for (int j = 0; j < op.nq; ++j) op.q[j] = pos[op.q[j]];
+            op.target = hi_first ? op.q[1] : op.q[0];
+        }
+        unsigned cm = 0;
+        for (int q = 0; q < n; ++q)
+            if ((op.ctrl_mask >> q) & 1) cm |= 1u << pos[q];
+        op.ctrl_mask = cm;
+        fill_fix(op);
+        newidx[k] = (int)dst.ops.size();
+        dst.ops.push_back(op);
+    }
+    for (int q = 0; q < 32; ++q) c->cl_fin[rho - 1][q] = (signed char)(q < n ? pos[q] : 0);
+    c->cl_resplits[rho - 1] = n_resplit;
+    dst.members = src.members;
+    dst.param_slot = src.param_slot;
+    dst.param_op = src.param_op;
+    for (auto& po : dst.param_op)
+        if (po >= 0) po = newidx[po];
+    dst.n_ops = (int)dst.ops.size();
+    dst.kern_total = src.kern_total;
+    dst.dkern_total = src.dkern_total;
+    dst.w_total = src.w_total;
+    dst.wmax = src.wmax;
+    dst.dense_stage = src.dense_stage;
+    dst.n_dense = dst.n_dense5 = 0;
+    dst.dense_logct = -1;
+    c->cl_ok[rho - 1] = true;
+    if (!upload) return true;
+    int rc;
+    const size_t np1 = std::max<size_t>(dst.param_op.size(), 1);
+    if ((rc = dst.dOps.ensure(std::max<size_t>(1, dst.ops.size()) * sizeof(DevOp))) || (rc = dst.dMembers.ensure(std::max<size_t>(1, dst.members.size()) * sizeof(DevMember))) ||
+        (rc = dst.dParamOp.ensure(2 * np1 * sizeof(int)))) {
+        *rc_out = rc;
+        return false;
+    }
+    cudaError_t e = cudaSuccess;
+    if (!dst.ops.empty()) e = cudaMemcpy(dst.dOps.p, dst.ops.data(), dst.ops.size() * sizeof(DevOp), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && !dst.members.empty()) e = cudaMemcpy(dst.dMembers.p, dst.members.data(), dst.members.size() * sizeof(DevMember), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && !dst.param_op.empty()) {
+        e = cudaMemcpy(dst.dParamOp.p, dst.param_op.data(), dst.param_op.size() * sizeof(int), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(dst.dParamOp.as<int>() + np1, dst.param_slot.data(), dst.param_slot.size() * sizeof(int), cudaMemcpyHostToDevice);
+    }
+    if (e != cudaSuccess) {
+        *rc_out = fail(SQGPU_ERR_CUDA, "cluster plan upload failed: %s", cudaGetErrorString(e));
+        c->cl_ok[rho - 1] = false;
+        return false;
+    }
+    return true;
+}
+
 // Lower one descriptor to a DevOp (offsets are assigned by the caller). Returns 0 or a status.
 int lower_gate(const sqgpu_gate_desc& g, int qbit_num, const double* pool, int64_t pool_len, DevOp* out, bool* unitary) {
     DevOp op;
@@ -681,6 +806,7 @@ struct FusedPlan {
     int log_ct = 0, threads = 32;
     int tiles = 0, tiles_per_cta = 1, chunks = 1;
     bool w_in_smem = false;
+    int rho = 0;            // cluster executor: log2(CTAs per cluster), rows per CTA = rows >> rho
     bool dbuf = false;      // window forward segments: two tile buffers
     bool w_direct = false;  // W' partials: one global slice per (parameter set, CTA, warp), see SQ_W_DIRECT
     int w_slices = 1;       // slices of w_part per parameter set = chunks * (w_direct ? warps per CTA : 1)
@@ -706,14 +832,15 @@ size_t fused_smem(int mode, int rows, int ct, int threads, int dense_stage, int 
     return s;
 }
 
-FusedPlan plan_fused(const sqgpu_ctx* c, int mode, int rows, int cols, int ysets, int default_split = 2, bool window = false) {
+FusedPlan plan_fused(const sqgpu_ctx* c, int mode, int rows, int cols, int ysets, int default_split = 2, bool window = false, int rho = 0) {
     FusedPlan p;
+    p.rho = rho;  // cluster executor: `rows` is what ONE CTA holds, chunks counts CTAs (clusters x 2^rho)
     // window forward segments: two tile buffers, the next tile streams in while the current one is computed (option async_tiles)
     const bool dbuf = (SQ_WIN_BULK != 0) && window && mode == MODE_APPLY && c->opt.async_tiles != 0;
     // test hook (option force_stream): cost / gradient evaluations go down the chunked streaming executor
     if (c->opt.force_stream && (mode == MODE_COST || mode == MODE_GRAD)) return p;
     const size_t budget = (size_t)c->smem_optin;
-    int max_log = 3;
+    int max_log = rho > 0 ? 1 : 3;  // (the cluster executor is instantiated for one- and two-column tiles)
     while ((1 << max_log) > cols && max_log > 0) --max_log;  // no wider than the matrix (cols = 1: state vector)
     auto threads_for = [&](int ct) {
         const int items = (rows / 4) * ct;  // groups of a two-qubit block
@@ -780,10 +907,11 @@ FusedPlan plan_fused(const sqgpu_ctx* c, int mode, int rows, int cols, int ysets
             // `slots` = SMs x resident CTAs -- so that the last wave is full (C5 backward: 19 chunks of 14 tiles need 9 waves for
             // 8.2 waves of work; 37 chunks of 7 tiles fill 16 waves exactly).
             const int per_sm = mode == MODE_BWD ? std::min(c->opt.ctas_per_sm, 8) : (mode == MODE_APPLY ? std::min(c->opt.ctas_per_sm, 16) : c->opt.ctas_per_sm);
-            const int want_ctas = c->sm_count * std::max(1, per_sm);
+            const int R = 1 << rho;  // the unit of the schedule is a cluster of R CTAs
+            const int want_ctas = std::max(1, c->sm_count * std::max(1, per_sm) / R);
             const int target = std::min(p.tiles, std::max(1, (want_ctas + ysets - 1) / ysets));
             const int resident = std::max(1, std::min((int)((size_t)c->smem_per_sm / (p.smem + 1024)), 65536 / (128 * std::max(p.threads, 32))));  // shared memory, 128 registers per thread
-            const long long slots = (long long)c->sm_count * resident;
+            const long long slots = std::max<long long>(1, (long long)c->sm_count * resident / R);
             long long best_cost = -1;
             int best_chunks = target;
             for (int ch = std::max(1, target / 2); ch <= std::min(p.tiles, 2 * target + 1); ++ch) {
@@ -798,7 +926,7 @@ FusedPlan plan_fused(const sqgpu_ctx* c, int mode, int rows, int cols, int ysets
                 }
             }
             p.tiles_per_cta = (p.tiles + best_chunks - 1) / best_chunks;
-            p.chunks = (p.tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
+            p.chunks = ((p.tiles + p.tiles_per_cta - 1) / p.tiles_per_cta) * R;
         }
         p.w_slices = p.chunks * (p.w_direct ? p.threads / 32 : 1);
     }
@@ -815,6 +943,39 @@ cudaError_t launch_fused_mode(const ExecArgs& a, const FusedPlan& p, int ysets, 
         if (e != cudaSuccess) return e;                                                                        \
         fused_exec<MODE, LC><<<grid, p.threads, p.smem, st>>>(a);                                              \
         break;
+    if (p.rho > 0) {
+        // cluster executor: 2^rho consecutive CTAs in x form a thread-block cluster (distributed shared memory)
+        if constexpr (MODE == MODE_COST || MODE == MODE_GRAD) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = grid;
+            cfg.blockDim = dim3(p.threads);
+            cfg.dynamicSmemBytes = p.smem;
+            cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 1u << p.rho;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+#define SQ_LAUNCH_CL(LC)                                                                                                  \
+    case LC:                                                                                                              \
+        e = cudaFuncSetAttribute(fused_exec<MODE, LC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);   \
+        if (e != cudaSuccess) return e;                                                                                   \
+        e = cudaLaunchKernelEx(&cfg, fused_exec<MODE, LC, true>, a);                                                      \
+        if (e != cudaSuccess) return e;                                                                                   \
+        break;
+            switch (p.log_ct) {
+                SQ_LAUNCH_CL(0)
+                SQ_LAUNCH_CL(1)
+                default: return cudaErrorInvalidValue;
+            }
+#undef SQ_LAUNCH_CL
+            return cudaGetLastError();
+        } else {
+            return cudaErrorInvalidValue;
+        }
+    }
     switch (p.log_ct) {
         SQ_LAUNCH(0)
         SQ_LAUNCH(1)
@@ -823,6 +984,31 @@ cudaError_t launch_fused_mode(const ExecArgs& a, const FusedPlan& p, int ysets, 
     }
 #undef SQ_LAUNCH
     return cudaGetLastError();
+}
+
+// launch plan of the cost / gradient executor for the evaluation in progress (single-CTA tiles or the cluster executor)
+FusedPlan plan_eval(const sqgpu_ctx* c, int mode, int ysets) {
+    if (c->use_rho > 0) return plan_fused(c, mode, c->rows >> c->use_rho, c->cols, ysets, 2, false, c->use_rho);
+    return plan_fused(c, mode, c->rows, c->cols, ysets);
+}
+
+// Cluster size (log2) for a cost / gradient evaluation: the smallest cluster whose per-CTA share of the column leaves two CTAs
+// per SM, else the smallest that fits at all; 0: no cluster plan for this circuit or nothing fits. Temporarily points c->P at
+// the candidate plans; the caller sets c->P afterwards.
+int pick_cluster_rho(sqgpu_ctx* c, bool grad, int batch) {
+    if (c->cfg.variant == SQGPU_SUM_OF_SQUARES || c->qbit_num < 12) return 0;
+    const int mode = grad ? MODE_GRAD : MODE_COST;
+    PlanScope keep(c);
+    int first_fit = 0;
+    for (int rho = 1; rho <= sqgpu_ctx::MAX_RHO; ++rho) {
+        if (!c->cl_ok[rho - 1]) continue;
+        c->P = &c->planC[rho - 1];
+        const FusedPlan p = plan_fused(c, mode, c->rows >> rho, c->cols, batch, 2, false, rho);
+        if (!p.ok) continue;
+        if (!first_fit) first_fit = rho;
+        if ((p.smem + 1024) * 2 <= (size_t)c->smem_per_sm) return rho;
+    }
+    return first_fit;
 }
 
 // ---- building blocks (all enqueue on `st`, no host sync) --------------------------------------------------------
@@ -902,6 +1088,8 @@ void fill_common_args(const sqgpu_ctx* c, const FusedPlan& p, ExecArgs& a, int r
     a.w_in_smem = p.w_in_smem ? 1 : 0;
     a.w_direct = p.w_direct ? 1 : 0;
     a.dbuf = p.dbuf ? 1 : 0;
+    a.rho = p.rho;
+    if (p.rho > 0) memcpy(a.fin_pos, c->cl_fin[p.rho - 1], sizeof(a.fin_pos));
 }
 
 void time_begin(sqgpu_ctx* c, const char* name, cudaStream_t st) {
@@ -928,7 +1116,7 @@ int launch_stream_gate(sqgpu_ctx* c, const DevOp& op, bool deriv, cplx* data, lo
 // fills wTrPart (and wWPart), then reduces into d_traces[batch][1+P or 1][3][2].
 int run_exec_resident(sqgpu_ctx* c, int batch, bool grad, const cplx* d_omega, double* d_traces, cudaStream_t st) {
     const int mode = grad ? MODE_GRAD : MODE_COST;
-    FusedPlan p = plan_fused(c, mode, c->rows, c->cols, batch);
+    FusedPlan p = plan_eval(c, mode, batch);
     if (!p.ok)  // column too tall for shared memory: windowed executor (planW) or one op per launch (plan2)
         return c->P == &c->planW ? run_exec_tall_window(c, batch, grad, d_omega, d_traces, st) : run_exec_streaming(c, batch, grad, d_omega, d_traces, st);
     int rc;
@@ -937,7 +1125,7 @@ int run_exec_resident(sqgpu_ctx* c, int batch, bool grad, const cplx* d_omega, d
     if ((rc = c->wTrPart.ensure((size_t)batch * p.chunks * 6 * sizeof(double)))) return rc;
     if (grad && (rc = c->wWPart.ensure(std::max<size_t>(1, (size_t)batch * p.w_slices * c->P->w_total) * sizeof(cplx)))) return rc;
     ExecArgs a;
-    fill_common_args(c, p, a, c->rows, c->cols);
+    fill_common_args(c, p, a, c->rows >> p.rho, c->cols);
     a.in = c->U.as<cplx>();
     a.in_ystride = 0;
     a.ld_in = c->cols;
@@ -950,7 +1138,7 @@ int run_exec_resident(sqgpu_ctx* c, int batch, bool grad, const cplx* d_omega, d
     if (grad && !p.w_in_smem && c->P->w_total > 0)
         CUDA_TRY(cudaMemsetAsync(c->wWPart.p, 0, (size_t)batch * p.w_slices * c->P->w_total * sizeof(cplx), st));
     c->last_shape[0] = p.log_ct; c->last_shape[1] = p.threads; c->last_shape[2] = p.chunks; c->last_shape[3] = p.tiles_per_cta;
-    c->last_shape[4] = (int)p.smem; c->last_shape[5] = 1;
+    c->last_shape[4] = (int)p.smem; c->last_shape[5] = 1 << p.rho;
     exec_flops(*c->P, c->rows, c->cols, p.log_ct, grad, batch, &c->last_flops[0], &c->last_flops[1]);
     time_begin(c, grad ? "fused_exec<GRAD>" : "fused_exec<COST>", st);
     cudaError_t e = grad ? launch_fused_mode<MODE_GRAD>(a, p, batch, st) : launch_fused_mode<MODE_COST>(a, p, batch, st);
@@ -980,6 +1168,7 @@ void exec_flops(const Plan& P, int rows, int cols, int log_ct, bool grad, int ys
     double t = 0, sc = 0;
     const double colsd = (double)cols;
     for (const DevOp& op : P.ops) {
+        if (op.type == SQ_OP_RESPLIT) continue;  // data exchange between the CTAs of a cluster: no arithmetic
         const bool has_w = op.w_off >= 0;
         if (op.dim == 2) {
             const double pairs = (double)(rows >> (op.ctrl_mask ? op.nfix : 1)) * colsd;
@@ -1002,7 +1191,7 @@ void exec_flops(const Plan& P, int rows, int cols, int log_ct, bool grad, int ys
         } else if (op.ctrl_mask == 0 && op.nq >= 3 && op.type == SQGPU_GENERAL && (!grad || op.dtab > 0) && ((((rows >> op.nq) << log_ct) & 7) == 0)) {
             const double nt = op.dim / 4.0;
             const double passes = grad ? 3.0 : 1.0;  // forward, and in the adjoint sweep K^dagger a and K^T beta (constant kernels: no W')
-            if (SQ_DENSE_3M) {  // three-product form: 3 x (dim / 8) x (dim / 4) DMMA and dim / 4 DADD per batch
+            if ((op.nq <= 4 && SQ_DENSE_3M) || (op.nq == 5 && SQ_DENSE5_3M)) {  // three-product form: 3 x (dim / 8) x (dim / 4) DMMA and dim / 4 DADD per batch
                 t += passes * items / 8.0 * (nt * nt * 1.5) * 512.0;
                 sc += passes * items / 8.0 * 32.0 * nt;
             } else {
@@ -1030,7 +1219,7 @@ int check_ready(const sqgpu_ctx* c, bool need_matrix) {
 // max parameter sets per executor launch so that the W partials stay below ~1.5 GiB
 int batch_slice(const sqgpu_ctx* c, int batch, bool grad) {
     {
-        FusedPlan pf = plan_fused(c, grad ? MODE_GRAD : MODE_COST, c->rows, c->cols, batch);
+        FusedPlan pf = plan_eval(c, grad ? MODE_GRAD : MODE_COST, batch);
         if (!pf.ok) return std::min(batch, 32);  // streaming fallback: bound the replicated chunk workspace
     }
     if (!grad || c->P->w_total == 0) return std::min(batch, 65535);
@@ -1038,7 +1227,7 @@ int batch_slice(const sqgpu_ctx* c, int batch, bool grad) {
     const size_t lim = (size_t)(SQ_W_DIRECT ? 8192 : 1536) << 20;  // B200: 180 GB of HBM
     int slice = std::min(batch, 65535);
     for (int it = 0; it < 16; ++it) {
-        const FusedPlan p = plan_fused(c, MODE_GRAD, c->rows, c->cols, slice);
+        const FusedPlan p = plan_eval(c, MODE_GRAD, slice);
         const size_t per = (size_t)std::max(1, p.w_slices) * c->P->w_total * sizeof(cplx);
         const int fit = (int)std::max<size_t>(1, std::min<size_t>((size_t)slice, lim / std::max<size_t>(per, 1)));
         if (fit >= slice) break;
@@ -1057,7 +1246,26 @@ int traces_dev(sqgpu_ctx* c, const double* d_params, int batch, bool with_grad, 
     if (batch <= 0) return SQGPU_OK;
     // three-qubit blocks for the shared-memory executor, two-qubit blocks for the streaming fallback
     c->P = &c->plan3;
-    if (!plan_fused(c, with_grad ? MODE_GRAD : MODE_COST, c->rows, c->cols, batch).ok) c->P = tall_window_fits(c, with_grad) ? &c->planW : &c->plan2;
+    c->use_rho = 0;
+    {
+        // Which executor (measured, profiles/README_r2.md): the single-CTA one wherever a column fits twice per SM; where it
+        // fits only once per SM (n = 12 gradient) a cluster of two CTAs with half the rows each (+2...6 %); where it does not
+        // fit at all (gradient n >= 13, cost n >= 14) the windowed executor, which beats the clusters from two adaptive levels
+        // on (n = 13: 180 against 172 evals/s, n = 14: 299 against 235) -- clusters there only on request (option cluster = 2)
+        // or when the circuit has no window plan; last the one-op-per-launch streaming kernels.
+        const FusedPlan p0 = plan_fused(c, with_grad ? MODE_GRAD : MODE_COST, c->rows, c->cols, batch);
+        int rho = 0;
+        if (c->opt.cluster) {
+            const bool one_per_sm = p0.ok && (p0.smem + 1024) * 2 > (size_t)c->smem_per_sm;
+            if (p0.ok ? (one_per_sm && c->qbit_num >= 12) : (c->opt.cluster == 2 || !tall_window_fits(c, with_grad))) rho = pick_cluster_rho(c, with_grad, batch);
+        }
+        if (rho > 0) {  // thread-block clusters share the column over distributed shared memory
+            c->P = &c->planC[rho - 1];
+            c->use_rho = rho;
+        } else if (!p0.ok) {
+            c->P = tall_window_fits(c, with_grad) ? &c->planW : &c->plan2;
+        }
+    }
     if (c->cols + effective_offset(c) > c->rows) return fail(SQGPU_ERR_INVALID, "trace_offset %d + cols %d exceeds rows %d", effective_offset(c), c->cols, c->rows);
     if (with_grad && !c->all_unitary) return fail(SQGPU_ERR_UNSUPPORTED, "gradient with a non-unitary GENERAL gate is not supported (the adjoint sweep needs K^-1 = K^dagger)");
     const bool hs_corr = c->cfg.variant == SQGPU_HILBERT_SCHMIDT_TEST_CORRECTION1 || c->cfg.variant == SQGPU_HILBERT_SCHMIDT_TEST_CORRECTION2;
@@ -1967,6 +2175,13 @@ static int set_circuit_impl(sqgpu_ctx* c, const sqgpu_gate_desc* gates, int n_ga
     c->n_const_fused = n_const_fused;
     c->qbit_num = qbit_num;
     if ((rc = build_window_plan(c, upload))) return rc;
+    for (int rho = 1; rho <= sqgpu_ctx::MAX_RHO; ++rho) {
+        c->cl_ok[rho - 1] = false;
+        if (qbit_num < 12 || !fuse) continue;
+        int rc2 = SQGPU_OK;
+        build_cluster_plan(c, rho, upload, &rc2);
+        if (rc2) return rc2;
+    }
     c->P = &c->plan2;
     c->n_gates = n_gates;
     c->n_params = n_params;
@@ -2021,14 +2236,23 @@ int sqgpu_plan_ops(const sqgpu_gate_desc* gates, int n_gates, int n_params, int 
     int rc = options_parse(tmp->opt, options);
     if (rc == SQGPU_OK) rc = set_circuit_impl(tmp, gates, n_gates, n_params, qbit_num, matrix_pool, pool_len, false);
     if (rc == SQGPU_OK) {
-        const Plan& P = which == 2 ? tmp->plan2 : (which == 3 ? tmp->plan3 : tmp->planW);
+        const int rho = which - 10;  // 11, 12, 13: the cluster plans for 2, 4, 8 CTAs
+        if (rho >= 1 && rho <= sqgpu_ctx::MAX_RHO && !tmp->cl_ok[rho - 1]) {
+            *n_ops = 0;  // no cluster plan for this circuit (fewer than 12 qubits, raw dense ops, ...)
+            delete tmp;
+            return SQGPU_OK;
+        }
+        const Plan& P = (rho >= 1 && rho <= sqgpu_ctx::MAX_RHO) ? tmp->planC[rho - 1] : (which == 2 ? tmp->plan2 : (which == 3 ? tmp->plan3 : tmp->planW));
         *n_ops = (int)P.ops.size();
         for (int i = 0; i < (int)P.ops.size() && i < cap; ++i) {
             const DevOp& op = P.ops[i];
             int32_t* o = ops + (size_t)i * 8;
             o[0] = op.dim;
             for (int j = 0; j < 5; ++j) o[1 + j] = -1;
-            if (op.dim == 2) o[1] = op.target;
+            if (op.type == SQ_OP_RESPLIT) {  // dim 0: {local row bit, cluster-rank bit}
+                o[1] = op.target;
+                o[2] = op.nq;
+            } else if (op.dim == 2) o[1] = op.target;
             else
                 for (int j = 0; j < op.nq && j < 5; ++j) o[1 + j] = op.q[j];
             o[6] = op.n_params;

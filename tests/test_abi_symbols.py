@@ -326,3 +326,33 @@ def test_constant_subcircuits_become_dense_kernels():
     # C3 / C5 structures: every CNOT-like gate sits between parametric ones, the plans are what they were
     assert sq.abi.plan_stats(H.adaptive_circuit(10, 4))["ops_plan3"] == 84
     assert sq.abi.plan_stats(H.hea_zyz_circuit(20, 10)) == sq.abi.plan_stats(H.hea_zyz_circuit(20, 10), const_fuse_qubits=0)
+
+
+def test_cluster_plan_without_gpu():
+    """the cluster planner (columns shared by 2 / 4 / 8 CTAs): RESPLIT ops are inserted so that no op touches a split qubit,
+    qubits are rewritten to row-bit positions, and the exchange count stays small (Belady choice of the qubit to split on).
+    The test replays the plan's bookkeeping: positions form a permutation and every op acts on local row bits only."""
+    import helpers as H
+
+    sq = H.sq
+    for n, levels, rho in ((13, 1, 1), (13, 1, 2), (12, 2, 1), (14, 1, 3)):
+        c = H.adaptive_circuit(n, levels)
+        base = sq.abi.plan_ops(c, which=3)
+        ops = sq.abi.plan_ops(c, which=10 + rho)
+        L = n - rho
+        resplits = [o for o in ops if o[0] == 0]
+        work = [o for o in ops if o[0] != 0]
+        assert len(work) == len(base) and [o[0] for o in work] == [o[0] for o in base]
+        assert 0 < len(resplits) <= len(base) // 3
+        for dim, qs, n_par, n_mem in work:
+            assert all(0 <= q < L for q in qs) and len(set(qs)) == len(qs)
+        for _, (j, i), _, _ in [(o[0], o[1][:2], o[2], o[3]) for o in resplits]:
+            assert 0 <= j < L and 0 <= i < rho
+        # the same logical qubits, only relabelled: supports have the same sizes op by op
+        assert [len(o[1]) for o in work] == [len(o[1]) for o in base]
+    # circuits with raw dense ops have no cluster plan; small circuits neither
+    g = sq.Circuit(12)
+    g.add_GENERAL(H.random_unitary(16, seed=1), [0, 3, 5, 9])
+    g.add_U3(2)
+    assert sq.abi.plan_ops(g, which=11) == []
+    assert sq.abi.plan_ops(H.adaptive_circuit(10, 1), which=11) == []

@@ -693,7 +693,7 @@ def test_n12_gradient_single_column_tiles(sq, port):
     U = (rng.standard_normal(((1 << n), 6)) + 1j * rng.standard_normal(((1 << n), 6))) / np.sqrt(1 << n)
     U = np.ascontiguousarray(U)
     p = H.random_params(P, seed=2)
-    e = sq.Engine(0)
+    e = sq.Engine(0, options={"cluster": 0})
     e.upload_matrix(U)
     e.set_circuit(c)
     for variant in (0, 3):
@@ -718,7 +718,7 @@ def test_n13_gradient_windowed_executor(sq, port, cols):
     theta = H.random_params(P, seed=8, batch=2)
     rng = np.random.default_rng(3)
     U = np.ascontiguousarray((rng.standard_normal((1 << n, cols)) + 1j * rng.standard_normal((1 << n, cols))) / 50.0)
-    e = sq.Engine(0)
+    e = sq.Engine(0, options={"cluster": 0})
     e.set_circuit(c)
     e.upload_matrix(U)
     for variant in (0, 3):
@@ -729,7 +729,7 @@ def test_n13_gradient_windowed_executor(sq, port, cols):
             f_ref, g_ref = port.cost_grad(d, P, theta[b], U, n, variant)
             assert close_rel(f[b], f_ref) and close_rel(g[b], g_ref)
     # the one-op-per-launch fallback gives the same numbers
-    es = sq.Engine(0, options={"tall_window": 0})
+    es = sq.Engine(0, options={"tall_window": 0, "cluster": 0})
     es.set_circuit(c)
     es.upload_matrix(U)
     es.set_cost(3, 0)
@@ -756,7 +756,7 @@ def test_n14_cost_windowed_executor(sq, port):
     theta = H.random_params(P, seed=4, batch=2)
     rng = np.random.default_rng(6)
     U = np.ascontiguousarray((rng.standard_normal((1 << n, 2)) + 1j * rng.standard_normal((1 << n, 2))) / 70.0)
-    e = sq.Engine(0)
+    e = sq.Engine(0, options={"cluster": 0})
     e.set_circuit(c)
     e.upload_matrix(U)
     for variant in (0, 1, 2, 3, 5):
@@ -1016,4 +1016,57 @@ def test_constant_subcircuit_fusion_matches_oracle(sq, port, n, support, opt):
         for b in range(2):
             f_ref, g_ref = port.cost_grad(d, P, ps[b], U, n, variant, pool=pool)
             assert close_rel(f[b], f_ref) and close_rel(fc[b], f_ref) and close_rel(g[b], g_ref)
+    e.close()
+
+
+# ---- cluster executor: thread-block clusters share a column over distributed shared memory -----------------------------
+
+@pytest.mark.parametrize("n,opt,want_cluster", [(12, {}, 2), (13, {"cluster": 2}, 4), (14, {"cluster": 2}, 8)])
+def test_cluster_executor_gradient_matches_oracle(sq, port, n, opt, want_cluster):
+    """the cluster executor: 2 / 4 / 8 CTAs of a thread-block cluster hold a column, RESPLIT ops exchange the split qubits
+    through distributed shared memory. Default at n = 12 (a column fits one CTA only once per SM), on request (option
+    cluster = 2) at n = 13 / 14, where the windowed executor is the default. Cost and ALL gradient
+    entries against the oracle on a column slice (variants 0, 2, 3, 4), against the windowed executor, and the cluster size
+    from the launch geometry."""
+    c = H.adaptive_circuit(n, 1, topology=[(q + 1, q) for q in range(n - 1)] + [(n - 1, 0), (n // 2, 1)])
+    d, pool = c.descriptors()
+    P = c.get_Parameter_Num()
+    theta = H.random_params(P, seed=18, batch=2)
+    rng = np.random.default_rng(13)
+    cols = 3
+    U = np.ascontiguousarray((rng.standard_normal((1 << n, cols)) + 1j * rng.standard_normal((1 << n, cols))) / 50.0)
+    e = sq.Engine(0, options=opt)
+    e.set_circuit(c)
+    e.upload_matrix(U)
+    for variant, off in ((0, 7), (2, 0), (3, 0), (4, 0)):
+        e.set_cost(variant, off, 0.3)
+        f, g = e.cost_grad_batched(theta)
+        assert e.last_launch_shape()["cluster"] == want_cluster, e.last_launch_shape()
+        fc = e.cost_batched(theta)
+        for b in range(2):
+            f_ref, g_ref = port.cost_grad(d, P, theta[b], U, n, variant, off, 0.3)
+            assert close_rel(f[b], f_ref) and close_rel(fc[b], f_ref) and close_rel(g[b], g_ref)
+    e.close()
+
+
+def test_cluster_executor_cost_n14(sq, port):
+    """n = 14 cost (option cluster = 2): a 256 KB column over a cluster of four CTAs; every trace variant with a trace offset,
+    random gate mix"""
+    n = 14
+    c = H.random_circuit(n, 80, seed=29, names=["U3", "RY", "CRY", "CNOT", "RZ", "adaptive", "CZ", "RX", "H", "CP"])
+    d, pool = c.descriptors()
+    P = c.get_Parameter_Num()
+    theta = H.random_params(P, seed=4, batch=3)
+    rng = np.random.default_rng(6)
+    U = np.ascontiguousarray((rng.standard_normal((1 << n, 4)) + 1j * rng.standard_normal((1 << n, 4))) / 70.0)
+    e = sq.Engine(0, options={"cluster": 2})
+    e.set_circuit(c)
+    e.upload_matrix(U)
+    for variant in (0, 1, 2, 3, 5, 9):
+        off = 5 if variant <= 2 else 0
+        e.set_cost(variant, off, 0.41)
+        f = e.cost_batched(theta)
+        assert e.last_launch_shape()["cluster"] == 4, e.last_launch_shape()
+        for b in range(3):
+            assert close_rel(f[b], port.cost(d, theta[b], U, n, variant, off, 0.41, pool=pool))
     e.close()
