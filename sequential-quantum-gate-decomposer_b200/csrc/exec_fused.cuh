@@ -27,9 +27,17 @@
 // XORs images of the row bits into the three bank-group bits (see elem() below), so that the 128-bit fragment accesses of
 // the DMMA paths are conflict-free and every address splits into B0(batch) ^ slot(lane).
 //
-// Window mode (state vectors too long for one tile, VQE): the rows of the tile are the configurations of an arbitrary
-// subset of `n_win` qubits (ExecArgs::wmask), the columns those of the other bits; MODE_APPLY / MODE_BWD run one SEGMENT of
-// the window plan (sqgpu.cu: build_window_plan) per launch.
+// Window mode (state vectors too long for one tile: VQE; column chunks of matrices with n >= 13): the rows of the tile are
+// the configurations of an arbitrary subset of `n_win` qubits (ExecArgs::wmask), the columns those of the other bits;
+// MODE_APPLY / MODE_BWD run one SEGMENT of the window plan (sqgpu.cu: build_window_plan) per launch. Tiles arrive by
+// per-element asynchronous copies (the whole tile in flight), CTAs are long-lived and take tiles round robin, the last op of
+// a segment stores straight to HBM.
+//
+// Cluster mode (CLU; n = 12 gradients by default): the CTAs of a thread-block cluster share a column tile, RESPLIT ops
+// exchange the split qubits through distributed shared memory (sqgpu.cu: build_cluster_plan).
+//
+// Complex arithmetic of the block paths: three real products per complex product, the second and third accumulated on
+// register copies of the first (SQ_BLOCK_3M / SQ_DENSE_3M below): 6 / 18 DMMA per batch forward / backward.
 #pragma once
 #include <cooperative_groups.h>
 #include "sq_types.cuh"
