@@ -384,6 +384,17 @@ static const int B0TAB = 64;  // batch bases precomputed per op (tiles with more
 #ifndef SQ_W_DIRECT
 #define SQ_W_DIRECT 0
 #endif
+// When the warps' W' partials of an op are folded: 0 (default): right after the op's end-of-op barrier, by the first nd / 32
+// warps (which then enter the next op ~600 clocks late -- three dependent DADDs queue behind the other warps' DMMAs -- and make
+// the others wait at the next barrier: 14 % of the gradient kernel's warp samples sit on the instruction after the barriers);
+// 1: one op later and BEFORE that op's barrier, by the warps that reach it first (a ticket from a shared-memory counter picks
+// the 32-element quarter a warp folds), i.e. in the slack of the fast warps. Same values, same summation order (bit-identical
+// results) -- and measured SLOWER: C3 1 391 against 1 498 evals/s, C5 backward sweep 48.4 against 44.6 ms
+// (profiles/README_r2.md): the ticket (atomic + shuffle) sits on every warp's path once per op and the fast warps' slack is
+// smaller than the fold. Kept as a switch with its measurement.
+#ifndef SQ_FOLD_EARLY
+#define SQ_FOLD_EARLY 0
+#endif
 
 // Raw dense 3-/4-qubit kernels (GENERAL blocks): 1 (default): the same three-product form as the fused blocks -- 24 instead of
 // 32 DMMA per 8 items for a 16 x 16 kernel, 6 instead of 8 for an 8 x 8 one, and 24 / 6 kernel-fragment registers per lane
@@ -1150,6 +1161,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
     // cluster executor: rank of this CTA inside its cluster, cluster index (tiles are dealt to clusters)
     unsigned crank = 0;
     int tile_owner = chunk;
+    __shared__ int s_fold_cnt[2];  // SQ_FOLD_EARLY: arrival tickets of the current / next op
     __shared__ signed char sfin[CLU ? 32 : 1];  // cluster executor: A.fin_pos (indexed dynamically: kept out of the parameter space)
     if constexpr (CLU) {
         crank = cooperative_groups::this_cluster().block_rank();
@@ -1237,6 +1249,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
         __syncthreads();
     }
     if (tid < 6) stsum[tid] = 0.0;
+    if (tid < 2) s_fold_cnt[tid] = 0;
     __syncthreads();
 
     // the 2 x 2 kernel of single-qubit block k (kind 0): 64 bytes that take the place of the table in the op's ring slot
@@ -1730,6 +1743,25 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
 
             // ---- backward sweep ---------------------------------------------------------------------------------
             int buf = 0;
+            // fold of one op's W' partials: element e of the op's dim x dim complex block (as doubles) summed over the warps'
+            // slots in a fixed order (a pairwise tree: three dependent DADDs instead of seven) and ONE fire-and-forget reduction
+            // into the CTA's slice: each address has a single writer, so the sums are bit-reproducible
+            auto fold_elem = [&](int e, int fbuf, int w_off) {
+                const double* base = reinterpret_cast<const double*>(swarp + (size_t)fbuf * nwarps * A.wmax) + e;
+                const size_t wstride = (size_t)A.wmax * 2;
+                double sum;
+                if (nwarps == 8) {
+                    const double a0 = base[0], a1 = base[wstride], a2 = base[2 * wstride], a3 = base[3 * wstride];
+                    const double a4 = base[4 * wstride], a5 = base[5 * wstride], a6 = base[6 * wstride], a7 = base[7 * wstride];
+                    sum = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+                } else {
+                    sum = 0;
+                    for (int w = 0; w < nwarps; ++w) sum += base[w * wstride];
+                }
+                if (A.w_in_smem) reinterpret_cast<double*>(swacc + w_off)[e] += sum;
+                else atomicAdd(reinterpret_cast<double*>(A.w_part + ((size_t)y * nchunks + chunk) * A.w_total + w_off) + e, sum);
+            };
+            int pend_nd = 0, pend_buf = 0, pend_off = 0, step = 0;  // SQ_FOLD_EARLY: the previous parametric op's fold, still to do
             for (int k = A.n_ops - 1; k >= 0; --k) {
                 const SOp s = sops[k];
                 const bool have_next = k > 0;
@@ -1878,35 +1910,35 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                     const SOp sn = sops[k - 1];
                     if (sn.kind == 2 && sn.dim == 8) blk_preload<3, true>(R, stab + ((k - 1) & (TAB_RING - 1)), (rows >> 3) << LOG_CT, lane, warp, nwarps);
                 }
+                if (SQ_FOLD_EARLY && pend_nd > 0) {
+                    // the PREVIOUS parametric op's fold, by the warps that get here first: ticket t folds elements [32 t, 32 t + 32)
+                    int ticket = 0;
+                    if (lane == 0) ticket = atomicAdd(&s_fold_cnt[step & 1], 1);
+                    ticket = __shfl_sync(0xffffffffu, ticket, 0);
+                    for (int e0 = ticket * 32; e0 < pend_nd; e0 += nwarps * 32)
+                        if (e0 + lane < pend_nd) fold_elem(e0 + lane, pend_buf, pend_off);
+                    pend_nd = 0;
+                }
                 tab_end_of_op();
                 __syncthreads();
+                if (SQ_FOLD_EARLY && tid == 0) s_fold_cnt[step & 1] = 0;  // next used two barriers from now
+                ++step;
                 if (has_w && !wdirect) {
                     const int nd = 2 * wdim * wdim;  // doubles
-                    // One thread per element folds the warps' partials in a fixed order (a pairwise tree: three dependent DADDs
-                    // instead of seven -- the fold shares the FP64 pipe with the other warps' queued DMMAs, so every dependent
-                    // add waits its turn) and issues ONE fire-and-forget reduction: each address of the CTA's slice has a single
-                    // writer, so the sums are bit-reproducible. Only the first nd / 32 warps fold; the others are already in the
-                    // next op and keep the tensor pipe fed (spreading the fold over all warps was measured slower: 1 282
-                    // against 1 339 evals/s on C3, profiles/r2_variants_exec.jsonl).
-                    for (int e = tid; e < nd; e += nthr) {
-                        const double* base = reinterpret_cast<const double*>(swarp + (size_t)buf * nwarps * A.wmax) + e;
-                        const size_t wstride = (size_t)A.wmax * 2;
-                        double sum;
-                        if (nwarps == 8) {
-                            const double a0 = base[0], a1 = base[wstride], a2 = base[2 * wstride], a3 = base[3 * wstride];
-                            const double a4 = base[4 * wstride], a5 = base[5 * wstride], a6 = base[6 * wstride], a7 = base[7 * wstride];
-                            sum = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
-                        } else {
-                            sum = 0;
-                            for (int w = 0; w < nwarps; ++w) sum += base[w * wstride];
-                        }
-                        if (A.w_in_smem) reinterpret_cast<double*>(swacc + s.w_off)[e] += sum;
-                        else
-                            atomicAdd(reinterpret_cast<double*>(A.w_part + ((size_t)y * nchunks + chunk) * A.w_total + s.w_off) + e, sum);
+                    if (SQ_FOLD_EARLY) {
+                        pend_nd = nd;
+                        pend_buf = buf;
+                        pend_off = s.w_off;
+                    } else {
+                        // only the first nd / 32 warps fold; the others are already in the next op (spreading the fold over all
+                        // warps was measured slower: 1 282 against 1 339 evals/s on C3, profiles/r2_variants_exec.jsonl)
+                        for (int e = tid; e < nd; e += nthr) fold_elem(e, buf, s.w_off);
                     }
                     buf ^= 1;
                 }
             }
+            if (SQ_FOLD_EARLY && pend_nd > 0)  // the last parametric op of the sweep (its slots were published by the barrier above)
+                for (int e = tid; e < pend_nd; e += nthr) fold_elem(e, pend_buf, pend_off);
             __syncthreads();
             if (MODE == MODE_BWD && !stored) {
                 for (int e = tid; e < rows * CT; e += nthr) {
