@@ -1126,7 +1126,10 @@ __device__ int g_trace_arrivals;
 // that exchange a split qubit with a local one through distributed shared memory (each CTA swaps half of its tile with ONE
 // partner) before an op needs it, and rewrites every op's qubits to the row-bit positions they have at that point. Everything
 // else -- block path, tables, W' slices, trace partials (one chunk per CTA) -- is the single-CTA executor.
-template <int MODE, int LOG_CT, bool CLU = false>
+// DBW: the adjoint sweep carries the tensor-core step for constant dense 3-/4-qubit kernels (GENERAL blocks, multiplied-out
+// constant sub-circuits). A separate instantiation, because the mere presence of that branch (24-48 fragment registers)
+// costs the block path of every other circuit: C5 backward sweep 45.7 ms with it, 42.8 ms without (profiles/README_r2.md).
+template <int MODE, int LOG_CT, bool CLU = false, bool DBW = false>
 __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int CT = 1 << LOG_CT;
@@ -1838,7 +1841,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                             sb[e1] = cfma(k11, b1, cmul(k01, b0));
                         }
                         if (has_w) warp_store_w<4>(W, wslot, lane, wdirect);
-                    } else if (A.dense_tabs && op.dtab > 0 && !has_w && op.ctrl_mask == 0 && ((((rows >> op.nq) << LOG_CT) & 7) == 0)) {
+                    } else if (DBW && A.dense_tabs && op.dtab > 0 && !has_w && op.ctrl_mask == 0 && ((((rows >> op.nq) << LOG_CT) & 7) == 0)) {
                         // constant dense 3-/4-qubit kernel (GENERAL blocks, multiplied-out constant sub-circuits): the adjoint
                         // step is two forward-style products on the tensor cores with the op's K^dagger and K^T tables
                         const DenseTab* T = A.dense_tabs + 3 * (op.dtab - 1);

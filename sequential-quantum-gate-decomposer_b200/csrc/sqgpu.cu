@@ -937,11 +937,21 @@ template <int MODE>
 cudaError_t launch_fused_mode(const ExecArgs& a, const FusedPlan& p, int ysets, cudaStream_t st) {
     dim3 grid(p.chunks, ysets);
     cudaError_t e = cudaSuccess;
+    // gradient / backward kernels come in two flavours: with the tensor-core adjoint step of constant dense kernels (only for
+    // circuits that have such ops: their fragment tables are attached) and without
+    constexpr bool HAS_ADJ = (MODE == MODE_GRAD || MODE == MODE_BWD);
+    const bool dbw = HAS_ADJ && a.dense_tabs != nullptr;
 #define SQ_LAUNCH(LC)                                                                                          \
     case LC:                                                                                                   \
-        e = cudaFuncSetAttribute(fused_exec<MODE, LC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem); \
-        if (e != cudaSuccess) return e;                                                                        \
-        fused_exec<MODE, LC><<<grid, p.threads, p.smem, st>>>(a);                                              \
+        if (dbw) {                                                                                             \
+            e = cudaFuncSetAttribute(fused_exec<MODE, LC, false, HAS_ADJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem); \
+            if (e != cudaSuccess) return e;                                                                    \
+            fused_exec<MODE, LC, false, HAS_ADJ><<<grid, p.threads, p.smem, st>>>(a);                          \
+        } else {                                                                                               \
+            e = cudaFuncSetAttribute(fused_exec<MODE, LC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem); \
+            if (e != cudaSuccess) return e;                                                                    \
+            fused_exec<MODE, LC><<<grid, p.threads, p.smem, st>>>(a);                                          \
+        }                                                                                                      \
         break;
     if (p.rho > 0) {
         // cluster executor: 2^rho consecutive CTAs in x form a thread-block cluster (distributed shared memory)
