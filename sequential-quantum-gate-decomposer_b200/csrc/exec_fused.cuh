@@ -94,6 +94,7 @@ struct ExecArgs {
     int dense_stage;         // complex elements of kernel staging for the generic dense path (0: none)
     int wmax;                // max dim*dim over parametric ops (complex), >= 4
     int dbuf;                // window forward segments: two tile buffers, the next tile streams in while this one is computed
+    int dns;                 // 1: the program has raw dense ops (or a materialised block derivative): launch the DNS = true kernels
     int rho;                 // cluster executor: log2(CTAs per cluster); `rows` is then the rows ONE CTA holds (2^(n - rho))
     signed char fin_pos[32]; // cluster executor: where logical qubit q sits after the forward sweep: local row bit p (p < 32) or
                              // cluster-rank bit p - 32
@@ -1126,10 +1127,12 @@ __device__ int g_trace_arrivals;
 // that exchange a split qubit with a local one through distributed shared memory (each CTA swaps half of its tile with ONE
 // partner) before an op needs it, and rewrites every op's qubits to the row-bit positions they have at that point. Everything
 // else -- block path, tables, W' slices, trace partials (one chunk per CTA) -- is the single-CTA executor.
-// DBW: the adjoint sweep carries the tensor-core step for constant dense 3-/4-qubit kernels (GENERAL blocks, multiplied-out
-// constant sub-circuits). A separate instantiation, because the mere presence of that branch (24-48 fragment registers)
-// costs the block path of every other circuit: C5 backward sweep 45.7 ms with it, 42.8 ms without (profiles/README_r2.md).
-template <int MODE, int LOG_CT, bool CLU = false, bool DBW = false>
+// DNS: the kernel carries the paths of RAW dense ops (GENERAL blocks, multiplied-out constant sub-circuits, controlled
+// two-target gates, materialised block derivatives): dense DMMA forward / adjoint steps and the generic scalar path. Circuits
+// without such ops -- every fused decomposition structure -- run the DNS = false instantiation: the mere presence of those
+// branches costs the block path registers and schedule (measured: C5 backward sweep 45.7 ms with the dense adjoint step
+// compiled in, 42.8 ms without; C3 1 496 -> 1 527 evals/s and 128 -> 112 registers without any dense path).
+template <int MODE, int LOG_CT, bool CLU = false, bool DNS = true>
 __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int CT = 1 << LOG_CT;
@@ -1544,7 +1547,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                             }
                         }
                     }
-                } else {
+                } else if (DNS) {
                     // dense dim x dim kernel on ascending qubits (apply_large_kernel_to_input.cpp:160-199)
                     const int nq = op.nq;
                     const int nitems = (rows >> nq) << LOG_CT;
@@ -1841,7 +1844,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                             sb[e1] = cfma(k11, b1, cmul(k01, b0));
                         }
                         if (has_w) warp_store_w<4>(W, wslot, lane, wdirect);
-                    } else if (DBW && A.dense_tabs && op.dtab > 0 && !has_w && op.ctrl_mask == 0 && ((((rows >> op.nq) << LOG_CT) & 7) == 0)) {
+                    } else if (DNS && A.dense_tabs && op.dtab > 0 && !has_w && op.ctrl_mask == 0 && ((((rows >> op.nq) << LOG_CT) & 7) == 0)) {
                         // constant dense 3-/4-qubit kernel (GENERAL blocks, multiplied-out constant sub-circuits): the adjoint
                         // step is two forward-style products on the tensor cores with the op's K^dagger and K^T tables
                         const DenseTab* T = A.dense_tabs + 3 * (op.dtab - 1);
@@ -1852,7 +1855,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                             dense_dmma_forward2<LOG_CT, 4>(sa, T + 1, op, rows, tid, nthr);
                             dense_dmma_forward2<LOG_CT, 4>(sb, T + 2, op, rows, tid, nthr);
                         }
-                    } else {
+                    } else if (DNS) {
                         // raw dense op (controlled two-target gates, GENERAL blocks, or a block too small for the tensor
                         // path): thread per (group, column), local arrays
                         const int dim = op.dim, nq = op.nq;

@@ -210,6 +210,7 @@ struct Plan {
     int n_dense = 0, n_dense5 = 0, dense_logct = -1;
     int n_ops = 0, kern_total = 0, dkern_total = 0, w_total = 0, wmax = 4;
     int dense_stage = 0;             // complex elements of kernel staging the executor's generic dense path needs
+    bool has_dense = false;          // raw ops wider than one qubit (GENERAL blocks, controlled two-target gates): DNS kernels
 };
 
 struct sqgpu_ctx {
@@ -569,6 +570,7 @@ int build_window_plan(sqgpu_ctx* c, bool upload) {
     dst.n_dense = src.n_dense;
     dst.n_dense5 = src.n_dense5;
     dst.dense_logct = -1;
+    dst.has_dense = src.has_dense || c->win_w <= 6;
     if (!upload) return SQGPU_OK;  // planning only (sqgpu_plan_stats)
     int rc;
     const size_t np1 = std::max<size_t>(dst.param_op.size(), 1);
@@ -674,6 +676,7 @@ bool build_cluster_plan(sqgpu_ctx* c, int rho, bool upload, int* rc_out) {
     dst.dense_stage = src.dense_stage;
     dst.n_dense = dst.n_dense5 = 0;
     dst.dense_logct = -1;
+    dst.has_dense = false;
     c->cl_ok[rho - 1] = true;
     if (!upload) return true;
     int rc;
@@ -937,20 +940,19 @@ template <int MODE>
 cudaError_t launch_fused_mode(const ExecArgs& a, const FusedPlan& p, int ysets, cudaStream_t st) {
     dim3 grid(p.chunks, ysets);
     cudaError_t e = cudaSuccess;
-    // gradient / backward kernels come in two flavours: with the tensor-core adjoint step of constant dense kernels (only for
-    // circuits that have such ops: their fragment tables are attached) and without
-    constexpr bool HAS_ADJ = (MODE == MODE_GRAD || MODE == MODE_BWD);
-    const bool dbw = HAS_ADJ && a.dense_tabs != nullptr;
+    // two flavours of every kernel: with the raw-dense-op paths (circuits with GENERAL blocks, controlled two-target gates,
+    // materialised block derivatives, tiny tiles) and without (see fused_exec, DNS)
+    const bool dns = a.dns != 0;
 #define SQ_LAUNCH(LC)                                                                                          \
     case LC:                                                                                                   \
-        if (dbw) {                                                                                             \
-            e = cudaFuncSetAttribute(fused_exec<MODE, LC, false, HAS_ADJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem); \
+        if (dns) {                                                                                             \
+            e = cudaFuncSetAttribute(fused_exec<MODE, LC, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem); \
             if (e != cudaSuccess) return e;                                                                    \
-            fused_exec<MODE, LC, false, HAS_ADJ><<<grid, p.threads, p.smem, st>>>(a);                          \
+            fused_exec<MODE, LC, false, true><<<grid, p.threads, p.smem, st>>>(a);                             \
         } else {                                                                                               \
-            e = cudaFuncSetAttribute(fused_exec<MODE, LC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem); \
+            e = cudaFuncSetAttribute(fused_exec<MODE, LC, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem); \
             if (e != cudaSuccess) return e;                                                                    \
-            fused_exec<MODE, LC><<<grid, p.threads, p.smem, st>>>(a);                                          \
+            fused_exec<MODE, LC, false, false><<<grid, p.threads, p.smem, st>>>(a);                            \
         }                                                                                                      \
         break;
     if (p.rho > 0) {
@@ -970,9 +972,9 @@ cudaError_t launch_fused_mode(const ExecArgs& a, const FusedPlan& p, int ysets, 
             cfg.numAttrs = 1;
 #define SQ_LAUNCH_CL(LC)                                                                                                  \
     case LC:                                                                                                              \
-        e = cudaFuncSetAttribute(fused_exec<MODE, LC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);   \
+        e = cudaFuncSetAttribute(fused_exec<MODE, LC, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);   \
         if (e != cudaSuccess) return e;                                                                                   \
-        e = cudaLaunchKernelEx(&cfg, fused_exec<MODE, LC, true>, a);                                                      \
+        e = cudaLaunchKernelEx(&cfg, fused_exec<MODE, LC, true, false>, a);                                                      \
         if (e != cudaSuccess) return e;                                                                                   \
         break;
             switch (p.log_ct) {
@@ -1099,6 +1101,7 @@ void fill_common_args(const sqgpu_ctx* c, const FusedPlan& p, ExecArgs& a, int r
     a.w_direct = p.w_direct ? 1 : 0;
     a.dbuf = p.dbuf ? 1 : 0;
     a.rho = p.rho;
+    a.dns = c->P->has_dense ? 1 : 0;
     if (p.rho > 0) memcpy(a.fin_pos, c->cl_fin[p.rho - 1], sizeof(a.fin_pos));
 }
 
@@ -1424,6 +1427,7 @@ int apply_program_dev(sqgpu_ctx* c, const cplx* d_in, long long in_ystride, cplx
         a.k_shared = 1;
         a.deriv_op = d_dop;
         a.deriv_slot = d_dp;
+        if (d_dop) a.dns = 1;  // the derivative kernel of a fused block goes down the generic dense path
         for (int y0 = 0; y0 < ysets; y0 += 65535) {
             const int ny = std::min(65535, ysets - y0);
             ExecArgs b = a;
@@ -2169,6 +2173,12 @@ static int set_circuit_impl(sqgpu_ctx* c, const sqgpu_gate_desc* gates, int n_ga
         out.n_dense = n_dense;
         out.n_dense5 = n_dense5;
         out.dense_logct = -1;
+        out.has_dense = false;
+        for (const DevOp& o : out.ops)
+            if (o.dim > 2 && o.type != SQ_OP_BLOCK) out.has_dense = true;
+        // a fused block too small for the tensor path (fewer than 8 (group, column) items per tile) takes the generic dense path:
+        // only circuits of up to ~5 qubits; they run the DNS kernels as well
+        if (qbit_num <= 6) out.has_dense = true;
         return (int)SQGPU_OK;
     };
 
