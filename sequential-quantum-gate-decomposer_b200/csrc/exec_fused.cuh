@@ -406,6 +406,11 @@ static const int B0TAB = 64;  // batch bases precomputed per op (tiles with more
 // The same for 5-qubit kernels (32 x 32): 96 instead of 128 DMMA per batch, but 16 more live operand registers -- measured: the
 // kernel spills (820 B at the 128-register cap), 64 5-qubit blocks at n = 12 run at 67.4 instead of 93.1 evals/s, and the extra
 // code costs the C3 gradient kernel 1.3 % (1 479 against 1 498 evals/s). 0 (default): 5-qubit kernels keep the real embedding.
+// Window segments: 1 (default): the last op of a segment writes its results straight to the state in HBM (no store phase, no
+// shared-memory round trip); 0: separate store loop. Measured on C5: forward 15.0 against 15.5 ms, backward 41.5 against 43.9 ms.
+#ifndef SQ_FUSE_STORE
+#define SQ_FUSE_STORE 1
+#endif
 #ifndef SQ_DENSE5_3M
 #define SQ_DENSE5_3M 0
 #endif
@@ -1487,7 +1492,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
             } else if (s.kind == 2) {
                 bool fused = false;
                 if constexpr (MODE == MODE_APPLY) {
-                    if (gst_a && k == A.n_ops - 1) {  // last op of a window segment: results go straight to the state in HBM
+                    if (SQ_FUSE_STORE && gst_a && k == A.n_ops - 1) {  // last op of a window segment: results go straight to the state in HBM
                         if (s.dim == 8) block_dmma_forward<LOG_CT, 3, true>(sa, stab + (k & (TAB_RING - 1)), R, s.q0, s.q1, s.q2, rows, tid, nthr, gst_a, sglob);
                         else block_dmma_forward<LOG_CT, 2, true>(sa, stab + (k & (TAB_RING - 1)), R, s.q0, s.q1, 30, rows, tid, nthr, gst_a, sglob);
                         fused = stored = true;
@@ -1784,7 +1789,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) fused_exec(const ExecArgs A)
                 } else if (s.kind == 2) {
                     bool fused = false;
                     if constexpr (MODE == MODE_BWD) {
-                        if (gst_a && k == 0) {  // last op of the segment's backward sweep: a and beta go straight to HBM
+                        if (SQ_FUSE_STORE && gst_a && k == 0) {  // last op of the segment's backward sweep: a and beta go straight to HBM
                             if (s.dim == 8) block_dmma_backward<LOG_CT, 3, true>(sa, sb, stab + (k & (TAB_RING - 1)), R, s.q0, s.q1, s.q2, rows, has_w, wslot_c, wdirect, tid, nthr, gst_a, gst_b, sglob);
                             else block_dmma_backward<LOG_CT, 2, true>(sa, sb, stab + (k & (TAB_RING - 1)), R, s.q0, s.q1, 30, rows, has_w, wslot_c, wdirect, tid, nthr, gst_a, gst_b, sglob);
                             fused = stored = true;
