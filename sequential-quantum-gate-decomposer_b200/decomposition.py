@@ -121,8 +121,9 @@ class N_Qubit_Decomposition_custom:
     def get_Num_of_Iters(self):
         return self._num_evaluations
 
-    def _optimize_structure(self, rng):
-        """minimise the cost over the current gate structure; returns (parameters, cost)"""
+    def _optimize_structure(self, rng, x0=None):
+        """minimise the cost over the current gate structure; returns (parameters, cost). x0: a start to polish (the
+        final optimisation of finalize_circuit) instead of random starts."""
         from . import optimize
 
         eng = self._sync()
@@ -131,10 +132,10 @@ class N_Qubit_Decomposition_custom:
         if P == 0:
             return np.zeros(0), float(eng.cost_batched(np.zeros((1, 0)))[0])
         if self._optimizer == "ADAM":
-            starts = int(self.config.get("adam_trajectories", 16))
+            starts = int(self.config.get("adam_trajectories", 16)) if x0 is None else 1
             steps_max = int(self.config.get("max_inner_iterations", 4000))
             X0 = rng.random((starts, P)) * 2 * np.pi
-            X0[0] = 0.0
+            X0[0] = 0.0 if x0 is None else np.asarray(x0, dtype=np.float64)
             eng.adam_init(X0, eta=float(self.config.get("eta", 1e-2)))
             done = 0
             while done < steps_max:
@@ -151,6 +152,11 @@ class N_Qubit_Decomposition_custom:
             f, g = eng.cost_grad_batched(x.reshape(1, -1))
             return float(f[0]), g[0]
 
+        if x0 is not None:
+            x, f, _, ne = optimize.lbfgs(cost_grad, eng.line_search_batched, np.asarray(x0, dtype=np.float64),
+                                         max_iter=int(self.config.get("max_inner_iterations_final", self.config.get("max_inner_iterations", 2000))), tol=tol * 1e-2)
+            self._num_evaluations += ne
+            return x, f
         x, f, _, ne = optimize.multistart_lbfgs(eng.cost_batched, cost_grad, eng.line_search_batched, P, rng,
                                                 starts=int(self.config.get("initial_points", 64)), keep=int(self.config.get("restarts", 4)),
                                                 max_iter=int(self.config.get("max_inner_iterations", 2000)), tol=tol * 1e-2)
@@ -234,6 +240,65 @@ class N_Qubit_Decomposition_custom:
         return m
 
 
+def replace_trivial_CRY_gates(circuit, parameters):
+    """N_Qubit_Decomposition_adaptive::replace_trivial_CRY_gates (N_Qubit_Decomposition_adaptive.cpp:1398-1590): rewrite the
+    adaptive (controlled-RY) gates of an optimised structure with their final parameters:
+
+    * |sin p| > 0.999 and |cos p| < 1e-3 (a half turn):  RX(target, -pi/4), CZ(target, control), RX(target, +pi/4),
+      RZ(control, +-pi/4) and the global phase exp(+-i pi/4) that the reference moves onto Umtx (:1443-1497);
+    * |sin p| < 1e-3 and |1 - cos p| < 1e-3 (the identity): the gate is dropped (:1503-1513);
+    * otherwise the standard CRY = RY(p/2) CNOT RY(-p/2) CNOT (:1515-1547).
+
+    `circuit` is a Circuit whose top-level items are blocks (as the adaptive builder makes them); parameters are the stored
+    (half-angle) values in application order. Returns (new_circuit, new_parameters, global_phase) with
+    global_phase * new_circuit(new_parameters) == circuit(parameters) as matrices."""
+    import cmath
+
+    params = np.asarray(parameters, dtype=np.float64).reshape(-1)
+    if params.size != circuit.get_Parameter_Num():
+        raise Exception("replace_trivial_CRY_gates: %d parameters for a circuit with %d" % (params.size, circuit.get_Parameter_Num()))
+    out = Circuit(circuit.qbit_num, circuit._device)
+    new_params = []
+    phase = 1.0 + 0.0j
+    idx = 0
+    for layer in circuit._items:
+        if not isinstance(layer, Circuit):
+            raise Exception("replace_trivial_adaptive_gates: Only block gates are accepted in this conversion.")
+        new_layer = Circuit(circuit.qbit_num, circuit._device)
+        for g in layer._flat_gates():
+            n_p = g.n_params
+            if g.type != abi.ADAPTIVE:
+                new_layer._add(g)
+                new_params.extend(params[idx:idx + n_p])
+                idx += n_p
+                continue
+            par = float(params[idx])  # activation_function(parameter, 1) is the identity (common/common.cpp:35-38)
+            idx += 1
+            sp, cp = np.sin(par), np.cos(par)
+            t, c = g.target, g.control
+            sub = Circuit(circuit.qbit_num, circuit._device)
+            if abs(sp) > 0.999 and abs(cp) < 1e-3:
+                sub.add_RX(t)
+                sub.add_CZ(t, c)
+                sub.add_RX(t)
+                sub.add_RZ(c)
+                sgn = -1.0 if sp < 0 else 1.0
+                new_params.extend([-np.pi / 4, np.pi / 4, sgn * np.pi / 4])
+                phase *= cmath.exp(1j * sgn * np.pi / 4)
+                new_layer.add_Circuit(sub)
+            elif abs(sp) < 1e-3 and abs(1 - cp) < 1e-3:
+                pass  # trivial gate released
+            else:
+                sub.add_RY(t)
+                sub.add_CNOT(t, c)
+                sub.add_RY(t)
+                sub.add_CNOT(t, c)
+                new_params.extend([par / 2, -par / 2])
+                new_layer.add_Circuit(sub)
+        out.add_Circuit(new_layer)
+    return out, np.asarray(new_params, dtype=np.float64), phase
+
+
 class N_Qubit_Decomposition_adaptive(N_Qubit_Decomposition_custom):
     """Adaptive gate structure builder + cost path (N_Qubit_Decomposition_adaptive.cpp:1820-1966)."""
 
@@ -278,8 +343,9 @@ class N_Qubit_Decomposition_adaptive(N_Qubit_Decomposition_custom):
         """The level search of determine_initial_gate_structure (N_Qubit_Decomposition_adaptive.cpp:786-1037): for
         level = level_limit_min .. level_limit_max build `level` adaptive layers + the finalizing layer, minimise the cost from
         random starts, stop at the first level whose minimum is below the optimization tolerance, keep the best level otherwise.
-        Compression and the CRY -> CNOT finalisation of the reference (compress_circuit / finalize_circuit, :372-686) are not
-        part of this thin loop. Afterwards: get_Circuit(), get_Optimized_Parameters(), get_Decomposition_Error()."""
+        Then Finalize_Circuit() (the CRY -> CNOT / CZ finalisation, :530-640) unless config["finalize"] is 0. The layer
+        compression of the reference (compress_circuit, :372-520) is not part of this thin loop.
+        Afterwards: get_Circuit(), get_Optimized_Parameters(), get_Decomposition_Error(), get_CNOT_Count()."""
         rng = np.random.default_rng(int(self.config.get("seed", 0)))
         best = None
         for level in range(self.level_limit_min, self.level_limit + 1):
@@ -294,4 +360,33 @@ class N_Qubit_Decomposition_adaptive(N_Qubit_Decomposition_custom):
                 break
         self._circuit, self._optimized_parameters, self._current_minimum, self.decomposition_level = best
         self._dirty = True
+        if int(self.config.get("finalize", 1)):
+            self.Finalize_Circuit()
         return self._current_minimum
+
+    def Finalize_Circuit(self):
+        """finalize_circuit (N_Qubit_Decomposition_adaptive.cpp:530-640): the adaptive gates are replaced by CZ / CNOT
+        constructions or dropped according to their optimised parameters (replace_trivial_CRY_gates), the global phase moves
+        onto Umtx, and the parameters are polished by one more optimisation of the new, CRY-free structure started from the
+        converted parameters."""
+        if self._optimized_parameters is None:
+            raise Exception("Finalize_Circuit: no optimised parameters (run Start_Decomposition or set_Optimized_Parameters)")
+        circ, x0, phase = replace_trivial_CRY_gates(self._circuit, self._optimized_parameters)
+        # C(x) U = phase C'(x') U = C'(x') (phase U): the reference moves the phase onto Umtx (apply_global_phase_factor,
+        # :1478-1495); the Frobenius-family costs take Re tr, so the matrix really has to carry it
+        self.Umtx = np.ascontiguousarray(self.Umtx * phase)
+        if self._engine_obj is not None:
+            self._engine_obj.upload_matrix(self.Umtx)
+        self._circuit = circ
+        self._dirty = True
+        self._optimized_parameters = np.asarray(x0, dtype=np.float64)
+        f0 = float(self.Optimization_Problem(self._optimized_parameters))
+        x, f = self._optimize_structure(np.random.default_rng(int(self.config.get("seed", 0)) + 1), x0=self._optimized_parameters)
+        if not (f <= f0):
+            x, f = self._optimized_parameters, f0
+        self._optimized_parameters, self._current_minimum = np.asarray(x, dtype=np.float64), float(f)
+        return self._current_minimum
+
+    def get_CNOT_Count(self):
+        """two-qubit gates (CNOT + CZ) of the current structure, the figure of merit of the decomposition"""
+        return sum(1 for g in self._circuit._flat_gates() if g.type in (abi.CNOT, abi.CZ))

@@ -988,6 +988,12 @@ def test_start_decomposition_config1(sq, optimizer):
     m = np.eye(16) * 2 - prod - prod.conj().T
     assert np.real(np.trace(m)) / 2 < 1e-3
     assert dec.get_Num_of_Iters() > 0 and 1 <= dec.decomposition_level <= 5
+    # finalize_circuit ran (N_Qubit_Decomposition_adaptive.cpp:530-640): no adaptive gate is left, the two-qubit gates are
+    # CNOT / CZ, at most two per adaptive gate of the level that was found
+    types = [int(r["type"]) for r in dec.get_Circuit().descriptors()[0]]
+    assert sq.abi.ADAPTIVE not in types
+    assert 0 < dec.get_CNOT_Count() <= 2 * 6 * dec.decomposition_level
+    assert close_rel(dec.Optimization_Problem(params), err, 1e-9)
 
 
 # ---- N3: constant sub-circuits multiplied out into dense kernels -----------------------------------------------------
