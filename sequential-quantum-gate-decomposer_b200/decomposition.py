@@ -343,8 +343,8 @@ class N_Qubit_Decomposition_adaptive(N_Qubit_Decomposition_custom):
         """The level search of determine_initial_gate_structure (N_Qubit_Decomposition_adaptive.cpp:786-1037): for
         level = level_limit_min .. level_limit_max build `level` adaptive layers + the finalizing layer, minimise the cost from
         random starts, stop at the first level whose minimum is below the optimization tolerance, keep the best level otherwise.
-        Then Finalize_Circuit() (the CRY -> CNOT / CZ finalisation, :530-640) unless config["finalize"] is 0. The layer
-        compression of the reference (compress_circuit, :372-520) is not part of this thin loop.
+        Then Compress_Circuit() (:372-520; config["compress"], default 1) and Finalize_Circuit() (the CRY -> CNOT / CZ
+        finalisation, :530-640; config["finalize"], default 1), as the reference's start_decomposition does (:255-280).
         Afterwards: get_Circuit(), get_Optimized_Parameters(), get_Decomposition_Error(), get_CNOT_Count()."""
         rng = np.random.default_rng(int(self.config.get("seed", 0)))
         best = None
@@ -360,9 +360,67 @@ class N_Qubit_Decomposition_adaptive(N_Qubit_Decomposition_custom):
                 break
         self._circuit, self._optimized_parameters, self._current_minimum, self.decomposition_level = best
         self._dirty = True
+        if int(self.config.get("compress", 1)) and self._current_minimum < self._optimization_tolerance:
+            self.Compress_Circuit()
         if int(self.config.get("finalize", 1)):
             self.Finalize_Circuit()
         return self._current_minimum
+
+    def Compress_Circuit(self):
+        """compress_circuit / compress_gate_structure (N_Qubit_Decomposition_adaptive.cpp:372-520, 1046-1335), thin form: as
+        long as some decomposing layer can go, the layers are tried for removal in the order of the rotation left in their
+        adaptive gate (|sin| of the stored parameter, smallest first, at most five candidates per round, :1067-1083); a candidate
+        is accepted when the reduced structure, re-optimised from the reduced parameters (create_reduced_parameters, :1337-1395;
+        config max_inner_iterations_compression), still reaches the optimization tolerance. The finalizing U3 layer is never
+        removed (:1051). Returns the number of layers removed."""
+        from . import optimize
+
+        if self._optimized_parameters is None:
+            raise Exception("Compress_Circuit: no optimised parameters (run Start_Decomposition or set_Optimized_Parameters)")
+        tol = self._optimization_tolerance
+        max_it = int(self.config.get("max_inner_iterations_compression", 200))
+        removed = 0
+        for _ in range(25):  # :420
+            layers = self._circuit._items
+            if len(layers) <= 1 or not all(isinstance(it, Circuit) for it in layers):
+                break
+            x = np.asarray(self._optimized_parameters, dtype=np.float64)
+            starts = np.cumsum([0] + [it.get_Parameter_Num() for it in layers])
+            theta = []
+            for li, it in enumerate(layers[:-1]):
+                off, val = starts[li], 15.0  # (the reference's default for layers without an adaptive gate)
+                for g in it._flat_gates():
+                    if g.type == abi.ADAPTIVE:
+                        val = abs(np.sin(x[off]))
+                    off += g.n_params
+                theta.append(val)
+            accepted = False
+            for li in np.argsort(theta, kind="stable")[:5]:
+                trial = Circuit(self.qbit_num, self._device)
+                for lj, it in enumerate(layers):
+                    if lj != li:
+                        trial.add_Circuit(it)
+                x_red = np.concatenate([x[: starts[li]], x[starts[li + 1]:]])
+                keep_c, keep_x, keep_f = self._circuit, self._optimized_parameters, self._current_minimum
+                self._circuit = trial
+                eng = self._sync()
+
+                def cost_grad(v):
+                    f, g = eng.cost_grad_batched(v.reshape(1, -1))
+                    return float(f[0]), g[0]
+
+                xr, fr, _, ne = optimize.lbfgs(cost_grad, eng.line_search_batched, x_red, max_iter=max_it, tol=tol * 1e-2)
+                self._num_evaluations += ne
+                if fr < tol:
+                    self._optimized_parameters, self._current_minimum = np.asarray(xr, dtype=np.float64), float(fr)
+                    removed += 1
+                    accepted = True
+                    break
+                self._circuit, self._optimized_parameters, self._current_minimum = keep_c, keep_x, keep_f
+            if not accepted:
+                break
+        self._sync()
+        return removed
 
     def Finalize_Circuit(self):
         """finalize_circuit (N_Qubit_Decomposition_adaptive.cpp:530-640): the adaptive gates are replaced by CZ / CNOT

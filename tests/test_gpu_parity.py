@@ -994,6 +994,9 @@ def test_start_decomposition_config1(sq, optimizer):
     assert sq.abi.ADAPTIVE not in types
     assert 0 < dec.get_CNOT_Count() <= 2 * 6 * dec.decomposition_level
     assert close_rel(dec.Optimization_Problem(params), err, 1e-9)
+    # compress_circuit ran before that: no more decomposing layers than the level search built (6 pairs per level + the
+    # finalizing layer), and removing layers kept the error below the tolerance of the test
+    assert dec.get_Circuit().get_Gate_Num() <= 6 * dec.decomposition_level + 1
 
 
 # ---- N3: constant sub-circuits multiplied out into dense kernels -----------------------------------------------------
