@@ -208,7 +208,7 @@ __device__ __forceinline__ void warp_mat_mul(const cplx* a, const cplx* b, cplx*
 // ws: 3 * 64 complex of shared memory owned by the warp.
 __device__ inline void build_block_warp(const DevOp& op, const DevMember* __restrict__ members, const double* __restrict__ params,
                                         const cplx* __restrict__ pool, cplx* __restrict__ kdst, cplx* __restrict__ dkdst,
-                                        bool with_deriv, cplx* ws, int lane) {
+                                        int with_deriv, cplx* ws, int lane) {
     const int dim = op.dim, d2 = dim * dim, nm = op.n_members;
     cplx* R = ws;        // running prefix / suffix
     cplx* E = ws + 64;   // embedded member
@@ -231,7 +231,9 @@ __device__ inline void build_block_warp(const DevOp& op, const DevMember* __rest
         __syncwarp();
     }
     for (int i = lane; i < d2; i += 32) kdst[i] = R[i];
-    if (!with_deriv || op.n_params == 0) return;
+    // with_deriv == 2: the derivative kernels are finished by build_block_derivs (one warp per member) instead of this warp
+    // walking all members again
+    if (with_deriv != 1 || op.n_params == 0) return;
     __syncwarp();
     for (int i = lane; i < d2; i += 32) R[i] = (i / dim == i % dim) ? cmake(1.0, 0.0) : czero();  // suffix
     __syncwarp();
@@ -272,6 +274,75 @@ __device__ inline void build_block_warp(const DevOp& op, const DevMember* __rest
 
 // One warp per (parameter set b, op): fills the forward kernel table and the derivative kernel table.
 // ktab[b * kern_total + op.kern_off + ...], dktab[b * dkern_total + op.dkern_off + slot * dim*dim + ...].
+
+// Second half of the block tables: dM/dtheta_p = E_{nm-1} .. E_{j+1} dE_j(p) E_{j-1} .. E_0 for the parameters p of member j.
+// build_block_warp left the prefix E_{j-1} .. E_0 in the parameter's slot; this warp rebuilds the suffix for ITS member (the
+// same left-to-right products the single-warp version accumulated, so the tables are bit-identical) and finishes the slots.
+// One warp per member: the critical path of a table build drops from ~2 P_block + 2 nm small matrix products to ~nm + 2 per
+// parameter of one member -- it is what a single evaluation (BFGS) waits for before the executor starts.
+__device__ inline void block_member_derivs(const DevOp& op, const DevMember* __restrict__ members, const double* __restrict__ params,
+                                           const cplx* __restrict__ pool, cplx* __restrict__ dkdst, int j, cplx* ws, int lane) {
+    const int dim = op.dim, d2 = dim * dim, nm = op.n_members;
+    cplx* R = ws;        // suffix E_{nm-1} .. E_{j+1}
+    cplx* E = ws + 64;   // embedded member
+    cplx* T = ws + 128;  // product scratch
+    cplx k[16];
+    const DevMember m = members[op.member_off + j];
+    if (m.n_params == 0) return;
+    for (int i = lane; i < d2; i += 32) R[i] = (i / dim == i % dim) ? cmake(1.0, 0.0) : czero();
+    __syncwarp();
+    for (int jj = nm - 1; jj > j; --jj) {
+        const DevMember mm = members[op.member_off + jj];
+        Trig tt;
+        member_trig(mm, params, tt);
+        member_kernel(mm, tt, -1, pool, k);
+        for (int i = lane; i < d2; i += 32) E[i] = embed_elem(mm, k, false, i / dim, i % dim);
+        __syncwarp();
+        warp_mat_mul(R, E, T, dim, lane);
+        for (int i = lane; i < d2; i += 32) R[i] = T[i];
+        __syncwarp();
+    }
+    Trig t;
+    member_trig(m, params, t);
+    for (int p = 0; p < m.n_params; ++p) {
+        cplx* dd = dkdst + (size_t)(m.slot0 + p) * d2;  // holds the prefix E_{j-1}..E_0
+        member_kernel(m, t, p, pool, k);
+        for (int i = lane; i < d2; i += 32) E[i] = embed_elem(m, k, true, i / dim, i % dim);
+        __syncwarp();
+        // T = dE * prefix (prefix read from global: written by build_kernel_tables)
+        for (int i = lane; i < d2; i += 32) {
+            const int r = i / dim, c = i - r * dim;
+            cplx acc = czero();
+            for (int l = 0; l < dim; ++l) acc = cfma(E[r * dim + l], dd[l * dim + c], acc);
+            T[i] = acc;
+        }
+        __syncwarp();
+        // dd = suffix * T
+        for (int i = lane; i < d2; i += 32) {
+            const int r = i / dim, c = i - r * dim;
+            cplx acc = czero();
+            for (int l = 0; l < dim; ++l) acc = cfma(R[r * dim + l], T[l * dim + c], acc);
+            dd[i] = acc;
+        }
+        __syncwarp();
+    }
+}
+
+static const int DERIV_WARPS = 8;
+// one CTA per (parameter set, op), its warps deal the block's members
+__global__ void __launch_bounds__(DERIV_WARPS * 32) build_block_derivs(const DevOp* __restrict__ ops, int n_ops, const DevMember* __restrict__ members,
+                                                                       const double* __restrict__ params, int n_params, const cplx* __restrict__ pool,
+                                                                       cplx* __restrict__ dktab, int dkern_total) {
+    __shared__ cplx ws[DERIV_WARPS][192];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.x / n_ops, kop = blockIdx.x - b * n_ops;
+    const DevOp op = ops[kop];
+    if (op.type != SQ_OP_BLOCK || op.n_params == 0 || op.kern_off < 0) return;
+    const double* __restrict__ pb = params + (size_t)b * n_params;
+    cplx* dkdst = dktab + (size_t)b * dkern_total + op.dkern_off;
+    for (int j = warp; j < op.n_members; j += DERIV_WARPS) block_member_derivs(op, members, pb, pool, dkdst, j, ws[warp], lane);
+}
+
 static const int TABLE_WARPS = 4;
 __global__ void __launch_bounds__(TABLE_WARPS * 32) build_kernel_tables(
     const DevOp* __restrict__ ops, int n_ops, const DevMember* __restrict__ members, const double* __restrict__ params,
@@ -288,7 +359,7 @@ __global__ void __launch_bounds__(TABLE_WARPS * 32) build_kernel_tables(
     cplx* kdst = ktab + (size_t)b * kern_total + op.kern_off;
     cplx* dkdst = dktab + (size_t)b * dkern_total + (op.dkern_off >= 0 ? op.dkern_off : 0);
     if (op.type == SQ_OP_BLOCK) {
-        build_block_warp(op, members, pb, pool, kdst, dkdst, with_deriv != 0, ws[warp], lane);
+        build_block_warp(op, members, pb, pool, kdst, dkdst, with_deriv, ws[warp], lane);
         return;
     }
     if (lane != 0) return;

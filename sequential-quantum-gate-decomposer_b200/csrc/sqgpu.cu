@@ -137,6 +137,8 @@ struct Options {
     int async_tiles = 1;       // windowed executor (SQ_WIN_BULK builds): double-buffered tiles in the forward segments
     int cluster = 1;           // thread-block-cluster executor: 0 off; 1 (default) where it is the measured winner (a column that
                                // fits one CTA only once per SM) or the only fused option; 2: also instead of the windowed executor
+    int split_tables = 1;      // derivative kernel tables of fused blocks by one warp per member (build_block_derivs): 0 off, 1 for small
+                               // batches (the single evaluation a BFGS line search waits for), 2 always; bit-identical tables either way
     int const_fuse_qubits = 4; // constant sub-circuits are multiplied out on the host into dense blocks of up to this many qubits (0: off)
 };
 
@@ -159,6 +161,7 @@ const OptionName kOptionNames[] = {
     {"async_tiles", &Options::async_tiles, 0, 1},
     {"const_fuse_qubits", &Options::const_fuse_qubits, 0, 5},
     {"cluster", &Options::cluster, 0, 2},
+    {"split_tables", &Options::split_tables, 0, 2},
 };
 
 int option_set(Options& o, const char* name, long long value) {
@@ -1025,17 +1028,29 @@ int pick_cluster_rho(sqgpu_ctx* c, bool grad, int batch) {
 
 // ---- building blocks (all enqueue on `st`, no host sync) --------------------------------------------------------
 
+static const int SPLIT_TABLES_MAX_BATCH = 8;
 int run_tables(sqgpu_ctx* c, const double* d_params, int batch, bool with_deriv, cudaStream_t st) {
     int rc;
     if ((rc = c->P->wKtab.ensure(std::max<size_t>(1, (size_t)batch * c->P->kern_total) * sizeof(cplx)))) return rc;
     if ((rc = c->P->wDKtab.ensure(std::max<size_t>(1, (size_t)batch * c->P->dkern_total) * sizeof(cplx)))) return rc;
     const long long total = (long long)batch * c->P->n_ops;
     if (total == 0) return SQGPU_OK;
+    // small batches: the table build is on the critical path of the evaluation, the member-parallel second kernel shortens it;
+    // large batches fill the device with one warp per (set, op) and the extra suffix products would only add work
+    const bool split = with_deriv && c->n_params > 0 && !c->P->members.empty() &&
+                       (c->opt.split_tables == 2 || (c->opt.split_tables == 1 && batch <= SPLIT_TABLES_MAX_BATCH));
     // one warp per (parameter set, op)
     build_kernel_tables<<<(unsigned)((total + TABLE_WARPS - 1) / TABLE_WARPS), TABLE_WARPS * 32, 0, st>>>(
         c->P->dOps.as<DevOp>(), c->P->n_ops, c->P->dMembers.as<DevMember>(), d_params, c->n_params, batch, c->dPool.as<cplx>(),
-        c->P->wKtab.as<cplx>(), c->P->kern_total, c->P->wDKtab.as<cplx>(), c->P->dkern_total, with_deriv ? 1 : 0);
+        c->P->wKtab.as<cplx>(), c->P->kern_total, c->P->wDKtab.as<cplx>(), c->P->dkern_total, with_deriv ? (split ? 2 : 1) : 0);
     c->launches++;
+    if (split) {
+        // derivative kernels of the fused blocks: the prefixes are in place, one warp per member finishes them
+        const long long ctas = (long long)batch * c->P->n_ops;
+        build_block_derivs<<<(unsigned)ctas, DERIV_WARPS * 32, 0, st>>>(c->P->dOps.as<DevOp>(), c->P->n_ops, c->P->dMembers.as<DevMember>(), d_params,
+                                                                          c->n_params, c->dPool.as<cplx>(), c->P->wDKtab.as<cplx>(), c->P->dkern_total);
+        c->launches++;
+    }
     CUDA_TRY(cudaGetLastError());
     return SQGPU_OK;
 }

@@ -1028,6 +1028,35 @@ def test_constant_subcircuit_fusion_matches_oracle(sq, port, n, support, opt):
     e.close()
 
 
+@pytest.mark.parametrize("n,batch", [(6, 1), (10, 1), (10, 3)])
+def test_member_parallel_derivative_tables_are_bit_identical(sq, port, n, batch):
+    """derivative kernel tables of the fused blocks (Gates_block::apply_derivate_to's product rule, Gates_block.cpp:1011-1150,
+    restricted to the block): built by one warp per block (option split_tables = 0) and by one warp per block MEMBER
+    (build_block_derivs, the default for small batches -- it shortens what a single BFGS evaluation waits for). Same products
+    in the same order: cost and gradient bit-identical, and against the oracle."""
+    c = H.adaptive_circuit(n, 2)
+    d, pool = c.descriptors()
+    P = c.get_Parameter_Num()
+    U = H.random_unitary(1 << n, seed=3).conj().T.copy()
+    ps = H.random_params(P, seed=8, batch=batch)
+    res = []
+    for mode in (0, 2):
+        e = sq.Engine(0, options={"split_tables": mode})
+        e.upload_matrix(U)
+        e.set_circuit(c)
+        e.set_cost(0, 0)
+        l0 = e.launch_count()
+        f, g = e.cost_grad_batched(ps)
+        res.append((f.copy(), g.copy(), e.launch_count() - l0))
+        e.close()
+    assert res[1][2] == res[0][2] + 1  # the member-parallel kernel is one more launch
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    if n <= 6:
+        for b in range(batch):
+            f_ref, g_ref = port.cost_grad(d, P, ps[b], U, n, 0, pool=pool)
+            assert close_rel(res[1][0][b], f_ref) and close_rel(res[1][1][b], g_ref)
+
+
 # ---- cluster executor: thread-block clusters share a column over distributed shared memory -----------------------------
 
 @pytest.mark.parametrize("n,opt,want_cluster", [(12, {}, 2), (13, {"cluster": 2}, 4), (14, {"cluster": 2}, 8)])
