@@ -94,11 +94,12 @@ class N_Qubit_Decomposition_custom:
 
     # ---- optimisation over the GPU cost path (thin; see the module docstring) ------------------------------------
     def set_Optimizer(self, optimizer="BFGS"):
-        """"BFGS": L-BFGS with a device-batched line search; "ADAM": device-resident ADAM trajectories. The reference's other
-        engines (AGENTS, COSINE, BAYES_OPT ...) stay with the reference: they run over this cost path through integration/."""
-        if optimizer not in ("BFGS", "ADAM"):
-            raise Exception("set_Optimizer: '%s' is not provided by this package (BFGS, ADAM); use the reference's engines over the "
-                            "GPU cost path through the drop-in of integration/" % optimizer)
+        """"BFGS": L-BFGS with a device-batched line search; "ADAM": device-resident ADAM trajectories; "COSINE": the reference's
+        parameter-shift engine with its shift batches and its line search as device batches (optimize.cosine). The reference's
+        other engines (AGENTS, BAYES_OPT ...) stay with the reference: they run over this cost path through integration/."""
+        if optimizer not in ("BFGS", "ADAM", "COSINE"):
+            raise Exception("set_Optimizer: '%s' is not provided by this package (BFGS, ADAM, COSINE); use the reference's engines "
+                            "over the GPU cost path through the drop-in of integration/" % optimizer)
         self._optimizer = optimizer
 
     def set_Optimization_Tolerance(self, tolerance):
@@ -147,6 +148,21 @@ class N_Qubit_Decomposition_custom:
             _, best_cost, best_theta, _ = eng.adam_get()
             b = int(np.argmin(best_cost))
             return best_theta[b], float(best_cost[b])
+
+        if self._optimizer == "COSINE":
+            # COSINE.cpp:226-228, 411-414: the three-point rule is defined for the Frobenius cost only (a sinusoid of period 2 pi
+            # in every parameter); the other variants throw there as well
+            if self._variant != abi.FROBENIUS_NORM:
+                raise Exception("solve_layer_optimization_problem_COSINE: Not implemented method.")
+            cfg = self.config
+            x, f, _, ne = optimize.cosine(
+                eng.cost_batched, rng.random(P) * 2 * np.pi if x0 is None else x0, rng,
+                batch_size=min(P, int(cfg.get("batch_size_cosine", cfg.get("batch_size", min(64, P))))),
+                max_iter=int(cfg.get("max_inner_iterations_cosine", cfg.get("max_inner_iterations", 2000))),
+                tol=float(cfg.get("optimization_tolerance_cosine", tol)), double_period=False,
+                check_for_convergence=bool(cfg.get("check_for_convergence", cfg.get("check_for_convergence_cosine", 1))))
+            self._num_evaluations += ne
+            return x, f
 
         def cost_grad(x):
             f, g = eng.cost_grad_batched(x.reshape(1, -1))

@@ -6,8 +6,12 @@ on the hot path: ``set_Ansatz``, ``Generate_Circuit``, ``set_Gate_Structure``, `
 ``Optimization_Problem``, ``Optimization_Problem_Grad``, ``Optimization_Problem_Combined``, ``Optimization_Problem_Batch``,
 ``apply_to``. Every evaluation runs on the GPU through the C-ABI (sqgpu_vqe_energy[_grad]_batched): there is no CPU path.
 
-The state-vector backend only; the density-matrix backend, the optimizers and the entropy helpers are outside the hot path
-(SURVEY.md §2.3).
+``Start_Optimization`` (with ``set_Optimizer``, ``set_Optimized_Parameters``, ``get_Optimized_Parameters``) is the thin N1 layer
+over that path: "COSINE" (the reference's parameter-shift engine, its shift batches and line search as device batches),
+and "BFGS" (L-BFGS, every line search one device batch).
+
+The state-vector backend only; the density-matrix backend, the reference's other optimizers and the entropy helpers are outside
+the hot path and run over this path through the drop-in of integration/.
 """
 import numpy as np
 
@@ -162,6 +166,62 @@ class Variational_Quantum_Eigensolver:
 
     def Optimization_Problem_Grad(self, parameters):
         return self.Optimization_Problem_Combined(parameters)[1]
+
+    # ---- optimisation over the hot path --------------------------------------------------------------
+    def set_Optimizer(self, alg="COSINE"):
+        if alg not in ("COSINE", "BFGS"):
+            raise Exception("set_Optimizer: '%s' is not provided by this package (COSINE, BFGS); use the reference's "
+                            "engines over the GPU energy path through the drop-in of integration/" % alg)
+        self._optimizer = alg
+
+    def set_Optimized_Parameters(self, parameters):
+        p = np.ascontiguousarray(parameters, dtype=np.float64).reshape(-1)
+        if p.size != self.get_Parameter_Num():
+            raise Exception("Number of free parameters should be %d, but got %d" % (self.get_Parameter_Num(), p.size))
+        self._optimized_parameters = p.copy()
+
+    def get_Optimized_Parameters(self):
+        if getattr(self, "_optimized_parameters", None) is None:
+            raise Exception("get_Optimized_Parameters: no parameters have been set or optimised")
+        return self._optimized_parameters.copy()
+
+    def Start_Optimization(self):
+        """start_optimization (...Base.cpp:100-160): minimise the energy from the stored parameters (set_Optimized_Parameters;
+        random in [0, 2 pi) otherwise, as the reference's engines draw them) with the engine chosen by set_Optimizer. Config keys
+        as in the reference: max_inner_iterations[_cosine], batch_size[_cosine], check_for_convergence, seed.
+        Returns the energy; the parameters are in get_Optimized_Parameters()."""
+        from . import optimize
+
+        eng = self._sync()
+        P = self.get_Parameter_Num()
+        cfg = self.config
+        rng = np.random.default_rng(int(cfg.get("seed", 0)))
+        x0 = getattr(self, "_optimized_parameters", None)
+        if x0 is None or x0.size != P:
+            x0 = rng.random(P) * 2 * np.pi
+        alg = getattr(self, "_optimizer", "COSINE")
+        max_iter = int(cfg.get("max_inner_iterations", 1000))
+
+        def energy_grad(x):
+            e, g = eng.vqe_energy_grad_batched(x.reshape(1, -1))
+            return float(e[0]), g[0]
+
+        if alg == "COSINE":
+            # COSINE.cpp:226-228: cost_fnc == VQE selects the three-point rule with the doubled period (shifts pi/4, pi/2)
+            x, f, it, ne = optimize.cosine(eng.vqe_energy_batched, x0, rng,
+                                           batch_size=min(P, int(cfg.get("batch_size_cosine", cfg.get("batch_size", min(64, P))))),
+                                           max_iter=int(cfg.get("max_inner_iterations_cosine", max_iter)), tol=-np.inf, double_period=True,
+                                           check_for_convergence=bool(cfg.get("check_for_convergence", 1)))
+        else:
+            def line_search(x, d, alphas):  # all trial step lengths of an iteration: one batched energy+gradient call
+                e, g = eng.vqe_energy_grad_batched(x[None, :] + np.asarray(alphas)[:, None] * d[None, :])
+                return e, g @ d
+
+            x, f, it, ne = optimize.lbfgs(energy_grad, line_search, x0, max_iter=max_iter, tol=-np.inf, gtol=float(cfg.get("gradient_tolerance", 1e-8)))
+        self._optimized_parameters = np.asarray(x, dtype=np.float64).copy()
+        self._num_evaluations = getattr(self, "_num_evaluations", 0) + ne
+        self._current_minimum = float(f)
+        return float(f)
 
     def apply_to(self, parameters_mtx, state_to_be_transformed):
         """in place: state <- C(parameters) state"""

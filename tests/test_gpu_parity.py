@@ -966,6 +966,77 @@ def test_batched_line_search(sq, port):
     e.close()
 
 
+def test_cosine_engine_on_the_device(sq, port):
+    """N1, the COSINE shift batches (optimization_engines/COSINE.cpp:255-291 through optimization_problem_batched): the engine of
+    optimize.cosine over the device's batched cost. Same trajectory as with the oracle as the cost callable for the first
+    iterations (same random draws; the costs agree to 1e-12, so the arg-min of the line-search grid and the updates do), a 4-qubit
+    decomposition through set_Optimizer("COSINE"), and the reference's refusal of the other cost variants."""
+    n = 3
+    c = H.adaptive_circuit(n, 2)
+    d, pool = c.descriptors()
+    P = c.get_Parameter_Num()
+    U = np.ascontiguousarray(port.apply_circuit(d, H.random_params(P, seed=5), np.eye(1 << n, dtype=np.complex128)).conj().T)
+    x0 = H.random_params(P, seed=9)
+    e = sq.Engine(0)
+    e.upload_matrix(U)
+    e.set_circuit(c)
+    e.set_cost(0, 0)
+    xg, fg, _, ne = sq.optimize.cosine(e.cost_batched, x0, np.random.default_rng(3), batch_size=16, max_iter=5, tol=1e-8)
+    xo, fo, _, _ = sq.optimize.cosine(lambda X: np.array([port.cost(d, v, U, n, 0) for v in X]), x0, np.random.default_rng(3), batch_size=16,
+                                      max_iter=5, tol=1e-8)
+    assert np.abs(xg - xo).max() < 1e-9 and close_rel(fg, fo) and ne == 1 + 5 * 48
+    xg, fg, it, _ = sq.optimize.cosine(e.cost_batched, x0, np.random.default_rng(3), batch_size=16, max_iter=600, tol=1e-8)
+    assert fg < 0.02 and close_rel(fg, port.cost(d, xg, U, n, 0))
+    e.close()
+    import golden_cases as G
+
+    Uct = G.load("C1_L3").U
+    dec = sq.N_Qubit_Decomposition_adaptive(Uct, level_limit_max=3, level_limit_min=3,
+                                            config={"optimization_tolerance": 1e-6, "max_inner_iterations_cosine": 300, "batch_size_cosine": 32,
+                                                    "compress": 0, "finalize": 0})
+    dec.set_Optimizer("COSINE")
+    err = dec.Start_Decomposition()
+    assert err < 0.5 and close_rel(dec.Optimization_Problem(dec.get_Optimized_Parameters()), err, 1e-9)
+    dec.set_Cost_Function_Variant(3)
+    with pytest.raises(Exception, match="Not implemented"):
+        dec._optimize_structure(np.random.default_rng(0))
+
+
+def test_vqe_start_optimization(sq, port):
+    """Variational_Quantum_Eigensolver.Start_Optimization over the device energy path (...Base.cpp:100-160; the reference's
+    tests/VQE/test_VQE.py:101-140 runs it with COSINE / BFGS): 6-qubit Heisenberg model, HEA_ZYZ ansatz. BFGS (every line search
+    one batched energy+gradient call) and COSINE (doubled period, COSINE.cpp:293-330) approach the exact ground energy from
+    above; both end points are re-evaluated by the oracle."""
+    import scipy.sparse as sp
+
+    n = 6
+    ip, ix, dat = H.heisenberg_csr_fast(n)
+    Hm = sp.csr_matrix((dat, ix, ip), shape=(1 << n, 1 << n))
+    e_min = float(np.linalg.eigvalsh(Hm.toarray())[0])
+    results = {}
+    for alg, cfg in (("BFGS", {"max_inner_iterations": 300}), ("COSINE", {"max_inner_iterations": 150, "batch_size": 16})):
+        vqe = sq.Variational_Quantum_Eigensolver(Hm, n, config=dict(cfg, seed=4))
+        vqe.set_Ansatz("HEA_ZYZ")
+        vqe.Generate_Circuit(3, 1)
+        P = vqe.get_Parameter_Num()
+        x0 = H.random_params(P, seed=11)
+        vqe.set_Optimizer(alg)
+        vqe.set_Optimized_Parameters(x0)
+        e0 = vqe.Optimization_Problem(x0)
+        ef = vqe.Start_Optimization()
+        x = vqe.get_Optimized_Parameters()
+        d, _ = vqe.get_Circuit().descriptors()
+        psi0 = np.zeros(1 << n, dtype=np.complex128)
+        psi0[0] = 1
+        assert close_rel(ef, port.vqe_energy(d, x, psi0, ip, ix, dat), 1e-10)
+        assert e_min - 1e-9 <= ef < e0 - 1.0
+        results[alg] = ef
+    # e_min < 0: both get within 30 % of the exact ground energy with a 3-layer ansatz (the oracle-driven runs end at 80 %)
+    assert results["BFGS"] < 0.7 * e_min and results["COSINE"] < 0.7 * e_min
+    with pytest.raises(Exception):
+        vqe.set_Optimizer("AGENTS")
+
+
 @pytest.mark.parametrize("optimizer", ["BFGS", "ADAM"])
 def test_start_decomposition_config1(sq, optimizer):
     """BASELINE configs[0] end to end through this package: N_Qubit_Decomposition_adaptive on data/Umtx.mat (4 qubits; the
