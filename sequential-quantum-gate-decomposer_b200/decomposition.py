@@ -95,10 +95,11 @@ class N_Qubit_Decomposition_custom:
     # ---- optimisation over the GPU cost path (thin; see the module docstring) ------------------------------------
     def set_Optimizer(self, optimizer="BFGS"):
         """"BFGS": L-BFGS with a device-batched line search; "ADAM": device-resident ADAM trajectories; "COSINE": the reference's
-        parameter-shift engine with its shift batches and its line search as device batches (optimize.cosine). The reference's
-        other engines (AGENTS, BAYES_OPT ...) stay with the reference: they run over this cost path through integration/."""
-        if optimizer not in ("BFGS", "ADAM", "COSINE"):
-            raise Exception("set_Optimizer: '%s' is not provided by this package (BFGS, ADAM, COSINE); use the reference's engines "
+        parameter-shift engine with its shift batches and its line search as device batches (optimize.cosine); "AGENTS": the
+        reference's independent walkers, all their shifted parameter sets one device batch per iteration (optimize.agents). The
+        reference's other engines (BAYES_OPT, BFGS2 ...) stay with the reference: they run over this cost path through integration/."""
+        if optimizer not in ("BFGS", "ADAM", "COSINE", "AGENTS"):
+            raise Exception("set_Optimizer: '%s' is not provided by this package (BFGS, ADAM, COSINE, AGENTS); use the reference's engines "
                             "over the GPU cost path through the drop-in of integration/" % optimizer)
         self._optimizer = optimizer
 
@@ -149,12 +150,25 @@ class N_Qubit_Decomposition_custom:
             b = int(np.argmin(best_cost))
             return best_theta[b], float(best_cost[b])
 
-        if self._optimizer == "COSINE":
-            # COSINE.cpp:226-228, 411-414: the three-point rule is defined for the Frobenius cost only (a sinusoid of period 2 pi
-            # in every parameter); the other variants throw there as well
+        if self._optimizer in ("COSINE", "AGENTS"):
+            # COSINE.cpp:226-228, 411-414 / AGENTS.cpp:333-335: the three-point rule is defined for the Frobenius cost (a sinusoid
+            # of period 2 pi in every parameter); COSINE throws for the other variants, AGENTS' five-point Hilbert-Schmidt rule
+            # is not provided here
             if self._variant != abi.FROBENIUS_NORM:
-                raise Exception("solve_layer_optimization_problem_COSINE: Not implemented method.")
+                raise Exception("solve_layer_optimization_problem_%s: Not implemented method." % self._optimizer)
             cfg = self.config
+            if self._optimizer == "AGENTS":
+                x, f, _, ne = optimize.agents(
+                    eng.cost_batched, rng.random(P) * 2 * np.pi if x0 is None else x0, rng,
+                    agent_num=int(cfg.get("agent_num_agent", cfg.get("agent_num", 64))),
+                    max_iter=int(cfg.get("max_inner_iterations_agent", cfg.get("max_inner_iterations", 10000))),
+                    tol=float(cfg.get("optimization_tolerance_agent", tol)),
+                    agent_lifetime=int(cfg.get("agent_lifetime_agent", cfg.get("agent_lifetime", 1000))),
+                    exploration_rate=float(cfg.get("agent_exploration_rate_agent", cfg.get("agent_exploration_rate", 0.2))),
+                    agent_randomization_rate=float(cfg.get("agent_randomization_rate", 0.2)), radius=float(cfg.get("Randomized_Radius", 1.0)),
+                    convergence_length=int(cfg.get("convergence_length_agent", cfg.get("convergence_length", 20))))
+                self._num_evaluations += ne
+                return x, f
             x, f, _, ne = optimize.cosine(
                 eng.cost_batched, rng.random(P) * 2 * np.pi if x0 is None else x0, rng,
                 batch_size=min(P, int(cfg.get("batch_size_cosine", cfg.get("batch_size", min(64, P))))),

@@ -164,3 +164,96 @@ def cosine(cost_batched, x0, rng, batch_size=None, max_iter=2000, tol=1e-10, dou
         if check_for_convergence and hist_mean != 0 and abs((hist_mean - f) / hist_mean) < 1e-7 and abs(var / hist_mean) < 1e-7:
             break
     return x, f, it, n_eval
+
+
+def agents(cost_batched, x0, rng, agent_num=64, max_iter=10000, tol=1e-10, double_period=False, agent_lifetime=1000,
+           exploration_rate=0.2, agent_randomization_rate=0.2, randomization_rate=0.3, radius=1.0, convergence_length=20,
+           scale_by_cost=True, callback=None):
+    """The reference's AGENTS engine (optimization_engines/AGENTS.cpp:60-938), three-point rule (Frobenius cost; doubled period for
+    the VQE energy, :333-335): ``agent_num`` parameter vectors walk independently -- per iteration every agent draws ONE of its
+    parameters and jumps to the minimum of the sinusoid the cost is along it (exact, no line search: the new cost is offset -
+    amplitude, :395-415) -- and every ``agent_lifetime`` iterations the costs are re-evaluated, the best agent is recorded,
+    and each worse agent adopts the best one's state with probability ``exploration_rate``, then perturbs it with probability
+    ``agent_randomization_rate`` (randomize_parameters, Optimization_Interface.cpp:576-603: each parameter with probability
+    ``randomization_rate`` moves by U(-2 pi, 2 pi) * radius [* sqrt(f) for the decomposition costs]).
+
+    Arranged for the device: the two shifted parameter sets of all agents are ONE cost_batched call of 2 x agent_num rows per
+    iteration (the reference issues two), and the perturbed agents of a census are re-scored by one batched call instead of one
+    single evaluation each. Stops when an agent is below ``tol`` or the recorded minimum stalls over ``convergence_length``
+    censuses (:849-866). Returns (x, f, iterations, evaluations)."""
+    x0 = np.array(x0, dtype=np.float64).reshape(-1)
+    P = x0.size
+    if P == 0:
+        return x0, float(np.asarray(cost_batched(x0.reshape(1, -1)))[0]), 0, 1
+    A = int(agent_num)
+    shift = np.pi / 4 if double_period else np.pi / 2
+
+    def randomized(src, f_ref):
+        out = src.copy()
+        mask = rng.random(P) <= randomization_rate
+        step = rng.uniform(-2 * np.pi, 2 * np.pi, P) * radius * (np.sqrt(max(f_ref, 0.0)) if scale_by_cost else 1.0)
+        out[mask] += step[mask]
+        return out
+
+    f_best = float(np.asarray(cost_batched(x0.reshape(1, -1)))[0])
+    x_best = x0.copy()
+    X = np.stack([x0] + [randomized(x0, f_best) for _ in range(A - 1)])
+    F = np.asarray(cost_batched(X), dtype=np.float64).copy()
+    n_eval = 1 + A
+    hist = np.zeros(convergence_length)
+    hist_mean, hist_idx = 0.0, 0
+    rows = np.arange(A)
+    it = 0
+    for it in range(max_iter):
+        idx = rng.integers(0, P, A)
+        S = np.concatenate([X, X])
+        S[rows, idx] += shift
+        S[A + rows, idx] += 2 * shift
+        vals = np.asarray(cost_batched(S))
+        n_eval += 2 * A
+        f_half, f_full = vals[:A], vals[A:]
+        a_cos, offset = (F - f_full) / 2, (F + f_full) / 2
+        a_sin = offset - f_half
+        X[rows, idx] += cosine_updates(F, f_half, f_full, double_period)
+        F = offset - np.sqrt(a_sin * a_sin + a_cos * a_cos)
+        census = it % agent_lifetime == 0
+        if census:
+            F = np.asarray(cost_batched(X), dtype=np.float64).copy()  # the predicted costs drift by rounding: re-evaluate (:700-705)
+            n_eval += A
+            b = int(np.argmin(F))
+            if F[b] <= f_best:
+                f_best, x_best = float(F[b]), X[b].copy()
+            moved = []
+            for a in range(A):
+                if a != b and F[a] > f_best and rng.random() < exploration_rate:
+                    X[a], F[a] = X[b], F[b]
+                    if rng.random() < agent_randomization_rate:
+                        X[a] = randomized(x_best, f_best)
+                        moved.append(a)
+            if moved:
+                F[moved] = np.asarray(cost_batched(X[moved]))
+                n_eval += len(moved)
+            hist_mean += (f_best - hist[hist_idx]) / hist.size
+            hist[hist_idx] = f_best
+            hist_idx = (hist_idx + 1) % hist.size
+            var = np.sqrt(((hist - hist_mean) ** 2).sum()) / hist.size
+            if callback is not None:
+                callback(it, x_best, f_best)
+            if abs(hist_mean - f_best) < 1e-7 and var < 1e-7:
+                break
+        if F.min() < tol:
+            b = int(np.argmin(F))
+            f_chk = float(np.asarray(cost_batched(X[b:b + 1]))[0])  # the stop is decided on an evaluated cost, not a predicted one
+            n_eval += 1
+            F[b] = f_chk
+            if f_chk < f_best:
+                f_best, x_best = f_chk, X[b].copy()
+            if f_chk < tol:
+                break
+    b = int(np.argmin(F))
+    if F[b] < f_best:
+        f_chk = float(np.asarray(cost_batched(X[b:b + 1]))[0])
+        n_eval += 1
+        if f_chk < f_best:
+            f_best, x_best = f_chk, X[b].copy()
+    return x_best, f_best, it + 1, n_eval

@@ -7,7 +7,7 @@ on the hot path: ``set_Ansatz``, ``Generate_Circuit``, ``set_Gate_Structure``, `
 ``apply_to``. Every evaluation runs on the GPU through the C-ABI (sqgpu_vqe_energy[_grad]_batched): there is no CPU path.
 
 ``Start_Optimization`` (with ``set_Optimizer``, ``set_Optimized_Parameters``, ``get_Optimized_Parameters``) is the thin N1 layer
-over that path: "COSINE" (the reference's parameter-shift engine, its shift batches and line search as device batches),
+over that path: "COSINE" and "AGENTS" (the reference's parameter-shift engines, their shift batches as device batches),
 and "BFGS" (L-BFGS, every line search one device batch).
 
 The state-vector backend only; the density-matrix backend, the reference's other optimizers and the entropy helpers are outside
@@ -169,8 +169,8 @@ class Variational_Quantum_Eigensolver:
 
     # ---- optimisation over the hot path --------------------------------------------------------------
     def set_Optimizer(self, alg="COSINE"):
-        if alg not in ("COSINE", "BFGS"):
-            raise Exception("set_Optimizer: '%s' is not provided by this package (COSINE, BFGS); use the reference's "
+        if alg not in ("COSINE", "AGENTS", "BFGS"):
+            raise Exception("set_Optimizer: '%s' is not provided by this package (COSINE, AGENTS, BFGS); use the reference's "
                             "engines over the GPU energy path through the drop-in of integration/" % alg)
         self._optimizer = alg
 
@@ -212,6 +212,16 @@ class Variational_Quantum_Eigensolver:
                                            batch_size=min(P, int(cfg.get("batch_size_cosine", cfg.get("batch_size", min(64, P))))),
                                            max_iter=int(cfg.get("max_inner_iterations_cosine", max_iter)), tol=-np.inf, double_period=True,
                                            check_for_convergence=bool(cfg.get("check_for_convergence", 1)))
+        elif alg == "AGENTS":
+            # AGENTS.cpp:334: cost_fnc == VQE with linesearch_points == 3 (the default) is the doubled-period three-point rule;
+            # randomize_parameters does not scale the radius by the cost for the VQE (Optimization_Interface.cpp:596)
+            x, f, it, ne = optimize.agents(eng.vqe_energy_batched, x0, rng, agent_num=int(cfg.get("agent_num_agent", cfg.get("agent_num", 64))),
+                                           max_iter=int(cfg.get("max_inner_iterations_agent", max_iter)), tol=-np.inf, double_period=True,
+                                           agent_lifetime=int(cfg.get("agent_lifetime_agent", cfg.get("agent_lifetime", 1000))),
+                                           exploration_rate=float(cfg.get("agent_exploration_rate", 0.2)),
+                                           agent_randomization_rate=float(cfg.get("agent_randomization_rate", 0.2)),
+                                           radius=float(cfg.get("Randomized_Radius", 1.0)),
+                                           convergence_length=int(cfg.get("convergence_length_agent", cfg.get("convergence_length", 20))), scale_by_cost=False)
         else:
             def line_search(x, d, alphas):  # all trial step lengths of an iteration: one batched energy+gradient call
                 e, g = eng.vqe_energy_grad_batched(x[None, :] + np.asarray(alphas)[:, None] * d[None, :])

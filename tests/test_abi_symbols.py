@@ -296,8 +296,9 @@ def test_lbfgs_host_loop_with_oracle_callables(port):
     assert f < 1e-4 and ne > it > 0  # far below the starting cost (~1); the decomposition tolerance of the reference is 1e-4
     dec = sq.N_Qubit_Decomposition_adaptive(U, level_limit_max=3, level_limit_min=1)
     with pytest.raises(Exception):
-        dec.set_Optimizer("AGENTS")
+        dec.set_Optimizer("BAYES_OPT")
     dec.set_Optimizer("COSINE")
+    dec.set_Optimizer("AGENTS")
     with pytest.raises(Exception):
         dec.get_Optimized_Parameters()
 
@@ -357,6 +358,25 @@ def test_cosine_engine_with_oracle_callables(port):
     assert fv < energy(xv) - 0.5
     with pytest.raises(Exception):
         sq.optimize.cosine(cost_batched, x, np.random.default_rng(3), batch_size=P + 1)
+    # AGENTS (AGENTS.cpp:333-415, 700-870): independent walkers, each jumps to the exact minimum along one random parameter per
+    # iteration, so the cost it PREDICTS (offset - amplitude) is the cost the oracle evaluates; census every `agent_lifetime`
+    calls.clear()
+    seen = []
+    def spy(X):
+        v = cost_batched(X)
+        seen.append((np.array(X), v))
+        return v
+    xa, fa, ita, nea = sq.optimize.agents(spy, x, np.random.default_rng(5), agent_num=8, max_iter=120, tol=1e-8, agent_lifetime=30)
+    assert fa < 0.4 and abs(fa - port.cost(d, xa, U, n, 0)) < 1e-12 and nea == sum(calls) and ita == 120
+    # one batch of 2 x agent_num shifted sets per iteration (+ a census of agent_num every 30 iterations)
+    assert calls.count(16) == 120 and calls.count(8) >= 1 + 4
+    # iteration k's shifted batch starts from iteration k-1's updated agents: the cost at the un-shifted point, recovered from the
+    # next census, equals the prediction chain -- checked through the census right after iteration 30
+    census = [i for i, (X, v) in enumerate(seen) if len(X) == 8][2]
+    Xc, vc = seen[census]
+    Xs, vs = seen[census - 1]  # the shifted batch of the same iteration: rows 0..7 are +pi/2 of the state BEFORE the update
+    assert np.abs(vc - np.array([min(port.cost(d, Xs[a] + t * (Xs[8 + a] - Xs[a]) * 2 / np.pi, U, n, 0) for t in scan) for a in range(8)])).max() < 1e-4
+    assert (vc <= np.array([port.cost(d, 2 * Xs[a] - Xs[8 + a], U, n, 0) for a in range(8)]) + 1e-12).all()
 
 
 def test_constant_subcircuits_become_dense_kernels():

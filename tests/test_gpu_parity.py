@@ -1000,12 +1000,19 @@ def test_cosine_engine_on_the_device(sq, port):
     dec.set_Cost_Function_Variant(3)
     with pytest.raises(Exception, match="Not implemented"):
         dec._optimize_structure(np.random.default_rng(0))
+    # AGENTS over the same path (AGENTS.cpp:333-415): 32 walkers, one batch of 64 shifted parameter sets per iteration
+    dec = sq.N_Qubit_Decomposition_adaptive(Uct, level_limit_max=3, level_limit_min=3,
+                                            config={"optimization_tolerance": 1e-6, "max_inner_iterations_agent": 400, "agent_num": 32,
+                                                    "agent_lifetime": 50, "compress": 0, "finalize": 0})
+    dec.set_Optimizer("AGENTS")
+    err = dec.Start_Decomposition()
+    assert err < 0.5 and close_rel(dec.Optimization_Problem(dec.get_Optimized_Parameters()), err, 1e-9)
 
 
 def test_vqe_start_optimization(sq, port):
     """Variational_Quantum_Eigensolver.Start_Optimization over the device energy path (...Base.cpp:100-160; the reference's
-    tests/VQE/test_VQE.py:101-140 runs it with COSINE / BFGS): 6-qubit Heisenberg model, HEA_ZYZ ansatz. BFGS (every line search
-    one batched energy+gradient call) and COSINE (doubled period, COSINE.cpp:293-330) approach the exact ground energy from
+    tests/VQE/test_VQE.py:101-140 runs it with AGENTS / COSINE / BFGS): 6-qubit Heisenberg model, HEA_ZYZ ansatz. BFGS (every line search
+    one batched energy+gradient call), COSINE and AGENTS (doubled period, COSINE.cpp:293-330, AGENTS.cpp:417-470) approach the exact ground energy from
     above; both end points are re-evaluated by the oracle."""
     import scipy.sparse as sp
 
@@ -1014,7 +1021,8 @@ def test_vqe_start_optimization(sq, port):
     Hm = sp.csr_matrix((dat, ix, ip), shape=(1 << n, 1 << n))
     e_min = float(np.linalg.eigvalsh(Hm.toarray())[0])
     results = {}
-    for alg, cfg in (("BFGS", {"max_inner_iterations": 300}), ("COSINE", {"max_inner_iterations": 150, "batch_size": 16})):
+    for alg, cfg in (("BFGS", {"max_inner_iterations": 300}), ("COSINE", {"max_inner_iterations": 150, "batch_size": 16}),
+                     ("AGENTS", {"max_inner_iterations": 300, "agent_num": 16, "agent_lifetime": 50})):
         vqe = sq.Variational_Quantum_Eigensolver(Hm, n, config=dict(cfg, seed=4))
         vqe.set_Ansatz("HEA_ZYZ")
         vqe.Generate_Circuit(3, 1)
@@ -1032,9 +1040,9 @@ def test_vqe_start_optimization(sq, port):
         assert e_min - 1e-9 <= ef < e0 - 1.0
         results[alg] = ef
     # e_min < 0: both get within 30 % of the exact ground energy with a 3-layer ansatz (the oracle-driven runs end at 80 %)
-    assert results["BFGS"] < 0.7 * e_min and results["COSINE"] < 0.7 * e_min
+    assert max(results.values()) < 0.7 * e_min
     with pytest.raises(Exception):
-        vqe.set_Optimizer("AGENTS")
+        vqe.set_Optimizer("BAYES_OPT")
 
 
 @pytest.mark.parametrize("optimizer", ["BFGS", "ADAM"])
