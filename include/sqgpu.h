@@ -206,6 +206,9 @@ int sqgpu_plan_ops(const sqgpu_gate_desc* gates, int n_gates, int n_params, int 
  *                          2 also instead of the windowed executor (gradient n >= 13, cost n >= 14)
  *   const_fuse_qubits (0, 4, 5)  constant sub-circuits (gates without parameters) are multiplied out on the host into dense
  *                          kernels of up to this many qubits where that needs fewer flops than 3-qubit blocks (default 4; 0: off)
+ *   split_tables (0/1/2)   derivative kernel tables of fused blocks built by one warp per block member in a second kernel instead of
+ *                          one warp per block: 0 off, 1 (default) for batches <= 8 -- it shortens what a single evaluation of a
+ *                          BFGS line search waits for --, 2 always; the tables are bit-identical either way
  *   split, split_force, threads, ctas_per_sm   CTA-shape experiments of the launch planner
  *   verbose (0/1) */
 int sqgpu_set_option(sqgpu_handle_t h, const char* name, int64_t value);

@@ -1,6 +1,6 @@
 """N1: steps per second of a single ADAM trajectory, device-resident loop (sqgpu_adam_steps) vs the host-driven loop (cost+gradient
 through the host C-ABI call, Adam::update on the host), and the batched line search vs k separate evaluations.
-usage: python profiles/bench_optim.py  -> one JSON line per configuration"""
+usage: python profiles/bench_optim.py [--shift]  -> one JSON line per configuration (--shift: the COSINE / AGENTS engines)"""
 import json
 import os
 import sys
@@ -66,8 +66,48 @@ def run(name, U, circ, steps):
     print(json.dumps(out), flush=True)
 
 
+def run_shift_engines(name, U, circ, iters):
+    """COSINE / AGENTS iterations per second over the device's batched cost: the arrangement of optimize.cosine / optimize.agents
+    (two, resp. one, batched call per iteration) against the reference's call pattern for the same iteration (COSINE.cpp:255-523:
+    two batched calls of batch_size sets, then ~12 dependent single evaluations of the golden-section line search)."""
+    P = circ.get_Parameter_Num()
+    e = sq.Engine(0)
+    e.upload_matrix(U)
+    e.set_circuit(circ)
+    e.set_cost(0, 0)
+    x0 = H.random_params(P, seed=3)
+    out = {"config": name, "P": P, "iterations": iters}
+    bs = min(64, P)
+    sq.optimize.cosine(e.cost_batched, x0, np.random.default_rng(1), batch_size=bs, max_iter=2, tol=0)
+    t0 = time.perf_counter()
+    _, f, it, ne = sq.optimize.cosine(e.cost_batched, x0, np.random.default_rng(1), batch_size=bs, max_iter=iters, tol=0, check_for_convergence=False)
+    dt = time.perf_counter() - t0
+    out.update(cosine_iters_per_s=round(it / dt, 2), cosine_cost_evals_per_s=round(ne / dt, 1), cosine_final_cost=f)
+    # the reference's call pattern for one iteration on the same engine
+    X = np.repeat(x0.reshape(1, -1), bs, axis=0)
+    t0 = time.perf_counter()
+    for _ in range(max(2, iters // 4)):
+        e.cost_batched(X)
+        e.cost_batched(X)
+        for _ in range(12):
+            e.cost_batched(x0.reshape(1, -1))
+    out["cosine_reference_call_pattern_iters_per_s"] = round(max(2, iters // 4) / (time.perf_counter() - t0), 2)
+    t0 = time.perf_counter()
+    _, f, it, ne = sq.optimize.agents(e.cost_batched, x0, np.random.default_rng(1), agent_num=64, max_iter=iters, tol=0, agent_lifetime=max(10, iters // 4))
+    dt = time.perf_counter() - t0
+    out.update(agents_iters_per_s=round(it / dt, 2), agents_cost_evals_per_s=round(ne / dt, 1), agents_final_cost=f)
+    e.close()
+    print(json.dumps(out), flush=True)
+
+
 if __name__ == "__main__":
     import golden_cases as G
+
+    if "--shift" in sys.argv:
+        run_shift_engines("C1: n=4 Umtx.mat, adaptive L=3", G.load("C1_L3").U, H.adaptive_circuit(4, 3), 400)
+        run_shift_engines("n=8 adaptive L=2", np.ascontiguousarray(H.random_unitary(256, seed=123).conj().T), H.adaptive_circuit(8, 2), 200)
+        run_shift_engines("C3: n=10 adaptive L=4", np.ascontiguousarray(H.random_unitary(1024, seed=123).conj().T), H.adaptive_circuit(10, 4), 40)
+        sys.exit(0)
 
     run("C1: n=4 Umtx.mat, adaptive L=3", G.load("C1_L3").U, H.adaptive_circuit(4, 3), 2000)
     g = G.load("C2_19CNOT")
