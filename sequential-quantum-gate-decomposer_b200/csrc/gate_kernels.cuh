@@ -189,6 +189,24 @@ __device__ __forceinline__ void member_kernel(const DevMember& m, const Trig& t,
     build_gate_kernel(m.type, t, which, k);
 }
 
+// What fills a parameter's slot of the "derivative" tables. shift == 0: dK/dtheta_p. shift != 0 (sqgpu_cost_shifted_batched):
+// the finite difference K(theta_p + shift) - K(theta_p). The trace functional is linear in each op's kernel, so the adjoint sweep
+// and reduce_partials, unchanged, then return L(theta + shift e_p) - L(theta) for EVERY p from one sweep -- the shifted costs
+// the COSINE engine asks for (optimization_engines/COSINE.cpp:255-291) without one forward pass per parameter. The embedding
+// keeps the derivative convention (zero where a control bit is 0): identity - identity = 0 there.
+__device__ __forceinline__ void slot_kernel(int type, const Trig& t, int p, double theta_p, double shift, cplx* k) {
+    if (shift == 0.0) {
+        build_gate_kernel(type, t, p, k);
+        return;
+    }
+    Trig ts = t;
+    sincos(theta_p + shift, &ts.s[p], &ts.c[p]);
+    cplx k0[16];
+    const int dim = build_gate_kernel(type, ts, -1, k);
+    build_gate_kernel(type, t, -1, k0);
+    for (int i = 0; i < dim * dim; ++i) k[i] = cmake(k[i].x - k0[i].x, k[i].y - k0[i].y);
+}
+
 // out = a * b (dim x dim, row-major) by one warp; out must not alias a or b
 __device__ __forceinline__ void warp_mat_mul(const cplx* a, const cplx* b, cplx* out, int dim, int lane) {
     for (int i = lane; i < dim * dim; i += 32) {
@@ -208,7 +226,7 @@ __device__ __forceinline__ void warp_mat_mul(const cplx* a, const cplx* b, cplx*
 // ws: 3 * 64 complex of shared memory owned by the warp.
 __device__ inline void build_block_warp(const DevOp& op, const DevMember* __restrict__ members, const double* __restrict__ params,
                                         const cplx* __restrict__ pool, cplx* __restrict__ kdst, cplx* __restrict__ dkdst,
-                                        int with_deriv, cplx* ws, int lane) {
+                                        int with_deriv, cplx* ws, int lane, double shift = 0.0) {
     const int dim = op.dim, d2 = dim * dim, nm = op.n_members;
     cplx* R = ws;        // running prefix / suffix
     cplx* E = ws + 64;   // embedded member
@@ -243,7 +261,7 @@ __device__ inline void build_block_warp(const DevOp& op, const DevMember* __rest
         member_trig(m, params, t);
         for (int p = 0; p < m.n_params; ++p) {
             cplx* dd = dkdst + (size_t)(m.slot0 + p) * d2;  // holds the prefix E_{j-1}..E_0
-            member_kernel(m, t, p, pool, k);
+            slot_kernel(m.type, t, p, params[m.param_start + p], shift, k);  // (GENERAL members have no parameters)
             for (int i = lane; i < d2; i += 32) E[i] = embed_elem(m, k, true, i / dim, i % dim);
             __syncwarp();
             // T = dE * prefix (prefix read from global: written by this warp in pass 1)
@@ -281,7 +299,7 @@ __device__ inline void build_block_warp(const DevOp& op, const DevMember* __rest
 // One warp per member: the critical path of a table build drops from ~2 P_block + 2 nm small matrix products to ~nm + 2 per
 // parameter of one member -- it is what a single evaluation (BFGS) waits for before the executor starts.
 __device__ inline void block_member_derivs(const DevOp& op, const DevMember* __restrict__ members, const double* __restrict__ params,
-                                           const cplx* __restrict__ pool, cplx* __restrict__ dkdst, int j, cplx* ws, int lane) {
+                                           const cplx* __restrict__ pool, cplx* __restrict__ dkdst, int j, cplx* ws, int lane, double shift) {
     const int dim = op.dim, d2 = dim * dim, nm = op.n_members;
     cplx* R = ws;        // suffix E_{nm-1} .. E_{j+1}
     cplx* E = ws + 64;   // embedded member
@@ -306,7 +324,7 @@ __device__ inline void block_member_derivs(const DevOp& op, const DevMember* __r
     member_trig(m, params, t);
     for (int p = 0; p < m.n_params; ++p) {
         cplx* dd = dkdst + (size_t)(m.slot0 + p) * d2;  // holds the prefix E_{j-1}..E_0
-        member_kernel(m, t, p, pool, k);
+        slot_kernel(m.type, t, p, params[m.param_start + p], shift, k);
         for (int i = lane; i < d2; i += 32) E[i] = embed_elem(m, k, true, i / dim, i % dim);
         __syncwarp();
         // T = dE * prefix (prefix read from global: written by build_kernel_tables)
@@ -332,7 +350,7 @@ static const int DERIV_WARPS = 8;
 // one CTA per (parameter set, op), its warps deal the block's members
 __global__ void __launch_bounds__(DERIV_WARPS * 32) build_block_derivs(const DevOp* __restrict__ ops, int n_ops, const DevMember* __restrict__ members,
                                                                        const double* __restrict__ params, int n_params, const cplx* __restrict__ pool,
-                                                                       cplx* __restrict__ dktab, int dkern_total) {
+                                                                       cplx* __restrict__ dktab, int dkern_total, double shift) {
     __shared__ cplx ws[DERIV_WARPS][192];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.x / n_ops, kop = blockIdx.x - b * n_ops;
@@ -340,14 +358,14 @@ __global__ void __launch_bounds__(DERIV_WARPS * 32) build_block_derivs(const Dev
     if (op.type != SQ_OP_BLOCK || op.n_params == 0 || op.kern_off < 0) return;
     const double* __restrict__ pb = params + (size_t)b * n_params;
     cplx* dkdst = dktab + (size_t)b * dkern_total + op.dkern_off;
-    for (int j = warp; j < op.n_members; j += DERIV_WARPS) block_member_derivs(op, members, pb, pool, dkdst, j, ws[warp], lane);
+    for (int j = warp; j < op.n_members; j += DERIV_WARPS) block_member_derivs(op, members, pb, pool, dkdst, j, ws[warp], lane, shift);
 }
 
 static const int TABLE_WARPS = 4;
 __global__ void __launch_bounds__(TABLE_WARPS * 32) build_kernel_tables(
     const DevOp* __restrict__ ops, int n_ops, const DevMember* __restrict__ members, const double* __restrict__ params,
     int n_params, int batch, const cplx* __restrict__ pool, cplx* __restrict__ ktab, int kern_total,
-    cplx* __restrict__ dktab, int dkern_total, int with_deriv) {
+    cplx* __restrict__ dktab, int dkern_total, int with_deriv, double shift) {
     __shared__ cplx ws[TABLE_WARPS][192];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long idx = (long long)blockIdx.x * TABLE_WARPS + warp;
@@ -359,7 +377,7 @@ __global__ void __launch_bounds__(TABLE_WARPS * 32) build_kernel_tables(
     cplx* kdst = ktab + (size_t)b * kern_total + op.kern_off;
     cplx* dkdst = dktab + (size_t)b * dkern_total + (op.dkern_off >= 0 ? op.dkern_off : 0);
     if (op.type == SQ_OP_BLOCK) {
-        build_block_warp(op, members, pb, pool, kdst, dkdst, with_deriv, ws[warp], lane);
+        build_block_warp(op, members, pb, pool, kdst, dkdst, with_deriv, ws[warp], lane, shift);
         return;
     }
     if (lane != 0) return;
@@ -382,7 +400,7 @@ __global__ void __launch_bounds__(TABLE_WARPS * 32) build_kernel_tables(
     for (int i = 0; i < dim * dim; ++i) kdst[i] = k[src(i)];
     if (with_deriv) {
         for (int p = 0; p < op.n_params; ++p) {
-            build_gate_kernel(op.type, t, p, k);
+            slot_kernel(op.type, t, p, pb[op.param_start + p], shift, k);
             cplx* dd = dkdst + p * dim * dim;
             for (int i = 0; i < dim * dim; ++i) dd[i] = k[src(i)];
         }

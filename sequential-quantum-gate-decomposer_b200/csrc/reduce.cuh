@@ -139,6 +139,22 @@ __device__ __forceinline__ double grad_formula(const CostCfg& c, const double* t
     }
 }
 
+// cost at theta + shift e_p from the traces of theta and dl = L(theta + shift e_p) - L(theta) (sqgpu_cost_shifted_batched): the
+// Frobenius variants are affine in L, the |trace|^2 variants take the shifted complex trace
+__device__ __forceinline__ double shifted_formula(const CostCfg& c, const double* t, const double* dl, double n) {
+    switch (c.variant) {
+        case SQGPU_FROBENIUS_NORM:
+        case SQGPU_FROBENIUS_NORM_CORRECTION1:
+        case SQGPU_FROBENIUS_NORM_CORRECTION2: return cost_formula(c, t, n) - dl[0] / n;
+        case SQGPU_HILBERT_SCHMIDT_TEST:
+        case SQGPU_INFIDELITY: {
+            const double ts[6] = {t[0] + dl[0], t[1] + dl[1], 0, 0, 0, 0};
+            return cost_formula(c, ts, n);
+        }
+        default: return nan("");
+    }
+}
+
 __global__ void cost_from_traces(const double* __restrict__ traces, int n_params, int with_grad, int cols_total,
                                  CostCfg cfg, double* __restrict__ cost, double* __restrict__ grad) {
     const int y = blockIdx.x;
@@ -148,7 +164,8 @@ __global__ void cost_from_traces(const double* __restrict__ traces, int n_params
     if (threadIdx.x == 0 && cost) cost[y] = cost_formula(cfg, t, n);
     if (!with_grad || !grad) return;
     for (int p = threadIdx.x; p < n_params; p += blockDim.x)
-        grad[(size_t)y * n_params + p] = grad_formula(cfg, t, traces + tr_index(y, 1 + p, n_k, 0), n);
+        grad[(size_t)y * n_params + p] = with_grad == 2 ? shifted_formula(cfg, t, traces + tr_index(y, 1 + p, n_k, 0), n)
+                                                        : grad_formula(cfg, t, traces + tr_index(y, 1 + p, n_k, 0), n);
 }
 
 // omega[y][3]: weights of the trace types in L. Variant defaults need no data; the HS-with-corrections variants take

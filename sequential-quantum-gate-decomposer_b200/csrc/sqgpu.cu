@@ -248,6 +248,7 @@ struct sqgpu_ctx {
     DevBuf dPool;
     int n_params = 0, qbit_num = 0, n_gates = 0, n_const_fused = 0;
     bool all_unitary = true, circuit_set = false;
+    double table_shift = 0.0;  // != 0 while sqgpu_cost_shifted_batched runs: the derivative tables hold K(theta_p + shift) - K(theta_p)
     std::vector<cplx> pool;
 
     // cost configuration
@@ -1042,13 +1043,13 @@ int run_tables(sqgpu_ctx* c, const double* d_params, int batch, bool with_deriv,
     // one warp per (parameter set, op)
     build_kernel_tables<<<(unsigned)((total + TABLE_WARPS - 1) / TABLE_WARPS), TABLE_WARPS * 32, 0, st>>>(
         c->P->dOps.as<DevOp>(), c->P->n_ops, c->P->dMembers.as<DevMember>(), d_params, c->n_params, batch, c->dPool.as<cplx>(),
-        c->P->wKtab.as<cplx>(), c->P->kern_total, c->P->wDKtab.as<cplx>(), c->P->dkern_total, with_deriv ? (split ? 2 : 1) : 0);
+        c->P->wKtab.as<cplx>(), c->P->kern_total, c->P->wDKtab.as<cplx>(), c->P->dkern_total, with_deriv ? (split ? 2 : 1) : 0, c->table_shift);
     c->launches++;
     if (split) {
         // derivative kernels of the fused blocks: the prefixes are in place, one warp per member finishes them
         const long long ctas = (long long)batch * c->P->n_ops;
         build_block_derivs<<<(unsigned)ctas, DERIV_WARPS * 32, 0, st>>>(c->P->dOps.as<DevOp>(), c->P->n_ops, c->P->dMembers.as<DevMember>(), d_params,
-                                                                          c->n_params, c->dPool.as<cplx>(), c->P->wDKtab.as<cplx>(), c->P->dkern_total);
+                                                                          c->n_params, c->dPool.as<cplx>(), c->P->wDKtab.as<cplx>(), c->P->dkern_total, c->table_shift);
         c->launches++;
     }
     CUDA_TRY(cudaGetLastError());
@@ -1329,13 +1330,13 @@ int traces_dev(sqgpu_ctx* c, const double* d_params, int batch, bool with_grad, 
 }
 
 int cost_from_traces_dev(sqgpu_ctx* c, const double* d_traces, int batch, bool with_grad, int cols_total, double* d_cost,
-                         double* d_grad, cudaStream_t st) {
+                         double* d_grad, cudaStream_t st, bool shifted = false) {
     if (batch <= 0) return SQGPU_OK;
     if (!variant_supported(c->cfg.variant)) return fail(SQGPU_ERR_UNSUPPORTED, "cost function variant %d is not supported on the device path", c->cfg.variant);
     for (int b0 = 0; b0 < batch; b0 += 65535) {
         const int nb = std::min(65535, batch - b0);
         const int n_k = 1 + (with_grad ? c->n_params : 0);
-        cost_from_traces<<<nb, 128, 0, st>>>(d_traces + (size_t)b0 * n_k * 6, c->n_params, with_grad ? 1 : 0, cols_total, c->cfg,
+        cost_from_traces<<<nb, 128, 0, st>>>(d_traces + (size_t)b0 * n_k * 6, c->n_params, with_grad ? (shifted ? 2 : 1) : 0, cols_total, c->cfg,
                                              d_cost ? d_cost + b0 : nullptr, d_grad ? d_grad + (size_t)b0 * c->n_params : nullptr);
         c->launches++;
     }
@@ -1351,6 +1352,24 @@ int eval_dev(sqgpu_ctx* c, const double* d_params, int batch, bool with_grad, do
     if ((rc = c->wTraces.ensure(std::max<size_t>(1, (size_t)batch * n_k * 6) * sizeof(double)))) return rc;
     if ((rc = traces_dev(c, d_params, batch, with_grad, c->wTraces.as<double>(), st, true))) return rc;
     return cost_from_traces_dev(c, c->wTraces.as<double>(), batch, with_grad, c->cols, d_cost, d_grad, st);  // a single, unsharded handle
+}
+
+// cost at theta + shift e_p for every parameter p of every set, from ONE adjoint sweep per set (see slot_kernel, gate_kernels.cuh)
+int shifted_eval_dev(sqgpu_ctx* c, const double* d_params, int batch, double shift, double* d_cost0, double* d_shifted, cudaStream_t st) {
+    const int v = c->cfg.variant;
+    if (v != SQGPU_FROBENIUS_NORM && v != SQGPU_FROBENIUS_NORM_CORRECTION1 && v != SQGPU_FROBENIUS_NORM_CORRECTION2 &&
+        v != SQGPU_HILBERT_SCHMIDT_TEST && v != SQGPU_INFIDELITY)
+        return fail(SQGPU_ERR_UNSUPPORTED, "shifted costs from one sweep need a cost that is a function of one linear trace functional (variants 0, 1, 2, 3, 9), not variant %d", v);
+    if (shift == 0.0) return fail(SQGPU_ERR_INVALID, "shift must not be 0");
+    int rc = check_ready(c, true);
+    if (rc) return rc;
+    const int n_k = 1 + c->n_params;
+    if ((rc = c->wTraces.ensure(std::max<size_t>(1, (size_t)batch * n_k * 6) * sizeof(double)))) return rc;
+    c->table_shift = shift;
+    rc = traces_dev(c, d_params, batch, true, c->wTraces.as<double>(), st, true);
+    c->table_shift = 0.0;
+    if (rc) return rc;
+    return cost_from_traces_dev(c, c->wTraces.as<double>(), batch, true, c->cols, d_cost0, d_shifted, st, true);
 }
 
 // ---- apply paths -------------------------------------------------------------------------------------------------
@@ -2328,6 +2347,40 @@ int sqgpu_cost_grad_batched_dev(sqgpu_handle_t c, const double* d_params, int ba
     return eval_dev(c, d_params, batch, true, d_cost, d_grad, (cudaStream_t)stream);
 }
 
+int sqgpu_cost_shifted_batched_dev(sqgpu_handle_t c, const double* d_params, int batch, double shift, double* d_cost, double* d_shifted, void* stream) {
+    if (!c) return fail(SQGPU_ERR_INVALID, "NULL handle");
+    SQ_NOT_ON_MULTI(c);
+    if (batch < 0 || (batch > 0 && (!d_params && c->n_params > 0)) || (batch > 0 && (!d_cost || (!d_shifted && c->n_params > 0)))) return fail(SQGPU_ERR_INVALID, "bad arguments");
+    if (batch == 0) return SQGPU_OK;
+    DeviceGuard guard(c->device);
+    std::lock_guard<std::mutex> lk(c->mtx);
+    CallScope cs(c, (cudaStream_t)stream);
+    return shifted_eval_dev(c, d_params, batch, shift, d_cost, d_shifted, (cudaStream_t)stream);
+}
+
+int sqgpu_cost_shifted_batched(sqgpu_handle_t c, const double* params, int batch, double shift, double* cost, double* shifted) {
+    if (!c) return fail(SQGPU_ERR_INVALID, "NULL handle");
+    SQ_NOT_ON_MULTI(c);
+    if (batch < 0) return fail(SQGPU_ERR_INVALID, "negative batch");
+    if (batch == 0) return SQGPU_OK;
+    if ((!params && c->n_params > 0) || !cost || (!shifted && c->n_params > 0)) return fail(SQGPU_ERR_INVALID, "NULL buffer");
+    DeviceGuard guard(c->device);
+    std::lock_guard<std::mutex> lk(c->mtx);
+    CallScope cs(c, c->stream);
+    int rc = check_ready(c, true);
+    if (rc) return rc;
+    const size_t np = (size_t)batch * c->n_params;
+    if ((rc = c->wParams.ensure(std::max<size_t>(1, np) * sizeof(double)))) return rc;
+    if ((rc = c->wCost.ensure((size_t)batch * sizeof(double)))) return rc;
+    if ((rc = c->wGrad.ensure(std::max<size_t>(1, np) * sizeof(double)))) return rc;
+    if (np) CUDA_TRY(cudaMemcpyAsync(c->wParams.p, params, np * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if ((rc = shifted_eval_dev(c, c->wParams.as<double>(), batch, shift, c->wCost.as<double>(), c->wGrad.as<double>(), c->stream))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(cost, c->wCost.p, (size_t)batch * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (np) CUDA_TRY(cudaMemcpyAsync(shifted, c->wGrad.p, np * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return SQGPU_OK;
+}
+
 int sqgpu_traces_batched_dev(sqgpu_handle_t c, const double* d_params, int batch, int with_grad, double* d_traces, void* stream) {
     if (!c) return fail(SQGPU_ERR_INVALID, "NULL handle");
     SQ_NOT_ON_MULTI(c);
@@ -2540,7 +2593,7 @@ static int apply_gate_on_device(sqgpu_ctx* c, const sqgpu_gate_desc* gate, const
         CUDA_TRY(cudaMemcpyAsync(base, &op, sizeof(DevOp), cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(base + off_par, pbuf, sizeof(pbuf), cudaMemcpyHostToDevice, st));
         build_kernel_tables<<<1, 32, 0, st>>>(reinterpret_cast<DevOp*>(base), 1, nullptr, reinterpret_cast<double*>(base + off_par), 4, 1,
-                                              nullptr, reinterpret_cast<cplx*>(base + off_k), d2, reinterpret_cast<cplx*>(base + off_dk), 4 * d2, 1);
+                                              nullptr, reinterpret_cast<cplx*>(base + off_k), d2, reinterpret_cast<cplx*>(base + off_dk), 4 * d2, 1, 0.0);
         c->launches++;
         CUDA_TRY(cudaGetLastError());
         K = deriv_param >= 0 ? reinterpret_cast<cplx*>(base + off_dk) + (size_t)deriv_param * d2 : reinterpret_cast<cplx*>(base + off_k);

@@ -174,7 +174,8 @@ class N_Qubit_Decomposition_custom:
                 batch_size=min(P, int(cfg.get("batch_size_cosine", cfg.get("batch_size", min(64, P))))),
                 max_iter=int(cfg.get("max_inner_iterations_cosine", cfg.get("max_inner_iterations", 2000))),
                 tol=float(cfg.get("optimization_tolerance_cosine", tol)), double_period=False,
-                check_for_convergence=bool(cfg.get("check_for_convergence", cfg.get("check_for_convergence_cosine", 1))))
+                check_for_convergence=bool(cfg.get("check_for_convergence", cfg.get("check_for_convergence_cosine", 1))),
+                cost_shifted=eng.cost_shifted_batched if int(cfg.get("cosine_shift_sweep", 1)) else None)
             self._num_evaluations += ne
             return x, f
 

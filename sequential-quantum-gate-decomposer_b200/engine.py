@@ -126,6 +126,16 @@ class Engine:
                                                              abi.as_dp(grad)))
         return cost, grad
 
+    def cost_shifted_batched(self, params, shift):
+        """(cost[b], shifted[b, p] = cost(params_b + shift e_p) for EVERY parameter p) from one adjoint sweep per set
+        (sqgpu_cost_shifted_batched): the shift batches of the COSINE engine without one forward pass per shifted parameter"""
+        p = self._params(params)
+        cost = np.empty(p.shape[0], dtype=np.float64)
+        shifted = np.empty_like(p)
+        abi.check(self.lib, self.lib.sqgpu_cost_shifted_batched(self._h, abi.as_dp(p), p.shape[0], float(shift), abi.as_dp(cost),
+                                                                abi.as_dp(shifted)))
+        return cost, shifted
+
     def traces_batched(self, params, with_grad):
         p = self._params(params)
         k = 1 + (self.n_params if with_grad else 0)
@@ -208,6 +218,9 @@ class Engine:
 
     def cost_grad_batched_dev(self, d_params, batch, d_cost, d_grad, stream=0):
         abi.check(self.lib, self.lib.sqgpu_cost_grad_batched_dev(self._h, d_params, int(batch), d_cost, d_grad, stream))
+
+    def cost_shifted_batched_dev(self, d_params, batch, shift, d_cost, d_shifted, stream=0):
+        abi.check(self.lib, self.lib.sqgpu_cost_shifted_batched_dev(self._h, d_params, int(batch), float(shift), d_cost, d_shifted, stream))
 
     def traces_batched_dev(self, d_params, batch, with_grad, d_traces, stream=0):
         abi.check(self.lib, self.lib.sqgpu_traces_batched_dev(self._h, d_params, int(batch), int(bool(with_grad)),

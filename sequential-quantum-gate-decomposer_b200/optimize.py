@@ -115,7 +115,7 @@ def cosine_updates(f0, f_half, f_full, double_period=False):
 
 
 def cosine(cost_batched, x0, rng, batch_size=None, max_iter=2000, tol=1e-10, double_period=False, line_points=16,
-           check_for_convergence=True, callback=None):
+           check_for_convergence=True, callback=None, cost_shifted=None):
     """The reference's COSINE engine (optimization_engines/COSINE.cpp:60-657) over a batched cost: per iteration, ``batch_size``
     distinct random parameters are each moved to the minimum of the cost as a function of that parameter alone (a sinusoid,
     fixed by the current value and two shifted evaluations), and the joint move is scaled by a line search on [0, 1].
@@ -124,7 +124,11 @@ def cosine(cost_batched, x0, rng, batch_size=None, max_iter=2000, tol=1e-10, dou
     sets of an iteration are ONE cost_batched call (the reference issues two batched calls), and the line search is ONE
     batched call over ``line_points`` step fractions instead of ~12 dependent single evaluations of a golden-section search
     (COSINE.cpp:417-523; the reference keeps the batched grid variant commented out at :531-568) -- two device round trips per
-    iteration instead of fourteen. ``double_period``: the VQE flavour (shifts pi/4, pi/2). Returns (x, f, iterations, evals)."""
+    iteration instead of fourteen. ``double_period``: the VQE flavour (shifts pi/4, pi/2).
+
+    ``cost_shifted(X, shift) -> (cost[b], shifted[b, p])`` (Engine.cost_shifted_batched; decomposition costs only): the shifted
+    costs of ALL parameters come from one adjoint sweep per shift -- two sweeps (about six forward passes) replace the
+    2 x batch_size forward passes of the shift batch, whatever the batch size. Returns (x, f, iterations, evals)."""
     x = np.array(x0, dtype=np.float64).reshape(-1)
     P = x.size
     bs = min(64, P) if batch_size is None else int(batch_size)
@@ -141,15 +145,20 @@ def cosine(cost_batched, x0, rng, batch_size=None, max_iter=2000, tol=1e-10, dou
     it = 0
     for it in range(1, max_iter + 1):
         idx = rng.choice(P, size=bs, replace=False)
-        X = np.repeat(x.reshape(1, -1), 2 * bs, axis=0)
-        X[np.arange(bs), idx] += shift
-        X[bs + np.arange(bs), idx] += 2 * shift
-        vals = np.asarray(cost_batched(X))
-        upd = cosine_updates(f, vals[:bs], vals[bs:], double_period)
+        if cost_shifted is not None:
+            f_half = np.asarray(cost_shifted(x.reshape(1, -1), shift)[1])[0, idx]
+            f_full = np.asarray(cost_shifted(x.reshape(1, -1), 2 * shift)[1])[0, idx]
+        else:
+            X = np.repeat(x.reshape(1, -1), 2 * bs, axis=0)
+            X[np.arange(bs), idx] += shift
+            X[bs + np.arange(bs), idx] += 2 * shift
+            vals = np.asarray(cost_batched(X))
+            f_half, f_full = vals[:bs], vals[bs:]
+        upd = cosine_updates(f, f_half, f_full, double_period)
         L = np.repeat(x.reshape(1, -1), line_points, axis=0)
         L[:, idx] += fractions[:, None] * upd[None, :]
         lv = np.asarray(cost_batched(L))
-        n_eval += 2 * bs + line_points
+        n_eval += (2 if cost_shifted is not None else 2 * bs) + line_points
         k = int(np.argmin(lv))
         if lv[k] < f:
             x, f = L[k].copy(), float(lv[k])

@@ -966,6 +966,93 @@ def test_batched_line_search(sq, port):
     e.close()
 
 
+@pytest.mark.parametrize("opt", [{}, {"no_fuse": 1}, {"force_stream": 1}, {"split_tables": 0}])
+def test_shifted_costs_from_one_sweep(sq, port, opt):
+    """sqgpu_cost_shifted_batched: cost(theta + shift e_p) for EVERY parameter p from one adjoint sweep (the tables hold
+    K(theta_p + shift) - K(theta_p) in place of dK / dtheta_p; the trace functional is linear in each kernel) -- the shift batches
+    of COSINE.cpp:255-291. Against the explicit batch of shifted parameter sets on the device (1e-12) and against the oracle, for
+    every gate family (fused blocks, raw and controlled ops, CROT's two branches, two-target rotations), the cost variants that
+    are functions of one trace functional, with and without a trace offset; the others are refused."""
+    cases = [(5, H.random_circuit(5, 60, seed=17)), (4, H.adaptive_circuit(4, 2)), (6, H.random_circuit(6, 50, seed=3, general_k=(2, 3)))]
+    if opt.get("force_stream"):  # the streaming gradient has no 3-qubit / controlled two-target kernels
+        cases = [(5, H.random_circuit(5, 60, seed=17, names=H.ONE_Q + H.CTRL)), (4, H.adaptive_circuit(4, 2))]
+    for n, c in cases:
+        d, pool = c.descriptors()
+        P = c.get_Parameter_Num()
+        U = H.random_unitary(1 << n, seed=12).conj().T.copy()
+        theta = H.random_params(P, seed=31, batch=2)
+        e = sq.Engine(0, options=opt)
+        e.upload_matrix(U)
+        e.set_circuit(c)
+        for variant, off, shift in ((0, 0, np.pi / 2), (0, 0, np.pi), (3, 0, np.pi / 4), (9, 0, 0.3), (1, 0, -1.1), (2, 0, np.pi / 2)):
+            e.set_cost(variant, off, 0.4)
+            f0, fs = e.cost_shifted_batched(theta, shift)
+            assert close_rel(f0, e.cost_batched(theta))
+            for b in range(2):
+                X = np.repeat(theta[b:b + 1], P, axis=0)
+                X[np.arange(P), np.arange(P)] += shift
+                want = e.cost_batched(X)
+                assert np.abs(fs[b] - want).max() < 1e-12, (n, variant, shift, np.abs(fs[b] - want).max())
+            for p in (0, P // 2, P - 1):
+                x = theta[1].copy()
+                x[p] += shift
+                assert abs(fs[1][p] - port.cost(d, x, U, n, variant, off, 0.4, pool=pool)) < 1e-11
+        for variant in (4, 5, 6):
+            e.set_cost(variant, 0)
+            with pytest.raises(sq.abi.SqgpuError):
+                e.cost_shifted_batched(theta, 0.5)
+        e.set_cost(0, 0)
+        with pytest.raises(sq.abi.SqgpuError):
+            e.cost_shifted_batched(theta, 0.0)
+        e.close()
+    # rectangular U with a trace offset
+    n = 5
+    c = H.adaptive_circuit(n, 1)
+    P = c.get_Parameter_Num()
+    U = np.ascontiguousarray(H.random_unitary(1 << n, seed=2)[:, :8])
+    e = sq.Engine(0, options=opt)
+    e.upload_matrix(U)
+    e.set_circuit(c)
+    e.set_cost(0, 5)
+    x = H.random_params(P, seed=1)
+    _, fs = e.cost_shifted_batched(x, np.pi / 2)
+    X = np.repeat(x.reshape(1, -1), P, axis=0)
+    X[np.arange(P), np.arange(P)] += np.pi / 2
+    assert np.abs(fs[0] - e.cost_batched(X)).max() < 1e-12
+    e.close()
+
+
+@pytest.mark.parametrize("n,opt,cols", [(10, {}, 1024), (12, {}, 4), (13, {}, 3), (13, {"cluster": 2}, 3)])
+def test_shifted_costs_large_executors(sq, n, opt, cols):
+    """the same on the executors of the large cases: the bench's instantiation at n = 10 (full matrix), the cluster executor
+    (n = 12), the windowed executor and clusters of four (n = 13) on column slices; 24 sampled parameters against explicit
+    shifted evaluations, and the COSINE engine takes the same first steps with the sweep as with the explicit shift batch"""
+    c = H.adaptive_circuit(n, 1 if n > 10 else 2)
+    P = c.get_Parameter_Num()
+    rng = np.random.default_rng(5)
+    if cols == 1 << n:
+        U = np.ascontiguousarray(H.random_unitary(1 << n, seed=123).conj().T)
+    else:
+        U = np.ascontiguousarray((rng.standard_normal((1 << n, cols)) + 1j * rng.standard_normal((1 << n, cols))) / 50.0)
+    e = sq.Engine(0, options=opt)
+    e.upload_matrix(U)
+    e.set_circuit(c)
+    e.set_cost(0, 0)
+    x = H.random_params(P, seed=8)
+    idx = rng.choice(P, 24, replace=False)
+    for shift in (np.pi / 2, np.pi):
+        f0, fs = e.cost_shifted_batched(x, shift)
+        X = np.repeat(x.reshape(1, -1), 24, axis=0)
+        X[np.arange(24), idx] += shift
+        want = e.cost_batched(X)
+        assert np.abs(fs[0][idx] - want).max() < 1e-11 * max(1.0, np.abs(want).max()), np.abs(fs[0][idx] - want).max()
+    if n == 10:
+        a = sq.optimize.cosine(e.cost_batched, x, np.random.default_rng(2), batch_size=32, max_iter=3, tol=0)
+        b = sq.optimize.cosine(e.cost_batched, x, np.random.default_rng(2), batch_size=32, max_iter=3, tol=0, cost_shifted=e.cost_shifted_batched)
+        assert np.abs(a[0] - b[0]).max() < 1e-8 and close_rel(a[1], b[1], 1e-10) and b[3] < a[3]
+    e.close()
+
+
 def test_cosine_engine_on_the_device(sq, port):
     """N1, the COSINE shift batches (optimization_engines/COSINE.cpp:255-291 through optimization_problem_batched): the engine of
     optimize.cosine over the device's batched cost. Same trajectory as with the oracle as the cost callable for the first
