@@ -83,6 +83,19 @@ def run_shift_engines(name, U, circ, iters):
     _, f, it, ne = sq.optimize.cosine(e.cost_batched, x0, np.random.default_rng(1), batch_size=bs, max_iter=iters, tol=0, check_for_convergence=False)
     dt = time.perf_counter() - t0
     out.update(cosine_iters_per_s=round(it / dt, 2), cosine_cost_evals_per_s=round(ne / dt, 1), cosine_final_cost=f)
+    # the shift batch from two adjoint sweeps (sqgpu_cost_shifted_batched) instead of 2 x batch_size forward passes
+    sq.optimize.cosine(e.cost_batched, x0, np.random.default_rng(1), batch_size=bs, max_iter=2, tol=0, cost_shifted=e.cost_shifted_batched)
+    t0 = time.perf_counter()
+    _, f2, it, ne = sq.optimize.cosine(e.cost_batched, x0, np.random.default_rng(1), batch_size=bs, max_iter=iters, tol=0, check_for_convergence=False,
+                                       cost_shifted=e.cost_shifted_batched)
+    dt = time.perf_counter() - t0
+    out.update(cosine_sweep_iters_per_s=round(it / dt, 2), cosine_sweep_final_cost=f2, cosine_sweep_same_result=bool(abs(f2 - f) < 1e-9 * max(1, abs(f))))
+    # ... and with ALL parameters updated per iteration (batch_size = P costs the same two sweeps)
+    t0 = time.perf_counter()
+    _, f3, it, ne = sq.optimize.cosine(e.cost_batched, x0, np.random.default_rng(1), batch_size=P, max_iter=iters, tol=0, check_for_convergence=False,
+                                       cost_shifted=e.cost_shifted_batched)
+    dt = time.perf_counter() - t0
+    out.update(cosine_sweep_all_params_iters_per_s=round(it / dt, 2), cosine_sweep_all_params_final_cost=f3)
     # the reference's call pattern for one iteration on the same engine
     X = np.repeat(x0.reshape(1, -1), bs, axis=0)
     t0 = time.perf_counter()
