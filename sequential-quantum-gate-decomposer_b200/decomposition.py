@@ -96,10 +96,12 @@ class N_Qubit_Decomposition_custom:
     def set_Optimizer(self, optimizer="BFGS"):
         """"BFGS": L-BFGS with a device-batched line search; "ADAM": device-resident ADAM trajectories; "COSINE": the reference's
         parameter-shift engine with its shift batches and its line search as device batches (optimize.cosine); "AGENTS": the
-        reference's independent walkers, all their shifted parameter sets one device batch per iteration (optimize.agents). The
+        reference's independent walkers, all their shifted parameter sets one device batch per iteration (optimize.agents);
+        "GRAD_DESCEND": steepest descent with the batched line search (Grad_Descend, common/grad_descend.cpp:459-480: d = -g);
+        "AGENTS_COMBINED": AGENTS, then GRAD_DESCEND from its result (AGENTS.cpp:914-933). The
         reference's other engines (BAYES_OPT, BFGS2 ...) stay with the reference: they run over this cost path through integration/."""
-        if optimizer not in ("BFGS", "ADAM", "COSINE", "AGENTS"):
-            raise Exception("set_Optimizer: '%s' is not provided by this package (BFGS, ADAM, COSINE, AGENTS); use the reference's engines "
+        if optimizer not in ("BFGS", "ADAM", "COSINE", "AGENTS", "GRAD_DESCEND", "AGENTS_COMBINED"):
+            raise Exception("set_Optimizer: '%s' is not provided by this package (BFGS, ADAM, COSINE, AGENTS, GRAD_DESCEND, AGENTS_COMBINED); use the reference's engines "
                             "over the GPU cost path through the drop-in of integration/" % optimizer)
         self._optimizer = optimizer
 
@@ -150,14 +152,14 @@ class N_Qubit_Decomposition_custom:
             b = int(np.argmin(best_cost))
             return best_theta[b], float(best_cost[b])
 
-        if self._optimizer in ("COSINE", "AGENTS"):
+        if self._optimizer in ("COSINE", "AGENTS", "AGENTS_COMBINED"):
             # COSINE.cpp:226-228, 411-414 / AGENTS.cpp:333-335: the three-point rule is defined for the Frobenius cost (a sinusoid
             # of period 2 pi in every parameter); COSINE throws for the other variants, AGENTS' five-point Hilbert-Schmidt rule
             # is not provided here
             if self._variant != abi.FROBENIUS_NORM:
                 raise Exception("solve_layer_optimization_problem_%s: Not implemented method." % self._optimizer)
             cfg = self.config
-            if self._optimizer == "AGENTS":
+            if self._optimizer in ("AGENTS", "AGENTS_COMBINED"):
                 x, f, _, ne = optimize.agents(
                     eng.cost_batched, rng.random(P) * 2 * np.pi if x0 is None else x0, rng,
                     agent_num=int(cfg.get("agent_num_agent", cfg.get("agent_num", 64))),
@@ -168,6 +170,11 @@ class N_Qubit_Decomposition_custom:
                     agent_randomization_rate=float(cfg.get("agent_randomization_rate", 0.2)), radius=float(cfg.get("Randomized_Radius", 1.0)),
                     convergence_length=int(cfg.get("convergence_length_agent", cfg.get("convergence_length", 20))))
                 self._num_evaluations += ne
+                if self._optimizer == "AGENTS_COMBINED":  # AGENTS.cpp:914-933: gradient descent from the agents' result
+                    x, f, _, ne = optimize.lbfgs(lambda v: tuple(a[0] for a in eng.cost_grad_batched(v.reshape(1, -1))), eng.line_search_batched, x,
+                                                 max_iter=int(cfg.get("max_inner_iterations_grad_descend", cfg.get("max_inner_iterations", 2000))),
+                                                 tol=tol * 1e-2, history=0)
+                    self._num_evaluations += ne
                 return x, f
             x, f, _, ne = optimize.cosine(
                 eng.cost_batched, rng.random(P) * 2 * np.pi if x0 is None else x0, rng,
@@ -185,6 +192,12 @@ class N_Qubit_Decomposition_custom:
             f, g = eng.cost_grad_batched(x.reshape(1, -1))
             return float(f[0]), g[0]
 
+        if self._optimizer == "GRAD_DESCEND":  # GRAD_DESCEND.cpp:126-150: Grad_Descend from the guess
+            x, f, _, ne = optimize.lbfgs(cost_grad, eng.line_search_batched, rng.random(P) * 2 * np.pi if x0 is None else np.asarray(x0, dtype=np.float64),
+                                         max_iter=int(self.config.get("max_inner_iterations_grad_descend", self.config.get("max_inner_iterations", 2000))),
+                                         tol=tol * 1e-2, history=0)
+            self._num_evaluations += ne
+            return x, f
         if x0 is not None:
             x, f, _, ne = optimize.lbfgs(cost_grad, eng.line_search_batched, np.asarray(x0, dtype=np.float64),
                                          max_iter=int(self.config.get("max_inner_iterations_final", self.config.get("max_inner_iterations", 2000))), tol=tol * 1e-2)

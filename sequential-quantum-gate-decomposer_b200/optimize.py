@@ -18,7 +18,8 @@ def lbfgs(cost_grad, line_search, x0, max_iter=500, tol=1e-10, gtol=1e-9, histor
 
     Per iteration: two-loop recursion for the direction, ONE batched line-search call over a geometric ladder of step lengths,
     the best point that satisfies the Armijo condition (preferring one that also satisfies the curvature condition), then one
-    cost+gradient evaluation at the accepted point. Returns (x, f, n_iterations, n_evaluations)."""
+    cost+gradient evaluation at the accepted point. ``history = 0``: steepest descent with the same line search (the reference's
+    Grad_Descend, common/grad_descend.cpp:459-480). Returns (x, f, n_iterations, n_evaluations)."""
     x = np.array(x0, dtype=np.float64).reshape(-1)
     if alphas is None:
         alphas = np.array([2.0 ** k for k in range(3, -14, -1)])  # 8, 4, 2, 1, 1/2, ... 2^-13

@@ -169,8 +169,8 @@ class Variational_Quantum_Eigensolver:
 
     # ---- optimisation over the hot path --------------------------------------------------------------
     def set_Optimizer(self, alg="COSINE"):
-        if alg not in ("COSINE", "AGENTS", "BFGS"):
-            raise Exception("set_Optimizer: '%s' is not provided by this package (COSINE, AGENTS, BFGS); use the reference's "
+        if alg not in ("COSINE", "AGENTS", "BFGS", "GRAD_DESCEND", "AGENTS_COMBINED"):
+            raise Exception("set_Optimizer: '%s' is not provided by this package (COSINE, AGENTS, BFGS, GRAD_DESCEND, AGENTS_COMBINED); use the reference's "
                             "engines over the GPU energy path through the drop-in of integration/" % alg)
         self._optimizer = alg
 
@@ -206,13 +206,20 @@ class Variational_Quantum_Eigensolver:
             e, g = eng.vqe_energy_grad_batched(x.reshape(1, -1))
             return float(e[0]), g[0]
 
+        ne = 0
         if alg == "COSINE":
             # COSINE.cpp:226-228: cost_fnc == VQE selects the three-point rule with the doubled period (shifts pi/4, pi/2)
             x, f, it, ne = optimize.cosine(eng.vqe_energy_batched, x0, rng,
                                            batch_size=min(P, int(cfg.get("batch_size_cosine", cfg.get("batch_size", min(64, P))))),
                                            max_iter=int(cfg.get("max_inner_iterations_cosine", max_iter)), tol=-np.inf, double_period=True,
                                            check_for_convergence=bool(cfg.get("check_for_convergence", 1)))
-        elif alg == "AGENTS":
+
+        def line_search(x, d, alphas):  # all trial step lengths of an iteration: one batched energy+gradient call
+            e, g = eng.vqe_energy_grad_batched(x[None, :] + np.asarray(alphas)[:, None] * d[None, :])
+            return e, g @ d
+
+        gtol = float(cfg.get("gradient_tolerance", 1e-8))
+        if alg in ("AGENTS", "AGENTS_COMBINED"):
             # AGENTS.cpp:334: cost_fnc == VQE with linesearch_points == 3 (the default) is the doubled-period three-point rule;
             # randomize_parameters does not scale the radius by the cost for the VQE (Optimization_Interface.cpp:596)
             x, f, it, ne = optimize.agents(eng.vqe_energy_batched, x0, rng, agent_num=int(cfg.get("agent_num_agent", cfg.get("agent_num", 64))),
@@ -222,12 +229,12 @@ class Variational_Quantum_Eigensolver:
                                            agent_randomization_rate=float(cfg.get("agent_randomization_rate", 0.2)),
                                            radius=float(cfg.get("Randomized_Radius", 1.0)),
                                            convergence_length=int(cfg.get("convergence_length_agent", cfg.get("convergence_length", 20))), scale_by_cost=False)
-        else:
-            def line_search(x, d, alphas):  # all trial step lengths of an iteration: one batched energy+gradient call
-                e, g = eng.vqe_energy_grad_batched(x[None, :] + np.asarray(alphas)[:, None] * d[None, :])
-                return e, g @ d
-
-            x, f, it, ne = optimize.lbfgs(energy_grad, line_search, x0, max_iter=max_iter, tol=-np.inf, gtol=float(cfg.get("gradient_tolerance", 1e-8)))
+            x0 = x
+        if alg in ("BFGS", "GRAD_DESCEND", "AGENTS_COMBINED"):
+            # GRAD_DESCEND / the second stage of AGENTS_COMBINED (AGENTS.cpp:914-933): steepest descent, same batched line search
+            x, f, it, ne2 = optimize.lbfgs(energy_grad, line_search, x0, max_iter=int(cfg.get("max_inner_iterations_grad_descend", max_iter)) if alg != "BFGS" else max_iter,
+                                           tol=-np.inf, gtol=gtol, **({} if alg == "BFGS" else {"history": 0}))
+            ne += ne2
         self._optimized_parameters = np.asarray(x, dtype=np.float64).copy()
         self._num_evaluations = getattr(self, "_num_evaluations", 0) + ne
         self._current_minimum = float(f)

@@ -297,8 +297,8 @@ def test_lbfgs_host_loop_with_oracle_callables(port):
     dec = sq.N_Qubit_Decomposition_adaptive(U, level_limit_max=3, level_limit_min=1)
     with pytest.raises(Exception):
         dec.set_Optimizer("BAYES_OPT")
-    dec.set_Optimizer("COSINE")
-    dec.set_Optimizer("AGENTS")
+    for name in ("COSINE", "AGENTS", "AGENTS_COMBINED", "GRAD_DESCEND", "ADAM", "BFGS"):
+        dec.set_Optimizer(name)
     with pytest.raises(Exception):
         dec.get_Optimized_Parameters()
 

@@ -1094,6 +1094,14 @@ def test_cosine_engine_on_the_device(sq, port):
     dec.set_Optimizer("AGENTS")
     err = dec.Start_Decomposition()
     assert err < 0.5 and close_rel(dec.Optimization_Problem(dec.get_Optimized_Parameters()), err, 1e-9)
+    # AGENTS_COMBINED (AGENTS.cpp:914-933): the agents' result polished by steepest descent with the batched line search
+    dec.config["max_inner_iterations_grad_descend"] = 200
+    dec.set_Optimizer("AGENTS_COMBINED")
+    err2 = dec.Start_Decomposition()
+    assert err2 <= err and close_rel(dec.Optimization_Problem(dec.get_Optimized_Parameters()), err2, 1e-9)
+    dec.set_Optimizer("GRAD_DESCEND")
+    err3 = dec.Start_Decomposition()
+    assert err3 < 0.5 and close_rel(dec.Optimization_Problem(dec.get_Optimized_Parameters()), err3, 1e-9)
 
 
 def test_vqe_start_optimization(sq, port):
@@ -1109,7 +1117,9 @@ def test_vqe_start_optimization(sq, port):
     e_min = float(np.linalg.eigvalsh(Hm.toarray())[0])
     results = {}
     for alg, cfg in (("BFGS", {"max_inner_iterations": 300}), ("COSINE", {"max_inner_iterations": 150, "batch_size": 16}),
-                     ("AGENTS", {"max_inner_iterations": 300, "agent_num": 16, "agent_lifetime": 50})):
+                     ("AGENTS", {"max_inner_iterations": 300, "agent_num": 16, "agent_lifetime": 50}),
+                     ("GRAD_DESCEND", {"max_inner_iterations": 300}),
+                     ("AGENTS_COMBINED", {"max_inner_iterations_agent": 100, "max_inner_iterations_grad_descend": 100, "agent_num": 16, "agent_lifetime": 50})):
         vqe = sq.Variational_Quantum_Eigensolver(Hm, n, config=dict(cfg, seed=4))
         vqe.set_Ansatz("HEA_ZYZ")
         vqe.Generate_Circuit(3, 1)
