@@ -324,14 +324,17 @@ int sqgpu_adam_get(sqgpu_handle_t h, double* theta, double* best_cost, double* b
 
 /* replaces the shift batches of the parameter-shift engines -- COSINE evaluates optimization_problem_batched on batch_size copies
  * of theta with ONE parameter each moved by pi/2, then by pi (optimization_engines/COSINE.cpp:255-291; GRAD_DESCEND_PARAMETER_
- * SHIFT_RULE.cpp likewise): shifted[b][p] = cost(params_b + shift e_p) for EVERY parameter p, cost[b] = cost(params_b), from one
- * adjoint sweep per parameter set (about three forward passes) instead of one forward pass per shifted parameter. The trace
- * functional is linear in each gate's kernel, so the sweep of sqgpu_cost_grad_batched run on K(theta_p + shift) - K(theta_p) in
- * place of dK/dtheta_p returns the exact change of the trace. Cost variants 0, 1, 2, 3, 9 (functions of one linear trace
- * functional); the others return SQGPU_ERR_UNSUPPORTED. shift != 0. Single-device handles. */
-int sqgpu_cost_shifted_batched(sqgpu_handle_t h, const double* params, int batch, double shift, double* cost, double* shifted);
-int sqgpu_cost_shifted_batched_dev(sqgpu_handle_t h, const double* d_params, int batch, double shift, double* d_cost, double* d_shifted,
-                                   void* stream);
+ * SHIFT_RULE.cpp likewise): shifted[s][b][p] = cost(params_b + shifts[s] e_p) for EVERY parameter p, cost[b] = cost(params_b),
+ * from one adjoint sweep per parameter set (about three forward passes) instead of one forward pass per shifted parameter. The
+ * trace functional is linear in each gate's kernel, so the sweep of sqgpu_cost_grad_batched run on K(theta_p + shift) - K(theta_p)
+ * in place of dK/dtheta_p returns the exact change of the trace; the sweep itself does not depend on the shift, so further shifts
+ * cost a table build and a reduction only. Cost variants 0, 1, 2, 3, 9 (functions of one linear trace functional); the others
+ * return SQGPU_ERR_UNSUPPORTED. shifts: n_shifts >= 1 host values != 0. Single-device handles. */
+int sqgpu_cost_shifted_batched(sqgpu_handle_t h, const double* params, int batch, const double* shifts, int n_shifts, double* cost,
+                               double* shifted);
+/* device buffers d_params / d_cost / d_shifted, `shifts` stays a host array */
+int sqgpu_cost_shifted_batched_dev(sqgpu_handle_t h, const double* d_params, int batch, const double* shifts, int n_shifts, double* d_cost,
+                                   double* d_shifted, void* stream);
 
 /* replaces the one-evaluation-per-trial-point line search of BFGS_Powell (common/BFGS_Powell.cpp:70-200) by ONE batch: the k
  * points x + alphas[j] * dir are formed on the device, cost[j] = f(x + alphas[j] dir) and, if dphi != NULL, the directional

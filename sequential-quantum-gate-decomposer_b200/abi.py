@@ -183,8 +183,8 @@ PROTOTYPES = {
     "sqgpu_adam_steps": (C.c_int, [_handle, C.c_int, _dp]),
     "sqgpu_adam_get": (C.c_int, [_handle, _dp, _dp, _dp, C.POINTER(C.c_int)]),
     "sqgpu_line_search_batched": (C.c_int, [_handle, _dp, _dp, _dp, C.c_int, _dp, _dp]),
-    "sqgpu_cost_shifted_batched": (C.c_int, [_handle, _dp, C.c_int, C.c_double, _dp, _dp]),
-    "sqgpu_cost_shifted_batched_dev": (C.c_int, [_handle, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sqgpu_cost_shifted_batched": (C.c_int, [_handle, _dp, C.c_int, _dp, C.c_int, _dp, _dp]),
+    "sqgpu_cost_shifted_batched_dev": (C.c_int, [_handle, C.c_void_p, C.c_int, _dp, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sqgpu_launch_count": (C.c_int, [_handle, C.POINTER(C.c_int64)]),
     "sqgpu_last_kernel_time": (C.c_int, [_handle, C.c_char_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "sqgpu_fp64_fma_peak": (C.c_int, [_handle, C.POINTER(C.c_double)]),

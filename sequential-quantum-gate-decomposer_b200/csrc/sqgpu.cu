@@ -249,6 +249,9 @@ struct sqgpu_ctx {
     int n_params = 0, qbit_num = 0, n_gates = 0, n_const_fused = 0;
     bool all_unitary = true, circuit_set = false;
     double table_shift = 0.0;  // != 0 while sqgpu_cost_shifted_batched runs: the derivative tables hold K(theta_p + shift) - K(theta_p)
+    // geometry of the last gradient reduction of the resident fused executor: its W' partials stay valid, so another shift of
+    // the same parameter sets needs new tables and a second reduce_partials only, not a second sweep
+    struct { bool valid = false; int batch = 0, chunks = 0, w_slices = 0; const void* plan = nullptr; } replay;
     std::vector<cplx> pool;
 
     // cost configuration
@@ -1184,6 +1187,11 @@ int run_exec_resident(sqgpu_ctx* c, int batch, bool grad, const cplx* d_omega, d
                                            p.w_slices);
     c->launches++;
     CUDA_TRY(cudaGetLastError());
+    c->replay.valid = grad;
+    c->replay.batch = batch;
+    c->replay.chunks = p.chunks;
+    c->replay.w_slices = p.w_slices;
+    c->replay.plan = c->P;
     return SQGPU_OK;
 }
 
@@ -1354,22 +1362,44 @@ int eval_dev(sqgpu_ctx* c, const double* d_params, int batch, bool with_grad, do
     return cost_from_traces_dev(c, c->wTraces.as<double>(), batch, with_grad, c->cols, d_cost, d_grad, st);  // a single, unsharded handle
 }
 
-// cost at theta + shift e_p for every parameter p of every set, from ONE adjoint sweep per set (see slot_kernel, gate_kernels.cuh)
-int shifted_eval_dev(sqgpu_ctx* c, const double* d_params, int batch, double shift, double* d_cost0, double* d_shifted, cudaStream_t st) {
+// cost at theta + shifts[s] e_p for every parameter p of every set, from ONE adjoint sweep per set (see slot_kernel, gate_kernels.cuh).
+// The sweep does not depend on the shift: further shifts re-build the tables and repeat reduce_partials on the W' partials of
+// the first one (resident fused executor, batch in one slice; otherwise one sweep per shift).
+int shifted_eval_dev(sqgpu_ctx* c, const double* d_params, int batch, const double* shifts, int n_shifts, double* d_cost0, double* d_shifted,
+                     cudaStream_t st) {
     const int v = c->cfg.variant;
     if (v != SQGPU_FROBENIUS_NORM && v != SQGPU_FROBENIUS_NORM_CORRECTION1 && v != SQGPU_FROBENIUS_NORM_CORRECTION2 &&
         v != SQGPU_HILBERT_SCHMIDT_TEST && v != SQGPU_INFIDELITY)
         return fail(SQGPU_ERR_UNSUPPORTED, "shifted costs from one sweep need a cost that is a function of one linear trace functional (variants 0, 1, 2, 3, 9), not variant %d", v);
-    if (shift == 0.0) return fail(SQGPU_ERR_INVALID, "shift must not be 0");
+    for (int s = 0; s < n_shifts; ++s)
+        if (shifts[s] == 0.0) return fail(SQGPU_ERR_INVALID, "shift must not be 0");
     int rc = check_ready(c, true);
     if (rc) return rc;
     const int n_k = 1 + c->n_params;
     if ((rc = c->wTraces.ensure(std::max<size_t>(1, (size_t)batch * n_k * 6) * sizeof(double)))) return rc;
-    c->table_shift = shift;
-    rc = traces_dev(c, d_params, batch, true, c->wTraces.as<double>(), st, true);
+    c->replay.valid = false;
+    for (int s = 0; s < n_shifts && !rc; ++s) {
+        c->table_shift = shifts[s];
+        if (s > 0 && c->replay.valid && c->replay.batch == batch && c->replay.plan == c->P && batch_slice(c, batch, true) >= batch) {
+            if (!(rc = run_tables(c, d_params, batch, true, st))) {
+                reduce_partials<<<dim3(batch, reduce_grid_y(c->n_params)), 128, 0, st>>>(
+                    c->wTrPart.as<double>(), c->replay.chunks, c->wWPart.as<cplx>(), c->P->w_total, c->P->dOps.as<DevOp>(), c->P->dParamOp.as<int>(),
+                    c->P->dParamOp.as<int>() + std::max(c->n_params, 1), c->P->wDKtab.as<cplx>(), c->P->dkern_total, c->P->wKtab.as<cplx>(),
+                    c->P->kern_total, c->n_params, 1, c->wTraces.as<double>(), 1, c->replay.w_slices);
+                c->launches++;
+                if (cudaGetLastError() != cudaSuccess) rc = fail(SQGPU_ERR_CUDA, "reduce_partials launch failed");
+            }
+        } else {
+            c->replay.valid = false;
+            rc = traces_dev(c, d_params, batch, true, c->wTraces.as<double>(), st, true);
+            if (batch_slice(c, batch, true) < batch) c->replay.valid = false;  // the partials hold the last slice only
+        }
+        c->table_shift = 0.0;
+        if (!rc) rc = cost_from_traces_dev(c, c->wTraces.as<double>(), batch, true, c->cols, d_cost0, d_shifted + (size_t)s * batch * c->n_params, st, true);
+    }
     c->table_shift = 0.0;
-    if (rc) return rc;
-    return cost_from_traces_dev(c, c->wTraces.as<double>(), batch, true, c->cols, d_cost0, d_shifted, st, true);
+    c->replay.valid = false;
+    return rc;
 }
 
 // ---- apply paths -------------------------------------------------------------------------------------------------
@@ -2347,21 +2377,22 @@ int sqgpu_cost_grad_batched_dev(sqgpu_handle_t c, const double* d_params, int ba
     return eval_dev(c, d_params, batch, true, d_cost, d_grad, (cudaStream_t)stream);
 }
 
-int sqgpu_cost_shifted_batched_dev(sqgpu_handle_t c, const double* d_params, int batch, double shift, double* d_cost, double* d_shifted, void* stream) {
+int sqgpu_cost_shifted_batched_dev(sqgpu_handle_t c, const double* d_params, int batch, const double* shifts, int n_shifts, double* d_cost, double* d_shifted,
+                                   void* stream) {
     if (!c) return fail(SQGPU_ERR_INVALID, "NULL handle");
     SQ_NOT_ON_MULTI(c);
-    if (batch < 0 || (batch > 0 && (!d_params && c->n_params > 0)) || (batch > 0 && (!d_cost || (!d_shifted && c->n_params > 0)))) return fail(SQGPU_ERR_INVALID, "bad arguments");
+    if (batch < 0 || n_shifts < 1 || !shifts || (batch > 0 && (!d_params && c->n_params > 0)) || (batch > 0 && (!d_cost || (!d_shifted && c->n_params > 0)))) return fail(SQGPU_ERR_INVALID, "bad arguments");
     if (batch == 0) return SQGPU_OK;
     DeviceGuard guard(c->device);
     std::lock_guard<std::mutex> lk(c->mtx);
     CallScope cs(c, (cudaStream_t)stream);
-    return shifted_eval_dev(c, d_params, batch, shift, d_cost, d_shifted, (cudaStream_t)stream);
+    return shifted_eval_dev(c, d_params, batch, shifts, n_shifts, d_cost, d_shifted, (cudaStream_t)stream);
 }
 
-int sqgpu_cost_shifted_batched(sqgpu_handle_t c, const double* params, int batch, double shift, double* cost, double* shifted) {
+int sqgpu_cost_shifted_batched(sqgpu_handle_t c, const double* params, int batch, const double* shifts, int n_shifts, double* cost, double* shifted) {
     if (!c) return fail(SQGPU_ERR_INVALID, "NULL handle");
     SQ_NOT_ON_MULTI(c);
-    if (batch < 0) return fail(SQGPU_ERR_INVALID, "negative batch");
+    if (batch < 0 || n_shifts < 1 || !shifts) return fail(SQGPU_ERR_INVALID, "negative batch or no shifts");
     if (batch == 0) return SQGPU_OK;
     if ((!params && c->n_params > 0) || !cost || (!shifted && c->n_params > 0)) return fail(SQGPU_ERR_INVALID, "NULL buffer");
     DeviceGuard guard(c->device);
@@ -2372,11 +2403,11 @@ int sqgpu_cost_shifted_batched(sqgpu_handle_t c, const double* params, int batch
     const size_t np = (size_t)batch * c->n_params;
     if ((rc = c->wParams.ensure(std::max<size_t>(1, np) * sizeof(double)))) return rc;
     if ((rc = c->wCost.ensure((size_t)batch * sizeof(double)))) return rc;
-    if ((rc = c->wGrad.ensure(std::max<size_t>(1, np) * sizeof(double)))) return rc;
+    if ((rc = c->wGrad.ensure(std::max<size_t>(1, np * n_shifts) * sizeof(double)))) return rc;
     if (np) CUDA_TRY(cudaMemcpyAsync(c->wParams.p, params, np * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    if ((rc = shifted_eval_dev(c, c->wParams.as<double>(), batch, shift, c->wCost.as<double>(), c->wGrad.as<double>(), c->stream))) return rc;
+    if ((rc = shifted_eval_dev(c, c->wParams.as<double>(), batch, shifts, n_shifts, c->wCost.as<double>(), c->wGrad.as<double>(), c->stream))) return rc;
     CUDA_TRY(cudaMemcpyAsync(cost, c->wCost.p, (size_t)batch * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    if (np) CUDA_TRY(cudaMemcpyAsync(shifted, c->wGrad.p, np * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (np) CUDA_TRY(cudaMemcpyAsync(shifted, c->wGrad.p, np * n_shifts * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return SQGPU_OK;
 }

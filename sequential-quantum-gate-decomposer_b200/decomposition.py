@@ -182,8 +182,8 @@ class N_Qubit_Decomposition_custom:
                 max_iter=int(cfg.get("max_inner_iterations_cosine", cfg.get("max_inner_iterations", 2000))),
                 tol=float(cfg.get("optimization_tolerance_cosine", tol)), double_period=False,
                 check_for_convergence=bool(cfg.get("check_for_convergence", cfg.get("check_for_convergence_cosine", 1))),
-                # the shift batch from two adjoint sweeps instead of 2 x batch_size forward passes (sqgpu_cost_shifted_batched):
-                # measured 5.0x at n = 10, 1.5x at n = 8, 0.5x at n = 4 (profiles/r2_shift_engines.jsonl) -- from 7 qubits on
+                # the shift batch from one adjoint sweep instead of 2 x batch_size forward passes (sqgpu_cost_shifted_batched):
+                # measured 6.1x at n = 10, 1.9x at n = 8, 0.6x at n = 4 (profiles/r2_shift_engines.jsonl) -- from 7 qubits on
                 cost_shifted=eng.cost_shifted_batched if int(cfg.get("cosine_shift_sweep", self.qbit_num >= 7)) else None)
             self._num_evaluations += ne
             return x, f

@@ -128,13 +128,16 @@ class Engine:
 
     def cost_shifted_batched(self, params, shift):
         """(cost[b], shifted[b, p] = cost(params_b + shift e_p) for EVERY parameter p) from one adjoint sweep per set
-        (sqgpu_cost_shifted_batched): the shift batches of the COSINE engine without one forward pass per shifted parameter"""
+        (sqgpu_cost_shifted_batched): the shift batches of the COSINE engine without one forward pass per shifted parameter.
+        ``shift``: a number, or a sequence of shifts -> shifted[s, b, p] (one sweep serves them all)"""
         p = self._params(params)
+        scalar = np.ndim(shift) == 0
+        sh = _f64(np.atleast_1d(shift)).reshape(-1)
         cost = np.empty(p.shape[0], dtype=np.float64)
-        shifted = np.empty_like(p)
-        abi.check(self.lib, self.lib.sqgpu_cost_shifted_batched(self._h, abi.as_dp(p), p.shape[0], float(shift), abi.as_dp(cost),
+        shifted = np.empty((sh.size,) + p.shape, dtype=np.float64)
+        abi.check(self.lib, self.lib.sqgpu_cost_shifted_batched(self._h, abi.as_dp(p), p.shape[0], abi.as_dp(sh), sh.size, abi.as_dp(cost),
                                                                 abi.as_dp(shifted)))
-        return cost, shifted
+        return cost, (shifted[0] if scalar else shifted)
 
     def traces_batched(self, params, with_grad):
         p = self._params(params)
@@ -219,8 +222,9 @@ class Engine:
     def cost_grad_batched_dev(self, d_params, batch, d_cost, d_grad, stream=0):
         abi.check(self.lib, self.lib.sqgpu_cost_grad_batched_dev(self._h, d_params, int(batch), d_cost, d_grad, stream))
 
-    def cost_shifted_batched_dev(self, d_params, batch, shift, d_cost, d_shifted, stream=0):
-        abi.check(self.lib, self.lib.sqgpu_cost_shifted_batched_dev(self._h, d_params, int(batch), float(shift), d_cost, d_shifted, stream))
+    def cost_shifted_batched_dev(self, d_params, batch, shifts, d_cost, d_shifted, stream=0):
+        sh = _f64(np.atleast_1d(shifts)).reshape(-1)
+        abi.check(self.lib, self.lib.sqgpu_cost_shifted_batched_dev(self._h, d_params, int(batch), abi.as_dp(sh), sh.size, d_cost, d_shifted, stream))
 
     def traces_batched_dev(self, d_params, batch, with_grad, d_traces, stream=0):
         abi.check(self.lib, self.lib.sqgpu_traces_batched_dev(self._h, d_params, int(batch), int(bool(with_grad)),

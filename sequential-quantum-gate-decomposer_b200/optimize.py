@@ -127,8 +127,8 @@ def cosine(cost_batched, x0, rng, batch_size=None, max_iter=2000, tol=1e-10, dou
     (COSINE.cpp:417-523; the reference keeps the batched grid variant commented out at :531-568) -- two device round trips per
     iteration instead of fourteen. ``double_period``: the VQE flavour (shifts pi/4, pi/2).
 
-    ``cost_shifted(X, shift) -> (cost[b], shifted[b, p])`` (Engine.cost_shifted_batched; decomposition costs only): the shifted
-    costs of ALL parameters come from one adjoint sweep per shift -- two sweeps (about six forward passes) replace the
+    ``cost_shifted(X, shifts) -> (cost[b], shifted[s, b, p])`` (Engine.cost_shifted_batched; decomposition costs only): the
+    shifted costs of ALL parameters for both shifts come from one adjoint sweep (about three forward passes) -- it replaces the
     2 x batch_size forward passes of the shift batch, whatever the batch size. Returns (x, f, iterations, evals)."""
     x = np.array(x0, dtype=np.float64).reshape(-1)
     P = x.size
@@ -147,8 +147,8 @@ def cosine(cost_batched, x0, rng, batch_size=None, max_iter=2000, tol=1e-10, dou
     for it in range(1, max_iter + 1):
         idx = rng.choice(P, size=bs, replace=False)
         if cost_shifted is not None:
-            f_half = np.asarray(cost_shifted(x.reshape(1, -1), shift)[1])[0, idx]
-            f_full = np.asarray(cost_shifted(x.reshape(1, -1), 2 * shift)[1])[0, idx]
+            both = np.asarray(cost_shifted(x.reshape(1, -1), (shift, 2 * shift))[1])  # [2][1][P]: one sweep serves both shifts
+            f_half, f_full = both[0, 0, idx], both[1, 0, idx]
         else:
             X = np.repeat(x.reshape(1, -1), 2 * bs, axis=0)
             X[np.arange(bs), idx] += shift
@@ -159,7 +159,7 @@ def cosine(cost_batched, x0, rng, batch_size=None, max_iter=2000, tol=1e-10, dou
         L = np.repeat(x.reshape(1, -1), line_points, axis=0)
         L[:, idx] += fractions[:, None] * upd[None, :]
         lv = np.asarray(cost_batched(L))
-        n_eval += (2 if cost_shifted is not None else 2 * bs) + line_points
+        n_eval += (1 if cost_shifted is not None else 2 * bs) + line_points
         k = int(np.argmin(lv))
         if lv[k] < f:
             x, f = L[k].copy(), float(lv[k])

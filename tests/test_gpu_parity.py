@@ -997,6 +997,18 @@ def test_shifted_costs_from_one_sweep(sq, port, opt):
                 x = theta[1].copy()
                 x[p] += shift
                 assert abs(fs[1][p] - port.cost(d, x, U, n, variant, off, 0.4, pool=pool)) < 1e-11
+        # several shifts from ONE sweep (the W' partials are re-reduced with new tables): bit-identical to one call per shift
+        e.set_cost(0, 0)
+        l0 = e.launch_count()
+        f0m, fm = e.cost_shifted_batched(theta, (np.pi / 2, np.pi, -0.7))
+        lm = e.launch_count() - l0
+        assert fm.shape == (3, 2, P)
+        l0 = e.launch_count()
+        singles = [e.cost_shifted_batched(theta, sh)[1] for sh in (np.pi / 2, np.pi, -0.7)]
+        ls = e.launch_count() - l0
+        assert all(np.array_equal(fm[i], singles[i]) for i in range(3)) and np.array_equal(f0m, e.cost_shifted_batched(theta, 1.0)[0])
+        if not opt.get("force_stream"):
+            assert lm < ls  # fewer launches: one executor sweep instead of three
         for variant in (4, 5, 6):
             e.set_cost(variant, 0)
             with pytest.raises(sq.abi.SqgpuError):
@@ -1040,12 +1052,13 @@ def test_shifted_costs_large_executors(sq, n, opt, cols):
     e.set_cost(0, 0)
     x = H.random_params(P, seed=8)
     idx = rng.choice(P, 24, replace=False)
-    for shift in (np.pi / 2, np.pi):
-        f0, fs = e.cost_shifted_batched(x, shift)
+    f0, fboth = e.cost_shifted_batched(x, (np.pi / 2, np.pi))
+    for k, shift in enumerate((np.pi / 2, np.pi)):
         X = np.repeat(x.reshape(1, -1), 24, axis=0)
         X[np.arange(24), idx] += shift
         want = e.cost_batched(X)
-        assert np.abs(fs[0][idx] - want).max() < 1e-11 * max(1.0, np.abs(want).max()), np.abs(fs[0][idx] - want).max()
+        assert np.abs(fboth[k][0][idx] - want).max() < 1e-11 * max(1.0, np.abs(want).max()), np.abs(fboth[k][0][idx] - want).max()
+        assert np.array_equal(e.cost_shifted_batched(x, shift)[1], fboth[k])
     if n == 10:
         a = sq.optimize.cosine(e.cost_batched, x, np.random.default_rng(2), batch_size=32, max_iter=3, tol=0)
         b = sq.optimize.cosine(e.cost_batched, x, np.random.default_rng(2), batch_size=32, max_iter=3, tol=0, cost_shifted=e.cost_shifted_batched)
