@@ -2,7 +2,8 @@
  * Builds the 3-qubit structure [U3(0) U3(1) CRY(0,1) U3(2) CNOT(2,0) RZ(1)], evaluates cost + gradient for two parameter
  * vectors on U = identity and prints them; tests/test_gpu_parity.py compares the numbers with the Python binding and the
  * oracle. Usage: abi_client [n_devices [mode]] -- n_devices > 1 (accelerator_num = G) makes ONE handle over G GPUs with
- * sqgpu_create_multi (mode: 0 auto, 1 batch, 2 columns); every other call is the same. Prints "cost[b] ..." / "grad[b] ..." lines. */
+ * sqgpu_create_multi (mode: 0 auto, 1 batch, 2 columns); every other call is the same. Prints "cost[b] ..." / "grad[b] ..." lines
+ * (single device: also "shift<s>[b] ..." = cost(params_b + shifts[s] e_p) for every p, sqgpu_cost_shifted_batched). */
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -70,6 +71,17 @@ int main(int argc, char** argv) {
         printf("grad[%d]", b);
         for (int p = 0; p < P; ++p) printf(" %.17g", grad[b * P + p]);
         printf("\n");
+    }
+    if (want == 1) {  /* the shift batch of the parameter-shift engines from one sweep (single-device handles) */
+        const double shifts[2] = {1.5707963267948966, 3.141592653589793};
+        double shifted[2 * 2 * 11];
+        CHECK(sqgpu_cost_shifted_batched(h, params, B, shifts, 2, cost, shifted));
+        for (int s = 0; s < 2; ++s)
+            for (int b = 0; b < B; ++b) {
+                printf("shift%d[%d]", s, b);
+                for (int p = 0; p < P; ++p) printf(" %.17g", shifted[(s * B + b) * P + p]);
+                printf("\n");
+            }
     }
     CHECK(sqgpu_destroy(h));
     return 0;

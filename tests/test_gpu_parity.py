@@ -404,11 +404,14 @@ def test_plain_c_client_matches_python_binding(sq, port, tmp_path):
     subprocess.check_call(["gcc", "-std=c11", "-Wall", "-I" + os.path.join(root, "include"), "-o", exe,
                            os.path.join(root, "tests", "c_abi", "abi_client.c"), "-L" + libdir, "-lsqgpu", "-Wl,-rpath," + libdir])
     out = subprocess.check_output([exe], text=True)
-    cost, grad = {}, {}
+    cost, grad, shifted = {}, {}, {}
     for line in out.splitlines():
         head, *vals = line.split()
         b = int(head[head.index("[") + 1:head.index("]")])
-        (cost if head.startswith("cost") else grad)[b] = np.array([float(v) for v in vals])
+        if head.startswith("shift"):
+            shifted[(int(head[5]), b)] = np.array([float(v) for v in vals])
+        else:
+            (cost if head.startswith("cost") else grad)[b] = np.array([float(v) for v in vals])
     c = sq.Circuit(3)
     c.add_U3(0)
     c.add_U3(1)
@@ -430,6 +433,13 @@ def test_plain_c_client_matches_python_binding(sq, port, tmp_path):
         assert cost[b][0] == f[b] and (grad[b] == g[b]).all()
         f_ref, g_ref = port.cost_grad(d, P, params[b], U, 3, 0)
         assert close_rel(cost[b][0], f_ref) and close_rel(grad[b], g_ref)
+    _, fs = e.cost_shifted_batched(params, (np.pi / 2, np.pi))
+    for s, sh in enumerate((np.pi / 2, np.pi)):
+        for b in range(2):
+            assert (shifted[(s, b)] == fs[s][b]).all()
+            x = params[b].copy()
+            x[4] += sh
+            assert abs(shifted[(s, b)][4] - port.cost(d, x, U, 3, 0)) < 1e-12
     e.close()
 
 
