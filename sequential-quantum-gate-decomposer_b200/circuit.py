@@ -247,6 +247,27 @@ class Circuit:
         eng.apply(parameters, out)
         return [out] + derivs
 
+    def get_Second_Renyi_Entropy(self, parameters=None, input_state=None, qubit_list=None):
+        """-log Tr rho_A^2 of the state C(parameters) |input_state> reduced to the qubits of ``qubit_list``
+        (Gates_block::get_second_Renyi_entropy, Gates_block.cpp:3625-3650; wrapper qgd_Circuit_Wrapper.cpp). The circuit runs on
+        the device; the reduction of the 2^n amplitudes is host-side numpy (second_renyi_entropy below)."""
+        if parameters is None:
+            raise Exception("get_Second_Renyi_entropy: array of input parameters is None")
+        n = self.qbit_num
+        if qubit_list is None:
+            qubit_list = list(range(n))
+        if any(not isinstance(q, (int, np.integer)) or q < 0 or q >= n for q in qubit_list):
+            raise Exception("Elements of qbit_list should be integers in [0, qbit_num)")
+        if input_state is None:
+            state = np.zeros(1 << n, dtype=np.complex128)
+            state[0] = 1.0
+        else:
+            state = np.array(input_state, dtype=np.complex128).reshape(-1)
+            if state.size != (1 << n):
+                raise Exception("input state should have 2^qbit_num elements")
+        self._get_engine().apply(parameters, state)
+        return second_renyi_entropy(state, n, sorted(set(int(q) for q in qubit_list)))
+
     def get_Matrix(self, parameters=None, is_f32=False):
         """C(parameters) as a dense 2^n x 2^n matrix (apply_to on the identity, Gates_block::get_matrix)."""
         if parameters is None:
@@ -254,3 +275,19 @@ class Circuit:
         m = np.eye(1 << self.qbit_num, dtype=np.complex128)
         self._get_engine().apply(parameters, m)
         return m
+
+
+def second_renyi_entropy(state, qbit_num, qubits):
+    """-log Tr rho_A^2 for the pure state ``state`` (2^n amplitudes, qubit q = bit q of the index) and the subsystem A = ``qubits``
+    (Gates_block::get_reduced_density_matrix + get_second_Renyi_entropy, Gates_block.cpp:3480-3650). With M the amplitudes as an
+    |A| x |rest| matrix, rho_A = M M^dagger and Tr rho_A^2 = || M M^dagger ||_F^2; for a pure state the complement has the same
+    purity, so the smaller side is the one that is squared."""
+    n = int(qbit_num)
+    qubits = list(qubits)
+    rest = [q for q in range(n) if q not in qubits]
+    if len(qubits) > len(rest):
+        qubits, rest = rest, qubits
+    psi = np.asarray(state, dtype=np.complex128).reshape((2,) * n)  # axis a <-> qubit n - 1 - a
+    m = np.transpose(psi, [n - 1 - q for q in qubits] + [n - 1 - q for q in rest]).reshape(1 << len(qubits), -1)
+    rho = m @ m.conj().T
+    return float(-np.log(np.sum(rho.real ** 2 + rho.imag ** 2)))

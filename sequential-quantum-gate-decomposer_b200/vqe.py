@@ -4,7 +4,7 @@
 ``qgd_Variational_Quantum_Eigensolver_Base`` (squander/VQA/qgd_Variational_Quantum_Eigensolver_Base.py:145-420) for the calls
 on the hot path: ``set_Ansatz``, ``Generate_Circuit``, ``set_Gate_Structure``, ``set_Initial_State``, ``get_Parameter_Num``,
 ``Optimization_Problem``, ``Optimization_Problem_Grad``, ``Optimization_Problem_Combined``, ``Optimization_Problem_Batch``,
-``apply_to``. Every evaluation runs on the GPU through the C-ABI (sqgpu_vqe_energy[_grad]_batched): there is no CPU path.
+``apply_to``, ``get_Second_Renyi_Entropy``. Every evaluation runs on the GPU through the C-ABI (sqgpu_vqe_energy[_grad]_batched): there is no CPU path.
 
 ``Start_Optimization`` (with ``set_Optimizer``, ``set_Optimized_Parameters``, ``get_Optimized_Parameters``) is the thin N1 layer
 over that path: "COSINE" and "AGENTS" (the reference's parameter-shift engines, their shift batches as device batches),
@@ -239,6 +239,17 @@ class Variational_Quantum_Eigensolver:
         self._num_evaluations = getattr(self, "_num_evaluations", 0) + ne
         self._current_minimum = float(f)
         return float(f)
+
+    def set_Optimization_Tolerance(self, tolerance):
+        self.config["gradient_tolerance"] = float(tolerance)
+
+    def set_Project_Name(self, project_name):
+        self.project_name = str(project_name)
+
+    def get_Second_Renyi_Entropy(self, parameters=None, input_state=None, qubit_list=None):
+        """qgd_Variational_Quantum_Eigensolver_Base.get_Second_Renyi_Entropy (…Base.py:288-323): the entropy of the ansatz state
+        on a subset of the qubits (default input: |0...0>)"""
+        return self._circuit.get_Second_Renyi_Entropy(parameters, input_state, qubit_list)
 
     def apply_to(self, parameters_mtx, state_to_be_transformed):
         """in place: state <- C(parameters) state"""

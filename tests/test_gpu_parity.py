@@ -1127,6 +1127,32 @@ def test_cosine_engine_on_the_device(sq, port):
     assert err3 < 0.5 and close_rel(dec.Optimization_Problem(dec.get_Optimized_Parameters()), err3, 1e-9)
 
 
+def test_second_renyi_entropy_on_device_state(sq, port):
+    """get_Second_Renyi_Entropy of the circuit and VQE classes (Gates_block.cpp:3625-3650): the ansatz state comes from the
+    device, the entropy equals the one of the oracle's state; a layer of single-qubit gates alone leaves a product state"""
+    n = 8
+    ip, ix, dat = H.heisenberg_csr_fast(n)
+    vqe = sq.Variational_Quantum_Eigensolver((ip, ix, dat), n)
+    vqe.set_Ansatz("HEA_ZYZ")
+    vqe.Generate_Circuit(2, 1)
+    x = H.random_params(vqe.get_Parameter_Num(), seed=6)
+    d, _ = vqe.get_Circuit().descriptors()
+    psi = np.zeros(1 << n, dtype=np.complex128)
+    psi[0] = 1
+    want_state = port.apply_circuit(d, x, psi)
+    for sub in ([0], [1, 2, 5], [0, 1, 2, 3], None):
+        got = vqe.get_Second_Renyi_Entropy(x, None, sub)
+        want = sq.circuit.second_renyi_entropy(want_state, n, list(range(n)) if sub is None else sub)
+        assert abs(got - want) < 1e-10
+        assert (got > 1e-3) == (sub is not None)  # entangled subsets; the full register of a pure state has entropy 0
+    c = sq.Circuit(n)
+    for q in range(n):
+        c.add_U3(q)
+    assert abs(c.get_Second_Renyi_Entropy(H.random_params(3 * n, seed=1), None, [2, 3])) < 1e-12
+    with pytest.raises(Exception):
+        c.get_Second_Renyi_Entropy(None)
+
+
 def test_vqe_start_optimization(sq, port):
     """Variational_Quantum_Eigensolver.Start_Optimization over the device energy path (...Base.cpp:100-160; the reference's
     tests/VQE/test_VQE.py:101-140 runs it with AGENTS / COSINE / BFGS): 6-qubit Heisenberg model, HEA_ZYZ ansatz. BFGS (every line search

@@ -61,3 +61,41 @@ def test_replace_trivial_cry_gates_keeps_the_unitary(port):
     flat = c.get_Flat_Circuit()
     with pytest.raises(Exception):
         replace(flat, x)  # only block gates are accepted, as in the reference
+
+
+def test_second_renyi_entropy_known_answers():
+    """second_renyi_entropy (Gates_block::get_second_Renyi_entropy, Gates_block.cpp:3625-3650): product state -> 0, a Bell pair cut
+    in the middle -> log 2, GHZ -> log 2 for every proper subset, a subset and its complement agree, and the value equals
+    -log Tr rho_A^2 of an explicitly traced-out density matrix for a random state"""
+    from squander_b200 import circuit as C
+
+    n = 4
+    prod = np.zeros(1 << n, dtype=np.complex128)
+    prod[5] = 1.0
+    assert abs(C.second_renyi_entropy(prod, n, [0, 2])) < 1e-14
+    bell = np.zeros(4, dtype=np.complex128)
+    bell[0] = bell[3] = 1 / np.sqrt(2)
+    assert abs(C.second_renyi_entropy(bell, 2, [0]) - np.log(2)) < 1e-14
+    assert abs(C.second_renyi_entropy(bell, 2, [0, 1])) < 1e-14
+    ghz = np.zeros(1 << n, dtype=np.complex128)
+    ghz[0] = ghz[-1] = 1 / np.sqrt(2)
+    for sub in ([0], [1, 3], [0, 1, 2]):
+        assert abs(C.second_renyi_entropy(ghz, n, sub) - np.log(2)) < 1e-14
+    rng = np.random.default_rng(3)
+    n = 5
+    psi = rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)
+    psi /= np.linalg.norm(psi)
+    sub = [1, 4]
+    # explicit partial trace: rho_A[a, a'] = sum_r psi[idx(a, r)] conj(psi[idx(a', r)]), qubit q = bit q of the index
+    rest = [q for q in range(n) if q not in sub]
+    def idx(a, r):
+        i = 0
+        for j, q in enumerate(sub):
+            i |= ((a >> j) & 1) << q
+        for j, q in enumerate(rest):
+            i |= ((r >> j) & 1) << q
+        return i
+    rho = np.array([[sum(psi[idx(a, r)] * np.conj(psi[idx(b, r)]) for r in range(1 << len(rest))) for b in range(4)] for a in range(4)])
+    want = -np.log(np.real(np.trace(rho @ rho)))
+    assert abs(C.second_renyi_entropy(psi, n, sub) - want) < 1e-12
+    assert abs(C.second_renyi_entropy(psi, n, rest) - want) < 1e-12
