@@ -86,6 +86,96 @@ class N_Qubit_Decomposition_custom:
     def get_Circuit(self):
         return self._circuit
 
+    # ---- the wrapper's data-format methods either side of the path (qgd_N_Qubit_Decompositions_Wrapper.cpp:3125-3248) -----
+    def get_Gate_Num(self):
+        return self._circuit.get_Gate_Num()
+
+    def get_Unitary(self):
+        return self.Umtx.copy()
+
+    def set_Unitary(self, Umtx):
+        """Decomposition_Base::set_unitary: a new matrix of the same register for the same gate structure; it is uploaded
+        with the next evaluation (or at once by Upload_Umtx_to_DFE)"""
+        U = np.ascontiguousarray(Umtx, dtype=np.complex128)
+        if U.ndim != 2 or U.shape[0] != (1 << self.qbit_num) or U.shape[1] > U.shape[0]:
+            raise Exception("set_Unitary: Umtx should be a 2^qbit_num x cols complex array, cols <= rows")
+        self.Umtx = U
+        if self._engine_obj is not None:
+            self._engine_obj.upload_matrix(self.Umtx)
+        self._dirty = True
+
+    def Upload_Umtx_to_DFE(self):
+        """upload_Umtx_to_DFE (Optimization_Interface.cpp:1819-1824), the hook the optimizers call before they start: the
+        matrix (and the gate structure) become resident on the device now instead of with the first evaluation"""
+        self._sync()
+
+    def export_Unitary(self, filename):
+        """Decomposition_Base::export_unitary (Decomposition_Base.cpp:1128-1146): int32 rows, int32 cols, rows x cols complex128"""
+        if getattr(self, "project_name", ""):
+            filename = self.project_name + "_" + filename
+        with open(filename, "wb") as f:
+            f.write(np.array(self.Umtx.shape, dtype=np.int32).tobytes())
+            f.write(np.ascontiguousarray(self.Umtx).tobytes())
+
+    def set_Unitary_From_Binary(self, filename):
+        """Decomposition_Base::import_unitary_from_binary (Decomposition_Base.cpp:1154-1177)"""
+        if getattr(self, "project_name", ""):
+            filename = self.project_name + "_" + filename
+        with open(filename, "rb") as f:
+            rows, cols = np.frombuffer(f.read(8), dtype=np.int32)
+            data = np.frombuffer(f.read(), dtype=np.complex128)
+        if rows <= 0 or cols <= 0 or data.size != int(rows) * int(cols):
+            raise Exception("set_Unitary_From_Binary: truncated or malformed file")
+        self.set_Unitary(data.reshape(int(rows), int(cols)).copy())
+
+    def set_Gate_Structure_From_Binary(self, filename):
+        """set_adaptive_gate_structure(filename) (N_Qubit_Decomposition_adaptive.cpp:1398-1420): gate structure and parameters
+        from a file written by export_gate_list_to_binary"""
+        from . import gate_io
+
+        circ, params = gate_io.import_gate_list_from_binary(filename, self._device)
+        self.set_Gate_Structure(circ)
+        self._optimized_parameters = np.asarray(params, dtype=np.float64).copy()
+
+    def add_Gate_Structure_From_Binary(self, filename):
+        """add_adaptive_gate_structure(filename) (N_Qubit_Decomposition_adaptive.cpp:1430-1460): the stored gates are applied
+        AFTER the current structure, their parameters follow the current ones"""
+        from . import gate_io
+
+        circ, params = gate_io.import_gate_list_from_binary(filename, self._device)
+        if circ.qbit_num != self.qbit_num:
+            raise Exception("add_Gate_Structure_From_Binary: qubit count mismatch")
+        old = self._optimized_parameters if self._optimized_parameters is not None else np.zeros(self.get_Parameter_Num())
+        self._circuit.add_Circuit(circ)
+        self._optimized_parameters = np.concatenate([old, np.asarray(params, dtype=np.float64)])
+        self._dirty = True
+
+    def get_Project_Name(self):
+        return getattr(self, "project_name", "")
+
+    def set_Project_Name(self, project_name):
+        self.project_name = str(project_name)
+
+    def set_Max_Iterations(self, max_iterations):
+        """Decomposition_Base::set_max_inner_iterations"""
+        self.config["max_inner_iterations"] = int(max_iterations)
+
+    def set_Verbose(self, verbose):
+        self.verbose = int(verbose)
+
+    def set_Debugfile(self, debugfile):
+        self.debugfile = str(debugfile)
+
+    def List_Gates(self):
+        """Gates_block::list_gates: one line per gate, in application order"""
+        names = {v: k for k, v in vars(abi).items() if isinstance(v, int) and k.isupper() and not k.startswith(("ERR", "SHARD", "OK"))}
+        descs = self._circuit.descriptors()[0]
+        for i, r in enumerate(descs):
+            print("%d: %s target %d control %d parameters %d" % (i, names.get(int(r["type"]), str(int(r["type"]))), int(r["target"]), int(r["control"]), int(r["n_params"])))
+
+    def get_Second_Renyi_Entropy(self, parameters=None, input_state=None, qubit_list=None):
+        return self._circuit.get_Second_Renyi_Entropy(parameters, input_state, qubit_list)
+
     def get_Parameter_Num(self):
         return self._circuit.get_Parameter_Num()
 

@@ -1127,6 +1127,27 @@ def test_cosine_engine_on_the_device(sq, port):
     assert err3 < 0.5 and close_rel(dec.Optimization_Problem(dec.get_Optimized_Parameters()), err3, 1e-9)
 
 
+def test_wrapper_set_unitary_and_upload(sq, port):
+    """set_Unitary / Upload_Umtx_to_DFE of the decomposition wrapper (Optimization_Interface.cpp:1819-1824 is the upload hook the
+    optimizers call): a new matrix for the same gate structure is what the next evaluation sees"""
+    n = 4
+    dec = sq.N_Qubit_Decomposition_adaptive(H.random_unitary(1 << n, seed=1), level_limit_max=2, level_limit_min=1)
+    dec.add_Adaptive_Layers()
+    dec.add_Finalyzing_Layer_To_Gate_Structure()
+    P = dec.get_Parameter_Num()
+    x = H.random_params(P, seed=3)
+    d, pool = dec.get_Circuit().descriptors()
+    for seed in (1, 7):
+        U = H.random_unitary(1 << n, seed=seed)
+        dec.set_Unitary(U)
+        dec.Upload_Umtx_to_DFE()
+        f_ref, g_ref = port.cost_grad(d, P, x, U, n, 0)
+        f, g = dec.Optimization_Problem_Combined(x)
+        assert close_rel(f, f_ref) and close_rel(g, g_ref)
+    assert abs(dec.get_Second_Renyi_Entropy(x, None, [0, 1]) - sq.circuit.second_renyi_entropy(
+        port.apply_circuit(d, x, np.eye(1 << n, dtype=np.complex128)[:, 0].copy()), n, [0, 1])) < 1e-10
+
+
 def test_second_renyi_entropy_on_device_state(sq, port):
     """get_Second_Renyi_Entropy of the circuit and VQE classes (Gates_block.cpp:3625-3650): the ansatz state comes from the
     device, the entropy equals the one of the oracle's state; a layer of single-qubit gates alone leaves a product state"""

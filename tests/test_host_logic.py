@@ -99,3 +99,59 @@ def test_second_renyi_entropy_known_answers():
     want = -np.log(np.real(np.trace(rho @ rho)))
     assert abs(C.second_renyi_entropy(psi, n, sub) - want) < 1e-12
     assert abs(C.second_renyi_entropy(psi, n, rest) - want) < 1e-12
+
+
+def test_wrapper_data_format_methods(tmp_path, capsys):
+    """the data-format methods of the decomposition wrapper either side of the cost path (qgd_N_Qubit_Decompositions_Wrapper.cpp:
+    3125-3248), none of which needs a device: unitary binary files (Decomposition_Base.cpp:1128-1177: int32 rows, int32 cols,
+    complex128 data), gate structures from binary gate lists (set_ / add_Gate_Structure_From_Binary), project name prefix,
+    gate listing"""
+    import struct
+
+    import helpers as H
+
+    sq = H.sq
+    n = 3
+    U = H.random_unitary(1 << n, seed=4)
+    dec = sq.N_Qubit_Decomposition_adaptive(U, level_limit_max=2, level_limit_min=1)
+    fn = str(tmp_path / "umtx.binary")
+    dec.export_Unitary(fn)
+    raw = open(fn, "rb").read()
+    assert struct.unpack("ii", raw[:8]) == (8, 8) and len(raw) == 8 + 64 * 16
+    assert np.array_equal(np.frombuffer(raw[8:], dtype=np.complex128).reshape(8, 8), U)
+    dec2 = sq.N_Qubit_Decomposition_adaptive(np.eye(8, dtype=np.complex128), level_limit_max=2, level_limit_min=1)
+    dec2.set_Unitary_From_Binary(fn)
+    assert np.array_equal(dec2.get_Unitary(), U)
+    with open(fn, "wb") as f:
+        f.write(raw[:-16])
+    with pytest.raises(Exception):
+        dec2.set_Unitary_From_Binary(fn)
+    with pytest.raises(Exception):
+        dec2.set_Unitary(np.eye(4))
+    # gate structures through the binary gate-list format
+    c = H.adaptive_circuit(n, 1)
+    P = c.get_Parameter_Num()
+    x = H.random_params(P, seed=2)
+    gl = str(tmp_path / "circuit.binary")
+    sq.gate_io.export_gate_list_to_binary(x, c, gl)
+    dec.set_Gate_Structure_From_Binary(gl)
+    assert dec.get_Parameter_Num() == P and np.array_equal(dec.get_Optimized_Parameters(), x)
+    assert dec.get_Gate_Num() == c.get_Gate_Num()
+    d0 = dec.get_Circuit().descriptors()[0]
+    dec.add_Gate_Structure_From_Binary(gl)
+    assert dec.get_Parameter_Num() == 2 * P and np.array_equal(dec.get_Optimized_Parameters(), np.concatenate([x, x]))
+    d1 = dec.get_Circuit().descriptors()[0]
+    flat = lambda d: [(int(r["type"]), int(r["target"]), int(r["control"])) for r in d if int(r["type"]) not in (sq.abi.BLOCK_BEGIN, sq.abi.BLOCK_END)]
+    assert flat(d1) == flat(d0) + flat(d0)
+    # project name prefixes the file names, as in the reference
+    dec.set_Project_Name(str(tmp_path / "proj"))
+    assert dec.get_Project_Name().endswith("proj")
+    dec.export_Unitary("u.binary")
+    assert (tmp_path / "proj_u.binary").exists()
+    dec.set_Max_Iterations(17)
+    assert dec.config["max_inner_iterations"] == 17
+    dec.set_Verbose(0)
+    dec.set_Debugfile("x.log")
+    dec.List_Gates()
+    out = capsys.readouterr().out.splitlines()
+    assert len(out) == len(d1) and "U3" in out[0] + out[1] + out[2]
