@@ -166,6 +166,53 @@ class Circuit:
     def set_min_fusion(self, min_fusion):
         self._min_fusion = int(min_fusion)
 
+    def get_Gates(self):
+        """the gates and sub-circuits of this block in application order (Gates_block::get_gates)"""
+        return list(self._items)
+
+    def get_Gate(self, idx):
+        return self._items[idx]
+
+    def get_Gate_Nums(self):
+        """{gate name: count} over the whole (nested) structure (Gates_block::get_gate_nums, Gates_block.cpp:2630-2637)"""
+        out = {}
+        for g in self._flat_gates():
+            name = abi.GATE_NAMES[g.type]
+            out[name] = out.get(name, 0) + 1
+        return out
+
+    @staticmethod
+    def _gate_qubits(g):
+        return [q for q in ([g.target, g.control, g.target2, g.control2] + list(g.qubits or [])) if q is not None and q >= 0]
+
+    def get_Qbits(self):
+        """sorted list of the qubits the circuit acts on (Gates_block::get_involved_qubits)"""
+        return sorted({int(q) for g in self._flat_gates() for q in self._gate_qubits(g)})
+
+    def Remap_Qbits(self, qbit_map, qbit_num=None):
+        """a new circuit with qubit q replaced by qbit_map[q] (Gates_block::create_remapped_circuit, qgd_Circuit.py:709-731);
+        the register may change its size; qubits without an entry keep their index"""
+        n = self.qbit_num if qbit_num is None else int(qbit_num)
+        m = lambda q: q if q is None or q < 0 else int(qbit_map.get(q, q))
+        out = Circuit(n, self._device)
+        for it in self._items:
+            if isinstance(it, Circuit):
+                out._add(it.Remap_Qbits(qbit_map, n))
+                continue
+            g = _Gate(it.type, m(it.target), m(it.control), m(it.target2), m(it.control2),
+                      None if it.qubits is None else [m(q) for q in it.qubits], it.matrix)
+            if it.qubits is not None and sorted(g.qubits) != list(g.qubits):
+                raise Exception("Remap_Qbits: the qubits of a GENERAL gate must stay in ascending order")
+            out._check_q(*self._gate_qubits(g))
+            out._add(g)
+        return out
+
+    def apply_to_list(self, inputs, parameters, parallel=1, is_f32=False):
+        """apply_to on every array of ``inputs`` in place (Gates_block::apply_to_list, Gates_block.cpp:575-600): the gate
+        structure and the kernel tables stay on the device between the inputs"""
+        for m in inputs:
+            self.apply_to(parameters, m, parallel, is_f32)
+
     def _flat_gates(self):
         for it in self._items:
             if isinstance(it, Circuit):

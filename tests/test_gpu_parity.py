@@ -1146,6 +1146,11 @@ def test_wrapper_set_unitary_and_upload(sq, port):
         assert close_rel(f, f_ref) and close_rel(g, g_ref)
     assert abs(dec.get_Second_Renyi_Entropy(x, None, [0, 1]) - sq.circuit.second_renyi_entropy(
         port.apply_circuit(d, x, np.eye(1 << n, dtype=np.complex128)[:, 0].copy()), n, [0, 1])) < 1e-10
+    # apply_to_list (Gates_block.cpp:575-600): every input transformed in place
+    ins = [H.random_unitary(1 << n, seed=5), H.random_state(1 << n), np.ascontiguousarray(H.random_unitary(1 << n, seed=6)[:, :3])]
+    want = [port.apply_circuit(d, x, m, pool) for m in ins]
+    dec.get_Circuit().apply_to_list(ins, x)
+    assert all(np.abs(a - b).max() < ENTRY_TOL for a, b in zip(ins, want))
 
 
 def test_second_renyi_entropy_on_device_state(sq, port):

@@ -155,3 +155,37 @@ def test_wrapper_data_format_methods(tmp_path, capsys):
     dec.List_Gates()
     out = capsys.readouterr().out.splitlines()
     assert len(out) == len(d1) and "U3" in out[0] + out[1] + out[2]
+
+
+def test_circuit_queries_and_remap():
+    """host-side queries of the circuit wrapper (qgd_Circuit_Wrapper.cpp:3109-3302): gate counts, involved qubits, remapping onto
+    another register -- the remapped structure equals the one built directly on the new qubits"""
+    import helpers as H
+
+    sq = H.sq
+    c = sq.Circuit(4)
+    c.add_U3(0)
+    c.add_CNOT(1, 0)
+    inner = sq.Circuit(4)
+    inner.add_RY(1)
+    inner.add_CRY(0, 1)
+    c.add_Circuit(inner)
+    c.add_U3(1)
+    assert c.get_Gate_Nums() == {"U3": 2, "CNOT": 1, "RY": 1, "CRY": 1}
+    assert c.get_Qbits() == [0, 1] and c.get_Gate_Num() == 4 and len(c.get_Gates()) == 4 and c.get_Gate(2) is inner
+    r = c.Remap_Qbits({0: 3, 1: 2}, 5)
+    want = sq.Circuit(5)
+    want.add_U3(3)
+    want.add_CNOT(2, 3)
+    wi = sq.Circuit(5)
+    wi.add_RY(2)
+    wi.add_CRY(3, 2)
+    want.add_Circuit(wi)
+    want.add_U3(2)
+    assert r.get_Qbit_Num() == 5 and r.get_Qbits() == [2, 3] and r.get_Parameter_Num() == c.get_Parameter_Num()
+    key = lambda circ: [tuple(int(x[f]) for f in ("type", "target", "control", "param_start", "n_params")) for x in circ.descriptors(nested=True)[0]]
+    assert key(r) == key(want)
+    with pytest.raises(Exception):
+        c.Remap_Qbits({0: 1})  # target == control after the map
+    with pytest.raises(Exception):
+        c.Remap_Qbits({0: 7})
