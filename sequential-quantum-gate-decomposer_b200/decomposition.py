@@ -150,6 +150,24 @@ class N_Qubit_Decomposition_custom:
         self._optimized_parameters = np.concatenate([old, np.asarray(params, dtype=np.float64)])
         self._dirty = True
 
+    def import_Qiskit_Circuit(self, qc_in):
+        """import_Qiskit_Circuit of the reference wrapper (Qiskit_IO.convert_Qiskit_to_Squander, then set_Gate_Structure +
+        set_Optimized_Parameters) without Qiskit: ``qc_in`` is OpenQASM 2 source, the path of a .qasm file, or any object whose
+        ``qasm()`` method returns the source (a Qiskit QuantumCircuit up to 0.46; newer ones: pass qiskit.qasm2.dumps(qc))"""
+        import os
+
+        from . import qasm
+
+        if hasattr(qc_in, "qasm") and callable(qc_in.qasm):
+            qc_in = qc_in.qasm()
+        if not isinstance(qc_in, str):
+            raise Exception("import_Qiskit_Circuit: expected OpenQASM 2 source, a .qasm path or an object with qasm()")
+        circ, params = qasm.load(qc_in) if ("OPENQASM" not in qc_in and os.path.exists(qc_in)) else qasm.loads(qc_in)
+        if circ.qbit_num != self.qbit_num:
+            raise Exception("import_Qiskit_Circuit: the circuit has %d qubits, the decomposition %d" % (circ.qbit_num, self.qbit_num))
+        self.set_Gate_Structure(circ)
+        self._optimized_parameters = np.asarray(params, dtype=np.float64).copy()
+
     def get_Project_Name(self):
         return getattr(self, "project_name", "")
 

@@ -189,3 +189,36 @@ def test_circuit_queries_and_remap():
         c.Remap_Qbits({0: 1})  # target == control after the map
     with pytest.raises(Exception):
         c.Remap_Qbits({0: 7})
+
+
+def test_import_qiskit_circuit_without_qiskit(tmp_path, port):
+    """import_Qiskit_Circuit of the decomposition wrapper over the Qiskit-free QASM importer: source text, a file path and an
+    object with qasm() give the same structure and parameters (theta / 2 convention of Qiskit_IO.py:330-461), and the oracle's
+    matrix of that structure is the circuit's unitary (checked on a Bell-pair preparation)"""
+    import helpers as H
+
+    sq = H.sq
+    src = 'OPENQASM 2.0;\ninclude "qelib1.inc";\nqreg q[2];\nh q[0];\ncx q[0],q[1];\nry(0.6) q[1];\nu3(0.2,0.4,-0.3) q[0];\n'
+    fn = tmp_path / "c.qasm"
+    fn.write_text(src)
+
+    class Qc:
+        def qasm(self):
+            return src
+
+    got = []
+    for arg in (src, str(fn), Qc()):
+        dec = sq.N_Qubit_Decomposition_custom(np.eye(4, dtype=np.complex128))
+        dec.import_Qiskit_Circuit(arg)
+        d, pool = dec.get_Circuit().descriptors()
+        got.append(([(int(r["type"]), int(r["target"]), int(r["control"])) for r in d], dec.get_Optimized_Parameters()))
+    assert got[0][0] == got[1][0] == got[2][0] == [(sq.abi.H, 0, -1), (sq.abi.CNOT, 1, 0), (sq.abi.RY, 1, -1), (sq.abi.U3, 0, -1)]
+    assert all(np.array_equal(g[1], got[0][1]) for g in got) and np.allclose(got[0][1], [0.3, 0.1, 0.4, -0.3])
+    psi = np.zeros(4, dtype=np.complex128)
+    psi[0] = 1
+    bell = port.apply_circuit(d[:2], [], psi, pool)
+    assert np.allclose(np.abs(bell) ** 2, [0.5, 0, 0, 0.5])
+    with pytest.raises(Exception):
+        sq.N_Qubit_Decomposition_custom(np.eye(8, dtype=np.complex128)).import_Qiskit_Circuit(src)
+    with pytest.raises(Exception):
+        dec.import_Qiskit_Circuit(42)
