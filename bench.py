@@ -20,7 +20,8 @@ Besides the headline line's keys the JSON carries, under "secondary" (skipped wi
               ranks (rank r holds U[:, r w:(r+1) w] with trace_offset = r w) and ONE all-reduce of the raw trace terms
               [64 x 3 x 2] per evaluation inside the timed region -- the north star's ">= 6x from 1 to 8 GPUs at 12 qubits".
   C5_vqe      BASELINE configs[4]: n = 20 Heisenberg VQE energy + gradient, 1024 parameter sets split over the ranks.
-  latency     one cost+gradient evaluation (batch 1): what a BFGS line search sees.
+  latency     one cost+gradient evaluation (batch 1): what a BFGS line search sees; the shift batch of a COSINE iteration from one
+              adjoint sweep against the explicit batch of shifted parameter sets.
 
 One JSON line on stdout (rank 0).
 """
@@ -667,6 +668,31 @@ def run_ours(args):
             abi.check(eng.lib, eng.lib.sqgpu_cost_batched(eng._h, abi.as_dp(one), 1, abi.as_dp(c1)))
         lat["cost_batch1_ms_host_call"] = (time.perf_counter() - t0) / reps * 1e3
         lat["evals_per_s_batch1"] = 1e3 / lat["cost_grad_batch1_ms_host_call"]
+        # the shift batch of a COSINE iteration (COSINE.cpp:255-291: 64 parameters x shifts pi/2 and pi): ONE adjoint sweep that
+        # returns the shifted costs of all P parameters (sqgpu_cost_shifted_batched) against the explicit batch of 128 sets
+        if args.variant in (0, 1, 2, 3, 9):
+            try:
+                sh = np.array([np.pi / 2, np.pi])
+                fs = np.zeros((2, 1, P))
+                for _ in range(2):
+                    abi.check(eng.lib, eng.lib.sqgpu_cost_shifted_batched(eng._h, abi.as_dp(one), 1, abi.as_dp(sh), 2, abi.as_dp(c1), abi.as_dp(fs)))
+                t0 = time.perf_counter()
+                for _ in range(reps):
+                    abi.check(eng.lib, eng.lib.sqgpu_cost_shifted_batched(eng._h, abi.as_dp(one), 1, abi.as_dp(sh), 2, abi.as_dp(c1), abi.as_dp(fs)))
+                lat["shift_batch_one_sweep_ms_host_call"] = (time.perf_counter() - t0) / reps * 1e3
+                idx = np.random.default_rng(1).choice(P, min(64, P), replace=False)
+                X = np.repeat(one, 2 * idx.size, axis=0)
+                X[np.arange(idx.size), idx] += np.pi / 2
+                X[idx.size + np.arange(idx.size), idx] += np.pi
+                cx = np.zeros(2 * idx.size)
+                abi.check(eng.lib, eng.lib.sqgpu_cost_batched(eng._h, abi.as_dp(X), 2 * idx.size, abi.as_dp(cx)))
+                t0 = time.perf_counter()
+                for _ in range(3):
+                    abi.check(eng.lib, eng.lib.sqgpu_cost_batched(eng._h, abi.as_dp(X), 2 * idx.size, abi.as_dp(cx)))
+                lat["shift_batch_explicit_%d_sets_ms_host_call" % (2 * idx.size)] = (time.perf_counter() - t0) / 3 * 1e3
+                lat["shift_batch_max_abs_difference"] = float(max(np.abs(fs[0, 0, idx] - cx[:idx.size]).max(), np.abs(fs[1, 0, idx] - cx[idx.size:]).max()))
+            except Exception as ex:  # the headline number must not depend on it
+                lat["shift_batch_error"] = repr(ex)
 
     secondary = {}
     if not args.no_secondary:
