@@ -602,3 +602,23 @@ class N_Qubit_Decomposition_adaptive(N_Qubit_Decomposition_custom):
     def get_CNOT_Count(self):
         """two-qubit gates (CNOT + CZ) of the current structure, the figure of merit of the decomposition"""
         return sum(1 for g in self._circuit._flat_gates() if g.type in (abi.CNOT, abi.CZ))
+
+
+class N_Qubit_State_Preparation_adaptive(N_Qubit_Decomposition_adaptive):
+    """qgd_N_Qubit_State_Preparation_adaptive (squander/decomposition/qgd_N_Qubit_State_Preparation_adaptive.py:35-62): the adaptive
+    decomposition with a 2^n x 1 column as "Umtx" -- the cost 1 - Re (C state)[0] is minimal when the circuit maps the state
+    onto |0...0>, so the inverse of the circuit found prepares the state. Same checks as the reference's constructor."""
+
+    def __init__(self, State, level_limit_max=8, level_limit_min=0, topology=None, config=None, accelerator_num=1, device=0):
+        if not isinstance(State, np.ndarray):
+            raise Exception("Initial state should be a numpy array")
+        if State.dtype != np.complex128:
+            raise Exception("Initial state should be made of complex values")
+        if not State.data.c_contiguous:
+            raise Exception("Initial state should be contiguous in memory")
+        if State.ndim == 1:
+            State = State.reshape((State.size, 1))
+        if not (State.ndim == 2 and State.shape[1] == 1):
+            raise Exception("Initial state not properly formatted. Input state must be a column vector")
+        super().__init__(State, level_limit_max=level_limit_max, level_limit_min=level_limit_min, topology=topology, config=config,
+                         accelerator_num=accelerator_num, device=device)

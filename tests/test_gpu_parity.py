@@ -1153,6 +1153,28 @@ def test_wrapper_set_unitary_and_upload(sq, port):
     assert all(np.abs(a - b).max() < ENTRY_TOL for a, b in zip(ins, want))
 
 
+def test_state_preparation_adaptive(sq, port):
+    """N_Qubit_State_Preparation_adaptive (qgd_N_Qubit_State_Preparation_adaptive.py:35-62; the reference's
+    tests/decomposition/test_State_Preparation.py): the adaptive decomposition on a 2^n x 1 column. The circuit found maps the
+    state onto |0...0> -- checked with the ORACLE's application of the final, CRY-free circuit -- and the constructor refuses
+    what the reference refuses."""
+    n = 3
+    state = H.random_state(1 << n)
+    prep = sq.N_Qubit_State_Preparation_adaptive(state, level_limit_max=3, level_limit_min=1, config={"optimization_tolerance": 1e-6})
+    err = prep.Start_Decomposition()
+    assert err < 1e-4
+    d, pool = prep.get_Circuit().descriptors()
+    out = port.apply_circuit(d, prep.get_Optimized_Parameters(), prep.get_Unitary()[:, 0].copy(), pool)
+    assert abs(out[0] - 1.0) < 1e-3 and np.abs(out[1:]).max() < 2e-2
+    assert sq.abi.ADAPTIVE not in [int(r["type"]) for r in d]
+    with pytest.raises(Exception):
+        sq.N_Qubit_State_Preparation_adaptive(np.eye(4, dtype=np.complex128))
+    with pytest.raises(Exception):
+        sq.N_Qubit_State_Preparation_adaptive(np.ones(4))
+    with pytest.raises(Exception):
+        sq.N_Qubit_State_Preparation_adaptive([1, 0, 0, 0])
+
+
 def test_second_renyi_entropy_on_device_state(sq, port):
     """get_Second_Renyi_Entropy of the circuit and VQE classes (Gates_block.cpp:3625-3650): the ansatz state comes from the
     device, the entropy equals the one of the oracle's state; a layer of single-qubit gates alone leaves a product state"""
