@@ -262,9 +262,10 @@ class N_Qubit_Decomposition_custom:
 
         if self._optimizer in ("COSINE", "AGENTS", "AGENTS_COMBINED"):
             # COSINE.cpp:226-228, 411-414 / AGENTS.cpp:333-335: the three-point rule is defined for the Frobenius cost (a sinusoid
-            # of period 2 pi in every parameter); COSINE throws for the other variants, AGENTS' five-point Hilbert-Schmidt rule
-            # is not provided here
-            if self._variant != abi.FROBENIUS_NORM:
+            # of period 2 pi in every parameter); COSINE throws for the other variants, AGENTS takes its five-point rule for the
+            # Hilbert-Schmidt test
+            five_point = self._optimizer != "COSINE" and self._variant == abi.HILBERT_SCHMIDT_TEST  # AGENTS.cpp:335, 536-660
+            if self._variant != abi.FROBENIUS_NORM and not five_point:
                 raise Exception("solve_layer_optimization_problem_%s: Not implemented method." % self._optimizer)
             cfg = self.config
             if self._optimizer in ("AGENTS", "AGENTS_COMBINED"):
@@ -276,7 +277,7 @@ class N_Qubit_Decomposition_custom:
                     agent_lifetime=int(cfg.get("agent_lifetime_agent", cfg.get("agent_lifetime", 1000))),
                     exploration_rate=float(cfg.get("agent_exploration_rate_agent", cfg.get("agent_exploration_rate", 0.2))),
                     agent_randomization_rate=float(cfg.get("agent_randomization_rate", 0.2)), radius=float(cfg.get("Randomized_Radius", 1.0)),
-                    convergence_length=int(cfg.get("convergence_length_agent", cfg.get("convergence_length", 20))))
+                    convergence_length=int(cfg.get("convergence_length_agent", cfg.get("convergence_length", 20))), five_point=five_point)
                 self._num_evaluations += ne
                 if self._optimizer == "AGENTS_COMBINED":  # AGENTS.cpp:914-933: gradient descent from the agents' result
                     x, f, _, ne = optimize.lbfgs(lambda v: tuple(a[0] for a in eng.cost_grad_batched(v.reshape(1, -1))), eng.line_search_batched, x,

@@ -176,9 +176,37 @@ def cosine(cost_batched, x0, rng, batch_size=None, max_iter=2000, tol=1e-10, dou
     return x, f, it, n_eval
 
 
+def five_point_updates(theta, f0, f_pi4, f_pi2, f_pi, f_3pi2):
+    """The five-point rule of AGENTS for costs quadratic in the trace (Hilbert-Schmidt test; AGENTS.cpp:583-660): along one
+    parameter f(p) = kappa sin(2 p + xi) + gamma sin(p + varphi) + offset, fixed by the value at p = theta and at the shifts
+    pi/4, pi/2, pi, 3 pi/2. Returns (shift to the minimum of that curve, its value there). The reference minimises the curve
+    with ten BFGS_Powell iterations from an analytic guess; here: a 1440-point scan of the period, then Newton steps."""
+    theta, f0, f_pi4, f_pi2, f_pi, f_3pi2 = (np.asarray(a, dtype=np.float64) for a in (theta, f0, f_pi4, f_pi2, f_pi, f_3pi2))
+    f1 = f0 - f_pi
+    f2 = f_pi2 - f_3pi2
+    gamma = 0.5 * np.sqrt(f1 * f1 + f2 * f2)
+    varphi = np.arctan2(f1, f2) - theta
+    offset = 0.25 * (f0 + f_pi + f_pi2 + f_3pi2)
+    f3 = 0.5 * (f0 + f_pi - 2 * offset)
+    f4 = f_pi4 - offset - gamma * np.sin(theta + np.pi / 4 + varphi)
+    kappa = np.sqrt(f3 * f3 + f4 * f4)
+    xi = np.arctan2(f3, f4) - 2 * theta
+    curve = lambda p: kappa * np.sin(2 * p + xi) + gamma * np.sin(p + varphi) + offset
+    grid = np.linspace(0.0, 2 * np.pi, 1440, endpoint=False)
+    vals = curve(grid[:, None]) if theta.ndim else curve(grid)
+    p = grid[np.argmin(vals, axis=0)]
+    for _ in range(4):
+        d1 = 2 * kappa * np.cos(2 * p + xi) + gamma * np.cos(p + varphi)
+        d2 = -4 * kappa * np.sin(2 * p + xi) - gamma * np.sin(p + varphi)
+        step = np.where(d2 > 1e-300, d1 / np.where(d2 > 1e-300, d2, 1.0), 0.0)
+        p = p - np.clip(step, -0.01, 0.01)
+    shift = np.mod(p - theta + np.pi, 2 * np.pi) - np.pi
+    return shift, curve(p)
+
+
 def agents(cost_batched, x0, rng, agent_num=64, max_iter=10000, tol=1e-10, double_period=False, agent_lifetime=1000,
            exploration_rate=0.2, agent_randomization_rate=0.2, randomization_rate=0.3, radius=1.0, convergence_length=20,
-           scale_by_cost=True, callback=None):
+           scale_by_cost=True, callback=None, five_point=False):
     """The reference's AGENTS engine (optimization_engines/AGENTS.cpp:60-938), three-point rule (Frobenius cost; doubled period for
     the VQE energy, :333-335): ``agent_num`` parameter vectors walk independently -- per iteration every agent draws ONE of its
     parameters and jumps to the minimum of the sinusoid the cost is along it (exact, no line search: the new cost is offset -
@@ -190,7 +218,8 @@ def agents(cost_batched, x0, rng, agent_num=64, max_iter=10000, tol=1e-10, doubl
     Arranged for the device: the two shifted parameter sets of all agents are ONE cost_batched call of 2 x agent_num rows per
     iteration (the reference issues two), and the perturbed agents of a census are re-scored by one batched call instead of one
     single evaluation each. Stops when an agent is below ``tol`` or the recorded minimum stalls over ``convergence_length``
-    censuses (:849-866). Returns (x, f, iterations, evaluations)."""
+    censuses (:849-866). ``five_point``: the rule for costs quadratic in the trace (Hilbert-Schmidt test, :335, :536-660): four
+    shifted sets per agent instead of two, still one batch per iteration. Returns (x, f, iterations, evaluations)."""
     x0 = np.array(x0, dtype=np.float64).reshape(-1)
     P = x0.size
     if P == 0:
@@ -216,16 +245,25 @@ def agents(cost_batched, x0, rng, agent_num=64, max_iter=10000, tol=1e-10, doubl
     it = 0
     for it in range(max_iter):
         idx = rng.integers(0, P, A)
-        S = np.concatenate([X, X])
-        S[rows, idx] += shift
-        S[A + rows, idx] += 2 * shift
-        vals = np.asarray(cost_batched(S))
-        n_eval += 2 * A
-        f_half, f_full = vals[:A], vals[A:]
-        a_cos, offset = (F - f_full) / 2, (F + f_full) / 2
-        a_sin = offset - f_half
-        X[rows, idx] += cosine_updates(F, f_half, f_full, double_period)
-        F = offset - np.sqrt(a_sin * a_sin + a_cos * a_cos)
+        if five_point:
+            S = np.concatenate([X, X, X, X])
+            for k, sh in enumerate((np.pi / 4, np.pi / 2, np.pi, 3 * np.pi / 2)):
+                S[k * A + rows, idx] += sh
+            vals = np.asarray(cost_batched(S))
+            n_eval += 4 * A
+            upd, F = five_point_updates(X[rows, idx], F, vals[:A], vals[A:2 * A], vals[2 * A:3 * A], vals[3 * A:])
+            X[rows, idx] += upd
+        else:
+            S = np.concatenate([X, X])
+            S[rows, idx] += shift
+            S[A + rows, idx] += 2 * shift
+            vals = np.asarray(cost_batched(S))
+            n_eval += 2 * A
+            f_half, f_full = vals[:A], vals[A:]
+            a_cos, offset = (F - f_full) / 2, (F + f_full) / 2
+            a_sin = offset - f_half
+            X[rows, idx] += cosine_updates(F, f_half, f_full, double_period)
+            F = offset - np.sqrt(a_sin * a_sin + a_cos * a_cos)
         census = it % agent_lifetime == 0
         if census:
             F = np.asarray(cost_batched(X), dtype=np.float64).copy()  # the predicted costs drift by rounding: re-evaluate (:700-705)

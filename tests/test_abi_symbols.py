@@ -377,6 +377,18 @@ def test_cosine_engine_with_oracle_callables(port):
     Xs, vs = seen[census - 1]  # the shifted batch of the same iteration: rows 0..7 are +pi/2 of the state BEFORE the update
     assert np.abs(vc - np.array([min(port.cost(d, Xs[a] + t * (Xs[8 + a] - Xs[a]) * 2 / np.pi, U, n, 0) for t in scan) for a in range(8)])).max() < 1e-4
     assert (vc <= np.array([port.cost(d, 2 * Xs[a] - Xs[8 + a], U, n, 0) for a in range(8)]) + 1e-12).all()
+    # the five-point rule for the Hilbert-Schmidt test (AGENTS.cpp:536-660): along one parameter the cost is
+    # kappa sin(2 p + xi) + gamma sin(p + varphi) + offset; the minimum of the fitted curve is the minimum of the oracle's cost
+    hs = lambda v: port.cost(d, v, U, n, 3)
+    for i in (0, 1, 7, P - 1):
+        e = np.zeros(P)
+        e[i] = 1.0
+        upd, pred = sq.optimize.five_point_updates(x[i], *[hs(x + s * e) for s in (0, np.pi / 4, np.pi / 2, np.pi, 3 * np.pi / 2)])
+        assert abs(hs(x + float(upd) * e) - float(pred)) < 1e-12 and float(pred) <= min(hs(x + t * e) for t in scan) + 1e-12
+    trace = []
+    xh, fh, _, _ = sq.optimize.agents(lambda X: np.array([hs(v) for v in X]), x, np.random.default_rng(3), agent_num=8, max_iter=120, tol=1e-8,
+                                      agent_lifetime=30, five_point=True, callback=lambda k, xx, ff: trace.append(ff))
+    assert fh < 0.5 * hs(x) and abs(fh - hs(xh)) < 1e-12 and all(b <= a for a, b in zip(trace, trace[1:]))
 
 
 def test_constant_subcircuits_become_dense_kernels():

@@ -1122,6 +1122,12 @@ def test_cosine_engine_on_the_device(sq, port):
     dec.set_Optimizer("AGENTS_COMBINED")
     err2 = dec.Start_Decomposition()
     assert err2 <= err and close_rel(dec.Optimization_Problem(dec.get_Optimized_Parameters()), err2, 1e-9)
+    # the Hilbert-Schmidt test through AGENTS' five-point rule (AGENTS.cpp:335, 536-660); COSINE refuses it as in the reference
+    dec.set_Cost_Function_Variant(3)
+    dec.set_Optimizer("AGENTS")
+    err_hs = dec.Start_Decomposition()
+    assert err_hs < 0.5 and close_rel(dec.Optimization_Problem(dec.get_Optimized_Parameters()), err_hs, 1e-9)
+    dec.set_Cost_Function_Variant(0)
     dec.set_Optimizer("GRAD_DESCEND")
     err3 = dec.Start_Decomposition()
     assert err3 < 0.5 and close_rel(dec.Optimization_Problem(dec.get_Optimized_Parameters()), err3, 1e-9)
