@@ -228,7 +228,8 @@ class Variational_Quantum_Eigensolver:
                                            exploration_rate=float(cfg.get("agent_exploration_rate", 0.2)),
                                            agent_randomization_rate=float(cfg.get("agent_randomization_rate", 0.2)),
                                            radius=float(cfg.get("Randomized_Radius", 1.0)),
-                                           convergence_length=int(cfg.get("convergence_length_agent", cfg.get("convergence_length", 20))), scale_by_cost=False)
+                                           convergence_length=int(cfg.get("convergence_length_agent", cfg.get("convergence_length", 20))), scale_by_cost=False,
+                                           five_point=int(cfg.get("linesearch_points_agent", cfg.get("linesearch_points", 3))) == 5)  # AGENTS.cpp:211-221, 335
             x0 = x
         if alg in ("BFGS", "GRAD_DESCEND", "AGENTS_COMBINED"):
             # GRAD_DESCEND / the second stage of AGENTS_COMBINED (AGENTS.cpp:914-933): steepest descent, same batched line search
