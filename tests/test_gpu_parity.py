@@ -1241,6 +1241,20 @@ def test_vqe_start_optimization(sq, port):
         results[alg] = ef
     # e_min < 0: both get within 30 % of the exact ground energy with a 3-layer ansatz (the oracle-driven runs end at 80 %)
     assert max(results.values()) < 0.7 * e_min
+    # AGENTS with linesearch_points = 5 (AGENTS.cpp:211-221, 335): the five-point rule, exact also for the phase parameters of a
+    # U3 ansatz (HEA), where the doubled-period three-point rule is only a model
+    vqe5 = sq.Variational_Quantum_Eigensolver(Hm, n, config={"max_inner_iterations": 200, "agent_num": 16, "agent_lifetime": 50, "linesearch_points": 5, "seed": 4})
+    vqe5.set_Ansatz("HEA")
+    vqe5.Generate_Circuit(2, 1)
+    x5 = H.random_params(vqe5.get_Parameter_Num(), seed=11)
+    vqe5.set_Optimizer("AGENTS")
+    vqe5.set_Optimized_Parameters(x5)
+    e5 = vqe5.Start_Optimization()
+    d5, _ = vqe5.get_Circuit().descriptors()
+    psi0 = np.zeros(1 << n, dtype=np.complex128)
+    psi0[0] = 1
+    assert close_rel(e5, port.vqe_energy(d5, vqe5.get_Optimized_Parameters(), psi0, ip, ix, dat), 1e-10)
+    assert e_min - 1e-9 <= e5 < vqe5.Optimization_Problem(x5) - 1.0
     with pytest.raises(Exception):
         vqe.set_Optimizer("BAYES_OPT")
 
