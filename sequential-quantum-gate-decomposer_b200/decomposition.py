@@ -208,8 +208,9 @@ class N_Qubit_Decomposition_custom:
         "GRAD_DESCEND": steepest descent with the batched line search (Grad_Descend, common/grad_descend.cpp:459-480: d = -g);
         "AGENTS_COMBINED": AGENTS, then GRAD_DESCEND from its result (AGENTS.cpp:914-933). The
         reference's other engines (BAYES_OPT, BFGS2 ...) stay with the reference: they run over this cost path through integration/."""
-        if optimizer not in ("BFGS", "ADAM", "COSINE", "AGENTS", "GRAD_DESCEND", "AGENTS_COMBINED"):
-            raise Exception("set_Optimizer: '%s' is not provided by this package (BFGS, ADAM, COSINE, AGENTS, GRAD_DESCEND, AGENTS_COMBINED); use the reference's engines "
+        if optimizer not in ("BFGS", "ADAM", "COSINE", "AGENTS", "GRAD_DESCEND", "AGENTS_COMBINED", "GRAD_DESCEND_PARAMETER_SHIFT_RULE"):
+            raise Exception("set_Optimizer: '%s' is not provided by this package (BFGS, ADAM, COSINE, AGENTS, GRAD_DESCEND, AGENTS_COMBINED, "
+                            "GRAD_DESCEND_PARAMETER_SHIFT_RULE); use the reference's engines "
                             "over the GPU cost path through the drop-in of integration/" % optimizer)
         self._optimizer = optimizer
 
@@ -293,7 +294,7 @@ class N_Qubit_Decomposition_custom:
                 check_for_convergence=bool(cfg.get("check_for_convergence", cfg.get("check_for_convergence_cosine", 1))),
                 # the shift batch from one adjoint sweep instead of 2 x batch_size forward passes (sqgpu_cost_shifted_batched):
                 # measured 6.1x at n = 10, 1.9x at n = 8, 0.6x at n = 4 (profiles/r2_shift_engines.jsonl) -- from 7 qubits on
-                cost_shifted=eng.cost_shifted_batched if int(cfg.get("cosine_shift_sweep", self.qbit_num >= 7)) else None)
+                cost_shifted=eng.cost_shifted_batched if self.accelerator_num == 1 and int(cfg.get("cosine_shift_sweep", self.qbit_num >= 7)) else None)
             self._num_evaluations += ne
             return x, f
 
@@ -301,6 +302,18 @@ class N_Qubit_Decomposition_custom:
             f, g = eng.cost_grad_batched(x.reshape(1, -1))
             return float(f[0]), g[0]
 
+        if self._optimizer == "GRAD_DESCEND_PARAMETER_SHIFT_RULE":
+            cfg = self.config
+            sweep_ok = self._variant in (0, 1, 2, 3, 9) and self.accelerator_num == 1
+            x, f, _, ne = optimize.grad_descend_shift_rule(
+                eng.cost_batched, rng.random(P) * 2 * np.pi if x0 is None else x0, rng,
+                batch_size=min(P, int(cfg.get("batch_size_grad_descend_shift_rule", cfg.get("batch_size", min(64, P))))),
+                max_iter=int(cfg.get("max_inner_iterations_grad_descend_shift_rule", cfg.get("max_inner_iterations", 2000))),
+                tol=float(cfg.get("optimization_tolerance_grad_descend_shift_rule", tol)),
+                eta=float(cfg.get("eta_grad_descend_shift_rule", cfg.get("eta", 1e-3))), use_line_search=bool(int(cfg.get("use_line_search", 1))),
+                cost_shifted=eng.cost_shifted_batched if sweep_ok and int(cfg.get("cosine_shift_sweep", self.qbit_num >= 7)) else None)
+            self._num_evaluations += ne
+            return x, f
         if self._optimizer == "GRAD_DESCEND":  # GRAD_DESCEND.cpp:126-150: Grad_Descend from the guess
             x, f, _, ne = optimize.lbfgs(cost_grad, eng.line_search_batched, rng.random(P) * 2 * np.pi if x0 is None else np.asarray(x0, dtype=np.float64),
                                          max_iter=int(self.config.get("max_inner_iterations_grad_descend", self.config.get("max_inner_iterations", 2000))),

@@ -176,6 +176,65 @@ def cosine(cost_batched, x0, rng, batch_size=None, max_iter=2000, tol=1e-10, dou
     return x, f, it, n_eval
 
 
+def grad_descend_shift_rule(cost_batched, x0, rng, batch_size=None, max_iter=2000, tol=1e-10, eta=1e-3, use_line_search=True,
+                            line_points=128, callback=None, cost_shifted=None):
+    """The reference's GRAD_DESCEND_PARAMETER_SHIFT_RULE engine (optimization_engines/GRAD_DESCEND_PARAMETER_SHIFT_RULE.cpp:
+    60-400): per iteration ``batch_size`` distinct random parameters get the gradient component f(+pi/4) - f(-pi/4), scaled by
+    ``eta``; the step along it is either taken as it is or (default) scaled by the best of ``line_points`` fractions k /
+    line_points, evaluated as one batch (:296-325, already batched in the reference). Same update and stopping rules; the two
+    shifted batches are one cost_batched call -- or, with ``cost_shifted`` (Engine.cost_shifted_batched), one adjoint sweep that
+    returns both shifted costs of every parameter. Returns (x, f, iterations, evaluations)."""
+    x = np.array(x0, dtype=np.float64).reshape(-1)
+    P = x.size
+    bs = min(64, P) if batch_size is None else int(batch_size)
+    if bs > P:
+        raise Exception("grad_descend_shift_rule: batch size should be lower or equal to the number of free parameters")
+    f = float(np.asarray(cost_batched(x.reshape(1, -1)))[0])
+    n_eval = 1
+    if P == 0:
+        return x, f, 0, n_eval
+    fractions = np.arange(line_points, dtype=np.float64) / line_points  # includes 0: the current point (:300-306)
+    hist = np.zeros(100)
+    hist_mean, hist_idx = 0.0, 0
+    it = 0
+    for it in range(1, max_iter + 1):
+        idx = rng.choice(P, size=bs, replace=False)
+        if cost_shifted is not None:
+            both = np.asarray(cost_shifted(x.reshape(1, -1), (np.pi / 4, -np.pi / 4))[1])
+            f_plus, f_minus = both[0, 0, idx], both[1, 0, idx]
+            n_eval += 1
+        else:
+            X = np.repeat(x.reshape(1, -1), 2 * bs, axis=0)
+            X[np.arange(bs), idx] += np.pi / 4
+            X[bs + np.arange(bs), idx] -= np.pi / 4
+            vals = np.asarray(cost_batched(X))
+            f_plus, f_minus = vals[:bs], vals[bs:]
+            n_eval += 2 * bs
+        upd = (f_plus - f_minus) * eta
+        if use_line_search:
+            L = np.repeat(x.reshape(1, -1), line_points, axis=0)
+            L[:, idx] -= fractions[:, None] * upd[None, :]
+            lv = np.asarray(cost_batched(L))
+            n_eval += line_points
+            k = int(np.argmin(lv))
+            x, f = L[k].copy(), float(lv[k])
+        else:
+            x[idx] -= upd
+            f = float(np.asarray(cost_batched(x.reshape(1, -1)))[0])
+            n_eval += 1
+        if callback is not None:
+            callback(it, x, f)
+        if f < tol:
+            break
+        hist_mean += (f - hist[hist_idx]) / hist.size
+        hist[hist_idx] = f
+        hist_idx = (hist_idx + 1) % hist.size
+        var = np.sqrt(((hist - hist_mean) ** 2).sum()) / hist.size
+        if hist_mean != 0 and abs(hist_mean - f) < 1e-7 and var / hist_mean < 1e-7:
+            break
+    return x, f, it, n_eval
+
+
 def five_point_updates(theta, f0, f_pi4, f_pi2, f_pi, f_3pi2):
     """The five-point rule of AGENTS for costs quadratic in the trace (Hilbert-Schmidt test; AGENTS.cpp:583-660): along one
     parameter f(p) = kappa sin(2 p + xi) + gamma sin(p + varphi) + offset, fixed by the value at p = theta and at the shifts

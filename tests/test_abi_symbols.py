@@ -297,7 +297,7 @@ def test_lbfgs_host_loop_with_oracle_callables(port):
     dec = sq.N_Qubit_Decomposition_adaptive(U, level_limit_max=3, level_limit_min=1)
     with pytest.raises(Exception):
         dec.set_Optimizer("BAYES_OPT")
-    for name in ("COSINE", "AGENTS", "AGENTS_COMBINED", "GRAD_DESCEND", "ADAM", "BFGS"):
+    for name in ("COSINE", "AGENTS", "AGENTS_COMBINED", "GRAD_DESCEND", "GRAD_DESCEND_PARAMETER_SHIFT_RULE", "ADAM", "BFGS"):
         dec.set_Optimizer(name)
     with pytest.raises(Exception):
         dec.get_Optimized_Parameters()
@@ -377,6 +377,19 @@ def test_cosine_engine_with_oracle_callables(port):
     Xs, vs = seen[census - 1]  # the shifted batch of the same iteration: rows 0..7 are +pi/2 of the state BEFORE the update
     assert np.abs(vc - np.array([min(port.cost(d, Xs[a] + t * (Xs[8 + a] - Xs[a]) * 2 / np.pi, U, n, 0) for t in scan) for a in range(8)])).max() < 1e-4
     assert (vc <= np.array([port.cost(d, 2 * Xs[a] - Xs[8 + a], U, n, 0) for a in range(8)]) + 1e-12).all()
+    # GRAD_DESCEND_PARAMETER_SHIFT_RULE (…SHIFT_RULE.cpp:249-325): its gradient component f(+pi/4) - f(-pi/4) is sqrt(2) times the
+    # oracle's derivative for the Frobenius cost, the line search (fraction 0 included) never lets the cost rise
+    g_ref = port.cost_grad(d, P, x, U, n, 0)[1]
+    for i in (0, 7, P - 1):
+        e = np.zeros(P)
+        e[i] = 1.0
+        assert abs((cost(x + np.pi / 4 * e) - cost(x - np.pi / 4 * e)) / np.sqrt(2) - g_ref[i]) < 1e-12
+    trace = []
+    xp, fp, itp, nep = sq.optimize.grad_descend_shift_rule(cost_batched, x, np.random.default_rng(3), batch_size=16, max_iter=40, tol=1e-8, eta=1.0,
+                                                           line_points=32, callback=lambda k, xx, ff: trace.append(ff))
+    assert all(b <= a for a, b in zip(trace, trace[1:])) and fp < 0.3 and abs(fp - cost(xp)) < 1e-12 and nep == 1 + 40 * (32 + 32)
+    xq, fq, _, _ = sq.optimize.grad_descend_shift_rule(cost_batched, x, np.random.default_rng(3), batch_size=16, max_iter=5, tol=1e-8, eta=0.05, use_line_search=False)
+    assert fq < cost(x)
     # the five-point rule for the Hilbert-Schmidt test (AGENTS.cpp:536-660): along one parameter the cost is
     # kappa sin(2 p + xi) + gamma sin(p + varphi) + offset; the minimum of the fitted curve is the minimum of the oracle's cost
     hs = lambda v: port.cost(d, v, U, n, 3)

@@ -1073,6 +1073,10 @@ def test_shifted_costs_large_executors(sq, n, opt, cols):
         a = sq.optimize.cosine(e.cost_batched, x, np.random.default_rng(2), batch_size=32, max_iter=3, tol=0)
         b = sq.optimize.cosine(e.cost_batched, x, np.random.default_rng(2), batch_size=32, max_iter=3, tol=0, cost_shifted=e.cost_shifted_batched)
         assert np.abs(a[0] - b[0]).max() < 1e-8 and close_rel(a[1], b[1], 1e-10) and b[3] < a[3]
+        a = sq.optimize.grad_descend_shift_rule(e.cost_batched, x, np.random.default_rng(2), batch_size=32, max_iter=3, tol=0, eta=1.0, line_points=16)
+        b = sq.optimize.grad_descend_shift_rule(e.cost_batched, x, np.random.default_rng(2), batch_size=32, max_iter=3, tol=0, eta=1.0, line_points=16,
+                                                cost_shifted=e.cost_shifted_batched)
+        assert np.abs(a[0] - b[0]).max() < 1e-8 and close_rel(a[1], b[1], 1e-10) and b[3] < a[3] and b[1] < e.cost_batched(x.reshape(1, -1))[0]
     e.close()
 
 
