@@ -169,8 +169,8 @@ class Variational_Quantum_Eigensolver:
 
     # ---- optimisation over the hot path --------------------------------------------------------------
     def set_Optimizer(self, alg="COSINE"):
-        if alg not in ("COSINE", "AGENTS", "BFGS", "GRAD_DESCEND", "AGENTS_COMBINED"):
-            raise Exception("set_Optimizer: '%s' is not provided by this package (COSINE, AGENTS, BFGS, GRAD_DESCEND, AGENTS_COMBINED); use the reference's "
+        if alg not in ("COSINE", "AGENTS", "BFGS", "GRAD_DESCEND", "AGENTS_COMBINED", "GRAD_DESCEND_PARAMETER_SHIFT_RULE"):
+            raise Exception("set_Optimizer: '%s' is not provided by this package (COSINE, AGENTS, BFGS, GRAD_DESCEND, AGENTS_COMBINED, GRAD_DESCEND_PARAMETER_SHIFT_RULE); use the reference's "
                             "engines over the GPU energy path through the drop-in of integration/" % alg)
         self._optimizer = alg
 
@@ -213,6 +213,12 @@ class Variational_Quantum_Eigensolver:
                                            batch_size=min(P, int(cfg.get("batch_size_cosine", cfg.get("batch_size", min(64, P))))),
                                            max_iter=int(cfg.get("max_inner_iterations_cosine", max_iter)), tol=-np.inf, double_period=True,
                                            check_for_convergence=bool(cfg.get("check_for_convergence", 1)))
+
+        if alg == "GRAD_DESCEND_PARAMETER_SHIFT_RULE":  # …SHIFT_RULE.cpp:249-325 over the batched energy
+            x, f, it, ne = optimize.grad_descend_shift_rule(
+                eng.vqe_energy_batched, x0, rng, batch_size=min(P, int(cfg.get("batch_size_grad_descend_shift_rule", cfg.get("batch_size", min(64, P))))),
+                max_iter=int(cfg.get("max_inner_iterations_grad_descend_shift_rule", max_iter)), tol=-np.inf,
+                eta=float(cfg.get("eta_grad_descend_shift_rule", cfg.get("eta", 1e-3))), use_line_search=bool(int(cfg.get("use_line_search", 1))))
 
         def line_search(x, d, alphas):  # all trial step lengths of an iteration: one batched energy+gradient call
             e, g = eng.vqe_energy_grad_batched(x[None, :] + np.asarray(alphas)[:, None] * d[None, :])

@@ -1226,6 +1226,7 @@ def test_vqe_start_optimization(sq, port):
     for alg, cfg in (("BFGS", {"max_inner_iterations": 300}), ("COSINE", {"max_inner_iterations": 150, "batch_size": 16}),
                      ("AGENTS", {"max_inner_iterations": 300, "agent_num": 16, "agent_lifetime": 50}),
                      ("GRAD_DESCEND", {"max_inner_iterations": 300}),
+                     ("GRAD_DESCEND_PARAMETER_SHIFT_RULE", {"max_inner_iterations": 150, "batch_size": 16, "eta": 1.0}),
                      ("AGENTS_COMBINED", {"max_inner_iterations_agent": 100, "max_inner_iterations_grad_descend": 100, "agent_num": 16, "agent_lifetime": 50})):
         vqe = sq.Variational_Quantum_Eigensolver(Hm, n, config=dict(cfg, seed=4))
         vqe.set_Ansatz("HEA_ZYZ")
