@@ -168,6 +168,13 @@ class N_Qubit_Decomposition_custom:
         self.set_Gate_Structure(circ)
         self._optimized_parameters = np.asarray(params, dtype=np.float64).copy()
 
+    def get_QASM(self, adaptive_as_cry=True):
+        """the circuit at the optimised parameters as OpenQASM 2 source (the reference hands out a Qiskit circuit,
+        get_Qiskit_Circuit; this is the Qiskit-free counterpart, readable by qiskit.QuantumCircuit.from_qasm_str)"""
+        from . import qasm
+
+        return qasm.dumps(self._circuit, self.get_Optimized_Parameters(), adaptive_as_cry=adaptive_as_cry)
+
     def get_Project_Name(self):
         return getattr(self, "project_name", "")
 

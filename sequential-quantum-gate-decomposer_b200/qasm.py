@@ -148,3 +148,65 @@ def loads(text):
 def load(path):
     with open(path) as f:
         return loads(f.read())
+
+
+# ---- the way out: (Circuit, parameters) -> OpenQASM 2 ---------------------------------------------------------------------
+# (the reference exports through Qiskit, Qiskit_IO.get_Qiskit_Circuit, squander/IO_interfaces/Qiskit_IO.py:40-275; same
+# conventions as above, inverted: halved angles are doubled, "g q[control],q[target]")
+def _export_tables():
+    from . import abi
+
+    one = {abi.U3: ("u3", {0}), abi.U2: ("u2", set()), abi.U1: ("u1", set()), abi.RX: ("rx", {0}), abi.RY: ("ry", {0}), abi.RZ: ("rz", {0}),
+           abi.R: ("r", {0}), abi.H: ("h", set()), abi.X: ("x", set()), abi.Y: ("y", set()), abi.Z: ("z", set()), abi.S: ("s", set()),
+           abi.SDG: ("sdg", set()), abi.T: ("t", set()), abi.TDG: ("tdg", set()), abi.SX: ("sx", set()), abi.SXDG: ("sxdg", set())}
+    ctrl = {abi.CNOT: ("cx", set()), abi.CZ: ("cz", set()), abi.CH: ("ch", set()), abi.CU: ("cu", {0}), abi.CRY: ("cry", {0}),
+            abi.CRX: ("crx", {0}), abi.CRZ: ("crz", {0}), abi.CP: ("cp", set())}
+    two = {abi.SWAP: ("swap", set()), abi.RXX: ("rxx", {0}), abi.RYY: ("ryy", {0}), abi.RZZ: ("rzz", {0})}
+    return one, ctrl, two
+
+
+def dumps(circuit, parameters, adaptive_as_cry=False):
+    """OpenQASM 2 source of ``circuit`` at ``parameters`` (nested blocks are flattened). ``loads(dumps(c, p))`` returns the flat
+    structure of c and p again. Gates outside qelib1 (GENERAL, CROT, CR, SYC) raise ValueError; the adaptive gate is a CRY
+    (gates/Adaptive.cpp) and is written as one with ``adaptive_as_cry`` (the structure then reads back with CRY in its place)."""
+    from . import abi
+
+    one, ctrl, two = _export_tables()
+    p = np.asarray(parameters, dtype=np.float64).reshape(-1)
+    if p.size != circuit.get_Parameter_Num():
+        raise ValueError("Number of free parameters should be %d, but got %d" % (circuit.get_Parameter_Num(), p.size))
+    lines = ["OPENQASM 2.0;", 'include "qelib1.inc";', "qreg q[%d];" % circuit.qbit_num]
+    pos = 0
+
+    def args(n, halved):
+        nonlocal pos
+        vals = [repr(float(p[pos + i] * 2 if i in halved else p[pos + i])) for i in range(n)]
+        pos += n
+        return "(" + ",".join(vals) + ")" if n else ""
+
+    for g in circuit._flat_gates():
+        t = g.type
+        if t == abi.ADAPTIVE and adaptive_as_cry:
+            t = abi.CRY
+        n = abi.PARAM_COUNT[g.type]
+        if t in one:
+            name, halved = one[t]
+            lines.append("%s%s q[%d];" % (name, args(n, halved), g.target))
+        elif t in ctrl:
+            name, halved = ctrl[t]
+            lines.append("%s%s q[%d],q[%d];" % (name, args(n, halved), g.control, g.target))
+        elif t in two:
+            name, halved = two[t]
+            lines.append("%s%s q[%d],q[%d];" % (name, args(n, halved), g.target2, g.target))
+        elif t == abi.CCX:
+            lines.append("ccx q[%d],q[%d],q[%d];" % (g.control2, g.control, g.target))
+        elif t == abi.CSWAP:
+            lines.append("cswap q[%d],q[%d],q[%d];" % (g.control, g.target2, g.target))
+        else:
+            raise ValueError("gate %s has no OpenQASM 2 (qelib1) counterpart" % abi.GATE_NAMES.get(g.type, g.type))
+    return "\n".join(lines) + "\n"
+
+
+def dump(circuit, parameters, path, **kw):
+    with open(path, "w") as f:
+        f.write(dumps(circuit, parameters, **kw))

@@ -222,3 +222,35 @@ def test_import_qiskit_circuit_without_qiskit(tmp_path, port):
         sq.N_Qubit_Decomposition_custom(np.eye(8, dtype=np.complex128)).import_Qiskit_Circuit(src)
     with pytest.raises(Exception):
         dec.import_Qiskit_Circuit(42)
+
+
+def test_qasm_export_roundtrip(port):
+    """qasm.dumps is the inverse of qasm.loads on every gate family of qelib1 (angle doubling, operand order of controlled,
+    two-target and three-qubit gates): the structure and the parameters read back unchanged, and the oracle's matrices of the
+    original and of the re-imported circuit are the same"""
+    import helpers as H
+
+    sq = H.sq
+    names = [x for x in H.ONE_Q + H.CTRL + H.TWO_T + ["CCX", "CSWAP"] if x not in ("CROT", "CR", "SYC", "adaptive")]
+    c = H.random_circuit(5, 120, seed=8, names=names, nested=True)
+    x = H.random_params(c.get_Parameter_Num(), seed=4)
+    text = sq.qasm.dumps(c, x)
+    c2, x2 = sq.qasm.loads(text)
+    key = lambda circ: [tuple(int(r[f]) for f in ("type", "target", "control", "target2", "control2", "param_start", "n_params")) for r in circ.descriptors()[0]]
+    assert key(c2) == key(c.get_Flat_Circuit()) and np.array_equal(x2, x) and len(c.get_Gate_Nums()) >= 20
+    I = np.eye(32, dtype=np.complex128)
+    d1, p1 = c.descriptors()
+    d2, p2 = c2.descriptors()
+    assert np.abs(port.apply_circuit(d1, x, I, p1) - port.apply_circuit(d2, x2, I, p2)).max() < 1e-14
+    a = H.adaptive_circuit(3, 1)
+    xa = H.random_params(a.get_Parameter_Num(), seed=1)
+    with pytest.raises(ValueError):
+        sq.qasm.dumps(a, xa)
+    ca, xb = sq.qasm.loads(sq.qasm.dumps(a, xa, adaptive_as_cry=True))
+    assert np.array_equal(xa, xb) and "CRY" in ca.get_Gate_Nums() and "Adaptive" not in ca.get_Gate_Nums()
+    da, pa = a.descriptors()
+    db, pb = ca.descriptors()
+    I8 = np.eye(8, dtype=np.complex128)
+    assert np.abs(port.apply_circuit(da, xa, I8, pa) - port.apply_circuit(db, xb, I8, pb)).max() < 1e-14
+    with pytest.raises(ValueError):
+        sq.qasm.dumps(c, x[:-1])
