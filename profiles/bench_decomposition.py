@@ -21,7 +21,6 @@ ENGINES = [("BFGS", {}), ("ADAM", {}), ("COSINE", {"max_inner_iterations": 1500}
 for name, cfg in ENGINES:
     dec = sq.N_Qubit_Decomposition_adaptive(Uct, level_limit_max=3, level_limit_min=3, config=dict(cfg, optimization_tolerance=1e-6, compress=0, finalize=0))
     dec.set_Optimizer(name)
-    dec.Optimization_Problem(np.zeros(0)) if False else None
     t0 = time.perf_counter()
     err = dec.Start_Decomposition()
     dt = time.perf_counter() - t0
