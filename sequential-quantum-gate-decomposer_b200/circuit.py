@@ -207,6 +207,71 @@ class Circuit:
             out._add(g)
         return out
 
+    # ---- the inverse structure and multiplication from the right ---------------------------------------------------------
+    # parameter maps of the inverse gates, each checked against the oracle's kernels (tests/test_host_logic.py): for the gate
+    # at parameters p the inverse is the SAME gate type at sign * p[perm] + offset
+    _INV_RULES = {
+        abi.U3: ([0, 2, 1], [-1, -1, -1], [0, 0, 0]), abi.CU: ([0, 2, 1, 3], [-1, -1, -1, -1], [0, 0, 0, 0]),
+        abi.U2: ([1, 0], [-1, -1], [-np.pi, np.pi]), abi.R: ([0, 1], [-1, 1], [0, 0]), abi.CR: ([0, 1], [-1, 1], [0, 0]),
+        abi.CROT: ([0, 1], [-1, 1], [0, 0]),
+    }
+    _INV_TYPE = {abi.S: abi.SDG, abi.SDG: abi.S, abi.T: abi.TDG, abi.TDG: abi.T, abi.SX: abi.SXDG, abi.SXDG: abi.SX}
+    # Sycamore gate fSim(pi/2, pi/6) (kernels/apply_dedicated_gate_kernel_to_input.cpp:582-640), symmetric in its two qubits
+    _SYC = np.array([[1, 0, 0, 0], [0, 0, -1j, 0], [0, -1j, 0, 0], [0, 0, 0, np.exp(-1j * np.pi / 6)]], dtype=np.complex128)
+
+    def get_Inverse(self):
+        """(inverse circuit, map) with inverse(map(p)) @ self(p) = identity for every parameter vector p: the gates in reverse
+        order, each replaced by its inverse -- the same gate type at mapped parameters (negated angles, U3's phi and lambda
+        exchanged, ...), S / T / SX exchanged with their daggers, GENERAL and SYC as GENERAL gates with the adjoint matrix.
+        ``map(p)`` returns the parameter vector of the inverse circuit. Cached per structure."""
+        key = self.structure_key()
+        if getattr(self, "_inverse_cache", None) is not None and self._inverse_cache[0] == key:
+            return self._inverse_cache[1], self._inverse_cache[2]
+        gates, starts, pos = list(self._flat_gates()), [], 0
+        for g in gates:
+            starts.append(pos)
+            pos += g.n_params
+        inv = Circuit(self.qbit_num, self._device)
+        src, sign, off = [], [], []
+        for g, st in zip(reversed(gates), reversed(starts)):
+            if g.type == abi.GENERAL:
+                inv._add(_Gate(abi.GENERAL, qubits=list(g.qubits), matrix=np.ascontiguousarray(g.matrix.conj().T)))
+                continue
+            if g.type == abi.SYC:
+                inv._add(_Gate(abi.GENERAL, qubits=sorted([g.target, g.control]), matrix=np.ascontiguousarray(self._SYC.conj().T)))
+                continue
+            inv._add(_Gate(self._INV_TYPE.get(g.type, g.type), g.target, g.control, g.target2, g.control2, g.qubits, g.matrix))
+            n = g.n_params
+            perm, sg, of = self._INV_RULES.get(g.type, (list(range(n)), [-1] * n, [0] * n))
+            src += [st + q for q in perm]
+            sign += sg
+            off += of
+        src, sign, off = np.array(src, dtype=np.int64), np.array(sign, dtype=np.float64), np.array(off, dtype=np.float64)
+
+        def pmap(parameters):
+            q = np.asarray(parameters, dtype=np.float64).reshape(-1)
+            if q.size != pos:
+                raise Exception("Number of free parameters should be %d, but got %d" % (pos, q.size))
+            return sign * q[src] + off if pos else np.zeros(0)
+
+        self._inverse_cache = (key, inv, pmap)
+        return inv, pmap
+
+    def apply_from_right(self, parameters, unitary):
+        """In place ``unitary <- unitary @ C(parameters)`` for a rows x 2^n complex128 array (Gates_block::apply_from_right,
+        Gates_block.cpp:717-760). On the device: U C = (C^dagger U^dagger)^dagger, and C^dagger = C^-1 is the inverse structure
+        of get_Inverse applied from the left to U^dagger (the gates must be unitary, as for the gradient)."""
+        u = np.asarray(unitary)
+        if u.dtype != np.complex128 or u.ndim != 2 or u.shape[1] != (1 << self.qbit_num):
+            raise Exception("apply_from_right: expected a rows x 2^qbit_num complex128 array")
+        for g in self._flat_gates():
+            if g.type == abi.GENERAL and np.abs(g.matrix.conj().T @ g.matrix - np.eye(g.matrix.shape[0])).max() > 1e-10:
+                raise Exception("apply_from_right: a GENERAL gate is not unitary")
+        inv, pmap = self.get_Inverse()
+        a = np.ascontiguousarray(u.conj().T)
+        inv.apply_to(pmap(parameters), a)
+        u[...] = a.conj().T
+
     def apply_to_list(self, inputs, parameters, parallel=1, is_f32=False):
         """apply_to on every array of ``inputs`` in place (Gates_block::apply_to_list, Gates_block.cpp:575-600): the gate
         structure and the kernel tables stay on the device between the inputs"""

@@ -1185,6 +1185,24 @@ def test_state_preparation_adaptive(sq, port):
         sq.N_Qubit_State_Preparation_adaptive([1, 0, 0, 0])
 
 
+def test_apply_from_right(sq, port):
+    """Circuit.apply_from_right (Gates_block::apply_from_right, Gates_block.cpp:717-760): U <- U C(parameters) on the device as
+    (C^-1 U^dagger)^dagger with the inverse structure; against U times the oracle's matrix of the circuit, square and rectangular
+    U, every gate family"""
+    n = 5
+    c = H.random_circuit(n, 80, seed=21, general_k=(2, 3), nested=True)
+    d, pool = c.descriptors()
+    x = H.random_params(c.get_Parameter_Num(), seed=2)
+    M = port.apply_circuit(d, x, np.eye(1 << n, dtype=np.complex128), pool)
+    for rows in (1 << n, 3):
+        U = np.ascontiguousarray(H.random_unitary(1 << n, seed=9)[:rows, :])
+        want = U @ M
+        c.apply_from_right(x, U)
+        assert np.abs(U - want).max() < ENTRY_TOL
+    with pytest.raises(Exception):
+        c.apply_from_right(x, np.zeros((4, 8), dtype=np.complex128))
+
+
 def test_second_renyi_entropy_on_device_state(sq, port):
     """get_Second_Renyi_Entropy of the circuit and VQE classes (Gates_block.cpp:3625-3650): the ansatz state comes from the
     device, the entropy equals the one of the oracle's state; a layer of single-qubit gates alone leaves a product state"""

@@ -254,3 +254,30 @@ def test_qasm_export_roundtrip(port):
     assert np.abs(port.apply_circuit(da, xa, I8, pa) - port.apply_circuit(db, xb, I8, pb)).max() < 1e-14
     with pytest.raises(ValueError):
         sq.qasm.dumps(c, x[:-1])
+
+
+def test_inverse_structure_against_oracle(port):
+    """Circuit.get_Inverse (the host half of apply_from_right, Gates_block.cpp:717-760): for a random nested circuit over EVERY
+    gate family (GENERAL and SYC included) the oracle's matrix of the inverse structure at the mapped parameters times the
+    matrix of the circuit is the identity; the inverse of the inverse reproduces the circuit's matrix; cached per structure"""
+    import helpers as H
+
+    n = 5
+    c = H.random_circuit(n, 150, seed=12, general_k=(1, 2, 3), nested=True)
+    assert len(c.get_Gate_Nums()) >= 30
+    x = H.random_params(c.get_Parameter_Num(), seed=7)
+    I = np.eye(1 << n, dtype=np.complex128)
+    d, pool = c.descriptors()
+    M = port.apply_circuit(d, x, I, pool)
+    inv, pmap = c.get_Inverse()
+    di, pooli = inv.descriptors()
+    Mi = port.apply_circuit(di, pmap(x), I, pooli)
+    assert np.abs(Mi @ M - I).max() < 1e-12 and np.abs(M @ Mi - I).max() < 1e-12
+    inv2, pmap2 = inv.get_Inverse()
+    d2, pool2 = inv2.descriptors()
+    assert np.abs(port.apply_circuit(d2, pmap2(pmap(x)), I, pool2) - M).max() < 1e-12
+    assert c.get_Inverse()[0] is inv
+    c.add_H(0)
+    assert c.get_Inverse()[0] is not inv
+    with pytest.raises(Exception):
+        pmap(x[:-1])
