@@ -168,6 +168,26 @@ class N_Qubit_Decomposition_custom:
         self.set_Gate_Structure(circ)
         self._optimized_parameters = np.asarray(params, dtype=np.float64).copy()
 
+    def Reorder_Qubits(self, qbit_list):
+        """Decomposition_Base::reorder_qubits (Decomposition_Base.cpp:910-950, Gate.cpp:1151-1200): the new qubit ``idx`` is the
+        old qubit ``qbit_list[idx]`` -- in every gate and in the rows and columns of the unitary, so the cost of a parameter
+        vector does not change"""
+        n = self.qbit_num
+        ql = [int(q) for q in qbit_list]
+        if sorted(ql) != list(range(n)):
+            raise Exception("Reorder_Qubits: Wrong number of qubits.")
+        if self.Umtx.shape[0] != self.Umtx.shape[1]:
+            raise Exception("Reorder_Qubits: the unitary should be square")
+        circ = self._circuit.Remap_Qbits({q: idx for idx, q in enumerate(ql)})
+        idx = np.arange(1 << n)
+        perm = np.zeros(1 << n, dtype=np.int64)
+        for new_bit, old_bit in enumerate(ql):
+            perm |= ((idx >> old_bit) & 1) << new_bit
+        U = np.empty_like(self.Umtx)
+        U[np.ix_(perm, perm)] = self.Umtx
+        self.set_Gate_Structure(circ)
+        self.set_Unitary(np.ascontiguousarray(U))
+
     def get_QASM(self, adaptive_as_cry=True):
         """the circuit at the optimised parameters as OpenQASM 2 source (the reference hands out a Qiskit circuit,
         get_Qiskit_Circuit; this is the Qiskit-free counterpart, readable by qiskit.QuantumCircuit.from_qasm_str)"""

@@ -281,3 +281,35 @@ def test_inverse_structure_against_oracle(port):
     assert c.get_Inverse()[0] is not inv
     with pytest.raises(Exception):
         pmap(x[:-1])
+
+
+def test_reorder_qubits_keeps_the_cost(port):
+    """Reorder_Qubits of the decomposition wrapper (Decomposition_Base.cpp:910-950): gates and unitary are relabelled together,
+    so the oracle's cost and gradient of a parameter vector are what they were; the permutation follows the reference's rule
+    (new qubit idx = old qubit qbit_list[idx])"""
+    import helpers as H
+
+    sq = H.sq
+    n = 3
+    U = H.random_unitary(1 << n, seed=6)
+    dec = sq.N_Qubit_Decomposition_adaptive(U, level_limit_max=2, level_limit_min=1)
+    dec.set_Gate_Structure(H.random_circuit(n, 40, seed=5, names=H.ONE_Q + H.CTRL + H.TWO_T + ["CCX", "CSWAP"]))
+    P = dec.get_Parameter_Num()
+    x = H.random_params(P, seed=9)
+    d0, p0 = dec.get_Circuit().descriptors()
+    f0, g0 = port.cost_grad(d0, P, x, U, n, 0, pool=p0)
+    dec.Reorder_Qubits([2, 0, 1])
+    d1, p1 = dec.get_Circuit().descriptors()
+    U1 = dec.get_Unitary()
+    f1, g1 = port.cost_grad(d1, P, x, U1, n, 0, pool=p1)
+    assert abs(f1 - f0) < 1e-13 and np.abs(g1 - g0).max() < 1e-13 and not np.array_equal(U1, U)
+    # the reference's index rule on one element: old index 0b011 (qubits 0, 1 set) -> new qubits 1, 2 set = 0b110
+    assert U1[0b110, 0] == U[0b011, 0]
+    # a gate on old qubit 2 now sits on new qubit 0
+    c = sq.Circuit(n)
+    c.add_RX(2)
+    dec.set_Gate_Structure(c)
+    dec.Reorder_Qubits([2, 0, 1])
+    assert int(dec.get_Circuit().descriptors()[0][0]["target"]) == 0
+    with pytest.raises(Exception):
+        dec.Reorder_Qubits([0, 1])
