@@ -185,6 +185,57 @@ class Circuit:
     def _gate_qubits(g):
         return [q for q in ([g.target, g.control, g.target2, g.control2] + list(g.qubits or [])) if q is not None and q >= 0]
 
+    def _item_qubits(self, it):
+        return set(it.get_Qbits()) if isinstance(it, Circuit) else {int(q) for q in self._gate_qubits(it)}
+
+    def get_Parents(self, gate):
+        """indices (in this block) of the gates that must run before gate ``gate``: for each of its qubits the closest earlier
+        gate on that qubit (Gates_block::determine_parents, Gates_block.cpp:3668-3720; qgd_Circuit.get_Parents)"""
+        idx = gate if isinstance(gate, (int, np.integer)) else self._items.index(gate)
+        need = self._item_qubits(self._items[idx])
+        out = []
+        for j in range(idx - 1, -1, -1):
+            hit = need & self._item_qubits(self._items[j])
+            if hit:
+                out.append(j)
+                need -= hit
+            if not need:
+                break
+        return sorted(out)
+
+    def get_Children(self, gate):
+        """indices of the gates that wait for gate ``gate``: for each of its qubits the closest later gate on that qubit
+        (Gates_block::determine_children)"""
+        idx = gate if isinstance(gate, (int, np.integer)) else self._items.index(gate)
+        need = self._item_qubits(self._items[idx])
+        out = []
+        for j in range(idx + 1, len(self._items)):
+            hit = need & self._item_qubits(self._items[j])
+            if hit:
+                out.append(j)
+                need -= hit
+            if not need:
+                break
+        return sorted(out)
+
+    def get_Parameter_Start_Index(self, gate=0):
+        """index of the first parameter of item ``gate`` of this block in the block's parameter vector"""
+        idx = gate if isinstance(gate, (int, np.integer)) else self._items.index(gate)
+        return sum(it.get_Parameter_Num() if isinstance(it, Circuit) else it.n_params for it in self._items[:idx])
+
+    def Extract_Parameters(self, parameters, gate=None):
+        """the slice of ``parameters`` that belongs to item ``gate`` of this block (Gate::extract_parameters); without ``gate``:
+        the block's own parameters, checked for their number"""
+        q = np.asarray(parameters, dtype=np.float64).reshape(-1)
+        if q.size != self.get_Parameter_Num():
+            raise Exception("Number of free parameters should be %d, but got %d" % (self.get_Parameter_Num(), q.size))
+        if gate is None:
+            return q.copy()
+        idx = gate if isinstance(gate, (int, np.integer)) else self._items.index(gate)
+        it = self._items[idx]
+        st = self.get_Parameter_Start_Index(idx)
+        return q[st:st + (it.get_Parameter_Num() if isinstance(it, Circuit) else it.n_params)].copy()
+
     def get_Qbits(self):
         """sorted list of the qubits the circuit acts on (Gates_block::get_involved_qubits)"""
         return sorted({int(q) for g in self._flat_gates() for q in self._gate_qubits(g)})

@@ -185,6 +185,22 @@ def test_circuit_queries_and_remap():
     assert r.get_Qbit_Num() == 5 and r.get_Qbits() == [2, 3] and r.get_Parameter_Num() == c.get_Parameter_Num()
     key = lambda circ: [tuple(int(x[f]) for f in ("type", "target", "control", "param_start", "n_params")) for x in circ.descriptors(nested=True)[0]]
     assert key(r) == key(want)
+    # dependency queries (Gates_block::determine_parents / determine_children): U3(0) -> CNOT(1,0) -> [RY(1) CRY(0,1)] -> U3(1)
+    assert c.get_Parents(0) == [] and c.get_Children(0) == [1]
+    assert c.get_Parents(1) == [0] and c.get_Children(1) == [2]
+    assert c.get_Parents(2) == [1] and c.get_Children(2) == [3] and c.get_Parents(inner) == [1]
+    assert c.get_Parents(3) == [2] and c.get_Children(3) == []
+    wide = sq.Circuit(4)
+    wide.add_H(0)
+    wide.add_H(2)
+    wide.add_CNOT(2, 0)
+    wide.add_X(3)
+    assert wide.get_Parents(2) == [0, 1] and wide.get_Children(0) == [2] and wide.get_Parents(3) == [] and wide.get_Children(2) == []
+    x = np.arange(c.get_Parameter_Num(), dtype=np.float64)
+    assert c.get_Parameter_Start_Index(2) == 3 and list(c.Extract_Parameters(x, 2)) == [3.0, 4.0] and list(c.Extract_Parameters(x, 3)) == [5.0, 6.0, 7.0]
+    assert list(c.Extract_Parameters(x, 1)) == [] and np.array_equal(c.Extract_Parameters(x), x)
+    with pytest.raises(Exception):
+        c.Extract_Parameters(x[:-1])
     with pytest.raises(Exception):
         c.Remap_Qbits({0: 1})  # target == control after the map
     with pytest.raises(Exception):
