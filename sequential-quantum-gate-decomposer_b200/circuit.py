@@ -188,6 +188,31 @@ class Circuit:
     def _item_qubits(self, it):
         return set(it.get_Qbits()) if isinstance(it, Circuit) else {int(q) for q in self._gate_qubits(it)}
 
+    def set_Qbit_Num(self, qbit_num):
+        """Gates_block::set_qbit_num: the register grows or shrinks; every gate must still fit"""
+        qbit_num = int(qbit_num)
+        used = self.get_Qbits()
+        if qbit_num < 1 or qbit_num > 30 or (used and used[-1] >= qbit_num):
+            raise Exception("set_Qbit_Num: a gate acts on a qubit outside the new register")
+        self.qbit_num = qbit_num
+        for it in self._items:
+            if isinstance(it, Circuit):
+                it.set_Qbit_Num(qbit_num)
+        self._version += 1
+        self._engine = None
+        self._engine_key = None
+
+    def __getstate__(self):
+        """pickling (qgd_Circuit_Wrapper __getstate__ / __setstate__): the gate structure travels, the device handle does not"""
+        st = dict(self.__dict__)
+        st["_engine"] = None
+        st["_engine_key"] = None
+        st.pop("_inverse_cache", None)
+        return st
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+
     def get_Parents(self, gate):
         """indices (in this block) of the gates that must run before gate ``gate``: for each of its qubits the closest earlier
         gate on that qubit (Gates_block::determine_parents, Gates_block.cpp:3668-3720; qgd_Circuit.get_Parents)"""

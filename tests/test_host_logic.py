@@ -201,6 +201,14 @@ def test_circuit_queries_and_remap():
     assert list(c.Extract_Parameters(x, 1)) == [] and np.array_equal(c.Extract_Parameters(x), x)
     with pytest.raises(Exception):
         c.Extract_Parameters(x[:-1])
+    import pickle
+
+    c2 = pickle.loads(pickle.dumps(c))
+    assert key(c2) == key(c) and c2.get_Gate_Nums() == c.get_Gate_Nums() and c2._engine is None
+    c2.set_Qbit_Num(6)
+    assert c2.get_Qbit_Num() == 6 and c2.get_Gate(2).get_Qbit_Num() == 6 and key(c2) == key(c)
+    with pytest.raises(Exception):
+        c2.set_Qbit_Num(1)
     with pytest.raises(Exception):
         c.Remap_Qbits({0: 1})  # target == control after the map
     with pytest.raises(Exception):
