@@ -541,6 +541,16 @@ class N_Qubit_Decomposition_adaptive(N_Qubit_Decomposition_custom):
         Then Compress_Circuit() (:372-520; config["compress"], default 1) and Finalize_Circuit() (the CRY -> CNOT / CZ
         finalisation, :530-640; config["finalize"], default 1), as the reference's start_decomposition does (:255-280).
         Afterwards: get_Circuit(), get_Optimized_Parameters(), get_Decomposition_Error(), get_CNOT_Count()."""
+        self.get_Initial_Circuit()
+        if int(self.config.get("compress", 1)) and self._current_minimum < self._optimization_tolerance:
+            self.Compress_Circuit()
+        if int(self.config.get("finalize", 1)):
+            self.Finalize_Circuit()
+        return self._current_minimum
+
+    def get_Initial_Circuit(self):
+        """get_initial_circuit (N_Qubit_Decomposition_adaptive.cpp:290-365): the first of the three phases of the decomposition,
+        callable on its own like Compress_Circuit and Finalize_Circuit -- the level search; returns the cost reached"""
         rng = np.random.default_rng(int(self.config.get("seed", 0)))
         best = None
         for level in range(self.level_limit_min, self.level_limit + 1):
@@ -555,10 +565,6 @@ class N_Qubit_Decomposition_adaptive(N_Qubit_Decomposition_custom):
                 break
         self._circuit, self._optimized_parameters, self._current_minimum, self.decomposition_level = best
         self._dirty = True
-        if int(self.config.get("compress", 1)) and self._current_minimum < self._optimization_tolerance:
-            self.Compress_Circuit()
-        if int(self.config.get("finalize", 1)):
-            self.Finalize_Circuit()
         return self._current_minimum
 
     def Compress_Circuit(self):
