@@ -195,6 +195,15 @@ class N_Qubit_Decomposition_custom:
 
         return qasm.dumps(self._circuit, self.get_Optimized_Parameters(), adaptive_as_cry=adaptive_as_cry)
 
+    def get_Qiskit_Circuit(self):
+        """the decomposition as a Qiskit QuantumCircuit (the reference goes through Qiskit_IO.get_Qiskit_Circuit): built from
+        get_QASM() when Qiskit is installed; this image has none, then the QASM source is what there is to hand out"""
+        try:
+            from qiskit import QuantumCircuit
+        except ImportError:
+            raise Exception("get_Qiskit_Circuit: Qiskit is not installed; get_QASM() returns the same circuit as OpenQASM 2 source")
+        return QuantumCircuit.from_qasm_str(self.get_QASM())
+
     def get_Project_Name(self):
         return getattr(self, "project_name", "")
 

@@ -148,6 +148,15 @@ def test_wrapper_data_format_methods(tmp_path, capsys):
     assert dec.get_Project_Name().endswith("proj")
     dec.export_Unitary("u.binary")
     assert (tmp_path / "proj_u.binary").exists()
+    # OpenQASM out of the wrapper (adaptive gates written as the CRY they are); a Qiskit object only where Qiskit exists
+    dec.set_Optimized_Parameters(np.concatenate([x, x]))
+    c_back, x_back = sq.qasm.loads(dec.get_QASM())
+    assert np.array_equal(x_back, np.concatenate([x, x])) and c_back.get_Gate_Num() == len(flat(d1)) and "Adaptive" not in c_back.get_Gate_Nums()
+    try:
+        import qiskit  # noqa: F401
+    except ImportError:
+        with pytest.raises(Exception, match="Qiskit is not installed"):
+            dec.get_Qiskit_Circuit()
     dec.set_Max_Iterations(17)
     assert dec.config["max_inner_iterations"] == 17
     dec.set_Verbose(0)
